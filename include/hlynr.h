@@ -1,0 +1,272 @@
+/*
+ * hlynr.h -- C ABI of the B200-native batched Hlynr Intercept simulator.
+ *
+ * This is the drop-in boundary for the reference's per-step hot path.  Nothing like it
+ * exists in the reference (it is pure Python); each entry point below names the reference
+ * interface it replaces.  All `file:line` citations are relative to the reference tree
+ * (RomanSlack/Hlynr_Intercept).
+ *
+ *   reference interface                                         replaced by
+ *   ---------------------------------------------------------  -------------------------
+ *   InterceptEnvironment.__init__   rl_system/environment.py:20  hlynr_create
+ *   InterceptEnvironment.reset      rl_system/environment.py:353 hlynr_reset / hlynr_reset_host
+ *   InterceptEnvironment.step       rl_system/environment.py:605 hlynr_step / hlynr_step_host
+ *   (SB3 DummyVecEnv.step_wait auto-reset, scripts/train_flat_ppo.py:371)   folded into hlynr_step
+ *   set_training_step_count / _update_radar_curriculum  environment.py:269-351  hlynr_set_curriculum
+ *   get_current_intercept_radius    environment.py:223          (host side, then hlynr_set_curriculum)
+ *   observation_generator.seed / np.random.seed  environment.py:357-359       hlynr_seed
+ *   env.interceptor_state / missile_state (get_attr, visualize.py:149-196)    hlynr_export_state
+ *   Monitor episode statistics (scripts/train_flat_ppo.py:292-303)            hlynr_get_stats
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - every function returns 0 on success, non-zero on failure; the message is available
+ *     (per thread) from hlynr_last_error().
+ *   - "dev" pointers are device pointers owned by the CALLER (e.g. torch tensors), valid on
+ *     the device the handle was created on.  "host" pointers are ordinary host memory.
+ *   - all device work is ordered on the `stream` argument (a cudaStream_t passed as void*;
+ *     NULL = the legacy default stream).  A handle is single-producer: one host thread at a
+ *     time.  Handles on different devices are independent.
+ *   - observation layout is the reference's 26-D vector (rl_system/core.py:700-721); the
+ *     17-D "radar" layout of the original project is obs[0:17].
+ */
+#ifndef HLYNR_H
+#define HLYNR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HLYNR_ABI_VERSION 1
+#define HLYNR_OBS_DIM 26
+#define HLYNR_ACT_DIM 6
+#define HLYNR_MAX_ONBOARD_DELAY 10 /* physics_randomizer.py:293 clamps the delay to [1,10] */
+#define HLYNR_MAX_GROUND_DELAY 31
+#define HLYNR_N_DR 13              /* physics_randomizer.py:166-214: 13 draws per episode */
+
+/* observation_mode, rl_system/environment.py:157-166 */
+enum { HLYNR_OBS_WORLD = 0, HLYNR_OBS_BODY = 1, HLYNR_OBS_LOS = 2 };
+/* precision of the build that a handle runs (north_star: fp32 build / fp64 build) */
+enum { HLYNR_FP32 = 32, HLYNR_FP64 = 64 };
+
+/*
+ * Resolved ("effective-key") configuration of one InterceptEnvironment.
+ * Produced on the host by hlynr_intercept_b200.config.resolve_config() with the reference's
+ * .get(key, default) semantics (rl_system/environment.py:24-186).  All reals are doubles --
+ * they are Python floats in the reference and are rounded to the compute type at the point of
+ * use exactly where NumPy-2 "weak scalar" promotion does it.
+ */
+typedef struct HlynrParams {
+    int32_t abi_version;  /* must be HLYNR_ABI_VERSION */
+    int32_t max_steps;    /* environment.py:26 */
+    double dt;            /* environment.py:25 */
+    double max_range;     /* environment.py:27 */
+    double max_velocity;  /* environment.py:28 */
+    double target[3];     /* environment.py:39 (float32-rounded) */
+
+    /* --- spawn, environment.py:375-467 --- */
+    int32_t m_spawn_spherical; /* missile_spawn.position_mode == 'spherical' */
+    int32_t i_vel_toward_missile; /* interceptor_spawn.velocity_mode == 'toward_missile' */
+    double m_pos_lo[3], m_pos_hi[3];
+    double m_speed_lo, m_speed_hi;    /* :413-415 (norms of the velocity box unless speed_min/max given) */
+    double m_radius_lo, m_radius_hi;  /* spherical mode :392-395 */
+    double m_az_lo, m_az_hi;          /* degrees */
+    double m_el_lo, m_el_hi;          /* degrees */
+    double i_pos_lo[3], i_pos_hi[3];
+    double i_vel_lo[3], i_vel_hi[3];
+    double i_speed_lo, i_speed_hi;    /* :449-450 */
+
+    /* --- wind, environment.py:71-73 --- */
+    double base_wind[3];  /* float32-rounded */
+    double wind_variability;
+
+    /* --- physics v2.0 switches, environment.py:52-106 --- */
+    int32_t isa_enabled;        /* atmospheric_model is not None */
+    int32_t mach_enabled;       /* mach_drag_model is not None */
+    int32_t enh_wind_enabled;   /* enhanced_wind_model is not None */
+    int32_t thrust_dyn_enabled; /* thrust_dynamics_enabled */
+    int32_t dr_enabled;         /* physics_randomizer is not None and .enabled */
+    int32_t validate_enabled;   /* physics_validation_enabled :106 */
+    int32_t evasion_enabled;    /* config['missile_evasion'] :1104 */
+    int32_t onboard_delay;      /* samples; 0 = no onboard delay buffer (core.py:292-293) */
+    double sub_mach, sup_mach, peak_mult, sup_mult; /* environment.py:65-68 */
+    double blh, turb_intensity, gust_scale;         /* environment.py:81-85 */
+    double thrust_tau;                              /* :94 */
+    double dr_variation[HLYNR_N_DR]; /* sigma of each draw, in physics_randomizer.py:166-214 order;
+                                        [1] is the temperature sigma in kelvin (0.05*20) */
+
+    /* --- onboard radar, environment.py:136-138,171-176; core.py:258-270 --- */
+    double radar_range;
+    double radar_quality;
+
+    /* --- ground radar + datalink, core.py:295-320 --- */
+    int32_t ground_enabled;
+    int32_t ground_delay; /* samples; 0 = no ground delay buffer */
+    double ground_pos[3]; /* float32-rounded */
+    double g_max_range, g_min_el, g_max_el; /* elevations in radians (np.radians of the YAML degrees) */
+    double g_sigma_r, g_sigma_v, g_base_quality;
+    double max_datalink_range, datalink_packet_loss;
+
+    /* --- modes --- */
+    int32_t obs_mode;        /* HLYNR_OBS_* */
+    int32_t precision_mode;  /* curriculum.precision_mode, environment.py:121 */
+    int32_t fuze_enabled;    /* proximity_fuze_enabled :128 */
+    int32_t reserved0;
+    double kill_radius;      /* proximity_kill_radius :129 */
+} HlynrParams;
+
+/*
+ * Host-pushed curriculum scalars (global to all envs): environment.py:223-234, 274-351.
+ * Recomputed on the host from training_step_count and pushed with hlynr_set_curriculum.
+ */
+typedef struct HlynrCurriculum {
+    double intercept_radius; /* get_current_intercept_radius() */
+    double beam_width_deg;   /* observation_generator.radar_beam_width */
+    double onboard_reliability;
+    double ground_reliability;
+} HlynrCurriculum;
+
+/*
+ * Optional per-env info, structure-of-arrays, device pointers (any may be NULL).
+ * Field meaning = the reference's info dict, environment.py:829-857.  Values are those of the
+ * tick just executed (i.e. of the terminal tick for envs that were auto-reset in this call).
+ */
+typedef struct HlynrInfoSoA {
+    float* distance;          /* [N] info['distance'] */
+    float* min_distance;      /* [N] info['min_distance'] */
+    float* fuel_remaining;    /* [N] info['fuel_remaining'] */
+    float* fuel_used;         /* [N] info['fuel_used'] */
+    int32_t* steps;           /* [N] info['steps'] */
+    uint8_t* flags;           /* [N] bit0 intercepted, bit1 missile_hit_target, bit2 clamped,
+                                 bit3 radar_detected (delayed onboard flag), bit4 ground detected,
+                                 bit5 crossed_threshold, bit6 proximity_fuze_triggered,
+                                 bit7 kalman initialised */
+    float* interceptor_pos;   /* [N,3] info['interceptor_pos'] */
+    float* missile_pos;       /* [N,3] info['missile_pos'] */
+    float* episode_return;    /* [N] Monitor 'r' of the episode that ended in this call (else running sum) */
+    int32_t* episode_length;  /* [N] Monitor 'l' */
+} HlynrInfoSoA;
+
+#define HLYNR_INFO_INTERCEPTED 0x01
+#define HLYNR_INFO_HIT_TARGET 0x02
+#define HLYNR_INFO_CLAMPED 0x04
+#define HLYNR_INFO_RADAR_DETECTED 0x08
+#define HLYNR_INFO_GROUND_DETECTED 0x10
+#define HLYNR_INFO_CROSSED 0x20
+#define HLYNR_INFO_FUZE 0x40
+#define HLYNR_INFO_KF_INIT 0x80
+
+/* Episode statistics accumulated on the device since the last reset of the block (per handle). */
+typedef struct HlynrStats {
+    double episodes;          /* finished episodes (terminated or truncated) */
+    double successes;         /* info['intercepted'] on the final tick */
+    double return_sum;
+    double length_sum;
+    double min_distance_sum;
+    double final_distance_sum;
+    double hit_target;        /* termination causes (first matching, in the reference's reward order) */
+    double interceptor_crash;
+    double fuel_out;
+    double missile_ground;    /* missile z<=0 away from the target */
+    double worsening;         /* smart early termination, environment.py:795-811 */
+    double timeouts;          /* truncated and not terminated */
+    double env_steps;         /* ticks simulated */
+    double onboard_locks;     /* ticks with the (delayed) onboard flag set */
+    double reserved[2];
+} HlynrStats;
+#define HLYNR_STATS_WORDS 16
+
+/*
+ * Full mutable state of one env, for oracle interchange.  Always double /
+ * int32 regardless of the precision of the handle.
+ */
+typedef struct HlynrEnvState {
+    double ipos[3], ivel[3], quat[4], fuel, fuel_used;
+    double mpos[3], mvel[3];
+    double wind[3], thrust[3];
+    double prev_d, last_d, min_d, episode_return;
+    double kf_x[6], kf_P[4]; /* P as (pp, pv, vp, vv) of the per-axis 2x2 block */
+    double T0, base_cd, peak;
+    int32_t steps, worsen_count, crossed, kf_init, onboard_delay, episode;
+} HlynrEnvState;
+
+typedef struct hlynr_sim hlynr_t;
+
+/* Error text of the last failing call on this thread. */
+const char* hlynr_last_error(void);
+int hlynr_abi_version(void);
+size_t hlynr_params_size(void);
+size_t hlynr_env_state_size(void);
+
+/* Replaces N x InterceptEnvironment(config) (environment.py:20).  `precision` is HLYNR_FP32 or
+ * HLYNR_FP64.  Envs get global ids [env_id_offset, env_id_offset + n_envs): trajectories depend
+ * only on (seed, global id), never on how envs are sharded over GPUs. */
+int hlynr_create(const HlynrParams* params, int64_t n_envs, int device, uint64_t seed,
+                 int64_t env_id_offset, int precision, hlynr_t** out);
+void hlynr_destroy(hlynr_t* sim);
+
+int hlynr_num_envs(const hlynr_t* sim, int64_t* out);
+int hlynr_set_curriculum(hlynr_t* sim, const HlynrCurriculum* cur);
+int hlynr_get_curriculum(const hlynr_t* sim, HlynrCurriculum* out);
+/* Re-keys the counter-based RNG (reference: reset(seed=...), environment.py:357-359). */
+int hlynr_seed(hlynr_t* sim, uint64_t seed);
+
+/* reset(): environment.py:353.  mask_dev: NULL = all envs, else uint8[N], non-zero = reset.
+ * obs_dev float[N,26] receives the initial observation of the envs that were reset (others
+ * untouched). */
+int hlynr_reset(hlynr_t* sim, const uint8_t* mask_dev, float* obs_dev, void* stream);
+
+/* step(): environment.py:605 + SB3 auto-reset.  One 10 ms tick of every env.
+ *   actions_dev      float[N,6] (caller clips to [-1,1] as SB3 does)
+ *   obs_dev          float[N,26]: observation after the tick; for envs that finished, the
+ *                    observation of the NEW episode (SB3 DummyVecEnv semantics)
+ *   reward_dev       float[N]
+ *   terminated_dev   uint8[N], truncated_dev uint8[N]   (done = terminated | truncated)
+ *   terminal_obs_dev float[N,26] or NULL: last observation of finished episodes
+ *                    (info['terminal_observation']); rows of unfinished envs are untouched
+ *   info             NULL or a struct of optional device arrays
+ *   auto_reset       non-zero: finished envs are reset inside the kernel */
+int hlynr_step(hlynr_t* sim, const float* actions_dev, float* obs_dev, float* reward_dev,
+               uint8_t* terminated_dev, uint8_t* truncated_dev, float* terminal_obs_dev,
+               const HlynrInfoSoA* info, int auto_reset, void* stream);
+
+/* k fused ticks in ONE launch with the state held in registers between ticks.
+ *   actions_dev  float[k,N,6] or NULL = in-kernel random actions U(-1,1)^6 from the Philox
+ *                stream (synthetic random-policy rollouts)
+ *   obs_dev      float[N,26]: observation after the last tick (or NULL)
+ *   reward_sum_dev float[N] or NULL: sum of the k rewards;  done_count_dev int32[N] or NULL */
+int hlynr_rollout(hlynr_t* sim, int k_steps, const float* actions_dev, float* obs_dev,
+                  float* reward_sum_dev, int32_t* done_count_dev, void* stream);
+
+/* Host-buffer variants (what a numpy VecEnv calls): copy in, run, copy out, synchronise.
+ * Pinned staging buffers are owned by the handle. */
+int hlynr_reset_host(hlynr_t* sim, const uint8_t* mask_host, float* obs_host);
+int hlynr_step_host(hlynr_t* sim, const float* actions_host, float* obs_host, float* reward_host,
+                    uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host,
+                    int auto_reset);
+/* Copies the info arrays of the last hlynr_step_host call to host (each pointer optional, host). */
+int hlynr_info_host(hlynr_t* sim, HlynrInfoSoA* host_arrays);
+
+/* Episode statistics block: device pointer (HLYNR_STATS_WORDS doubles, for an in-place NCCL
+ * all-reduce), host read-back, and zeroing. */
+int hlynr_stats_device_ptr(hlynr_t* sim, double** out_dev);
+int hlynr_get_stats(hlynr_t* sim, HlynrStats* host_out, int zero_after, void* stream);
+
+/* Oracle interchange: copy `count` envs starting at local index `first`. */
+int hlynr_export_state(hlynr_t* sim, int64_t first, int64_t count, HlynrEnvState* host_out);
+int hlynr_import_state(hlynr_t* sim, int64_t first, int64_t count, const HlynrEnvState* host_in);
+
+/* Test hook: raw Philox4x32-10 block and the derived draws for (env, episode, step, block). */
+int hlynr_debug_draws(hlynr_t* sim, int64_t env_global_id, uint32_t episode, uint32_t step,
+                      uint32_t block, uint32_t raw_out[4], float uniform_out[4], float normal_out[4]);
+
+/* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
+int hlynr_launch_count(const hlynr_t* sim, int64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HLYNR_H */

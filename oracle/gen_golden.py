@@ -1,0 +1,124 @@
+"""TEST INFRASTRUCTURE -- generates tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):   python -m oracle.gen_golden [case ...]
+
+Every fixture is one run of oracle.ref_harness.RefBatch (the imported reference environment with
+SB3-DummyVecEnv auto-reset and the site-keyed draws of include/hlynr_rng.h injected in place of its NumPy
+generators).  The reference publishes no golden vectors of its own, so these fixtures are what
+pins the oracle -- and through it the CUDA path -- to the reference.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+from hlynr_intercept_b200 import config
+from . import ref_harness as rh
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+# merged curriculum as scripts/train_hrl_pretrain.py:337-338 would pass it (values of rl_system/config.yaml:74-111)
+CONFIG_YAML_CURRICULUM = dict(
+    enabled=True, initial_radius=100.0, final_radius=5.0, curriculum_steps=2000000,
+    radar_curriculum=dict(enabled=True, initial_beam_width=120.0, final_beam_width=60.0,
+                          beam_width_transition_start=5000000, beam_width_transition_end=8000000,
+                          initial_detection_reliability=1.0, final_detection_reliability=0.8,
+                          reliability_transition_start=1000000, reliability_transition_end=2000000,
+                          initial_ground_reliability=1.0, final_ground_reliability=0.9,
+                          ground_reliability_transition_start=1000000, ground_reliability_transition_end=2000000))
+
+
+def case_config(base, extra=None):
+    cfg = config.baseline_config(base)
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+CASES = {
+    # name: (base cfg, extra env keys, n_envs, T, float64, policy, training_step_count)
+    "cfg1_f32_random_episode": ("cfg1", None, 1, 2000, False, "random", None),
+    "cfg1_f64_random_episode": ("cfg1", None, 1, 2000, True, "random", None),
+    "cfg2_f32_random": ("cfg2", None, 16, 128, False, "random", None),
+    "cfg2_f64_random": ("cfg2", None, 16, 128, True, "random", None),
+    "cfg3_f32_random": ("cfg3", None, 16, 128, False, "random", None),
+    "cfg3_f64_random": ("cfg3", None, 16, 128, True, "random", None),
+    "cfg3radar_f32_random": ("cfg3_radar", None, 16, 128, False, "random", None),
+    "cfg4_f32_random": ("cfg4", None, 16, 128, False, "random", None),
+    "cfg4_f64_random": ("cfg4", None, 16, 128, True, "random", None),
+    "cfg4_f32_pursuit_long": ("cfg4", None, 8, 1500, False, "pursuit", None),
+    "cfg4_f64_pursuit_long": ("cfg4", None, 4, 1500, True, "pursuit", None),
+    "cfg3_f32_random_long": ("cfg3", None, 6, 1800, False, "random", None),
+    "cfg2_f32_pursuit_long": ("cfg2", None, 6, 1500, False, "pursuit", None),
+    "cfg4_f32_curriculum": ("cfg4", dict(curriculum=CONFIG_YAML_CURRICULUM), 8, 128, False, "pursuit", 1500000),
+}
+
+
+def generate(name):
+    base, extra, n, T, f64, policy, tsc = CASES[name]
+    cfg = case_config(base, extra)
+    seed = 1234
+    ref = rh.RefBatch(cfg, n, seed=seed, float64=f64, training_step_count=tsc)
+    pol = rh.policy_random(7) if policy == "random" else rh.policy_pursuit()
+    obs0 = ref.reset()
+    obs = obs0
+    rec = dict(actions=[], obs=[], reward=[], terminated=[], truncated=[], terminal_obs=[], distance=[],
+               min_distance=[], fuel_remaining=[], fuel_used=[], steps=[], flags=[], interceptor_pos=[],
+               missile_pos=[], episode_return=[], episode_length=[])
+    stop_after_first_done = name.startswith("cfg1")
+    for t in range(T):
+        a = pol(t, obs)
+        obs, r, te, tr, tobs, info = ref.step(a)
+        rec["actions"].append(a)
+        rec["obs"].append(obs)
+        rec["reward"].append(r)
+        rec["terminated"].append(te)
+        rec["truncated"].append(tr)
+        rec["terminal_obs"].append(tobs)
+        for k in ("distance", "min_distance", "fuel_remaining", "fuel_used", "steps", "flags", "interceptor_pos",
+                  "missile_pos", "episode_return", "episode_length"):
+            rec[k].append(info[k])
+        if stop_after_first_done and (te | tr).any():
+            break
+    out = {k: np.stack(v) for k, v in rec.items()}
+    out["actions"] = out["actions"].astype(np.float32)
+    out["obs"] = out["obs"].astype(np.float32)
+    done = (out["terminated"] | out["truncated"]).astype(bool)
+    # terminal observations only where an episode ended (sparse)
+    idx = np.argwhere(done)
+    out["terminal_idx"] = idx.astype(np.int32)
+    out["terminal_obs"] = out["terminal_obs"][done].astype(np.float32)
+    for k in ("distance", "min_distance", "fuel_remaining", "fuel_used", "interceptor_pos", "missile_pos",
+              "episode_return"):
+        out[k] = out[k].astype(np.float64 if f64 else np.float32)
+    out["obs0"] = obs0
+    st = ref.export_state()
+    for k, v in st.items():
+        out["final_" + k] = v
+    meta = dict(name=name, base=base, env_cfg=cfg, n_envs=n, steps=int(out["obs"].shape[0]), float64=f64, policy=policy,
+                training_step_count=tsc, seed=seed, curriculum=ref.curriculum(), numpy=np.__version__,
+                generator="oracle/gen_golden.py", reference="RomanSlack/Hlynr_Intercept rl_system/environment.py")
+    out["meta"] = np.array(json.dumps(meta))
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    n_done = int(done.sum())
+    print(f"{name}: T={out['obs'].shape[0]} n={n} episodes_finished={n_done} "
+          f"intercepts={int(((out['flags'] & 1) > 0)[done].sum())} -> {os.path.getsize(path) / 1e3:.0f} kB")
+
+
+def load(name):
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    z = np.load(path, allow_pickle=False)
+    d = {k: z[k] for k in z.files}
+    d["meta"] = json.loads(str(d["meta"]))
+    return d
+
+
+if __name__ == "__main__":
+    if not rh.reference_available():
+        sys.exit("reference tree not found at " + rh.REFERENCE_ROOT)
+    names = sys.argv[1:] or list(CASES)
+    for nm in names:
+        generate(nm)

@@ -1,0 +1,102 @@
+"""Shared helpers for the parity tests."""
+import json
+import os
+
+import numpy as np
+
+from hlynr_intercept_b200 import config
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+
+STATE_FLOAT_FIELDS = ["ipos", "ivel", "quat", "mpos", "mvel", "wind", "thrust", "fuel", "fuel_used", "prev_d",
+                      "last_d", "min_d", "kf_x", "kf_P", "T0", "base_cd", "peak"]
+LOOSE_OBS = [9, 10, 11, 13, 16]
+STATE_INT_FIELDS = ["steps", "worsen_count", "crossed", "kf_init", "onboard_delay", "episode"]
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    d = {k: z[k] for k in z.files}
+    d["meta"] = json.loads(str(d["meta"]))
+    return d
+
+
+def golden_setup(g):
+    """(HlynrParams, Curriculum) of a golden case."""
+    meta = g["meta"]
+    P, cur = config.resolve_config(meta["env_cfg"], warn_dead=False)
+    if meta["training_step_count"] is not None:
+        cur.set_training_step_count(meta["training_step_count"])
+    got = cur.as_dict()
+    for k, v in meta["curriculum"].items():
+        assert abs(got[k] - v) < 1e-12, (k, got[k], v)
+    return P, cur
+
+
+def replay_against_golden(sim, g, rtol_state, obs_atol, reward_rtol, reward_atol, margin_fn=None, margin_tol=0.0,
+                          tti_atol=None):
+    """Replays the golden action sequence through `sim` (oracle or CUDA wrapper with the RefBatch call surface)
+    and compares every output.  Integer/boolean outputs must match exactly, except for envs whose decision
+    margin (as reported by margin_fn) dropped below margin_tol at some earlier tick: those are dropped from
+    the comparison from that tick on and counted.  Returns a dict of worst-case errors."""
+    T, n = g["obs"].shape[:2]
+    obs0 = sim.reset()
+    np.testing.assert_allclose(obs0, g["obs0"], rtol=0, atol=obs_atol)
+    alive = np.ones(n, bool)
+    worst = dict(obs=0.0, reward=0.0, dropped=0)
+    term_k = 0
+    tti_atol = obs_atol if tti_atol is None else tti_atol
+    for t in range(T):
+        obs, rew, te, tr, tobs, info = sim.step(g["actions"][t])
+        if margin_fn is not None:
+            m = margin_fn()
+            newly = alive & (m < margin_tol)
+            # a low-margin env is only dropped if it actually disagrees somewhere
+            bad = newly & ((te != g["terminated"][t]) | (tr != g["truncated"][t]) | (info["flags"] != g["flags"][t])
+                           | (np.abs(obs - g["obs"][t]).max(axis=1) > obs_atol))
+            alive &= ~bad
+            worst["dropped"] += int(bad.sum())
+        a = alive
+        assert (te[a] == g["terminated"][t][a]).all(), f"terminated mismatch at t={t}"
+        assert (tr[a] == g["truncated"][t][a]).all(), f"truncated mismatch at t={t}"
+        assert (info["flags"][a] == g["flags"][t][a]).all(), \
+            f"info flag mismatch at t={t}: {info['flags'][a]} vs {g['flags'][t][a]}"
+        assert (info["steps"][a] == g["steps"][t][a]).all(), f"steps mismatch at t={t}"
+        assert (info["episode_length"][a] == g["episode_length"][t][a]).all()
+        d = np.abs(obs[a] - g["obs"][t][a])
+        if d.size:
+            # ill-conditioned channels get their own tolerance: euler angles / off-axis cosine (functions of the
+            # quaternion, whose sin/cos ulps accumulate) and obs[13] = 1 - (range/closing)/100
+            dl = d[:, LOOSE_OBS].max()
+            d[:, LOOSE_OBS] = 0
+            assert d.max() <= obs_atol, f"obs mismatch at t={t}: {d.max()} at {np.unravel_index(d.argmax(), d.shape)}"
+            assert dl <= tti_atol, f"ill-conditioned obs channel mismatch at t={t}: {dl}"
+            worst["obs"] = max(worst["obs"], float(d.max()))
+        rg = g["reward"][t][a]
+        err = np.abs(rew[a] - rg)
+        assert (err <= reward_atol + reward_rtol * np.abs(rg)).all(), \
+            f"reward mismatch at t={t}: {rew[a]} vs {rg}"
+        if err.size:
+            worst["reward"] = max(worst["reward"], float((err / (np.abs(rg) + 1e-3)).max()))
+        for k in ("distance", "min_distance", "fuel_remaining", "fuel_used", "episode_return"):
+            np.testing.assert_allclose(info[k][a], g[k][t][a], rtol=max(rtol_state, reward_rtol), atol=reward_atol,
+                                       err_msg=f"info[{k}] at t={t}")
+        for k in ("interceptor_pos", "missile_pos"):
+            np.testing.assert_allclose(info[k][a], g[k][t][a], rtol=rtol_state, atol=rtol_state * 100,
+                                       err_msg=f"info[{k}] at t={t}")
+        done = (g["terminated"][t] | g["truncated"][t]).astype(bool)
+        for i in np.nonzero(done)[0]:
+            assert tuple(g["terminal_idx"][term_k]) == (t, i)
+            if alive[i]:
+                np.testing.assert_allclose(tobs[i], g["terminal_obs"][term_k], rtol=0, atol=max(obs_atol, tti_atol))
+            term_k += 1
+    st = sim.export_state()
+    for k in STATE_INT_FIELDS:
+        assert (st[k][alive] == g["final_" + k][alive]).all(), k
+    for k in STATE_FLOAT_FIELDS:
+        ref = g["final_" + k][alive]
+        scale = np.abs(ref).max() + 1e-6 if ref.size else 1.0
+        np.testing.assert_allclose(st[k][alive], ref, rtol=rtol_state, atol=rtol_state * scale,
+                                   err_msg=f"final state {k}")
+    return worst
