@@ -1,0 +1,79 @@
+"""Loader of the C-ABI CUDA library (ctypes).  There is NO CPU fallback: if the library is missing or does
+not load, importing the simulator fails loudly."""
+import ctypes as C
+import os
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libhlynr_b200.so")
+_LIB = None
+
+# every symbol include/hlynr.h declares
+EXPORTS = [
+    "hlynr_last_error", "hlynr_abi_version", "hlynr_params_size", "hlynr_env_state_size", "hlynr_create",
+    "hlynr_destroy", "hlynr_num_envs", "hlynr_set_curriculum", "hlynr_get_curriculum", "hlynr_seed", "hlynr_reset",
+    "hlynr_step", "hlynr_rollout", "hlynr_reset_host", "hlynr_step_host", "hlynr_pinned_buffers", "hlynr_info_host",
+    "hlynr_stats_device_ptr", "hlynr_stats_reduce", "hlynr_get_stats", "hlynr_export_state", "hlynr_import_state",
+    "hlynr_debug_draws", "hlynr_launch_count",
+]
+
+
+class HlynrError(RuntimeError):
+    pass
+
+
+def load(build_if_missing=True):
+    """Returns the ctypes handle of libhlynr_b200.so, building it in-tree with nvcc if it is stale/missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if build_if_missing:
+        from . import build as _build
+
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on this box: fall through to the prebuilt library, if any
+            if not os.path.exists(SO_PATH):
+                raise HlynrError(f"libhlynr_b200.so is missing and could not be built: {e}") from e
+    if not os.path.exists(SO_PATH):
+        raise HlynrError("libhlynr_b200.so is missing; run `python -m hlynr_intercept_b200.build`")
+    L = C.CDLL(SO_PATH)
+    vp, i64, u64, i32, u32 = C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_uint32
+    L.hlynr_last_error.restype = C.c_char_p
+    L.hlynr_params_size.restype = C.c_size_t
+    L.hlynr_env_state_size.restype = C.c_size_t
+    L.hlynr_create.argtypes = [C.POINTER(abi.HlynrParams), i64, i32, u64, i64, i32, C.POINTER(vp)]
+    L.hlynr_destroy.argtypes = [vp]
+    L.hlynr_destroy.restype = None
+    L.hlynr_num_envs.argtypes = [vp, C.POINTER(i64)]
+    L.hlynr_set_curriculum.argtypes = [vp, C.POINTER(abi.HlynrCurriculum)]
+    L.hlynr_get_curriculum.argtypes = [vp, C.POINTER(abi.HlynrCurriculum)]
+    L.hlynr_seed.argtypes = [vp, u64]
+    L.hlynr_reset.argtypes = [vp, vp, vp, vp]
+    L.hlynr_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(abi.HlynrInfoSoA), i32, vp]
+    L.hlynr_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.hlynr_reset_host.argtypes = [vp, vp, vp]
+    L.hlynr_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32]
+    L.hlynr_pinned_buffers.argtypes = [vp] + [C.POINTER(vp)] * 5
+    L.hlynr_info_host.argtypes = [vp, C.POINTER(abi.HlynrInfoSoA)]
+    L.hlynr_stats_device_ptr.argtypes = [vp, C.POINTER(vp)]
+    L.hlynr_stats_reduce.argtypes = [vp, vp]
+    L.hlynr_get_stats.argtypes = [vp, C.POINTER(abi.HlynrStats), i32, vp]
+    L.hlynr_export_state.argtypes = [vp, i64, i64, vp]
+    L.hlynr_import_state.argtypes = [vp, i64, i64, vp]
+    L.hlynr_debug_draws.argtypes = [vp, i64, u32, u32, u32, vp, vp, vp]
+    L.hlynr_launch_count.argtypes = [vp, C.POINTER(i64)]
+    if L.hlynr_abi_version() != abi.ABI_VERSION:
+        raise HlynrError("ABI version mismatch between libhlynr_b200.so and hlynr_intercept_b200.abi")
+    if L.hlynr_params_size() != C.sizeof(abi.HlynrParams):
+        raise HlynrError(f"HlynrParams layout mismatch: C {L.hlynr_params_size()} vs ctypes {C.sizeof(abi.HlynrParams)}")
+    if L.hlynr_env_state_size() != C.sizeof(abi.HlynrEnvState):
+        raise HlynrError("HlynrEnvState layout mismatch")
+    _LIB = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise HlynrError(load().hlynr_last_error().decode("utf-8", "replace"))

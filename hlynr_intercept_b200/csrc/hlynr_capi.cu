@@ -1,0 +1,578 @@
+// hlynr_capi.cu -- host side of the C ABI declared in include/hlynr.h.
+// Owns the SoA state planes, the ring planes and the statistics block of one GPU shard and launches the
+// kernels of hlynr_device.cuh.  No torch types: callers pass raw device/host pointers and a stream.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "hlynr_device.cuh"
+
+using namespace hlynr;
+
+static thread_local char g_err[512] = "";
+static int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+struct HostIO {  // pinned host + device staging for the *_host entry points
+    float *h_actions = nullptr, *h_obs = nullptr, *h_reward = nullptr, *h_tobs = nullptr;
+    uint8_t *h_term = nullptr, *h_trunc = nullptr, *h_mask = nullptr;
+    float *d_actions = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_tobs = nullptr;
+    uint8_t *d_term = nullptr, *d_trunc = nullptr, *d_mask = nullptr;
+    HlynrInfoSoA d_info;
+    bool ready = false;
+};
+
+struct hlynr_sim {
+    HlynrParams params;
+    HlynrCurriculum cur;
+    int64_t n = 0, n_pad = 0, env_offset = 0;
+    int device = 0, precision = HLYNR_FP32;
+    uint64_t seed = 0;
+    uint32_t tick = 0;
+    int64_t launches = 0;
+    void* state_mem = nullptr;
+    size_t state_bytes = 0;
+    StatePlanes<float> pf;
+    StatePlanes<double> pd;
+    double* stats = nullptr;        // [HLYNR_STAT_SLOTS + 1][HLYNR_STATS_WORDS]; last row = reduced block
+    HlynrEnvState* xchg = nullptr;  // device staging for export/import
+    int64_t xchg_cap = 0;
+    cudaStream_t own_stream = nullptr;
+    HostIO hio;
+};
+
+// ------------------------------------------------------------------------------------------------
+// parameter conversion
+// ------------------------------------------------------------------------------------------------
+static float round_down_f(double x) { float f = (float)x; if ((double)f > x) f = nextafterf(f, -INFINITY); return f; }
+static float round_up_f(double x) { float f = (float)x; if ((double)f < x) f = nextafterf(f, INFINITY); return f; }
+
+template <typename R> static KParams<R> make_kparams(const HlynrParams& p) {
+    KParams<R> k;
+    memset(&k, 0, sizeof(k));
+    k.dt = (R)p.dt; k.dt_d = p.dt; k.tau = (R)p.thrust_tau;
+    k.isa_expo = (R)(9.80665 / (287.05 * 0.0065));  // physics_models.py:99
+    k.gas_R = (R)287.05; k.gamma_R = (R)(1.4 * 287.05);
+    k.sub_mach = (R)p.sub_mach; k.sup_mach = (R)p.sup_mach; k.sup_minus_sub = (R)(p.sup_mach - p.sub_mach);
+    k.peak_minus1 = (R)(p.peak_mult - 1.0);
+    k.cd_base = (R)0.3; k.cd_sup = (R)(0.3 * p.sup_mult); k.sup_mult_d = p.sup_mult;
+    k.missile_ratio = (R)((0.3 * 1.5) / 0.3);       // environment.py:1090,1095
+    k.rho_weak = (R)1.225; k.cs_weak = (R)343.0; k.half_rho_weak = (R)(0.5 * 1.225); k.nhcr_weak = (R)(-0.5 * 0.3 * 1.225);
+    k.blh = (R)p.blh; k.pf_top = (R)pow(p.blh / 10.0, 0.143);
+    k.ti_low = (R)(p.turb_intensity * 2.0); k.ti_high = (R)(p.turb_intensity * 0.3); k.turb = (R)p.turb_intensity;
+    k.lp = (R)(1.0 - exp(-p.dt / 0.1));
+    k.gust_scale = (R)p.gust_scale; k.gust_scale_d = p.gust_scale; k.wind_var = (R)p.wind_variability;
+    k.kill_radius = (R)p.kill_radius; k.target_x = (R)p.target[0]; k.target_y = (R)p.target[1];
+    for (int i = 0; i < 3; ++i) {
+        k.base_wind[i] = (R)p.base_wind[i]; k.gpos[i] = (float)p.ground_pos[i]; k.target_d[i] = p.target[i];
+        k.m_pos_lo[i] = p.m_pos_lo[i]; k.m_pos_hi[i] = p.m_pos_hi[i]; k.i_pos_lo[i] = p.i_pos_lo[i]; k.i_pos_hi[i] = p.i_pos_hi[i];
+        k.i_vel_lo[i] = p.i_vel_lo[i]; k.i_vel_hi[i] = p.i_vel_hi[i];
+    }
+    k.radar_range = (float)p.radar_range; k.radar_quality = (float)p.radar_quality; k.radar_quality_d = p.radar_quality;
+    k.max_range_f = (float)p.max_range; k.max_velocity_f = (float)p.max_velocity;
+    k.g_max_range = (float)p.g_max_range; k.g_min_el_up = round_up_f(p.g_min_el); k.g_max_el_dn = round_down_f(p.g_max_el);
+    k.g_base_q = (float)p.g_base_quality; k.max_link = (float)p.max_datalink_range; k.pkt_loss = (float)p.datalink_packet_loss;
+    k.dtf = (float)p.dt;
+    const double q = 25.0;  // process_noise 5.0 squared (core.py:331-335)
+    k.q_pp = (float)(q * pow(p.dt, 4) / 4); k.q_pv = (float)(q * pow(p.dt, 3) / 2); k.q_vv = (float)(q * p.dt * p.dt);
+    k.sigma_r = (R)p.g_sigma_r; k.sigma_v = (R)p.g_sigma_v; k.max_range_w = (R)p.max_range; k.max_velocity_w = (R)p.max_velocity;
+    k.fus_035q = (float)(0.35 * p.radar_quality);
+    k.m_speed_lo = p.m_speed_lo; k.m_speed_hi = p.m_speed_hi; k.m_radius_lo = p.m_radius_lo; k.m_radius_hi = p.m_radius_hi;
+    k.m_az_lo = p.m_az_lo; k.m_az_hi = p.m_az_hi; k.m_el_lo = p.m_el_lo; k.m_el_hi = p.m_el_hi;
+    k.i_speed_lo = p.i_speed_lo; k.i_speed_hi = p.i_speed_hi;
+    for (int i = 0; i < HLYNR_N_DR; ++i) k.dr_var[i] = p.dr_variation[i];
+    k.peak_mult_d = p.peak_mult;
+    k.max_steps = p.max_steps; k.isa = p.isa_enabled; k.mach = p.mach_enabled; k.enh_wind = p.enh_wind_enabled;
+    k.thrust_dyn = p.thrust_dyn_enabled; k.dr = p.dr_enabled; k.validate = p.validate_enabled; k.evasion = p.evasion_enabled;
+    k.onboard_delay = p.onboard_delay; k.ground = p.ground_enabled; k.ground_delay = p.ground_enabled ? p.ground_delay : 0;
+    k.spherical = p.m_spawn_spherical; k.toward_missile = p.i_vel_toward_missile; k.obs_mode = p.obs_mode;
+    k.precision_mode = p.precision_mode; k.fuze = p.fuze_enabled;
+    k.onb_ring_len = p.onboard_delay > 0 ? (p.dr_enabled ? HLYNR_MAX_ONBOARD_DELAY + 1 : p.onboard_delay + 1) : 0;
+    k.gnd_ring_len = k.ground_delay > 0 ? k.ground_delay + 1 : 0;
+    return k;
+}
+template <typename R> static KCurriculum<R> make_kcur(const HlynrCurriculum& c) {
+    KCurriculum<R> k;
+    k.intercept_radius = (R)c.intercept_radius; k.intercept_radius_d = c.intercept_radius;
+    k.half_beam_dn = round_down_f((c.beam_width_deg / 2.0) * (M_PI / 180.0));  // np.radians(width / 2.0), core.py:548
+    k.onboard_rel = (float)c.onboard_reliability; k.ground_rel = (float)c.ground_reliability;
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small utility kernels
+// ------------------------------------------------------------------------------------------------
+template <typename R> __global__ void init_kernel(StatePlanes<R> s, int64_t n_pad, float peak, bool has_r6) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    Vec4<R> z{R(0), R(0), R(0), R(0)};
+    for (int k = 0; k < 6; ++k) s.r[k][i] = z;
+    s.r[6][i] = Vec4<R>{R(0), R(0), R(0), R(288.15)};  // SEA_LEVEL_TEMPERATURE, physics_models.py:22
+    s.f[0][i] = make_float4(1.f, 0.f, 0.f, 0.f);
+    s.f[1][i] = make_float4(0.f, 0.f, 0.f, 1000.f);
+    s.f[2][i] = make_float4(0.f, 0.f, 1000.f, 0.3f);
+    s.f[3][i] = make_float4(peak, 0.f, 0.f, 0.f);
+    s.i0[i] = make_int4(0, 0, 0, -1);  // episode -1: the first reset starts episode 0
+    (void)has_r6;
+}
+
+__global__ void stats_reduce_kernel(double* stats) {  // [SLOTS+1][WORDS]: last row = sum of the slots
+    int k = threadIdx.x;
+    if (k >= HLYNR_STATS_WORDS) return;
+    double s = 0.0;
+    for (int j = 0; j < HLYNR_STAT_SLOTS; ++j) s += stats[j * HLYNR_STATS_WORDS + k];
+    stats[HLYNR_STAT_SLOTS * HLYNR_STATS_WORDS + k] = s;
+}
+
+template <typename R> __global__ void export_kernel(KernelArgs<R> A, int64_t first, int64_t count, HlynrEnvState* out) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    Env<R> e;
+    // the optional planes are always allocated and initialised, so read them unconditionally here
+    KernelArgs<R> B = A;
+    B.P.thrust_dyn = 1; B.P.dr = 1;
+    load_env(B, first + j, e);
+    HlynrEnvState s;
+    memset(&s, 0, sizeof(s));
+    s.ipos[0] = e.ipx; s.ipos[1] = e.ipy; s.ipos[2] = e.ipz; s.ivel[0] = e.ivx; s.ivel[1] = e.ivy; s.ivel[2] = e.ivz;
+    s.quat[0] = e.qw; s.quat[1] = e.qx; s.quat[2] = e.qy; s.quat[3] = e.qz; s.fuel = e.fuel; s.fuel_used = e.fuel_used;
+    s.mpos[0] = e.mpx; s.mpos[1] = e.mpy; s.mpos[2] = e.mpz; s.mvel[0] = e.mvx; s.mvel[1] = e.mvy; s.mvel[2] = e.mvz;
+    s.wind[0] = e.wx; s.wind[1] = e.wy; s.wind[2] = e.wz; s.thrust[0] = e.thx; s.thrust[1] = e.thy; s.thrust[2] = e.thz;
+    s.prev_d = e.prev_d; s.last_d = e.last_d; s.min_d = e.min_d; s.episode_return = e.ep_ret;
+    s.kf_x[0] = e.kpx; s.kf_x[1] = e.kpy; s.kf_x[2] = e.kpz; s.kf_x[3] = e.kvx; s.kf_x[4] = e.kvy; s.kf_x[5] = e.kvz;
+    s.kf_P[0] = e.Ppp; s.kf_P[1] = e.Ppv; s.kf_P[2] = e.Pvp; s.kf_P[3] = e.Pvv;
+    s.T0 = e.T0; s.base_cd = e.base_cd; s.peak = e.peak;
+    s.steps = e.steps; s.worsen_count = e.worsen; s.crossed = (e.flags & FLAG_CROSSED) ? 1 : 0;
+    s.kf_init = (e.flags & FLAG_KF_INIT) ? 1 : 0; s.onboard_delay = A.P.onboard_delay > 0 ? (e.flags >> 8) : 0; s.episode = e.episode;
+    out[j] = s;
+}
+template <typename R> __global__ void import_kernel(KernelArgs<R> A, int64_t first, int64_t count, const HlynrEnvState* in) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const HlynrEnvState s = in[j];
+    Env<R> e;
+    e.ipx = (R)s.ipos[0]; e.ipy = (R)s.ipos[1]; e.ipz = (R)s.ipos[2]; e.ivx = (R)s.ivel[0]; e.ivy = (R)s.ivel[1]; e.ivz = (R)s.ivel[2];
+    e.qw = (float)s.quat[0]; e.qx = (float)s.quat[1]; e.qy = (float)s.quat[2]; e.qz = (float)s.quat[3];
+    e.fuel = (R)s.fuel; e.fuel_used = (R)s.fuel_used;
+    e.mpx = (R)s.mpos[0]; e.mpy = (R)s.mpos[1]; e.mpz = (R)s.mpos[2]; e.mvx = (R)s.mvel[0]; e.mvy = (R)s.mvel[1]; e.mvz = (R)s.mvel[2];
+    e.wx = (float)s.wind[0]; e.wy = (float)s.wind[1]; e.wz = (float)s.wind[2];
+    e.thx = (R)s.thrust[0]; e.thy = (R)s.thrust[1]; e.thz = (R)s.thrust[2];
+    e.prev_d = (R)s.prev_d; e.last_d = (R)s.last_d; e.min_d = (R)s.min_d; e.ep_ret = (R)s.episode_return;
+    e.kpx = (R)s.kf_x[0]; e.kpy = (R)s.kf_x[1]; e.kpz = (R)s.kf_x[2]; e.kvx = (R)s.kf_x[3]; e.kvy = (R)s.kf_x[4]; e.kvz = (R)s.kf_x[5];
+    e.Ppp = (float)s.kf_P[0]; e.Ppv = (float)s.kf_P[1]; e.Pvp = (float)s.kf_P[2]; e.Pvv = (float)s.kf_P[3];
+    e.T0 = (R)s.T0; e.base_cd = (float)s.base_cd; e.peak = (float)s.peak;
+    e.steps = s.steps; e.worsen = s.worsen_count;
+    e.flags = (s.crossed ? FLAG_CROSSED : 0) | (s.kf_init ? FLAG_KF_INIT : 0) | (s.onboard_delay << 8);
+    e.episode = s.episode;
+    KernelArgs<R> B = A;
+    B.P.thrust_dyn = 1; B.P.dr = 1;
+    store_env(B, first + j, e);
+}
+
+__global__ void debug_draw_kernel(uint32_t seed_lo, uint32_t seed_hi, int64_t env, uint32_t episode, uint32_t step,
+                                  uint32_t blk, uint32_t* raw, float* uni, float* nrm) {
+    RngKey k = make_key(seed_lo, seed_hi, env);
+    uint4 r = draw_raw(k, episode, step, blk);
+    raw[0] = r.x; raw[1] = r.y; raw[2] = r.z; raw[3] = r.w;
+    uni[0] = u01(r.x); uni[1] = u01(r.y); uni[2] = u01(r.z); uni[3] = u01(r.w);
+    box_muller(r.x, r.y, &nrm[0], &nrm[1]);
+    box_muller(r.z, r.w, &nrm[2], &nrm[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// allocation
+// ------------------------------------------------------------------------------------------------
+template <typename R> static size_t carve(StatePlanes<R>& s, char* base, int64_t n_pad, int gl, int ol) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += (bytes + 255) & ~size_t(255); return p; };
+    for (int k = 0; k < 7; ++k) s.r[k] = (Vec4<R>*)take(sizeof(Vec4<R>) * n_pad);
+    for (int k = 0; k < 4; ++k) s.f[k] = (float4*)take(sizeof(float4) * n_pad);
+    s.i0 = (int4*)take(sizeof(int4) * n_pad);
+    s.gring = (Vec4<R>*)take(sizeof(Vec4<R>) * n_pad * 2 * (gl > 0 ? gl : 1));
+    s.oring = (float4*)take(sizeof(float4) * n_pad * (ol > 0 ? ol : 1));
+    return off;
+}
+
+template <typename R> static KernelArgs<R> base_args(hlynr_sim* s, const StatePlanes<R>& planes) {
+    KernelArgs<R> A;
+    memset(&A, 0, sizeof(A));
+    A.P = make_kparams<R>(s->params);
+    A.C = make_kcur<R>(s->cur);
+    A.st = planes;
+    A.n = s->n;
+    A.ring_stride = s->n_pad;
+    A.env_offset = s->env_offset;
+    A.seed_lo = (uint32_t)s->seed; A.seed_hi = (uint32_t)(s->seed >> 32);
+    A.tick = s->tick;
+    A.io.stats = s->stats;
+    A.k_steps = 1;
+    return A;
+}
+static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* hlynr_last_error(void) { return g_err; }
+int hlynr_abi_version(void) { return HLYNR_ABI_VERSION; }
+size_t hlynr_params_size(void) { return sizeof(HlynrParams); }
+size_t hlynr_env_state_size(void) { return sizeof(HlynrEnvState); }
+
+void hlynr_destroy(hlynr_t* s) {
+    if (!s) return;
+    DeviceGuard g(s->device);
+    cudaFree(s->state_mem); cudaFree(s->stats); cudaFree(s->xchg);
+    HostIO& h = s->hio;
+    cudaFreeHost(h.h_actions); cudaFreeHost(h.h_obs); cudaFreeHost(h.h_reward); cudaFreeHost(h.h_tobs);
+    cudaFreeHost(h.h_term); cudaFreeHost(h.h_trunc); cudaFreeHost(h.h_mask);
+    cudaFree(h.d_actions); cudaFree(h.d_obs); cudaFree(h.d_reward); cudaFree(h.d_tobs); cudaFree(h.d_term); cudaFree(h.d_trunc); cudaFree(h.d_mask);
+    cudaFree(h.d_info.distance); cudaFree(h.d_info.min_distance); cudaFree(h.d_info.fuel_remaining); cudaFree(h.d_info.fuel_used);
+    cudaFree(h.d_info.steps); cudaFree(h.d_info.flags); cudaFree(h.d_info.interceptor_pos); cudaFree(h.d_info.missile_pos);
+    cudaFree(h.d_info.episode_return); cudaFree(h.d_info.episode_length);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+}
+
+int hlynr_create(const HlynrParams* p, int64_t n_envs, int device, uint64_t seed, int64_t env_id_offset, int precision,
+                 hlynr_t** out) {
+    if (!p || !out) return fail("hlynr_create: null argument");
+    if (p->abi_version != HLYNR_ABI_VERSION) return fail("hlynr_create: params.abi_version %d != %d", p->abi_version, HLYNR_ABI_VERSION);
+    if (n_envs <= 0) return fail("hlynr_create: n_envs must be positive");
+    if (precision != HLYNR_FP32 && precision != HLYNR_FP64) return fail("hlynr_create: precision must be 32 or 64");
+    if (p->obs_mode != HLYNR_OBS_WORLD) return fail("hlynr_create: observation_mode other than world_frame is not implemented yet");
+    if (p->onboard_delay < 0 || p->onboard_delay > HLYNR_MAX_ONBOARD_DELAY) return fail("hlynr_create: onboard_delay out of range");
+    if (p->ground_delay < 0 || p->ground_delay > HLYNR_MAX_GROUND_DELAY) return fail("hlynr_create: ground_delay out of range");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail("hlynr_create: device %d not available (%d devices)", device, ndev);
+    DeviceGuard g(device);
+    if (!g.ok) return fail("hlynr_create: cannot select device %d", device);
+    hlynr_sim* s = new (std::nothrow) hlynr_sim();
+    if (!s) return fail("hlynr_create: out of host memory");
+    s->params = *p;
+    s->cur = HlynrCurriculum{200.0, 60.0, 1.0, 1.0};
+    s->n = n_envs; s->n_pad = (n_envs + 31) & ~int64_t(31);
+    s->device = device; s->precision = precision; s->seed = seed; s->env_offset = env_id_offset;
+    KParams<float> kp = make_kparams<float>(*p);
+    const int gl = kp.gnd_ring_len, ol = kp.onb_ring_len;
+    cudaError_t e;
+    if (precision == HLYNR_FP32) s->state_bytes = carve<float>(s->pf, nullptr, s->n_pad, gl, ol);
+    else s->state_bytes = carve<double>(s->pd, nullptr, s->n_pad, gl, ol);
+    e = cudaMalloc(&s->state_mem, s->state_bytes);
+    if (e != cudaSuccess) { int r = fail("hlynr_create: cudaMalloc(%zu bytes) failed: %s", s->state_bytes, cudaGetErrorString(e)); delete s; return r; }
+    e = cudaMalloc(&s->stats, sizeof(double) * (HLYNR_STAT_SLOTS + 1) * HLYNR_STATS_WORDS);
+    if (e != cudaSuccess) { int r = fail("hlynr_create: cudaMalloc(stats) failed: %s", cudaGetErrorString(e)); cudaFree(s->state_mem); delete s; return r; }
+    cudaMemset(s->state_mem, 0, s->state_bytes);
+    cudaMemset(s->stats, 0, sizeof(double) * (HLYNR_STAT_SLOTS + 1) * HLYNR_STATS_WORDS);
+    cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+    const int blk = 256;
+    if (precision == HLYNR_FP32) {
+        carve<float>(s->pf, (char*)s->state_mem, s->n_pad, gl, ol);
+        init_kernel<float><<<grid_for(s->n_pad, blk), blk>>>(s->pf, s->n_pad, (float)p->peak_mult, true);
+    } else {
+        carve<double>(s->pd, (char*)s->state_mem, s->n_pad, gl, ol);
+        init_kernel<double><<<grid_for(s->n_pad, blk), blk>>>(s->pd, s->n_pad, (float)p->peak_mult, true);
+    }
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { int r = fail("hlynr_create: init kernel failed: %s", cudaGetErrorString(e)); hlynr_destroy(s); return r; }
+    s->launches += 1;
+    *out = s;
+    return 0;
+}
+
+int hlynr_num_envs(const hlynr_t* s, int64_t* out) { if (!s || !out) return fail("null argument"); *out = s->n; return 0; }
+int hlynr_set_curriculum(hlynr_t* s, const HlynrCurriculum* c) { if (!s || !c) return fail("null argument"); s->cur = *c; return 0; }
+int hlynr_get_curriculum(const hlynr_t* s, HlynrCurriculum* c) { if (!s || !c) return fail("null argument"); *c = s->cur; return 0; }
+int hlynr_seed(hlynr_t* s, uint64_t seed) { if (!s) return fail("null handle"); s->seed = seed; return 0; }
+int hlynr_launch_count(const hlynr_t* s, int64_t* out) { if (!s || !out) return fail("null argument"); *out = s->launches; return 0; }
+
+int hlynr_reset(hlynr_t* s, const uint8_t* mask_dev, float* obs_dev, void* stream) {
+    if (!s) return fail("hlynr_reset: null handle");
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->precision == HLYNR_FP32) {
+        KernelArgs<float> A = base_args<float>(s, s->pf);
+        A.io.reset_mask = mask_dev; A.io.obs = obs_dev;
+        reset_kernel<float><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+    } else {
+        KernelArgs<double> A = base_args<double>(s, s->pd);
+        A.io.reset_mask = mask_dev; A.io.obs = obs_dev;
+        reset_kernel<double><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+    }
+    CK(cudaGetLastError());
+    s->launches += 1;
+    return 0;
+}
+
+int hlynr_step(hlynr_t* s, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* terminated_dev,
+               uint8_t* truncated_dev, float* terminal_obs_dev, const HlynrInfoSoA* info, int auto_reset, void* stream) {
+    if (!s) return fail("hlynr_step: null handle");
+    if (!actions_dev || !obs_dev || !reward_dev || !terminated_dev || !truncated_dev) return fail("hlynr_step: null output/input pointer");
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    s->tick += 1;
+    if (s->precision == HLYNR_FP32) {
+        KernelArgs<float> A = base_args<float>(s, s->pf);
+        A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward = reward_dev; A.io.terminated = terminated_dev;
+        A.io.truncated = truncated_dev; A.io.terminal_obs = terminal_obs_dev; A.auto_reset = auto_reset;
+        if (info) A.io.info = *info;
+        step_kernel<float, false><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+    } else {
+        KernelArgs<double> A = base_args<double>(s, s->pd);
+        A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward = reward_dev; A.io.terminated = terminated_dev;
+        A.io.truncated = truncated_dev; A.io.terminal_obs = terminal_obs_dev; A.auto_reset = auto_reset;
+        if (info) A.io.info = *info;
+        step_kernel<double, false><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+    }
+    CK(cudaGetLastError());
+    s->launches += 1;
+    return 0;
+}
+
+int hlynr_rollout(hlynr_t* s, int k_steps, const float* actions_dev, float* obs_dev, float* reward_sum_dev,
+                  int32_t* done_count_dev, void* stream) {
+    if (!s) return fail("hlynr_rollout: null handle");
+    if (k_steps <= 0) return fail("hlynr_rollout: k_steps must be positive");
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->precision == HLYNR_FP32) {
+        KernelArgs<float> A = base_args<float>(s, s->pf);
+        A.tick = s->tick + 1; A.k_steps = k_steps; A.auto_reset = 1;
+        A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward_sum = reward_sum_dev; A.io.done_count = done_count_dev;
+        step_kernel<float, true><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+    } else {
+        KernelArgs<double> A = base_args<double>(s, s->pd);
+        A.tick = s->tick + 1; A.k_steps = k_steps; A.auto_reset = 1;
+        A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward_sum = reward_sum_dev; A.io.done_count = done_count_dev;
+        step_kernel<double, true><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+    }
+    CK(cudaGetLastError());
+    s->tick += (uint32_t)k_steps;
+    s->launches += 1;
+    return 0;
+}
+
+int hlynr_stats_device_ptr(hlynr_t* s, double** out) {
+    if (!s || !out) return fail("null argument");
+    *out = s->stats + HLYNR_STAT_SLOTS * HLYNR_STATS_WORDS;
+    return 0;
+}
+
+// Folds the per-block slots into the reduced row (device side; call before an NCCL all-reduce on it).
+int hlynr_stats_reduce(hlynr_t* s, void* stream) {
+    if (!s) return fail("null handle");
+    DeviceGuard g(s->device);
+    stats_reduce_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(s->stats);
+    CK(cudaGetLastError());
+    s->launches += 1;
+    return 0;
+}
+
+int hlynr_get_stats(hlynr_t* s, HlynrStats* host_out, int zero_after, void* stream) {
+    if (!s || !host_out) return fail("null argument");
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (hlynr_stats_reduce(s, stream)) return 1;
+    CK(cudaMemcpyAsync(host_out, s->stats + HLYNR_STAT_SLOTS * HLYNR_STATS_WORDS, sizeof(double) * HLYNR_STATS_WORDS,
+                       cudaMemcpyDeviceToHost, st));
+    if (zero_after) CK(cudaMemsetAsync(s->stats, 0, sizeof(double) * (HLYNR_STAT_SLOTS + 1) * HLYNR_STATS_WORDS, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int ensure_xchg(hlynr_sim* s, int64_t count) {
+    if (s->xchg_cap >= count) return 0;
+    cudaFree(s->xchg);
+    s->xchg = nullptr; s->xchg_cap = 0;
+    CK(cudaMalloc(&s->xchg, sizeof(HlynrEnvState) * count));
+    s->xchg_cap = count;
+    return 0;
+}
+
+int hlynr_export_state(hlynr_t* s, int64_t first, int64_t count, HlynrEnvState* host_out) {
+    if (!s || !host_out) return fail("null argument");
+    if (first < 0 || count < 0 || first + count > s->n) return fail("hlynr_export_state: range out of bounds");
+    if (count == 0) return 0;
+    DeviceGuard g(s->device);
+    CK(cudaDeviceSynchronize());
+    if (ensure_xchg(s, count)) return 1;
+    if (s->precision == HLYNR_FP32) export_kernel<float><<<grid_for(count, 128), 128>>>(base_args<float>(s, s->pf), first, count, s->xchg);
+    else export_kernel<double><<<grid_for(count, 128), 128>>>(base_args<double>(s, s->pd), first, count, s->xchg);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(host_out, s->xchg, sizeof(HlynrEnvState) * count, cudaMemcpyDeviceToHost));
+    s->launches += 1;
+    return 0;
+}
+
+int hlynr_import_state(hlynr_t* s, int64_t first, int64_t count, const HlynrEnvState* host_in) {
+    if (!s || !host_in) return fail("null argument");
+    if (first < 0 || count < 0 || first + count > s->n) return fail("hlynr_import_state: range out of bounds");
+    if (count == 0) return 0;
+    DeviceGuard g(s->device);
+    CK(cudaDeviceSynchronize());
+    if (ensure_xchg(s, count)) return 1;
+    CK(cudaMemcpy(s->xchg, host_in, sizeof(HlynrEnvState) * count, cudaMemcpyHostToDevice));
+    if (s->precision == HLYNR_FP32) import_kernel<float><<<grid_for(count, 128), 128>>>(base_args<float>(s, s->pf), first, count, s->xchg);
+    else import_kernel<double><<<grid_for(count, 128), 128>>>(base_args<double>(s, s->pd), first, count, s->xchg);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    s->launches += 1;
+    return 0;
+}
+
+int hlynr_debug_draws(hlynr_t* s, int64_t env_global_id, uint32_t episode, uint32_t step, uint32_t block, uint32_t raw_out[4],
+                      float uniform_out[4], float normal_out[4]) {
+    if (!s) return fail("null handle");
+    DeviceGuard g(s->device);
+    void* buf = nullptr;
+    CK(cudaMalloc(&buf, 48));
+    debug_draw_kernel<<<1, 1>>>((uint32_t)s->seed, (uint32_t)(s->seed >> 32), env_global_id, episode, step, block,
+                                (uint32_t*)buf, (float*)((char*)buf + 16), (float*)((char*)buf + 32));
+    char host[48];
+    cudaError_t e = cudaMemcpy(host, buf, 48, cudaMemcpyDeviceToHost);
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail("hlynr_debug_draws: %s", cudaGetErrorString(e));
+    memcpy(raw_out, host, 16); memcpy(uniform_out, host + 16, 16); memcpy(normal_out, host + 32, 16);
+    s->launches += 1;
+    return 0;
+}
+
+// ---- host-buffer entry points ----------------------------------------------------------------
+static int ensure_hostio(hlynr_sim* s) {
+    HostIO& h = s->hio;
+    if (h.ready) return 0;
+    const size_t n = (size_t)s->n;
+    CK(cudaMallocHost(&h.h_actions, n * 6 * sizeof(float)));
+    CK(cudaMallocHost(&h.h_obs, n * 26 * sizeof(float)));
+    CK(cudaMallocHost(&h.h_tobs, n * 26 * sizeof(float)));
+    CK(cudaMallocHost(&h.h_reward, n * sizeof(float)));
+    CK(cudaMallocHost(&h.h_term, n)); CK(cudaMallocHost(&h.h_trunc, n)); CK(cudaMallocHost(&h.h_mask, n));
+    CK(cudaMalloc(&h.d_actions, n * 6 * sizeof(float)));
+    CK(cudaMalloc(&h.d_obs, n * 26 * sizeof(float)));
+    CK(cudaMalloc(&h.d_tobs, n * 26 * sizeof(float)));
+    CK(cudaMalloc(&h.d_reward, n * sizeof(float)));
+    CK(cudaMalloc(&h.d_term, n)); CK(cudaMalloc(&h.d_trunc, n)); CK(cudaMalloc(&h.d_mask, n));
+    memset(&h.d_info, 0, sizeof(h.d_info));
+    CK(cudaMalloc(&h.d_info.distance, n * 4)); CK(cudaMalloc(&h.d_info.min_distance, n * 4));
+    CK(cudaMalloc(&h.d_info.fuel_remaining, n * 4)); CK(cudaMalloc(&h.d_info.fuel_used, n * 4));
+    CK(cudaMalloc(&h.d_info.steps, n * 4)); CK(cudaMalloc(&h.d_info.flags, n));
+    CK(cudaMalloc(&h.d_info.interceptor_pos, n * 12)); CK(cudaMalloc(&h.d_info.missile_pos, n * 12));
+    CK(cudaMalloc(&h.d_info.episode_return, n * 4)); CK(cudaMalloc(&h.d_info.episode_length, n * 4));
+    h.ready = true;
+    return 0;
+}
+
+int hlynr_reset_host(hlynr_t* s, const uint8_t* mask_host, float* obs_host) {
+    if (!s || !obs_host) return fail("hlynr_reset_host: null argument");
+    DeviceGuard g(s->device);
+    if (ensure_hostio(s)) return 1;
+    HostIO& h = s->hio;
+    cudaStream_t st = s->own_stream;
+    const size_t n = (size_t)s->n;
+    if (mask_host) {
+        memcpy(h.h_mask, mask_host, n);
+        CK(cudaMemcpyAsync(h.d_mask, h.h_mask, n, cudaMemcpyHostToDevice, st));
+        // rows of envs that are not reset keep the caller's content
+        if (obs_host != h.h_obs) memcpy(h.h_obs, obs_host, n * 26 * 4);
+        CK(cudaMemcpyAsync(h.d_obs, h.h_obs, n * 26 * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (hlynr_reset(s, mask_host ? h.d_mask : nullptr, h.d_obs, st)) return 1;
+    CK(cudaMemcpyAsync(h.h_obs, h.d_obs, n * 26 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (obs_host != h.h_obs) memcpy(obs_host, h.h_obs, n * 26 * 4);
+    return 0;
+}
+
+int hlynr_step_host(hlynr_t* s, const float* actions_host, float* obs_host, float* reward_host, uint8_t* terminated_host,
+                    uint8_t* truncated_host, float* terminal_obs_host, int auto_reset) {
+    if (!s || !actions_host || !obs_host || !reward_host || !terminated_host || !truncated_host) return fail("hlynr_step_host: null argument");
+    DeviceGuard g(s->device);
+    if (ensure_hostio(s)) return 1;
+    HostIO& h = s->hio;
+    cudaStream_t st = s->own_stream;
+    const size_t n = (size_t)s->n;
+    if (actions_host != h.h_actions) memcpy(h.h_actions, actions_host, n * 6 * 4);
+    CK(cudaMemcpyAsync(h.d_actions, h.h_actions, n * 6 * 4, cudaMemcpyHostToDevice, st));
+    if (hlynr_step(s, h.d_actions, h.d_obs, h.d_reward, h.d_term, h.d_trunc, terminal_obs_host ? h.d_tobs : nullptr, &h.d_info,
+                   auto_reset, st)) return 1;
+    CK(cudaMemcpyAsync(h.h_obs, h.d_obs, n * 26 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h.h_reward, h.d_reward, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h.h_term, h.d_term, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h.h_trunc, h.d_trunc, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (obs_host != h.h_obs) memcpy(obs_host, h.h_obs, n * 26 * 4);
+    if (reward_host != h.h_reward) memcpy(reward_host, h.h_reward, n * 4);
+    if (terminated_host != h.h_term) memcpy(terminated_host, h.h_term, n);
+    if (truncated_host != h.h_trunc) memcpy(truncated_host, h.h_trunc, n);
+    if (terminal_obs_host) {  // only rows of finished envs are meaningful; copy only if something finished
+        bool any = false;
+        for (size_t i = 0; i < n && !any; ++i) any = (h.h_term[i] | h.h_trunc[i]) != 0;
+        if (any) {
+            CK(cudaMemcpyAsync(h.h_tobs, h.d_tobs, n * 26 * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (size_t i = 0; i < n; ++i)
+                if (h.h_term[i] | h.h_trunc[i]) memcpy(terminal_obs_host + i * 26, h.h_tobs + i * 26, 26 * 4);
+        }
+    }
+    return 0;
+}
+
+int hlynr_info_host(hlynr_t* s, HlynrInfoSoA* o) {
+    if (!s || !o) return fail("hlynr_info_host: null argument");
+    if (!s->hio.ready) return fail("hlynr_info_host: no hlynr_step_host call yet");
+    DeviceGuard g(s->device);
+    const HlynrInfoSoA& d = s->hio.d_info;
+    const size_t n = (size_t)s->n;
+    cudaStream_t st = s->own_stream;
+    if (o->distance) CK(cudaMemcpyAsync(o->distance, d.distance, n * 4, cudaMemcpyDeviceToHost, st));
+    if (o->min_distance) CK(cudaMemcpyAsync(o->min_distance, d.min_distance, n * 4, cudaMemcpyDeviceToHost, st));
+    if (o->fuel_remaining) CK(cudaMemcpyAsync(o->fuel_remaining, d.fuel_remaining, n * 4, cudaMemcpyDeviceToHost, st));
+    if (o->fuel_used) CK(cudaMemcpyAsync(o->fuel_used, d.fuel_used, n * 4, cudaMemcpyDeviceToHost, st));
+    if (o->steps) CK(cudaMemcpyAsync(o->steps, d.steps, n * 4, cudaMemcpyDeviceToHost, st));
+    if (o->flags) CK(cudaMemcpyAsync(o->flags, d.flags, n, cudaMemcpyDeviceToHost, st));
+    if (o->interceptor_pos) CK(cudaMemcpyAsync(o->interceptor_pos, d.interceptor_pos, n * 12, cudaMemcpyDeviceToHost, st));
+    if (o->missile_pos) CK(cudaMemcpyAsync(o->missile_pos, d.missile_pos, n * 12, cudaMemcpyDeviceToHost, st));
+    if (o->episode_return) CK(cudaMemcpyAsync(o->episode_return, d.episode_return, n * 4, cudaMemcpyDeviceToHost, st));
+    if (o->episode_length) CK(cudaMemcpyAsync(o->episode_length, d.episode_length, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// Pinned host buffers owned by the handle (numpy callers wrap them to avoid the staging memcpy).
+int hlynr_pinned_buffers(hlynr_t* s, float** actions, float** obs, float** reward, uint8_t** terminated, uint8_t** truncated) {
+    if (!s) return fail("null handle");
+    DeviceGuard g(s->device);
+    if (ensure_hostio(s)) return 1;
+    if (actions) *actions = s->hio.h_actions;
+    if (obs) *obs = s->hio.h_obs;
+    if (reward) *reward = s->hio.h_reward;
+    if (terminated) *terminated = s->hio.h_term;
+    if (truncated) *truncated = s->hio.h_trunc;
+    return 0;
+}
+
+}  // extern "C"

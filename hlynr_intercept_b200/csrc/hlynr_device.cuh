@@ -1,0 +1,1042 @@
+// hlynr_device.cuh -- device code of the batched Hlynr Intercept simulator (sm_100a).
+//
+// One environment per thread.  State lives in HBM as planes of 16-byte (fp32 build) or 32-byte
+// (fp64 build) vectors, one plane per group of four words, so every load/store of a warp is one fully
+// coalesced 512-byte (or 1 KiB) transaction.  The sensor-delay FIFOs of the reference
+// (rl_system/core.py:147 SensorDelayBuffer) are ring planes indexed by the GLOBAL tick, so all envs
+// read and write the same ring row in a step: one slot read + one slot write per env, coalesced.
+//
+// The arithmetic restates the reference step (rl_system/environment.py:605-859 and callees) with the
+// same rounding points as NumPy-2 produces (SURVEY 8a precision map).  mul/add/sub/dvd below are the
+// never-contracted IEEE operations; plain operators are used where contraction is harmless.
+//   R = float : "fp32 build" (matches the native reference; float64 islands of the reference are
+//               evaluated in float unless noted)
+//   R = double: "fp64 build" (matches the up-cast float64 reference: integrator, ISA, drag, distance,
+//               reward in double; observation geometry in float as the reference forces it)
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/hlynr.h"
+#include "../../include/hlynr_rng.h"
+
+namespace hlynr {
+
+#define HD __device__ __forceinline__
+
+// ------------------------------------------------------------------------------------------------
+// never-contracted arithmetic
+// ------------------------------------------------------------------------------------------------
+HD float mul(float a, float b) { return __fmul_rn(a, b); }
+HD float add(float a, float b) { return __fadd_rn(a, b); }
+HD float sub(float a, float b) { return __fsub_rn(a, b); }
+HD float dvd(float a, float b) { return __fdiv_rn(a, b); }
+HD float sqr(float a) { return __fsqrt_rn(a); }
+HD double mul(double a, double b) { return __dmul_rn(a, b); }
+HD double add(double a, double b) { return __dadd_rn(a, b); }
+HD double sub(double a, double b) { return __dsub_rn(a, b); }
+HD double dvd(double a, double b) { return __ddiv_rn(a, b); }
+HD double sqr(double a) { return __dsqrt_rn(a); }
+
+// np.dot / np.linalg.norm on float32 vectors: float products, double accumulator, one final rounding
+// (OpenBLAS sdot as used by the reference's NumPy; see oracle/hlynr_oracle.c dotn).
+HD float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+    double s = (double)__fmul_rn(ax, bx) + (double)__fmul_rn(ay, by);
+    s += (double)__fmul_rn(az, bz);
+    return (float)s;
+}
+HD double dot3(double ax, double ay, double az, double bx, double by, double bz) {
+    return add(add(mul(ax, bx), mul(ay, by)), mul(az, bz));
+}
+template <typename T> HD T norm3(T x, T y, T z) { return sqr(dot3(x, y, z, x, y, z)); }
+HD float dot2(float ax, float ay, float bx, float by) { return (float)((double)__fmul_rn(ax, bx) + (double)__fmul_rn(ay, by)); }
+HD double dot2(double ax, double ay, double bx, double by) { return add(mul(ax, bx), mul(ay, by)); }
+
+template <typename T> HD T clip(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+HD void sincos_r(float x, float* s, float* c) { sincosf(x, s, c); }
+HD void sincos_r(double x, double* s, double* c) { sincos(x, s, c); }
+HD float pow_r(float x, float y) { return powf(x, y); }
+HD double pow_r(double x, double y) { return pow(x, y); }
+HD float exp_r(float x) { return expf(x); }
+HD double exp_r(double x) { return exp(x); }
+
+template <typename T> struct alignas(sizeof(T) * 4) Vec4 { T x, y, z, w; };
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 + the draw contract of include/hlynr_rng.h
+// ------------------------------------------------------------------------------------------------
+struct RngKey { uint32_t k0, k1, c0, c3hi; };  // key = seed halves; c0 = env id low, c3hi = (env id >> 32) << 16
+
+HD uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(HLYNR_PHILOX_M0, c0), lo0 = HLYNR_PHILOX_M0 * c0;
+        uint32_t hi1 = __umulhi(HLYNR_PHILOX_M1, c2), lo1 = HLYNR_PHILOX_M1 * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += HLYNR_PHILOX_W0; k1 += HLYNR_PHILOX_W1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+HD uint4 draw_raw(const RngKey& k, uint32_t episode, uint32_t step, uint32_t blk) {
+    return philox4x32_10(k.c0, episode, step, blk | k.c3hi, k.k0, k.k1);
+}
+HD float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
+HD float u01_open(uint32_t x) { return (float)((x >> 8) + 1u) * 5.9604644775390625e-8f; }
+HD void box_muller(uint32_t xa, uint32_t xb, float* z0, float* z1) {
+    float r = sqrtf(-2.0f * logf(u01_open(xa)));
+    float s, c;
+    sincospif(2.0f * u01(xb), &s, &c);
+    *z0 = r * c; *z1 = r * s;
+}
+HD void draw_normal3(const RngKey& k, uint32_t episode, uint32_t step, uint32_t blk, float* z0, float* z1, float* z2) {
+    uint4 r = draw_raw(k, episode, step, blk);
+    float z3;
+    box_muller(r.x, r.y, z0, z1);
+    box_muller(r.z, r.w, z2, &z3);
+}
+
+// ------------------------------------------------------------------------------------------------
+// resolved parameters, pre-rounded on the host to the dtype they meet in the reference
+// ------------------------------------------------------------------------------------------------
+template <typename R> struct KParams {
+    // ---- S context (integrator dtype) ----
+    R dt, tau, isa_expo, gas_R, gamma_R, sub_mach, sup_mach, sup_minus_sub, peak_minus1, cd_sup, cd_base;
+    R missile_ratio, rho_weak, cs_weak, half_rho_weak, nhcr_weak;  // weak python-float constants (ISA off)
+    R blh, pf_top, ti_low, ti_high, turb, lp, gust_scale, wind_var;
+    R kill_radius, target_x, target_y;
+    R base_wind[3];
+    double sup_mult_d;  // DR: base_cd * sup_mult in float64
+    double dt_d;        // dt as the Python float it is in the reference
+    double radar_quality_d;
+    // ---- float context (observation geometry) ----
+    float radar_range, radar_quality, max_range_f, max_velocity_f;
+    float gpos[3], g_max_range, g_min_el_up, g_max_el_dn, g_base_q, max_link, pkt_loss;
+    float dtf, q_pp, q_pv, q_vv;  // Kalman F/Q entries (float32 matrices, core.py:33-56)
+    // ---- island context (W = R) ----
+    R sigma_r, sigma_v, max_range_w, max_velocity_w;
+    float fus_035q;
+    // ---- spawn / DR (double, reset path only) ----
+    double m_pos_lo[3], m_pos_hi[3], m_speed_lo, m_speed_hi, m_radius_lo, m_radius_hi, m_az_lo, m_az_hi, m_el_lo, m_el_hi;
+    double i_pos_lo[3], i_pos_hi[3], i_vel_lo[3], i_vel_hi[3], i_speed_lo, i_speed_hi, target_d[3];
+    double dr_var[HLYNR_N_DR];
+    double peak_mult_d, gust_scale_d;
+    // ---- switches ----
+    int32_t max_steps, isa, mach, enh_wind, thrust_dyn, dr, validate, evasion, onboard_delay, ground, ground_delay;
+    int32_t spherical, toward_missile, obs_mode, precision_mode, fuze, onb_ring_len, gnd_ring_len;
+};
+
+template <typename R> struct KCurriculum {
+    R intercept_radius;        // S context
+    float half_beam_dn;        // float threshold equivalent to the float64 comparison beam > radians(width/2)
+    float onboard_rel, ground_rel;
+    double intercept_radius_d;
+};
+
+template <typename R> struct StatePlanes {
+    Vec4<R>* r[7];   // r0 ipos+fuel, r1 ivel+fuel_used, r2 mpos+prev_d, r3 mvel+last_d, r4 kf_xp+min_d,
+                     // r5 kf_xv+ep_return, r6 thrust+T0
+    float4* f[4];    // f0 quat, f1 wind+Ppp, f2 Ppv,Pvp,Pvv,base_cd, f3 peak (DR only)
+    int4* i0;        // steps, worsen, flags (bit0 crossed, bit1 kf_init, bits 8.. onboard delay), episode
+    Vec4<R>* gring;  // [gnd_ring_len][2][N]: {rel.xyz, quality}, {vel.xyz, -}
+    float4* oring;   // [onb_ring_len][N]: {rel.xyz, detected}
+};
+
+struct StepIO {
+    const float* actions;   // [N,6] (or [k,N,6] for the fused rollout; NULL = in-kernel random policy)
+    float* obs;             // [N,26]
+    float* reward;          // [N]
+    uint8_t* terminated;    // [N]
+    uint8_t* truncated;     // [N]
+    float* terminal_obs;    // [N,26] or NULL
+    HlynrInfoSoA info;      // optional arrays
+    const uint8_t* reset_mask;  // reset kernel only
+    float* reward_sum;      // rollout
+    int32_t* done_count;    // rollout
+    double* stats;          // [STAT_SLOTS][HLYNR_STATS_WORDS]
+};
+#define HLYNR_STAT_SLOTS 64
+
+template <typename R> struct KernelArgs {
+    KParams<R> P;
+    KCurriculum<R> C;
+    StatePlanes<R> st;
+    StepIO io;
+    int64_t n;
+    int64_t ring_stride;  // row pitch of the ring planes (n rounded up to 32 envs)
+    int64_t env_offset;
+    uint32_t seed_lo, seed_hi;
+    uint32_t tick;       // global tick of this launch (rollout: tick of the first fused step)
+    int32_t auto_reset;
+    int32_t k_steps;
+};
+
+// ------------------------------------------------------------------------------------------------
+// per-env register state
+// ------------------------------------------------------------------------------------------------
+template <typename R> struct Env {
+    R ipx, ipy, ipz, fuel;
+    R ivx, ivy, ivz, fuel_used;
+    R mpx, mpy, mpz, prev_d;
+    R mvx, mvy, mvz, last_d;
+    R kpx, kpy, kpz, min_d;
+    R kvx, kvy, kvz, ep_ret;
+    R thx, thy, thz, T0;
+    float qw, qx, qy, qz;
+    float wx, wy, wz, Ppp;
+    float Ppv, Pvp, Pvv, base_cd;
+    float peak;
+    int steps, worsen, flags, episode;
+};
+#define FLAG_CROSSED 1
+#define FLAG_KF_INIT 2
+
+template <typename R> HD void load_env(const KernelArgs<R>& A, int64_t i, Env<R>& e) {
+    const StatePlanes<R>& s = A.st;
+    Vec4<R> v;
+    v = s.r[0][i]; e.ipx = v.x; e.ipy = v.y; e.ipz = v.z; e.fuel = v.w;
+    v = s.r[1][i]; e.ivx = v.x; e.ivy = v.y; e.ivz = v.z; e.fuel_used = v.w;
+    v = s.r[2][i]; e.mpx = v.x; e.mpy = v.y; e.mpz = v.z; e.prev_d = v.w;
+    v = s.r[3][i]; e.mvx = v.x; e.mvy = v.y; e.mvz = v.z; e.last_d = v.w;
+    v = s.r[4][i]; e.kpx = v.x; e.kpy = v.y; e.kpz = v.z; e.min_d = v.w;
+    v = s.r[5][i]; e.kvx = v.x; e.kvy = v.y; e.kvz = v.z; e.ep_ret = v.w;
+    if (A.P.thrust_dyn | A.P.dr) { v = s.r[6][i]; e.thx = v.x; e.thy = v.y; e.thz = v.z; e.T0 = v.w; }
+    else { e.thx = e.thy = e.thz = R(0); e.T0 = R(288.15); }
+    float4 f;
+    f = s.f[0][i]; e.qw = f.x; e.qx = f.y; e.qy = f.z; e.qz = f.w;
+    f = s.f[1][i]; e.wx = f.x; e.wy = f.y; e.wz = f.z; e.Ppp = f.w;
+    f = s.f[2][i]; e.Ppv = f.x; e.Pvp = f.y; e.Pvv = f.z; e.base_cd = f.w;
+    if (A.P.dr) { f = s.f[3][i]; e.peak = f.x; } else e.peak = 0.f;
+    int4 q = s.i0[i]; e.steps = q.x; e.worsen = q.y; e.flags = q.z; e.episode = q.w;
+}
+template <typename R> HD void store_env(const KernelArgs<R>& A, int64_t i, const Env<R>& e) {
+    const StatePlanes<R>& s = A.st;
+    s.r[0][i] = Vec4<R>{e.ipx, e.ipy, e.ipz, e.fuel};
+    s.r[1][i] = Vec4<R>{e.ivx, e.ivy, e.ivz, e.fuel_used};
+    s.r[2][i] = Vec4<R>{e.mpx, e.mpy, e.mpz, e.prev_d};
+    s.r[3][i] = Vec4<R>{e.mvx, e.mvy, e.mvz, e.last_d};
+    s.r[4][i] = Vec4<R>{e.kpx, e.kpy, e.kpz, e.min_d};
+    s.r[5][i] = Vec4<R>{e.kvx, e.kvy, e.kvz, e.ep_ret};
+    if (A.P.thrust_dyn | A.P.dr) s.r[6][i] = Vec4<R>{e.thx, e.thy, e.thz, e.T0};
+    s.f[0][i] = make_float4(e.qw, e.qx, e.qy, e.qz);
+    s.f[1][i] = make_float4(e.wx, e.wy, e.wz, e.Ppp);
+    s.f[2][i] = make_float4(e.Ppv, e.Pvp, e.Pvv, e.base_cd);
+    if (A.P.dr) s.f[3][i] = make_float4(e.peak, 0.f, 0.f, 0.f);
+    s.i0[i] = make_int4(e.steps, e.worsen, e.flags, e.episode);
+}
+
+// ------------------------------------------------------------------------------------------------
+// physics_models.py
+// ------------------------------------------------------------------------------------------------
+// AtmosphericModel.get_atmospheric_properties (physics_models.py:154-177)
+template <typename R> HD void isa_props(const KParams<R>& P, R T0, R alt, R* rho, R* cs) {
+    R T, Pr;
+    if (alt <= R(11000.0)) {
+        T = sub(T0, mul(R(0.0065), alt));
+        R ratio = dvd(T, T0);
+        Pr = mul(R(101325.0), pow_r(ratio, P.isa_expo));
+    } else if (alt <= R(20000.0)) {
+        T = R(216.65);
+        R ex = sub(alt, R(11000.0));
+        R arg = dvd(mul(R(-9.80665), ex), R(287.05 * 216.65));
+        Pr = mul(R(22632.0), exp_r(arg));
+    } else {
+        R ex = sub(alt, R(20000.0));
+        T = mul(R(216.65), exp_r(dvd(-ex, R(10000.0))));
+        Pr = mul(R(5474.889421808574), exp_r(dvd(-ex, R(6000.0))));  // get_pressure(20000.0) in python floats
+    }
+    *rho = dvd(Pr, mul(P.gas_R, T));
+    *cs = sqr(mul(P.gamma_R, T));
+}
+
+// MachDragModel.get_drag_force (physics_models.py:236-264) divided by mass -> acceleration.
+// With domain randomization base_cd/peak are np.float64 scalars and the whole product is float64
+// (physics_randomizer.py:273,278); the fp32 build evaluates that island in float.
+template <typename R>
+HD void mach_drag_accel(const KParams<R>& P, const Env<R>& e, R vx, R vy, R vz, R vmag, R rho, R cs, bool weak_atm,
+                        R area, R post_scale, R mass, R* ax, R* ay, R* az) {
+    R mach = dvd(vmag, weak_atm ? P.cs_weak : cs);
+    R cd;
+    if (P.dr) {
+        double bc = (double)e.base_cd, pk = (double)e.peak;
+        double m = (double)mach;
+        double c;
+        if (mach < P.sub_mach) c = bc;
+        else if (mach < P.sup_mach) {
+            R frac = dvd(sub(mach, P.sub_mach), P.sup_minus_sub);
+            c = bc * (1.0 + (pk - 1.0) * (double)frac);
+        } else c = bc * P.sup_mult_d;
+        (void)m;
+        cd = (R)c;
+    } else {
+        if (mach < P.sub_mach) cd = P.cd_base;
+        else if (mach < P.sup_mach) {
+            R frac = dvd(sub(mach, P.sub_mach), P.sup_minus_sub);
+            cd = mul(P.cd_base, add(R(1.0), mul(P.peak_minus1, frac)));
+        } else cd = P.cd_sup;
+    }
+    R t = weak_atm ? P.half_rho_weak : mul(R(0.5), rho);
+    t = mul(t, mul(vmag, vmag));
+    t = mul(t, cd);
+    t = mul(t, area);
+    R fx = mul(dvd(-vx, vmag), t), fy = mul(dvd(-vy, vmag), t), fz = mul(dvd(-vz, vmag), t);
+    if (post_scale != R(1.0)) { fx = mul(fx, post_scale); fy = mul(fy, post_scale); fz = mul(fz, post_scale); }
+    *ax = dvd(fx, mass); *ay = dvd(fy, mass); *az = dvd(fz, mass);
+}
+
+template <typename R>
+HD void drag_accel(const KParams<R>& P, const Env<R>& e, R vx, R vy, R vz, R alt, R area, R post_scale, R mass, R* ax,
+                   R* ay, R* az) {
+    R rho = P.rho_weak, cs = P.cs_weak;
+    bool weak = true;
+    if (P.isa) { isa_props(P, e.T0, alt, &rho, &cs); weak = false; }
+    R vmag = norm3(vx, vy, vz);
+    if (P.mach && vmag > R(1e-6)) {
+        mach_drag_accel(P, e, vx, vy, vz, vmag, rho, cs, weak, area, post_scale, mass, ax, ay, az);
+    } else {  // environment.py:920-921 / :1099-1100
+        R c = weak ? P.nhcr_weak : mul(R(-0.5 * 0.3), rho);
+        c = mul(c, vmag);
+        *ax = dvd(mul(c, vx), mass); *ay = dvd(mul(c, vy), mass); *az = dvd(mul(c, vz), mass);
+    }
+}
+
+template <typename R> HD R nan_guard(R a, R lim) {  // np.nan_to_num(nan=0, posinf=lim, neginf=-lim)
+    if (a != a) return R(0);
+    if (isinf(a)) return a > R(0) ? lim : -lim;
+    return a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// core.py helpers (float32 always)
+// ------------------------------------------------------------------------------------------------
+HD void forward_vector(float w, float x, float y, float z, float* fx, float* fy, float* fz) {  // core.py:1143-1152
+    float a = mul(2.f, add(mul(x, z), mul(w, y)));
+    float b = mul(2.f, sub(mul(y, z), mul(w, x)));
+    float c = sub(1.f, mul(2.f, add(mul(x, x), mul(y, y))));
+    float n = add(norm3(a, b, c), 1e-6f);
+    *fx = dvd(a, n); *fy = dvd(b, n); *fz = dvd(c, n);
+}
+
+struct ObsOut {
+    float o[HLYNR_OBS_DIM];
+    bool onboard_det, ground_det;
+};
+
+// Radar26DObservation.compute_radar_detection + compute (core.py:511-1032), world_frame.
+// `tick` indexes the ring planes; `e.steps` is the call index since reset (0 = the reset call).
+template <typename R>
+HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i, uint32_t tick, ObsOut& out) {
+    typedef R W;  // dtype of the reference's float64 islands in this build
+    const KParams<R>& P = A.P;
+    const KCurriculum<R>& C = A.C;
+    const int64_t n = A.ring_stride;
+    float ipx = (float)e.ipx, ipy = (float)e.ipy, ipz = (float)e.ipz;
+    float ivx = (float)e.ivx, ivy = (float)e.ivy, ivz = (float)e.ivz;
+    float mpx = (float)e.mpx, mpy = (float)e.mpy, mpz = (float)e.mpz;
+    float mvx = (float)e.mvx, mvy = (float)e.mvy, mvz = (float)e.mvz;
+    uint4 ur = draw_raw(key, (uint32_t)e.episode, (uint32_t)e.steps, HLYNR_BLK_UNI);
+
+    // === onboard radar, core.py:531-593 ===
+    float rx = sub(mpx, ipx), ry = sub(mpy, ipy), rz = sub(mpz, ipz);
+    float range = norm3(rx, ry, rz);
+    bool onb = !(range > P.radar_range);
+    float fx, fy, fz;
+    forward_vector(e.qw, e.qx, e.qy, e.qz, &fx, &fy, &fz);
+    if (onb) {
+        float rd = add(range, 1e-6f);
+        float cb = clip(dot3(fx, fy, fz, dvd(rx, rd), dvd(ry, rd), dvd(rz, rd)), -1.f, 1.f);
+        if (acosf(cb) > C.half_beam_dn) onb = false;
+    }
+    if (onb) {
+        float rf = sub(1.f, mul(dvd(range, P.radar_range), 0.5f));
+        float q = mul(mul(P.radar_quality, rf), C.onboard_rel);
+        if (u01(ur.y) > q) onb = false;
+    }
+    float orx, ory, orz;
+    bool o_det;
+    int odelay = P.dr ? (e.flags >> 8) : P.onboard_delay;
+    if (P.onboard_delay > 0) {
+        const int L = P.onb_ring_len;
+        A.st.oring[(int64_t)(tick % (uint32_t)L) * n + i] = make_float4(rx, ry, rz, onb ? 1.f : 0.f);
+        if (e.steps >= odelay) {
+            float4 s = A.st.oring[(int64_t)((tick + (uint32_t)(L - odelay)) % (uint32_t)L) * n + i];
+            orx = s.x; ory = s.y; orz = s.z; o_det = s.w != 0.f;
+        } else { orx = ory = orz = 0.f; o_det = false; }
+    } else { orx = rx; ory = ry; orz = rz; o_det = onb; }
+
+    // === ground radar, core.py:368-438 ===
+    bool gdet = false;
+    W grx = W(0), gry = W(0), grz = W(0), gvx = W(0), gvy = W(0), gvz = W(0);
+    float gq = 0.f;
+    if (P.ground) {
+        float gx = sub(mpx, P.gpos[0]), gy = sub(mpy, P.gpos[1]), gz = sub(mpz, P.gpos[2]);
+        float gr = norm3(gx, gy, gz);
+        bool ok = !(gr > P.g_max_range);
+        if (ok && gr > 1e-6f) {
+            float el = asinf(clip(dvd(gz, gr), -1.f, 1.f));
+            if (el < P.g_min_el_up || el > P.g_max_el_dn) ok = false;
+        }
+        if (ok && mpz < 50.f) ok = false;
+        if (ok) {
+            float prob = mul(P.g_base_q, sub(1.f, mul(dvd(gr, P.g_max_range), 0.4f)));
+            prob = mul(prob, C.ground_rel);
+            if (u01(ur.z) > prob) ok = false;
+            else {
+                float z0, z1, z2, y0, y1, y2;
+                draw_normal3(key, (uint32_t)e.episode, (uint32_t)e.steps, HLYNR_BLK_GPOS, &z0, &z1, &z2);
+                draw_normal3(key, (uint32_t)e.episode, (uint32_t)e.steps, HLYNR_BLK_GVEL, &y0, &y1, &y2);
+                grx = (W)rx + P.sigma_r * (W)z0; gry = (W)ry + P.sigma_r * (W)z1; grz = (W)rz + P.sigma_r * (W)z2;
+                gvx = (W)sub(mvx, ivx) + P.sigma_v * (W)y0;
+                gvy = (W)sub(mvy, ivy) + P.sigma_v * (W)y1;
+                gvz = (W)sub(mvz, ivz) + P.sigma_v * (W)y2;
+                gq = prob; gdet = true;
+            }
+        }
+    }
+    W dgx, dgy, dgz, dvx, dvy, dvz;
+    float dgq;
+    bool dg_det;
+    if (P.ground && P.ground_delay > 0) {  // delayed values, CURRENT flag (core.py:626, quirk Q3)
+        const int L = P.gnd_ring_len;
+        Vec4<W>* wr = A.st.gring + (int64_t)(tick % (uint32_t)L) * 2 * n;
+        wr[i] = Vec4<W>{grx, gry, grz, (W)gq};
+        wr[n + i] = Vec4<W>{gvx, gvy, gvz, W(0)};
+        if (e.steps >= P.ground_delay) {
+            const Vec4<W>* rr = A.st.gring + (int64_t)((tick + 1u) % (uint32_t)L) * 2 * n;
+            Vec4<W> a = rr[i], b = rr[n + i];
+            dgx = a.x; dgy = a.y; dgz = a.z; dgq = (float)a.w; dvx = b.x; dvy = b.y; dvz = b.z;
+            dg_det = gdet;
+        } else { dgx = dgy = dgz = dvx = dvy = dvz = W(0); dgq = 0.f; dg_det = false; }
+    } else { dgx = grx; dgy = gry; dgz = grz; dvx = gvx; dvy = gvy; dvz = gvz; dgq = gq; dg_det = gdet; }
+
+    // === datalink, core.py:440-474 ===
+    float link = 0.f;
+    if (P.ground) {
+        float lr = norm3(sub(ipx, P.gpos[0]), sub(ipy, P.gpos[1]), sub(ipz, P.gpos[2]));
+        if (!(lr > P.max_link)) {
+            float r1 = dvd(lr, P.max_link);
+            float rf = sub(1.f, mul(r1, r1));
+            float dv = dvd(norm3(ivx, ivy, ivz), 1000.f);
+            float dop = sub(1.f, dv < 0.3f ? dv : 0.3f);
+            if (u01(ur.w) < P.pkt_loss) link = 0.f;
+            else link = clip(mul(mul(rf, dop), 0.95f), 0.f, 1.f);
+        }
+    }
+
+    // === fusion confidence, core.py:476-509 ===
+    float fus;
+    if (!o_det && !dg_det) fus = 0.f;
+    else if (o_det && !dg_det) fus = (float)(P.radar_quality_d * 0.5);
+    else if (!o_det) fus = mul(dgq, 0.6f);
+    else {
+        W perr = norm3((W)orx - dgx, (W)ory - dgy, (W)orz - dgz);
+        W r = dvd(perr, W(200.0));
+        W agr = sub(W(1.0), r < W(1.0) ? r : W(1.0));
+        float t = add(P.fus_035q, mul(0.5f, dgq));
+        fus = (float)clip(add((W)t, mul(W(0.15), agr)), W(0.0), W(1.0));
+    }
+    out.onboard_det = o_det;
+    out.ground_det = dg_det;
+
+    // === Kalman filter (core.py:12-133) reduced to x[6] + one shared 2x2 covariance block ===
+    bool kf_init = (e.flags & FLAG_KF_INIT) != 0;
+    if (o_det || dg_det) {
+        W zx, zy, zz;
+        if (o_det && dg_det) {  // quality-weighted fusion, core.py:734-739
+            float ow = P.radar_quality;
+            float tw = add(ow, dgq);
+            zx = add((W)ipx, dvd(add((W)mul(orx, ow), mul(dgx, (W)dgq)), (W)tw));
+            zy = add((W)ipy, dvd(add((W)mul(ory, ow), mul(dgy, (W)dgq)), (W)tw));
+            zz = add((W)ipz, dvd(add((W)mul(orz, ow), mul(dgz, (W)dgq)), (W)tw));
+        } else if (o_det) {
+            zx = (W)add(ipx, orx); zy = (W)add(ipy, ory); zz = (W)add(ipz, orz);
+        } else {
+            zx = add((W)ipx, dgx); zy = add((W)ipy, dgy); zz = add((W)ipz, dgz);
+        }
+        if (!kf_init) {  // first measurement only initialises (core.py:93-96), state array is float32
+            e.kpx = (W)(float)zx; e.kpy = (W)(float)zy; e.kpz = (W)(float)zz;
+            e.kvx = e.kvy = e.kvz = W(0);
+            kf_init = true;
+        } else {
+            float Si = __fdiv_rn(1.f, add(e.Ppp, 400.f));
+            float Kp = mul(e.Ppp, Si), Kv = mul(e.Pvp, Si);
+            W yx = sub(zx, e.kpx), yy = sub(zy, e.kpy), yz = sub(zz, e.kpz);
+            e.kpx = add(e.kpx, mul((W)Kp, yx)); e.kpy = add(e.kpy, mul((W)Kp, yy)); e.kpz = add(e.kpz, mul((W)Kp, yz));
+            e.kvx = add(e.kvx, mul((W)Kv, yx)); e.kvy = add(e.kvy, mul((W)Kv, yy)); e.kvz = add(e.kvz, mul((W)Kv, yz));
+            float a = sub(1.f, Kp);
+            float npp = mul(a, e.Ppp), npv = mul(a, e.Ppv);
+            float nvp = add(e.Pvp, mul(-Kv, e.Ppp)), nvv = add(e.Pvv, mul(-Kv, e.Ppv));
+            e.Ppp = npp; e.Ppv = npv; e.Pvp = nvp; e.Pvv = nvv;
+        }
+    } else if (kf_init) {  // predict only when no measurement (quirk Q4)
+        W d = (W)P.dtf;
+        e.kpx = add(e.kpx, mul(d, e.kvx)); e.kpy = add(e.kpy, mul(d, e.kvy)); e.kpz = add(e.kpz, mul(d, e.kvz));
+        float fpp = __fmaf_rn(P.dtf, e.Pvp, e.Ppp), fpv = __fmaf_rn(P.dtf, e.Pvv, e.Ppv);  // F @ P (sgemm uses FMA)
+        float cpp = __fmaf_rn(fpv, P.dtf, fpp), cvp = __fmaf_rn(e.Pvv, P.dtf, e.Pvp);      // (F P) @ F^T
+        e.Ppp = add(cpp, P.q_pp); e.Ppv = add(fpv, P.q_pv); e.Pvp = add(cvp, P.q_pv); e.Pvv = add(e.Pvv, P.q_vv);
+    }
+    e.flags = (e.flags & ~FLAG_KF_INIT) | (kf_init ? FLAG_KF_INIT : 0);
+
+    float* o = out.o;
+    if (kf_init) {
+        W px = sub(e.kpx, (W)ipx), py = sub(e.kpy, (W)ipy), pz = sub(e.kpz, (W)ipz);
+        W vx = sub(e.kvx, (W)ivx), vy = sub(e.kvy, (W)ivy), vz = sub(e.kvz, (W)ivz);
+        W rr = norm3(px, py, pz);
+        W cl = dvd(-dot3(px, py, pz, vx, vy, vz), add(rr, W(1e-6)));
+        o[0] = (float)clip(dvd(px, P.max_range_w), W(-1), W(1));
+        o[1] = (float)clip(dvd(py, P.max_range_w), W(-1), W(1));
+        o[2] = (float)clip(dvd(pz, P.max_range_w), W(-1), W(1));
+        o[3] = (float)clip(dvd(vx, P.max_velocity_w), W(-1), W(1));
+        o[4] = (float)clip(dvd(vy, P.max_velocity_w), W(-1), W(1));
+        o[5] = (float)clip(dvd(vz, P.max_velocity_w), W(-1), W(1));
+        if (cl > W(0)) o[13] = (float)clip(sub(W(1), dvd(dvd(rr, cl), W(100))), W(-1), W(1));
+        else o[13] = -1.f;
+        float tr = add(add(e.Ppp, e.Ppp), e.Ppp);
+        double tq = clip(1.0 - (double)tr / 10000.0, 0.0, 1.0);
+        if (o_det) tq *= P.radar_quality_d;
+        o[14] = (float)tq;
+        o[15] = (float)clip(dvd(cl, P.max_velocity_w), W(-1), W(1));
+        if (rr > W(1e-6)) o[16] = (float)dot3((W)fx, (W)fy, (W)fz, dvd(px, rr), dvd(py, rr), dvd(pz, rr));
+        else o[16] = 1.f;
+    } else {
+        o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = -2.f;
+        o[13] = -1.f; o[14] = 0.f; o[15] = 0.f; o[16] = 0.f;
+    }
+    o[6] = clip(dvd(ivx, P.max_velocity_f), -1.f, 1.f);
+    o[7] = clip(dvd(ivy, P.max_velocity_f), -1.f, 1.f);
+    o[8] = clip(dvd(ivz, P.max_velocity_f), -1.f, 1.f);
+    {   // quaternion_to_euler, core.py:1103-1121 (float32) divided by pi
+        float w = e.qw, x = e.qx, y = e.qy, z = e.qz;
+        float sinr = mul(2.f, add(mul(w, x), mul(y, z)));
+        float cosr = sub(1.f, mul(2.f, add(mul(x, x), mul(y, y))));
+        float sinp = mul(2.f, sub(mul(w, y), mul(z, x)));
+        float siny = mul(2.f, add(mul(w, z), mul(x, y)));
+        float cosy = sub(1.f, mul(2.f, add(mul(y, y), mul(z, z))));
+        const float pif = 3.14159274101257324f;
+        o[9] = dvd(atan2f(sinr, cosr), pif);
+        o[10] = dvd(asinf(clip(sinp, -1.f, 1.f)), pif);
+        o[11] = dvd(atan2f(siny, cosy), pif);
+    }
+    o[12] = (float)clip(dvd(e.fuel, R(100.0)), R(0), R(1));
+    if (dg_det && link > 0.1f) {
+        o[17] = (float)clip(dvd(dgx, P.max_range_w), W(-1), W(1));
+        o[18] = (float)clip(dvd(dgy, P.max_range_w), W(-1), W(1));
+        o[19] = (float)clip(dvd(dgz, P.max_range_w), W(-1), W(1));
+        o[20] = (float)clip(dvd(dvx, P.max_velocity_w), W(-1), W(1));
+        o[21] = (float)clip(dvd(dvy, P.max_velocity_w), W(-1), W(1));
+        o[22] = (float)clip(dvd(dvz, P.max_velocity_w), W(-1), W(1));
+        o[23] = dgq;
+    } else {
+        o[17] = o[18] = o[19] = o[20] = o[21] = o[22] = -2.f;
+        o[23] = 0.f;
+    }
+    o[24] = link;
+    o[25] = fus;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reset (environment.py:353-603).  Rare path: double arithmetic where the reference has float64.
+// ------------------------------------------------------------------------------------------------
+template <typename R> HD void spawn(const KernelArgs<R>& A, Env<R>& e, const RngKey& key) {
+    const KParams<R>& P = A.P;
+    const uint32_t ep = (uint32_t)e.episode;
+    uint4 r0 = draw_raw(key, ep, 0u, HLYNR_BLK_SPAWN0);
+    uint4 r1 = draw_raw(key, ep, 0u, HLYNR_BLK_SPAWN1);
+    uint4 r2 = draw_raw(key, ep, 0u, HLYNR_BLK_SPAWN2);
+    double u00 = u01(r0.x), u01_ = u01(r0.y), u02 = u01(r0.z), u03 = u01(r0.w);
+    double u10 = u01(r1.x), u11 = u01(r1.y), u12 = u01(r1.z), u13 = u01(r1.w);
+    double u20 = u01(r2.x), u21 = u01(r2.y);
+    float mx, my, mz;
+    if (P.spherical) {
+        double radius = P.m_radius_lo + (P.m_radius_hi - P.m_radius_lo) * u00;
+        double az = (P.m_az_lo + (P.m_az_hi - P.m_az_lo) * u01_) * CUDART_PI / 180.0;
+        double el = (P.m_el_lo + (P.m_el_hi - P.m_el_lo) * u02) * CUDART_PI / 180.0;
+        mx = (float)(P.target_d[0] + radius * cos(el) * cos(az));
+        my = (float)(P.target_d[1] + radius * cos(el) * sin(az));
+        mz = (float)(P.target_d[2] + radius * sin(el));
+    } else {
+        mx = (float)(P.m_pos_lo[0] + (P.m_pos_hi[0] - P.m_pos_lo[0]) * u00);
+        my = (float)(P.m_pos_lo[1] + (P.m_pos_hi[1] - P.m_pos_lo[1]) * u01_);
+        mz = (float)(P.m_pos_lo[2] + (P.m_pos_hi[2] - P.m_pos_lo[2]) * u02);
+    }
+    float speed = (float)(P.m_speed_lo + (P.m_speed_hi - P.m_speed_lo) * u03);
+    float tx = sub((float)P.target_d[0], mx), ty = sub((float)P.target_d[1], my), tz = sub((float)P.target_d[2], mz);
+    float td = norm3(tx, ty, tz);
+    float mvx = mul(dvd(tx, td), speed), mvy = mul(dvd(ty, td), speed), mvz = mul(dvd(tz, td), speed);
+    float ix = (float)(P.i_pos_lo[0] + (P.i_pos_hi[0] - P.i_pos_lo[0]) * u10);
+    float iy = (float)(P.i_pos_lo[1] + (P.i_pos_hi[1] - P.i_pos_lo[1]) * u11);
+    float iz = (float)(P.i_pos_lo[2] + (P.i_pos_hi[2] - P.i_pos_lo[2]) * u12);
+    float vx, vy, vz;
+    float lx = sub(mx, ix), ly = sub(my, iy), lz = sub(mz, iz);
+    float ld = norm3(lx, ly, lz);
+    if (P.toward_missile) {
+        float sp = (float)(P.i_speed_lo + (P.i_speed_hi - P.i_speed_lo) * u13);
+        vx = mul(dvd(lx, ld), sp); vy = mul(dvd(ly, ld), sp); vz = mul(dvd(lz, ld), sp);
+    } else {
+        vx = (float)(P.i_vel_lo[0] + (P.i_vel_hi[0] - P.i_vel_lo[0]) * u13);
+        vy = (float)(P.i_vel_lo[1] + (P.i_vel_hi[1] - P.i_vel_lo[1]) * u20);
+        vz = (float)(P.i_vel_lo[2] + (P.i_vel_hi[2] - P.i_vel_lo[2]) * u21);
+    }
+    // orientation: rotate +Z onto the line of sight (environment.py:492-530); float64 on float32 inputs
+    float qw = 1.f, qx = 0.f, qy = 0.f, qz = 0.f;
+    if (ld > 1e-6f) {
+        double fx = dvd(lx, ld), fy = dvd(ly, ld), fz = dvd(lz, ld);
+        double ax = -fy, ay = fx;
+        double al = sqrt(ax * ax + ay * ay + 0.0);
+        if (al > 1e-6) {
+            ax /= al; ay /= al;
+            double h = acos(clip(fz, -1.0, 1.0)) / 2.0, sh = sin(h);
+            qw = (float)cos(h); qx = (float)(ax * sh); qy = (float)(ay * sh); qz = (float)(0.0 * sh);
+        } else if (!(fz > 0)) { qw = 0.f; qx = 1.f; }  // anti-aligned (quirk Q9: aligned -> identity)
+    }
+    e.mpx = mx; e.mpy = my; e.mpz = mz; e.mvx = mvx; e.mvy = mvy; e.mvz = mvz;
+    e.ipx = ix; e.ipy = iy; e.ipz = iz; e.ivx = vx; e.ivy = vy; e.ivz = vz;
+    e.qw = qw; e.qx = qx; e.qy = qy; e.qz = qz;
+    e.fuel = R(100.0); e.fuel_used = R(0);
+    e.wx = (float)P.base_wind[0]; e.wy = (float)P.base_wind[1]; e.wz = (float)P.base_wind[2];
+    e.thx = e.thy = e.thz = R(0);
+    int odelay = P.onboard_delay;
+    if (P.dr) {  // physics_randomizer.py:166-214, 243-297
+        float z0, z1, z2, z3, z4, zd;
+        uint4 a = draw_raw(key, ep, 0u, HLYNR_BLK_DR0), b = draw_raw(key, ep, 0u, HLYNR_BLK_DR1);
+        box_muller(a.x, a.y, &z0, &z1);
+        box_muller(a.z, a.w, &z2, &z3);
+        box_muller(b.x, b.y, &z4, &zd);
+        (void)z0;
+        if (P.isa) e.T0 = (R)((double)e.T0 + (0.0 + P.dr_var[1] * (double)z1));  // compounding random walk (quirk Q7)
+        if (P.mach) {
+            e.base_cd = (float)(0.3 * clip(1.0 + P.dr_var[2] * (double)z2, 0.1, 3.0));
+            e.peak = (float)(3.0 * clip(1.0 + P.dr_var[3] * (double)z3, 0.1, 3.0));
+        }
+        if (P.onboard_delay > 0) {
+            int nd = (int)(3.0 * clip(1.0 + P.dr_var[4] * (double)z4, 0.1, 3.0));
+            odelay = nd < 1 ? 1 : (nd > 10 ? 10 : nd);
+        }
+    }
+    e.steps = 0; e.worsen = 0;
+    e.flags = odelay << 8;  // crossed = false, kalman not initialised
+    e.kpx = e.kpy = e.kpz = e.kvx = e.kvy = e.kvz = R(0);
+    e.Ppp = 1000.f; e.Ppv = 0.f; e.Pvp = 0.f; e.Pvv = 1000.f;
+    float d0 = norm3(sub(mx, ix), sub(my, iy), sub(mz, iz));  // float32 state at this point in both builds
+    e.prev_d = e.last_d = e.min_d = (R)d0;
+    e.ep_ret = R(0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// one tick (environment.py:605-859)
+// ------------------------------------------------------------------------------------------------
+struct TickOut {
+    float reward;
+    float distance;
+    bool terminated, truncated, intercepted, hit, clamped, fuze;
+};
+
+template <typename R>
+HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const float act[6], TickOut& t) {
+    const KParams<R>& P = A.P;
+    e.steps += 1;
+    const uint32_t ep = (uint32_t)e.episode, st = (uint32_t)e.steps;
+    R a0 = (R)act[0], a1 = (R)act[1], a2 = (R)act[2], a3 = (R)act[3], a4 = (R)act[4], a5 = (R)act[5];
+    // SafetyClamp.apply (core.py:1069-1100); limits are in action units (quirk Q8)
+    bool clamped = false;
+    if (e.fuel <= R(0)) { a0 = a1 = a2 = R(0); clamped = true; }
+    if (a0 * a0 + a1 * a1 + a2 * a2 > R(2499.0)) {
+        R am = norm3(a0, a1, a2);
+        if (am > R(50.0)) { R f = dvd(R(50.0), am); a0 = mul(a0, f); a1 = mul(a1, f); a2 = mul(a2, f); clamped = true; }
+    }
+    if (a3 * a3 + a4 * a4 + a5 * a5 > R(24.9)) {
+        R gm = norm3(a3, a4, a5);
+        if (gm > R(5.0)) { R f = dvd(R(5.0), gm); a3 = mul(a3, f); a4 = mul(a4, f); a5 = mul(a5, f); clamped = true; }
+    }
+    t.clamped = clamped;
+    const R dt = P.dt;
+    // ---- _update_interceptor (environment.py:861-963) ----
+    {
+        R Tx = mul(a0, R(10000.0)), Ty = mul(a1, R(10000.0)), Tz = mul(a2, R(10000.0));
+        R wx = mul(a3, R(20.0)), wy = mul(a4, R(20.0)), wz = mul(a5, R(20.0));
+        if (P.thrust_dyn) {
+            e.thx = add(e.thx, dvd(mul(sub(Tx, e.thx), dt), P.tau));
+            e.thy = add(e.thy, dvd(mul(sub(Ty, e.thy), dt), P.tau));
+            e.thz = add(e.thz, dvd(mul(sub(Tz, e.thz), dt), P.tau));
+            Tx = e.thx; Ty = e.thy; Tz = e.thz;
+        }
+        R tm = norm3(Tx, Ty, Tz);
+        R burn = mul(mul(dvd(tm, R(500.0)), R(0.1)), dt);
+        e.fuel = sub(e.fuel, burn);
+        e.fuel_used = add(e.fuel_used, burn);
+        if (e.fuel <= R(0)) { e.fuel = R(0); Tx = Ty = Tz = R(0); e.thx = e.thy = e.thz = R(0); }
+        R tax = dvd(Tx, R(500.0)), tay = dvd(Ty, R(500.0)), taz = dvd(Tz, R(500.0));
+        R alt = e.ipz > R(0) ? e.ipz : R(0);
+        R vax = sub(e.ivx, (R)e.wx), vay = sub(e.ivy, (R)e.wy), vaz = sub(e.ivz, (R)e.wz);
+        R dax, day, daz;
+        drag_accel(P, e, vax, vay, vaz, alt, R(1.0), R(1.0), R(500.0), &dax, &day, &daz);
+        R ax = add(add(tax, dax), R(0)), ay = add(add(tay, day), R(0)), az = add(add(taz, daz), (R)(-9.81f));
+        if (P.validate && !(isfinite(ax) && isfinite(ay) && isfinite(az))) {
+            ax = nan_guard(ax, R(50)); ay = nan_guard(ay, R(50)); az = nan_guard(az, R(50));
+        }
+        e.ivx = add(e.ivx, mul(ax, dt)); e.ivy = add(e.ivy, mul(ay, dt)); e.ivz = add(e.ivz, mul(az, dt));
+        e.ipx = add(e.ipx, mul(e.ivx, dt)); e.ipy = add(e.ipy, mul(e.ivy, dt)); e.ipz = add(e.ipz, mul(e.ivz, dt));
+        R wn = norm3(wx, wy, wz);
+        R ang = mul(wn, dt);
+        if (ang > R(1e-6)) {  // quaternion integration, :937-956; product rounded to float32 (:1331)
+            R sh, ch;
+            sincos_r(mul(ang, R(0.5)), &sh, &ch);
+            R w1 = ch, x1 = mul(dvd(wx, wn), sh), y1 = mul(dvd(wy, wn), sh), z1 = mul(dvd(wz, wn), sh);
+            R w2 = (R)e.qw, x2 = (R)e.qx, y2 = (R)e.qy, z2 = (R)e.qz;
+            float nw = (float)sub(sub(sub(mul(w1, w2), mul(x1, x2)), mul(y1, y2)), mul(z1, z2));
+            float nx = (float)sub(add(add(mul(w1, x2), mul(x1, w2)), mul(y1, z2)), mul(z1, y2));
+            float ny = (float)add(add(sub(mul(w1, y2), mul(x1, z2)), mul(y1, w2)), mul(z1, x2));
+            float nz = (float)add(sub(add(mul(w1, z2), mul(x1, y2)), mul(y1, x2)), mul(z1, w2));
+            double s2 = (double)__fmul_rn(nw, nw) + (double)__fmul_rn(nx, nx);
+            s2 += (double)__fmul_rn(ny, ny);
+            s2 += (double)__fmul_rn(nz, nz);
+            float nn = __fsqrt_rn((float)s2);
+            e.qw = dvd(nw, nn); e.qx = dvd(nx, nn); e.qy = dvd(ny, nn); e.qz = dvd(nz, nn);
+        }
+    }
+    // ---- _update_missile_state (environment.py:1069-1117), same current_wind ----
+    {
+        R alt = e.mpz > R(0) ? e.mpz : R(0);
+        R vax = sub(e.mvx, (R)e.wx), vay = sub(e.mvy, (R)e.wy), vaz = sub(e.mvz, (R)e.wz);
+        R dax, day, daz;
+        drag_accel(P, e, vax, vay, vaz, alt, R(2.0), P.missile_ratio, R(1000.0), &dax, &day, &daz);
+        double ex = 0.0, ey = 0.0, ez = 0.0;
+        if (P.evasion) {
+            float z0, z1, z2;
+            draw_normal3(key, ep, st, HLYNR_BLK_EVADE, &z0, &z1, &z2);
+            ex = (double)z0 * 2.0; ey = (double)z1 * 2.0; ez = (double)z2 * 2.0;
+        }
+        // total_accel = drag + gravity + evasion is float64 in the reference even without evasion
+        // (evasion = np.zeros(3)), and velocity += total_accel * dt is evaluated in float64: kept as is.
+        double ax = (double)add(dax, R(0)) + ex, ay = (double)add(day, R(0)) + ey, az = (double)add(daz, (R)(-9.81f)) + ez;
+        if (P.validate && !(isfinite(ax) && isfinite(ay) && isfinite(az))) {
+            ax = nan_guard(ax, 20.0); ay = nan_guard(ay, 20.0); az = nan_guard(az, 20.0);
+        }
+        e.mvx = (R)add((double)e.mvx, mul(ax, P.dt_d));
+        e.mvy = (R)add((double)e.mvy, mul(ay, P.dt_d));
+        e.mvz = (R)add((double)e.mvz, mul(az, P.dt_d));
+        e.mpx = add(e.mpx, mul(e.mvx, dt)); e.mpy = add(e.mpy, mul(e.mvy, dt)); e.mpz = add(e.mpz, mul(e.mvz, dt));
+    }
+    // ---- _update_wind (environment.py:1119-1129): the wind used by the NEXT tick ----
+    if (P.enh_wind) {  // EnhancedWindModel.get_wind_vector, physics_models.py:351-387
+        R alt = e.ipz > R(0) ? e.ipz : R(0);
+        R pf;
+        if (alt <= R(10.0)) pf = R(1.0);
+        else if (alt <= P.blh) pf = pow_r(dvd(alt, R(10.0)), R(0.143));
+        else pf = P.pf_top;
+        R wvx = mul(P.base_wind[0], pf), wvy = mul(P.base_wind[1], pf), wvz = mul(P.base_wind[2], pf);
+        R ti;
+        if (alt <= R(10.0)) ti = P.ti_low;
+        else if (alt <= P.blh) ti = mul(P.turb, sub(R(1.0), mul(dvd(alt, P.blh), R(0.7))));
+        else ti = P.ti_high;
+        if (ti > R(0)) {
+            R scale = mul(ti, norm3(wvx, wvy, wvz));
+            float z0, z1, z2;
+            draw_normal3(key, ep, st, HLYNR_BLK_WIND, &z0, &z1, &z2);
+            wvx = wvx + (scale * (R)z0) * P.lp; wvy = wvy + (scale * (R)z1) * P.lp; wvz = wvz + (scale * (R)z2) * P.lp;
+        }
+        uint4 ur = draw_raw(key, ep, st, HLYNR_BLK_UNI);
+        if (u01(ur.x) < 0.001f) {  // gust, :381-385 (0.1 % of ticks)
+            float g0, g1, g2;
+            draw_normal3(key, ep, st, HLYNR_BLK_GUST_DIR, &g0, &g1, &g2);
+            uint4 gm = draw_raw(key, ep, st, HLYNR_BLK_GUST_MAG);
+            double nn = sqrt((double)g0 * g0 + (double)g1 * g1 + (double)g2 * g2) + 1e-6;
+            double mag = P.gust_scale_d * (double)(-logf(u01_open(gm.x)));
+            wvx = (R)((double)wvx + ((double)g0 / nn) * mag);
+            wvy = (R)((double)wvy + ((double)g1 / nn) * mag);
+            wvz = (R)((double)wvz + ((double)g2 / nn) * mag);
+        }
+        e.wx = (float)wvx; e.wy = (float)wvy; e.wz = (float)wvz;
+    } else if (P.wind_var > R(0)) {  // AR(1) wind, environment.py:1127-1129 (float64 in the reference)
+        float z0, z1, z2;
+        draw_normal3(key, ep, st, HLYNR_BLK_WIND, &z0, &z1, &z2);
+        e.wx = (float)(R(0.95) * (R)e.wx + R(0.05) * (P.base_wind[0] + (R)z0 * P.wind_var));
+        e.wy = (float)(R(0.95) * (R)e.wy + R(0.05) * (P.base_wind[1] + (R)z1 * P.wind_var));
+        e.wz = (float)(R(0.95) * (R)e.wz + R(0.05) * (P.base_wind[2] + (R)z2 * P.wind_var));
+    }
+    // ---- distance / intercept / termination (environment.py:657-814) ----
+    R dist = norm3(sub(e.mpx, e.ipx), sub(e.mpy, e.ipy), sub(e.mpz, e.ipz));
+    bool intercepted = dist < (P.fuze ? P.kill_radius : A.C.intercept_radius);
+    if (dist < e.min_d) e.min_d = dist;
+    if (intercepted) e.flags |= FLAG_CROSSED;
+    bool fuze = false;
+    if (P.fuze && e.min_d < P.kill_radius) { fuze = true; intercepted = true; }
+    bool term = false, hit = false;
+    bool missile_down = e.mpz <= R(0);
+    if (P.precision_mode ? missile_down : (!intercepted && missile_down)) {
+        R gx = sub(e.mpx, P.target_x), gy = sub(e.mpy, P.target_y);
+        hit = sqr(dot2(gx, gy, gx, gy)) < R(500.0);
+    }
+    if (P.precision_mode) term = missile_down;
+    else term = intercepted || missile_down;
+    if (e.ipz < R(0)) term = true;
+    else if (e.fuel <= R(0)) term = true;
+    else if (e.steps > 1000) {  // smart early termination, :795-811 (last_d only refreshed here, quirk Q11)
+        if (dist > e.last_d) e.worsen += 1;
+        else e.worsen = e.worsen - 5 > 0 ? e.worsen - 5 : 0;
+        e.last_d = dist;
+        if (e.worsen > 500 && dist > R(2500.0)) term = true;
+    }
+    t.truncated = e.steps >= P.max_steps;
+    t.terminated = term; t.intercepted = intercepted; t.hit = hit; t.fuze = fuze;
+    t.distance = (float)dist;
+    // ---- _calculate_reward (environment.py:1131-1320) ----
+    R r;
+    const bool crashed = e.ipz < R(0), dry = e.fuel <= R(0);
+    if (P.precision_mode) {
+        if (term) {
+            R md = e.min_d;
+            if (e.flags & FLAG_CROSSED) {
+                R cr = A.C.intercept_radius;
+                r = R(3000.0);
+                if (md < cr) r = add(r, mul(dvd(sub(cr, md), cr), R(1000.0)));
+                r = add(r, mul(exp_r(dvd(-md, R(25.0))), R(500.0)));
+                r = add(r, mul(exp_r(dvd(-md, R(10.0))), R(1000.0)));
+                r = add(r, mul(exp_r(dvd(-md, R(3.0))), R(500.0)));
+                r = add(r, (R)((double)(P.max_steps - e.steps) * 0.3));
+            } else {
+                r = mul(-md, R(0.5));
+                if (r < R(-2000.0)) r = R(-2000.0);
+                if (hit) r = sub(r, R(1000.0));
+                else if (crashed) r = sub(r, R(500.0));
+                else if (dry) r = sub(r, R(300.0));
+            }
+        } else {
+            R dl = sub(e.prev_d, dist);
+            r = mul(clip(dvd(dvd(dl, dt), R(100.0)), R(-0.5), R(2.0)), R(0.5));
+            if (dist < R(50.0)) { r = add(r, mul(dl, R(5.0))); r = add(r, exp_r(dvd(-dist, R(10.0)))); }
+            else if (dist < R(150.0)) r = add(r, mul(dl, R(3.0)));
+            else if (dist < R(500.0)) r = add(r, mul(dl, R(1.5)));
+            else r = add(r, mul(dl, R(0.8)));
+            R sp = norm3(e.ivx, e.ivy, e.ivz);
+            if (sp > R(1.0) && dist > R(10.0)) {
+                R al = dot3(dvd(e.ivx, sp), dvd(e.ivy, sp), dvd(e.ivz, sp), dvd(sub(e.mpx, e.ipx), dist),
+                            dvd(sub(e.mpy, e.ipy), dist), dvd(sub(e.mpz, e.ipz), dist));
+                r = add(r, mul(al, R(0.3)));
+            }
+            r = sub(r, R(0.2));
+            e.prev_d = dist;
+        }
+    } else if (intercepted) {
+        r = (R)(5000.0 + (double)(P.max_steps - e.steps) * 0.5);
+    } else if (term) {
+        r = mul(-dist, R(0.5));
+        if (r < R(-2000.0)) r = R(-2000.0);
+        if (hit) r = sub(r, R(1000.0));
+        else if (crashed) r = sub(r, R(500.0));
+        else if (dry) r = sub(r, R(300.0));
+    } else {
+        R dl = sub(e.prev_d, dist);
+        r = mul(clip(dvd(dvd(dl, dt), R(100.0)), R(-0.5), R(2.0)), R(0.3));
+        r = add(r, mul(dl, dist < R(200.0) ? R(2.0) : (dist < R(500.0) ? R(1.0) : R(0.5))));
+        r = sub(r, R(0.5));
+        e.prev_d = dist;
+    }
+    e.ep_ret = e.ep_ret + r;
+    t.reward = (float)r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// episode statistics: warp-level reduction, one atomic per warp per finished-episode event
+// ------------------------------------------------------------------------------------------------
+HD double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename R>
+HD void account_episodes(const KernelArgs<R>& A, bool active, bool done, const Env<R>& e, const TickOut& t) {
+    // called by all lanes of the warp
+    unsigned any = __ballot_sync(0xffffffffu, active && done);
+    if (any == 0u) return;
+    const bool d = active && done;
+    double v[12];
+    v[0] = d ? 1.0 : 0.0;
+    v[1] = (d && t.intercepted) ? 1.0 : 0.0;
+    v[2] = d ? (double)e.ep_ret : 0.0;
+    v[3] = d ? (double)e.steps : 0.0;
+    v[4] = d ? (double)e.min_d : 0.0;
+    v[5] = d ? (double)t.distance : 0.0;
+    bool te = d && t.terminated && !t.intercepted;
+    bool c_hit = te && t.hit;
+    bool c_crash = te && !c_hit && e.ipz < R(0);
+    bool c_fuel = te && !c_hit && !c_crash && e.fuel <= R(0);
+    bool c_ground = te && !c_hit && !c_crash && !c_fuel && e.mpz <= R(0);
+    bool c_worse = te && !c_hit && !c_crash && !c_fuel && !c_ground;
+    v[6] = c_hit; v[7] = c_crash; v[8] = c_fuel; v[9] = c_ground; v[10] = c_worse;
+    v[11] = (d && !t.terminated) ? 1.0 : 0.0;
+    double* slot = A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        double s = warp_sum(v[k]);
+        if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(slot + k, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// coalesced [N,26] / [N,6] transfers through shared memory (one warp-private tile per warp)
+// ------------------------------------------------------------------------------------------------
+#define OBS_PAD 27  // odd row pitch -> conflict-free column writes
+
+// every lane writes its 26 values into the warp tile, then the warp streams 32*26 floats out linearly
+HD void store_obs_rows(float* tile, const float o[HLYNR_OBS_DIM], float* dst, int64_t warp_first_env, int64_t n,
+                       unsigned lane) {
+#pragma unroll
+    for (int k = 0; k < HLYNR_OBS_DIM; ++k) tile[lane * OBS_PAD + k] = o[k];
+    __syncwarp();
+    int64_t rows = n - warp_first_env;
+    int valid = rows >= 32 ? 32 * HLYNR_OBS_DIM : (int)rows * HLYNR_OBS_DIM;
+    float* base = dst + warp_first_env * HLYNR_OBS_DIM;
+#pragma unroll
+    for (int k = 0; k < HLYNR_OBS_DIM; ++k) {
+        int idx = k * 32 + (int)lane;
+        if (idx < valid) base[idx] = tile[(idx / HLYNR_OBS_DIM) * OBS_PAD + (idx % HLYNR_OBS_DIM)];
+    }
+    __syncwarp();
+}
+
+template <typename R> HD void write_info(const KernelArgs<R>& A, int64_t i, const Env<R>& e, const TickOut& t, const ObsOut& ob) {
+    const HlynrInfoSoA& f = A.io.info;
+    if (f.distance) f.distance[i] = t.distance;
+    if (f.min_distance) f.min_distance[i] = (float)e.min_d;
+    if (f.fuel_remaining) f.fuel_remaining[i] = (float)e.fuel;
+    if (f.fuel_used) f.fuel_used[i] = (float)e.fuel_used;
+    if (f.steps) f.steps[i] = e.steps;
+    if (f.flags)
+        f.flags[i] = (uint8_t)((t.intercepted ? 1 : 0) | (t.hit ? 2 : 0) | (t.clamped ? 4 : 0) | (ob.onboard_det ? 8 : 0) |
+                               (ob.ground_det ? 16 : 0) | ((e.flags & FLAG_CROSSED) ? 32 : 0) | (t.fuze ? 64 : 0) |
+                               ((e.flags & FLAG_KF_INIT) ? 128 : 0));
+    if (f.interceptor_pos) { f.interceptor_pos[3 * i] = (float)e.ipx; f.interceptor_pos[3 * i + 1] = (float)e.ipy; f.interceptor_pos[3 * i + 2] = (float)e.ipz; }
+    if (f.missile_pos) { f.missile_pos[3 * i] = (float)e.mpx; f.missile_pos[3 * i + 1] = (float)e.mpy; f.missile_pos[3 * i + 2] = (float)e.mpz; }
+    if (f.episode_return) f.episode_return[i] = (float)e.ep_ret;
+    if (f.episode_length) f.episode_length[i] = e.steps;
+}
+
+HD RngKey make_key(uint32_t seed_lo, uint32_t seed_hi, int64_t global_env) {
+    RngKey k;
+    k.k0 = seed_lo; k.k1 = seed_hi;
+    k.c0 = (uint32_t)((uint64_t)global_env & 0xffffffffu);
+    k.c3hi = (uint32_t)((uint64_t)global_env >> 32) << 16;
+    return k;
+}
+
+#define HLYNR_BLOCK 128
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+// step(): one tick of every env + SB3 auto-reset.  k_steps > 1 = fused rollout (state stays in registers).
+template <typename R, bool kRollout>
+__global__ void __launch_bounds__(HLYNR_BLOCK) step_kernel(const __grid_constant__ KernelArgs<R> A) {
+    __shared__ float tiles[HLYNR_BLOCK / 32][32 * OBS_PAD];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * HLYNR_BLOCK + threadIdx.x;
+    const int64_t warp_first = i - lane;
+    const bool active = i < A.n;
+    const int64_t ii = active ? i : A.n - 1;  // inactive lanes shadow the last env and never store
+    Env<R> e;
+    load_env(A, ii, e);
+    const RngKey key = make_key(A.seed_lo, A.seed_hi, A.env_offset + ii);
+    const int steps = kRollout ? A.k_steps : 1;
+    float rsum = 0.f;
+    int dcount = 0, locks = 0;
+    ObsOut ob;
+#pragma unroll 1
+    for (int s = 0; s < steps; ++s) {
+        const uint32_t tick = A.tick + (uint32_t)s;
+        float act[6];
+        if (kRollout && A.io.actions == nullptr) {  // synthetic random policy, a = 2u-1
+            uint4 r0 = draw_raw(key, (uint32_t)e.episode, (uint32_t)e.steps + 1u, HLYNR_BLK_ACT0);
+            uint4 r1 = draw_raw(key, (uint32_t)e.episode, (uint32_t)e.steps + 1u, HLYNR_BLK_ACT1);
+            act[0] = 2.f * u01(r0.x) - 1.f; act[1] = 2.f * u01(r0.y) - 1.f; act[2] = 2.f * u01(r0.z) - 1.f;
+            act[3] = 2.f * u01(r0.w) - 1.f; act[4] = 2.f * u01(r1.x) - 1.f; act[5] = 2.f * u01(r1.y) - 1.f;
+        } else {
+            const float2* ap = reinterpret_cast<const float2*>(A.io.actions + ((int64_t)s * A.n + ii) * HLYNR_ACT_DIM);
+            float2 p0 = __ldg(ap), p1 = __ldg(ap + 1), p2 = __ldg(ap + 2);
+            act[0] = p0.x; act[1] = p0.y; act[2] = p1.x; act[3] = p1.y; act[4] = p2.x; act[5] = p2.y;
+        }
+        TickOut t;
+        tick_physics(A, e, key, act, t);
+        bool need_reset = false;
+        bool done = false;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {  // pass 1 = in-kernel auto-reset of finished envs (one copy of observe)
+            if (pass == 1) {
+                if (!need_reset) break;
+                e.episode += 1;
+                spawn(A, e, key);
+            }
+            observe(A, e, key, ii, tick, ob);
+            if (pass == 0) {
+                done = t.terminated || t.truncated;
+                if (ob.onboard_det) locks += 1;
+                if (!kRollout && active) {
+                    A.io.reward[i] = t.reward;
+                    A.io.terminated[i] = t.terminated ? 1 : 0;
+                    A.io.truncated[i] = t.truncated ? 1 : 0;
+                    write_info(A, i, e, t, ob);
+                }
+                rsum += t.reward;
+                account_episodes(A, active, done, e, t);
+                need_reset = done && A.auto_reset;
+                if (need_reset) {
+                    dcount += 1;
+                    if (!kRollout && active && A.io.terminal_obs) {
+#pragma unroll
+                        for (int k = 0; k < HLYNR_OBS_DIM; ++k) A.io.terminal_obs[i * HLYNR_OBS_DIM + k] = ob.o[k];
+                    }
+                }
+            }
+        }
+    }
+    if (A.io.obs) store_obs_rows(tiles[warp], ob.o, A.io.obs, warp_first, A.n, lane);
+    if (kRollout && active) {
+        if (A.io.reward_sum) A.io.reward_sum[i] = rsum;
+        if (A.io.done_count) A.io.done_count[i] = dcount;
+    }
+    if (active) store_env(A, i, e);
+    {   // ticks simulated and onboard-lock ticks: one atomic pair per block, spread over the stat slots
+        __shared__ int s_locks[HLYNR_BLOCK / 32], s_act[HLYNR_BLOCK / 32];
+        int wl = __reduce_add_sync(0xffffffffu, active ? locks : 0);
+        int wa = __reduce_add_sync(0xffffffffu, active ? steps : 0);
+        if (lane == 0) { s_locks[warp] = wl; s_act[warp] = wa; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tl = 0, ta = 0;
+            for (int w = 0; w < HLYNR_BLOCK / 32; ++w) { tl += s_locks[w]; ta += s_act[w]; }
+            double* slot = A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS;
+            atomicAdd(slot + 12, (double)ta);
+            if (tl) atomicAdd(slot + 13, (double)tl);
+        }
+    }
+}
+
+// reset(): environment.py:353.  mask == NULL resets every env.
+template <typename R> __global__ void __launch_bounds__(HLYNR_BLOCK) reset_kernel(const __grid_constant__ KernelArgs<R> A) {
+    __shared__ float tiles[HLYNR_BLOCK / 32][32 * OBS_PAD];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * HLYNR_BLOCK + threadIdx.x;
+    const bool active = i < A.n;
+    const int64_t ii = active ? i : A.n - 1;
+    const bool doit = active && (A.io.reset_mask == nullptr || A.io.reset_mask[ii] != 0);
+    if (!__any_sync(0xffffffffu, doit)) return;
+    Env<R> e;
+    load_env(A, ii, e);
+    const RngKey key = make_key(A.seed_lo, A.seed_hi, A.env_offset + ii);
+    ObsOut ob;
+    if (doit) {
+        e.episode += 1;
+        spawn(A, e, key);
+        observe(A, e, key, ii, A.tick, ob);
+        store_env(A, i, e);
+        if (A.io.obs) {
+#pragma unroll
+            for (int k = 0; k < HLYNR_OBS_DIM; ++k) A.io.obs[i * HLYNR_OBS_DIM + k] = ob.o[k];
+        }
+    }
+    (void)tiles; (void)lane; (void)warp;
+}
+
+}  // namespace hlynr

@@ -247,12 +247,18 @@ int hlynr_reset_host(hlynr_t* sim, const uint8_t* mask_host, float* obs_host);
 int hlynr_step_host(hlynr_t* sim, const float* actions_host, float* obs_host, float* reward_host,
                     uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host,
                     int auto_reset);
+/* Pinned host buffers owned by the handle: float[N,6], float[N,26], float[N], uint8[N], uint8[N].  Passing
+ * these very pointers to hlynr_step_host / hlynr_reset_host skips the staging memcpy. */
+int hlynr_pinned_buffers(hlynr_t* sim, float** actions, float** obs, float** reward, uint8_t** terminated,
+                         uint8_t** truncated);
 /* Copies the info arrays of the last hlynr_step_host call to host (each pointer optional, host). */
 int hlynr_info_host(hlynr_t* sim, HlynrInfoSoA* host_arrays);
 
 /* Episode statistics block: device pointer (HLYNR_STATS_WORDS doubles, for an in-place NCCL
  * all-reduce), host read-back, and zeroing. */
 int hlynr_stats_device_ptr(hlynr_t* sim, double** out_dev);
+/* Folds the per-block partial sums into the block hlynr_stats_device_ptr points at (stream-ordered). */
+int hlynr_stats_reduce(hlynr_t* sim, void* stream);
 int hlynr_get_stats(hlynr_t* sim, HlynrStats* host_out, int zero_after, void* stream);
 
 /* Oracle interchange: copy `count` envs starting at local index `first`. */

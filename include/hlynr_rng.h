@@ -18,8 +18,9 @@
  *   uniform  [0,1):  u(x)  = (x >> 8) * 2^-24                      (exact in float32)
  *   uniform  (0,1]:  uo(x) = ((x >> 8) + 1) * 2^-24
  *   normals  (float32 Box-Muller, 4 per block):
- *        r = sqrtf(-2 logf(uo(x0))), t = 2*pi_f * u(x1):  z0 = r cosf(t), z1 = r sinf(t)
- *        r = sqrtf(-2 logf(uo(x2))), t = 2*pi_f * u(x3):  z2 = r cosf(t), z3 = r sinf(t)
+ *        r = sqrtf(-2 logf(uo(x0))), t = 2 * u(x1) (exact):  z0 = r cospif(t), z1 = r sinpif(t)
+ *        r = sqrtf(-2 logf(uo(x2))), t = 2 * u(x3) (exact):  z2 = r cospif(t), z3 = r sinpif(t)
+ *        (cospif(t) = cos(pi t) evaluated to float accuracy; no range reduction is needed for t in [0,2))
  *   exponential(1):  e = -logf(uo(x0))
  *
  * The same draws are injected into the unmodified reference by oracle/ref_harness.py (tape

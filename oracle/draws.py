@@ -65,18 +65,15 @@ def u01_open(x):
     return (((np.asarray(x, dtype=np.uint32) >> np.uint32(8)) + np.uint32(1)).astype(np.float32)) * np.float32(2.0 ** -24)
 
 
-TWO_PI_F = np.float32(6.283185307179586)
-
-
 def normals(raw):
     """raw (..., 4) uint32 -> (..., 4) float32 standard normals (float32 Box-Muller)."""
     raw = np.asarray(raw, dtype=np.uint32)
     out = np.empty(raw.shape, dtype=np.float32)
     for a in (0, 2):
         r = np.sqrt(np.float32(-2.0) * np.log(u01_open(raw[..., a])))
-        t = TWO_PI_F * u01(raw[..., a + 1])
-        out[..., a] = r * np.cos(t)
-        out[..., a + 1] = r * np.sin(t)
+        t = np.float64(2.0) * u01(raw[..., a + 1]).astype(np.float64)  # exact
+        out[..., a] = r * np.cos(np.pi * t).astype(np.float32)
+        out[..., a + 1] = r * np.sin(np.pi * t).astype(np.float32)
     return out
 
 

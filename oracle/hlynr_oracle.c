@@ -117,9 +117,9 @@ static void draw_normal4(const DrawCtx* c, uint32_t step, uint32_t blk, double z
     draw_raw(c, step, blk, r);
     for (int a = 0; a < 4; a += 2) {
         float rad = sqrtf(-2.0f * logf(u01_open(r[a])));
-        float th = 6.283185307179586f * u01(r[a + 1]);
-        z[a] = (double)(rad * cosf(th));
-        z[a + 1] = (double)(rad * sinf(th));
+        double t = 2.0 * (double)u01(r[a + 1]); /* exact */
+        z[a] = (double)(rad * (float)cos(M_PI * t));
+        z[a + 1] = (double)(rad * (float)sin(M_PI * t));
     }
 }
 static double draw_exp(const DrawCtx* c, uint32_t step, uint32_t blk) {

@@ -100,3 +100,55 @@ def replay_against_golden(sim, g, rtol_state, obs_atol, reward_rtol, reward_atol
         np.testing.assert_allclose(st[k][alive], ref, rtol=rtol_state, atol=rtol_state * scale,
                                    err_msg=f"final state {k}")
     return worst
+
+
+class CudaBatch:
+    """HlynrSim behind the RefBatch / OracleBatch call surface (numpy in, numpy out), calling through the C ABI
+    with device tensors."""
+
+    def __init__(self, params, curriculum, n_envs, seed=1234, env_id_offset=0, float64=False, device=0):
+        import torch
+        from hlynr_intercept_b200.sim import HlynrSim
+
+        self.torch = torch
+        self.sim = HlynrSim(params=params, curriculum=curriculum, n_envs=n_envs, device=device, seed=seed,
+                            env_id_offset=env_id_offset, precision="fp64" if float64 else "fp32")
+        self.n = n_envs
+
+    def reset(self, mask=None):
+        m = None if mask is None else self.torch.as_tensor(np.asarray(mask, np.uint8))
+        return self.sim.reset(m).cpu().numpy().copy()
+
+    def step(self, actions, auto_reset=True):
+        a = self.torch.as_tensor(np.ascontiguousarray(actions, np.float32)).to(self.sim.device)
+        self.sim._alloc_out()["terminal_obs"].fill_(float("nan"))
+        obs, rew, te, tr, tobs, info = self.sim.step(a, auto_reset=auto_reset, want_info=True)
+        self.torch.cuda.synchronize()
+        return (obs.cpu().numpy().copy(), rew.cpu().numpy().astype(np.float64), te.cpu().numpy().copy(),
+                tr.cpu().numpy().copy(), tobs.cpu().numpy().copy(), {k: v.cpu().numpy().copy() for k, v in info.items()})
+
+    def export_state(self):
+        return self.sim.export_state()
+
+    def stats(self, zero_after=False):
+        return self.sim.stats(zero_after)
+
+
+class Lockstep:
+    """Steps a primary simulator and the oracle on the same actions; exposes the oracle's decision margins."""
+
+    def __init__(self, primary, shadow):
+        self.primary, self.shadow = primary, shadow
+        self.margin = None
+
+    def reset(self):
+        self.shadow.reset()
+        return self.primary.reset()
+
+    def step(self, actions):
+        self.shadow_out = self.shadow.step(actions)
+        self.margin = self.shadow.margin
+        return self.primary.step(actions)
+
+    def export_state(self):
+        return self.primary.export_state()

@@ -1,0 +1,189 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden fixtures generated from the unmodified
+reference and against the C oracle on identical seeds, actions and injected draws.
+
+Tolerances are the north_star's: integers / booleans bit-exact; floats rtol 1e-3 (fp32 build vs native
+reference) and rtol 1e-5 (fp64 build vs up-cast float64 reference), over 1-step and >=100-step horizons.
+Envs whose decision margin (distance to a threshold, reported by the oracle) is below the tolerance are
+excluded from the exact comparison from that tick on, and counted.
+"""
+import numpy as np
+import pytest
+
+from common import (GOLDEN_CASES, STATE_FLOAT_FIELDS, STATE_INT_FIELDS, CudaBatch, Lockstep, golden_setup, load_golden,
+                    replay_against_golden)
+from hlynr_intercept_b200 import config
+from oracle import draws, oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = {  # float64 flag -> tolerances
+    False: dict(rtol_state=1e-3, obs_atol=1e-3, reward_rtol=1e-3, reward_atol=2e-3, margin_tol=1e-4, tti_atol=5e-3),
+    True: dict(rtol_state=1e-5, obs_atol=1e-5, reward_rtol=1e-5, reward_atol=1e-5, margin_tol=1e-6, tti_atol=1e-4),
+}
+
+
+def test_philox_on_device_matches_contract():
+    P, cur = config.resolve_config(config.baseline_config("cfg2"), warn_dead=False)
+    sim = CudaBatch(P, cur, 32, seed=0x1234567890AB).sim
+    for env, ep, st, blk in [(0, 0, 0, 0), (5, 3, 17, 2), (2 ** 33 + 7, 9, 1999, 4), (123456, 0, 1, 16)]:
+        raw, uni, nrm = sim.debug_draws(env, ep, st, blk)
+        want = draws.block(0x1234567890AB, env, ep, st, blk)
+        assert (raw == want).all()
+        assert (uni == draws.u01(want)).all()
+        np.testing.assert_allclose(nrm, draws.normals(want), rtol=2e-6, atol=2e-7)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_cuda_matches_reference_golden(name):
+    g = load_golden(name)
+    meta = g["meta"]
+    P, cur = golden_setup(g)
+    f64 = meta["float64"]
+    cuda = CudaBatch(P, cur, meta["n_envs"], seed=meta["seed"], float64=f64)
+    shadow = oracle.OracleBatch(P, cur, meta["n_envs"], seed=meta["seed"], float64=f64)
+    sim = Lockstep(cuda, shadow)
+    tol = TOL[f64]
+    w = replay_against_golden(sim, g, margin_fn=lambda: sim.margin, **tol)
+    assert w["dropped"] <= max(1, meta["n_envs"] // 8), w
+
+
+@pytest.mark.parametrize("base", ["cfg2", "cfg3", "cfg4"])
+@pytest.mark.parametrize("f64", [False, True])
+def test_cuda_matches_oracle_4096_envs_100_steps(base, f64):
+    """BASELINE cfg2 size (4096 envs): CUDA vs oracle, 1-step and 100-step horizon."""
+    n, T, seed = 4096, 100, 4242
+    P, cur = config.resolve_config(config.baseline_config(base), warn_dead=False)
+    cuda = CudaBatch(P, cur, n, seed=seed, float64=f64)
+    orc = oracle.OracleBatch(P, cur, n, seed=seed, float64=f64, threads=8)
+    tol = TOL[f64]
+    o_c, o_o = cuda.reset(), orc.reset()
+    np.testing.assert_allclose(o_c, o_o, rtol=0, atol=tol["obs_atol"])
+    alive = np.ones(n, bool)
+    env_ids = np.arange(n)
+    episode = np.zeros(n, np.int64)
+    steps = np.zeros(n, np.int64)
+    for t in range(T):
+        act = draws.random_actions(seed, env_ids, episode, steps + 1)
+        oc, rc, tec, trc, _, ic = cuda.step(act)
+        oo, ro, teo, tro, _, io = orc.step(act)
+        low = orc.margin < tol["margin_tol"]
+        differs = (tec != teo) | (trc != tro) | (ic["flags"] != io["flags"]) | (np.abs(oc - oo).max(axis=1) > tol["tti_atol"])
+        alive &= ~(low & differs)
+        a = alive
+        assert (tec[a] == teo[a]).all() and (trc[a] == tro[a]).all(), f"done mismatch at t={t}"
+        assert (ic["flags"][a] == io["flags"][a]).all(), f"flag mismatch at t={t}"
+        assert (ic["steps"][a] == io["steps"][a]).all()
+        d = np.abs(oc[a] - oo[a])
+        loose = d[:, [9, 10, 11, 13, 16]].max()
+        d[:, [9, 10, 11, 13, 16]] = 0
+        assert d.max() <= tol["obs_atol"], f"obs mismatch t={t}: {d.max()} idx {np.unravel_index(d.argmax(), d.shape)}"
+        assert loose <= tol["tti_atol"], f"ill-conditioned obs mismatch t={t}: {loose}"
+        err = np.abs(rc[a] - ro[a])
+        assert (err <= tol["reward_atol"] + tol["reward_rtol"] * np.abs(ro[a])).all(), f"reward mismatch t={t}: {err.max()}"
+        for k in ("distance", "min_distance", "fuel_remaining", "fuel_used"):
+            np.testing.assert_allclose(ic[k][a], io[k][a], rtol=tol["rtol_state"], atol=tol["reward_atol"])
+        done = (teo | tro).astype(bool)
+        episode += done
+        steps = np.where(done, 0, steps + 1)
+    assert alive.mean() > 0.995, f"too many low-margin exclusions: {(~alive).sum()}"
+    sc, so = cuda.export_state(), orc.export_state()
+    for k in STATE_INT_FIELDS:
+        assert (sc[k][alive] == so[k][alive]).all(), k
+    for k in STATE_FLOAT_FIELDS:
+        ref = so[k][alive]
+        np.testing.assert_allclose(sc[k][alive], ref, rtol=tol["rtol_state"], atol=tol["rtol_state"] * (np.abs(ref).max() + 1e-6),
+                                   err_msg=k)
+
+
+def test_sharding_invariance_and_rollout_equivalence():
+    """Global env ids key the RNG: two half shards == one full batch, bit for bit; and the fused k-step rollout
+    kernel == k single-step launches, bit for bit."""
+    import torch
+
+    P, cur = config.resolve_config(config.baseline_config("cfg4"), warn_dead=False)
+    n, seed, K = 512, 77, 40
+    full = CudaBatch(P, cur, n, seed=seed)
+    lo = CudaBatch(P, cur, n // 2, seed=seed, env_id_offset=0)
+    hi = CudaBatch(P, cur, n // 2, seed=seed, env_id_offset=n // 2)
+    fused = CudaBatch(P, cur, n, seed=seed)
+    o_full = full.reset()
+    assert (np.concatenate([lo.reset(), hi.reset()]) == o_full).all()
+    assert (fused.reset() == o_full).all()
+    rng = np.random.default_rng(1)
+    acts = rng.uniform(-1, 1, (K, n, 6)).astype(np.float32)
+    rsum = np.zeros(n, np.float64)
+    for k in range(K):
+        of, rf, tef, trf, _, _ = full.step(acts[k])
+        ol, rl, tel, trl, _, _ = lo.step(acts[k][: n // 2])
+        oh, rh, teh, trh, _, _ = hi.step(acts[k][n // 2:])
+        assert (np.concatenate([ol, oh]) == of).all() and (np.concatenate([rl, rh]) == rf).all()
+        assert (np.concatenate([tel, teh]) == tef).all()
+        rsum += rf
+    obs_k, rs, dc = fused.sim.rollout(K, torch.as_tensor(acts).cuda())
+    torch.cuda.synchronize()
+    assert (obs_k.cpu().numpy() == of).all()
+    np.testing.assert_allclose(rs.cpu().numpy(), rsum, rtol=1e-5, atol=1e-3)
+    sa, sb = full.export_state(), fused.export_state()
+    for k in STATE_INT_FIELDS + STATE_FLOAT_FIELDS:
+        assert (sa[k] == sb[k]).all(), k
+
+
+def test_random_policy_rollout_matches_host_actions():
+    """hlynr_rollout(actions=NULL) uses the BLK_ACT draws: same trajectory as stepping with draws.random_actions."""
+    P, cur = config.resolve_config(config.baseline_config("cfg2"), warn_dead=False)
+    n, seed, K = 256, 31, 25
+    a = CudaBatch(P, cur, n, seed=seed)
+    b = CudaBatch(P, cur, n, seed=seed)
+    a.reset(); b.reset()
+    ids = np.arange(n)
+    for k in range(K):
+        oa = a.step(draws.random_actions(seed, ids, 0, k + 1))[0]
+    ob, _, _ = b.sim.rollout(K, None)
+    assert (ob.cpu().numpy() == oa).all()
+
+
+def test_episode_statistics_match_oracle():
+    g = load_golden("cfg4_f32_pursuit_long")
+    P, cur = golden_setup(g)
+    n = g["meta"]["n_envs"]
+    cuda = CudaBatch(P, cur, n, seed=g["meta"]["seed"])
+    orc = oracle.OracleBatch(P, cur, n, seed=g["meta"]["seed"])
+    cuda.reset(); orc.reset()
+    for t in range(g["obs"].shape[0]):
+        cuda.step(g["actions"][t]); orc.step(g["actions"][t])
+    sc, so = cuda.stats(), orc.stats()
+    for k in ("episodes", "successes", "hit_target", "interceptor_crash", "fuel_out", "missile_ground", "worsening",
+              "timeouts", "env_steps", "onboard_locks", "length_sum"):
+        assert sc[k] == so[k], (k, sc[k], so[k])
+    for k in ("return_sum", "min_distance_sum", "final_distance_sum"):
+        np.testing.assert_allclose(sc[k], so[k], rtol=1e-3)
+    assert sc["episodes"] == int((g["terminated"] | g["truncated"]).sum())
+
+
+def test_full_size_invariants_1m_envs():
+    """BASELINE cfg4 size (2^20 envs): size-independent properties."""
+    import torch
+
+    n = 1 << 20
+    P, cur = config.resolve_config(config.baseline_config("cfg4"), warn_dead=False)
+    sim = CudaBatch(P, cur, n, seed=9).sim
+    obs = sim.reset()
+    assert torch.isfinite(obs).all() and obs.min() >= -2.0 and obs.max() <= 1.0
+    assert (obs[:, 12] == 1.0).all()  # full fuel
+    obs2, rsum, dcount = sim.rollout(64, None)
+    torch.cuda.synchronize()
+    assert torch.isfinite(obs2).all() and obs2.min() >= -2.0 and obs2.max() <= 1.0
+    assert torch.isfinite(rsum).all()
+    st = sim.export_state(0, 4096)
+    q = st["quat"]
+    np.testing.assert_allclose((q * q).sum(axis=1), 1.0, atol=1e-5)
+    assert (st["steps"] == 64).all() and (st["episode"] == 0).all()
+    assert (st["fuel"] <= 100.0).all() and (st["fuel"] > 90.0).all()
+    s = sim.stats()
+    assert s["env_steps"] == 64 * n
+    # a reset with an all-zero mask changes nothing
+    small = CudaBatch(P, cur, 4096, seed=9).sim
+    first = small.reset().cpu().clone()
+    again = small.reset(torch.zeros(4096, dtype=torch.uint8)).cpu()
+    assert (again == first).all()
+    assert (small.export_state()["episode"] == 0).all()
