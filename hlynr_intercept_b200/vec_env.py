@@ -1,0 +1,254 @@
+"""HlynrVecEnv: the GPU simulator behind the Stable-Baselines3 `VecEnv` contract the reference uses.
+
+Boundary: the reference builds `DummyVecEnv([lambda: Monitor(InterceptEnvironment(cfg))] * n)`
+(rl_system/scripts/train_flat_ppo.py:344-371, inference.py:413) or `SubprocVecEnv` (scripts/train_hrl_pretrain.py:358)
+and drives it through reset / step_async / step_wait / env_method / get_attr.  This class provides exactly that
+surface over `hlynr_step_host` (numpy in, numpy out, pinned staging inside the C library), with the SB3
+auto-reset semantics: on done the returned observation is the reset observation and
+infos[i] = {..., 'terminal_observation', 'TimeLimit.truncated', 'episode': {'r','l','t'}}.
+
+If stable_baselines3 / gymnasium are importable the class subclasses the real `VecEnv` and uses real
+`spaces.Box`; otherwise it is duck-typed (neither package exists in the build image).
+"""
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _lib, abi
+from .sim import HlynrSim
+
+try:  # pragma: no cover - not installed in the build image
+    from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase
+    from gymnasium import spaces as _spaces
+
+    _HAVE_SB3 = True
+except Exception:  # duck-typed stand-ins
+    _HAVE_SB3 = False
+
+    class _VecEnvBase:  # minimal mirror of stable_baselines3.common.vec_env.VecEnv
+        def __init__(self, num_envs, observation_space, action_space):
+            self.num_envs = num_envs
+            self.observation_space = observation_space
+            self.action_space = action_space
+            self.reset_infos = [{} for _ in range(num_envs)]
+            self.render_mode = None
+            self._seeds = [None] * num_envs
+            self._options = [{} for _ in range(num_envs)]
+
+        def step(self, actions):
+            self.step_async(actions)
+            return self.step_wait()
+
+        @property
+        def unwrapped(self):
+            return self
+
+    class _Box:
+        def __init__(self, low, high, shape, dtype):
+            self.low = np.full(shape, low, dtype=dtype)
+            self.high = np.full(shape, high, dtype=dtype)
+            self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+
+        def sample(self):
+            return np.random.uniform(self.low, self.high).astype(self.dtype)
+
+        def contains(self, x):
+            return np.asarray(x).shape == self.shape
+
+    class _spaces:  # noqa: N801
+        Box = _Box
+
+
+class _ObservationGeneratorView:
+    """What `get_attr('observation_generator')[0]` exposes to the reference's callbacks
+    (scripts/train_flat_ppo.py:221-232)."""
+
+    def __init__(self, venv):
+        self._v = venv
+
+    @property
+    def radar_beam_width(self):
+        return self._v.sim.curriculum.beam_width
+
+    @property
+    def onboard_detection_reliability(self):
+        return self._v.sim.curriculum.onboard_reliability
+
+    @property
+    def ground_detection_reliability(self):
+        return self._v.sim.curriculum.ground_reliability
+
+    @property
+    def measurement_noise_level(self):
+        return self._v.sim.curriculum.noise_level
+
+
+class HlynrVecEnv(_VecEnvBase):
+    def __init__(self, env_cfg=None, n_envs=1, device=0, seed=1234, env_id_offset=0, precision="fp32", warn_dead=True,
+                 lazy_infos=None, copy_outputs=None):
+        self.sim = HlynrSim(env_cfg, n_envs=n_envs, device=device, seed=seed, env_id_offset=env_id_offset,
+                            precision=precision, warn_dead=warn_dead)
+        self.config = dict(env_cfg or {})
+        n = self.sim.n
+        obs_space = _spaces.Box(low=-2.0, high=1.0, shape=(26,), dtype=np.float32)   # environment.py:192-194
+        act_space = _spaces.Box(low=-1.0, high=1.0, shape=(6,), dtype=np.float32)    # environment.py:195-197
+        super().__init__(n, obs_space, act_space)
+        # many envs: no per-env Python dict churn unless asked for
+        self.lazy_infos = (n > 4096) if lazy_infos is None else bool(lazy_infos)
+        self.copy_outputs = (n <= 65536) if copy_outputs is None else bool(copy_outputs)
+        L = self.sim.L
+        ptrs = [C.c_void_p() for _ in range(5)]
+        _lib.check(L.hlynr_pinned_buffers(self.sim.h, *[C.byref(p) for p in ptrs]))
+
+        def view(p, shape, ctype, dtype):
+            cnt = int(np.prod(shape))
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(cnt,)).view(dtype).reshape(shape)
+
+        self._act = view(ptrs[0], (n, 6), C.c_float, np.float32)
+        self._obs = view(ptrs[1], (n, 26), C.c_float, np.float32)
+        self._rew = view(ptrs[2], (n,), C.c_float, np.float32)
+        self._term = view(ptrs[3], (n,), C.c_uint8, np.uint8)
+        self._trunc = view(ptrs[4], (n,), C.c_uint8, np.uint8)
+        self._tobs = np.zeros((n, 26), np.float32)
+        self._info = {nm: np.zeros((n,) + shp, dtype=dt) for nm, dt, shp in abi.INFO_FIELDS}
+        self._info_struct = abi.HlynrInfoSoA(**{nm: self._info[nm].ctypes.data for nm, _, _ in abi.INFO_FIELDS})
+        self._t_start = time.time()
+        self._shared_info = {}
+        self._pending = None
+        self.training_step_count = 0
+        self.observation_generator = _ObservationGeneratorView(self)
+
+    # ---- VecEnv API -----------------------------------------------------------------------------------
+    def reset(self):
+        _lib.check(self.sim.L.hlynr_reset_host(self.sim.h, None, self._obs.ctypes.data_as(C.c_void_p)))
+        self.reset_infos = [{} for _ in range(self.num_envs)] if not self.lazy_infos else [self._shared_info] * self.num_envs
+        return self._obs.copy() if self.copy_outputs else self._obs
+
+    def step_async(self, actions):
+        a = np.asarray(actions, dtype=np.float32)  # other callers pass float64 zeros (helpers/check_missile_trajectory.py:58)
+        if a.shape != (self.num_envs, 6):
+            a = a.reshape(self.num_envs, 6)
+        np.copyto(self._act, a)
+        self._pending = True
+
+    def step_wait(self):
+        assert self._pending, "step_wait() without step_async()"
+        self._pending = None
+        p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+        _lib.check(self.sim.L.hlynr_step_host(self.sim.h, p(self._act), p(self._obs), p(self._rew), p(self._term),
+                                              p(self._trunc), p(self._tobs), 1))
+        dones = (self._term | self._trunc).astype(bool)
+        infos = self._build_infos(dones)
+        if self.copy_outputs:
+            return self._obs.copy(), self._rew.copy(), dones, infos
+        return self._obs, self._rew, dones, infos
+
+    def _build_infos(self, dones):
+        n = self.num_envs
+        idx_done = np.nonzero(dones)[0]
+        if self.lazy_infos and idx_done.size == 0:
+            return [self._shared_info] * n
+        _lib.check(self.sim.L.hlynr_info_host(self.sim.h, C.byref(self._info_struct)))
+        f = self._info
+        if self.lazy_infos:
+            infos = [self._shared_info] * n
+            todo = idx_done
+        else:
+            infos = [None] * n
+            todo = range(n)
+        P = self.sim.params
+        for i in todo:
+            fl = int(f["flags"][i])
+            d = {
+                "distance": float(f["distance"][i]), "intercepted": bool(fl & abi.INFO_INTERCEPTED),
+                "missile_hit_target": bool(fl & abi.INFO_HIT_TARGET), "fuel_remaining": float(f["fuel_remaining"][i]),
+                "fuel_used": float(f["fuel_used"][i]), "clamped": bool(fl & abi.INFO_CLAMPED),
+                "missile_pos": f["missile_pos"][i].copy(), "interceptor_pos": f["interceptor_pos"][i].copy(),
+                "steps": int(f["steps"][i]), "radar_detected": bool(fl & abi.INFO_RADAR_DETECTED),
+                "radar_quality": float(P.radar_quality), "ground_radar_detected": bool(fl & abi.INFO_GROUND_DETECTED),
+                "volley_mode": False, "volley_size": 1, "missiles_intercepted": int(bool(fl & abi.INFO_INTERCEPTED)),
+                "missiles_remaining": 0 if fl & abi.INFO_INTERCEPTED else 1,
+                "missile_min_distances": [float(f["distance"][i])], "min_distance": float(f["min_distance"][i]),
+                "crossed_threshold": bool(fl & abi.INFO_CROSSED), "precision_mode": bool(P.precision_mode),
+                "proximity_fuze_enabled": bool(P.fuze_enabled), "proximity_fuze_triggered": bool(fl & abi.INFO_FUZE),
+                "proximity_kill_radius": float(P.kill_radius),
+            }
+            if dones[i]:
+                d["terminal_observation"] = self._tobs[i].copy()
+                d["TimeLimit.truncated"] = bool(self._trunc[i] and not self._term[i])
+                d["episode"] = {"r": round(float(f["episode_return"][i]), 6), "l": int(f["episode_length"][i]),
+                                "t": round(time.time() - self._t_start, 6)}
+            infos[i] = d
+        return infos
+
+    def close(self):
+        self.sim.close()
+
+    def seed(self, seed=None):
+        if seed is not None:
+            self.sim.seed(int(seed))
+        return [seed] * self.num_envs
+
+    def _indices(self, indices):
+        if indices is None:
+            return range(self.num_envs)
+        if isinstance(indices, int):
+            return [indices]
+        return indices
+
+    def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+        idx = self._indices(indices)
+        if method_name == "set_training_step_count":   # scripts/train_flat_ppo.py:173-177, every step
+            self.training_step_count = int(method_args[0]) if method_args else int(method_kwargs["step_count"])
+            self.sim.set_training_step_count(self.training_step_count)
+            return [None for _ in idx]
+        if method_name == "get_current_intercept_radius":  # scripts/train_hrl_pretrain.py:157
+            r = self.sim.get_current_intercept_radius()
+            return [r for _ in idx]
+        if method_name == "seed":                           # scripts/compare_policies.py:150
+            self.seed(method_args[0] if method_args else method_kwargs.get("seed"))
+            return [None for _ in idx]
+        raise AttributeError(f"HlynrVecEnv.env_method: '{method_name}' is not part of the accelerated path")
+
+    def get_attr(self, attr_name, indices=None):
+        idx = list(self._indices(indices))
+        if attr_name == "get_current_intercept_radius":
+            return [self.sim.get_current_intercept_radius for _ in idx]
+        if attr_name == "observation_generator":
+            return [self.observation_generator for _ in idx]
+        if attr_name in ("interceptor_state", "missile_state"):   # visualize.py:149-196
+            out = []
+            for i in idx:
+                s = self.sim.export_state(i, 1)
+                if attr_name == "interceptor_state":
+                    out.append({"position": s["ipos"][0].astype(np.float32), "velocity": s["ivel"][0].astype(np.float32),
+                                "orientation": s["quat"][0].astype(np.float32), "angular_velocity": np.zeros(3, np.float32),
+                                "fuel": float(s["fuel"][0]), "active": True})
+                else:
+                    out.append({"position": s["mpos"][0].astype(np.float32), "velocity": s["mvel"][0].astype(np.float32),
+                                "orientation": np.array([1, 0, 0, 0], np.float32), "angular_velocity": np.zeros(3, np.float32),
+                                "active": True})
+            return out
+        if attr_name in ("training_step_count", "config", "render_mode"):
+            return [getattr(self, attr_name) for _ in idx]
+        if attr_name in ("max_steps", "dt"):
+            return [getattr(self.sim.params, attr_name) for _ in idx]
+        raise AttributeError(f"HlynrVecEnv.get_attr: '{attr_name}' is not exposed")
+
+    def set_attr(self, attr_name, value, indices=None):
+        if attr_name == "training_step_count":
+            self.env_method("set_training_step_count", value)
+            return
+        raise AttributeError(f"HlynrVecEnv.set_attr: '{attr_name}' cannot be set")
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        # Monitor statistics (info['episode']) are produced natively, so evaluate_policy's Monitor check passes
+        name = getattr(wrapper_class, "__name__", "")
+        return [name == "Monitor" for _ in self._indices(indices)]
+
+    def get_images(self):
+        return [None] * self.num_envs
+
+    def render(self, mode=None):
+        return None
