@@ -66,44 +66,48 @@ struct hlynr_sim {
 // ------------------------------------------------------------------------------------------------
 // parameter conversion
 // ------------------------------------------------------------------------------------------------
-static float round_down_f(double x) { float f = (float)x; if ((double)f > x) f = nextafterf(f, -INFINITY); return f; }
-static float round_up_f(double x) { float f = (float)x; if ((double)f < x) f = nextafterf(f, INFINITY); return f; }
-
 template <typename R> static KParams<R> make_kparams(const HlynrParams& p) {
     KParams<R> k;
     memset(&k, 0, sizeof(k));
-    k.dt = (R)p.dt; k.dt_d = p.dt; k.tau = (R)p.thrust_tau;
-    k.isa_expo = (R)(9.80665 / (287.05 * 0.0065));  // physics_models.py:99
+    const R dt_r = (R)p.dt, tau_r = (R)p.thrust_tau;
+    k.dt = dt_r; k.dt_d = p.dt; k.tau = tau_r;
+    k.rc_dt = (R)(1.0 / (double)dt_r);               // RN(1/dt) for the Markstein constant division
+    k.dt_over_tau = (R)((double)dt_r / (double)tau_r);
+    k.isa_expo = (R)(9.80665 / (287.05 * 0.0065));   // physics_models.py:99
     k.gas_R = (R)287.05; k.gamma_R = (R)(1.4 * 287.05);
     k.sub_mach = (R)p.sub_mach; k.sup_mach = (R)p.sup_mach; k.sup_minus_sub = (R)(p.sup_mach - p.sub_mach);
     k.peak_minus1 = (R)(p.peak_mult - 1.0);
     k.cd_base = (R)0.3; k.cd_sup = (R)(0.3 * p.sup_mult); k.sup_mult_d = p.sup_mult;
-    k.missile_ratio = (R)((0.3 * 1.5) / 0.3);       // environment.py:1090,1095
+    k.missile_ratio = (R)((0.3 * 1.5) / 0.3);        // environment.py:1090,1095
     k.rho_weak = (R)1.225; k.cs_weak = (R)343.0; k.half_rho_weak = (R)(0.5 * 1.225); k.nhcr_weak = (R)(-0.5 * 0.3 * 1.225);
-    k.blh = (R)p.blh; k.pf_top = (R)pow(p.blh / 10.0, 0.143);
+    k.blh = (R)p.blh; k.rc_blh = (R)(1.0 / p.blh); k.pf_top = (R)pow(p.blh / 10.0, 0.143);
     k.ti_low = (R)(p.turb_intensity * 2.0); k.ti_high = (R)(p.turb_intensity * 0.3); k.turb = (R)p.turb_intensity;
     k.lp = (R)(1.0 - exp(-p.dt / 0.1));
-    k.gust_scale = (R)p.gust_scale; k.gust_scale_d = p.gust_scale; k.wind_var = (R)p.wind_variability;
+    k.gust_scale_d = p.gust_scale; k.wind_var = (R)p.wind_variability;
     k.kill_radius = (R)p.kill_radius; k.target_x = (R)p.target[0]; k.target_y = (R)p.target[1];
     for (int i = 0; i < 3; ++i) {
         k.base_wind[i] = (R)p.base_wind[i]; k.gpos[i] = (float)p.ground_pos[i]; k.target_d[i] = p.target[i];
         k.m_pos_lo[i] = p.m_pos_lo[i]; k.m_pos_hi[i] = p.m_pos_hi[i]; k.i_pos_lo[i] = p.i_pos_lo[i]; k.i_pos_hi[i] = p.i_pos_hi[i];
         k.i_vel_lo[i] = p.i_vel_lo[i]; k.i_vel_hi[i] = p.i_vel_hi[i];
     }
-    k.radar_range = (float)p.radar_range; k.radar_quality = (float)p.radar_quality; k.radar_quality_d = p.radar_quality;
-    k.max_range_f = (float)p.max_range; k.max_velocity_f = (float)p.max_velocity;
-    k.g_max_range = (float)p.g_max_range; k.g_min_el_up = round_up_f(p.g_min_el); k.g_max_el_dn = round_down_f(p.g_max_el);
-    k.g_base_q = (float)p.g_base_quality; k.max_link = (float)p.max_datalink_range; k.pkt_loss = (float)p.datalink_packet_loss;
+    k.radar_range = (float)p.radar_range; k.rc_radar_range = (float)(1.0 / p.radar_range);
+    k.radar_quality = (float)p.radar_quality; k.radar_quality_d = p.radar_quality;
+    k.rc_max_velocity_f = (float)(1.0 / p.max_velocity);
+    k.g_max_range = (float)p.g_max_range; k.rc_g_max_range = (float)(1.0 / p.g_max_range);
+    // elevation gates asin(s) < min_el / > max_el (core.py:402-406) as thresholds on s itself
+    k.g_sin_min_el = (float)sin(p.g_min_el); k.g_sin_max_el = (float)sin(p.g_max_el);
+    k.g_base_q = (float)p.g_base_quality; k.max_link = (float)p.max_datalink_range; k.rc_max_link = (float)(1.0 / p.max_datalink_range);
+    k.pkt_loss = (float)p.datalink_packet_loss;
     k.dtf = (float)p.dt;
     const double q = 25.0;  // process_noise 5.0 squared (core.py:331-335)
     k.q_pp = (float)(q * pow(p.dt, 4) / 4); k.q_pv = (float)(q * pow(p.dt, 3) / 2); k.q_vv = (float)(q * p.dt * p.dt);
-    k.sigma_r = (R)p.g_sigma_r; k.sigma_v = (R)p.g_sigma_v; k.max_range_w = (R)p.max_range; k.max_velocity_w = (R)p.max_velocity;
+    k.sigma_r = (R)p.g_sigma_r; k.sigma_v = (R)p.g_sigma_v;
+    k.rc_max_range_w = (R)(1.0 / p.max_range); k.rc_max_velocity_w = (R)(1.0 / p.max_velocity);
     k.fus_035q = (float)(0.35 * p.radar_quality);
     k.m_speed_lo = p.m_speed_lo; k.m_speed_hi = p.m_speed_hi; k.m_radius_lo = p.m_radius_lo; k.m_radius_hi = p.m_radius_hi;
     k.m_az_lo = p.m_az_lo; k.m_az_hi = p.m_az_hi; k.m_el_lo = p.m_el_lo; k.m_el_hi = p.m_el_hi;
     k.i_speed_lo = p.i_speed_lo; k.i_speed_hi = p.i_speed_hi;
     for (int i = 0; i < HLYNR_N_DR; ++i) k.dr_var[i] = p.dr_variation[i];
-    k.peak_mult_d = p.peak_mult;
     k.max_steps = p.max_steps; k.isa = p.isa_enabled; k.mach = p.mach_enabled; k.enh_wind = p.enh_wind_enabled;
     k.thrust_dyn = p.thrust_dyn_enabled; k.dr = p.dr_enabled; k.validate = p.validate_enabled; k.evasion = p.evasion_enabled;
     k.onboard_delay = p.onboard_delay; k.ground = p.ground_enabled; k.ground_delay = p.ground_enabled ? p.ground_delay : 0;
@@ -115,10 +119,18 @@ template <typename R> static KParams<R> make_kparams(const HlynrParams& p) {
 }
 template <typename R> static KCurriculum<R> make_kcur(const HlynrCurriculum& c) {
     KCurriculum<R> k;
-    k.intercept_radius = (R)c.intercept_radius; k.intercept_radius_d = c.intercept_radius;
-    k.half_beam_dn = round_down_f((c.beam_width_deg / 2.0) * (M_PI / 180.0));  // np.radians(width / 2.0), core.py:548
+    k.intercept_radius = (R)c.intercept_radius;
+    // beam gate acos(clip(c)) > np.radians(width / 2) (core.py:547-553)  <=>  c < cos(radians(width / 2))
+    const double hb = (c.beam_width_deg / 2.0) * (M_PI / 180.0);
+    k.cos_half_beam = hb >= M_PI ? -2.0f : (float)cos(hb);
     k.onboard_rel = (float)c.onboard_reliability; k.ground_rel = (float)c.ground_reliability;
     return k;
+}
+static RoundKeys make_round_keys(uint64_t seed) {
+    RoundKeys rk;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { rk.k[2 * r] = k0; rk.k[2 * r + 1] = k1; k0 += HLYNR_PHILOX_W0; k1 += HLYNR_PHILOX_W1; }
+    return rk;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -191,9 +203,12 @@ template <typename R> __global__ void import_kernel(KernelArgs<R> A, int64_t fir
     store_env(B, first + j, e);
 }
 
-__global__ void debug_draw_kernel(uint32_t seed_lo, uint32_t seed_hi, int64_t env, uint32_t episode, uint32_t step,
+__global__ void debug_draw_kernel(const __grid_constant__ RoundKeys rk, int64_t env, uint32_t episode, uint32_t step,
                                   uint32_t blk, uint32_t* raw, float* uni, float* nrm) {
-    RngKey k = make_key(seed_lo, seed_hi, env);
+    RngKey k;
+    k.rk = &rk;
+    k.c0 = (uint32_t)((uint64_t)env & 0xffffffffu);
+    k.c3hi = (uint32_t)((uint64_t)env >> 32) << 16;
     uint4 r = draw_raw(k, episode, step, blk);
     raw[0] = r.x; raw[1] = r.y; raw[2] = r.z; raw[3] = r.w;
     uni[0] = u01(r.x); uni[1] = u01(r.y); uni[2] = u01(r.z); uni[3] = u01(r.w);
@@ -224,7 +239,7 @@ template <typename R> static KernelArgs<R> base_args(hlynr_sim* s, const StatePl
     A.n = s->n;
     A.ring_stride = s->n_pad;
     A.env_offset = s->env_offset;
-    A.seed_lo = (uint32_t)s->seed; A.seed_hi = (uint32_t)(s->seed >> 32);
+    A.rk = make_round_keys(s->seed);
     A.tick = s->tick;
     A.io.stats = s->stats;
     A.k_steps = 1;
@@ -339,13 +354,13 @@ int hlynr_step(hlynr_t* s, const float* actions_dev, float* obs_dev, float* rewa
         KernelArgs<float> A = base_args<float>(s, s->pf);
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward = reward_dev; A.io.terminated = terminated_dev;
         A.io.truncated = truncated_dev; A.io.terminal_obs = terminal_obs_dev; A.auto_reset = auto_reset;
-        if (info) A.io.info = *info;
+        if (info) { A.io.info = *info; A.has_info = 1; }
         step_kernel<float, false><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
     } else {
         KernelArgs<double> A = base_args<double>(s, s->pd);
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward = reward_dev; A.io.terminated = terminated_dev;
         A.io.truncated = truncated_dev; A.io.terminal_obs = terminal_obs_dev; A.auto_reset = auto_reset;
-        if (info) A.io.info = *info;
+        if (info) { A.io.info = *info; A.has_info = 1; }
         step_kernel<double, false><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
     }
     CK(cudaGetLastError());
@@ -450,7 +465,7 @@ int hlynr_debug_draws(hlynr_t* s, int64_t env_global_id, uint32_t episode, uint3
     DeviceGuard g(s->device);
     void* buf = nullptr;
     CK(cudaMalloc(&buf, 48));
-    debug_draw_kernel<<<1, 1>>>((uint32_t)s->seed, (uint32_t)(s->seed >> 32), env_global_id, episode, step, block,
+    debug_draw_kernel<<<1, 1>>>(make_round_keys(s->seed), env_global_id, episode, step, block,
                                 (uint32_t*)buf, (float*)((char*)buf + 16), (float*)((char*)buf + 32));
     char host[48];
     cudaError_t e = cudaMemcpy(host, buf, 48, cudaMemcpyDeviceToHost);

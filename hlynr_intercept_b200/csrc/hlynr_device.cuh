@@ -6,17 +6,22 @@
 // (rl_system/core.py:147 SensorDelayBuffer) are ring planes indexed by the GLOBAL tick, so all envs
 // read and write the same ring row in a step: one slot read + one slot write per env, coalesced.
 //
-// The arithmetic restates the reference step (rl_system/environment.py:605-859 and callees) with the
-// same rounding points as NumPy-2 produces (SURVEY 8a precision map).  mul/add/sub/dvd below are the
-// never-contracted IEEE operations; plain operators are used where contraction is harmless.
-//   R = float : "fp32 build" (matches the native reference; float64 islands of the reference are
-//               evaluated in float unless noted)
-//   R = double: "fp64 build" (matches the up-cast float64 reference: integrator, ISA, drag, distance,
-//               reward in double; observation geometry in float as the reference forces it)
+// The arithmetic restates the reference step (rl_system/environment.py:605-859 and callees).
+//   R = float : "fp32 build".  The integration sums, the distance and the reward -- the quantities whose
+//               rounding the parity contract can see (reward = f(prev_distance - distance)) -- use the
+//               never-contracted IEEE operations in the reference's order, so positions, velocities,
+//               distances and rewards stay bit-identical to the native NumPy-2 reference almost always.
+//               Everything that enters those sums far below one ulp (ISA, drag, wind) or only reaches an
+//               observation channel uses cheap forms (MUFU reciprocal / rsqrt / lg2 / ex2, FMA chains).
+//   R = double: "fp64 build" (matches the up-cast float64 reference): integrator, ISA,
+//               drag, distance, reward in exact double operations; observation geometry in float as the
+//               reference forces it.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+
+#include <type_traits>
 
 #include "../../include/hlynr.h"
 #include "../../include/hlynr_rng.h"
@@ -26,7 +31,7 @@ namespace hlynr {
 #define HD __device__ __forceinline__
 
 // ------------------------------------------------------------------------------------------------
-// never-contracted arithmetic
+// never-contracted IEEE arithmetic (parity-critical sums)
 // ------------------------------------------------------------------------------------------------
 HD float mul(float a, float b) { return __fmul_rn(a, b); }
 HD float add(float a, float b) { return __fadd_rn(a, b); }
@@ -53,48 +58,79 @@ template <typename T> HD T norm3(T x, T y, T z) { return sqr(dot3(x, y, z, x, y,
 HD float dot2(float ax, float ay, float bx, float by) { return (float)((double)__fmul_rn(ax, bx) + (double)__fmul_rn(ay, by)); }
 HD double dot2(double ax, double ay, double bx, double by) { return add(mul(ax, bx), mul(ay, by)); }
 
-template <typename T> HD T clip(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
+HD double clip(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+HD float clip(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
-HD void sincos_r(float x, float* s, float* c) { sincosf(x, s, c); }
-HD void sincos_r(double x, double* s, double* c) { sincos(x, s, c); }
-HD float pow_r(float x, float y) { return powf(x, y); }
-HD double pow_r(double x, double y) { return pow(x, y); }
-HD float exp_r(float x) { return expf(x); }
-HD double exp_r(double x) { return exp(x); }
+// ------------------------------------------------------------------------------------------------
+// "near" operations: used where an error of a few float ulps is far below what the parity contract can see.
+// float: MUFU approximations / FMA chains; double (fp64 build): the exact operation.
+// ------------------------------------------------------------------------------------------------
+HD float nrcp(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+HD double nrcp(double a) { return dvd(1.0, a); }
+HD float ndiv(float a, float b) { return a * nrcp(b); }
+HD double ndiv(double a, double b) { return dvd(a, b); }
+HD float nsqrt(float a) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+HD double nsqrt(double a) { return sqr(a); }
+HD float ndot3(float ax, float ay, float az, float bx, float by, float bz) { return fmaf(az, bz, fmaf(ay, by, ax * bx)); }
+HD double ndot3(double ax, double ay, double az, double bx, double by, double bz) { return dot3(ax, ay, az, bx, by, bz); }
+template <typename T> HD T nnorm3(T x, T y, T z) { return nsqrt(ndot3(x, y, z, x, y, z)); }
+HD float npow(float x, float y) { return exp2f(y * __log2f(x)); }
+HD double npow(double x, double y) { return pow(x, y); }
+HD float nexp(float x) { return __expf(x); }
+HD double nexp(double x) { return exp(x); }
+// x / c for a constant c with rc = RN(1/c): Markstein's correction yields the correctly rounded quotient
+// in 3 instructions instead of the ~13 of an IEEE division.
+HD float cdiv(float x, float c, float rc) {
+    float q = __fmul_rn(x, rc);
+    float r = __fmaf_rn(-q, c, x);
+    return __fmaf_rn(r, rc, q);
+}
+HD double cdiv(double x, double c, double) { return __ddiv_rn(x, c); }
 
 template <typename T> struct alignas(sizeof(T) * 4) Vec4 { T x, y, z, w; };
 
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 + the draw contract of include/hlynr_rng.h
 // ------------------------------------------------------------------------------------------------
-struct RngKey { uint32_t k0, k1, c0, c3hi; };  // key = seed halves; c0 = env id low, c3hi = (env id >> 32) << 16
+// The key schedule k_r = k + r*W depends only on the seed: the 10 round keys are computed on the host and
+// read from the kernel-parameter bank; each round is two 32x32->64 multiplies (IMAD.WIDE) and two LOP3.
+struct RoundKeys { uint32_t k[20]; };
+struct RngKey { const RoundKeys* rk; uint32_t c0, c3hi; };  // c0 = env id low word, c3hi = (env id >> 32) << 16
 
-HD uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+HD uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const RoundKeys& rk) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        uint32_t hi0 = __umulhi(HLYNR_PHILOX_M0, c0), lo0 = HLYNR_PHILOX_M0 * c0;
-        uint32_t hi1 = __umulhi(HLYNR_PHILOX_M1, c2), lo1 = HLYNR_PHILOX_M1 * c2;
-        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
-        k0 += HLYNR_PHILOX_W0; k1 += HLYNR_PHILOX_W1;
+        uint64_t p0 = (uint64_t)HLYNR_PHILOX_M0 * c0, p1 = (uint64_t)HLYNR_PHILOX_M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk.k[2 * r], n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk.k[2 * r + 1];
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
     }
     return make_uint4(c0, c1, c2, c3);
 }
 HD uint4 draw_raw(const RngKey& k, uint32_t episode, uint32_t step, uint32_t blk) {
-    return philox4x32_10(k.c0, episode, step, blk | k.c3hi, k.k0, k.k1);
+    return philox4x32_10(k.c0, episode, step, blk | k.c3hi, *k.rk);
 }
 HD float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
 HD float u01_open(uint32_t x) { return (float)((x >> 8) + 1u) * 5.9604644775390625e-8f; }
+// accurate Box-Muller (reset path: domain-randomization draws, gust direction)
 HD void box_muller(uint32_t xa, uint32_t xb, float* z0, float* z1) {
     float r = sqrtf(-2.0f * logf(u01_open(xa)));
     float s, c;
     sincospif(2.0f * u01(xb), &s, &c);
     *z0 = r * c; *z1 = r * s;
 }
+// per-tick draws: the same Box-Muller pairs evaluated with MUFU lg2/sqrt/sin/cos (absolute error ~1e-6 on a
+// standard normal, i.e. ~1e-5 m on the noisiest channel: far below every parity tolerance)
+HD void fast_pair(uint32_t xa, uint32_t xb, float* z0, float* z1) {
+    float r = nsqrt(-1.3862943611198906f * __log2f(u01_open(xa)));  // sqrt(-2 ln u)
+    float t = 2.0f * u01(xb);
+    t = (t < 1.0f ? t : t - 2.0f) * 3.14159265358979f;             // pi*t folded into [-pi, pi)
+    *z0 = r * __cosf(t); *z1 = r * __sinf(t);
+}
 HD void draw_normal3(const RngKey& k, uint32_t episode, uint32_t step, uint32_t blk, float* z0, float* z1, float* z2) {
     uint4 r = draw_raw(k, episode, step, blk);
     float z3;
-    box_muller(r.x, r.y, z0, z1);
-    box_muller(r.z, r.w, z2, &z3);
+    fast_pair(r.x, r.y, z0, z1);
+    fast_pair(r.z, r.w, z2, &z3);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -102,36 +138,34 @@ HD void draw_normal3(const RngKey& k, uint32_t episode, uint32_t step, uint32_t 
 // ------------------------------------------------------------------------------------------------
 template <typename R> struct KParams {
     // ---- S context (integrator dtype) ----
-    R dt, tau, isa_expo, gas_R, gamma_R, sub_mach, sup_mach, sup_minus_sub, peak_minus1, cd_sup, cd_base;
-    R missile_ratio, rho_weak, cs_weak, half_rho_weak, nhcr_weak;  // weak python-float constants (ISA off)
-    R blh, pf_top, ti_low, ti_high, turb, lp, gust_scale, wind_var;
+    R dt, rc_dt, tau, dt_over_tau, isa_expo, gas_R, gamma_R, sub_mach, sup_mach, sup_minus_sub;
+    R peak_minus1, cd_sup, cd_base, missile_ratio, rho_weak, cs_weak, half_rho_weak, nhcr_weak;
+    R blh, rc_blh, pf_top, ti_low, ti_high, turb, lp, wind_var;
     R kill_radius, target_x, target_y;
     R base_wind[3];
     double sup_mult_d;  // DR: base_cd * sup_mult in float64
     double dt_d;        // dt as the Python float it is in the reference
-    double radar_quality_d;
+    double radar_quality_d, gust_scale_d;
     // ---- float context (observation geometry) ----
-    float radar_range, radar_quality, max_range_f, max_velocity_f;
-    float gpos[3], g_max_range, g_min_el_up, g_max_el_dn, g_base_q, max_link, pkt_loss;
+    float radar_range, rc_radar_range, radar_quality, rc_max_velocity_f;
+    float gpos[3], g_max_range, rc_g_max_range, g_sin_min_el, g_sin_max_el, g_base_q, max_link, rc_max_link, pkt_loss;
     float dtf, q_pp, q_pv, q_vv;  // Kalman F/Q entries (float32 matrices, core.py:33-56)
-    // ---- island context (W = R) ----
-    R sigma_r, sigma_v, max_range_w, max_velocity_w;
     float fus_035q;
+    // ---- island context (W = R) ----
+    R sigma_r, sigma_v, rc_max_range_w, rc_max_velocity_w;
     // ---- spawn / DR (double, reset path only) ----
     double m_pos_lo[3], m_pos_hi[3], m_speed_lo, m_speed_hi, m_radius_lo, m_radius_hi, m_az_lo, m_az_hi, m_el_lo, m_el_hi;
     double i_pos_lo[3], i_pos_hi[3], i_vel_lo[3], i_vel_hi[3], i_speed_lo, i_speed_hi, target_d[3];
     double dr_var[HLYNR_N_DR];
-    double peak_mult_d, gust_scale_d;
     // ---- switches ----
     int32_t max_steps, isa, mach, enh_wind, thrust_dyn, dr, validate, evasion, onboard_delay, ground, ground_delay;
     int32_t spherical, toward_missile, obs_mode, precision_mode, fuze, onb_ring_len, gnd_ring_len;
 };
 
 template <typename R> struct KCurriculum {
-    R intercept_radius;        // S context
-    float half_beam_dn;        // float threshold equivalent to the float64 comparison beam > radians(width/2)
+    R intercept_radius;   // S context
+    float cos_half_beam;  // beam gate acos(c) > radians(width/2)  <=>  c < cos(radians(width/2))
     float onboard_rel, ground_rel;
-    double intercept_radius_d;
 };
 
 template <typename R> struct StatePlanes {
@@ -139,8 +173,8 @@ template <typename R> struct StatePlanes {
                      // r5 kf_xv+ep_return, r6 thrust+T0
     float4* f[4];    // f0 quat, f1 wind+Ppp, f2 Ppv,Pvp,Pvv,base_cd, f3 peak (DR only)
     int4* i0;        // steps, worsen, flags (bit0 crossed, bit1 kf_init, bits 8.. onboard delay), episode
-    Vec4<R>* gring;  // [gnd_ring_len][2][N]: {rel.xyz, quality}, {vel.xyz, -}
-    float4* oring;   // [onb_ring_len][N]: {rel.xyz, detected}
+    Vec4<R>* gring;  // [gnd_ring_len][2][stride]: {rel.xyz, quality}, {vel.xyz, -}
+    float4* oring;   // [onb_ring_len][stride]: {rel.xyz, detected}
 };
 
 struct StepIO {
@@ -163,13 +197,14 @@ template <typename R> struct KernelArgs {
     KCurriculum<R> C;
     StatePlanes<R> st;
     StepIO io;
+    RoundKeys rk;
     int64_t n;
     int64_t ring_stride;  // row pitch of the ring planes (n rounded up to 32 envs)
     int64_t env_offset;
-    uint32_t seed_lo, seed_hi;
-    uint32_t tick;       // global tick of this launch (rollout: tick of the first fused step)
+    uint32_t tick;        // global tick of this launch (rollout: tick of the first fused step)
     int32_t auto_reset;
     int32_t k_steps;
+    int32_t has_info;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -234,70 +269,59 @@ template <typename R> HD void isa_props(const KParams<R>& P, R T0, R alt, R* rho
     R T, Pr;
     if (alt <= R(11000.0)) {
         T = sub(T0, mul(R(0.0065), alt));
-        R ratio = dvd(T, T0);
-        Pr = mul(R(101325.0), pow_r(ratio, P.isa_expo));
+        Pr = mul(R(101325.0), npow(ndiv(T, T0), P.isa_expo));
     } else if (alt <= R(20000.0)) {
         T = R(216.65);
-        R ex = sub(alt, R(11000.0));
-        R arg = dvd(mul(R(-9.80665), ex), R(287.05 * 216.65));
-        Pr = mul(R(22632.0), exp_r(arg));
+        Pr = mul(R(22632.0), nexp(ndiv(mul(R(-9.80665), sub(alt, R(11000.0))), R(287.05 * 216.65))));
     } else {
         R ex = sub(alt, R(20000.0));
-        T = mul(R(216.65), exp_r(dvd(-ex, R(10000.0))));
-        Pr = mul(R(5474.889421808574), exp_r(dvd(-ex, R(6000.0))));  // get_pressure(20000.0) in python floats
+        T = mul(R(216.65), nexp(ndiv(-ex, R(10000.0))));
+        Pr = mul(R(5474.889421808574), nexp(ndiv(-ex, R(6000.0))));  // get_pressure(20000.0) in python floats
     }
-    *rho = dvd(Pr, mul(P.gas_R, T));
-    *cs = sqr(mul(P.gamma_R, T));
+    *rho = ndiv(Pr, mul(P.gas_R, T));
+    *cs = nsqrt(mul(P.gamma_R, T));
 }
 
-// MachDragModel.get_drag_force (physics_models.py:236-264) divided by mass -> acceleration.
-// With domain randomization base_cd/peak are np.float64 scalars and the whole product is float64
-// (physics_randomizer.py:273,278); the fp32 build evaluates that island in float.
+// Drag acceleration: MachDragModel.get_drag_force (physics_models.py:236-264) / mass, or the constant-Cd
+// fallback (environment.py:920-921, :1099-1100).  F = -(v/|v|) * (0.5 rho |v|^2 Cd A) * post_scale.
+// With domain randomization base_cd/peak are np.float64 scalars and the product is a float64 island
+// (physics_randomizer.py:273,278); the fp32 build evaluates it in float.
 template <typename R>
-HD void mach_drag_accel(const KParams<R>& P, const Env<R>& e, R vx, R vy, R vz, R vmag, R rho, R cs, bool weak_atm,
-                        R area, R post_scale, R mass, R* ax, R* ay, R* az) {
-    R mach = dvd(vmag, weak_atm ? P.cs_weak : cs);
-    R cd;
-    if (P.dr) {
-        double bc = (double)e.base_cd, pk = (double)e.peak;
-        double m = (double)mach;
-        double c;
-        if (mach < P.sub_mach) c = bc;
-        else if (mach < P.sup_mach) {
-            R frac = dvd(sub(mach, P.sub_mach), P.sup_minus_sub);
-            c = bc * (1.0 + (pk - 1.0) * (double)frac);
-        } else c = bc * P.sup_mult_d;
-        (void)m;
-        cd = (R)c;
-    } else {
-        if (mach < P.sub_mach) cd = P.cd_base;
-        else if (mach < P.sup_mach) {
-            R frac = dvd(sub(mach, P.sub_mach), P.sup_minus_sub);
-            cd = mul(P.cd_base, add(R(1.0), mul(P.peak_minus1, frac)));
-        } else cd = P.cd_sup;
-    }
-    R t = weak_atm ? P.half_rho_weak : mul(R(0.5), rho);
-    t = mul(t, mul(vmag, vmag));
-    t = mul(t, cd);
-    t = mul(t, area);
-    R fx = mul(dvd(-vx, vmag), t), fy = mul(dvd(-vy, vmag), t), fz = mul(dvd(-vz, vmag), t);
-    if (post_scale != R(1.0)) { fx = mul(fx, post_scale); fy = mul(fy, post_scale); fz = mul(fz, post_scale); }
-    *ax = dvd(fx, mass); *ay = dvd(fy, mass); *az = dvd(fz, mass);
-}
-
-template <typename R>
-HD void drag_accel(const KParams<R>& P, const Env<R>& e, R vx, R vy, R vz, R alt, R area, R post_scale, R mass, R* ax,
-                   R* ay, R* az) {
+HD void drag_accel(const KParams<R>& P, const Env<R>& e, R vx, R vy, R vz, R alt, R area, R post_scale, R rc_mass, R mass,
+                   R* ax, R* ay, R* az) {
     R rho = P.rho_weak, cs = P.cs_weak;
     bool weak = true;
     if (P.isa) { isa_props(P, e.T0, alt, &rho, &cs); weak = false; }
-    R vmag = norm3(vx, vy, vz);
+    R vmag = nnorm3(vx, vy, vz);
     if (P.mach && vmag > R(1e-6)) {
-        mach_drag_accel(P, e, vx, vy, vz, vmag, rho, cs, weak, area, post_scale, mass, ax, ay, az);
-    } else {  // environment.py:920-921 / :1099-1100
-        R c = weak ? P.nhcr_weak : mul(R(-0.5 * 0.3), rho);
-        c = mul(c, vmag);
-        *ax = dvd(mul(c, vx), mass); *ay = dvd(mul(c, vy), mass); *az = dvd(mul(c, vz), mass);
+        R mach = ndiv(vmag, cs);
+        R cd;
+        if (P.dr) {
+            double bc = (double)e.base_cd, pk = (double)e.peak, c;
+            if (mach < P.sub_mach) c = bc;
+            else if (mach < P.sup_mach) c = bc * (1.0 + (pk - 1.0) * (double)ndiv(sub(mach, P.sub_mach), P.sup_minus_sub));
+            else c = bc * P.sup_mult_d;
+            cd = (R)c;
+        } else {
+            if (mach < P.sub_mach) cd = P.cd_base;
+            else if (mach < P.sup_mach)
+                cd = mul(P.cd_base, add(R(1.0), mul(P.peak_minus1, ndiv(sub(mach, P.sub_mach), P.sup_minus_sub))));
+            else cd = P.cd_sup;
+        }
+        if constexpr (std::is_same<R, float>::value) {
+            float k = -((weak ? P.half_rho_weak : 0.5f * rho) * vmag * cd * area * post_scale * rc_mass);
+            *ax = k * vx; *ay = k * vy; *az = k * vz;
+        } else {
+            R t = weak ? P.half_rho_weak : mul(R(0.5), rho);
+            t = mul(mul(mul(t, mul(vmag, vmag)), cd), area);
+            R fx = mul(dvd(-vx, vmag), t), fy = mul(dvd(-vy, vmag), t), fz = mul(dvd(-vz, vmag), t);
+            if (post_scale != R(1.0)) { fx = mul(fx, post_scale); fy = mul(fy, post_scale); fz = mul(fz, post_scale); }
+            *ax = dvd(fx, mass); *ay = dvd(fy, mass); *az = dvd(fz, mass);
+        }
+    } else {
+        R c = mul(weak ? P.nhcr_weak : mul(R(-0.5 * 0.3), rho), vmag);
+        if constexpr (std::is_same<R, float>::value) { c *= rc_mass; *ax = c * vx; *ay = c * vy; *az = c * vz; }
+        else { *ax = dvd(mul(c, vx), mass); *ay = dvd(mul(c, vy), mass); *az = dvd(mul(c, vz), mass); }
     }
 }
 
@@ -307,57 +331,53 @@ template <typename R> HD R nan_guard(R a, R lim) {  // np.nan_to_num(nan=0, posi
     return a;
 }
 
-// ------------------------------------------------------------------------------------------------
-// core.py helpers (float32 always)
-// ------------------------------------------------------------------------------------------------
-HD void forward_vector(float w, float x, float y, float z, float* fx, float* fy, float* fz) {  // core.py:1143-1152
-    float a = mul(2.f, add(mul(x, z), mul(w, y)));
-    float b = mul(2.f, sub(mul(y, z), mul(w, x)));
-    float c = sub(1.f, mul(2.f, add(mul(x, x), mul(y, y))));
-    float n = add(norm3(a, b, c), 1e-6f);
-    *fx = dvd(a, n); *fy = dvd(b, n); *fz = dvd(c, n);
-}
-
 struct ObsOut {
     float o[HLYNR_OBS_DIM];
     bool onboard_det, ground_det;
 };
 
+// ------------------------------------------------------------------------------------------------
 // Radar26DObservation.compute_radar_detection + compute (core.py:511-1032), world_frame.
 // `tick` indexes the ring planes; `e.steps` is the call index since reset (0 = the reset call).
+// Geometry is float32 in both builds (the reference casts the state to float32 on entry, core.py:522-529);
+// W = R is the dtype of the reference's float64 islands (ground measurement, Kalman state).
+// ------------------------------------------------------------------------------------------------
 template <typename R>
 HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i, uint32_t tick, ObsOut& out) {
-    typedef R W;  // dtype of the reference's float64 islands in this build
+    typedef R W;
     const KParams<R>& P = A.P;
     const KCurriculum<R>& C = A.C;
     const int64_t n = A.ring_stride;
-    float ipx = (float)e.ipx, ipy = (float)e.ipy, ipz = (float)e.ipz;
-    float ivx = (float)e.ivx, ivy = (float)e.ivy, ivz = (float)e.ivz;
-    float mpx = (float)e.mpx, mpy = (float)e.mpy, mpz = (float)e.mpz;
-    float mvx = (float)e.mvx, mvy = (float)e.mvy, mvz = (float)e.mvz;
-    uint4 ur = draw_raw(key, (uint32_t)e.episode, (uint32_t)e.steps, HLYNR_BLK_UNI);
+    const float ipx = (float)e.ipx, ipy = (float)e.ipy, ipz = (float)e.ipz;
+    const float ivx = (float)e.ivx, ivy = (float)e.ivy, ivz = (float)e.ivz;
+    const float mpx = (float)e.mpx, mpy = (float)e.mpy, mpz = (float)e.mpz;
+    const uint4 ur = draw_raw(key, (uint32_t)e.episode, (uint32_t)e.steps, HLYNR_BLK_UNI);
 
     // === onboard radar, core.py:531-593 ===
-    float rx = sub(mpx, ipx), ry = sub(mpy, ipy), rz = sub(mpz, ipz);
-    float range = norm3(rx, ry, rz);
-    bool onb = !(range > P.radar_range);
+    const float rx = sub(mpx, ipx), ry = sub(mpy, ipy), rz = sub(mpz, ipz);
+    const float range = nnorm3(rx, ry, rz);
+    // forward vector, core.py:1143-1152
     float fx, fy, fz;
-    forward_vector(e.qw, e.qx, e.qy, e.qz, &fx, &fy, &fz);
+    {
+        const float w = e.qw, x = e.qx, y = e.qy, z = e.qz;
+        float a = 2.f * fmaf(x, z, w * y), b = 2.f * fmaf(y, z, -(w * x)), c = 1.f - 2.f * fmaf(x, x, y * y);
+        float inv = nrcp(nnorm3(a, b, c) + 1e-6f);
+        fx = a * inv; fy = b * inv; fz = c * inv;
+    }
+    bool onb = !(range > P.radar_range);
     if (onb) {
-        float rd = add(range, 1e-6f);
-        float cb = clip(dot3(fx, fy, fz, dvd(rx, rd), dvd(ry, rd), dvd(rz, rd)), -1.f, 1.f);
-        if (acosf(cb) > C.half_beam_dn) onb = false;
+        float cb = ndot3(fx, fy, fz, rx, ry, rz) * nrcp(range + 1e-6f);
+        if (cb < C.cos_half_beam) onb = false;  // acos(clip(cb)) > radians(beam/2), core.py:547-553
     }
     if (onb) {
-        float rf = sub(1.f, mul(dvd(range, P.radar_range), 0.5f));
-        float q = mul(mul(P.radar_quality, rf), C.onboard_rel);
+        float q = P.radar_quality * (1.f - range * P.rc_radar_range * 0.5f) * C.onboard_rel;
         if (u01(ur.y) > q) onb = false;
     }
     float orx, ory, orz;
     bool o_det;
-    int odelay = P.dr ? (e.flags >> 8) : P.onboard_delay;
     if (P.onboard_delay > 0) {
         const int L = P.onb_ring_len;
+        const int odelay = e.flags >> 8;
         A.st.oring[(int64_t)(tick % (uint32_t)L) * n + i] = make_float4(rx, ry, rz, onb ? 1.f : 0.f);
         if (e.steps >= odelay) {
             float4 s = A.st.oring[(int64_t)((tick + (uint32_t)(L - odelay)) % (uint32_t)L) * n + i];
@@ -370,22 +390,22 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i,
     W grx = W(0), gry = W(0), grz = W(0), gvx = W(0), gvy = W(0), gvz = W(0);
     float gq = 0.f;
     if (P.ground) {
-        float gx = sub(mpx, P.gpos[0]), gy = sub(mpy, P.gpos[1]), gz = sub(mpz, P.gpos[2]);
-        float gr = norm3(gx, gy, gz);
+        float gx = mpx - P.gpos[0], gy = mpy - P.gpos[1], gz = mpz - P.gpos[2];
+        float gr = nnorm3(gx, gy, gz);
         bool ok = !(gr > P.g_max_range);
-        if (ok && gr > 1e-6f) {
-            float el = asinf(clip(dvd(gz, gr), -1.f, 1.f));
-            if (el < P.g_min_el_up || el > P.g_max_el_dn) ok = false;
+        if (ok && gr > 1e-6f) {  // elevation gates: asin(s) < min  <=>  s < sin(min)
+            float se = gz * nrcp(gr);
+            if (se < P.g_sin_min_el || se > P.g_sin_max_el) ok = false;
         }
         if (ok && mpz < 50.f) ok = false;
         if (ok) {
-            float prob = mul(P.g_base_q, sub(1.f, mul(dvd(gr, P.g_max_range), 0.4f)));
-            prob = mul(prob, C.ground_rel);
+            float prob = P.g_base_q * (1.f - gr * P.rc_g_max_range * 0.4f) * C.ground_rel;
             if (u01(ur.z) > prob) ok = false;
             else {
                 float z0, z1, z2, y0, y1, y2;
                 draw_normal3(key, (uint32_t)e.episode, (uint32_t)e.steps, HLYNR_BLK_GPOS, &z0, &z1, &z2);
                 draw_normal3(key, (uint32_t)e.episode, (uint32_t)e.steps, HLYNR_BLK_GVEL, &y0, &y1, &y2);
+                const float mvx = (float)e.mvx, mvy = (float)e.mvy, mvz = (float)e.mvz;
                 grx = (W)rx + P.sigma_r * (W)z0; gry = (W)ry + P.sigma_r * (W)z1; grz = (W)rz + P.sigma_r * (W)z2;
                 gvx = (W)sub(mvx, ivx) + P.sigma_v * (W)y0;
                 gvy = (W)sub(mvy, ivy) + P.sigma_v * (W)y1;
@@ -413,14 +433,12 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i,
     // === datalink, core.py:440-474 ===
     float link = 0.f;
     if (P.ground) {
-        float lr = norm3(sub(ipx, P.gpos[0]), sub(ipy, P.gpos[1]), sub(ipz, P.gpos[2]));
+        float lr = nnorm3(ipx - P.gpos[0], ipy - P.gpos[1], ipz - P.gpos[2]);
         if (!(lr > P.max_link)) {
-            float r1 = dvd(lr, P.max_link);
-            float rf = sub(1.f, mul(r1, r1));
-            float dv = dvd(norm3(ivx, ivy, ivz), 1000.f);
-            float dop = sub(1.f, dv < 0.3f ? dv : 0.3f);
+            float r1 = lr * P.rc_max_link;
+            float dop = 1.f - fminf(nnorm3(ivx, ivy, ivz) * 1e-3f, 0.3f);
             if (u01(ur.w) < P.pkt_loss) link = 0.f;
-            else link = clip(mul(mul(rf, dop), 0.95f), 0.f, 1.f);
+            else link = clip((1.f - r1 * r1) * dop * 0.95f, 0.f, 1.f);
         }
     }
 
@@ -428,13 +446,12 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i,
     float fus;
     if (!o_det && !dg_det) fus = 0.f;
     else if (o_det && !dg_det) fus = (float)(P.radar_quality_d * 0.5);
-    else if (!o_det) fus = mul(dgq, 0.6f);
+    else if (!o_det) fus = dgq * 0.6f;
     else {
-        W perr = norm3((W)orx - dgx, (W)ory - dgy, (W)orz - dgz);
-        W r = dvd(perr, W(200.0));
-        W agr = sub(W(1.0), r < W(1.0) ? r : W(1.0));
-        float t = add(P.fus_035q, mul(0.5f, dgq));
-        fus = (float)clip(add((W)t, mul(W(0.15), agr)), W(0.0), W(1.0));
+        W perr = nnorm3((W)orx - dgx, (W)ory - dgy, (W)orz - dgz);
+        W r = perr * W(0.005);
+        W agr = W(1.0) - (r < W(1.0) ? r : W(1.0));
+        fus = (float)clip((W)(P.fus_035q + 0.5f * dgq) + W(0.15) * agr, W(0.0), W(1.0));
     }
     out.onboard_det = o_det;
     out.ground_det = dg_det;
@@ -444,88 +461,83 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i,
     if (o_det || dg_det) {
         W zx, zy, zz;
         if (o_det && dg_det) {  // quality-weighted fusion, core.py:734-739
-            float ow = P.radar_quality;
-            float tw = add(ow, dgq);
-            zx = add((W)ipx, dvd(add((W)mul(orx, ow), mul(dgx, (W)dgq)), (W)tw));
-            zy = add((W)ipy, dvd(add((W)mul(ory, ow), mul(dgy, (W)dgq)), (W)tw));
-            zz = add((W)ipz, dvd(add((W)mul(orz, ow), mul(dgz, (W)dgq)), (W)tw));
+            const float ow = P.radar_quality;
+            const W itw = nrcp((W)(ow + dgq));
+            zx = (W)ipx + ((W)(orx * ow) + dgx * (W)dgq) * itw;
+            zy = (W)ipy + ((W)(ory * ow) + dgy * (W)dgq) * itw;
+            zz = (W)ipz + ((W)(orz * ow) + dgz * (W)dgq) * itw;
         } else if (o_det) {
             zx = (W)add(ipx, orx); zy = (W)add(ipy, ory); zz = (W)add(ipz, orz);
         } else {
-            zx = add((W)ipx, dgx); zy = add((W)ipy, dgy); zz = add((W)ipz, dgz);
+            zx = (W)ipx + dgx; zy = (W)ipy + dgy; zz = (W)ipz + dgz;
         }
         if (!kf_init) {  // first measurement only initialises (core.py:93-96), state array is float32
             e.kpx = (W)(float)zx; e.kpy = (W)(float)zy; e.kpz = (W)(float)zz;
             e.kvx = e.kvy = e.kvz = W(0);
             kf_init = true;
         } else {
-            float Si = __fdiv_rn(1.f, add(e.Ppp, 400.f));
-            float Kp = mul(e.Ppp, Si), Kv = mul(e.Pvp, Si);
-            W yx = sub(zx, e.kpx), yy = sub(zy, e.kpy), yz = sub(zz, e.kpz);
-            e.kpx = add(e.kpx, mul((W)Kp, yx)); e.kpy = add(e.kpy, mul((W)Kp, yy)); e.kpz = add(e.kpz, mul((W)Kp, yz));
-            e.kvx = add(e.kvx, mul((W)Kv, yx)); e.kvy = add(e.kvy, mul((W)Kv, yy)); e.kvz = add(e.kvz, mul((W)Kv, yz));
-            float a = sub(1.f, Kp);
-            float npp = mul(a, e.Ppp), npv = mul(a, e.Ppv);
-            float nvp = add(e.Pvp, mul(-Kv, e.Ppp)), nvv = add(e.Pvv, mul(-Kv, e.Ppv));
+            const float Si = nrcp(e.Ppp + 400.f);
+            const float Kp = e.Ppp * Si, Kv = e.Pvp * Si;
+            const W yx = zx - e.kpx, yy = zy - e.kpy, yz = zz - e.kpz;
+            e.kpx += (W)Kp * yx; e.kpy += (W)Kp * yy; e.kpz += (W)Kp * yz;
+            e.kvx += (W)Kv * yx; e.kvy += (W)Kv * yy; e.kvz += (W)Kv * yz;
+            const float a = 1.f - Kp;  // P = (I - K H) P
+            const float npp = a * e.Ppp, npv = a * e.Ppv;
+            const float nvp = fmaf(-Kv, e.Ppp, e.Pvp), nvv = fmaf(-Kv, e.Ppv, e.Pvv);
             e.Ppp = npp; e.Ppv = npv; e.Pvp = nvp; e.Pvv = nvv;
         }
     } else if (kf_init) {  // predict only when no measurement (quirk Q4)
-        W d = (W)P.dtf;
-        e.kpx = add(e.kpx, mul(d, e.kvx)); e.kpy = add(e.kpy, mul(d, e.kvy)); e.kpz = add(e.kpz, mul(d, e.kvz));
-        float fpp = __fmaf_rn(P.dtf, e.Pvp, e.Ppp), fpv = __fmaf_rn(P.dtf, e.Pvv, e.Ppv);  // F @ P (sgemm uses FMA)
-        float cpp = __fmaf_rn(fpv, P.dtf, fpp), cvp = __fmaf_rn(e.Pvv, P.dtf, e.Pvp);      // (F P) @ F^T
-        e.Ppp = add(cpp, P.q_pp); e.Ppv = add(fpv, P.q_pv); e.Pvp = add(cvp, P.q_pv); e.Pvv = add(e.Pvv, P.q_vv);
+        const W d = (W)P.dtf;
+        e.kpx += d * e.kvx; e.kpy += d * e.kvy; e.kpz += d * e.kvz;
+        const float fpp = fmaf(P.dtf, e.Pvp, e.Ppp), fpv = fmaf(P.dtf, e.Pvv, e.Ppv);  // F @ P
+        const float cpp = fmaf(fpv, P.dtf, fpp), cvp = fmaf(e.Pvv, P.dtf, e.Pvp);      // (F P) @ F^T
+        e.Ppp = cpp + P.q_pp; e.Ppv = fpv + P.q_pv; e.Pvp = cvp + P.q_pv; e.Pvv = e.Pvv + P.q_vv;
     }
     e.flags = (e.flags & ~FLAG_KF_INIT) | (kf_init ? FLAG_KF_INIT : 0);
 
     float* o = out.o;
     if (kf_init) {
-        W px = sub(e.kpx, (W)ipx), py = sub(e.kpy, (W)ipy), pz = sub(e.kpz, (W)ipz);
-        W vx = sub(e.kvx, (W)ivx), vy = sub(e.kvy, (W)ivy), vz = sub(e.kvz, (W)ivz);
-        W rr = norm3(px, py, pz);
-        W cl = dvd(-dot3(px, py, pz, vx, vy, vz), add(rr, W(1e-6)));
-        o[0] = (float)clip(dvd(px, P.max_range_w), W(-1), W(1));
-        o[1] = (float)clip(dvd(py, P.max_range_w), W(-1), W(1));
-        o[2] = (float)clip(dvd(pz, P.max_range_w), W(-1), W(1));
-        o[3] = (float)clip(dvd(vx, P.max_velocity_w), W(-1), W(1));
-        o[4] = (float)clip(dvd(vy, P.max_velocity_w), W(-1), W(1));
-        o[5] = (float)clip(dvd(vz, P.max_velocity_w), W(-1), W(1));
-        if (cl > W(0)) o[13] = (float)clip(sub(W(1), dvd(dvd(rr, cl), W(100))), W(-1), W(1));
-        else o[13] = -1.f;
-        float tr = add(add(e.Ppp, e.Ppp), e.Ppp);
-        double tq = clip(1.0 - (double)tr / 10000.0, 0.0, 1.0);
-        if (o_det) tq *= P.radar_quality_d;
-        o[14] = (float)tq;
-        o[15] = (float)clip(dvd(cl, P.max_velocity_w), W(-1), W(1));
-        if (rr > W(1e-6)) o[16] = (float)dot3((W)fx, (W)fy, (W)fz, dvd(px, rr), dvd(py, rr), dvd(pz, rr));
-        else o[16] = 1.f;
+        const W px = e.kpx - (W)ipx, py = e.kpy - (W)ipy, pz = e.kpz - (W)ipz;
+        const W vx = e.kvx - (W)ivx, vy = e.kvy - (W)ivy, vz = e.kvz - (W)ivz;
+        const W rr = nnorm3(px, py, pz);
+        const W cl = -ndot3(px, py, pz, vx, vy, vz) * nrcp(rr + W(1e-6));
+        o[0] = (float)clip(px * P.rc_max_range_w, W(-1), W(1));
+        o[1] = (float)clip(py * P.rc_max_range_w, W(-1), W(1));
+        o[2] = (float)clip(pz * P.rc_max_range_w, W(-1), W(1));
+        o[3] = (float)clip(vx * P.rc_max_velocity_w, W(-1), W(1));
+        o[4] = (float)clip(vy * P.rc_max_velocity_w, W(-1), W(1));
+        o[5] = (float)clip(vz * P.rc_max_velocity_w, W(-1), W(1));
+        o[13] = cl > W(0) ? (float)clip(W(1) - rr * nrcp(cl) * W(0.01), W(-1), W(1)) : -1.f;
+        float tq = clip(1.f - (e.Ppp * 3.f) * 1e-4f, 0.f, 1.f);
+        if (o_det) tq *= P.radar_quality;
+        o[14] = tq;
+        o[15] = (float)clip(cl * P.rc_max_velocity_w, W(-1), W(1));
+        o[16] = rr > W(1e-6) ? (float)(ndot3((W)fx, (W)fy, (W)fz, px, py, pz) * nrcp(rr)) : 1.f;
     } else {
         o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = -2.f;
         o[13] = -1.f; o[14] = 0.f; o[15] = 0.f; o[16] = 0.f;
     }
-    o[6] = clip(dvd(ivx, P.max_velocity_f), -1.f, 1.f);
-    o[7] = clip(dvd(ivy, P.max_velocity_f), -1.f, 1.f);
-    o[8] = clip(dvd(ivz, P.max_velocity_f), -1.f, 1.f);
-    {   // quaternion_to_euler, core.py:1103-1121 (float32) divided by pi
-        float w = e.qw, x = e.qx, y = e.qy, z = e.qz;
-        float sinr = mul(2.f, add(mul(w, x), mul(y, z)));
-        float cosr = sub(1.f, mul(2.f, add(mul(x, x), mul(y, y))));
-        float sinp = mul(2.f, sub(mul(w, y), mul(z, x)));
-        float siny = mul(2.f, add(mul(w, z), mul(x, y)));
-        float cosy = sub(1.f, mul(2.f, add(mul(y, y), mul(z, z))));
-        const float pif = 3.14159274101257324f;
-        o[9] = dvd(atan2f(sinr, cosr), pif);
-        o[10] = dvd(asinf(clip(sinp, -1.f, 1.f)), pif);
-        o[11] = dvd(atan2f(siny, cosy), pif);
+    o[6] = clip(ivx * P.rc_max_velocity_f, -1.f, 1.f);
+    o[7] = clip(ivy * P.rc_max_velocity_f, -1.f, 1.f);
+    o[8] = clip(ivz * P.rc_max_velocity_f, -1.f, 1.f);
+    {   // quaternion_to_euler, core.py:1103-1121 (float32), divided by pi
+        const float w = e.qw, x = e.qx, y = e.qy, z = e.qz;
+        const float sinr = 2.f * fmaf(w, x, y * z), cosr = 1.f - 2.f * fmaf(x, x, y * y);
+        const float sinp = 2.f * fmaf(w, y, -(z * x));
+        const float siny = 2.f * fmaf(w, z, x * y), cosy = 1.f - 2.f * fmaf(y, y, z * z);
+        const float ipi = 0.318309886183790672f;
+        o[9] = atan2f(sinr, cosr) * ipi;
+        o[10] = asinf(clip(sinp, -1.f, 1.f)) * ipi;
+        o[11] = atan2f(siny, cosy) * ipi;
     }
-    o[12] = (float)clip(dvd(e.fuel, R(100.0)), R(0), R(1));
+    o[12] = clip((float)e.fuel * 0.01f, 0.f, 1.f);
     if (dg_det && link > 0.1f) {
-        o[17] = (float)clip(dvd(dgx, P.max_range_w), W(-1), W(1));
-        o[18] = (float)clip(dvd(dgy, P.max_range_w), W(-1), W(1));
-        o[19] = (float)clip(dvd(dgz, P.max_range_w), W(-1), W(1));
-        o[20] = (float)clip(dvd(dvx, P.max_velocity_w), W(-1), W(1));
-        o[21] = (float)clip(dvd(dvy, P.max_velocity_w), W(-1), W(1));
-        o[22] = (float)clip(dvd(dvz, P.max_velocity_w), W(-1), W(1));
+        o[17] = (float)clip(dgx * P.rc_max_range_w, W(-1), W(1));
+        o[18] = (float)clip(dgy * P.rc_max_range_w, W(-1), W(1));
+        o[19] = (float)clip(dgz * P.rc_max_range_w, W(-1), W(1));
+        o[20] = (float)clip(dvx * P.rc_max_velocity_w, W(-1), W(1));
+        o[21] = (float)clip(dvy * P.rc_max_velocity_w, W(-1), W(1));
+        o[22] = (float)clip(dvz * P.rc_max_velocity_w, W(-1), W(1));
         o[23] = dgq;
     } else {
         o[17] = o[18] = o[19] = o[20] = o[21] = o[22] = -2.f;
@@ -538,7 +550,7 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i,
 // ------------------------------------------------------------------------------------------------
 // reset (environment.py:353-603).  Rare path: double arithmetic where the reference has float64.
 // ------------------------------------------------------------------------------------------------
-template <typename R> HD void spawn(const KernelArgs<R>& A, Env<R>& e, const RngKey& key) {
+template <typename R> __device__ __noinline__ void spawn(const KernelArgs<R>& A, Env<R>& e, const RngKey& key) {
     const KParams<R>& P = A.P;
     const uint32_t ep = (uint32_t)e.episode;
     uint4 r0 = draw_raw(key, ep, 0u, HLYNR_BLK_SPAWN0);
@@ -632,6 +644,46 @@ struct TickOut {
     bool terminated, truncated, intercepted, hit, clamped, fuze;
 };
 
+// quaternion integration (environment.py:937-956): q <- normalize(dq(w dt) (x) q), product rounded to float32
+HD void quat_step(Env<float>& e, float wx, float wy, float wz, float dt) {
+    float w2 = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
+    float wn = nsqrt(w2);
+    if (wn * dt > 1e-6f) {
+        float h = 0.5f * wn * dt, h2 = h * h;  // h <= 0.18 rad for |a| <= 1: Taylor to float accuracy
+        float sh = h * fmaf(h2, fmaf(h2, fmaf(h2, -1.98412698e-4f, 8.33333333e-3f), -1.66666667e-1f), 1.f);
+        float ch = fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, 2.48015873e-5f, -1.38888889e-3f), 4.16666667e-2f), -0.5f), 1.f);
+        if (h > 0.5f) { sh = sinf(h); ch = cosf(h); }  // actions outside [-1,1]
+        float k = sh * nrcp(wn);
+        float w1 = ch, x1 = wx * k, y1 = wy * k, z1 = wz * k;
+        float w2q = e.qw, x2 = e.qx, y2 = e.qy, z2 = e.qz;
+        float nw = fmaf(-z1, z2, fmaf(-y1, y2, fmaf(-x1, x2, w1 * w2q)));
+        float nx = fmaf(-z1, y2, fmaf(y1, z2, fmaf(x1, w2q, w1 * x2)));
+        float ny = fmaf(z1, x2, fmaf(y1, w2q, fmaf(-x1, z2, w1 * y2)));
+        float nz = fmaf(z1, w2q, fmaf(-y1, x2, fmaf(x1, y2, w1 * z2)));
+        float inv = rsqrtf(fmaf(nz, nz, fmaf(ny, ny, fmaf(nx, nx, nw * nw))));
+        e.qw = nw * inv; e.qx = nx * inv; e.qy = ny * inv; e.qz = nz * inv;
+    }
+}
+HD void quat_step(Env<double>& e, double wx, double wy, double wz, double dt) {
+    double wn = norm3(wx, wy, wz);
+    double ang = mul(wn, dt);
+    if (ang > 1e-6) {
+        double sh, ch;
+        sincos(mul(ang, 0.5), &sh, &ch);
+        double w1 = ch, x1 = mul(dvd(wx, wn), sh), y1 = mul(dvd(wy, wn), sh), z1 = mul(dvd(wz, wn), sh);
+        double w2 = (double)e.qw, x2 = (double)e.qx, y2 = (double)e.qy, z2 = (double)e.qz;
+        float nw = (float)sub(sub(sub(mul(w1, w2), mul(x1, x2)), mul(y1, y2)), mul(z1, z2));
+        float nx = (float)sub(add(add(mul(w1, x2), mul(x1, w2)), mul(y1, z2)), mul(z1, y2));
+        float ny = (float)add(add(sub(mul(w1, y2), mul(x1, z2)), mul(y1, w2)), mul(z1, x2));
+        float nz = (float)add(sub(add(mul(w1, z2), mul(x1, y2)), mul(y1, x2)), mul(z1, w2));
+        double s2 = (double)__fmul_rn(nw, nw) + (double)__fmul_rn(nx, nx);
+        s2 += (double)__fmul_rn(ny, ny);
+        s2 += (double)__fmul_rn(nz, nz);
+        float nn = __fsqrt_rn((float)s2);
+        e.qw = dvd(nw, nn); e.qx = dvd(nx, nn); e.qy = dvd(ny, nn); e.qz = dvd(nz, nn);
+    }
+}
+
 template <typename R>
 HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const float act[6], TickOut& t) {
     const KParams<R>& P = A.P;
@@ -654,62 +706,52 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
     // ---- _update_interceptor (environment.py:861-963) ----
     {
         R Tx = mul(a0, R(10000.0)), Ty = mul(a1, R(10000.0)), Tz = mul(a2, R(10000.0));
-        R wx = mul(a3, R(20.0)), wy = mul(a4, R(20.0)), wz = mul(a5, R(20.0));
-        if (P.thrust_dyn) {
-            e.thx = add(e.thx, dvd(mul(sub(Tx, e.thx), dt), P.tau));
-            e.thy = add(e.thy, dvd(mul(sub(Ty, e.thy), dt), P.tau));
-            e.thz = add(e.thz, dvd(mul(sub(Tz, e.thz), dt), P.tau));
+        if (P.thrust_dyn) {  // first-order lag, :874-880
+            if constexpr (std::is_same<R, float>::value) {
+                e.thx = fmaf(Tx - e.thx, P.dt_over_tau, e.thx);
+                e.thy = fmaf(Ty - e.thy, P.dt_over_tau, e.thy);
+                e.thz = fmaf(Tz - e.thz, P.dt_over_tau, e.thz);
+            } else {
+                e.thx = add(e.thx, dvd(mul(sub(Tx, e.thx), dt), P.tau));
+                e.thy = add(e.thy, dvd(mul(sub(Ty, e.thy), dt), P.tau));
+                e.thz = add(e.thz, dvd(mul(sub(Tz, e.thz), dt), P.tau));
+            }
             Tx = e.thx; Ty = e.thy; Tz = e.thz;
         }
-        R tm = norm3(Tx, Ty, Tz);
-        R burn = mul(mul(dvd(tm, R(500.0)), R(0.1)), dt);
+        R tm = nnorm3(Tx, Ty, Tz);
+        R burn = mul(mul(cdiv(tm, R(500.0), R(1.0 / 500.0)), R(0.1)), dt);
         e.fuel = sub(e.fuel, burn);
         e.fuel_used = add(e.fuel_used, burn);
         if (e.fuel <= R(0)) { e.fuel = R(0); Tx = Ty = Tz = R(0); e.thx = e.thy = e.thz = R(0); }
-        R tax = dvd(Tx, R(500.0)), tay = dvd(Ty, R(500.0)), taz = dvd(Tz, R(500.0));
+        R tax = cdiv(Tx, R(500.0), R(1.0 / 500.0)), tay = cdiv(Ty, R(500.0), R(1.0 / 500.0)), taz = cdiv(Tz, R(500.0), R(1.0 / 500.0));
         R alt = e.ipz > R(0) ? e.ipz : R(0);
         R vax = sub(e.ivx, (R)e.wx), vay = sub(e.ivy, (R)e.wy), vaz = sub(e.ivz, (R)e.wz);
         R dax, day, daz;
-        drag_accel(P, e, vax, vay, vaz, alt, R(1.0), R(1.0), R(500.0), &dax, &day, &daz);
-        R ax = add(add(tax, dax), R(0)), ay = add(add(tay, day), R(0)), az = add(add(taz, daz), (R)(-9.81f));
+        drag_accel(P, e, vax, vay, vaz, alt, R(1.0), R(1.0), R(1.0 / 500.0), R(500.0), &dax, &day, &daz);
+        R ax = add(tax, dax), ay = add(tay, day), az = add(add(taz, daz), (R)(-9.81f));
         if (P.validate && !(isfinite(ax) && isfinite(ay) && isfinite(az))) {
             ax = nan_guard(ax, R(50)); ay = nan_guard(ay, R(50)); az = nan_guard(az, R(50));
         }
+        // semi-implicit Euler, :933-934 (exact float ops, reference order)
         e.ivx = add(e.ivx, mul(ax, dt)); e.ivy = add(e.ivy, mul(ay, dt)); e.ivz = add(e.ivz, mul(az, dt));
         e.ipx = add(e.ipx, mul(e.ivx, dt)); e.ipy = add(e.ipy, mul(e.ivy, dt)); e.ipz = add(e.ipz, mul(e.ivz, dt));
-        R wn = norm3(wx, wy, wz);
-        R ang = mul(wn, dt);
-        if (ang > R(1e-6)) {  // quaternion integration, :937-956; product rounded to float32 (:1331)
-            R sh, ch;
-            sincos_r(mul(ang, R(0.5)), &sh, &ch);
-            R w1 = ch, x1 = mul(dvd(wx, wn), sh), y1 = mul(dvd(wy, wn), sh), z1 = mul(dvd(wz, wn), sh);
-            R w2 = (R)e.qw, x2 = (R)e.qx, y2 = (R)e.qy, z2 = (R)e.qz;
-            float nw = (float)sub(sub(sub(mul(w1, w2), mul(x1, x2)), mul(y1, y2)), mul(z1, z2));
-            float nx = (float)sub(add(add(mul(w1, x2), mul(x1, w2)), mul(y1, z2)), mul(z1, y2));
-            float ny = (float)add(add(sub(mul(w1, y2), mul(x1, z2)), mul(y1, w2)), mul(z1, x2));
-            float nz = (float)add(sub(add(mul(w1, z2), mul(x1, y2)), mul(y1, x2)), mul(z1, w2));
-            double s2 = (double)__fmul_rn(nw, nw) + (double)__fmul_rn(nx, nx);
-            s2 += (double)__fmul_rn(ny, ny);
-            s2 += (double)__fmul_rn(nz, nz);
-            float nn = __fsqrt_rn((float)s2);
-            e.qw = dvd(nw, nn); e.qx = dvd(nx, nn); e.qy = dvd(ny, nn); e.qz = dvd(nz, nn);
-        }
+        quat_step(e, mul(a3, R(20.0)), mul(a4, R(20.0)), mul(a5, R(20.0)), dt);
     }
     // ---- _update_missile_state (environment.py:1069-1117), same current_wind ----
     {
         R alt = e.mpz > R(0) ? e.mpz : R(0);
         R vax = sub(e.mvx, (R)e.wx), vay = sub(e.mvy, (R)e.wy), vaz = sub(e.mvz, (R)e.wz);
         R dax, day, daz;
-        drag_accel(P, e, vax, vay, vaz, alt, R(2.0), P.missile_ratio, R(1000.0), &dax, &day, &daz);
+        drag_accel(P, e, vax, vay, vaz, alt, R(2.0), P.missile_ratio, R(1.0 / 1000.0), R(1000.0), &dax, &day, &daz);
         double ex = 0.0, ey = 0.0, ez = 0.0;
         if (P.evasion) {
             float z0, z1, z2;
             draw_normal3(key, ep, st, HLYNR_BLK_EVADE, &z0, &z1, &z2);
-            ex = (double)z0 * 2.0; ey = (double)z1 * 2.0; ez = (double)z2 * 2.0;
+            ex = (double)(z0 * 2.0f); ey = (double)(z1 * 2.0f); ez = (double)(z2 * 2.0f);
         }
         // total_accel = drag + gravity + evasion is float64 in the reference even without evasion
         // (evasion = np.zeros(3)), and velocity += total_accel * dt is evaluated in float64: kept as is.
-        double ax = (double)add(dax, R(0)) + ex, ay = (double)add(day, R(0)) + ey, az = (double)add(daz, (R)(-9.81f)) + ez;
+        double ax = (double)dax + ex, ay = (double)day + ey, az = (double)add(daz, (R)(-9.81f)) + ez;
         if (P.validate && !(isfinite(ax) && isfinite(ay) && isfinite(az))) {
             ax = nan_guard(ax, 20.0); ay = nan_guard(ay, 20.0); az = nan_guard(az, 20.0);
         }
@@ -721,25 +763,23 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
     // ---- _update_wind (environment.py:1119-1129): the wind used by the NEXT tick ----
     if (P.enh_wind) {  // EnhancedWindModel.get_wind_vector, physics_models.py:351-387
         R alt = e.ipz > R(0) ? e.ipz : R(0);
-        R pf;
-        if (alt <= R(10.0)) pf = R(1.0);
-        else if (alt <= P.blh) pf = pow_r(dvd(alt, R(10.0)), R(0.143));
-        else pf = P.pf_top;
-        R wvx = mul(P.base_wind[0], pf), wvy = mul(P.base_wind[1], pf), wvz = mul(P.base_wind[2], pf);
-        R ti;
-        if (alt <= R(10.0)) ti = P.ti_low;
-        else if (alt <= P.blh) ti = mul(P.turb, sub(R(1.0), mul(dvd(alt, P.blh), R(0.7))));
-        else ti = P.ti_high;
+        R pf, ti;
+        if (alt <= R(10.0)) { pf = R(1.0); ti = P.ti_low; }
+        else if (alt <= P.blh) { pf = npow(alt * R(0.1), R(0.143)); ti = P.turb * (R(1.0) - alt * P.rc_blh * R(0.7)); }
+        else { pf = P.pf_top; ti = P.ti_high; }
+        R wvx = P.base_wind[0] * pf, wvy = P.base_wind[1] * pf, wvz = P.base_wind[2] * pf;
         if (ti > R(0)) {
-            R scale = mul(ti, norm3(wvx, wvy, wvz));
+            R scale = ti * nnorm3(wvx, wvy, wvz) * P.lp;
             float z0, z1, z2;
             draw_normal3(key, ep, st, HLYNR_BLK_WIND, &z0, &z1, &z2);
-            wvx = wvx + (scale * (R)z0) * P.lp; wvy = wvy + (scale * (R)z1) * P.lp; wvz = wvz + (scale * (R)z2) * P.lp;
+            wvx += scale * (R)z0; wvy += scale * (R)z1; wvz += scale * (R)z2;
         }
         uint4 ur = draw_raw(key, ep, st, HLYNR_BLK_UNI);
         if (u01(ur.x) < 0.001f) {  // gust, :381-385 (0.1 % of ticks)
-            float g0, g1, g2;
-            draw_normal3(key, ep, st, HLYNR_BLK_GUST_DIR, &g0, &g1, &g2);
+            float g0, g1, g2, g3;
+            uint4 gd = draw_raw(key, ep, st, HLYNR_BLK_GUST_DIR);
+            box_muller(gd.x, gd.y, &g0, &g1);
+            box_muller(gd.z, gd.w, &g2, &g3);
             uint4 gm = draw_raw(key, ep, st, HLYNR_BLK_GUST_MAG);
             double nn = sqrt((double)g0 * g0 + (double)g1 * g1 + (double)g2 * g2) + 1e-6;
             double mag = P.gust_scale_d * (double)(-logf(u01_open(gm.x)));
@@ -756,14 +796,14 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
         e.wz = (float)(R(0.95) * (R)e.wz + R(0.05) * (P.base_wind[2] + (R)z2 * P.wind_var));
     }
     // ---- distance / intercept / termination (environment.py:657-814) ----
-    R dist = norm3(sub(e.mpx, e.ipx), sub(e.mpy, e.ipy), sub(e.mpz, e.ipz));
+    const R dist = norm3(sub(e.mpx, e.ipx), sub(e.mpy, e.ipy), sub(e.mpz, e.ipz));  // exact: feeds the reward
     bool intercepted = dist < (P.fuze ? P.kill_radius : A.C.intercept_radius);
     if (dist < e.min_d) e.min_d = dist;
     if (intercepted) e.flags |= FLAG_CROSSED;
     bool fuze = false;
     if (P.fuze && e.min_d < P.kill_radius) { fuze = true; intercepted = true; }
     bool term = false, hit = false;
-    bool missile_down = e.mpz <= R(0);
+    const bool missile_down = e.mpz <= R(0);
     if (P.precision_mode ? missile_down : (!intercepted && missile_down)) {
         R gx = sub(e.mpx, P.target_x), gy = sub(e.mpy, P.target_y);
         hit = sqr(dot2(gx, gy, gx, gy)) < R(500.0);
@@ -781,7 +821,7 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
     t.truncated = e.steps >= P.max_steps;
     t.terminated = term; t.intercepted = intercepted; t.hit = hit; t.fuze = fuze;
     t.distance = (float)dist;
-    // ---- _calculate_reward (environment.py:1131-1320) ----
+    // ---- _calculate_reward (environment.py:1131-1320), exact ops in the reference order ----
     R r;
     const bool crashed = e.ipz < R(0), dry = e.fuel <= R(0);
     if (P.precision_mode) {
@@ -791,9 +831,9 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
                 R cr = A.C.intercept_radius;
                 r = R(3000.0);
                 if (md < cr) r = add(r, mul(dvd(sub(cr, md), cr), R(1000.0)));
-                r = add(r, mul(exp_r(dvd(-md, R(25.0))), R(500.0)));
-                r = add(r, mul(exp_r(dvd(-md, R(10.0))), R(1000.0)));
-                r = add(r, mul(exp_r(dvd(-md, R(3.0))), R(500.0)));
+                r = add(r, mul(nexp(dvd(-md, R(25.0))), R(500.0)));
+                r = add(r, mul(nexp(dvd(-md, R(10.0))), R(1000.0)));
+                r = add(r, mul(nexp(dvd(-md, R(3.0))), R(500.0)));
                 r = add(r, (R)((double)(P.max_steps - e.steps) * 0.3));
             } else {
                 r = mul(-md, R(0.5));
@@ -804,8 +844,8 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
             }
         } else {
             R dl = sub(e.prev_d, dist);
-            r = mul(clip(dvd(dvd(dl, dt), R(100.0)), R(-0.5), R(2.0)), R(0.5));
-            if (dist < R(50.0)) { r = add(r, mul(dl, R(5.0))); r = add(r, exp_r(dvd(-dist, R(10.0)))); }
+            r = mul(clip(cdiv(cdiv(dl, dt, P.rc_dt), R(100.0), R(0.01)), R(-0.5), R(2.0)), R(0.5));
+            if (dist < R(50.0)) { r = add(r, mul(dl, R(5.0))); r = add(r, nexp(dvd(-dist, R(10.0)))); }
             else if (dist < R(150.0)) r = add(r, mul(dl, R(3.0)));
             else if (dist < R(500.0)) r = add(r, mul(dl, R(1.5)));
             else r = add(r, mul(dl, R(0.8)));
@@ -828,7 +868,7 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
         else if (dry) r = sub(r, R(300.0));
     } else {
         R dl = sub(e.prev_d, dist);
-        r = mul(clip(dvd(dvd(dl, dt), R(100.0)), R(-0.5), R(2.0)), R(0.3));
+        r = mul(clip(cdiv(cdiv(dl, dt, P.rc_dt), R(100.0), R(0.01)), R(-0.5), R(2.0)), R(0.3));
         r = add(r, mul(dl, dist < R(200.0) ? R(2.0) : (dist < R(500.0) ? R(1.0) : R(0.5))));
         r = sub(r, R(0.5));
         e.prev_d = dist;
@@ -846,28 +886,19 @@ HD double warp_sum(double v) {
     return v;
 }
 
-template <typename R>
-HD void account_episodes(const KernelArgs<R>& A, bool active, bool done, const Env<R>& e, const TickOut& t) {
-    // called by all lanes of the warp
-    unsigned any = __ballot_sync(0xffffffffu, active && done);
-    if (any == 0u) return;
-    const bool d = active && done;
+__device__ __noinline__ void account_episodes_slow(double* stats, bool d, float ep_ret, int steps, float min_d, float dist,
+                                                   int cause, bool intercepted, bool terminated) {
     double v[12];
     v[0] = d ? 1.0 : 0.0;
-    v[1] = (d && t.intercepted) ? 1.0 : 0.0;
-    v[2] = d ? (double)e.ep_ret : 0.0;
-    v[3] = d ? (double)e.steps : 0.0;
-    v[4] = d ? (double)e.min_d : 0.0;
-    v[5] = d ? (double)t.distance : 0.0;
-    bool te = d && t.terminated && !t.intercepted;
-    bool c_hit = te && t.hit;
-    bool c_crash = te && !c_hit && e.ipz < R(0);
-    bool c_fuel = te && !c_hit && !c_crash && e.fuel <= R(0);
-    bool c_ground = te && !c_hit && !c_crash && !c_fuel && e.mpz <= R(0);
-    bool c_worse = te && !c_hit && !c_crash && !c_fuel && !c_ground;
-    v[6] = c_hit; v[7] = c_crash; v[8] = c_fuel; v[9] = c_ground; v[10] = c_worse;
-    v[11] = (d && !t.terminated) ? 1.0 : 0.0;
-    double* slot = A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS;
+    v[1] = (d && intercepted) ? 1.0 : 0.0;
+    v[2] = d ? (double)ep_ret : 0.0;
+    v[3] = d ? (double)steps : 0.0;
+    v[4] = d ? (double)min_d : 0.0;
+    v[5] = d ? (double)dist : 0.0;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) v[6 + c] = (d && cause == c) ? 1.0 : 0.0;
+    v[11] = (d && !terminated) ? 1.0 : 0.0;
+    double* slot = stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS;
 #pragma unroll
     for (int k = 0; k < 12; ++k) {
         double s = warp_sum(v[k]);
@@ -875,8 +906,25 @@ HD void account_episodes(const KernelArgs<R>& A, bool active, bool done, const E
     }
 }
 
+template <typename R>
+HD void account_episodes(const KernelArgs<R>& A, bool active, bool done, const Env<R>& e, const TickOut& t) {
+    // called by all lanes of the warp; finished episodes are rare (~1 per 1000 ticks per env)
+    if (__ballot_sync(0xffffffffu, active && done) == 0u) return;
+    const bool d = active && done;
+    int cause = -1;  // first matching termination cause, in the reference's reward order
+    if (d && t.terminated && !t.intercepted) {
+        if (t.hit) cause = 0;
+        else if (e.ipz < R(0)) cause = 1;
+        else if (e.fuel <= R(0)) cause = 2;
+        else if (e.mpz <= R(0)) cause = 3;
+        else cause = 4;
+    }
+    account_episodes_slow(A.io.stats, d, (float)e.ep_ret, e.steps, (float)e.min_d, t.distance, cause, t.intercepted,
+                          t.terminated);
+}
+
 // ------------------------------------------------------------------------------------------------
-// coalesced [N,26] / [N,6] transfers through shared memory (one warp-private tile per warp)
+// coalesced [N,26] store through shared memory (one warp-private tile per warp)
 // ------------------------------------------------------------------------------------------------
 #define OBS_PAD 27  // odd row pitch -> conflict-free column writes
 
@@ -886,13 +934,17 @@ HD void store_obs_rows(float* tile, const float o[HLYNR_OBS_DIM], float* dst, in
 #pragma unroll
     for (int k = 0; k < HLYNR_OBS_DIM; ++k) tile[lane * OBS_PAD + k] = o[k];
     __syncwarp();
-    int64_t rows = n - warp_first_env;
-    int valid = rows >= 32 ? 32 * HLYNR_OBS_DIM : (int)rows * HLYNR_OBS_DIM;
+    const int64_t rows = n - warp_first_env;
+    const int valid = rows >= 32 ? 32 * HLYNR_OBS_DIM : (int)rows * HLYNR_OBS_DIM;
     float* base = dst + warp_first_env * HLYNR_OBS_DIM;
+    // linear index idx = 32k + lane -> (row, col) = (idx / 26, idx % 26), advanced incrementally (32 = 26 + 6)
+    int row = lane >= 26 ? 1 : 0, col = lane >= 26 ? (int)lane - 26 : (int)lane;
 #pragma unroll
     for (int k = 0; k < HLYNR_OBS_DIM; ++k) {
-        int idx = k * 32 + (int)lane;
-        if (idx < valid) base[idx] = tile[(idx / HLYNR_OBS_DIM) * OBS_PAD + (idx % HLYNR_OBS_DIM)];
+        const int idx = k * 32 + (int)lane;
+        if (idx < valid) base[idx] = tile[row * OBS_PAD + col];
+        col += 6; row += 1;
+        if (col >= 26) { col -= 26; row += 1; }
     }
     __syncwarp();
 }
@@ -914,9 +966,9 @@ template <typename R> HD void write_info(const KernelArgs<R>& A, int64_t i, cons
     if (f.episode_length) f.episode_length[i] = e.steps;
 }
 
-HD RngKey make_key(uint32_t seed_lo, uint32_t seed_hi, int64_t global_env) {
+template <typename R> HD RngKey make_key(const KernelArgs<R>& A, int64_t global_env) {
     RngKey k;
-    k.k0 = seed_lo; k.k1 = seed_hi;
+    k.rk = &A.rk;
     k.c0 = (uint32_t)((uint64_t)global_env & 0xffffffffu);
     k.c3hi = (uint32_t)((uint64_t)global_env >> 32) << 16;
     return k;
@@ -927,7 +979,7 @@ HD RngKey make_key(uint32_t seed_lo, uint32_t seed_hi, int64_t global_env) {
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-// step(): one tick of every env + SB3 auto-reset.  k_steps > 1 = fused rollout (state stays in registers).
+// step(): one tick of every env + SB3 auto-reset.  kRollout: k fused ticks, state stays in registers.
 template <typename R, bool kRollout>
 __global__ void __launch_bounds__(HLYNR_BLOCK) step_kernel(const __grid_constant__ KernelArgs<R> A) {
     __shared__ float tiles[HLYNR_BLOCK / 32][32 * OBS_PAD];
@@ -938,7 +990,7 @@ __global__ void __launch_bounds__(HLYNR_BLOCK) step_kernel(const __grid_constant
     const int64_t ii = active ? i : A.n - 1;  // inactive lanes shadow the last env and never store
     Env<R> e;
     load_env(A, ii, e);
-    const RngKey key = make_key(A.seed_lo, A.seed_hi, A.env_offset + ii);
+    const RngKey key = make_key(A, A.env_offset + ii);
     const int steps = kRollout ? A.k_steps : 1;
     float rsum = 0.f;
     int dcount = 0, locks = 0;
@@ -960,7 +1012,6 @@ __global__ void __launch_bounds__(HLYNR_BLOCK) step_kernel(const __grid_constant
         TickOut t;
         tick_physics(A, e, key, act, t);
         bool need_reset = false;
-        bool done = false;
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {  // pass 1 = in-kernel auto-reset of finished envs (one copy of observe)
             if (pass == 1) {
@@ -970,13 +1021,13 @@ __global__ void __launch_bounds__(HLYNR_BLOCK) step_kernel(const __grid_constant
             }
             observe(A, e, key, ii, tick, ob);
             if (pass == 0) {
-                done = t.terminated || t.truncated;
+                const bool done = t.terminated || t.truncated;
                 if (ob.onboard_det) locks += 1;
                 if (!kRollout && active) {
                     A.io.reward[i] = t.reward;
                     A.io.terminated[i] = t.terminated ? 1 : 0;
                     A.io.truncated[i] = t.truncated ? 1 : 0;
-                    write_info(A, i, e, t, ob);
+                    if (A.has_info) write_info(A, i, e, t, ob);
                 }
                 rsum += t.reward;
                 account_episodes(A, active, done, e, t);
@@ -1015,28 +1066,21 @@ __global__ void __launch_bounds__(HLYNR_BLOCK) step_kernel(const __grid_constant
 
 // reset(): environment.py:353.  mask == NULL resets every env.
 template <typename R> __global__ void __launch_bounds__(HLYNR_BLOCK) reset_kernel(const __grid_constant__ KernelArgs<R> A) {
-    __shared__ float tiles[HLYNR_BLOCK / 32][32 * OBS_PAD];
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int64_t i = (int64_t)blockIdx.x * HLYNR_BLOCK + threadIdx.x;
-    const bool active = i < A.n;
-    const int64_t ii = active ? i : A.n - 1;
-    const bool doit = active && (A.io.reset_mask == nullptr || A.io.reset_mask[ii] != 0);
-    if (!__any_sync(0xffffffffu, doit)) return;
+    if (i >= A.n) return;
+    if (A.io.reset_mask != nullptr && A.io.reset_mask[i] == 0) return;
     Env<R> e;
-    load_env(A, ii, e);
-    const RngKey key = make_key(A.seed_lo, A.seed_hi, A.env_offset + ii);
+    load_env(A, i, e);
+    const RngKey key = make_key(A, A.env_offset + i);
     ObsOut ob;
-    if (doit) {
-        e.episode += 1;
-        spawn(A, e, key);
-        observe(A, e, key, ii, A.tick, ob);
-        store_env(A, i, e);
-        if (A.io.obs) {
+    e.episode += 1;
+    spawn(A, e, key);
+    observe(A, e, key, i, A.tick, ob);
+    store_env(A, i, e);
+    if (A.io.obs) {
 #pragma unroll
-            for (int k = 0; k < HLYNR_OBS_DIM; ++k) A.io.obs[i * HLYNR_OBS_DIM + k] = ob.o[k];
-        }
+        for (int k = 0; k < HLYNR_OBS_DIM; ++k) A.io.obs[i * HLYNR_OBS_DIM + k] = ob.o[k];
     }
-    (void)tiles; (void)lane; (void)warp;
 }
 
 }  // namespace hlynr
