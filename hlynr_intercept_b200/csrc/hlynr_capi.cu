@@ -52,6 +52,7 @@ struct hlynr_sim {
     uint64_t seed = 0;
     uint32_t tick = 0;
     int64_t launches = 0;
+    double env_steps = 0.0;  // ticks simulated since the statistics were last zeroed (n per launch tick)
     void* state_mem = nullptr;
     size_t state_bytes = 0;
     StatePlanes<float> pf;
@@ -150,12 +151,13 @@ template <typename R> __global__ void init_kernel(StatePlanes<R> s, int64_t n_pa
     (void)has_r6;
 }
 
-__global__ void stats_reduce_kernel(double* stats) {  // [SLOTS+1][WORDS]: last row = sum of the slots
+// [SLOTS+1][WORDS]: last row = sum of the slots; word 12 (ticks simulated) is known on the host
+__global__ void stats_reduce_kernel(double* stats, double env_steps) {
     int k = threadIdx.x;
     if (k >= HLYNR_STATS_WORDS) return;
     double s = 0.0;
     for (int j = 0; j < HLYNR_STAT_SLOTS; ++j) s += stats[j * HLYNR_STATS_WORDS + k];
-    stats[HLYNR_STAT_SLOTS * HLYNR_STATS_WORDS + k] = s;
+    stats[HLYNR_STAT_SLOTS * HLYNR_STATS_WORDS + k] = (k == 12) ? env_steps : s;
 }
 
 template <typename R> __global__ void export_kernel(KernelArgs<R> A, int64_t first, int64_t count, HlynrEnvState* out) {
@@ -241,6 +243,8 @@ template <typename R> static KernelArgs<R> base_args(hlynr_sim* s, const StatePl
     A.env_offset = s->env_offset;
     A.rk = make_round_keys(s->seed);
     A.tick = s->tick;
+    A.g_row = A.P.gnd_ring_len > 0 ? (int32_t)(s->tick % (uint32_t)A.P.gnd_ring_len) : 0;
+    A.o_row = A.P.onb_ring_len > 0 ? (int32_t)(s->tick % (uint32_t)A.P.onb_ring_len) : 0;
     A.io.stats = s->stats;
     A.k_steps = 1;
     return A;
@@ -365,6 +369,7 @@ int hlynr_step(hlynr_t* s, const float* actions_dev, float* obs_dev, float* rewa
     }
     CK(cudaGetLastError());
     s->launches += 1;
+    s->env_steps += (double)s->n;
     return 0;
 }
 
@@ -377,17 +382,22 @@ int hlynr_rollout(hlynr_t* s, int k_steps, const float* actions_dev, float* obs_
     if (s->precision == HLYNR_FP32) {
         KernelArgs<float> A = base_args<float>(s, s->pf);
         A.tick = s->tick + 1; A.k_steps = k_steps; A.auto_reset = 1;
+        A.g_row = A.P.gnd_ring_len > 0 ? (int32_t)(A.tick % (uint32_t)A.P.gnd_ring_len) : 0;
+        A.o_row = A.P.onb_ring_len > 0 ? (int32_t)(A.tick % (uint32_t)A.P.onb_ring_len) : 0;
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward_sum = reward_sum_dev; A.io.done_count = done_count_dev;
         step_kernel<float, true><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
     } else {
         KernelArgs<double> A = base_args<double>(s, s->pd);
         A.tick = s->tick + 1; A.k_steps = k_steps; A.auto_reset = 1;
+        A.g_row = A.P.gnd_ring_len > 0 ? (int32_t)(A.tick % (uint32_t)A.P.gnd_ring_len) : 0;
+        A.o_row = A.P.onb_ring_len > 0 ? (int32_t)(A.tick % (uint32_t)A.P.onb_ring_len) : 0;
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward_sum = reward_sum_dev; A.io.done_count = done_count_dev;
         step_kernel<double, true><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
     }
     CK(cudaGetLastError());
     s->tick += (uint32_t)k_steps;
     s->launches += 1;
+    s->env_steps += (double)s->n * k_steps;
     return 0;
 }
 
@@ -401,7 +411,7 @@ int hlynr_stats_device_ptr(hlynr_t* s, double** out) {
 int hlynr_stats_reduce(hlynr_t* s, void* stream) {
     if (!s) return fail("null handle");
     DeviceGuard g(s->device);
-    stats_reduce_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(s->stats);
+    stats_reduce_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(s->stats, s->env_steps);
     CK(cudaGetLastError());
     s->launches += 1;
     return 0;
@@ -414,7 +424,10 @@ int hlynr_get_stats(hlynr_t* s, HlynrStats* host_out, int zero_after, void* stre
     if (hlynr_stats_reduce(s, stream)) return 1;
     CK(cudaMemcpyAsync(host_out, s->stats + HLYNR_STAT_SLOTS * HLYNR_STATS_WORDS, sizeof(double) * HLYNR_STATS_WORDS,
                        cudaMemcpyDeviceToHost, st));
-    if (zero_after) CK(cudaMemsetAsync(s->stats, 0, sizeof(double) * (HLYNR_STAT_SLOTS + 1) * HLYNR_STATS_WORDS, st));
+    if (zero_after) {
+        CK(cudaMemsetAsync(s->stats, 0, sizeof(double) * (HLYNR_STAT_SLOTS + 1) * HLYNR_STATS_WORDS, st));
+        s->env_steps = 0.0;
+    }
     CK(cudaStreamSynchronize(st));
     return 0;
 }

@@ -202,6 +202,7 @@ template <typename R> struct KernelArgs {
     int64_t ring_stride;  // row pitch of the ring planes (n rounded up to 32 envs)
     int64_t env_offset;
     uint32_t tick;        // global tick of this launch (rollout: tick of the first fused step)
+    int32_t g_row, o_row; // ring rows written at `tick` (tick % ring_len, computed on the host)
     int32_t auto_reset;
     int32_t k_steps;
     int32_t has_info;
@@ -343,7 +344,7 @@ struct ObsOut {
 // W = R is the dtype of the reference's float64 islands (ground measurement, Kalman state).
 // ------------------------------------------------------------------------------------------------
 template <typename R>
-HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i, uint32_t tick, ObsOut& out) {
+HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i, int g_row, int o_row, ObsOut& out) {
     typedef R W;
     const KParams<R>& P = A.P;
     const KCurriculum<R>& C = A.C;
@@ -378,9 +379,11 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i,
     if (P.onboard_delay > 0) {
         const int L = P.onb_ring_len;
         const int odelay = e.flags >> 8;
-        A.st.oring[(int64_t)(tick % (uint32_t)L) * n + i] = make_float4(rx, ry, rz, onb ? 1.f : 0.f);
+        A.st.oring[(int64_t)o_row * n + i] = make_float4(rx, ry, rz, onb ? 1.f : 0.f);
         if (e.steps >= odelay) {
-            float4 s = A.st.oring[(int64_t)((tick + (uint32_t)(L - odelay)) % (uint32_t)L) * n + i];
+            int rrow = o_row - odelay;  // sample written `odelay` ticks ago
+            if (rrow < 0) rrow += L;
+            float4 s = A.st.oring[(int64_t)rrow * n + i];
             orx = s.x; ory = s.y; orz = s.z; o_det = s.w != 0.f;
         } else { orx = ory = orz = 0.f; o_det = false; }
     } else { orx = rx; ory = ry; orz = rz; o_det = onb; }
@@ -419,11 +422,12 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i,
     bool dg_det;
     if (P.ground && P.ground_delay > 0) {  // delayed values, CURRENT flag (core.py:626, quirk Q3)
         const int L = P.gnd_ring_len;
-        Vec4<W>* wr = A.st.gring + (int64_t)(tick % (uint32_t)L) * 2 * n;
+        Vec4<W>* wr = A.st.gring + (int64_t)g_row * 2 * n;
         wr[i] = Vec4<W>{grx, gry, grz, (W)gq};
         wr[n + i] = Vec4<W>{gvx, gvy, gvz, W(0)};
         if (e.steps >= P.ground_delay) {
-            const Vec4<W>* rr = A.st.gring + (int64_t)((tick + 1u) % (uint32_t)L) * 2 * n;
+            const int rrow = g_row + 1 == L ? 0 : g_row + 1;  // oldest slot = written ground_delay ticks ago
+            const Vec4<W>* rr = A.st.gring + (int64_t)rrow * 2 * n;
             Vec4<W> a = rr[i], b = rr[n + i];
             dgx = a.x; dgy = a.y; dgz = a.z; dgq = (float)a.w; dvx = b.x; dvy = b.y; dvz = b.z;
             dg_det = gdet;
@@ -550,9 +554,21 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i,
 // ------------------------------------------------------------------------------------------------
 // reset (environment.py:353-603).  Rare path: double arithmetic where the reference has float64.
 // ------------------------------------------------------------------------------------------------
-template <typename R> __device__ __noinline__ void spawn(const KernelArgs<R>& A, Env<R>& e, const RngKey& key) {
+// The draws and the float64 geometry live in an out-of-line function that RETURNS its results by value, so the
+// (rare) reset path is the only code that touches the stack and the env state never has its address taken.
+struct SpawnOut {
+    float mx, my, mz, mvx, mvy, mvz, ix, iy, iz, vx, vy, vz, qw, qx, qy, qz, d0;
+    float base_cd, peak;
+    double dT0;
+    int odelay;
+};
+
+template <typename R>
+__device__ __noinline__ SpawnOut spawn_values(const KernelArgs<R>& A, uint32_t c0, uint32_t c3hi, uint32_t ep) {
     const KParams<R>& P = A.P;
-    const uint32_t ep = (uint32_t)e.episode;
+    RngKey key;
+    key.rk = &A.rk; key.c0 = c0; key.c3hi = c3hi;
+    SpawnOut o;
     uint4 r0 = draw_raw(key, ep, 0u, HLYNR_BLK_SPAWN0);
     uint4 r1 = draw_raw(key, ep, 0u, HLYNR_BLK_SPAWN1);
     uint4 r2 = draw_raw(key, ep, 0u, HLYNR_BLK_SPAWN2);
@@ -560,14 +576,14 @@ template <typename R> __device__ __noinline__ void spawn(const KernelArgs<R>& A,
     double u10 = u01(r1.x), u11 = u01(r1.y), u12 = u01(r1.z), u13 = u01(r1.w);
     double u20 = u01(r2.x), u21 = u01(r2.y);
     float mx, my, mz;
-    if (P.spherical) {
+    if (P.spherical) {  // environment.py:390-406
         double radius = P.m_radius_lo + (P.m_radius_hi - P.m_radius_lo) * u00;
         double az = (P.m_az_lo + (P.m_az_hi - P.m_az_lo) * u01_) * CUDART_PI / 180.0;
         double el = (P.m_el_lo + (P.m_el_hi - P.m_el_lo) * u02) * CUDART_PI / 180.0;
         mx = (float)(P.target_d[0] + radius * cos(el) * cos(az));
         my = (float)(P.target_d[1] + radius * cos(el) * sin(az));
         mz = (float)(P.target_d[2] + radius * sin(el));
-    } else {
+    } else {            // :409
         mx = (float)(P.m_pos_lo[0] + (P.m_pos_hi[0] - P.m_pos_lo[0]) * u00);
         my = (float)(P.m_pos_lo[1] + (P.m_pos_hi[1] - P.m_pos_lo[1]) * u01_);
         mz = (float)(P.m_pos_lo[2] + (P.m_pos_hi[2] - P.m_pos_lo[2]) * u02);
@@ -575,23 +591,22 @@ template <typename R> __device__ __noinline__ void spawn(const KernelArgs<R>& A,
     float speed = (float)(P.m_speed_lo + (P.m_speed_hi - P.m_speed_lo) * u03);
     float tx = sub((float)P.target_d[0], mx), ty = sub((float)P.target_d[1], my), tz = sub((float)P.target_d[2], mz);
     float td = norm3(tx, ty, tz);
-    float mvx = mul(dvd(tx, td), speed), mvy = mul(dvd(ty, td), speed), mvz = mul(dvd(tz, td), speed);
+    o.mvx = mul(dvd(tx, td), speed); o.mvy = mul(dvd(ty, td), speed); o.mvz = mul(dvd(tz, td), speed);
     float ix = (float)(P.i_pos_lo[0] + (P.i_pos_hi[0] - P.i_pos_lo[0]) * u10);
     float iy = (float)(P.i_pos_lo[1] + (P.i_pos_hi[1] - P.i_pos_lo[1]) * u11);
     float iz = (float)(P.i_pos_lo[2] + (P.i_pos_hi[2] - P.i_pos_lo[2]) * u12);
-    float vx, vy, vz;
     float lx = sub(mx, ix), ly = sub(my, iy), lz = sub(mz, iz);
     float ld = norm3(lx, ly, lz);
     if (P.toward_missile) {
         float sp = (float)(P.i_speed_lo + (P.i_speed_hi - P.i_speed_lo) * u13);
-        vx = mul(dvd(lx, ld), sp); vy = mul(dvd(ly, ld), sp); vz = mul(dvd(lz, ld), sp);
+        o.vx = mul(dvd(lx, ld), sp); o.vy = mul(dvd(ly, ld), sp); o.vz = mul(dvd(lz, ld), sp);
     } else {
-        vx = (float)(P.i_vel_lo[0] + (P.i_vel_hi[0] - P.i_vel_lo[0]) * u13);
-        vy = (float)(P.i_vel_lo[1] + (P.i_vel_hi[1] - P.i_vel_lo[1]) * u20);
-        vz = (float)(P.i_vel_lo[2] + (P.i_vel_hi[2] - P.i_vel_lo[2]) * u21);
+        o.vx = (float)(P.i_vel_lo[0] + (P.i_vel_hi[0] - P.i_vel_lo[0]) * u13);
+        o.vy = (float)(P.i_vel_lo[1] + (P.i_vel_hi[1] - P.i_vel_lo[1]) * u20);
+        o.vz = (float)(P.i_vel_lo[2] + (P.i_vel_hi[2] - P.i_vel_lo[2]) * u21);
     }
     // orientation: rotate +Z onto the line of sight (environment.py:492-530); float64 on float32 inputs
-    float qw = 1.f, qx = 0.f, qy = 0.f, qz = 0.f;
+    o.qw = 1.f; o.qx = 0.f; o.qy = 0.f; o.qz = 0.f;
     if (ld > 1e-6f) {
         double fx = dvd(lx, ld), fy = dvd(ly, ld), fz = dvd(lz, ld);
         double ax = -fy, ay = fx;
@@ -599,16 +614,12 @@ template <typename R> __device__ __noinline__ void spawn(const KernelArgs<R>& A,
         if (al > 1e-6) {
             ax /= al; ay /= al;
             double h = acos(clip(fz, -1.0, 1.0)) / 2.0, sh = sin(h);
-            qw = (float)cos(h); qx = (float)(ax * sh); qy = (float)(ay * sh); qz = (float)(0.0 * sh);
-        } else if (!(fz > 0)) { qw = 0.f; qx = 1.f; }  // anti-aligned (quirk Q9: aligned -> identity)
+            o.qw = (float)cos(h); o.qx = (float)(ax * sh); o.qy = (float)(ay * sh); o.qz = (float)(0.0 * sh);
+        } else if (!(fz > 0)) { o.qw = 0.f; o.qx = 1.f; }  // anti-aligned (quirk Q9: aligned -> identity)
     }
-    e.mpx = mx; e.mpy = my; e.mpz = mz; e.mvx = mvx; e.mvy = mvy; e.mvz = mvz;
-    e.ipx = ix; e.ipy = iy; e.ipz = iz; e.ivx = vx; e.ivy = vy; e.ivz = vz;
-    e.qw = qw; e.qx = qx; e.qy = qy; e.qz = qz;
-    e.fuel = R(100.0); e.fuel_used = R(0);
-    e.wx = (float)P.base_wind[0]; e.wy = (float)P.base_wind[1]; e.wz = (float)P.base_wind[2];
-    e.thx = e.thy = e.thz = R(0);
-    int odelay = P.onboard_delay;
+    o.mx = mx; o.my = my; o.mz = mz; o.ix = ix; o.iy = iy; o.iz = iz;
+    o.d0 = ld;  // |mpos - ipos| on the float32 state (environment.py:579-581)
+    o.dT0 = 0.0; o.base_cd = 0.3f; o.peak = (float)(P.peak_minus1 + R(1.0)); o.odelay = P.onboard_delay;
     if (P.dr) {  // physics_randomizer.py:166-214, 243-297
         float z0, z1, z2, z3, z4, zd;
         uint4 a = draw_raw(key, ep, 0u, HLYNR_BLK_DR0), b = draw_raw(key, ep, 0u, HLYNR_BLK_DR1);
@@ -616,22 +627,35 @@ template <typename R> __device__ __noinline__ void spawn(const KernelArgs<R>& A,
         box_muller(a.z, a.w, &z2, &z3);
         box_muller(b.x, b.y, &z4, &zd);
         (void)z0;
-        if (P.isa) e.T0 = (R)((double)e.T0 + (0.0 + P.dr_var[1] * (double)z1));  // compounding random walk (quirk Q7)
-        if (P.mach) {
-            e.base_cd = (float)(0.3 * clip(1.0 + P.dr_var[2] * (double)z2, 0.1, 3.0));
-            e.peak = (float)(3.0 * clip(1.0 + P.dr_var[3] * (double)z3, 0.1, 3.0));
-        }
-        if (P.onboard_delay > 0) {
-            int nd = (int)(3.0 * clip(1.0 + P.dr_var[4] * (double)z4, 0.1, 3.0));
-            odelay = nd < 1 ? 1 : (nd > 10 ? 10 : nd);
-        }
+        o.dT0 = 0.0 + P.dr_var[1] * (double)z1;
+        o.base_cd = (float)(0.3 * clip(1.0 + P.dr_var[2] * (double)z2, 0.1, 3.0));
+        o.peak = (float)(3.0 * clip(1.0 + P.dr_var[3] * (double)z3, 0.1, 3.0));
+        int nd = (int)(3.0 * clip(1.0 + P.dr_var[4] * (double)z4, 0.1, 3.0));
+        o.odelay = nd < 1 ? 1 : (nd > 10 ? 10 : nd);
+    }
+    return o;
+}
+
+template <typename R> HD void spawn(const KernelArgs<R>& A, Env<R>& e, const RngKey& key) {
+    const KParams<R>& P = A.P;
+    const SpawnOut o = spawn_values(A, key.c0, key.c3hi, (uint32_t)e.episode);
+    e.mpx = o.mx; e.mpy = o.my; e.mpz = o.mz; e.mvx = o.mvx; e.mvy = o.mvy; e.mvz = o.mvz;
+    e.ipx = o.ix; e.ipy = o.iy; e.ipz = o.iz; e.ivx = o.vx; e.ivy = o.vy; e.ivz = o.vz;
+    e.qw = o.qw; e.qx = o.qx; e.qy = o.qy; e.qz = o.qz;
+    e.fuel = R(100.0); e.fuel_used = R(0);
+    e.wx = (float)P.base_wind[0]; e.wy = (float)P.base_wind[1]; e.wz = (float)P.base_wind[2];
+    e.thx = e.thy = e.thz = R(0);
+    int odelay = P.onboard_delay;
+    if (P.dr) {
+        if (P.isa) e.T0 = (R)((double)e.T0 + o.dT0);  // compounding random walk (quirk Q7)
+        if (P.mach) { e.base_cd = o.base_cd; e.peak = o.peak; }
+        if (P.onboard_delay > 0) odelay = o.odelay;
     }
     e.steps = 0; e.worsen = 0;
     e.flags = odelay << 8;  // crossed = false, kalman not initialised
     e.kpx = e.kpy = e.kpz = e.kvx = e.kvy = e.kvz = R(0);
     e.Ppp = 1000.f; e.Ppv = 0.f; e.Pvp = 0.f; e.Pvv = 1000.f;
-    float d0 = norm3(sub(mx, ix), sub(my, iy), sub(mz, iz));  // float32 state at this point in both builds
-    e.prev_d = e.last_d = e.min_d = (R)d0;
+    e.prev_d = e.last_d = e.min_d = (R)o.d0;
     e.ep_ret = R(0);
 }
 
@@ -926,25 +950,28 @@ HD void account_episodes(const KernelArgs<R>& A, bool active, bool done, const E
 // ------------------------------------------------------------------------------------------------
 // coalesced [N,26] store through shared memory (one warp-private tile per warp)
 // ------------------------------------------------------------------------------------------------
-#define OBS_PAD 27  // odd row pitch -> conflict-free column writes
-
-// every lane writes its 26 values into the warp tile, then the warp streams 32*26 floats out linearly
+// Every lane writes its 26 values as 13 float2 (row pitch 26 words: conflict-free for 64-bit stores), then the
+// warp streams the 32*26 floats out linearly as float4 (the tile offset of a linear index is the index itself).
+#define OBS_TILE (32 * HLYNR_OBS_DIM)
 HD void store_obs_rows(float* tile, const float o[HLYNR_OBS_DIM], float* dst, int64_t warp_first_env, int64_t n,
                        unsigned lane) {
+    float2* t2 = reinterpret_cast<float2*>(tile + lane * HLYNR_OBS_DIM);
 #pragma unroll
-    for (int k = 0; k < HLYNR_OBS_DIM; ++k) tile[lane * OBS_PAD + k] = o[k];
+    for (int k = 0; k < HLYNR_OBS_DIM / 2; ++k) t2[k] = make_float2(o[2 * k], o[2 * k + 1]);
     __syncwarp();
     const int64_t rows = n - warp_first_env;
-    const int valid = rows >= 32 ? 32 * HLYNR_OBS_DIM : (int)rows * HLYNR_OBS_DIM;
-    float* base = dst + warp_first_env * HLYNR_OBS_DIM;
-    // linear index idx = 32k + lane -> (row, col) = (idx / 26, idx % 26), advanced incrementally (32 = 26 + 6)
-    int row = lane >= 26 ? 1 : 0, col = lane >= 26 ? (int)lane - 26 : (int)lane;
+    float* base = dst + warp_first_env * HLYNR_OBS_DIM;  // 32 * 104 B per warp: 16-byte aligned
+    if (rows >= 32) {
+        const float4* t4 = reinterpret_cast<const float4*>(tile);
+        float4* b4 = reinterpret_cast<float4*>(base);
 #pragma unroll
-    for (int k = 0; k < HLYNR_OBS_DIM; ++k) {
-        const int idx = k * 32 + (int)lane;
-        if (idx < valid) base[idx] = tile[row * OBS_PAD + col];
-        col += 6; row += 1;
-        if (col >= 26) { col -= 26; row += 1; }
+        for (int k = 0; k < 7; ++k) {
+            const int idx = k * 32 + (int)lane;
+            if (k < 6 || idx < OBS_TILE / 4) b4[idx] = t4[idx];
+        }
+    } else {
+        const int valid = (int)rows * HLYNR_OBS_DIM;
+        for (int idx = (int)lane; idx < valid; idx += 32) base[idx] = tile[idx];
     }
     __syncwarp();
 }
@@ -981,8 +1008,8 @@ template <typename R> HD RngKey make_key(const KernelArgs<R>& A, int64_t global_
 // ------------------------------------------------------------------------------------------------
 // step(): one tick of every env + SB3 auto-reset.  kRollout: k fused ticks, state stays in registers.
 template <typename R, bool kRollout>
-__global__ void __launch_bounds__(HLYNR_BLOCK) step_kernel(const __grid_constant__ KernelArgs<R> A) {
-    __shared__ float tiles[HLYNR_BLOCK / 32][32 * OBS_PAD];
+__global__ void __launch_bounds__(HLYNR_BLOCK, 4) step_kernel(const __grid_constant__ KernelArgs<R> A) {
+    __shared__ __align__(16) float tiles[HLYNR_BLOCK / 32][OBS_TILE];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int64_t i = (int64_t)blockIdx.x * HLYNR_BLOCK + threadIdx.x;
     const int64_t warp_first = i - lane;
@@ -995,9 +1022,9 @@ __global__ void __launch_bounds__(HLYNR_BLOCK) step_kernel(const __grid_constant
     float rsum = 0.f;
     int dcount = 0, locks = 0;
     ObsOut ob;
+    int g_row = A.g_row, o_row = A.o_row;
 #pragma unroll 1
     for (int s = 0; s < steps; ++s) {
-        const uint32_t tick = A.tick + (uint32_t)s;
         float act[6];
         if (kRollout && A.io.actions == nullptr) {  // synthetic random policy, a = 2u-1
             uint4 r0 = draw_raw(key, (uint32_t)e.episode, (uint32_t)e.steps + 1u, HLYNR_BLK_ACT0);
@@ -1019,7 +1046,7 @@ __global__ void __launch_bounds__(HLYNR_BLOCK) step_kernel(const __grid_constant
                 e.episode += 1;
                 spawn(A, e, key);
             }
-            observe(A, e, key, ii, tick, ob);
+            observe(A, e, key, ii, g_row, o_row, ob);
             if (pass == 0) {
                 const bool done = t.terminated || t.truncated;
                 if (ob.onboard_det) locks += 1;
@@ -1041,6 +1068,10 @@ __global__ void __launch_bounds__(HLYNR_BLOCK) step_kernel(const __grid_constant
                 }
             }
         }
+        if (kRollout) {  // next tick's ring rows
+            g_row = g_row + 1 >= A.P.gnd_ring_len ? 0 : g_row + 1;
+            o_row = o_row + 1 >= A.P.onb_ring_len ? 0 : o_row + 1;
+        }
     }
     if (A.io.obs) store_obs_rows(tiles[warp], ob.o, A.io.obs, warp_first, A.n, lane);
     if (kRollout && active) {
@@ -1048,19 +1079,9 @@ __global__ void __launch_bounds__(HLYNR_BLOCK) step_kernel(const __grid_constant
         if (A.io.done_count) A.io.done_count[i] = dcount;
     }
     if (active) store_env(A, i, e);
-    {   // ticks simulated and onboard-lock ticks: one atomic pair per block, spread over the stat slots
-        __shared__ int s_locks[HLYNR_BLOCK / 32], s_act[HLYNR_BLOCK / 32];
-        int wl = __reduce_add_sync(0xffffffffu, active ? locks : 0);
-        int wa = __reduce_add_sync(0xffffffffu, active ? steps : 0);
-        if (lane == 0) { s_locks[warp] = wl; s_act[warp] = wa; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int tl = 0, ta = 0;
-            for (int w = 0; w < HLYNR_BLOCK / 32; ++w) { tl += s_locks[w]; ta += s_act[w]; }
-            double* slot = A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS;
-            atomicAdd(slot + 12, (double)ta);
-            if (tl) atomicAdd(slot + 13, (double)tl);
-        }
+    {   // onboard-lock ticks: one atomic per warp that saw a lock, spread over the stat slots
+        const int wl = __reduce_add_sync(0xffffffffu, active ? locks : 0);
+        if (lane == 0 && wl) atomicAdd(A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS + 13, (double)wl);
     }
 }
 
@@ -1075,7 +1096,7 @@ template <typename R> __global__ void __launch_bounds__(HLYNR_BLOCK) reset_kerne
     ObsOut ob;
     e.episode += 1;
     spawn(A, e, key);
-    observe(A, e, key, i, A.tick, ob);
+    observe(A, e, key, i, A.g_row, A.o_row, ob);
     store_env(A, i, e);
     if (A.io.obs) {
 #pragma unroll
