@@ -52,7 +52,9 @@ struct hlynr_sim {
     uint64_t seed = 0;
     uint32_t tick = 0;
     int64_t launches = 0;
-    double env_steps = 0.0;  // ticks simulated since the statistics were last zeroed (n per launch tick)
+    double env_steps = 0.0;
+    int kernel_variant = 0;  // 0 auto, 1 direct, 2 TMA-prefetched persistent kernel
+    int sm_count = 148;  // ticks simulated since the statistics were last zeroed (n per launch tick)
     void* state_mem = nullptr;
     size_t state_bytes = 0;
     StatePlanes<float> pf;
@@ -252,6 +254,51 @@ template <typename R> static KernelArgs<R> base_args(hlynr_sim* s, const StatePl
 static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
 // ------------------------------------------------------------------------------------------------
+// TMA-prefetched persistent step kernel: host-side plan
+// ------------------------------------------------------------------------------------------------
+static TmaPlan make_tma_plan(const hlynr_sim* s, const KernelArgs<float>& A, const float* actions_dev) {
+    TmaPlan T;
+    memset(&T, 0, sizeof(T));
+    uint32_t off = 0;
+    int c = 0;
+    auto add = [&](const void* base, uint32_t stride, uint32_t* off_out) {
+        T.src[c] = (const char*)base; T.stride[c] = stride; T.smem_off[c] = off;
+        if (off_out) *off_out = off;
+        off += stride * TMA_TILE;
+        off = (off + 127u) & ~127u;
+        return c++;
+    };
+    const KParams<float>& P = A.P;
+    for (int k = 0; k < 6; ++k) add(A.st.r[k], 16, &T.off_r[k]);
+    if (P.thrust_dyn | P.dr) add(A.st.r[6], 16, &T.off_r[6]);
+    for (int k = 0; k < 3; ++k) add(A.st.f[k], 16, &T.off_f[k]);
+    if (P.dr) add(A.st.f[3], 16, &T.off_f[3]);
+    add(A.st.i0, 16, &T.off_i0);
+    if (P.onboard_delay > 0 && !P.dr) {  // the row read this tick: written onboard_delay ticks ago
+        int rrow = A.o_row - P.onboard_delay;
+        if (rrow < 0) rrow += P.onb_ring_len;
+        add(A.st.oring + (int64_t)rrow * A.ring_stride, 16, &T.off_oring);
+    }
+    if (P.ground_delay > 0) {            // oldest ground slot: two planes {rel, quality}, {vel}
+        const int rrow = A.g_row + 1 == P.gnd_ring_len ? 0 : A.g_row + 1;
+        const Vec4<float>* row = A.st.gring + (int64_t)rrow * 2 * A.ring_stride;
+        add(row, 16, &T.off_gring);
+        uint32_t dummy;
+        add(row + A.ring_stride, 16, &dummy);
+    }
+    T.actions_idx = add(actions_dev, 24, &T.off_actions);
+    T.count = c;
+    T.tx_full = 0;
+    for (int k = 0; k < c; ++k) T.tx_full += T.stride[k] * TMA_TILE;
+    T.off_obs_tile = off; off += (HLYNR_BLOCK / 32) * OBS_TILE * sizeof(float);
+    off = (off + 15u) & ~15u;
+    T.off_bar = off; off += 16;
+    (void)s;
+    return T;
+}
+static uint32_t tma_smem_bytes(const TmaPlan& T) { return T.off_bar + 16; }
+
+// ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
 extern "C" {
@@ -294,7 +341,7 @@ int hlynr_create(const HlynrParams* p, int64_t n_envs, int device, uint64_t seed
     if (!s) return fail("hlynr_create: out of host memory");
     s->params = *p;
     s->cur = HlynrCurriculum{200.0, 60.0, 1.0, 1.0};
-    s->n = n_envs; s->n_pad = (n_envs + 31) & ~int64_t(31);
+    s->n = n_envs; s->n_pad = (n_envs + 127) & ~int64_t(127);  // whole 128-env tiles (TMA kernel)
     s->device = device; s->precision = precision; s->seed = seed; s->env_offset = env_id_offset;
     KParams<float> kp = make_kparams<float>(*p);
     const int gl = kp.gnd_ring_len, ol = kp.onb_ring_len;
@@ -308,6 +355,7 @@ int hlynr_create(const HlynrParams* p, int64_t n_envs, int device, uint64_t seed
     cudaMemset(s->state_mem, 0, s->state_bytes);
     cudaMemset(s->stats, 0, sizeof(double) * (HLYNR_STAT_SLOTS + 1) * HLYNR_STATS_WORDS);
     cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+    cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     const int blk = 256;
     if (precision == HLYNR_FP32) {
         carve<float>(s->pf, (char*)s->state_mem, s->n_pad, gl, ol);
@@ -327,6 +375,15 @@ int hlynr_num_envs(const hlynr_t* s, int64_t* out) { if (!s || !out) return fail
 int hlynr_set_curriculum(hlynr_t* s, const HlynrCurriculum* c) { if (!s || !c) return fail("null argument"); s->cur = *c; return 0; }
 int hlynr_get_curriculum(const hlynr_t* s, HlynrCurriculum* c) { if (!s || !c) return fail("null argument"); *c = s->cur; return 0; }
 int hlynr_seed(hlynr_t* s, uint64_t seed) { if (!s) return fail("null handle"); s->seed = seed; return 0; }
+int hlynr_set_option(hlynr_t* s, const char* name, int64_t value) {
+    if (!s || !name) return fail("null argument");
+    if (strcmp(name, "step_kernel_variant") == 0) {
+        if (value < 0 || value > 2) return fail("step_kernel_variant must be 0 (auto), 1 (direct) or 2 (tma)");
+        s->kernel_variant = (int)value;
+        return 0;
+    }
+    return fail("hlynr_set_option: unknown option '%s'", name);
+}
 int hlynr_launch_count(const hlynr_t* s, int64_t* out) { if (!s || !out) return fail("null argument"); *out = s->launches; return 0; }
 
 int hlynr_reset(hlynr_t* s, const uint8_t* mask_dev, float* obs_dev, void* stream) {
@@ -359,7 +416,26 @@ int hlynr_step(hlynr_t* s, const float* actions_dev, float* obs_dev, float* rewa
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward = reward_dev; A.io.terminated = terminated_dev;
         A.io.truncated = truncated_dev; A.io.terminal_obs = terminal_obs_dev; A.auto_reset = auto_reset;
         if (info) { A.io.info = *info; A.has_info = 1; }
-        step_kernel<float, false><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+        // variant: the TMA-prefetched persistent kernel needs 16-byte aligned actions and >= a wave of tiles
+        const int64_t n_tiles = (s->n + TMA_TILE - 1) / TMA_TILE;
+        // measured on B200 (profiles/r01_c): the direct kernel is faster (the step is bound by in-warp dependency
+        // latency, not by load latency), so auto = direct; the TMA variant stays selectable and parity-tested
+        bool use_tma = s->kernel_variant == 2;
+        if (((uintptr_t)actions_dev & 15u) != 0) use_tma = false;
+        if (use_tma) {
+            const TmaPlan T = make_tma_plan(s, A, actions_dev);
+            const uint32_t smem = tma_smem_bytes(T);
+            static thread_local uint32_t smem_set = 0;
+            if (smem > smem_set) {
+                CK(cudaFuncSetAttribute(step_kernel_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                smem_set = smem;
+            }
+            const int64_t max_ctas = (int64_t)s->sm_count * 4;
+            const int grid = (int)(n_tiles < max_ctas ? n_tiles : max_ctas);
+            step_kernel_tma<<<grid, HLYNR_BLOCK, smem, st>>>(A, T);
+        } else {
+            step_kernel<float, false><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+        }
     } else {
         KernelArgs<double> A = base_args<double>(s, s->pd);
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward = reward_dev; A.io.terminated = terminated_dev;

@@ -343,8 +343,12 @@ struct ObsOut {
 // Geometry is float32 in both builds (the reference casts the state to float32 on entry, core.py:522-529);
 // W = R is the dtype of the reference's float64 islands (ground measurement, Kalman state).
 // ------------------------------------------------------------------------------------------------
-template <typename R>
-HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i, int g_row, int o_row, ObsOut& out) {
+// ring samples already staged by the caller (TMA kernel); used instead of the global ring reads when kPre
+template <typename R> struct RingPre { float4 o; Vec4<R> ga, gb; };
+
+template <typename R, bool kPre = false>
+HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i, int g_row, int o_row, const RingPre<R>& pre,
+                ObsOut& out) {
     typedef R W;
     const KParams<R>& P = A.P;
     const KCurriculum<R>& C = A.C;
@@ -381,9 +385,13 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i,
         const int odelay = e.flags >> 8;
         A.st.oring[(int64_t)o_row * n + i] = make_float4(rx, ry, rz, onb ? 1.f : 0.f);
         if (e.steps >= odelay) {
-            int rrow = o_row - odelay;  // sample written `odelay` ticks ago
-            if (rrow < 0) rrow += L;
-            float4 s = A.st.oring[(int64_t)rrow * n + i];
+            float4 s;
+            if (kPre && !P.dr) s = pre.o;
+            else {
+                int rrow = o_row - odelay;  // sample written `odelay` ticks ago
+                if (rrow < 0) rrow += L;
+                s = A.st.oring[(int64_t)rrow * n + i];
+            }
             orx = s.x; ory = s.y; orz = s.z; o_det = s.w != 0.f;
         } else { orx = ory = orz = 0.f; o_det = false; }
     } else { orx = rx; ory = ry; orz = rz; o_det = onb; }
@@ -426,9 +434,13 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i,
         wr[i] = Vec4<W>{grx, gry, grz, (W)gq};
         wr[n + i] = Vec4<W>{gvx, gvy, gvz, W(0)};
         if (e.steps >= P.ground_delay) {
-            const int rrow = g_row + 1 == L ? 0 : g_row + 1;  // oldest slot = written ground_delay ticks ago
-            const Vec4<W>* rr = A.st.gring + (int64_t)rrow * 2 * n;
-            Vec4<W> a = rr[i], b = rr[n + i];
+            Vec4<W> a, b;
+            if (kPre) { a = pre.ga; b = pre.gb; }
+            else {
+                const int rrow = g_row + 1 == L ? 0 : g_row + 1;  // oldest slot = written ground_delay ticks ago
+                const Vec4<W>* rr = A.st.gring + (int64_t)rrow * 2 * n;
+                a = rr[i]; b = rr[n + i];
+            }
             dgx = a.x; dgy = a.y; dgz = a.z; dgq = (float)a.w; dvx = b.x; dvy = b.y; dvz = b.z;
             dg_det = gdet;
         } else { dgx = dgy = dgz = dvx = dvy = dvz = W(0); dgq = 0.f; dg_det = false; }
@@ -1046,7 +1058,7 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, 4) step_kernel(const __grid_const
                 e.episode += 1;
                 spawn(A, e, key);
             }
-            observe(A, e, key, ii, g_row, o_row, ob);
+            observe(A, e, key, ii, g_row, o_row, RingPre<R>{}, ob);
             if (pass == 0) {
                 const bool done = t.terminated || t.truncated;
                 if (ob.onboard_det) locks += 1;
@@ -1085,6 +1097,184 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, 4) step_kernel(const __grid_const
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent step kernel with TMA-prefetched tiles (fp32 build, API mode).
+//
+// The direct kernel above is latency-bound: every warp waits ~1 us for its 11 plane loads before ~1.9 k
+// instructions of arithmetic, with only ~16 warps resident per SM.  Here each CTA owns a 128-env tile buffer in
+// shared memory that one elected thread fills with 1-D bulk copies (cp.async.bulk -> UBLKCP, completion on an
+// mbarrier): 2 KiB per state plane, the ring rows read this tick and the tile's actions.  As soon as every
+// thread has moved its env from the buffer into registers the NEXT tile's copies are issued, so they land
+// while the current tile computes.  Tiles are assigned round-robin to a persistent grid.
+// ------------------------------------------------------------------------------------------------
+#define TMA_TILE HLYNR_BLOCK
+#define TMA_MAX_PLANES 18
+
+struct TmaPlan {              // what one tile transfer consists of (built on the host)
+    const char* src[TMA_MAX_PLANES];   // global base of each source array
+    uint32_t stride[TMA_MAX_PLANES];   // bytes per env in that array (16 for planes, 24 for actions)
+    uint32_t smem_off[TMA_MAX_PLANES]; // byte offset of the copy inside the tile buffer
+    int32_t count;
+    int32_t actions_idx;               // index of the actions copy (skipped for a partial tile), or -1
+    uint32_t off_r[7], off_f[4], off_i0, off_oring, off_gring, off_actions, off_obs_tile, off_bar;
+    uint32_t tx_full;                  // bytes per full tile
+};
+
+HD uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+HD void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+HD void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+HD void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+HD bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+HD void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 26)) __trap();  // never hang the GPU: a lost transfer becomes a launch failure
+}
+
+__device__ __forceinline__ void tma_issue_tile(const TmaPlan& T, uint32_t buf, uint32_t bar, int64_t tile, int rows) {
+    uint32_t tx = 0;
+#pragma unroll 1
+    for (int p = 0; p < T.count; ++p)
+        if (p != T.actions_idx || rows == TMA_TILE) tx += T.stride[p] * TMA_TILE;
+    mbar_expect_tx(bar, tx);
+#pragma unroll 1
+    for (int p = 0; p < T.count; ++p) {
+        if (p == T.actions_idx && rows != TMA_TILE) continue;
+        const uint32_t bytes = T.stride[p] * TMA_TILE;
+        bulk_g2s(buf + T.smem_off[p], T.src[p] + (size_t)tile * bytes, bytes, bar);
+    }
+}
+
+__global__ void __launch_bounds__(HLYNR_BLOCK, 4)
+step_kernel_tma(const __grid_constant__ KernelArgs<float> A, const __grid_constant__ TmaPlan T) {
+    typedef float R;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t buf = smem_u32(smem), bar = buf + T.off_bar;
+    float* tiles = reinterpret_cast<float*>(smem + T.off_obs_tile);
+    const int64_t n_tiles = (A.n + TMA_TILE - 1) / TMA_TILE;
+    int64_t tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int64_t left = A.n - tile * TMA_TILE;
+        tma_issue_tile(T, buf, bar, tile, left >= TMA_TILE ? TMA_TILE : (int)left);
+    }
+    uint32_t parity = 0;
+    int locks = 0;
+#pragma unroll 1
+    for (; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i = tile * TMA_TILE + threadIdx.x;
+        const int64_t warp_first = i - lane;
+        const bool active = i < A.n;
+        const int64_t ii = active ? i : A.n - 1;
+        const int rows_here = (A.n - tile * TMA_TILE) >= TMA_TILE ? TMA_TILE : (int)(A.n - tile * TMA_TILE);
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        // ---- tile buffer -> registers ----
+        Env<R> e;
+        float act[6];
+        RingPre<R> pre;
+        {
+            const unsigned t = threadIdx.x;
+            const float4* pl;
+            float4 v;
+            pl = reinterpret_cast<const float4*>(smem + T.off_r[0]); v = pl[t]; e.ipx = v.x; e.ipy = v.y; e.ipz = v.z; e.fuel = v.w;
+            pl = reinterpret_cast<const float4*>(smem + T.off_r[1]); v = pl[t]; e.ivx = v.x; e.ivy = v.y; e.ivz = v.z; e.fuel_used = v.w;
+            pl = reinterpret_cast<const float4*>(smem + T.off_r[2]); v = pl[t]; e.mpx = v.x; e.mpy = v.y; e.mpz = v.z; e.prev_d = v.w;
+            pl = reinterpret_cast<const float4*>(smem + T.off_r[3]); v = pl[t]; e.mvx = v.x; e.mvy = v.y; e.mvz = v.z; e.last_d = v.w;
+            pl = reinterpret_cast<const float4*>(smem + T.off_r[4]); v = pl[t]; e.kpx = v.x; e.kpy = v.y; e.kpz = v.z; e.min_d = v.w;
+            pl = reinterpret_cast<const float4*>(smem + T.off_r[5]); v = pl[t]; e.kvx = v.x; e.kvy = v.y; e.kvz = v.z; e.ep_ret = v.w;
+            if (A.P.thrust_dyn | A.P.dr) {
+                pl = reinterpret_cast<const float4*>(smem + T.off_r[6]); v = pl[t]; e.thx = v.x; e.thy = v.y; e.thz = v.z; e.T0 = v.w;
+            } else { e.thx = e.thy = e.thz = 0.f; e.T0 = 288.15f; }
+            pl = reinterpret_cast<const float4*>(smem + T.off_f[0]); v = pl[t]; e.qw = v.x; e.qx = v.y; e.qy = v.z; e.qz = v.w;
+            pl = reinterpret_cast<const float4*>(smem + T.off_f[1]); v = pl[t]; e.wx = v.x; e.wy = v.y; e.wz = v.z; e.Ppp = v.w;
+            pl = reinterpret_cast<const float4*>(smem + T.off_f[2]); v = pl[t]; e.Ppv = v.x; e.Pvp = v.y; e.Pvv = v.z; e.base_cd = v.w;
+            if (A.P.dr) { pl = reinterpret_cast<const float4*>(smem + T.off_f[3]); e.peak = pl[t].x; } else e.peak = 0.f;
+            const int4 q = reinterpret_cast<const int4*>(smem + T.off_i0)[t];
+            e.steps = q.x; e.worsen = q.y; e.flags = q.z; e.episode = q.w;
+            pre.o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (A.P.onboard_delay > 0 && !A.P.dr) pre.o = reinterpret_cast<const float4*>(smem + T.off_oring)[t];
+            pre.ga = Vec4<R>{0.f, 0.f, 0.f, 0.f}; pre.gb = pre.ga;
+            if (A.P.ground_delay > 0) {
+                const float4 a = reinterpret_cast<const float4*>(smem + T.off_gring)[t];
+                const float4 b = reinterpret_cast<const float4*>(smem + T.off_gring)[TMA_TILE + t];
+                pre.ga = Vec4<R>{a.x, a.y, a.z, a.w}; pre.gb = Vec4<R>{b.x, b.y, b.z, b.w};
+            }
+            if (rows_here == TMA_TILE) {
+                const float2* ap = reinterpret_cast<const float2*>(smem + T.off_actions) + 3 * t;
+                const float2 p0 = ap[0], p1 = ap[1], p2 = ap[2];
+                act[0] = p0.x; act[1] = p0.y; act[2] = p1.x; act[3] = p1.y; act[4] = p2.x; act[5] = p2.y;
+            } else {
+                const float2* ap = reinterpret_cast<const float2*>(A.io.actions + ii * HLYNR_ACT_DIM);
+                const float2 p0 = __ldg(ap), p1 = __ldg(ap + 1), p2 = __ldg(ap + 2);
+                act[0] = p0.x; act[1] = p0.y; act[2] = p1.x; act[3] = p1.y; act[4] = p2.x; act[5] = p2.y;
+            }
+        }
+        __syncthreads();  // every thread has drained the tile buffer
+        if (threadIdx.x == 0) {
+            const int64_t nt = tile + gridDim.x;
+            if (nt < n_tiles) {
+                const int64_t left = A.n - nt * TMA_TILE;
+                tma_issue_tile(T, buf, bar, nt, left >= TMA_TILE ? TMA_TILE : (int)left);
+            }
+        }
+        // ---- one tick + SB3 auto-reset (same device functions as the direct kernel) ----
+        const RngKey key = make_key(A, A.env_offset + ii);
+        TickOut t;
+        tick_physics(A, e, key, act, t);
+        ObsOut ob;
+        bool need_reset = false;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) {
+                if (!need_reset) break;
+                e.episode += 1;
+                spawn(A, e, key);
+            }
+            observe<R, true>(A, e, key, i, A.g_row, A.o_row, pre, ob);  // i < n_pad: padded lanes touch only padding
+            if (pass == 0) {
+                const bool done = t.terminated || t.truncated;
+                if (active && ob.onboard_det) locks += 1;
+                if (active) {
+                    A.io.reward[i] = t.reward;
+                    A.io.terminated[i] = t.terminated ? 1 : 0;
+                    A.io.truncated[i] = t.truncated ? 1 : 0;
+                    if (A.has_info) write_info(A, i, e, t, ob);
+                }
+                account_episodes(A, active, done, e, t);
+                need_reset = done && A.auto_reset;
+                if (need_reset && active && A.io.terminal_obs) {
+#pragma unroll
+                    for (int k = 0; k < HLYNR_OBS_DIM; ++k) A.io.terminal_obs[i * HLYNR_OBS_DIM + k] = ob.o[k];
+                }
+            }
+        }
+        if (A.io.obs) store_obs_rows(tiles + warp * OBS_TILE, ob.o, A.io.obs, warp_first, A.n, lane);
+        if (active) store_env(A, i, e);
+    }
+    const int wl = __reduce_add_sync(0xffffffffu, locks);
+    if (lane == 0 && wl) atomicAdd(A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS + 13, (double)wl);
+}
+
 // reset(): environment.py:353.  mask == NULL resets every env.
 template <typename R> __global__ void __launch_bounds__(HLYNR_BLOCK) reset_kernel(const __grid_constant__ KernelArgs<R> A) {
     const int64_t i = (int64_t)blockIdx.x * HLYNR_BLOCK + threadIdx.x;
@@ -1096,7 +1286,7 @@ template <typename R> __global__ void __launch_bounds__(HLYNR_BLOCK) reset_kerne
     ObsOut ob;
     e.episode += 1;
     spawn(A, e, key);
-    observe(A, e, key, i, A.g_row, A.o_row, ob);
+    observe(A, e, key, i, A.g_row, A.o_row, RingPre<R>{}, ob);
     store_env(A, i, e);
     if (A.io.obs) {
 #pragma unroll

@@ -159,6 +159,9 @@ class HlynrSim:
                                             uni.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p)))
         return raw, uni, nrm
 
+    def set_option(self, name, value):
+        _lib.check(self.L.hlynr_set_option(self.h, name.encode(), int(value)))
+
     def launch_count(self):
         v = C.c_int64()
         _lib.check(self.L.hlynr_launch_count(self.h, C.byref(v)))

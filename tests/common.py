@@ -7,7 +7,7 @@ import numpy as np
 from hlynr_intercept_b200 import config
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+GOLDEN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("stat_"))
 
 STATE_FLOAT_FIELDS = ["ipos", "ivel", "quat", "mpos", "mvel", "wind", "thrust", "fuel", "fuel_used", "prev_d",
                       "last_d", "min_d", "kf_x", "kf_P", "T0", "base_cd", "peak"]
@@ -106,7 +106,7 @@ class CudaBatch:
     """HlynrSim behind the RefBatch / OracleBatch call surface (numpy in, numpy out), calling through the C ABI
     with device tensors."""
 
-    def __init__(self, params, curriculum, n_envs, seed=1234, env_id_offset=0, float64=False, device=0):
+    def __init__(self, params, curriculum, n_envs, seed=1234, env_id_offset=0, float64=False, device=0, variant=None):
         import torch
         from hlynr_intercept_b200.sim import HlynrSim
 
@@ -114,6 +114,8 @@ class CudaBatch:
         self.sim = HlynrSim(params=params, curriculum=curriculum, n_envs=n_envs, device=device, seed=seed,
                             env_id_offset=env_id_offset, precision="fp64" if float64 else "fp32")
         self.n = n_envs
+        if variant is not None:
+            self.sim.set_option("step_kernel_variant", variant)
 
     def reset(self, mask=None):
         m = None if mask is None else self.torch.as_tensor(np.asarray(mask, np.uint8))

@@ -33,13 +33,20 @@ def test_philox_on_device_matches_contract():
         np.testing.assert_allclose(nrm, draws.normals(want), rtol=2e-6, atol=2e-7)
 
 
-@pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_cuda_matches_reference_golden(name):
+TRAJ_CASES = [c for c in GOLDEN_CASES if not c.startswith("stat_")]
+DIRECT, TMA = 1, 2  # step_kernel_variant
+
+
+@pytest.mark.parametrize("variant", [DIRECT, TMA])
+@pytest.mark.parametrize("name", TRAJ_CASES)
+def test_cuda_matches_reference_golden(name, variant):
     g = load_golden(name)
     meta = g["meta"]
     P, cur = golden_setup(g)
     f64 = meta["float64"]
-    cuda = CudaBatch(P, cur, meta["n_envs"], seed=meta["seed"], float64=f64)
+    if f64 and variant == TMA:
+        pytest.skip("the TMA-prefetched kernel is the fp32 build's")
+    cuda = CudaBatch(P, cur, meta["n_envs"], seed=meta["seed"], float64=f64, variant=variant)
     shadow = oracle.OracleBatch(P, cur, meta["n_envs"], seed=meta["seed"], float64=f64)
     sim = Lockstep(cuda, shadow)
     tol = TOL[f64]
@@ -48,12 +55,12 @@ def test_cuda_matches_reference_golden(name):
 
 
 @pytest.mark.parametrize("base", ["cfg2", "cfg3", "cfg4"])
-@pytest.mark.parametrize("f64", [False, True])
-def test_cuda_matches_oracle_4096_envs_100_steps(base, f64):
-    """BASELINE cfg2 size (4096 envs): CUDA vs oracle, 1-step and 100-step horizon."""
-    n, T, seed = 4096, 100, 4242
+@pytest.mark.parametrize("f64,variant", [(False, DIRECT), (False, TMA), (True, DIRECT)])
+def test_cuda_matches_oracle_4096_envs_100_steps(base, f64, variant):
+    """BASELINE cfg2 size (4096 envs, here 4100 to exercise a partial tile): CUDA vs oracle, 1-step and 100-step horizon."""
+    n, T, seed = 4100, 100, 4242
     P, cur = config.resolve_config(config.baseline_config(base), warn_dead=False)
-    cuda = CudaBatch(P, cur, n, seed=seed, float64=f64)
+    cuda = CudaBatch(P, cur, n, seed=seed, float64=f64, variant=variant)
     orc = oracle.OracleBatch(P, cur, n, seed=seed, float64=f64, threads=8)
     tol = TOL[f64]
     o_c, o_o = cuda.reset(), orc.reset()
@@ -102,8 +109,8 @@ def test_sharding_invariance_and_rollout_equivalence():
 
     P, cur = config.resolve_config(config.baseline_config("cfg4"), warn_dead=False)
     n, seed, K = 512, 77, 40
-    full = CudaBatch(P, cur, n, seed=seed)
-    lo = CudaBatch(P, cur, n // 2, seed=seed, env_id_offset=0)
+    full = CudaBatch(P, cur, n, seed=seed, variant=TMA)      # the two step-kernel variants must agree bit for bit
+    lo = CudaBatch(P, cur, n // 2, seed=seed, env_id_offset=0, variant=DIRECT)
     hi = CudaBatch(P, cur, n // 2, seed=seed, env_id_offset=n // 2)
     fused = CudaBatch(P, cur, n, seed=seed)
     o_full = full.reset()

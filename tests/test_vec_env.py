@@ -1,0 +1,110 @@
+"""HlynrVecEnv: the Stable-Baselines3 VecEnv contract the reference's trainers rely on."""
+import numpy as np
+import pytest
+
+from common import golden_setup, load_golden
+from hlynr_intercept_b200 import config
+
+pytestmark = pytest.mark.gpu
+
+
+def make(n, cfg="cfg4", **kw):
+    from hlynr_intercept_b200.vec_env import HlynrVecEnv
+
+    return HlynrVecEnv(config.baseline_config(cfg), n_envs=n, seed=1234, warn_dead=False, **kw)
+
+
+def test_spaces_and_shapes():
+    v = make(3)
+    assert v.num_envs == 3
+    assert v.observation_space.shape == (26,) and v.observation_space.dtype == np.float32
+    assert float(v.observation_space.low.min()) == -2.0 and float(v.observation_space.high.max()) == 1.0
+    assert v.action_space.shape == (6,) and float(v.action_space.low.min()) == -1.0
+    obs = v.reset()
+    assert obs.shape == (3, 26) and obs.dtype == np.float32
+    obs, rew, dones, infos = v.step(np.zeros((3, 6)))          # float64 zeros as helpers/check_missile_trajectory.py:58
+    assert obs.shape == (3, 26) and rew.shape == (3,) and rew.dtype == np.float32 and dones.dtype == bool
+    assert isinstance(infos, list) and len(infos) == 3
+    for k in ("distance", "intercepted", "missile_hit_target", "fuel_remaining", "fuel_used", "clamped", "missile_pos",
+              "interceptor_pos", "steps", "radar_detected", "radar_quality", "min_distance", "crossed_threshold"):
+        assert k in infos[0], k
+    assert infos[0]["steps"] == 1 and infos[0]["missile_pos"].shape == (3,)
+    v.close()
+
+
+def test_matches_reference_golden_through_the_vecenv_api():
+    """Same trajectory as the golden fixture when driven through reset/step_async/step_wait, including the SB3
+    auto-reset semantics (terminal_observation, TimeLimit.truncated, Monitor-style episode info)."""
+    from hlynr_intercept_b200.vec_env import HlynrVecEnv
+
+    g = load_golden("cfg4_f32_pursuit_long")
+    meta = g["meta"]
+    v = HlynrVecEnv(meta["env_cfg"], n_envs=meta["n_envs"], seed=meta["seed"], warn_dead=False)
+    obs = v.reset()
+    np.testing.assert_allclose(obs, g["obs0"], atol=1e-3)
+    k = 0
+    for t in range(g["obs"].shape[0]):
+        v.step_async(g["actions"][t])
+        obs, rew, dones, infos = v.step_wait()
+        want_done = (g["terminated"][t] | g["truncated"][t]).astype(bool)
+        assert (dones == want_done).all(), t
+        d = np.abs(obs - g["obs"][t]); d[:, [9, 10, 11, 13, 16]] = 0
+        assert d.max() < 1e-3
+        np.testing.assert_allclose(rew, g["reward"][t], rtol=1e-3, atol=2e-3)
+        for i in np.nonzero(want_done)[0]:
+            inf = infos[i]
+            np.testing.assert_allclose(inf["terminal_observation"], g["terminal_obs"][k], atol=5e-3)
+            assert inf["TimeLimit.truncated"] == bool(g["truncated"][t][i] and not g["terminated"][t][i])
+            assert inf["episode"]["l"] == int(g["episode_length"][t][i])
+            np.testing.assert_allclose(inf["episode"]["r"], g["episode_return"][t][i], rtol=1e-3)
+            assert inf["intercepted"] == bool(g["flags"][t][i] & 1)
+            k += 1
+        for i in np.nonzero(~want_done)[0]:
+            assert "terminal_observation" not in infos[i] and "episode" not in infos[i]
+    assert k == len(g["terminal_idx"]) and k > 0
+    v.close()
+
+
+def test_env_method_and_get_attr_surface():
+    cfg = config.baseline_config("cfg4")
+    cfg["curriculum"] = dict(enabled=True, initial_radius=100.0, final_radius=5.0, curriculum_steps=2000000)
+    from hlynr_intercept_b200.vec_env import HlynrVecEnv
+
+    v = HlynrVecEnv(cfg, n_envs=4, warn_dead=False)
+    v.reset()
+    assert v.env_method("get_current_intercept_radius") == [100.0] * 4
+    v.env_method("set_training_step_count", 1000000)                        # scripts/train_flat_ppo.py:173-177
+    assert abs(v.get_attr("get_current_intercept_radius")[0]() - 52.5) < 1e-9   # scripts/train_flat_ppo.py:221
+    og = v.get_attr("observation_generator")[0]
+    assert og.radar_beam_width == 60.0 and og.onboard_detection_reliability == 1.0
+    st = v.get_attr("interceptor_state")[0]
+    assert st["position"].shape == (3,) and st["orientation"].shape == (4,) and 0 < st["fuel"] <= 100.0
+    ms = v.get_attr("missile_state", indices=[1, 2])
+    assert len(ms) == 2 and ms[0]["velocity"].shape == (3,)
+    assert v.env_is_wrapped(type("Monitor", (), {})) == [True] * 4
+    with pytest.raises(AttributeError):
+        v.env_method("render_everything")
+    v.env_method("seed", 7)
+    v.close()
+
+
+def test_seed_reproducibility_and_curriculum_effect():
+    a, b = make(16), make(16)
+    a.seed(5); b.seed(5)
+    oa, ob = a.reset(), b.reset()
+    assert (oa == ob).all()
+    act = np.random.default_rng(0).uniform(-1, 1, (16, 6)).astype(np.float32)
+    for _ in range(20):
+        ra, rb = a.step(act), b.step(act)
+        assert (ra[0] == rb[0]).all() and (ra[1] == rb[1]).all()
+    b.seed(6)
+    assert not (b.reset() == a.reset()).all()
+    a.close(); b.close()
+
+
+def test_lazy_infos_large_batch():
+    v = make(8192, lazy_infos=True, copy_outputs=False)
+    v.reset()
+    obs, rew, dones, infos = v.step(np.zeros((8192, 6), np.float32))
+    assert len(infos) == 8192 and infos[0] is infos[1] and not dones.any()
+    v.close()
