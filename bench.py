@@ -34,6 +34,17 @@ ALGO_BYTES = {"cfg2": 526, "cfg3": 630, "cfg3_radar": 630, "cfg4": 630, "cfg1": 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
+def measured_traffic(workload, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel from the committed ncu --set full
+    capture (profiles/traffic.json), scaled to n envs; None if no capture matches."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))[workload]
+        return t["dram_bytes_per_launch"] * n / t["n_envs"]
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -294,7 +305,7 @@ def main():
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "hlynr::step_kernel<float,false>",
+                         "traffic": measured_traffic(args.workload, n), "peak_source": peak_src, "kernel": "hlynr::step_kernel<float,false>",
                          "algorithmic_bytes_per_env_step": bytes_per_step, "units_per_launch": n,
                          "kernel_us_per_launch": per_launch_ms * 1e3},
             "fused_rollout": fused,
