@@ -54,6 +54,7 @@ struct hlynr_sim {
     int64_t launches = 0;
     double env_steps = 0.0;
     int kernel_variant = 0;  // 0 auto, 1 direct, 2 TMA-prefetched persistent kernel
+    int specialise = 1;      // use the feature-specialised instantiations when the configuration matches one
     int sm_count = 148;  // ticks simulated since the statistics were last zeroed (n per launch tick)
     void* state_mem = nullptr;
     size_t state_bytes = 0;
@@ -253,6 +254,28 @@ template <typename R> static KernelArgs<R> base_args(hlynr_sim* s, const StatePl
 }
 static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
+// Feature set of a resolved configuration; a specialised instantiation exists for FT_V2ON and FT_V2OFF.
+static int feature_set(const HlynrParams& p) {
+    if (p.dr_enabled || p.precision_mode || p.fuze_enabled) return FT_GENERIC;
+    int f = 0;
+    if (p.isa_enabled) f |= FT_ISA;
+    if (p.mach_enabled) f |= FT_MACH;
+    if (p.enh_wind_enabled) f |= FT_ENHW;
+    if (p.thrust_dyn_enabled) f |= FT_THRUST;
+    if (p.onboard_delay > 0) f |= FT_ONBD;
+    if (p.ground_enabled) f |= FT_GROUND;
+    if (p.ground_enabled && p.ground_delay > 0) f |= FT_GDELAY;
+    if (p.evasion_enabled) f |= FT_EVADE;
+    return (f == FT_V2ON || f == FT_V2OFF) ? f : FT_GENERIC;
+}
+template <bool kRollout> static void launch_step_f32(const hlynr_sim* s, const KernelArgs<float>& A, cudaStream_t st, bool specialise) {
+    const int grid = grid_for(s->n, HLYNR_BLOCK);
+    const int f = specialise ? feature_set(s->params) : FT_GENERIC;
+    if (f == FT_V2ON) step_kernel<float, kRollout, FT_V2ON><<<grid, HLYNR_BLOCK, 0, st>>>(A);
+    else if (f == FT_V2OFF) step_kernel<float, kRollout, FT_V2OFF><<<grid, HLYNR_BLOCK, 0, st>>>(A);
+    else step_kernel<float, kRollout, FT_GENERIC><<<grid, HLYNR_BLOCK, 0, st>>>(A);
+}
+
 // ------------------------------------------------------------------------------------------------
 // TMA-prefetched persistent step kernel: host-side plan
 // ------------------------------------------------------------------------------------------------
@@ -382,6 +405,7 @@ int hlynr_set_option(hlynr_t* s, const char* name, int64_t value) {
         s->kernel_variant = (int)value;
         return 0;
     }
+    if (strcmp(name, "specialise") == 0) { s->specialise = value != 0; return 0; }
     return fail("hlynr_set_option: unknown option '%s'", name);
 }
 int hlynr_launch_count(const hlynr_t* s, int64_t* out) { if (!s || !out) return fail("null argument"); *out = s->launches; return 0; }
@@ -434,14 +458,14 @@ int hlynr_step(hlynr_t* s, const float* actions_dev, float* obs_dev, float* rewa
             const int grid = (int)(n_tiles < max_ctas ? n_tiles : max_ctas);
             step_kernel_tma<<<grid, HLYNR_BLOCK, smem, st>>>(A, T);
         } else {
-            step_kernel<float, false><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+            launch_step_f32<false>(s, A, st, s->specialise != 0);
         }
     } else {
         KernelArgs<double> A = base_args<double>(s, s->pd);
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward = reward_dev; A.io.terminated = terminated_dev;
         A.io.truncated = truncated_dev; A.io.terminal_obs = terminal_obs_dev; A.auto_reset = auto_reset;
         if (info) { A.io.info = *info; A.has_info = 1; }
-        step_kernel<double, false><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+        step_kernel<double, false, FT_GENERIC><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
     }
     CK(cudaGetLastError());
     s->launches += 1;
@@ -461,14 +485,14 @@ int hlynr_rollout(hlynr_t* s, int k_steps, const float* actions_dev, float* obs_
         A.g_row = A.P.gnd_ring_len > 0 ? (int32_t)(A.tick % (uint32_t)A.P.gnd_ring_len) : 0;
         A.o_row = A.P.onb_ring_len > 0 ? (int32_t)(A.tick % (uint32_t)A.P.onb_ring_len) : 0;
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward_sum = reward_sum_dev; A.io.done_count = done_count_dev;
-        step_kernel<float, true><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+        launch_step_f32<true>(s, A, st, s->specialise != 0);
     } else {
         KernelArgs<double> A = base_args<double>(s, s->pd);
         A.tick = s->tick + 1; A.k_steps = k_steps; A.auto_reset = 1;
         A.g_row = A.P.gnd_ring_len > 0 ? (int32_t)(A.tick % (uint32_t)A.P.gnd_ring_len) : 0;
         A.o_row = A.P.onb_ring_len > 0 ? (int32_t)(A.tick % (uint32_t)A.P.onb_ring_len) : 0;
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward_sum = reward_sum_dev; A.io.done_count = done_count_dev;
-        step_kernel<double, true><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+        step_kernel<double, true, FT_GENERIC><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
     }
     CK(cudaGetLastError());
     s->tick += (uint32_t)k_steps;

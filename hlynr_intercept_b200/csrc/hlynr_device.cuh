@@ -162,6 +162,31 @@ template <typename R> struct KParams {
     int32_t spherical, toward_missile, obs_mode, precision_mode, fuze, onb_ring_len, gnd_ring_len;
 };
 
+// ------------------------------------------------------------------------------------------------
+// Feature sets: F < 0 = generic (every switch read from the parameters at run time); F >= 0 = the switches are
+// compile-time constants, so the uniform flag tests and the dead branches disappear.  The host launches a
+// specialised instantiation when the resolved configuration matches one, else the generic kernel.
+// ------------------------------------------------------------------------------------------------
+enum { FT_ISA = 1, FT_MACH = 2, FT_ENHW = 4, FT_THRUST = 8, FT_ONBD = 16, FT_GROUND = 32, FT_GDELAY = 64, FT_EVADE = 128 };
+#define FT_GENERIC (-1)
+#define FT_V2ON (FT_ISA | FT_MACH | FT_ENHW | FT_THRUST | FT_ONBD | FT_GROUND | FT_GDELAY | FT_EVADE)  /* cfg4: medium, v2.0 on */
+#define FT_V2OFF (FT_GROUND | FT_GDELAY | FT_EVADE)                                                   /* cfg2: medium, v2.0 off */
+template <int F> struct Feat {
+    static constexpr bool generic = F < 0;
+    template <typename P> static HD bool isa(const P& p) { if constexpr (F < 0) return p.isa != 0; else return (F & FT_ISA) != 0; }
+    template <typename P> static HD bool mach(const P& p) { if constexpr (F < 0) return p.mach != 0; else return (F & FT_MACH) != 0; }
+    template <typename P> static HD bool enh_wind(const P& p) { if constexpr (F < 0) return p.enh_wind != 0; else return (F & FT_ENHW) != 0; }
+    template <typename P> static HD bool thrust_dyn(const P& p) { if constexpr (F < 0) return p.thrust_dyn != 0; else return (F & FT_THRUST) != 0; }
+    template <typename P> static HD bool onboard_delay(const P& p) { if constexpr (F < 0) return p.onboard_delay > 0; else return (F & FT_ONBD) != 0; }
+    template <typename P> static HD bool ground(const P& p) { if constexpr (F < 0) return p.ground != 0; else return (F & FT_GROUND) != 0; }
+    template <typename P> static HD bool ground_delay(const P& p) { if constexpr (F < 0) return p.ground_delay > 0; else return (F & FT_GDELAY) != 0; }
+    template <typename P> static HD bool evasion(const P& p) { if constexpr (F < 0) return p.evasion != 0; else return (F & FT_EVADE) != 0; }
+    // never part of a specialised set: domain randomization and the non-standard modes
+    template <typename P> static HD bool dr(const P& p) { if constexpr (F < 0) return p.dr != 0; else return false; }
+    template <typename P> static HD bool precision_mode(const P& p) { if constexpr (F < 0) return p.precision_mode != 0; else return false; }
+    template <typename P> static HD bool fuze(const P& p) { if constexpr (F < 0) return p.fuze != 0; else return false; }
+};
+
 template <typename R> struct KCurriculum {
     R intercept_radius;   // S context
     float cos_half_beam;  // beam gate acos(c) > radians(width/2)  <=>  c < cos(radians(width/2))
@@ -228,7 +253,8 @@ template <typename R> struct Env {
 #define FLAG_CROSSED 1
 #define FLAG_KF_INIT 2
 
-template <typename R> HD void load_env(const KernelArgs<R>& A, int64_t i, Env<R>& e) {
+template <typename R, int F = FT_GENERIC> HD void load_env(const KernelArgs<R>& A, int64_t i, Env<R>& e) {
+    typedef Feat<F> FT;
     const StatePlanes<R>& s = A.st;
     Vec4<R> v;
     v = s.r[0][i]; e.ipx = v.x; e.ipy = v.y; e.ipz = v.z; e.fuel = v.w;
@@ -237,16 +263,17 @@ template <typename R> HD void load_env(const KernelArgs<R>& A, int64_t i, Env<R>
     v = s.r[3][i]; e.mvx = v.x; e.mvy = v.y; e.mvz = v.z; e.last_d = v.w;
     v = s.r[4][i]; e.kpx = v.x; e.kpy = v.y; e.kpz = v.z; e.min_d = v.w;
     v = s.r[5][i]; e.kvx = v.x; e.kvy = v.y; e.kvz = v.z; e.ep_ret = v.w;
-    if (A.P.thrust_dyn | A.P.dr) { v = s.r[6][i]; e.thx = v.x; e.thy = v.y; e.thz = v.z; e.T0 = v.w; }
+    if (FT::thrust_dyn(A.P) || FT::dr(A.P)) { v = s.r[6][i]; e.thx = v.x; e.thy = v.y; e.thz = v.z; e.T0 = v.w; }
     else { e.thx = e.thy = e.thz = R(0); e.T0 = R(288.15); }
     float4 f;
     f = s.f[0][i]; e.qw = f.x; e.qx = f.y; e.qy = f.z; e.qz = f.w;
     f = s.f[1][i]; e.wx = f.x; e.wy = f.y; e.wz = f.z; e.Ppp = f.w;
     f = s.f[2][i]; e.Ppv = f.x; e.Pvp = f.y; e.Pvv = f.z; e.base_cd = f.w;
-    if (A.P.dr) { f = s.f[3][i]; e.peak = f.x; } else e.peak = 0.f;
+    if (FT::dr(A.P)) { f = s.f[3][i]; e.peak = f.x; } else e.peak = 0.f;
     int4 q = s.i0[i]; e.steps = q.x; e.worsen = q.y; e.flags = q.z; e.episode = q.w;
 }
-template <typename R> HD void store_env(const KernelArgs<R>& A, int64_t i, const Env<R>& e) {
+template <typename R, int F = FT_GENERIC> HD void store_env(const KernelArgs<R>& A, int64_t i, const Env<R>& e) {
+    typedef Feat<F> FT;
     const StatePlanes<R>& s = A.st;
     s.r[0][i] = Vec4<R>{e.ipx, e.ipy, e.ipz, e.fuel};
     s.r[1][i] = Vec4<R>{e.ivx, e.ivy, e.ivz, e.fuel_used};
@@ -254,11 +281,11 @@ template <typename R> HD void store_env(const KernelArgs<R>& A, int64_t i, const
     s.r[3][i] = Vec4<R>{e.mvx, e.mvy, e.mvz, e.last_d};
     s.r[4][i] = Vec4<R>{e.kpx, e.kpy, e.kpz, e.min_d};
     s.r[5][i] = Vec4<R>{e.kvx, e.kvy, e.kvz, e.ep_ret};
-    if (A.P.thrust_dyn | A.P.dr) s.r[6][i] = Vec4<R>{e.thx, e.thy, e.thz, e.T0};
+    if (FT::thrust_dyn(A.P) || FT::dr(A.P)) s.r[6][i] = Vec4<R>{e.thx, e.thy, e.thz, e.T0};
     s.f[0][i] = make_float4(e.qw, e.qx, e.qy, e.qz);
     s.f[1][i] = make_float4(e.wx, e.wy, e.wz, e.Ppp);
     s.f[2][i] = make_float4(e.Ppv, e.Pvp, e.Pvv, e.base_cd);
-    if (A.P.dr) s.f[3][i] = make_float4(e.peak, 0.f, 0.f, 0.f);
+    if (FT::dr(A.P)) s.f[3][i] = make_float4(e.peak, 0.f, 0.f, 0.f);
     s.i0[i] = make_int4(e.steps, e.worsen, e.flags, e.episode);
 }
 
@@ -287,17 +314,18 @@ template <typename R> HD void isa_props(const KParams<R>& P, R T0, R alt, R* rho
 // fallback (environment.py:920-921, :1099-1100).  F = -(v/|v|) * (0.5 rho |v|^2 Cd A) * post_scale.
 // With domain randomization base_cd/peak are np.float64 scalars and the product is a float64 island
 // (physics_randomizer.py:273,278); the fp32 build evaluates it in float.
-template <typename R>
+template <typename R, int F>
 HD void drag_accel(const KParams<R>& P, const Env<R>& e, R vx, R vy, R vz, R alt, R area, R post_scale, R rc_mass, R mass,
                    R* ax, R* ay, R* az) {
+    typedef Feat<F> FT;
     R rho = P.rho_weak, cs = P.cs_weak;
     bool weak = true;
-    if (P.isa) { isa_props(P, e.T0, alt, &rho, &cs); weak = false; }
+    if (FT::isa(P)) { isa_props(P, e.T0, alt, &rho, &cs); weak = false; }
     R vmag = nnorm3(vx, vy, vz);
-    if (P.mach && vmag > R(1e-6)) {
+    if (FT::mach(P) && vmag > R(1e-6)) {
         R mach = ndiv(vmag, cs);
         R cd;
-        if (P.dr) {
+        if (FT::dr(P)) {
             double bc = (double)e.base_cd, pk = (double)e.peak, c;
             if (mach < P.sub_mach) c = bc;
             else if (mach < P.sup_mach) c = bc * (1.0 + (pk - 1.0) * (double)ndiv(sub(mach, P.sub_mach), P.sup_minus_sub));
@@ -332,9 +360,14 @@ template <typename R> HD R nan_guard(R a, R lim) {  // np.nan_to_num(nan=0, posi
     return a;
 }
 
+// Observation sink: channel k of this lane's row goes straight into the warp's shared-memory tile (row pitch 26
+// words), so the 26 channels never occupy registers at the same time.  emit == false (non-final fused ticks)
+// drops the stores and lets the compiler remove the channel arithmetic.
 struct ObsOut {
-    float o[HLYNR_OBS_DIM];
+    float* row;  // tile + lane * 26
+    bool emit;
     bool onboard_det, ground_det;
+    HD void put(int k, float v) const { if (emit) row[k] = v; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -346,17 +379,18 @@ struct ObsOut {
 // ring samples already staged by the caller (TMA kernel); used instead of the global ring reads when kPre
 template <typename R> struct RingPre { float4 o; Vec4<R> ga, gb; };
 
-template <typename R, bool kPre = false>
-HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i, int g_row, int o_row, const RingPre<R>& pre,
-                ObsOut& out) {
+template <typename R, int F, bool kPre = false>
+HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint4 ur, int64_t i, int g_row, int o_row,
+                const RingPre<R>& pre, ObsOut& out) {
     typedef R W;
+    typedef Feat<F> FT;
     const KParams<R>& P = A.P;
     const KCurriculum<R>& C = A.C;
     const int64_t n = A.ring_stride;
     const float ipx = (float)e.ipx, ipy = (float)e.ipy, ipz = (float)e.ipz;
     const float ivx = (float)e.ivx, ivy = (float)e.ivy, ivz = (float)e.ivz;
     const float mpx = (float)e.mpx, mpy = (float)e.mpy, mpz = (float)e.mpz;
-    const uint4 ur = draw_raw(key, (uint32_t)e.episode, (uint32_t)e.steps, HLYNR_BLK_UNI);
+    // ur = the tick's BLK_UNI block (x gust, y onboard dropout, z ground dropout, w packet loss)
 
     // === onboard radar, core.py:531-593 ===
     const float rx = sub(mpx, ipx), ry = sub(mpy, ipy), rz = sub(mpz, ipz);
@@ -380,13 +414,13 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i,
     }
     float orx, ory, orz;
     bool o_det;
-    if (P.onboard_delay > 0) {
+    if (FT::onboard_delay(P)) {
         const int L = P.onb_ring_len;
         const int odelay = e.flags >> 8;
         A.st.oring[(int64_t)o_row * n + i] = make_float4(rx, ry, rz, onb ? 1.f : 0.f);
         if (e.steps >= odelay) {
             float4 s;
-            if (kPre && !P.dr) s = pre.o;
+            if (kPre && !FT::dr(P)) s = pre.o;
             else {
                 int rrow = o_row - odelay;  // sample written `odelay` ticks ago
                 if (rrow < 0) rrow += L;
@@ -400,7 +434,7 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i,
     bool gdet = false;
     W grx = W(0), gry = W(0), grz = W(0), gvx = W(0), gvy = W(0), gvz = W(0);
     float gq = 0.f;
-    if (P.ground) {
+    if (FT::ground(P)) {
         float gx = mpx - P.gpos[0], gy = mpy - P.gpos[1], gz = mpz - P.gpos[2];
         float gr = nnorm3(gx, gy, gz);
         bool ok = !(gr > P.g_max_range);
@@ -428,7 +462,7 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i,
     W dgx, dgy, dgz, dvx, dvy, dvz;
     float dgq;
     bool dg_det;
-    if (P.ground && P.ground_delay > 0) {  // delayed values, CURRENT flag (core.py:626, quirk Q3)
+    if (FT::ground(P) && FT::ground_delay(P)) {  // delayed values, CURRENT flag (core.py:626, quirk Q3)
         const int L = P.gnd_ring_len;
         Vec4<W>* wr = A.st.gring + (int64_t)g_row * 2 * n;
         wr[i] = Vec4<W>{grx, gry, grz, (W)gq};
@@ -448,7 +482,7 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i,
 
     // === datalink, core.py:440-474 ===
     float link = 0.f;
-    if (P.ground) {
+    if (FT::ground(P)) {
         float lr = nnorm3(ipx - P.gpos[0], ipy - P.gpos[1], ipz - P.gpos[2]);
         if (!(lr > P.max_link)) {
             float r1 = lr * P.rc_max_link;
@@ -511,56 +545,57 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t i,
     }
     e.flags = (e.flags & ~FLAG_KF_INIT) | (kf_init ? FLAG_KF_INIT : 0);
 
-    float* o = out.o;
     if (kf_init) {
         const W px = e.kpx - (W)ipx, py = e.kpy - (W)ipy, pz = e.kpz - (W)ipz;
         const W vx = e.kvx - (W)ivx, vy = e.kvy - (W)ivy, vz = e.kvz - (W)ivz;
         const W rr = nnorm3(px, py, pz);
         const W cl = -ndot3(px, py, pz, vx, vy, vz) * nrcp(rr + W(1e-6));
-        o[0] = (float)clip(px * P.rc_max_range_w, W(-1), W(1));
-        o[1] = (float)clip(py * P.rc_max_range_w, W(-1), W(1));
-        o[2] = (float)clip(pz * P.rc_max_range_w, W(-1), W(1));
-        o[3] = (float)clip(vx * P.rc_max_velocity_w, W(-1), W(1));
-        o[4] = (float)clip(vy * P.rc_max_velocity_w, W(-1), W(1));
-        o[5] = (float)clip(vz * P.rc_max_velocity_w, W(-1), W(1));
-        o[13] = cl > W(0) ? (float)clip(W(1) - rr * nrcp(cl) * W(0.01), W(-1), W(1)) : -1.f;
+        out.put(0, (float)clip(px * P.rc_max_range_w, W(-1), W(1)));
+        out.put(1, (float)clip(py * P.rc_max_range_w, W(-1), W(1)));
+        out.put(2, (float)clip(pz * P.rc_max_range_w, W(-1), W(1)));
+        out.put(3, (float)clip(vx * P.rc_max_velocity_w, W(-1), W(1)));
+        out.put(4, (float)clip(vy * P.rc_max_velocity_w, W(-1), W(1)));
+        out.put(5, (float)clip(vz * P.rc_max_velocity_w, W(-1), W(1)));
+        out.put(13, cl > W(0) ? (float)clip(W(1) - rr * nrcp(cl) * W(0.01), W(-1), W(1)) : -1.f);
         float tq = clip(1.f - (e.Ppp * 3.f) * 1e-4f, 0.f, 1.f);
         if (o_det) tq *= P.radar_quality;
-        o[14] = tq;
-        o[15] = (float)clip(cl * P.rc_max_velocity_w, W(-1), W(1));
-        o[16] = rr > W(1e-6) ? (float)(ndot3((W)fx, (W)fy, (W)fz, px, py, pz) * nrcp(rr)) : 1.f;
+        out.put(14, tq);
+        out.put(15, (float)clip(cl * P.rc_max_velocity_w, W(-1), W(1)));
+        out.put(16, rr > W(1e-6) ? (float)(ndot3((W)fx, (W)fy, (W)fz, px, py, pz) * nrcp(rr)) : 1.f);
     } else {
-        o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = -2.f;
-        o[13] = -1.f; o[14] = 0.f; o[15] = 0.f; o[16] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) out.put(k, -2.f);
+        out.put(13, -1.f); out.put(14, 0.f); out.put(15, 0.f); out.put(16, 0.f);
     }
-    o[6] = clip(ivx * P.rc_max_velocity_f, -1.f, 1.f);
-    o[7] = clip(ivy * P.rc_max_velocity_f, -1.f, 1.f);
-    o[8] = clip(ivz * P.rc_max_velocity_f, -1.f, 1.f);
-    {   // quaternion_to_euler, core.py:1103-1121 (float32), divided by pi
+    out.put(6, clip(ivx * P.rc_max_velocity_f, -1.f, 1.f));
+    out.put(7, clip(ivy * P.rc_max_velocity_f, -1.f, 1.f));
+    out.put(8, clip(ivz * P.rc_max_velocity_f, -1.f, 1.f));
+    if (out.emit) {  // quaternion_to_euler, core.py:1103-1121 (float32), divided by pi
         const float w = e.qw, x = e.qx, y = e.qy, z = e.qz;
         const float sinr = 2.f * fmaf(w, x, y * z), cosr = 1.f - 2.f * fmaf(x, x, y * y);
         const float sinp = 2.f * fmaf(w, y, -(z * x));
         const float siny = 2.f * fmaf(w, z, x * y), cosy = 1.f - 2.f * fmaf(y, y, z * z);
         const float ipi = 0.318309886183790672f;
-        o[9] = atan2f(sinr, cosr) * ipi;
-        o[10] = asinf(clip(sinp, -1.f, 1.f)) * ipi;
-        o[11] = atan2f(siny, cosy) * ipi;
+        out.put(9, atan2f(sinr, cosr) * ipi);
+        out.put(10, asinf(clip(sinp, -1.f, 1.f)) * ipi);
+        out.put(11, atan2f(siny, cosy) * ipi);
     }
-    o[12] = clip((float)e.fuel * 0.01f, 0.f, 1.f);
+    out.put(12, clip((float)e.fuel * 0.01f, 0.f, 1.f));
     if (dg_det && link > 0.1f) {
-        o[17] = (float)clip(dgx * P.rc_max_range_w, W(-1), W(1));
-        o[18] = (float)clip(dgy * P.rc_max_range_w, W(-1), W(1));
-        o[19] = (float)clip(dgz * P.rc_max_range_w, W(-1), W(1));
-        o[20] = (float)clip(dvx * P.rc_max_velocity_w, W(-1), W(1));
-        o[21] = (float)clip(dvy * P.rc_max_velocity_w, W(-1), W(1));
-        o[22] = (float)clip(dvz * P.rc_max_velocity_w, W(-1), W(1));
-        o[23] = dgq;
+        out.put(17, (float)clip(dgx * P.rc_max_range_w, W(-1), W(1)));
+        out.put(18, (float)clip(dgy * P.rc_max_range_w, W(-1), W(1)));
+        out.put(19, (float)clip(dgz * P.rc_max_range_w, W(-1), W(1)));
+        out.put(20, (float)clip(dvx * P.rc_max_velocity_w, W(-1), W(1)));
+        out.put(21, (float)clip(dvy * P.rc_max_velocity_w, W(-1), W(1)));
+        out.put(22, (float)clip(dvz * P.rc_max_velocity_w, W(-1), W(1)));
+        out.put(23, dgq);
     } else {
-        o[17] = o[18] = o[19] = o[20] = o[21] = o[22] = -2.f;
-        o[23] = 0.f;
+#pragma unroll
+        for (int k = 17; k < 23; ++k) out.put(k, -2.f);
+        out.put(23, 0.f);
     }
-    o[24] = link;
-    o[25] = fus;
+    out.put(24, link);
+    out.put(25, fus);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -675,6 +710,7 @@ template <typename R> HD void spawn(const KernelArgs<R>& A, Env<R>& e, const Rng
 // one tick (environment.py:605-859)
 // ------------------------------------------------------------------------------------------------
 struct TickOut {
+    uint4 ur;  // the tick's BLK_UNI block, drawn once (gust / onboard dropout / ground dropout / packet loss)
     float reward;
     float distance;
     bool terminated, truncated, intercepted, hit, clamped, fuze;
@@ -720,11 +756,13 @@ HD void quat_step(Env<double>& e, double wx, double wy, double wz, double dt) {
     }
 }
 
-template <typename R>
+template <typename R, int F>
 HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const float act[6], TickOut& t) {
+    typedef Feat<F> FT;
     const KParams<R>& P = A.P;
     e.steps += 1;
     const uint32_t ep = (uint32_t)e.episode, st = (uint32_t)e.steps;
+    t.ur = draw_raw(key, ep, st, HLYNR_BLK_UNI);
     R a0 = (R)act[0], a1 = (R)act[1], a2 = (R)act[2], a3 = (R)act[3], a4 = (R)act[4], a5 = (R)act[5];
     // SafetyClamp.apply (core.py:1069-1100); limits are in action units (quirk Q8)
     bool clamped = false;
@@ -742,7 +780,7 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
     // ---- _update_interceptor (environment.py:861-963) ----
     {
         R Tx = mul(a0, R(10000.0)), Ty = mul(a1, R(10000.0)), Tz = mul(a2, R(10000.0));
-        if (P.thrust_dyn) {  // first-order lag, :874-880
+        if (FT::thrust_dyn(P)) {  // first-order lag, :874-880
             if constexpr (std::is_same<R, float>::value) {
                 e.thx = fmaf(Tx - e.thx, P.dt_over_tau, e.thx);
                 e.thy = fmaf(Ty - e.thy, P.dt_over_tau, e.thy);
@@ -763,7 +801,7 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
         R alt = e.ipz > R(0) ? e.ipz : R(0);
         R vax = sub(e.ivx, (R)e.wx), vay = sub(e.ivy, (R)e.wy), vaz = sub(e.ivz, (R)e.wz);
         R dax, day, daz;
-        drag_accel(P, e, vax, vay, vaz, alt, R(1.0), R(1.0), R(1.0 / 500.0), R(500.0), &dax, &day, &daz);
+        drag_accel<R, F>(P, e, vax, vay, vaz, alt, R(1.0), R(1.0), R(1.0 / 500.0), R(500.0), &dax, &day, &daz);
         R ax = add(tax, dax), ay = add(tay, day), az = add(add(taz, daz), (R)(-9.81f));
         if (P.validate && !(isfinite(ax) && isfinite(ay) && isfinite(az))) {
             ax = nan_guard(ax, R(50)); ay = nan_guard(ay, R(50)); az = nan_guard(az, R(50));
@@ -778,9 +816,9 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
         R alt = e.mpz > R(0) ? e.mpz : R(0);
         R vax = sub(e.mvx, (R)e.wx), vay = sub(e.mvy, (R)e.wy), vaz = sub(e.mvz, (R)e.wz);
         R dax, day, daz;
-        drag_accel(P, e, vax, vay, vaz, alt, R(2.0), P.missile_ratio, R(1.0 / 1000.0), R(1000.0), &dax, &day, &daz);
+        drag_accel<R, F>(P, e, vax, vay, vaz, alt, R(2.0), P.missile_ratio, R(1.0 / 1000.0), R(1000.0), &dax, &day, &daz);
         double ex = 0.0, ey = 0.0, ez = 0.0;
-        if (P.evasion) {
+        if (FT::evasion(P)) {
             float z0, z1, z2;
             draw_normal3(key, ep, st, HLYNR_BLK_EVADE, &z0, &z1, &z2);
             ex = (double)(z0 * 2.0f); ey = (double)(z1 * 2.0f); ez = (double)(z2 * 2.0f);
@@ -797,7 +835,7 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
         e.mpx = add(e.mpx, mul(e.mvx, dt)); e.mpy = add(e.mpy, mul(e.mvy, dt)); e.mpz = add(e.mpz, mul(e.mvz, dt));
     }
     // ---- _update_wind (environment.py:1119-1129): the wind used by the NEXT tick ----
-    if (P.enh_wind) {  // EnhancedWindModel.get_wind_vector, physics_models.py:351-387
+    if (FT::enh_wind(P)) {  // EnhancedWindModel.get_wind_vector, physics_models.py:351-387
         R alt = e.ipz > R(0) ? e.ipz : R(0);
         R pf, ti;
         if (alt <= R(10.0)) { pf = R(1.0); ti = P.ti_low; }
@@ -810,8 +848,7 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
             draw_normal3(key, ep, st, HLYNR_BLK_WIND, &z0, &z1, &z2);
             wvx += scale * (R)z0; wvy += scale * (R)z1; wvz += scale * (R)z2;
         }
-        uint4 ur = draw_raw(key, ep, st, HLYNR_BLK_UNI);
-        if (u01(ur.x) < 0.001f) {  // gust, :381-385 (0.1 % of ticks)
+        if (u01(t.ur.x) < 0.001f) {  // gust, :381-385 (0.1 % of ticks)
             float g0, g1, g2, g3;
             uint4 gd = draw_raw(key, ep, st, HLYNR_BLK_GUST_DIR);
             box_muller(gd.x, gd.y, &g0, &g1);
@@ -833,18 +870,18 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
     }
     // ---- distance / intercept / termination (environment.py:657-814) ----
     const R dist = norm3(sub(e.mpx, e.ipx), sub(e.mpy, e.ipy), sub(e.mpz, e.ipz));  // exact: feeds the reward
-    bool intercepted = dist < (P.fuze ? P.kill_radius : A.C.intercept_radius);
+    bool intercepted = dist < (FT::fuze(P) ? P.kill_radius : A.C.intercept_radius);
     if (dist < e.min_d) e.min_d = dist;
     if (intercepted) e.flags |= FLAG_CROSSED;
     bool fuze = false;
-    if (P.fuze && e.min_d < P.kill_radius) { fuze = true; intercepted = true; }
+    if (FT::fuze(P) && e.min_d < P.kill_radius) { fuze = true; intercepted = true; }
     bool term = false, hit = false;
     const bool missile_down = e.mpz <= R(0);
-    if (P.precision_mode ? missile_down : (!intercepted && missile_down)) {
+    if (FT::precision_mode(P) ? missile_down : (!intercepted && missile_down)) {
         R gx = sub(e.mpx, P.target_x), gy = sub(e.mpy, P.target_y);
         hit = sqr(dot2(gx, gy, gx, gy)) < R(500.0);
     }
-    if (P.precision_mode) term = missile_down;
+    if (FT::precision_mode(P)) term = missile_down;
     else term = intercepted || missile_down;
     if (e.ipz < R(0)) term = true;
     else if (e.fuel <= R(0)) term = true;
@@ -860,7 +897,7 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
     // ---- _calculate_reward (environment.py:1131-1320), exact ops in the reference order ----
     R r;
     const bool crashed = e.ipz < R(0), dry = e.fuel <= R(0);
-    if (P.precision_mode) {
+    if (FT::precision_mode(P)) {
         if (term) {
             R md = e.min_d;
             if (e.flags & FLAG_CROSSED) {
@@ -962,14 +999,10 @@ HD void account_episodes(const KernelArgs<R>& A, bool active, bool done, const E
 // ------------------------------------------------------------------------------------------------
 // coalesced [N,26] store through shared memory (one warp-private tile per warp)
 // ------------------------------------------------------------------------------------------------
-// Every lane writes its 26 values as 13 float2 (row pitch 26 words: conflict-free for 64-bit stores), then the
+// The observation channels are written by observe() straight into the warp's tile (row pitch 26 words); here the
 // warp streams the 32*26 floats out linearly as float4 (the tile offset of a linear index is the index itself).
 #define OBS_TILE (32 * HLYNR_OBS_DIM)
-HD void store_obs_rows(float* tile, const float o[HLYNR_OBS_DIM], float* dst, int64_t warp_first_env, int64_t n,
-                       unsigned lane) {
-    float2* t2 = reinterpret_cast<float2*>(tile + lane * HLYNR_OBS_DIM);
-#pragma unroll
-    for (int k = 0; k < HLYNR_OBS_DIM / 2; ++k) t2[k] = make_float2(o[2 * k], o[2 * k + 1]);
+HD void flush_obs_tile(const float* tile, float* dst, int64_t warp_first_env, int64_t n, unsigned lane) {
     __syncwarp();
     const int64_t rows = n - warp_first_env;
     float* base = dst + warp_first_env * HLYNR_OBS_DIM;  // 32 * 104 B per warp: 16-byte aligned
@@ -981,11 +1014,16 @@ HD void store_obs_rows(float* tile, const float o[HLYNR_OBS_DIM], float* dst, in
             const int idx = k * 32 + (int)lane;
             if (k < 6 || idx < OBS_TILE / 4) b4[idx] = t4[idx];
         }
-    } else {
+    } else if (rows > 0) {
         const int valid = (int)rows * HLYNR_OBS_DIM;
         for (int idx = (int)lane; idx < valid; idx += 32) base[idx] = tile[idx];
     }
     __syncwarp();
+}
+// this lane's row of the tile -> one row of a [N,26] array (terminal observation of a finished episode: rare)
+HD void copy_obs_row(const float* row, float* dst_row) {
+#pragma unroll
+    for (int k = 0; k < HLYNR_OBS_DIM; ++k) dst_row[k] = row[k];
 }
 
 template <typename R> HD void write_info(const KernelArgs<R>& A, int64_t i, const Env<R>& e, const TickOut& t, const ObsOut& ob) {
@@ -1019,7 +1057,7 @@ template <typename R> HD RngKey make_key(const KernelArgs<R>& A, int64_t global_
 // kernels
 // ------------------------------------------------------------------------------------------------
 // step(): one tick of every env + SB3 auto-reset.  kRollout: k fused ticks, state stays in registers.
-template <typename R, bool kRollout>
+template <typename R, bool kRollout, int F>
 __global__ void __launch_bounds__(HLYNR_BLOCK, 4) step_kernel(const __grid_constant__ KernelArgs<R> A) {
     __shared__ __align__(16) float tiles[HLYNR_BLOCK / 32][OBS_TILE];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -1028,12 +1066,13 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, 4) step_kernel(const __grid_const
     const bool active = i < A.n;
     const int64_t ii = active ? i : A.n - 1;  // inactive lanes shadow the last env and never store
     Env<R> e;
-    load_env(A, ii, e);
+    load_env<R, F>(A, ii, e);
     const RngKey key = make_key(A, A.env_offset + ii);
     const int steps = kRollout ? A.k_steps : 1;
     float rsum = 0.f;
     int dcount = 0, locks = 0;
     ObsOut ob;
+    ob.row = tiles[warp] + lane * HLYNR_OBS_DIM;
     int g_row = A.g_row, o_row = A.o_row;
 #pragma unroll 1
     for (int s = 0; s < steps; ++s) {
@@ -1049,7 +1088,9 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, 4) step_kernel(const __grid_const
             act[0] = p0.x; act[1] = p0.y; act[2] = p1.x; act[3] = p1.y; act[4] = p2.x; act[5] = p2.y;
         }
         TickOut t;
-        tick_physics(A, e, key, act, t);
+        tick_physics<R, F>(A, e, key, act, t);
+        ob.emit = !kRollout || (s == steps - 1 && A.io.obs != nullptr);
+        uint4 ur = t.ur;
         bool need_reset = false;
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {  // pass 1 = in-kernel auto-reset of finished envs (one copy of observe)
@@ -1057,8 +1098,9 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, 4) step_kernel(const __grid_const
                 if (!need_reset) break;
                 e.episode += 1;
                 spawn(A, e, key);
+                ur = draw_raw(key, (uint32_t)e.episode, 0u, HLYNR_BLK_UNI);
             }
-            observe(A, e, key, ii, g_row, o_row, RingPre<R>{}, ob);
+            observe<R, F>(A, e, key, ur, ii, g_row, o_row, RingPre<R>{}, ob);
             if (pass == 0) {
                 const bool done = t.terminated || t.truncated;
                 if (ob.onboard_det) locks += 1;
@@ -1073,10 +1115,7 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, 4) step_kernel(const __grid_const
                 need_reset = done && A.auto_reset;
                 if (need_reset) {
                     dcount += 1;
-                    if (!kRollout && active && A.io.terminal_obs) {
-#pragma unroll
-                        for (int k = 0; k < HLYNR_OBS_DIM; ++k) A.io.terminal_obs[i * HLYNR_OBS_DIM + k] = ob.o[k];
-                    }
+                    if (!kRollout && active && A.io.terminal_obs) copy_obs_row(ob.row, A.io.terminal_obs + i * HLYNR_OBS_DIM);
                 }
             }
         }
@@ -1085,12 +1124,12 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, 4) step_kernel(const __grid_const
             o_row = o_row + 1 >= A.P.onb_ring_len ? 0 : o_row + 1;
         }
     }
-    if (A.io.obs) store_obs_rows(tiles[warp], ob.o, A.io.obs, warp_first, A.n, lane);
+    if (A.io.obs) flush_obs_tile(tiles[warp], A.io.obs, warp_first, A.n, lane);
     if (kRollout && active) {
         if (A.io.reward_sum) A.io.reward_sum[i] = rsum;
         if (A.io.done_count) A.io.done_count[i] = dcount;
     }
-    if (active) store_env(A, i, e);
+    if (active) store_env<R, F>(A, i, e);
     {   // onboard-lock ticks: one atomic per warp that saw a lock, spread over the stat slots
         const int wl = __reduce_add_sync(0xffffffffu, active ? locks : 0);
         if (lane == 0 && wl) atomicAdd(A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS + 13, (double)wl);
@@ -1240,8 +1279,11 @@ step_kernel_tma(const __grid_constant__ KernelArgs<float> A, const __grid_consta
         // ---- one tick + SB3 auto-reset (same device functions as the direct kernel) ----
         const RngKey key = make_key(A, A.env_offset + ii);
         TickOut t;
-        tick_physics(A, e, key, act, t);
+        tick_physics<R, FT_GENERIC>(A, e, key, act, t);
         ObsOut ob;
+        ob.row = tiles + warp * OBS_TILE + lane * HLYNR_OBS_DIM;
+        ob.emit = true;
+        uint4 ur = t.ur;
         bool need_reset = false;
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
@@ -1249,8 +1291,9 @@ step_kernel_tma(const __grid_constant__ KernelArgs<float> A, const __grid_consta
                 if (!need_reset) break;
                 e.episode += 1;
                 spawn(A, e, key);
+                ur = draw_raw(key, (uint32_t)e.episode, 0u, HLYNR_BLK_UNI);
             }
-            observe<R, true>(A, e, key, i, A.g_row, A.o_row, pre, ob);  // i < n_pad: padded lanes touch only padding
+            observe<R, FT_GENERIC, true>(A, e, key, ur, i, A.g_row, A.o_row, pre, ob);  // i < n_pad: padded lanes touch only padding
             if (pass == 0) {
                 const bool done = t.terminated || t.truncated;
                 if (active && ob.onboard_det) locks += 1;
@@ -1262,13 +1305,10 @@ step_kernel_tma(const __grid_constant__ KernelArgs<float> A, const __grid_consta
                 }
                 account_episodes(A, active, done, e, t);
                 need_reset = done && A.auto_reset;
-                if (need_reset && active && A.io.terminal_obs) {
-#pragma unroll
-                    for (int k = 0; k < HLYNR_OBS_DIM; ++k) A.io.terminal_obs[i * HLYNR_OBS_DIM + k] = ob.o[k];
-                }
+                if (need_reset && active && A.io.terminal_obs) copy_obs_row(ob.row, A.io.terminal_obs + i * HLYNR_OBS_DIM);
             }
         }
-        if (A.io.obs) store_obs_rows(tiles + warp * OBS_TILE, ob.o, A.io.obs, warp_first, A.n, lane);
+        if (A.io.obs) flush_obs_tile(tiles + warp * OBS_TILE, A.io.obs, warp_first, A.n, lane);
         if (active) store_env(A, i, e);
     }
     const int wl = __reduce_add_sync(0xffffffffu, locks);
@@ -1277,6 +1317,8 @@ step_kernel_tma(const __grid_constant__ KernelArgs<float> A, const __grid_consta
 
 // reset(): environment.py:353.  mask == NULL resets every env.
 template <typename R> __global__ void __launch_bounds__(HLYNR_BLOCK) reset_kernel(const __grid_constant__ KernelArgs<R> A) {
+    __shared__ __align__(16) float tiles[HLYNR_BLOCK / 32][OBS_TILE];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int64_t i = (int64_t)blockIdx.x * HLYNR_BLOCK + threadIdx.x;
     if (i >= A.n) return;
     if (A.io.reset_mask != nullptr && A.io.reset_mask[i] == 0) return;
@@ -1284,14 +1326,14 @@ template <typename R> __global__ void __launch_bounds__(HLYNR_BLOCK) reset_kerne
     load_env(A, i, e);
     const RngKey key = make_key(A, A.env_offset + i);
     ObsOut ob;
+    ob.row = tiles[warp] + lane * HLYNR_OBS_DIM;
+    ob.emit = true;
     e.episode += 1;
     spawn(A, e, key);
-    observe(A, e, key, i, A.g_row, A.o_row, RingPre<R>{}, ob);
+    const uint4 ur = draw_raw(key, (uint32_t)e.episode, 0u, HLYNR_BLK_UNI);
+    observe<R, FT_GENERIC>(A, e, key, ur, i, A.g_row, A.o_row, RingPre<R>{}, ob);
     store_env(A, i, e);
-    if (A.io.obs) {
-#pragma unroll
-        for (int k = 0; k < HLYNR_OBS_DIM; ++k) A.io.obs[i * HLYNR_OBS_DIM + k] = ob.o[k];
-    }
+    if (A.io.obs) copy_obs_row(ob.row, A.io.obs + i * HLYNR_OBS_DIM);
 }
 
 }  // namespace hlynr

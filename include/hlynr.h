@@ -270,7 +270,9 @@ int hlynr_debug_draws(hlynr_t* sim, int64_t env_global_id, uint32_t episode, uin
                       uint32_t block, uint32_t raw_out[4], float uniform_out[4], float normal_out[4]);
 
 /* Tuning options.  "step_kernel_variant": 0 = auto, 1 = direct kernel (one CTA per 128 envs, plane loads from
- * registers), 2 = persistent kernel whose CTAs prefetch the next tile's planes with TMA bulk copies. */
+ * registers), 2 = persistent kernel whose CTAs prefetch the next tile's planes with TMA bulk copies.
+ * "specialise": 1 (default) = use the compile-time feature-specialised step kernels when the configuration matches
+ * one (medium scenario with physics v2.0 all on / all off), 0 = always the generic kernel. */
 int hlynr_set_option(hlynr_t* sim, const char* name, int64_t value);
 
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
