@@ -214,6 +214,9 @@ struct StepIO {
     float* reward_sum;      // rollout
     int32_t* done_count;    // rollout
     double* stats;          // [STAT_SLOTS][HLYNR_STATS_WORDS]
+    HlynrDoneRecord* done_records;  // optional compact list of the episodes that finished in this call
+    int32_t* done_counter;          // records appended so far (atomic); may exceed done_cap (then the tail is dropped)
+    int32_t done_cap;
 };
 #define HLYNR_STAT_SLOTS 64
 
@@ -224,6 +227,7 @@ template <typename R> struct KernelArgs {
     StepIO io;
     RoundKeys rk;
     int64_t n;
+    int64_t first, lim;   // env range [first, lim) of this launch (host-pipelined chunks; whole shard = [0, n))
     int64_t ring_stride;  // row pitch of the ring planes (n rounded up to 32 envs)
     int64_t env_offset;
     uint32_t tick;        // global tick of this launch (rollout: tick of the first fused step)
@@ -1033,14 +1037,32 @@ template <typename R> HD void write_info(const KernelArgs<R>& A, int64_t i, cons
     if (f.fuel_remaining) f.fuel_remaining[i] = (float)e.fuel;
     if (f.fuel_used) f.fuel_used[i] = (float)e.fuel_used;
     if (f.steps) f.steps[i] = e.steps;
-    if (f.flags)
-        f.flags[i] = (uint8_t)((t.intercepted ? 1 : 0) | (t.hit ? 2 : 0) | (t.clamped ? 4 : 0) | (ob.onboard_det ? 8 : 0) |
-                               (ob.ground_det ? 16 : 0) | ((e.flags & FLAG_CROSSED) ? 32 : 0) | (t.fuze ? 64 : 0) |
-                               ((e.flags & FLAG_KF_INIT) ? 128 : 0));
+    if (f.flags) f.flags[i] = (uint8_t)info_flags(e.flags, t.intercepted, t.hit, t.clamped, ob.onboard_det, ob.ground_det, t.fuze);
     if (f.interceptor_pos) { f.interceptor_pos[3 * i] = (float)e.ipx; f.interceptor_pos[3 * i + 1] = (float)e.ipy; f.interceptor_pos[3 * i + 2] = (float)e.ipz; }
     if (f.missile_pos) { f.missile_pos[3 * i] = (float)e.mpx; f.missile_pos[3 * i + 1] = (float)e.mpy; f.missile_pos[3 * i + 2] = (float)e.mpz; }
     if (f.episode_return) f.episode_return[i] = (float)e.ep_ret;
     if (f.episode_length) f.episode_length[i] = e.steps;
+}
+
+// Appends the finished episode of env i to the compact done list (rare: ~1 per 1000 ticks per env).  Out of line
+// and fed by value so the env state never has its address taken.
+__device__ __noinline__ void append_done_record(HlynrDoneRecord* recs, int32_t* counter, int32_t cap, int32_t env, int32_t steps,
+                                                uint32_t flags, float distance, float min_d, float fuel, float fuel_used,
+                                                float ep_ret, float ix, float iy, float iz, float mx, float my, float mz,
+                                                const float* obs_row) {
+    const int32_t slot = atomicAdd(counter, 1);
+    if (slot >= cap) return;
+    HlynrDoneRecord* r = recs + slot;
+    r->env = env; r->steps = steps; r->flags = flags;
+    r->distance = distance; r->min_distance = min_d; r->fuel_remaining = fuel; r->fuel_used = fuel_used; r->episode_return = ep_ret;
+    r->interceptor_pos[0] = ix; r->interceptor_pos[1] = iy; r->interceptor_pos[2] = iz;
+    r->missile_pos[0] = mx; r->missile_pos[1] = my; r->missile_pos[2] = mz;
+#pragma unroll
+    for (int k = 0; k < HLYNR_OBS_DIM; ++k) r->terminal_obs[k] = obs_row[k];
+}
+HD uint32_t info_flags(int eflags, bool intercepted, bool hit, bool clamped, bool onboard_det, bool ground_det, bool fuze) {
+    return (uint32_t)((intercepted ? 1 : 0) | (hit ? 2 : 0) | (clamped ? 4 : 0) | (onboard_det ? 8 : 0) | (ground_det ? 16 : 0) |
+                      ((eflags & FLAG_CROSSED) ? 32 : 0) | (fuze ? 64 : 0) | ((eflags & FLAG_KF_INIT) ? 128 : 0));
 }
 
 template <typename R> HD RngKey make_key(const KernelArgs<R>& A, int64_t global_env) {
@@ -1058,13 +1080,13 @@ template <typename R> HD RngKey make_key(const KernelArgs<R>& A, int64_t global_
 // ------------------------------------------------------------------------------------------------
 // step(): one tick of every env + SB3 auto-reset.  kRollout: k fused ticks, state stays in registers.
 template <typename R, bool kRollout, int F>
-__global__ void __launch_bounds__(HLYNR_BLOCK, 4) step_kernel(const __grid_constant__ KernelArgs<R> A) {
+__global__ void __launch_bounds__(HLYNR_BLOCK, (F == FT_V2OFF && sizeof(R) == 4) ? 5 : 4) step_kernel(const __grid_constant__ KernelArgs<R> A) {
     __shared__ __align__(16) float tiles[HLYNR_BLOCK / 32][OBS_TILE];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const int64_t i = (int64_t)blockIdx.x * HLYNR_BLOCK + threadIdx.x;
+    const int64_t i = A.first + (int64_t)blockIdx.x * HLYNR_BLOCK + threadIdx.x;
     const int64_t warp_first = i - lane;
-    const bool active = i < A.n;
-    const int64_t ii = active ? i : A.n - 1;  // inactive lanes shadow the last env and never store
+    const bool active = i < A.lim;
+    const int64_t ii = active ? i : A.lim - 1;  // inactive lanes shadow the last env and never store
     Env<R> e;
     load_env<R, F>(A, ii, e);
     const RngKey key = make_key(A, A.env_offset + ii);
@@ -1112,6 +1134,12 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, 4) step_kernel(const __grid_const
                 }
                 rsum += t.reward;
                 account_episodes(A, active, done, e, t);
+                if (!kRollout && done && active && A.io.done_records)
+                    append_done_record(A.io.done_records, A.io.done_counter, A.io.done_cap, (int32_t)i, e.steps,
+                                       info_flags(e.flags, t.intercepted, t.hit, t.clamped, ob.onboard_det, ob.ground_det, t.fuze) |
+                                           (t.terminated ? HLYNR_DONE_TERMINATED : 0u) | (t.truncated ? HLYNR_DONE_TRUNCATED : 0u),
+                                       t.distance, (float)e.min_d, (float)e.fuel, (float)e.fuel_used, (float)e.ep_ret, (float)e.ipx,
+                                       (float)e.ipy, (float)e.ipz, (float)e.mpx, (float)e.mpy, (float)e.mpz, ob.row);
                 need_reset = done && A.auto_reset;
                 if (need_reset) {
                     dcount += 1;
@@ -1124,7 +1152,7 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, 4) step_kernel(const __grid_const
             o_row = o_row + 1 >= A.P.onb_ring_len ? 0 : o_row + 1;
         }
     }
-    if (A.io.obs) flush_obs_tile(tiles[warp], A.io.obs, warp_first, A.n, lane);
+    if (A.io.obs) flush_obs_tile(tiles[warp], A.io.obs, warp_first, A.lim, lane);
     if (kRollout && active) {
         if (A.io.reward_sum) A.io.reward_sum[i] = rsum;
         if (A.io.done_count) A.io.done_count[i] = dcount;
