@@ -15,7 +15,7 @@ EXPORTS = [
     "hlynr_destroy", "hlynr_num_envs", "hlynr_set_curriculum", "hlynr_get_curriculum", "hlynr_seed", "hlynr_reset",
     "hlynr_step", "hlynr_rollout", "hlynr_reset_host", "hlynr_step_host", "hlynr_pinned_buffers", "hlynr_info_host",
     "hlynr_stats_device_ptr", "hlynr_stats_reduce", "hlynr_get_stats", "hlynr_export_state", "hlynr_import_state",
-    "hlynr_debug_draws", "hlynr_launch_count", "hlynr_set_option",
+    "hlynr_debug_draws", "hlynr_launch_count", "hlynr_set_option", "hlynr_set_done_list", "hlynr_done_records_host",
 ]
 
 
@@ -65,6 +65,8 @@ def load(build_if_missing=True):
     L.hlynr_debug_draws.argtypes = [vp, i64, u32, u32, u32, vp, vp, vp]
     L.hlynr_launch_count.argtypes = [vp, C.POINTER(i64)]
     L.hlynr_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.hlynr_set_done_list.argtypes = [vp, vp, vp, C.c_int32]
+    L.hlynr_done_records_host.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int32)]
     if L.hlynr_abi_version() != abi.ABI_VERSION:
         raise HlynrError("ABI version mismatch between libhlynr_b200.so and hlynr_intercept_b200.abi")
     if L.hlynr_params_size() != C.sizeof(abi.HlynrParams):

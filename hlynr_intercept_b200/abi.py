@@ -68,6 +68,21 @@ INFO_FIELDS = [  # name, numpy dtype, trailing shape
 INFO_INTERCEPTED, INFO_HIT_TARGET, INFO_CLAMPED, INFO_RADAR_DETECTED = 0x01, 0x02, 0x04, 0x08
 INFO_GROUND_DETECTED, INFO_CROSSED, INFO_FUZE, INFO_KF_INIT = 0x10, 0x20, 0x40, 0x80
 
+DONE_TERMINATED, DONE_TRUNCATED = 0x100, 0x200
+
+
+def done_record_numpy_dtype():
+    """numpy structured dtype with the exact memory layout of HlynrDoneRecord (40 words)."""
+    import numpy as np
+
+    dt = np.dtype([("env", np.int32), ("steps", np.int32), ("flags", np.uint32), ("distance", np.float32),
+                   ("min_distance", np.float32), ("fuel_remaining", np.float32), ("fuel_used", np.float32),
+                   ("episode_return", np.float32), ("interceptor_pos", np.float32, (3,)), ("missile_pos", np.float32, (3,)),
+                   ("terminal_obs", np.float32, (OBS_DIM,))])
+    assert dt.itemsize == 160, dt.itemsize
+    return dt
+
+
 STATS_FIELDS = ["episodes", "successes", "return_sum", "length_sum", "min_distance_sum", "final_distance_sum",
                 "hit_target", "interceptor_crash", "fuel_out", "missile_ground", "worsening", "timeouts",
                 "env_steps", "onboard_locks", "reserved0", "reserved1"]

@@ -1,15 +1,22 @@
 // hlynr_capi.cu -- host side of the C ABI declared in include/hlynr.h.
 // Owns the SoA state planes, the ring planes and the statistics block of one GPU shard and launches the
 // kernels of hlynr_device.cuh.  No torch types: callers pass raw device/host pointers and a stream.
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "hlynr_device.cuh"
 
 using namespace hlynr;
+
+static_assert(sizeof(HlynrDoneRecord) == 160, "HlynrDoneRecord is 40 words (mirrored by abi.done_record_numpy_dtype)");
 
 static thread_local char g_err[512] = "";
 static int fail(const char* fmt, ...) {
@@ -35,13 +42,79 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// Staging memcpys between unpinned caller buffers and the pinned buffers: a few persistent helper threads pull
+// 1 MiB blocks off an atomic counter (a single thread copies ~10 GB/s, less than the PCIe link moves).
+class CopyPool {
+  public:
+    explicit CopyPool(int helpers) {
+        for (int k = 0; k < helpers; ++k) th_.emplace_back([this] { worker(); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    void copy(void* dst, const void* src, size_t bytes) {
+        if (bytes < (size_t(4) << 20) || th_.empty()) { memcpy(dst, src, bytes); return; }
+        {
+            std::lock_guard<std::mutex> l(m_);
+            dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes;
+            next_.store(0); busy_ = (int)th_.size(); ++gen_;
+        }
+        cv_.notify_all();
+        run_blocks();
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this] { return busy_ == 0; });
+    }
+
+  private:
+    static constexpr size_t kBlock = size_t(1) << 20;
+    void run_blocks() {
+        for (;;) {
+            const size_t b = next_.fetch_add(1);
+            const size_t off = b * kBlock;
+            if (off >= bytes_) break;
+            memcpy(dst_ + off, src_ + off, bytes_ - off < kBlock ? bytes_ - off : kBlock);
+        }
+    }
+    void worker() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+            }
+            run_blocks();
+            { std::lock_guard<std::mutex> l(m_); --busy_; }
+            done_.notify_one();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    std::atomic<size_t> next_{0};
+    char* dst_ = nullptr; const char* src_ = nullptr; size_t bytes_ = 0;
+    int busy_ = 0; uint64_t gen_ = 0; bool stop_ = false;
+};
+
+#define HLYNR_HOST_STREAMS 3
+#define HLYNR_DONE_PREFIX 4096  // records fetched together with the count; the rest (rare) in a second copy
+
 struct HostIO {  // pinned host + device staging for the *_host entry points
-    float *h_actions = nullptr, *h_obs = nullptr, *h_reward = nullptr, *h_tobs = nullptr;
+    float *h_actions = nullptr, *h_obs = nullptr, *h_reward = nullptr;
     uint8_t *h_term = nullptr, *h_trunc = nullptr, *h_mask = nullptr;
-    float *d_actions = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_tobs = nullptr;
+    float *d_actions = nullptr, *d_obs = nullptr, *d_reward = nullptr;
     uint8_t *d_term = nullptr, *d_trunc = nullptr, *d_mask = nullptr;
     HlynrInfoSoA d_info;
-    bool ready = false;
+    HlynrDoneRecord *d_records = nullptr, *h_records = nullptr;  // capacity n
+    int32_t *d_counter = nullptr, *h_count = nullptr;
+    int32_t last_count = 0;
+    cudaStream_t streams[HLYNR_HOST_STREAMS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_start = nullptr, ev_done[HLYNR_HOST_STREAMS] = {nullptr, nullptr, nullptr};
+    CopyPool* pool = nullptr;
+    bool ready = false, info_ready = false;
 };
 
 struct hlynr_sim {
@@ -65,6 +138,10 @@ struct hlynr_sim {
     int64_t xchg_cap = 0;
     cudaStream_t own_stream = nullptr;
     HostIO hio;
+    int host_info = 1, host_chunks = 0, host_threads = 0;
+    HlynrDoneRecord* done_records = nullptr;  // attached compact done list (hlynr_set_done_list)
+    int32_t* done_counter = nullptr;
+    int32_t done_cap = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -241,7 +318,8 @@ template <typename R> static KernelArgs<R> base_args(hlynr_sim* s, const StatePl
     A.P = make_kparams<R>(s->params);
     A.C = make_kcur<R>(s->cur);
     A.st = planes;
-    A.n = s->n;
+    A.n = s->n; A.first = 0; A.lim = s->n;
+    A.io.done_records = s->done_records; A.io.done_counter = s->done_counter; A.io.done_cap = s->done_cap;
     A.ring_stride = s->n_pad;
     A.env_offset = s->env_offset;
     A.rk = make_round_keys(s->seed);
@@ -269,7 +347,7 @@ static int feature_set(const HlynrParams& p) {
     return (f == FT_V2ON || f == FT_V2OFF) ? f : FT_GENERIC;
 }
 template <bool kRollout> static void launch_step_f32(const hlynr_sim* s, const KernelArgs<float>& A, cudaStream_t st, bool specialise) {
-    const int grid = grid_for(s->n, HLYNR_BLOCK);
+    const int grid = grid_for(A.lim - A.first, HLYNR_BLOCK);
     const int f = specialise ? feature_set(s->params) : FT_GENERIC;
     if (f == FT_V2ON) step_kernel<float, kRollout, FT_V2ON><<<grid, HLYNR_BLOCK, 0, st>>>(A);
     else if (f == FT_V2OFF) step_kernel<float, kRollout, FT_V2OFF><<<grid, HLYNR_BLOCK, 0, st>>>(A);
@@ -336,9 +414,16 @@ void hlynr_destroy(hlynr_t* s) {
     DeviceGuard g(s->device);
     cudaFree(s->state_mem); cudaFree(s->stats); cudaFree(s->xchg);
     HostIO& h = s->hio;
-    cudaFreeHost(h.h_actions); cudaFreeHost(h.h_obs); cudaFreeHost(h.h_reward); cudaFreeHost(h.h_tobs);
+    delete h.pool;
+    cudaFreeHost(h.h_actions); cudaFreeHost(h.h_obs); cudaFreeHost(h.h_reward); cudaFreeHost(h.h_records); cudaFreeHost(h.h_count);
     cudaFreeHost(h.h_term); cudaFreeHost(h.h_trunc); cudaFreeHost(h.h_mask);
-    cudaFree(h.d_actions); cudaFree(h.d_obs); cudaFree(h.d_reward); cudaFree(h.d_tobs); cudaFree(h.d_term); cudaFree(h.d_trunc); cudaFree(h.d_mask);
+    cudaFree(h.d_actions); cudaFree(h.d_obs); cudaFree(h.d_reward); cudaFree(h.d_records); cudaFree(h.d_counter);
+    cudaFree(h.d_term); cudaFree(h.d_trunc); cudaFree(h.d_mask);
+    for (int k = 0; k < HLYNR_HOST_STREAMS; ++k) {
+        if (h.streams[k]) cudaStreamDestroy(h.streams[k]);
+        if (h.ev_done[k]) cudaEventDestroy(h.ev_done[k]);
+    }
+    if (h.ev_start) cudaEventDestroy(h.ev_start);
     cudaFree(h.d_info.distance); cudaFree(h.d_info.min_distance); cudaFree(h.d_info.fuel_remaining); cudaFree(h.d_info.fuel_used);
     cudaFree(h.d_info.steps); cudaFree(h.d_info.flags); cudaFree(h.d_info.interceptor_pos); cudaFree(h.d_info.missile_pos);
     cudaFree(h.d_info.episode_return); cudaFree(h.d_info.episode_length);
@@ -398,6 +483,7 @@ int hlynr_num_envs(const hlynr_t* s, int64_t* out) { if (!s || !out) return fail
 int hlynr_set_curriculum(hlynr_t* s, const HlynrCurriculum* c) { if (!s || !c) return fail("null argument"); s->cur = *c; return 0; }
 int hlynr_get_curriculum(const hlynr_t* s, HlynrCurriculum* c) { if (!s || !c) return fail("null argument"); *c = s->cur; return 0; }
 int hlynr_seed(hlynr_t* s, uint64_t seed) { if (!s) return fail("null handle"); s->seed = seed; return 0; }
+static int make_pool(hlynr_sim* s);
 int hlynr_set_option(hlynr_t* s, const char* name, int64_t value) {
     if (!s || !name) return fail("null argument");
     if (strcmp(name, "step_kernel_variant") == 0) {
@@ -406,6 +492,17 @@ int hlynr_set_option(hlynr_t* s, const char* name, int64_t value) {
         return 0;
     }
     if (strcmp(name, "specialise") == 0) { s->specialise = value != 0; return 0; }
+    if (strcmp(name, "host_info") == 0) { s->host_info = value != 0; return 0; }
+    if (strcmp(name, "host_chunks") == 0) {
+        if (value < 0 || value > 64) return fail("host_chunks must be in [0, 64]");
+        s->host_chunks = (int)value;
+        return 0;
+    }
+    if (strcmp(name, "host_threads") == 0) {
+        if (value < 0 || value > 64) return fail("host_threads must be in [0, 64]");
+        s->host_threads = (int)value;
+        return s->hio.ready ? make_pool(s) : 0;
+    }
     return fail("hlynr_set_option: unknown option '%s'", name);
 }
 int hlynr_launch_count(const hlynr_t* s, int64_t* out) { if (!s || !out) return fail("null argument"); *out = s->launches; return 0; }
@@ -428,25 +525,25 @@ int hlynr_reset(hlynr_t* s, const uint8_t* mask_dev, float* obs_dev, void* strea
     return 0;
 }
 
-int hlynr_step(hlynr_t* s, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* terminated_dev,
-               uint8_t* truncated_dev, float* terminal_obs_dev, const HlynrInfoSoA* info, int auto_reset, void* stream) {
-    if (!s) return fail("hlynr_step: null handle");
-    if (!actions_dev || !obs_dev || !reward_dev || !terminated_dev || !truncated_dev) return fail("hlynr_step: null output/input pointer");
-    DeviceGuard g(s->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    s->tick += 1;
+// One tick of the envs [first, lim) (multiples of 128 except lim == n); the caller has advanced s->tick.  The
+// pointers are the [N]-sized arrays (indexed by the local env id), not chunk-relative ones.
+static int step_range(hlynr_sim* s, int64_t first, int64_t lim, const float* actions_dev, float* obs_dev, float* reward_dev,
+                      uint8_t* terminated_dev, uint8_t* truncated_dev, float* terminal_obs_dev, const HlynrInfoSoA* info,
+                      int auto_reset, cudaStream_t st) {
+    const bool whole = first == 0 && lim == s->n;
     if (s->precision == HLYNR_FP32) {
         KernelArgs<float> A = base_args<float>(s, s->pf);
+        A.first = first; A.lim = lim;
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward = reward_dev; A.io.terminated = terminated_dev;
         A.io.truncated = truncated_dev; A.io.terminal_obs = terminal_obs_dev; A.auto_reset = auto_reset;
         if (info) { A.io.info = *info; A.has_info = 1; }
-        // variant: the TMA-prefetched persistent kernel needs 16-byte aligned actions and >= a wave of tiles
-        const int64_t n_tiles = (s->n + TMA_TILE - 1) / TMA_TILE;
-        // measured on B200 (profiles/r01_c): the direct kernel is faster (the step is bound by in-warp dependency
-        // latency, not by load latency), so auto = direct; the TMA variant stays selectable and parity-tested
-        bool use_tma = s->kernel_variant == 2;
+        // measured on B200 (profiles/r01_b): the direct kernel is faster than the TMA-prefetched persistent one (the
+        // step is bound by in-warp dependency latency, not by load latency), so auto = direct; the TMA variant stays
+        // selectable and parity-tested.  It needs 16-byte aligned actions and works on the whole shard only.
+        bool use_tma = s->kernel_variant == 2 && whole;
         if (((uintptr_t)actions_dev & 15u) != 0) use_tma = false;
         if (use_tma) {
+            const int64_t n_tiles = (s->n + TMA_TILE - 1) / TMA_TILE;
             const TmaPlan T = make_tma_plan(s, A, actions_dev);
             const uint32_t smem = tma_smem_bytes(T);
             static thread_local uint32_t smem_set = 0;
@@ -462,14 +559,32 @@ int hlynr_step(hlynr_t* s, const float* actions_dev, float* obs_dev, float* rewa
         }
     } else {
         KernelArgs<double> A = base_args<double>(s, s->pd);
+        A.first = first; A.lim = lim;
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward = reward_dev; A.io.terminated = terminated_dev;
         A.io.truncated = truncated_dev; A.io.terminal_obs = terminal_obs_dev; A.auto_reset = auto_reset;
         if (info) { A.io.info = *info; A.has_info = 1; }
-        step_kernel<double, false, FT_GENERIC><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+        step_kernel<double, false, FT_GENERIC><<<grid_for(lim - first, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
     }
     CK(cudaGetLastError());
     s->launches += 1;
-    s->env_steps += (double)s->n;
+    s->env_steps += (double)(lim - first);
+    return 0;
+}
+
+int hlynr_step(hlynr_t* s, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* terminated_dev,
+               uint8_t* truncated_dev, float* terminal_obs_dev, const HlynrInfoSoA* info, int auto_reset, void* stream) {
+    if (!s) return fail("hlynr_step: null handle");
+    if (!actions_dev || !obs_dev || !reward_dev || !terminated_dev || !truncated_dev) return fail("hlynr_step: null output/input pointer");
+    DeviceGuard g(s->device);
+    s->tick += 1;
+    return step_range(s, 0, s->n, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev, info,
+                      auto_reset, (cudaStream_t)stream);
+}
+
+int hlynr_set_done_list(hlynr_t* s, HlynrDoneRecord* records_dev, int32_t* counter_dev, int32_t capacity) {
+    if (!s) return fail("hlynr_set_done_list: null handle");
+    if (records_dev && (!counter_dev || capacity <= 0)) return fail("hlynr_set_done_list: counter_dev and a positive capacity are required");
+    s->done_records = records_dev; s->done_counter = records_dev ? counter_dev : nullptr; s->done_cap = records_dev ? capacity : 0;
     return 0;
 }
 
@@ -590,27 +705,64 @@ int hlynr_debug_draws(hlynr_t* s, int64_t env_global_id, uint32_t episode, uint3
 }
 
 // ---- host-buffer entry points ----------------------------------------------------------------
+static int make_pool(hlynr_sim* s) {
+    HostIO& h = s->hio;
+    delete h.pool;
+    h.pool = nullptr;
+    int helpers = s->host_threads > 0 ? s->host_threads - 1 : 3;
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && helpers > hw - 1) helpers = hw - 1;
+    if ((size_t)s->n * 26 * sizeof(float) < (size_t(4) << 20)) helpers = 0;  // small shards never reach the pool's threshold
+    h.pool = new (std::nothrow) CopyPool(helpers);
+    if (!h.pool) return fail("out of host memory");
+    return 0;
+}
 static int ensure_hostio(hlynr_sim* s) {
     HostIO& h = s->hio;
     if (h.ready) return 0;
     const size_t n = (size_t)s->n;
     CK(cudaMallocHost(&h.h_actions, n * 6 * sizeof(float)));
     CK(cudaMallocHost(&h.h_obs, n * 26 * sizeof(float)));
-    CK(cudaMallocHost(&h.h_tobs, n * 26 * sizeof(float)));
     CK(cudaMallocHost(&h.h_reward, n * sizeof(float)));
     CK(cudaMallocHost(&h.h_term, n)); CK(cudaMallocHost(&h.h_trunc, n)); CK(cudaMallocHost(&h.h_mask, n));
+    CK(cudaMallocHost(&h.h_records, n * sizeof(HlynrDoneRecord)));
+    CK(cudaMallocHost(&h.h_count, sizeof(int32_t)));
     CK(cudaMalloc(&h.d_actions, n * 6 * sizeof(float)));
     CK(cudaMalloc(&h.d_obs, n * 26 * sizeof(float)));
-    CK(cudaMalloc(&h.d_tobs, n * 26 * sizeof(float)));
     CK(cudaMalloc(&h.d_reward, n * sizeof(float)));
     CK(cudaMalloc(&h.d_term, n)); CK(cudaMalloc(&h.d_trunc, n)); CK(cudaMalloc(&h.d_mask, n));
+    CK(cudaMalloc(&h.d_records, n * sizeof(HlynrDoneRecord)));
+    CK(cudaMalloc(&h.d_counter, sizeof(int32_t)));
+    CK(cudaMemset(h.d_counter, 0, sizeof(int32_t)));
     memset(&h.d_info, 0, sizeof(h.d_info));
+    for (int k = 0; k < HLYNR_HOST_STREAMS; ++k) {
+        CK(cudaStreamCreateWithFlags(&h.streams[k], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h.ev_done[k], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&h.ev_start, cudaEventDisableTiming));
+    if (make_pool(s)) return 1;
+    h.ready = true;
+    return 0;
+}
+// Orders the handle's own streams after the work already queued on the legacy default stream (where torch's
+// current stream normally is), so that a tensor-API call followed by a *_host call on the same handle is safe.
+// Work queued on other caller streams must be synchronised by the caller.
+static int host_streams_begin(hlynr_sim* s) {
+    HostIO& h = s->hio;
+    CK(cudaEventRecord(h.ev_start, cudaStreamLegacy));
+    for (int k = 0; k < HLYNR_HOST_STREAMS; ++k) CK(cudaStreamWaitEvent(h.streams[k], h.ev_start, 0));
+    return 0;
+}
+static int ensure_host_info(hlynr_sim* s) {
+    HostIO& h = s->hio;
+    if (h.info_ready) return 0;
+    const size_t n = (size_t)s->n;
     CK(cudaMalloc(&h.d_info.distance, n * 4)); CK(cudaMalloc(&h.d_info.min_distance, n * 4));
     CK(cudaMalloc(&h.d_info.fuel_remaining, n * 4)); CK(cudaMalloc(&h.d_info.fuel_used, n * 4));
     CK(cudaMalloc(&h.d_info.steps, n * 4)); CK(cudaMalloc(&h.d_info.flags, n));
     CK(cudaMalloc(&h.d_info.interceptor_pos, n * 12)); CK(cudaMalloc(&h.d_info.missile_pos, n * 12));
     CK(cudaMalloc(&h.d_info.episode_return, n * 4)); CK(cudaMalloc(&h.d_info.episode_length, n * 4));
-    h.ready = true;
+    h.info_ready = true;
     return 0;
 }
 
@@ -619,63 +771,102 @@ int hlynr_reset_host(hlynr_t* s, const uint8_t* mask_host, float* obs_host) {
     DeviceGuard g(s->device);
     if (ensure_hostio(s)) return 1;
     HostIO& h = s->hio;
-    cudaStream_t st = s->own_stream;
+    cudaStream_t st = h.streams[0];
     const size_t n = (size_t)s->n;
+    if (host_streams_begin(s)) return 1;
     if (mask_host) {
         memcpy(h.h_mask, mask_host, n);
         CK(cudaMemcpyAsync(h.d_mask, h.h_mask, n, cudaMemcpyHostToDevice, st));
         // rows of envs that are not reset keep the caller's content
-        if (obs_host != h.h_obs) memcpy(h.h_obs, obs_host, n * 26 * 4);
+        if (obs_host != h.h_obs) h.pool->copy(h.h_obs, obs_host, n * 26 * 4);
         CK(cudaMemcpyAsync(h.d_obs, h.h_obs, n * 26 * 4, cudaMemcpyHostToDevice, st));
     }
     if (hlynr_reset(s, mask_host ? h.d_mask : nullptr, h.d_obs, st)) return 1;
     CK(cudaMemcpyAsync(h.h_obs, h.d_obs, n * 26 * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (obs_host != h.h_obs) memcpy(obs_host, h.h_obs, n * 26 * 4);
+    if (obs_host != h.h_obs) h.pool->copy(obs_host, h.h_obs, n * 26 * 4);
     return 0;
 }
 
+// step through host buffers.  The shard is cut into chunks of whole 128-env tiles; chunk c runs
+//   H2D(actions) -> step kernel -> D2H(obs, reward, terminated, truncated)
+// on stream c % 3, so the upload of one chunk, the kernel of another and the download of a third overlap (PCIe is
+// full duplex; the download, 110 B per env, is what bounds the call).  Finished episodes come back as a compact
+// record list (count + first records in one small copy), never as [N]-sized arrays.
 int hlynr_step_host(hlynr_t* s, const float* actions_host, float* obs_host, float* reward_host, uint8_t* terminated_host,
                     uint8_t* truncated_host, float* terminal_obs_host, int auto_reset) {
     if (!s || !actions_host || !obs_host || !reward_host || !terminated_host || !truncated_host) return fail("hlynr_step_host: null argument");
     DeviceGuard g(s->device);
     if (ensure_hostio(s)) return 1;
+    if (s->host_info && ensure_host_info(s)) return 1;
     HostIO& h = s->hio;
-    cudaStream_t st = s->own_stream;
-    const size_t n = (size_t)s->n;
-    if (actions_host != h.h_actions) memcpy(h.h_actions, actions_host, n * 6 * 4);
-    CK(cudaMemcpyAsync(h.d_actions, h.h_actions, n * 6 * 4, cudaMemcpyHostToDevice, st));
-    if (hlynr_step(s, h.d_actions, h.d_obs, h.d_reward, h.d_term, h.d_trunc, terminal_obs_host ? h.d_tobs : nullptr, &h.d_info,
-                   auto_reset, st)) return 1;
-    CK(cudaMemcpyAsync(h.h_obs, h.d_obs, n * 26 * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h.h_reward, h.d_reward, n * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h.h_term, h.d_term, n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h.h_trunc, h.d_trunc, n, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (obs_host != h.h_obs) memcpy(obs_host, h.h_obs, n * 26 * 4);
-    if (reward_host != h.h_reward) memcpy(reward_host, h.h_reward, n * 4);
-    if (terminated_host != h.h_term) memcpy(terminated_host, h.h_term, n);
-    if (truncated_host != h.h_trunc) memcpy(truncated_host, h.h_trunc, n);
-    if (terminal_obs_host) {  // only rows of finished envs are meaningful; copy only if something finished
-        bool any = false;
-        for (size_t i = 0; i < n && !any; ++i) any = (h.h_term[i] | h.h_trunc[i]) != 0;
-        if (any) {
-            CK(cudaMemcpyAsync(h.h_tobs, h.d_tobs, n * 26 * 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            for (size_t i = 0; i < n; ++i)
-                if (h.h_term[i] | h.h_trunc[i]) memcpy(terminal_obs_host + i * 26, h.h_tobs + i * 26, 26 * 4);
-        }
+    const int64_t n = s->n;
+    int64_t chunks = s->host_chunks > 0 ? s->host_chunks : (n >= (int64_t(1) << 17) ? 8 : (n >= (int64_t(1) << 15) ? 4 : 1));
+    int64_t per = ((n + chunks - 1) / chunks + 127) & ~int64_t(127);
+    chunks = (n + per - 1) / per;
+    // the handle's own done list for this call (a caller-attached list is restored afterwards)
+    HlynrDoneRecord* keep_r = s->done_records; int32_t* keep_c = s->done_counter; const int32_t keep_cap = s->done_cap;
+    s->done_records = h.d_records; s->done_counter = h.d_counter; s->done_cap = (int32_t)(n < INT32_MAX ? n : INT32_MAX);
+    struct Restore { hlynr_sim* s; HlynrDoneRecord* r; int32_t* c; int32_t cap; ~Restore() { s->done_records = r; s->done_counter = c; s->done_cap = cap; } }
+        restore{s, keep_r, keep_c, keep_cap};
+    if (host_streams_begin(s)) return 1;
+    CK(cudaMemsetAsync(h.d_counter, 0, sizeof(int32_t), h.streams[0]));
+    CK(cudaEventRecord(h.ev_start, h.streams[0]));
+    for (int k = 1; k < HLYNR_HOST_STREAMS; ++k) CK(cudaStreamWaitEvent(h.streams[k], h.ev_start, 0));
+    s->tick += 1;
+    const HlynrInfoSoA* info = s->host_info ? &h.d_info : nullptr;
+    for (int64_t c = 0; c < chunks; ++c) {
+        const int64_t first = c * per, lim = first + per < n ? first + per : n, cnt = lim - first;
+        cudaStream_t st = h.streams[c % HLYNR_HOST_STREAMS];
+        if (actions_host != h.h_actions) h.pool->copy(h.h_actions + first * 6, actions_host + first * 6, (size_t)cnt * 24);
+        CK(cudaMemcpyAsync(h.d_actions + first * 6, h.h_actions + first * 6, (size_t)cnt * 24, cudaMemcpyHostToDevice, st));
+        if (step_range(s, first, lim, h.d_actions, h.d_obs, h.d_reward, h.d_term, h.d_trunc, nullptr, info, auto_reset, st)) return 1;
+        CK(cudaMemcpyAsync(h.h_obs + first * 26, h.d_obs + first * 26, (size_t)cnt * 104, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h.h_reward + first, h.d_reward + first, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h.h_term + first, h.d_term + first, (size_t)cnt, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h.h_trunc + first, h.d_trunc + first, (size_t)cnt, cudaMemcpyDeviceToHost, st));
     }
+    // done list: after every chunk's kernel; count + the first records in one go on stream 0
+    for (int k = 1; k < HLYNR_HOST_STREAMS; ++k) {
+        CK(cudaEventRecord(h.ev_done[k], h.streams[k]));
+        CK(cudaStreamWaitEvent(h.streams[0], h.ev_done[k], 0));
+    }
+    const size_t prefix = (size_t)(n < HLYNR_DONE_PREFIX ? n : HLYNR_DONE_PREFIX);
+    CK(cudaMemcpyAsync(h.h_count, h.d_counter, sizeof(int32_t), cudaMemcpyDeviceToHost, h.streams[0]));
+    CK(cudaMemcpyAsync(h.h_records, h.d_records, prefix * sizeof(HlynrDoneRecord), cudaMemcpyDeviceToHost, h.streams[0]));
+    for (int k = HLYNR_HOST_STREAMS - 1; k >= 0; --k) CK(cudaStreamSynchronize(h.streams[k]));
+    if (obs_host != h.h_obs) h.pool->copy(obs_host, h.h_obs, (size_t)n * 104);
+    if (reward_host != h.h_reward) h.pool->copy(reward_host, h.h_reward, (size_t)n * 4);
+    if (terminated_host != h.h_term) h.pool->copy(terminated_host, h.h_term, (size_t)n);
+    if (truncated_host != h.h_trunc) h.pool->copy(truncated_host, h.h_trunc, (size_t)n);
+    int32_t count = *h.h_count;
+    if (count > s->done_cap) count = s->done_cap;
+    if ((size_t)count > prefix) {
+        CK(cudaMemcpyAsync(h.h_records + prefix, h.d_records + prefix, ((size_t)count - prefix) * sizeof(HlynrDoneRecord),
+                           cudaMemcpyDeviceToHost, h.streams[0]));
+        CK(cudaStreamSynchronize(h.streams[0]));
+    }
+    h.last_count = count;
+    if (terminal_obs_host)  // only rows of finished envs are written (info['terminal_observation'])
+        for (int32_t k = 0; k < count; ++k)
+            memcpy(terminal_obs_host + (size_t)h.h_records[k].env * 26, h.h_records[k].terminal_obs, 26 * sizeof(float));
+    return 0;
+}
+
+int hlynr_done_records_host(hlynr_t* s, const HlynrDoneRecord** records, int32_t* count) {
+    if (!s || !records || !count) return fail("hlynr_done_records_host: null argument");
+    if (!s->hio.ready) return fail("hlynr_done_records_host: no hlynr_step_host call yet");
+    *records = s->hio.h_records; *count = s->hio.last_count;
     return 0;
 }
 
 int hlynr_info_host(hlynr_t* s, HlynrInfoSoA* o) {
     if (!s || !o) return fail("hlynr_info_host: null argument");
-    if (!s->hio.ready) return fail("hlynr_info_host: no hlynr_step_host call yet");
+    if (!s->hio.ready || !s->hio.info_ready) return fail("hlynr_info_host: no hlynr_step_host call with option host_info = 1 yet");
     DeviceGuard g(s->device);
     const HlynrInfoSoA& d = s->hio.d_info;
     const size_t n = (size_t)s->n;
-    cudaStream_t st = s->own_stream;
+    cudaStream_t st = s->hio.streams[0];
     if (o->distance) CK(cudaMemcpyAsync(o->distance, d.distance, n * 4, cudaMemcpyDeviceToHost, st));
     if (o->min_distance) CK(cudaMemcpyAsync(o->min_distance, d.min_distance, n * 4, cudaMemcpyDeviceToHost, st));
     if (o->fuel_remaining) CK(cudaMemcpyAsync(o->fuel_remaining, d.fuel_remaining, n * 4, cudaMemcpyDeviceToHost, st));

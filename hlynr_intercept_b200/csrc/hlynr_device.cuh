@@ -1030,6 +1030,11 @@ HD void copy_obs_row(const float* row, float* dst_row) {
     for (int k = 0; k < HLYNR_OBS_DIM; ++k) dst_row[k] = row[k];
 }
 
+HD uint32_t info_flags(int eflags, bool intercepted, bool hit, bool clamped, bool onboard_det, bool ground_det, bool fuze) {
+    return (uint32_t)((intercepted ? 1 : 0) | (hit ? 2 : 0) | (clamped ? 4 : 0) | (onboard_det ? 8 : 0) | (ground_det ? 16 : 0) |
+                      ((eflags & FLAG_CROSSED) ? 32 : 0) | (fuze ? 64 : 0) | ((eflags & FLAG_KF_INIT) ? 128 : 0));
+}
+
 template <typename R> HD void write_info(const KernelArgs<R>& A, int64_t i, const Env<R>& e, const TickOut& t, const ObsOut& ob) {
     const HlynrInfoSoA& f = A.io.info;
     if (f.distance) f.distance[i] = t.distance;
@@ -1060,11 +1065,6 @@ __device__ __noinline__ void append_done_record(HlynrDoneRecord* recs, int32_t* 
 #pragma unroll
     for (int k = 0; k < HLYNR_OBS_DIM; ++k) r->terminal_obs[k] = obs_row[k];
 }
-HD uint32_t info_flags(int eflags, bool intercepted, bool hit, bool clamped, bool onboard_det, bool ground_det, bool fuze) {
-    return (uint32_t)((intercepted ? 1 : 0) | (hit ? 2 : 0) | (clamped ? 4 : 0) | (onboard_det ? 8 : 0) | (ground_det ? 16 : 0) |
-                      ((eflags & FLAG_CROSSED) ? 32 : 0) | (fuze ? 64 : 0) | ((eflags & FLAG_KF_INIT) ? 128 : 0));
-}
-
 template <typename R> HD RngKey make_key(const KernelArgs<R>& A, int64_t global_env) {
     RngKey k;
     k.rk = &A.rk;
@@ -1122,7 +1122,9 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, (F == FT_V2OFF && sizeof(R) == 4)
                 spawn(A, e, key);
                 ur = draw_raw(key, (uint32_t)e.episode, 0u, HLYNR_BLK_UNI);
             }
-            observe<R, F>(A, e, key, ur, ii, g_row, o_row, RingPre<R>{}, ob);
+            // ring planes are indexed by the lane's OWN (padded) slot: a shadow lane of another warp may run ticks
+            // ahead in a fused rollout and must never touch the rows of the env it shadows
+            observe<R, F>(A, e, key, ur, i, g_row, o_row, RingPre<R>{}, ob);
             if (pass == 0) {
                 const bool done = t.terminated || t.truncated;
                 if (ob.onboard_det) locks += 1;

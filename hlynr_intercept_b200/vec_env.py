@@ -10,7 +10,9 @@ infos[i] = {..., 'terminal_observation', 'TimeLimit.truncated', 'episode': {'r',
 If stable_baselines3 / gymnasium are importable the class subclasses the real `VecEnv` and uses real
 `spaces.Box`; otherwise it is duck-typed (neither package exists in the build image).
 """
+import collections.abc
 import ctypes as C
+import itertools
 import time
 
 import numpy as np
@@ -84,6 +86,45 @@ class _ObservationGeneratorView:
         return self._v.sim.curriculum.noise_level
 
 
+class LazyInfos(collections.abc.Sequence):
+    """`infos` of one step for a large batch: a read-only sequence of length num_envs whose entry i is the
+    reference's info dict (+ the SB3 done keys) when env i finished an episode in this step, materialised on first
+    access and cached (so wrappers that patch infos[i]['terminal_observation'] in place keep working), and one shared
+    empty dict otherwise.  Creating it is O(1) Python work; vectorised consumers read `.records` (structured array,
+    abi.done_record_numpy_dtype) and `.done_indices` instead of touching dicts at all."""
+
+    def __init__(self, venv, records, now):
+        self._venv, self.records, self._now = venv, records, now
+        self._n = venv.num_envs
+        self._index = None
+        self._cache = {}
+
+    @property
+    def done_indices(self):
+        return self.records["env"]
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(self._n))]
+        i = int(i)
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        if self._index is None:
+            self._index = {e: k for k, e in enumerate(self.records["env"].tolist())}
+        k = self._index.get(i)
+        if k is None:
+            return self._venv._shared_info
+        d = self._cache.get(k)
+        if d is None:
+            d = self._cache[k] = self._venv._done_info_dicts(self.records[k:k + 1], self._now)[0]
+        return d
+
+
 class HlynrVecEnv(_VecEnvBase):
     def __init__(self, env_cfg=None, n_envs=1, device=0, seed=1234, env_id_offset=0, precision="fp32", warn_dead=True,
                  lazy_infos=None, copy_outputs=None):
@@ -110,9 +151,10 @@ class HlynrVecEnv(_VecEnvBase):
         self._rew = view(ptrs[2], (n,), C.c_float, np.float32)
         self._term = view(ptrs[3], (n,), C.c_uint8, np.uint8)
         self._trunc = view(ptrs[4], (n,), C.c_uint8, np.uint8)
-        self._tobs = np.zeros((n, 26), np.float32)
-        self._info = {nm: np.zeros((n,) + shp, dtype=dt) for nm, dt, shp in abi.INFO_FIELDS}
-        self._info_struct = abi.HlynrInfoSoA(**{nm: self._info[nm].ctypes.data for nm, _, _ in abi.INFO_FIELDS})
+        self._info = None           # [N]-sized info arrays, only in the eager (small-n) mode
+        self._info_struct = None
+        self.sim.set_option("host_info", 0 if self.lazy_infos else 1)
+        self._rec_dtype = abi.done_record_numpy_dtype()
         self._t_start = time.time()
         self._shared_info = {}
         self._pending = None
@@ -122,64 +164,95 @@ class HlynrVecEnv(_VecEnvBase):
     # ---- VecEnv API -----------------------------------------------------------------------------------
     def reset(self):
         _lib.check(self.sim.L.hlynr_reset_host(self.sim.h, None, self._obs.ctypes.data_as(C.c_void_p)))
-        self.reset_infos = [{} for _ in range(self.num_envs)] if not self.lazy_infos else [self._shared_info] * self.num_envs
+        self.reset_infos = ([{} for _ in range(self.num_envs)] if not self.lazy_infos
+                            else LazyInfos(self, np.zeros(0, dtype=self._rec_dtype), 0.0))
         return self._obs.copy() if self.copy_outputs else self._obs
 
     def step_async(self, actions):
         a = np.asarray(actions, dtype=np.float32)  # other callers pass float64 zeros (helpers/check_missile_trajectory.py:58)
         if a.shape != (self.num_envs, 6):
             a = a.reshape(self.num_envs, 6)
-        np.copyto(self._act, a)
-        self._pending = True
+        if not a.flags.c_contiguous:
+            np.copyto(self._act, a)
+            a = self._act
+        self._pending = a   # C-contiguous float32: staged chunk by chunk inside hlynr_step_host, overlapped with the copies
 
     def step_wait(self):
-        assert self._pending, "step_wait() without step_async()"
-        self._pending = None
+        assert self._pending is not None, "step_wait() without step_async()"
+        a, self._pending = self._pending, None
         p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
-        _lib.check(self.sim.L.hlynr_step_host(self.sim.h, p(self._act), p(self._obs), p(self._rew), p(self._term),
-                                              p(self._trunc), p(self._tobs), 1))
-        dones = (self._term | self._trunc).astype(bool)
-        infos = self._build_infos(dones)
+        _lib.check(self.sim.L.hlynr_step_host(self.sim.h, p(a), p(self._obs), p(self._rew), p(self._term),
+                                              p(self._trunc), None, 1))
+        dones = np.logical_or(self._term, self._trunc)
+        infos = self._build_infos()
         if self.copy_outputs:
             return self._obs.copy(), self._rew.copy(), dones, infos
         return self._obs, self._rew, dones, infos
 
-    def _build_infos(self, dones):
+    def done_records(self):
+        """Finished episodes of the last step as a structured array (abi.done_record_numpy_dtype), a view of pinned
+        memory owned by the C library that the next step overwrites."""
+        ptr, cnt = C.c_void_p(), C.c_int32()
+        _lib.check(self.sim.L.hlynr_done_records_host(self.sim.h, C.byref(ptr), C.byref(cnt)))
+        if cnt.value == 0:
+            return np.zeros(0, dtype=self._rec_dtype)
+        buf = (C.c_char * (cnt.value * self._rec_dtype.itemsize)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=self._rec_dtype, count=cnt.value)
+
+    _INFO_KEYS = ("distance", "intercepted", "missile_hit_target", "fuel_remaining", "fuel_used", "clamped", "missile_pos",
+                  "interceptor_pos", "steps", "radar_detected", "radar_quality", "ground_radar_detected", "volley_mode",
+                  "volley_size", "missiles_intercepted", "missiles_remaining", "missile_min_distances", "min_distance",
+                  "crossed_threshold", "precision_mode", "proximity_fuze_enabled", "proximity_fuze_triggered",
+                  "proximity_kill_radius")
+
+    def _info_dicts(self, fl, distance, min_distance, fuel_remaining, fuel_used, steps, missile_pos, interceptor_pos, extra=None):
+        """The reference's info dict, environment.py:829-857 (single-missile mode), for a batch of envs given as
+        arrays.  All conversions are vectorised; the per-env Python work is one dict(zip(keys, row)).
+        extra: (terminal_obs[k,26], truncated_only list, episode dicts) appended as the SB3 done keys."""
+        P = self.sim.params
+        fl = np.asarray(fl).astype(np.int64)
+        m = len(fl)
+        bit = lambda mask: ((fl & mask) != 0).tolist()  # noqa: E731
+        hit = (fl & abi.INFO_INTERCEPTED) != 0
+        dist = np.asarray(distance).tolist()
+        rep = itertools.repeat
+        cols = [dist, hit.tolist(), bit(abi.INFO_HIT_TARGET), np.asarray(fuel_remaining).tolist(), np.asarray(fuel_used).tolist(),
+                bit(abi.INFO_CLAMPED), list(np.array(missile_pos, dtype=np.float32)), list(np.array(interceptor_pos, dtype=np.float32)),
+                np.asarray(steps).tolist(), bit(abi.INFO_RADAR_DETECTED), rep(float(P.radar_quality), m), bit(abi.INFO_GROUND_DETECTED),
+                rep(False, m), rep(1, m), hit.astype(np.int64).tolist(), (1 - hit.astype(np.int64)).tolist(), [[d] for d in dist],
+                np.asarray(min_distance).tolist(), bit(abi.INFO_CROSSED), rep(bool(P.precision_mode), m), rep(bool(P.fuze_enabled), m),
+                bit(abi.INFO_FUZE), rep(float(P.kill_radius), m)]
+        keys = self._INFO_KEYS
+        if extra is not None:
+            keys = keys + ("terminal_observation", "TimeLimit.truncated", "episode")
+            cols += [list(extra[0]), extra[1], extra[2]]
+        return [dict(zip(keys, row)) for row in zip(*cols)]
+
+    def _done_info_dicts(self, rec, now):
+        fl = rec["flags"]
+        tl = (((fl & abi.DONE_TRUNCATED) != 0) & ((fl & abi.DONE_TERMINATED) == 0)).tolist()
+        ret, ln = rec["episode_return"].astype(np.float64).round(6).tolist(), rec["steps"].tolist()
+        episodes = [{"r": r, "l": l, "t": now} for r, l in zip(ret, ln)]
+        return self._info_dicts(fl, rec["distance"], rec["min_distance"], rec["fuel_remaining"], rec["fuel_used"],
+                                rec["steps"], rec["missile_pos"], rec["interceptor_pos"],
+                                extra=(rec["terminal_obs"].copy(), tl, episodes))
+
+    def _build_infos(self):
         n = self.num_envs
-        idx_done = np.nonzero(dones)[0]
-        if self.lazy_infos and idx_done.size == 0:
-            return [self._shared_info] * n
+        rec = self.done_records()
+        now = round(time.time() - self._t_start, 6)
+        if self.lazy_infos:
+            return LazyInfos(self, rec.copy(), now)
+        if self._info is None:
+            self._info = {nm: np.zeros((n,) + shp, dtype=dt) for nm, dt, shp in abi.INFO_FIELDS}
+            self._info_struct = abi.HlynrInfoSoA(**{nm: self._info[nm].ctypes.data for nm, _, _ in abi.INFO_FIELDS})
         _lib.check(self.sim.L.hlynr_info_host(self.sim.h, C.byref(self._info_struct)))
         f = self._info
-        if self.lazy_infos:
-            infos = [self._shared_info] * n
-            todo = idx_done
-        else:
-            infos = [None] * n
-            todo = range(n)
-        P = self.sim.params
-        for i in todo:
-            fl = int(f["flags"][i])
-            d = {
-                "distance": float(f["distance"][i]), "intercepted": bool(fl & abi.INFO_INTERCEPTED),
-                "missile_hit_target": bool(fl & abi.INFO_HIT_TARGET), "fuel_remaining": float(f["fuel_remaining"][i]),
-                "fuel_used": float(f["fuel_used"][i]), "clamped": bool(fl & abi.INFO_CLAMPED),
-                "missile_pos": f["missile_pos"][i].copy(), "interceptor_pos": f["interceptor_pos"][i].copy(),
-                "steps": int(f["steps"][i]), "radar_detected": bool(fl & abi.INFO_RADAR_DETECTED),
-                "radar_quality": float(P.radar_quality), "ground_radar_detected": bool(fl & abi.INFO_GROUND_DETECTED),
-                "volley_mode": False, "volley_size": 1, "missiles_intercepted": int(bool(fl & abi.INFO_INTERCEPTED)),
-                "missiles_remaining": 0 if fl & abi.INFO_INTERCEPTED else 1,
-                "missile_min_distances": [float(f["distance"][i])], "min_distance": float(f["min_distance"][i]),
-                "crossed_threshold": bool(fl & abi.INFO_CROSSED), "precision_mode": bool(P.precision_mode),
-                "proximity_fuze_enabled": bool(P.fuze_enabled), "proximity_fuze_triggered": bool(fl & abi.INFO_FUZE),
-                "proximity_kill_radius": float(P.kill_radius),
-            }
-            if dones[i]:
-                d["terminal_observation"] = self._tobs[i].copy()
-                d["TimeLimit.truncated"] = bool(self._trunc[i] and not self._term[i])
-                d["episode"] = {"r": round(float(f["episode_return"][i]), 6), "l": int(f["episode_length"][i]),
-                                "t": round(time.time() - self._t_start, 6)}
-            infos[i] = d
+        infos = self._info_dicts(f["flags"], f["distance"], f["min_distance"], f["fuel_remaining"], f["fuel_used"],
+                                 f["steps"], f["missile_pos"], f["interceptor_pos"])
+        if len(rec):
+            for i, d in zip(rec["env"].tolist(), self._done_info_dicts(rec, now)):
+                infos[i] = d
         return infos
 
     def close(self):

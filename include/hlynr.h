@@ -159,6 +159,25 @@ typedef struct HlynrInfoSoA {
 #define HLYNR_INFO_FUZE 0x40
 #define HLYNR_INFO_KF_INIT 0x80
 
+/*
+ * One finished episode (done = terminated | truncated), appended by hlynr_step to an optional compact list so that
+ * a VecEnv with many envs fetches `count` small records instead of [N]-sized info / terminal-observation arrays.
+ * Fields = the reference's info dict on the terminal tick (environment.py:829-857) + what SB3 adds on done
+ * (info['terminal_observation'], info['TimeLimit.truncated'], Monitor's info['episode']).  The order of the
+ * records within one call is unspecified (sort by `env` if needed).
+ */
+typedef struct HlynrDoneRecord {
+    int32_t env;             /* local env index */
+    int32_t steps;           /* info['steps'] == Monitor 'l' */
+    uint32_t flags;          /* HLYNR_INFO_* bits | HLYNR_DONE_TERMINATED | HLYNR_DONE_TRUNCATED */
+    float distance, min_distance, fuel_remaining, fuel_used;
+    float episode_return;    /* Monitor 'r' */
+    float interceptor_pos[3], missile_pos[3];
+    float terminal_obs[HLYNR_OBS_DIM];
+} HlynrDoneRecord;           /* 40 words = 160 bytes */
+#define HLYNR_DONE_TERMINATED 0x100u
+#define HLYNR_DONE_TRUNCATED 0x200u
+
 /* Episode statistics accumulated on the device since the last reset of the block (per handle). */
 typedef struct HlynrStats {
     double episodes;          /* finished episodes (terminated or truncated) */
@@ -233,6 +252,11 @@ int hlynr_step(hlynr_t* sim, const float* actions_dev, float* obs_dev, float* re
                uint8_t* terminated_dev, uint8_t* truncated_dev, float* terminal_obs_dev,
                const HlynrInfoSoA* info, int auto_reset, void* stream);
 
+/* Attaches (records_dev != NULL) or detaches the compact done list used by subsequent hlynr_step calls:
+ * records_dev HlynrDoneRecord[capacity], counter_dev int32 (appended count; the CALLER zeroes it, it may end above
+ * `capacity`, in which case the excess records were dropped). */
+int hlynr_set_done_list(hlynr_t* sim, HlynrDoneRecord* records_dev, int32_t* counter_dev, int32_t capacity);
+
 /* k fused ticks in ONE launch with the state held in registers between ticks.
  *   actions_dev  float[k,N,6] or NULL = in-kernel random actions U(-1,1)^6 from the Philox
  *                stream (synthetic random-policy rollouts)
@@ -247,6 +271,9 @@ int hlynr_reset_host(hlynr_t* sim, const uint8_t* mask_host, float* obs_host);
 int hlynr_step_host(hlynr_t* sim, const float* actions_host, float* obs_host, float* reward_host,
                     uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host,
                     int auto_reset);
+/* Finished episodes of the last hlynr_step_host call: pointer to `*count` records in pinned host memory owned by
+ * the handle (valid until the next call on the handle). */
+int hlynr_done_records_host(hlynr_t* sim, const HlynrDoneRecord** records, int32_t* count);
 /* Pinned host buffers owned by the handle: float[N,6], float[N,26], float[N], uint8[N], uint8[N].  Passing
  * these very pointers to hlynr_step_host / hlynr_reset_host skips the staging memcpy. */
 int hlynr_pinned_buffers(hlynr_t* sim, float** actions, float** obs, float** reward, uint8_t** terminated,
@@ -272,7 +299,11 @@ int hlynr_debug_draws(hlynr_t* sim, int64_t env_global_id, uint32_t episode, uin
 /* Tuning options.  "step_kernel_variant": 0 = auto, 1 = direct kernel (one CTA per 128 envs, plane loads from
  * registers), 2 = persistent kernel whose CTAs prefetch the next tile's planes with TMA bulk copies.
  * "specialise": 1 (default) = use the compile-time feature-specialised step kernels when the configuration matches
- * one (medium scenario with physics v2.0 all on / all off), 0 = always the generic kernel. */
+ * one (medium scenario with physics v2.0 all on / all off), 0 = always the generic kernel.
+ * "host_info": 1 (default) = hlynr_step_host also fills the [N]-sized info arrays read by hlynr_info_host, 0 = skip them
+ * (finished episodes are still reported through hlynr_done_records_host).
+ * "host_chunks": number of chunks hlynr_step_host pipelines (H2D | kernel | D2H on separate streams), 0 = auto.
+ * "host_threads": threads used for staging memcpys of unpinned caller buffers, 0 = auto. */
 int hlynr_set_option(hlynr_t* sim, const char* name, int64_t value);
 
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */

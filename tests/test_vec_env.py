@@ -106,5 +106,84 @@ def test_lazy_infos_large_batch():
     v = make(8192, lazy_infos=True, copy_outputs=False)
     v.reset()
     obs, rew, dones, infos = v.step(np.zeros((8192, 6), np.float32))
-    assert len(infos) == 8192 and infos[0] is infos[1] and not dones.any()
+    assert len(infos) == 8192 and infos[0] is infos[1] and not dones.any() and len(infos.records) == 0
     v.close()
+
+
+def test_host_pipeline_is_bit_identical_to_the_device_api_and_reports_done_records():
+    """hlynr_step_host pipelines the shard in chunks over three streams (H2D | kernel | D2H) and returns finished
+    episodes as compact records: obs / reward / done flags must equal the single-launch device API bit for bit
+    (chunking invariance), and every record must equal the [N]-sized info arrays and terminal observation rows."""
+    import torch
+
+    from hlynr_intercept_b200.sim import HlynrSim
+    from hlynr_intercept_b200 import abi
+
+    n = 40001  # not a multiple of 128: ragged last chunk
+    ref = HlynrSim(config.baseline_config("cfg4"), n_envs=n, seed=77, warn_dead=False)
+    v = make(n, lazy_infos=True, copy_outputs=False)
+    v.seed(77)
+    v.sim.set_option("host_chunks", 5)
+    ref.reset(); v.reset()
+    ref.rollout(850, None); v.sim.rollout(850, None)  # age the episodes with the in-kernel random policy (same streams)
+    rng = np.random.default_rng(3)
+    total_done = 0
+    for t in range(120):
+        a = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        o, r, te, tr, tobs, info = ref.step(torch.as_tensor(a).cuda(), want_info=True)
+        obs, rew, dones, infos = v.step(a)
+        assert (obs == o.cpu().numpy()).all() and (rew == r.cpu().numpy()).all(), t
+        want_done = (te | tr).cpu().numpy().astype(bool)
+        assert (dones == want_done).all(), t
+        rec = np.sort(infos.records, order="env")
+        idx = np.nonzero(want_done)[0]
+        assert (rec["env"] == idx).all(), t
+        total_done += len(idx)
+        if len(idx) == 0:
+            continue
+        inf = {k: x.cpu().numpy() for k, x in info.items()}
+        assert (rec["terminal_obs"] == tobs.cpu().numpy()[idx]).all()
+        for name in ("distance", "min_distance", "fuel_remaining", "fuel_used", "steps", "episode_return"):
+            assert (rec[name] == inf[name][idx]).all(), name
+        assert ((rec["flags"] & 0xff) == inf["flags"][idx]).all()
+        assert (((rec["flags"] & abi.DONE_TERMINATED) != 0) == te.cpu().numpy()[idx].astype(bool)).all()
+        assert (rec["missile_pos"] == inf["missile_pos"][idx]).all() and (rec["interceptor_pos"] == inf["interceptor_pos"][idx]).all()
+        i = int(idx[0])  # lazily materialised dict of a finished env; others alias the shared empty dict
+        d = infos[i]
+        assert d["steps"] == int(inf["steps"][i]) and d["episode"]["l"] == d["steps"] and "terminal_observation" in d
+        assert d is infos[i] and len(infos) == n
+        other = int(np.nonzero(~want_done)[0][0])
+        assert infos[other] == {}
+    assert total_done > 50
+    ref.close(); v.close()
+
+
+def test_step_host_with_unpinned_buffers_and_terminal_rows():
+    """The plain C-ABI call with caller-owned (unpinned) numpy buffers: staging copies + terminal rows scattered from
+    the done records."""
+    import ctypes as C
+
+    from hlynr_intercept_b200 import _lib
+
+    n = 3000
+    a_env, b_env = make(n), make(n)
+    a_env.reset(); b_env.reset()
+    a_env.sim.rollout(900, None); b_env.sim.rollout(900, None)
+    rng = np.random.default_rng(5)
+    obs, rew = np.zeros((n, 26), np.float32), np.zeros(n, np.float32)
+    te, tr = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    tobs = np.full((n, 26), np.nan, np.float32)
+    p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+    seen = 0
+    for t in range(200):
+        act = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        _lib.check(b_env.sim.L.hlynr_step_host(b_env.sim.h, p(act), p(obs), p(rew), p(te), p(tr), p(tobs), 1))
+        o2, r2, d2, infos = a_env.step(act)
+        np.testing.assert_array_equal(o2, obs, err_msg=f"tick {t}")
+        np.testing.assert_array_equal(r2, rew)
+        np.testing.assert_array_equal(d2, (te | tr) != 0)
+        for i in np.nonzero(d2)[0]:
+            assert (infos[i]["terminal_observation"] == tobs[i]).all()
+            seen += 1
+    assert seen > 5 and np.isnan(tobs).any()
+    a_env.close(); b_env.close()
