@@ -173,7 +173,7 @@ template <typename R> static KParams<R> make_kparams(const HlynrParams& p) {
     }
     k.radar_range = (float)p.radar_range; k.rc_radar_range = (float)(1.0 / p.radar_range);
     k.radar_quality = (float)p.radar_quality; k.radar_quality_d = p.radar_quality;
-    k.rc_max_velocity_f = (float)(1.0 / p.max_velocity);
+    k.rc_max_velocity_f = (float)(1.0 / p.max_velocity); k.rc_max_range_f = (float)(1.0 / p.max_range);
     k.g_max_range = (float)p.g_max_range; k.rc_g_max_range = (float)(1.0 / p.g_max_range);
     // elevation gates asin(s) < min_el / > max_el (core.py:402-406) as thresholds on s itself
     k.g_sin_min_el = (float)sin(p.g_min_el); k.g_sin_max_el = (float)sin(p.g_max_el);
@@ -334,6 +334,7 @@ static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) 
 
 // Feature set of a resolved configuration; a specialised instantiation exists for FT_V2ON and FT_V2OFF.
 static int feature_set(const HlynrParams& p) {
+    if (p.obs_mode != HLYNR_OBS_WORLD) return FT_GENERIC_MODES;
     if (p.dr_enabled || p.precision_mode || p.fuze_enabled) return FT_GENERIC;
     int f = 0;
     if (p.isa_enabled) f |= FT_ISA;
@@ -348,9 +349,11 @@ static int feature_set(const HlynrParams& p) {
 }
 template <bool kRollout> static void launch_step_f32(const hlynr_sim* s, const KernelArgs<float>& A, cudaStream_t st, bool specialise) {
     const int grid = grid_for(A.lim - A.first, HLYNR_BLOCK);
-    const int f = specialise ? feature_set(s->params) : FT_GENERIC;
+    int f = feature_set(s->params);
+    if (!specialise && f >= 0) f = FT_GENERIC;
     if (f == FT_V2ON) step_kernel<float, kRollout, FT_V2ON><<<grid, HLYNR_BLOCK, 0, st>>>(A);
     else if (f == FT_V2OFF) step_kernel<float, kRollout, FT_V2OFF><<<grid, HLYNR_BLOCK, 0, st>>>(A);
+    else if (f == FT_GENERIC_MODES) step_kernel<float, kRollout, FT_GENERIC_MODES><<<grid, HLYNR_BLOCK, 0, st>>>(A);
     else step_kernel<float, kRollout, FT_GENERIC><<<grid, HLYNR_BLOCK, 0, st>>>(A);
 }
 
@@ -437,7 +440,8 @@ int hlynr_create(const HlynrParams* p, int64_t n_envs, int device, uint64_t seed
     if (p->abi_version != HLYNR_ABI_VERSION) return fail("hlynr_create: params.abi_version %d != %d", p->abi_version, HLYNR_ABI_VERSION);
     if (n_envs <= 0) return fail("hlynr_create: n_envs must be positive");
     if (precision != HLYNR_FP32 && precision != HLYNR_FP64) return fail("hlynr_create: precision must be 32 or 64");
-    if (p->obs_mode != HLYNR_OBS_WORLD) return fail("hlynr_create: observation_mode other than world_frame is not implemented yet");
+    if (p->obs_mode != HLYNR_OBS_WORLD && p->obs_mode != HLYNR_OBS_BODY && p->obs_mode != HLYNR_OBS_LOS)
+        return fail("hlynr_create: unknown observation_mode %d", p->obs_mode);
     if (p->onboard_delay < 0 || p->onboard_delay > HLYNR_MAX_ONBOARD_DELAY) return fail("hlynr_create: onboard_delay out of range");
     if (p->ground_delay < 0 || p->ground_delay > HLYNR_MAX_GROUND_DELAY) return fail("hlynr_create: ground_delay out of range");
     int ndev = 0;
@@ -563,7 +567,10 @@ static int step_range(hlynr_sim* s, int64_t first, int64_t lim, const float* act
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward = reward_dev; A.io.terminated = terminated_dev;
         A.io.truncated = truncated_dev; A.io.terminal_obs = terminal_obs_dev; A.auto_reset = auto_reset;
         if (info) { A.io.info = *info; A.has_info = 1; }
-        step_kernel<double, false, FT_GENERIC><<<grid_for(lim - first, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+        if (s->params.obs_mode != HLYNR_OBS_WORLD)
+            step_kernel<double, false, FT_GENERIC_MODES><<<grid_for(lim - first, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+        else
+            step_kernel<double, false, FT_GENERIC><<<grid_for(lim - first, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
     }
     CK(cudaGetLastError());
     s->launches += 1;
@@ -607,7 +614,10 @@ int hlynr_rollout(hlynr_t* s, int k_steps, const float* actions_dev, float* obs_
         A.g_row = A.P.gnd_ring_len > 0 ? (int32_t)(A.tick % (uint32_t)A.P.gnd_ring_len) : 0;
         A.o_row = A.P.onb_ring_len > 0 ? (int32_t)(A.tick % (uint32_t)A.P.onb_ring_len) : 0;
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward_sum = reward_sum_dev; A.io.done_count = done_count_dev;
-        step_kernel<double, true, FT_GENERIC><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+        if (s->params.obs_mode != HLYNR_OBS_WORLD)
+            step_kernel<double, true, FT_GENERIC_MODES><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+        else
+            step_kernel<double, true, FT_GENERIC><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
     }
     CK(cudaGetLastError());
     s->tick += (uint32_t)k_steps;

@@ -147,7 +147,7 @@ template <typename R> struct KParams {
     double dt_d;        // dt as the Python float it is in the reference
     double radar_quality_d, gust_scale_d;
     // ---- float context (observation geometry) ----
-    float radar_range, rc_radar_range, radar_quality, rc_max_velocity_f;
+    float radar_range, rc_radar_range, radar_quality, rc_max_velocity_f, rc_max_range_f;
     float gpos[3], g_max_range, rc_g_max_range, g_sin_min_el, g_sin_max_el, g_base_q, max_link, rc_max_link, pkt_loss;
     float dtf, q_pp, q_pv, q_vv;  // Kalman F/Q entries (float32 matrices, core.py:33-56)
     float fus_035q;
@@ -168,7 +168,8 @@ template <typename R> struct KParams {
 // specialised instantiation when the resolved configuration matches one, else the generic kernel.
 // ------------------------------------------------------------------------------------------------
 enum { FT_ISA = 1, FT_MACH = 2, FT_ENHW = 4, FT_THRUST = 8, FT_ONBD = 16, FT_GROUND = 32, FT_GDELAY = 64, FT_EVADE = 128 };
-#define FT_GENERIC (-1)
+#define FT_GENERIC (-1)        /* every switch at run time, world_frame observations */
+#define FT_GENERIC_MODES (-2)  /* the same + observation_mode body_frame / los_frame (and the LOS action transform) */
 #define FT_V2ON (FT_ISA | FT_MACH | FT_ENHW | FT_THRUST | FT_ONBD | FT_GROUND | FT_GDELAY | FT_EVADE)  /* cfg4: medium, v2.0 on */
 #define FT_V2OFF (FT_GROUND | FT_GDELAY | FT_EVADE)                                                   /* cfg2: medium, v2.0 off */
 template <int F> struct Feat {
@@ -185,6 +186,7 @@ template <int F> struct Feat {
     template <typename P> static HD bool dr(const P& p) { if constexpr (F < 0) return p.dr != 0; else return false; }
     template <typename P> static HD bool precision_mode(const P& p) { if constexpr (F < 0) return p.precision_mode != 0; else return false; }
     template <typename P> static HD bool fuze(const P& p) { if constexpr (F < 0) return p.fuze != 0; else return false; }
+    template <typename P> static HD int obs_mode(const P& p) { if constexpr (F == FT_GENERIC_MODES) return p.obs_mode; else return HLYNR_OBS_WORLD; }
 };
 
 template <typename R> struct KCurriculum {
@@ -362,6 +364,20 @@ template <typename R> HD R nan_guard(R a, R lim) {  // np.nan_to_num(nan=0, posi
     if (a != a) return R(0);
     if (isinf(a)) return a > R(0) ? lim : -lim;
     return a;
+}
+
+// The LOS basis shared by the observation (core.py:803-845, :929-945) and the action transform
+// (environment.py:965-1020): lu = rel/|rel|, lh = normalize(lu x world_up) = (lu.y, -lu.x, 0)/n, lv = lu x lh.
+template <typename T> struct LosBasis { T ux, uy, uz, hx, hy, vx, vy, vz; };  // lh.z == 0
+template <typename T> HD LosBasis<T> los_basis_near(T px, T py, T pz, T rr) {
+    LosBasis<T> b;
+    if (rr > T(1e-6)) { const T ir = nrcp(rr); b.ux = px * ir; b.uy = py * ir; b.uz = pz * ir; }
+    else { b.ux = T(1); b.uy = T(0); b.uz = T(0); }
+    const T n = nsqrt(b.ux * b.ux + b.uy * b.uy);
+    if (n > T(1e-6)) { const T in = nrcp(n); b.hx = b.uy * in; b.hy = -b.ux * in; }
+    else { b.hx = T(1); b.hy = T(0); }
+    b.vx = -(b.uz * b.hy); b.vy = b.uz * b.hx; b.vz = b.ux * b.hy - b.uy * b.hx;
+    return b;
 }
 
 // Observation sink: channel k of this lane's row goes straight into the warp's shared-memory tile (row pitch 26
@@ -549,17 +565,55 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
     }
     e.flags = (e.flags & ~FLAG_KF_INIT) | (kf_init ? FLAG_KF_INIT : 0);
 
+    const int mode = FT::obs_mode(P);
+    LosBasis<W> lb;
+    bool have_los = false;
+    struct { float rx, ry, rz, ux, uy, uz; } bx;  // body right / up axes (core.py:1155-1176), body_frame only
+    if (mode == HLYNR_OBS_BODY) {
+        const float w = e.qw, x = e.qx, y = e.qy, z = e.qz;
+        float a = 1.f - 2.f * fmaf(y, y, z * z), b = 2.f * fmaf(x, y, w * z), c = 2.f * fmaf(x, z, -(w * y));
+        float inv = nrcp(nnorm3(a, b, c) + 1e-6f);
+        bx.rx = a * inv; bx.ry = b * inv; bx.rz = c * inv;
+        a = 2.f * fmaf(x, y, -(w * z)); b = 1.f - 2.f * fmaf(x, x, z * z); c = 2.f * fmaf(y, z, w * x);
+        inv = nrcp(nnorm3(a, b, c) + 1e-6f);
+        bx.ux = a * inv; bx.uy = b * inv; bx.uz = c * inv;
+    }
     if (kf_init) {
         const W px = e.kpx - (W)ipx, py = e.kpy - (W)ipy, pz = e.kpz - (W)ipz;
         const W vx = e.kvx - (W)ivx, vy = e.kvy - (W)ivy, vz = e.kvz - (W)ivz;
         const W rr = nnorm3(px, py, pz);
         const W cl = -ndot3(px, py, pz, vx, vy, vz) * nrcp(rr + W(1e-6));
+        if (mode == HLYNR_OBS_LOS) {  // core.py:791-872
+            lb = los_basis_near<W>(px, py, pz, rr);
+            have_los = true;
+            out.put(0, (float)clip(rr * P.rc_max_range_w, W(0), W(1)));
+            out.put(1, (float)clip(cl * P.rc_max_velocity_w, W(-1), W(1)));
+            const W ird = nrcp(rr + W(1e-6));
+            const W tx = (vx - cl * lb.ux) * ird, ty = (vy - cl * lb.uy) * ird, tz = (vz - cl * lb.uz) * ird;  // LOS rate vector
+            out.put(2, (float)clip((tx * lb.hx + ty * lb.hy) * W(2), W(-1), W(1)));                 // / max_los_rate 0.5
+            out.put(3, (float)clip(ndot3(tx, ty, tz, lb.vx, lb.vy, lb.vz) * W(2), W(-1), W(1)));
+            const float ivm = nnorm3(ivx, ivy, ivz);
+            out.put(4, ivm > 1e-6f ? (float)(ndot3((W)ivx, (W)ivy, (W)ivz, lb.ux, lb.uy, lb.uz) * (W)nrcp(ivm)) : 0.f);
+            const W ax = vx + (W)ivx, ay = vy + (W)ivy, az = vz + (W)ivz;  // approximate target velocity
+            const W am = nnorm3(ax, ay, az);
+            out.put(5, am > W(1e-6) ? (float)(-ndot3(ax, ay, az, lb.ux, lb.uy, lb.uz) * nrcp(am)) : 0.f);
+        } else if (mode == HLYNR_OBS_BODY) {  // core.py:874-880: np.dot against the float32 body axes, float32 result
+            const float b0 = (float)ndot3(px, py, pz, (W)fx, (W)fy, (W)fz), b1 = (float)ndot3(px, py, pz, (W)bx.rx, (W)bx.ry, (W)bx.rz);
+            const float b2 = (float)ndot3(px, py, pz, (W)bx.ux, (W)bx.uy, (W)bx.uz);
+            const float c0 = (float)ndot3(vx, vy, vz, (W)fx, (W)fy, (W)fz), c1 = (float)ndot3(vx, vy, vz, (W)bx.rx, (W)bx.ry, (W)bx.rz);
+            const float c2 = (float)ndot3(vx, vy, vz, (W)bx.ux, (W)bx.uy, (W)bx.uz);
+            out.put(0, clip(b0 * P.rc_max_range_f, -1.f, 1.f)); out.put(1, clip(b1 * P.rc_max_range_f, -1.f, 1.f));
+            out.put(2, clip(b2 * P.rc_max_range_f, -1.f, 1.f));
+            out.put(3, clip(c0 * P.rc_max_velocity_f, -1.f, 1.f)); out.put(4, clip(c1 * P.rc_max_velocity_f, -1.f, 1.f));
+            out.put(5, clip(c2 * P.rc_max_velocity_f, -1.f, 1.f));
+        } else {
         out.put(0, (float)clip(px * P.rc_max_range_w, W(-1), W(1)));
         out.put(1, (float)clip(py * P.rc_max_range_w, W(-1), W(1)));
         out.put(2, (float)clip(pz * P.rc_max_range_w, W(-1), W(1)));
         out.put(3, (float)clip(vx * P.rc_max_velocity_w, W(-1), W(1)));
         out.put(4, (float)clip(vy * P.rc_max_velocity_w, W(-1), W(1)));
         out.put(5, (float)clip(vz * P.rc_max_velocity_w, W(-1), W(1)));
+        }
         out.put(13, cl > W(0) ? (float)clip(W(1) - rr * nrcp(cl) * W(0.01), W(-1), W(1)) : -1.f);
         float tq = clip(1.f - (e.Ppp * 3.f) * 1e-4f, 0.f, 1.f);
         if (o_det) tq *= P.radar_quality;
@@ -571,10 +625,23 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
         for (int k = 0; k < 6; ++k) out.put(k, -2.f);
         out.put(13, -1.f); out.put(14, 0.f); out.put(15, 0.f); out.put(16, 0.f);
     }
+    if (mode == HLYNR_OBS_LOS) {  // core.py:920-958
+        out.put(6, clip(nnorm3(ivx, ivy, ivz) * P.rc_max_velocity_f, 0.f, 1.f));
+        if (have_los) {
+            out.put(7, (float)clip(((W)ivx * lb.hx + (W)ivy * lb.hy) * P.rc_max_velocity_w, W(-1), W(1)));
+            out.put(8, (float)clip(ndot3((W)ivx, (W)ivy, (W)ivz, lb.vx, lb.vy, lb.vz) * P.rc_max_velocity_w, W(-1), W(1)));
+        } else { out.put(7, 0.f); out.put(8, 0.f); }
+    } else if (mode == HLYNR_OBS_BODY) {  // :959-962
+        out.put(6, clip(ndot3(ivx, ivy, ivz, fx, fy, fz) * P.rc_max_velocity_f, -1.f, 1.f));
+        out.put(7, clip(ndot3(ivx, ivy, ivz, bx.rx, bx.ry, bx.rz) * P.rc_max_velocity_f, -1.f, 1.f));
+        out.put(8, clip(ndot3(ivx, ivy, ivz, bx.ux, bx.uy, bx.uz) * P.rc_max_velocity_f, -1.f, 1.f));
+    } else {
     out.put(6, clip(ivx * P.rc_max_velocity_f, -1.f, 1.f));
     out.put(7, clip(ivy * P.rc_max_velocity_f, -1.f, 1.f));
     out.put(8, clip(ivz * P.rc_max_velocity_f, -1.f, 1.f));
-    if (out.emit) {  // quaternion_to_euler, core.py:1103-1121 (float32), divided by pi
+    }
+    if (mode != HLYNR_OBS_WORLD) { out.put(9, 0.f); out.put(10, 0.f); out.put(11, 0.f); }  // core.py:966-970
+    else if (out.emit) {  // quaternion_to_euler, core.py:1103-1121 (float32), divided by pi
         const float w = e.qw, x = e.qx, y = e.qy, z = e.qz;
         const float sinr = 2.f * fmaf(w, x, y * z), cosr = 1.f - 2.f * fmaf(x, x, y * y);
         const float sinp = 2.f * fmaf(w, y, -(z * x));
@@ -585,7 +652,27 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
         out.put(11, atan2f(siny, cosy) * ipi);
     }
     out.put(12, clip((float)e.fuel * 0.01f, 0.f, 1.f));
-    if (dg_det && link > 0.1f) {
+    if (dg_det && link > 0.1f && mode == HLYNR_OBS_LOS) {  // core.py:985-1006: redundant range / rate measurements
+        const W gr = nnorm3(dgx, dgy, dgz);
+        const W gc = -ndot3(dgx, dgy, dgz, dvx, dvy, dvz) * nrcp(gr + W(1e-6));
+        out.put(17, (float)clip(gr * P.rc_max_range_w, W(0), W(1)));
+        out.put(18, (float)clip(gc * P.rc_max_velocity_w, W(-1), W(1)));
+        if (gr > W(1e-6)) {
+            const W ig = nrcp(gr);
+            const W k = gc * ig;
+            out.put(19, (float)clip(nnorm3(dvx - k * dgx, dvy - k * dgy, dvz - k * dgz) * ig * W(2), W(0), W(1)));
+        } else out.put(19, 0.f);
+        out.put(20, 0.f); out.put(21, 0.f); out.put(22, 0.f);
+        out.put(23, dgq);
+    } else if (dg_det && link > 0.1f && mode == HLYNR_OBS_BODY) {  // :1008-1012
+        out.put(17, clip((float)ndot3(dgx, dgy, dgz, (W)fx, (W)fy, (W)fz) * P.rc_max_range_f, -1.f, 1.f));
+        out.put(18, clip((float)ndot3(dgx, dgy, dgz, (W)bx.rx, (W)bx.ry, (W)bx.rz) * P.rc_max_range_f, -1.f, 1.f));
+        out.put(19, clip((float)ndot3(dgx, dgy, dgz, (W)bx.ux, (W)bx.uy, (W)bx.uz) * P.rc_max_range_f, -1.f, 1.f));
+        out.put(20, clip((float)ndot3(dvx, dvy, dvz, (W)fx, (W)fy, (W)fz) * P.rc_max_velocity_f, -1.f, 1.f));
+        out.put(21, clip((float)ndot3(dvx, dvy, dvz, (W)bx.rx, (W)bx.ry, (W)bx.rz) * P.rc_max_velocity_f, -1.f, 1.f));
+        out.put(22, clip((float)ndot3(dvx, dvy, dvz, (W)bx.ux, (W)bx.uy, (W)bx.uz) * P.rc_max_velocity_f, -1.f, 1.f));
+        out.put(23, dgq);
+    } else if (dg_det && link > 0.1f) {
         out.put(17, (float)clip(dgx * P.rc_max_range_w, W(-1), W(1)));
         out.put(18, (float)clip(dgy * P.rc_max_range_w, W(-1), W(1)));
         out.put(19, (float)clip(dgz * P.rc_max_range_w, W(-1), W(1)));
@@ -768,6 +855,21 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
     const uint32_t ep = (uint32_t)e.episode, st = (uint32_t)e.steps;
     t.ur = draw_raw(key, ep, st, HLYNR_BLK_UNI);
     R a0 = (R)act[0], a1 = (R)act[1], a2 = (R)act[2], a3 = (R)act[3], a4 = (R)act[4], a5 = (R)act[5];
+    if (FT::obs_mode(P) == HLYNR_OBS_LOS) {
+        // _update_los_frame + _transform_los_action_to_world (environment.py:965-1061): the basis is built in float32
+        // from the TRUE positions before the physics update; thrust = a0 * lu + a1 * lh + a2 * lv
+        const float rx = sub((float)e.mpx, (float)e.ipx), ry = sub((float)e.mpy, (float)e.ipy), rz = sub((float)e.mpz, (float)e.ipz);
+        const float rr = norm3(rx, ry, rz);
+        float ux = 1.f, uy = 0.f, uz = 0.f, hx = 1.f, hy = 0.f;
+        if (rr > 1e-6f) { ux = dvd(rx, rr); uy = dvd(ry, rr); uz = dvd(rz, rr); }
+        const float hn = norm3(uy, -ux, 0.f);
+        if (hn > 1e-6f) { hx = dvd(uy, hn); hy = dvd(-ux, hn); }
+        const float vx = -mul(uz, hy), vy = mul(uz, hx), vz = sub(mul(ux, hy), mul(uy, hx));
+        const R t0 = add(add(mul(a0, (R)ux), mul(a1, (R)hx)), mul(a2, (R)vx));
+        const R t1 = add(add(mul(a0, (R)uy), mul(a1, (R)hy)), mul(a2, (R)vy));
+        const R t2 = add(mul(a0, (R)uz), mul(a2, (R)vz));  // lh.z == 0
+        a0 = t0; a1 = t1; a2 = t2;
+    }
     // SafetyClamp.apply (core.py:1069-1100); limits are in action units (quirk Q8)
     bool clamped = false;
     if (e.fuel <= R(0)) { a0 = a1 = a2 = R(0); clamped = true; }
@@ -932,6 +1034,7 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
                             dvd(sub(e.mpy, e.ipy), dist), dvd(sub(e.mpz, e.ipz), dist));
                 r = add(r, mul(al, R(0.3)));
             }
+            if (FT::obs_mode(P) == HLYNR_OBS_LOS) r = add(r, mul((R)act[0], R(0.4)));  // forward-thrust shaping, :1252-1264
             r = sub(r, R(0.2));
             e.prev_d = dist;
         }
@@ -1361,7 +1464,7 @@ template <typename R> __global__ void __launch_bounds__(HLYNR_BLOCK) reset_kerne
     e.episode += 1;
     spawn(A, e, key);
     const uint4 ur = draw_raw(key, (uint32_t)e.episode, 0u, HLYNR_BLK_UNI);
-    observe<R, FT_GENERIC>(A, e, key, ur, i, A.g_row, A.o_row, RingPre<R>{}, ob);
+    observe<R, FT_GENERIC_MODES>(A, e, key, ur, i, A.g_row, A.o_row, RingPre<R>{}, ob);
     store_env(A, i, e);
     if (A.io.obs) copy_obs_row(ob.row, A.io.obs + i * HLYNR_OBS_DIM);
 }

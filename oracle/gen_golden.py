@@ -55,12 +55,60 @@ CASES = {
 }
 
 
+def reference_yaml_env(rel_path):
+    """Env dict exactly as scripts/train_hrl_pretrain.py builds it: load_config (:270-296, child sections update the
+    parent's) then environment + top-level curriculum + physics_enhancements (:333-338)."""
+    import yaml
+
+    path = os.path.join(rh.REFERENCE_ROOT, "rl_system", rel_path)
+    with open(path) as f:
+        cfg = yaml.safe_load(f)
+    if "parent_config" in cfg:
+        with open(os.path.normpath(os.path.join(os.path.dirname(path), cfg["parent_config"]))) as f:
+            merged = yaml.safe_load(f)
+        for key, val in cfg.items():
+            if key == "parent_config":
+                continue
+            if isinstance(val, dict) and key in merged:
+                merged[key].update(val)
+            else:
+                merged[key] = val
+        cfg = merged
+    env = dict(cfg.get("environment", {}))
+    env["curriculum"] = cfg.get("curriculum", {})
+    env["physics_enhancements"] = cfg.get("physics_enhancements", {})
+    return env
+
+
+# HRL specialist configs (SURVEY 8f rank 2): precision-mode reward/termination, proximity fuze, spherical spawn,
+# toward_missile launch, body_frame / los_frame observations and the LOS-frame action transform
+CASES.update({
+    "hrl_terminal360v1_f32_pursuit": ("yaml:configs/hrl/terminal_360_v1.yaml", None, 8, 1200, False, "pursuit", 400000),
+    "hrl_terminal360v1_f32_zem": ("yaml:configs/hrl/terminal_360_v1.yaml", None, 8, 1200, False, "zem", 400000),
+    "hrl_terminal360v1_f64_zem": ("yaml:configs/hrl/terminal_360_v1.yaml", None, 4, 1000, True, "zem", 400000),
+    "hrl_rotinv_f32_mixed": ("yaml:configs/hrl/terminal_360_rotinv.yaml", None, 8, 900, False, "mixed", 1000000),
+    "hrl_rotinv_f32_zem": ("yaml:configs/hrl/terminal_360_rotinv.yaml", None, 8, 1200, False, "zem", 1000000),
+    "hrl_rotinv_f64_zem": ("yaml:configs/hrl/terminal_360_rotinv.yaml", None, 4, 800, True, "zem", 1000000),
+    "hrl_terminal_los_f32_pn": ("yaml:configs/hrl/terminal_los.yaml", None, 8, 1200, False, "los_pn", 500000),
+    "hrl_terminal_los_f32_zem": ("yaml:configs/hrl/terminal_los.yaml", None, 8, 1200, False, "zem_los", 500000),
+    "hrl_terminal_los_f64_zem": ("yaml:configs/hrl/terminal_los.yaml", None, 4, 1000, True, "zem_los", 500000),
+    "hrl_search_los_f32_random": ("yaml:configs/hrl/search_los.yaml", None, 8, 400, False, "random", None),
+    "hrl_eval360los_f32_pn": ("yaml:configs/eval_360_los.yaml", None, 8, 1000, False, "los_pn", None),
+})
+
+
+def make_policy(policy, ref):
+    return {"random": lambda: rh.policy_random(7), "pursuit": rh.policy_pursuit, "mixed": lambda: rh.policy_mixed(11),
+            "los_pn": lambda: rh.policy_los_pn(13), "zem": lambda: rh.policy_true_guidance(ref),
+            "zem_los": lambda: rh.policy_true_guidance(ref, los_frame=True)}[policy]()
+
+
 def generate(name):
     base, extra, n, T, f64, policy, tsc = CASES[name]
-    cfg = case_config(base, extra)
+    cfg = reference_yaml_env(base[5:]) if base.startswith("yaml:") else case_config(base, extra)
     seed = 1234
     ref = rh.RefBatch(cfg, n, seed=seed, float64=f64, training_step_count=tsc)
-    pol = rh.policy_random(7) if policy == "random" else rh.policy_pursuit()
+    pol = make_policy(policy, ref)
     obs0 = ref.reset()
     obs = obs0
     rec = dict(actions=[], obs=[], reward=[], terminated=[], truncated=[], terminal_obs=[], distance=[],

@@ -419,8 +419,52 @@ static void quat_to_euler(const double q[4], double eul[3]) { /* :1103-1121, flo
     eul[2] = rn(atan2(siny, cosy), F32);
 }
 
+static void right_vector(const double q[4], double r[3]) { /* core.py:1155-1164, all float32 */
+    double w = q[0], x = q[1], y = q[2], z = q[3];
+    r[0] = sub(1.0, mul(2.0, add(mul(y, y, F32), mul(z, z, F32), F32), F32), F32);
+    r[1] = mul(2.0, add(mul(x, y, F32), mul(w, z, F32), F32), F32);
+    r[2] = mul(2.0, sub(mul(x, z, F32), mul(w, y, F32), F32), F32);
+    double n = add(norm3(r, F32), wk(1e-6, F32), F32);
+    for (int i = 0; i < 3; ++i) r[i] = dvd(r[i], n, F32);
+}
+static void up_vector(const double q[4], double u[3]) { /* core.py:1167-1176, all float32 */
+    double w = q[0], x = q[1], y = q[2], z = q[3];
+    u[0] = mul(2.0, sub(mul(x, y, F32), mul(w, z, F32), F32), F32);
+    u[1] = sub(1.0, mul(2.0, add(mul(x, x, F32), mul(z, z, F32), F32), F32), F32);
+    u[2] = mul(2.0, add(mul(y, z, F32), mul(w, x, F32), F32), F32);
+    double n = add(norm3(u, F32), wk(1e-6, F32), F32);
+    for (int i = 0; i < 3; ++i) u[i] = dvd(u[i], n, F32);
+}
+/* np.cross for 3-vectors: cp0 = a1*b2 - a2*b1, cp1 = a2*b0 - a0*b2, cp2 = a0*b1 - a1*b0, each product and each
+ * difference rounded to the result dtype */
+static void cross3(const double a[3], const double b[3], double c[3], Prec p) {
+    c[0] = sub(mul(a[1], b[2], p), mul(a[2], b[1], p), p);
+    c[1] = sub(mul(a[2], b[0], p), mul(a[0], b[2], p), p);
+    c[2] = sub(mul(a[0], b[1], p), mul(a[1], b[0], p), p);
+}
+/* The LOS basis both the observation (core.py:803-845, :929-945) and the action transform (environment.py:965-1020)
+ * build from a relative position: los_unit, los_horizontal = normalize(los_unit x world_up), los_vertical =
+ * los_unit x los_horizontal. */
+static void los_basis(const double rel[3], double range, Prec p, double lu[3], double lh[3], double lv[3]) {
+    const double up[3] = {0.0, 0.0, 1.0};
+    if (range > 1e-6) for (int i = 0; i < 3; ++i) lu[i] = dvd(rel[i], range, p);
+    else { lu[0] = 1.0; lu[1] = 0.0; lu[2] = 0.0; }
+    double lr[3];
+    cross3(lu, up, lr, p);
+    double n = norm3(lr, p);
+    if (n > 1e-6) for (int i = 0; i < 3; ++i) lh[i] = dvd(lr[i], n, p);
+    else { lh[0] = 1.0; lh[1] = 0.0; lh[2] = 0.0; }
+    cross3(lu, lh, lv, p);
+}
+/* world_to_body_frame core.py:1179-1205: np.dot against the float32 body axes, result array forced to float32 */
+static void to_body(const double v[3], Prec pv, const double fwd[3], const double right[3], const double up[3], double out[3]) {
+    out[0] = rn(dot3(v, fwd, pv), F32);
+    out[1] = rn(dot3(v, right, pv), F32);
+    out[2] = rn(dot3(v, up, pv), F32);
+}
+
 /* ---------------------------------------------------------------------------------------------- */
-/* Radar26DObservation.compute_radar_detection :511-691 + compute :693-1032 (world_frame)          */
+/* Radar26DObservation.compute_radar_detection :511-691 + compute :693-1032 (all observation modes) */
 /* ---------------------------------------------------------------------------------------------- */
 static void observe(Oracle* o, Env* e, uint32_t step, float obs[26]) {
     const HlynrParams* P = &o->P;
@@ -438,8 +482,11 @@ static void observe(Oracle* o, Env* e, uint32_t step, float obs[26]) {
     double range = norm3(rel, F32);
     int onb = 1;
     if (GT(e, range, wk(P->radar_range, F32))) onb = 0;
-    double fwd[3], tom[3];
+    double fwd[3], tom[3], right[3] = {0, 0, 0}, up[3] = {0, 0, 0};
+    double lu[3] = {1, 0, 0}, lh[3] = {1, 0, 0}, lv[3] = {0, 0, 0};
+    int have_los = 0;
     forward_vector(q, fwd);
+    if (P->obs_mode == HLYNR_OBS_BODY) { right_vector(q, right); up_vector(q, up); }
     double rden = add(range, wk(1e-6, F32), F32);
     for (int i = 0; i < 3; ++i) tom[i] = dvd(rel[i], rden, F32);
     double beam = rn(acos(clipd(dot3(fwd, tom, F32), -1.0, 1.0)), F32);
@@ -595,6 +642,39 @@ static void observe(Oracle* o, Env* e, uint32_t step, float obs[26]) {
         for (int i = 0; i < 3; ++i) { frp[i] = sub(kf->x[i], ip[i], pk); frv[i] = sub(kf->x[3 + i], iv[i], pk); }
         double rr = norm3(frp, pk);
         double cl = dvd(-dot3(frp, frv, pk), add(rr, wk(1e-6, pk), pk), pk);
+        if (P->obs_mode == HLYNR_OBS_LOS) { /* core.py:791-872 */
+            have_los = 1;
+            obs[0] = (float)clipd(dvd(rr, wk(P->max_range, pk), pk), 0.0, 1.0);
+            obs[1] = (float)clipd(dvd(cl, wk(P->max_velocity, pk), pk), -1.0, 1.0);
+            los_basis(frp, rr, pk, lu, lh, lv);
+            double rate[3];
+            double rden2 = add(rr, wk(1e-6, pk), pk);
+            for (int i = 0; i < 3; ++i) rate[i] = dvd(sub(frv[i], mul(cl, lu[i], pk), pk), rden2, pk);
+            obs[2] = (float)clipd(dvd(dot3(rate, lh, pk), wk(0.5, pk), pk), -1.0, 1.0);
+            obs[3] = (float)clipd(dvd(dot3(rate, lv, pk), wk(0.5, pk), pk), -1.0, 1.0);
+            double ivm = norm3(iv, F32);
+            if (ivm > 1e-6) {
+                double un[3];
+                for (int i = 0; i < 3; ++i) un[i] = dvd(iv[i], ivm, F32);
+                obs[4] = (float)dot3(un, lu, pk);
+            } else obs[4] = 0.f;
+            double tv[3];
+            for (int i = 0; i < 3; ++i) tv[i] = add(frv[i], iv[i], pk);
+            double tvm = norm3(tv, pk);
+            if (tvm > 1e-6) {
+                double un[3], nl[3];
+                for (int i = 0; i < 3; ++i) { un[i] = dvd(tv[i], tvm, pk); nl[i] = -lu[i]; }
+                obs[5] = (float)dot3(un, nl, pk);
+            } else obs[5] = 0.f;
+        } else if (P->obs_mode == HLYNR_OBS_BODY) { /* core.py:874-880 */
+            double bp[3], bv[3];
+            to_body(frp, pk, fwd, right, up, bp);
+            to_body(frv, pk, fwd, right, up, bv);
+            for (int i = 0; i < 3; ++i) {
+                obs[i] = (float)clipd(dvd(bp[i], wk(P->max_range, F32), F32), -1.0, 1.0);
+                obs[3 + i] = (float)clipd(dvd(bv[i], wk(P->max_velocity, F32), F32), -1.0, 1.0);
+            }
+        } else
         for (int i = 0; i < 3; ++i) {
             obs[i] = (float)clipd(dvd(frp[i], wk(P->max_range, pk), pk), -1.0, 1.0);
             obs[3 + i] = (float)clipd(dvd(frv[i], wk(P->max_velocity, pk), pk), -1.0, 1.0);
@@ -617,16 +697,50 @@ static void observe(Oracle* o, Env* e, uint32_t step, float obs[26]) {
         for (int i = 0; i < 6; ++i) obs[i] = -2.f;
         obs[13] = -1.f; obs[14] = 0.f; obs[15] = 0.f; obs[16] = 0.f;
     }
+    if (P->obs_mode == HLYNR_OBS_LOS) { /* core.py:920-958 */
+        double sp = norm3(iv, F32);
+        obs[6] = (float)clipd(dvd(sp, wk(P->max_velocity, F32), F32), 0.0, 1.0);
+        if (have_los) {
+            obs[7] = (float)clipd(dvd(dot3(iv, lh, pk), wk(P->max_velocity, pk), pk), -1.0, 1.0);
+            obs[8] = (float)clipd(dvd(dot3(iv, lv, pk), wk(P->max_velocity, pk), pk), -1.0, 1.0);
+        } else { obs[7] = 0.f; obs[8] = 0.f; }
+    } else if (P->obs_mode == HLYNR_OBS_BODY) { /* :959-962 */
+        double bv[3];
+        to_body(iv, F32, fwd, right, up, bv);
+        for (int i = 0; i < 3; ++i) obs[6 + i] = (float)clipd(dvd(bv[i], wk(P->max_velocity, F32), F32), -1.0, 1.0);
+    } else
     for (int i = 0; i < 3; ++i) obs[6 + i] = (float)clipd(dvd(iv[i], wk(P->max_velocity, F32), F32), -1.0, 1.0);
-    double eul[3];
-    quat_to_euler(q, eul);
-    for (int i = 0; i < 3; ++i) obs[9 + i] = (float)dvd(eul[i], wk(M_PI, F32), F32);
+    if (P->obs_mode == HLYNR_OBS_WORLD) { /* :967-974; zeros in the other modes */
+        double eul[3];
+        quat_to_euler(q, eul);
+        for (int i = 0; i < 3; ++i) obs[9 + i] = (float)dvd(eul[i], wk(M_PI, F32), F32);
+    }
     {
         Prec pf = e->steps == 0 && !e->started ? F64 : S; /* fuel is a Python float until the first tick */
         obs[12] = (float)clipd(dvd(e->fuel, wk(100.0, pf), pf), 0.0, 1.0);
     }
     if (dg_det && GT(e, link, wk(0.1, F32))) {
         Prec pg = dg_f64 ? F64 : F32;
+        if (P->obs_mode == HLYNR_OBS_LOS) { /* core.py:985-1006 */
+            double gr = norm3(dg_rel, pg);
+            double gc = dvd(-dot3(dg_rel, dg_vel, pg), add(gr, wk(1e-6, pg), pg), pg);
+            obs[17] = (float)clipd(dvd(gr, wk(P->max_range, pg), pg), 0.0, 1.0);
+            obs[18] = (float)clipd(dvd(gc, wk(P->max_velocity, pg), pg), -1.0, 1.0);
+            if (gr > 1e-6) {
+                double tv[3];
+                for (int i = 0; i < 3; ++i) tv[i] = sub(dg_vel[i], mul(gc, dvd(dg_rel[i], gr, pg), pg), pg);
+                obs[19] = (float)clipd(dvd(dvd(norm3(tv, pg), gr, pg), wk(0.5, pg), pg), 0.0, 1.0);
+            } else obs[19] = 0.f;
+            obs[20] = obs[21] = obs[22] = 0.f;
+        } else if (P->obs_mode == HLYNR_OBS_BODY) { /* :1008-1012 */
+            double bp[3], bv[3];
+            to_body(dg_rel, pg, fwd, right, up, bp);
+            to_body(dg_vel, pg, fwd, right, up, bv);
+            for (int i = 0; i < 3; ++i) {
+                obs[17 + i] = (float)clipd(dvd(bp[i], wk(P->max_range, F32), F32), -1.0, 1.0);
+                obs[20 + i] = (float)clipd(dvd(bv[i], wk(P->max_velocity, F32), F32), -1.0, 1.0);
+            }
+        } else
         for (int i = 0; i < 3; ++i) {
             obs[17 + i] = (float)clipd(dvd(dg_rel[i], wk(P->max_range, pg), pg), -1.0, 1.0);
             obs[20 + i] = (float)clipd(dvd(dg_vel[i], wk(P->max_velocity, pg), pg), -1.0, 1.0);
@@ -759,6 +873,15 @@ static void env_step(Oracle* o, Env* e, const float act[6], StepOut* out) {
     uint32_t step = (uint32_t)e->steps;
     double a[6];
     for (int i = 0; i < 6; ++i) a[i] = (double)act[i];
+    if (P->obs_mode == HLYNR_OBS_LOS) { /* _update_los_frame + _transform_los_action_to_world, environment.py:965-1061 */
+        double rel[3], lu[3], lh[3], lv[3];
+        for (int i = 0; i < 3; ++i) rel[i] = sub(rn(e->mpos[i], F32), rn(e->ipos[i], F32), F32); /* float32 copies of the state */
+        los_basis(rel, norm3(rel, F32), F32, lu, lh, lv);
+        double w[3]; /* action scalar (float32, or float64 in the up-cast oracle) times float32 basis vectors */
+        for (int i = 0; i < 3; ++i)
+            w[i] = add(add(mul(a[0], lu[i], S), mul(a[1], lh[i], S), S), mul(a[2], lv[i], S), S);
+        for (int i = 0; i < 3; ++i) a[i] = w[i];
+    }
     /* SafetyClamp.apply core.py:1069-1100 */
     int clamped = 0;
     if (e->fuel <= 0) { a[0] = a[1] = a[2] = 0.0; clamped = 1; }
@@ -1012,6 +1135,8 @@ static void env_step(Oracle* o, Env* e, const float act[6], StepOut* out) {
                 for (int i = 0; i < 3; ++i) al = add(al, mul(dvd(e->ivel[i], sp, S), dvd(sub(e->mpos[i], e->ipos[i], S), dist, S), S), S);
                 r = add(r, mul(al, wk(0.3, S), S), S);
             }
+            /* forward-thrust shaping on the ORIGINAL LOS-frame action, environment.py:1252-1264 */
+            if (P->obs_mode == HLYNR_OBS_LOS) r = add(r, mul((double)act[0], wk(0.4, S), S), S);
             r = sub(r, wk(0.2, S), S);
             e->prev_d = dist;
         }

@@ -382,3 +382,70 @@ def policy_pursuit(gain=1.0):
         return a.astype(np.float32)
 
     return f
+
+
+def policy_mixed(seed, bias=(0.3, 0.3, 0.7)):
+    """Biased random thrust + random angular rates (exercises every action dimension; used where the observation
+    frame gives no world direction to pursue, i.e. body_frame)."""
+    rng = np.random.default_rng(seed)
+
+    def f(t, obs):
+        a = rng.uniform(-1, 1, (obs.shape[0], 6)).astype(np.float32)
+        a[:, 0:3] = np.clip(0.5 * a[:, 0:3] + np.asarray(bias, np.float32), -1, 1)
+        a[:, 3:6] *= np.float32(0.3)
+        return a.astype(np.float32)
+
+    return f
+
+
+def policy_los_pn(seed, gain=3.0, jitter=0.15):
+    """LOS-frame guidance on the observation only (observation_mode 'los_frame'): full thrust along the LOS
+    (action[0]) plus proportional-navigation style corrections from the LOS rates obs[2], obs[3]
+    (action[1], action[2]; same basis, core.py:812-845 / environment.py:1006-1020), small random jitter."""
+    rng = np.random.default_rng(seed)
+
+    def f(t, obs):
+        n = obs.shape[0]
+        a = np.zeros((n, 6), np.float32)
+        track = obs[:, 0] > -1.5
+        a[:, 0] = 1.0
+        a[track, 1] = np.clip(gain * obs[track, 2], -1, 1)
+        a[track, 2] = np.clip(gain * obs[track, 3], -1, 1)
+        a += (jitter * rng.uniform(-1, 1, (n, 6))).astype(np.float32)
+        return np.clip(a, -1, 1).astype(np.float32)
+
+    return f
+
+
+def policy_true_guidance(ref, los_frame=False, seed=17, jitter=0.05):
+    """Scripted interceptor for fixtures that must reach the intercept / proximity-fuze / crossed-threshold branches:
+    zero-effort-miss guidance computed from the TRUE simulator state of the reference envs (a fixture only needs an
+    action sequence, it does not have to be a legal radar-only policy).  los_frame=True expresses the thrust in the
+    LOS basis the reference's action transform uses (environment.py:965-1061)."""
+    rng = np.random.default_rng(seed)
+
+    def f(t, obs):
+        n = obs.shape[0]
+        a = np.zeros((n, 6), np.float32)
+        for i, env in enumerate(ref.envs):
+            ip = np.asarray(env.interceptor_state["position"], np.float64)
+            iv = np.asarray(env.interceptor_state["velocity"], np.float64)
+            mp = np.asarray(env.missile_state["position"], np.float64)
+            mv = np.asarray(env.missile_state["velocity"], np.float64)
+            rel, vrel = mp - ip, mv - iv
+            rng_ = np.linalg.norm(rel) + 1e-9
+            closing = max(-np.dot(rel, vrel) / rng_, 20.0)
+            tgo = min(rng_ / closing, 12.0)
+            zem = rel + vrel * tgo + np.array([0.0, 0.0, 0.5 * 9.81 * tgo * tgo])
+            d = zem / (np.linalg.norm(zem) + 1e-9)
+            if los_frame:
+                lu = rel / rng_
+                lr = np.cross(lu, [0.0, 0.0, 1.0])
+                lh = lr / np.linalg.norm(lr) if np.linalg.norm(lr) > 1e-6 else np.array([1.0, 0.0, 0.0])
+                lv = np.cross(lu, lh)
+                d = np.array([np.dot(d, lu), np.dot(d, lh), np.dot(d, lv)])
+            a[i, 0:3] = d
+        a += (jitter * rng.uniform(-1, 1, (n, 6))).astype(np.float32)
+        return np.clip(a, -1, 1).astype(np.float32)
+
+    return f
