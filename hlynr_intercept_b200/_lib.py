@@ -16,6 +16,10 @@ EXPORTS = [
     "hlynr_step", "hlynr_rollout", "hlynr_reset_host", "hlynr_step_host", "hlynr_pinned_buffers", "hlynr_info_host",
     "hlynr_stats_device_ptr", "hlynr_stats_reduce", "hlynr_get_stats", "hlynr_export_state", "hlynr_import_state",
     "hlynr_debug_draws", "hlynr_launch_count", "hlynr_set_option", "hlynr_set_done_list", "hlynr_done_records_host",
+    # include/hlynr_post.h
+    "hlynr_post_create", "hlynr_post_destroy", "hlynr_post_obs_dim", "hlynr_post_obs_target", "hlynr_post_reset",
+    "hlynr_post_step", "hlynr_post_original", "hlynr_post_normalize", "hlynr_post_get_stats", "hlynr_post_set_stats",
+    "hlynr_post_check_sums", "hlynr_post_launch_count",
 ]
 
 
@@ -67,6 +71,20 @@ def load(build_if_missing=True):
     L.hlynr_set_option.argtypes = [vp, C.c_char_p, i64]
     L.hlynr_set_done_list.argtypes = [vp, vp, vp, C.c_int32]
     L.hlynr_done_records_host.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int32)]
+    dbl, pd = C.c_double, C.POINTER(C.c_double)
+    L.hlynr_post_create.argtypes = [i64, i32, i32, dbl, dbl, dbl, C.POINTER(vp)]
+    L.hlynr_post_destroy.argtypes = [vp]
+    L.hlynr_post_destroy.restype = None
+    L.hlynr_post_obs_dim.argtypes = [vp, C.POINTER(i32)]
+    L.hlynr_post_obs_target.argtypes = [vp, C.POINTER(vp)]
+    L.hlynr_post_reset.argtypes = [vp, vp, i32, vp]
+    L.hlynr_post_step.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int32, vp, vp, i32, vp]
+    L.hlynr_post_original.argtypes = [vp, vp, vp]
+    L.hlynr_post_normalize.argtypes = [vp, vp, i64, vp, vp]
+    L.hlynr_post_get_stats.argtypes = [vp, vp, vp, pd, pd, pd, pd, vp]
+    L.hlynr_post_set_stats.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl, vp]
+    L.hlynr_post_check_sums.argtypes = [vp, i32, pd, vp]
+    L.hlynr_post_launch_count.argtypes = [vp, C.POINTER(i64)]
     if L.hlynr_abi_version() != abi.ABI_VERSION:
         raise HlynrError("ABI version mismatch between libhlynr_b200.so and hlynr_intercept_b200.abi")
     if L.hlynr_params_size() != C.sizeof(abi.HlynrParams):

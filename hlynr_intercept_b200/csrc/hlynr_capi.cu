@@ -26,6 +26,14 @@ static int fail(const char* fmt, ...) {
     va_end(ap);
     return 1;
 }
+// error reporting for the other translation units of the library (hlynr_post.cu)
+extern "C" int hlynr_internal_fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
 #define CK(call)                                                                                      \
     do {                                                                                              \
         cudaError_t _e = (call);                                                                      \
