@@ -72,14 +72,20 @@ __global__ void __launch_bounds__(16 * OD) colsum_kernel(const float* __restrict
 }
 
 // ---- VecNormalize._update_reward: returns = returns * gamma + reward; ret_rms sums; returns[done] = 0 ----
+// Also the per-env part of VecFrameStack: age_new = done ? 0 : min(age_old + 1, k - 1) (how many older frames of the
+// ring belong to the env's current episode).
 __global__ void __launch_bounds__(256) returns_kernel(double* __restrict__ ret, const float* __restrict__ rew,
                                                       const uint8_t* __restrict__ term, const uint8_t* __restrict__ trunc, int64_t n,
-                                                      double gamma, double* ret_sum, double* ret_sq, int training) {
+                                                      double gamma, double* ret_sum, double* ret_sq, int training,
+                                                      const uint8_t* __restrict__ age_in, uint8_t* __restrict__ age_out, int k) {
     double s = 0.0, q = 0.0;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         double r = ret[e];
         if (training) { r = r * gamma + (double)rew[e]; s += r; q += r * r; }
-        ret[e] = (term[e] | trunc[e]) ? 0.0 : r;  // returns[dones] = 0 happens whether or not the statistics move
+        const bool done = (term[e] | trunc[e]) != 0;
+        ret[e] = done ? 0.0 : r;  // returns[dones] = 0 happens whether or not the statistics move
+        const int a = (int)age_in[e] + 1;
+        age_out[e] = (uint8_t)(done ? 0 : (a < k - 1 ? a : k - 1));
     }
     if (!training) return;
 #pragma unroll
@@ -161,28 +167,44 @@ __global__ void merge_kernel(PostStats* st, int k, double n, int shift, int trai
     }
 }
 
-// ---- stacked (+ normalised) observation: thread-constant feature, coalesced [N, 26k] output ----
-// age_mode 0: ages are current (no update);  1: step (age_new = done ? 0 : min(age_old + 1, k - 1), written to age_out);
-// 2: reset (age_new = 0 for every env)
-__global__ void __launch_bounds__(512) normalize_kernel(const float* __restrict__ frames, int64_t plane, const uint8_t* __restrict__ age_in,
-                                                        uint8_t* __restrict__ age_out, const uint8_t* __restrict__ term,
-                                                        const uint8_t* __restrict__ trunc, const PostStats* __restrict__ st,
-                                                        float* __restrict__ out, int64_t n, int k, int newest, float clip, int raw,
-                                                        int age_mode) {
-    const int D = k * OD, lanes = blockDim.x / D, t = threadIdx.x;
-    if (t >= lanes * D) return;
-    const int r = t / D, f = t % D, j = f / OD, c = f % OD, lag = k - 1 - j;
-    const double mean = st->mean[f], inv = st->inv_std[f];
+// ---- stacked (+ normalised) observation: thread-constant feature PAIR (26 is even, so a float2 never straddles two
+// ring slots and every load/store is 8-byte aligned), 4 envs in flight per thread, coalesced [N, 26k] output ----
+#define NORM_UNROLL 8
+__global__ void __launch_bounds__(512) normalize_kernel(const float* __restrict__ frames, int64_t plane, const uint8_t* __restrict__ age,
+                                                        const PostStats* __restrict__ st, float* __restrict__ out, int64_t n, int k,
+                                                        int newest, float clip, int raw) {
+    const int D = k * OD, P = D / 2, lanes = blockDim.x / P, t = threadIdx.x;
+    if (t >= lanes * P) return;
+    const int r = t / P, p = t % P, f = 2 * p, j = f / OD, c = f % OD, lag = k - 1 - j;
+    // SB3 evaluates (obs_f32 - mean_f64) / sqrt(var + eps) in float64 and rounds the result to float32.  Here the mean is
+    // split into a float pair (hi + lo), so the cancellation obs - mean keeps ~48 bits; the product and the clip are float:
+    // the result is within 2 float ulps of SB3's, without touching the FP64 pipe.
+    const float m0h = (float)st->mean[f], m0l = (float)(st->mean[f] - (double)m0h), i0 = (float)st->inv_std[f];
+    const float m1h = (float)st->mean[f + 1], m1l = (float)(st->mean[f + 1] - (double)m1h), i1 = (float)st->inv_std[f + 1];
     const float* src = frames + (int64_t)ring_slot(newest, lag, k) * plane + c;
-    for (int64_t e = (int64_t)blockIdx.x * lanes + r; e < n; e += (int64_t)gridDim.x * lanes) {
-        int age = age_mode == 2 ? 0 : (int)age_in[e];
-        if (age_mode == 1) {
-            age = (term[e] | trunc[e]) ? 0 : (age + 1 < k - 1 ? age + 1 : k - 1);
+    const int64_t stride = (int64_t)gridDim.x * lanes;
+    for (int64_t e0 = (int64_t)blockIdx.x * lanes + r; e0 < n; e0 += stride * NORM_UNROLL) {
+        float2 v[NORM_UNROLL];
+        int ag[NORM_UNROLL];
+        bool ok[NORM_UNROLL];
+#pragma unroll
+        for (int u = 0; u < NORM_UNROLL; ++u) {  // frame and age loads are independent: all in flight together; a slot
+            const int64_t e = e0 + u * stride;   // older than the env's episode holds stale but readable data
+            ok[u] = e < n;
+            v[u] = make_float2(0.f, 0.f);
+            ag[u] = 0;
+            if (ok[u]) { v[u] = __ldcs(reinterpret_cast<const float2*>(src + e * OD)); ag[u] = (int)__ldg(age + e); }
         }
-        if (age_mode != 0 && f == 0) age_out[e] = (uint8_t)age;
-        float v = lag <= age ? src[e * OD] : 0.f;
-        if (!raw) v = (float)fmin(fmax(((double)v - mean) * inv, -(double)clip), (double)clip);
-        out[e * D + f] = v;
+#pragma unroll
+        for (int u = 0; u < NORM_UNROLL; ++u) {
+            if (!ok[u]) continue;
+            float2 w = lag <= ag[u] ? v[u] : make_float2(0.f, 0.f);
+            if (!raw) {
+                w.x = fminf(fmaxf(((w.x - m0h) - m0l) * i0, -clip), clip);
+                w.y = fminf(fmaxf(((w.y - m1h) - m1l) * i1, -clip), clip);
+            }
+            __stcs(reinterpret_cast<float2*>(out + (e0 + u * stride) * D + f), w);
+        }
     }
 }
 
@@ -310,17 +332,14 @@ int hlynr_post_obs_target(hlynr_post_t* p, float** obs_dev) {
     return 0;
 }
 
-static int launch_normalize(hlynr_post* p, const uint8_t* term, const uint8_t* trunc, float* out, int raw, int age_mode, cudaStream_t st) {
-    const int lanes = 512 / p->D > 0 ? 512 / p->D : 1;
-    const int threads = lanes * p->D;
+static int launch_normalize(hlynr_post* p, float* out, int raw, cudaStream_t st) {
+    const int P = p->D / 2;
+    const int lanes = 512 / P > 0 ? 512 / P : 1;
     const int newest = (int)((p->t - 1) % (uint32_t)p->k);
-    const uint8_t* age_in = p->age[p->age_cur];
-    uint8_t* age_out = p->age[p->age_cur ^ 1];
-    normalize_kernel<<<blocks_for(p, p->n, lanes), threads, 0, st>>>(p->frames, p->plane, age_in, age_out, term, trunc, p->st, out, p->n,
-                                                                    p->k, newest, (float)p->clip, raw, age_mode);
+    normalize_kernel<<<blocks_for(p, (p->n + NORM_UNROLL - 1) / NORM_UNROLL, lanes), lanes * P, 0, st>>>(
+        p->frames, p->plane, p->age[p->age_cur], p->st, out, p->n, p->k, newest, (float)p->clip, raw);
     CK(cudaGetLastError());
     p->launches += 1;
-    if (age_mode != 0) p->age_cur ^= 1;
     return 0;
 }
 
@@ -336,7 +355,8 @@ int hlynr_post_reset(hlynr_post_t* p, float* out_dev, int training, void* stream
     CK(cudaGetLastError());
     p->launches += 2;
     p->sums_valid = true;
-    return launch_normalize(p, nullptr, nullptr, out_dev, 0, 2, st);
+    CK(cudaMemsetAsync(p->age[p->age_cur], 0, p->n, st));  // VecFrameStack.reset: only the newest frame is valid
+    return launch_normalize(p, out_dev, 0, st);
 }
 
 int hlynr_post_step(hlynr_post_t* p, const float* reward_dev, const uint8_t* terminated_dev, const uint8_t* truncated_dev,
@@ -356,7 +376,7 @@ int hlynr_post_step(hlynr_post_t* p, const float* reward_dev, const uint8_t* ter
     const uint8_t* age_old = p->age[p->age_cur];
     p->t += 1;
     returns_kernel<<<blocks_for(p, p->n, 256), 256, 0, st>>>(p->returns, reward_dev, terminated_dev, truncated_dev, p->n, p->gamma,
-                                                             &p->st->ret_sum, &p->st->ret_sq, training);
+                                                             &p->st->ret_sum, &p->st->ret_sq, training, age_old, p->age[p->age_cur ^ 1], p->k);
     p->launches += 1;
     if (can_maintain && p->sums_valid) {  // the sums follow the ring on every step; obs_rms / ret_rms only move when training
         colsum_kernel<<<blocks_for(p, p->n, 16), 16 * OD, 0, st>>>(frame, p->n, p->st->col, p->st->colq);
@@ -378,14 +398,15 @@ int hlynr_post_step(hlynr_post_t* p, const float* reward_dev, const uint8_t* ter
         p->launches += 1;
     }
     CK(cudaGetLastError());
-    return launch_normalize(p, terminated_dev, truncated_dev, out_dev, 0, 1, st);
+    p->age_cur ^= 1;  // returns_kernel wrote the new ages; done_corr / terminal above used the old ones
+    return launch_normalize(p, out_dev, 0, st);
 }
 
 int hlynr_post_original(hlynr_post_t* p, float* out_dev, void* stream) {
     if (!p || !out_dev) return fail("hlynr_post_original: null argument");
     if (p->t == 0) return fail("hlynr_post_original: no observation yet");
     DeviceGuard g(p->device);
-    return launch_normalize(p, nullptr, nullptr, out_dev, 1, 0, (cudaStream_t)stream);
+    return launch_normalize(p, out_dev, 1, (cudaStream_t)stream);
 }
 
 int hlynr_post_normalize(hlynr_post_t* p, const float* stacked_dev, int64_t rows, float* out_dev, void* stream) {
