@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--ref-envs", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused", type=int, default=64, help="k of the extra fused-rollout measurement (0 = skip)")
+    ap.add_argument("--post-steps", type=int, default=200, help="steps of the extra step + frame-stack/normalise measurement (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -264,6 +265,31 @@ def main():
         fused = {"k": args.fused, "value": world * n * args.fused * reps / (float(tf.item()) * 1e-3), "unit": "env-steps/s",
                  "note": "hlynr_rollout: k ticks per launch, in-kernel Philox random policy, obs written once"}
 
+    # extra: step + on-device VecFrameStack(4) + VecNormalize, the tensor a policy on the same GPU consumes
+    post = None
+    if args.post_steps > 0:
+        from hlynr_intercept_b200.post import HlynrObsPipeline
+
+        pipe = HlynrObsPipeline(sim, n_stack=4, training=True)
+        pipe.reset()
+        for k in range(5):
+            pipe.step(pool[k % 4])
+        barrier()
+        e0.record()
+        for k in range(args.post_steps):
+            pipe.step(pool[k % 4])
+        e1.record()
+        barrier()
+        tp = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        ms_post = float(tp.item()) / args.post_steps
+        post = {"value": world * n / (ms_post * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_post, "n_stack": 4,
+                "note": "hlynr_step writing into the frame ring + hlynr_post_step (stacked, normalised [N,104] output, running "
+                        "mean/var updated every step, stacked terminal observations)",
+                "algorithmic_bytes_per_env_step_post": 104 + 416 + 416 + 25}
+        pipe.close()
+
     # e2e: the numpy VecEnv API a Stable-Baselines3 user calls (host buffers, H2D + D2H inside the timed region)
     venv = HlynrVecEnv(env_cfg, n_envs=n, device=local_rank, seed=99, env_id_offset=rank * n, precision=args.precision,
                        warn_dead=False, lazy_infos=True)
@@ -314,6 +340,7 @@ def main():
                          "algorithmic_bytes_per_env_step": bytes_per_step, "units_per_launch": n,
                          "kernel_us_per_launch": per_launch_ms * 1e3},
             "fused_rollout": fused,
+            "obs_pipeline": post,
             "episode_stats": dict(zip(["episodes", "successes", "return_sum", "length_sum"], stats_host[:4])),
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -552,7 +552,7 @@ static int step_range(hlynr_sim* s, int64_t first, int64_t lim, const float* act
         // measured on B200 (profiles/r01_b): the direct kernel is faster than the TMA-prefetched persistent one (the
         // step is bound by in-warp dependency latency, not by load latency), so auto = direct; the TMA variant stays
         // selectable and parity-tested.  It needs 16-byte aligned actions and works on the whole shard only.
-        bool use_tma = s->kernel_variant == 2 && whole;
+        bool use_tma = s->kernel_variant == 2 && whole && s->params.obs_mode == HLYNR_OBS_WORLD;  // world_frame only
         if (((uintptr_t)actions_dev & 15u) != 0) use_tma = false;
         if (use_tma) {
             const int64_t n_tiles = (s->n + TMA_TILE - 1) / TMA_TILE;

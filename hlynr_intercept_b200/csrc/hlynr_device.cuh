@@ -87,6 +87,29 @@ HD float cdiv(float x, float c, float rc) {
 }
 HD double cdiv(double x, double c, double) { return __ddiv_rn(x, c); }
 
+// atan2 / asin for the euler-angle channels obs[9:12] (core.py:1103-1121): degree-7 minimax polynomial of atan(a)/a in
+// a^2 on [0,1] (max error 1.9e-7 rad, fitted and checked in float32), one MUFU reciprocal, quadrant fix-up: ~20
+// instructions instead of the ~57 of atan2f.  The channels are observations only (they never feed the dynamics).
+HD float fast_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mx > 0.f ? mn * nrcp(mx) : 0.f;
+    const float s = a * a;
+    float p = -0.004780525807291269f;
+    p = fmaf(p, s, 0.024557389318943024f);
+    p = fmaf(p, s, -0.05990511178970337f);
+    p = fmaf(p, s, 0.09942789375782013f);
+    p = fmaf(p, s, -0.14029431343078613f);
+    p = fmaf(p, s, 0.1997137814760208f);
+    p = fmaf(p, s, -0.3333209455013275f);
+    p = fmaf(p, s, 0.9999999403953552f);
+    float r = p * a;
+    if (ay > ax) r = 1.57079632679489662f - r;
+    if (x < 0.f) r = 3.14159265358979324f - r;
+    return copysignf(r, y);
+}
+HD float fast_asin(float x) { return fast_atan2(x, nsqrt((1.f - x) * (1.f + x))); }  // x already clipped to [-1, 1]
+
 template <typename T> struct alignas(sizeof(T) * 4) Vec4 { T x, y, z, w; };
 
 // ------------------------------------------------------------------------------------------------
@@ -360,6 +383,12 @@ HD void drag_accel(const KParams<R>& P, const Env<R>& e, R vx, R vy, R vz, R alt
     }
 }
 
+// true iff any of the three is NaN or +-inf: 0 * x is NaN exactly for those (float); exponent test on the high words (double)
+HD bool any_nonfinite(float a, float b, float c) { const float t = fmaf(a, 0.f, fmaf(b, 0.f, c * 0.f)); return t != t; }
+HD bool any_nonfinite(double a, double b, double c) {
+    const int e = max(max(__double2hiint(a) & 0x7ff00000, __double2hiint(b) & 0x7ff00000), __double2hiint(c) & 0x7ff00000);
+    return e == 0x7ff00000;
+}
 template <typename R> HD R nan_guard(R a, R lim) {  // np.nan_to_num(nan=0, posinf=lim, neginf=-lim)
     if (a != a) return R(0);
     if (isinf(a)) return a > R(0) ? lim : -lim;
@@ -647,9 +676,9 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
         const float sinp = 2.f * fmaf(w, y, -(z * x));
         const float siny = 2.f * fmaf(w, z, x * y), cosy = 1.f - 2.f * fmaf(y, y, z * z);
         const float ipi = 0.318309886183790672f;
-        out.put(9, atan2f(sinr, cosr) * ipi);
-        out.put(10, asinf(clip(sinp, -1.f, 1.f)) * ipi);
-        out.put(11, atan2f(siny, cosy) * ipi);
+        out.put(9, fast_atan2(sinr, cosr) * ipi);
+        out.put(10, fast_asin(clip(sinp, -1.f, 1.f)) * ipi);
+        out.put(11, fast_atan2(siny, cosy) * ipi);
     }
     out.put(12, clip((float)e.fuel * 0.01f, 0.f, 1.f));
     if (dg_det && link > 0.1f && mode == HLYNR_OBS_LOS) {  // core.py:985-1006: redundant range / rate measurements
@@ -909,7 +938,7 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
         R dax, day, daz;
         drag_accel<R, F>(P, e, vax, vay, vaz, alt, R(1.0), R(1.0), R(1.0 / 500.0), R(500.0), &dax, &day, &daz);
         R ax = add(tax, dax), ay = add(tay, day), az = add(add(taz, daz), (R)(-9.81f));
-        if (P.validate && !(isfinite(ax) && isfinite(ay) && isfinite(az))) {
+        if (P.validate && any_nonfinite(ax, ay, az)) {
             ax = nan_guard(ax, R(50)); ay = nan_guard(ay, R(50)); az = nan_guard(az, R(50));
         }
         // semi-implicit Euler, :933-934 (exact float ops, reference order)
@@ -932,7 +961,7 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
         // total_accel = drag + gravity + evasion is float64 in the reference even without evasion
         // (evasion = np.zeros(3)), and velocity += total_accel * dt is evaluated in float64: kept as is.
         double ax = (double)dax + ex, ay = (double)day + ey, az = (double)add(daz, (R)(-9.81f)) + ez;
-        if (P.validate && !(isfinite(ax) && isfinite(ay) && isfinite(az))) {
+        if (P.validate && any_nonfinite(ax, ay, az)) {
             ax = nan_guard(ax, 20.0); ay = nan_guard(ay, 20.0); az = nan_guard(az, 20.0);
         }
         e.mvx = (R)add((double)e.mvx, mul(ax, P.dt_d));
