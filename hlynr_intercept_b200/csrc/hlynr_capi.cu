@@ -147,6 +147,7 @@ struct hlynr_sim {
     cudaStream_t own_stream = nullptr;
     HostIO hio;
     int host_info = 1, host_chunks = 0, host_threads = 0;
+    int prefetch_waves = 1;  // CTAs per SM the step kernel looks ahead when it prefetches upcoming planes into L2 (0 = off)
     HlynrDoneRecord* done_records = nullptr;  // attached compact done list (hlynr_set_done_list)
     int32_t* done_counter = nullptr;
     int32_t done_cap = 0;
@@ -336,6 +337,7 @@ template <typename R> static KernelArgs<R> base_args(hlynr_sim* s, const StatePl
     A.o_row = A.P.onb_ring_len > 0 ? (int32_t)(s->tick % (uint32_t)A.P.onb_ring_len) : 0;
     A.io.stats = s->stats;
     A.k_steps = 1;
+    A.prefetch_ahead = s->sm_count * s->prefetch_waves * HLYNR_BLOCK;
     return A;
 }
 static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
@@ -505,6 +507,11 @@ int hlynr_set_option(hlynr_t* s, const char* name, int64_t value) {
     }
     if (strcmp(name, "specialise") == 0) { s->specialise = value != 0; return 0; }
     if (strcmp(name, "host_info") == 0) { s->host_info = value != 0; return 0; }
+    if (strcmp(name, "prefetch_waves") == 0) {
+        if (value < 0 || value > 64) return fail("prefetch_waves must be in [0, 64]");
+        s->prefetch_waves = (int)value;
+        return 0;
+    }
     if (strcmp(name, "host_chunks") == 0) {
         if (value < 0 || value > 64) return fail("host_chunks must be in [0, 64]");
         s->host_chunks = (int)value;

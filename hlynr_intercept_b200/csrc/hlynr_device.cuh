@@ -260,6 +260,7 @@ template <typename R> struct KernelArgs {
     int32_t auto_reset;
     int32_t k_steps;
     int32_t has_info;
+    int32_t prefetch_ahead;  // envs per resident wave of CTAs (0 = no L2 prefetch of the next wave's planes)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1207,6 +1208,45 @@ template <typename R> HD RngKey make_key(const KernelArgs<R>& A, int64_t global_
 
 #define HLYNR_BLOCK 128
 
+// The delay-ring samples a tick reads (one onboard slot, two ground planes) are needed only deep inside observe(),
+// ~1000 instructions after the kernel starts; without help their DRAM latency is fully exposed there (9 % + 3 % of all
+// stall samples in profiles/r01_c).  Their addresses depend only on the tick, so the lines are pulled into L1 up front,
+// at no register cost.  (With domain randomization the onboard delay is per-env state: that row is not prefetched.)
+HD void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+HD void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// State planes + actions of the CTA `prefetch_ahead` envs further on are touched with prefetch.global.L2 right after this
+// CTA's own loads are issued.  The up-front plane loads are the one latency nothing else in a warp can hide (16 % of the
+// stall samples in profiles/r01_c sit on their first use); measured on B200 at 2^20 envs (cfg4, 2000-tick bench):
+// look-ahead 0 / 1 / 2 / 3 / 4 CTAs per SM -> 122.9 / 116.0 / 118.4 / 119.7 / 124 us per launch.  DRAM traffic is unchanged.
+template <typename R, int F> HD void prefetch_next_wave(const KernelArgs<R>& A, int64_t j) {
+    typedef Feat<F> FT;
+    const StatePlanes<R>& s = A.st;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) prefetch_l2(s.r[k] + j);
+    if (FT::thrust_dyn(A.P) || FT::dr(A.P)) prefetch_l2(s.r[6] + j);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) prefetch_l2(s.f[k] + j);
+    if (FT::dr(A.P)) prefetch_l2(s.f[3] + j);
+    prefetch_l2(s.i0 + j);
+    if (A.io.actions) prefetch_l2(A.io.actions + j * HLYNR_ACT_DIM);
+}
+template <typename R, int F> HD void prefetch_ring_reads(const KernelArgs<R>& A, int64_t i, int g_row, int o_row) {
+    typedef Feat<F> FT;
+    const KParams<R>& P = A.P;
+    const int64_t n = A.ring_stride;
+    if (FT::onboard_delay(P) && !FT::dr(P)) {
+        int rrow = o_row - P.onboard_delay;
+        if (rrow < 0) rrow += P.onb_ring_len;
+        prefetch_l1(A.st.oring + (int64_t)rrow * n + i);
+    }
+    if (FT::ground(P) && FT::ground_delay(P)) {
+        const int rrow = g_row + 1 == P.gnd_ring_len ? 0 : g_row + 1;
+        const Vec4<R>* rr = A.st.gring + (int64_t)rrow * 2 * n;
+        prefetch_l1(rr + i);
+        prefetch_l1(rr + n + i);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
@@ -1219,8 +1259,10 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, (F == FT_V2OFF && sizeof(R) == 4)
     const int64_t warp_first = i - lane;
     const bool active = i < A.lim;
     const int64_t ii = active ? i : A.lim - 1;  // inactive lanes shadow the last env and never store
+    prefetch_ring_reads<R, F>(A, i, A.g_row, A.o_row);
     Env<R> e;
     load_env<R, F>(A, ii, e);
+    if (!kRollout && A.prefetch_ahead > 0 && i + A.prefetch_ahead < A.lim) prefetch_next_wave<R, F>(A, i + A.prefetch_ahead);
     const RngKey key = make_key(A, A.env_offset + ii);
     const int steps = kRollout ? A.k_steps : 1;
     float rsum = 0.f;
@@ -1284,6 +1326,7 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, (F == FT_V2OFF && sizeof(R) == 4)
         if (kRollout) {  // next tick's ring rows
             g_row = g_row + 1 >= A.P.gnd_ring_len ? 0 : g_row + 1;
             o_row = o_row + 1 >= A.P.onb_ring_len ? 0 : o_row + 1;
+            if (s + 1 < steps) prefetch_ring_reads<R, F>(A, i, g_row, o_row);
         }
     }
     if (A.io.obs) flush_obs_tile(tiles[warp], A.io.obs, warp_first, A.lim, lane);

@@ -303,7 +303,9 @@ int hlynr_debug_draws(hlynr_t* sim, int64_t env_global_id, uint32_t episode, uin
  * "host_info": 1 (default) = hlynr_step_host also fills the [N]-sized info arrays read by hlynr_info_host, 0 = skip them
  * (finished episodes are still reported through hlynr_done_records_host).
  * "host_chunks": number of chunks hlynr_step_host pipelines (H2D | kernel | D2H on separate streams), 0 = auto.
- * "host_threads": threads used for staging memcpys of unpinned caller buffers, 0 = auto. */
+ * "host_threads": threads used for staging memcpys of unpinned caller buffers, 0 = auto.
+ * "prefetch_waves": the step kernel prefetches into L2 the state planes of the CTA this many CTAs-per-SM further on
+ * (default 1, measured best on B200; 0 = off). */
 int hlynr_set_option(hlynr_t* sim, const char* name, int64_t value);
 
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
