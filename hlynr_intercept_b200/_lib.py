@@ -20,6 +20,8 @@ EXPORTS = [
     "hlynr_post_create", "hlynr_post_destroy", "hlynr_post_obs_dim", "hlynr_post_obs_target", "hlynr_post_reset",
     "hlynr_post_step", "hlynr_post_original", "hlynr_post_normalize", "hlynr_post_get_stats", "hlynr_post_set_stats",
     "hlynr_post_check_sums", "hlynr_post_launch_count",
+    # include/hlynr_rollout.h
+    "hlynr_bootstrap_timeouts", "hlynr_gae",
 ]
 
 
@@ -85,6 +87,8 @@ def load(build_if_missing=True):
     L.hlynr_post_set_stats.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl, vp]
     L.hlynr_post_check_sums.argtypes = [vp, i32, pd, vp]
     L.hlynr_post_launch_count.argtypes = [vp, C.POINTER(i64)]
+    L.hlynr_bootstrap_timeouts.argtypes = [vp, vp, vp, C.c_int32, vp, C.c_double, vp, i32, vp]
+    L.hlynr_gae.argtypes = [vp, vp, vp, vp, vp, i64, i64, C.c_double, C.c_double, vp, vp, i32, vp]
     if L.hlynr_abi_version() != abi.ABI_VERSION:
         raise HlynrError("ABI version mismatch between libhlynr_b200.so and hlynr_intercept_b200.abi")
     if L.hlynr_params_size() != C.sizeof(abi.HlynrParams):

@@ -54,7 +54,13 @@ struct DeviceGuard {
 __device__ __forceinline__ int ring_slot(int newest, int lag, int k) { int s = newest - lag; return s < 0 ? s + k : s; }
 
 // ---- sums over the new frame: thread-constant channel, 16 envs per 416-thread block iteration, coalesced ----
-__global__ void __launch_bounds__(16 * OD) colsum_kernel(const float* __restrict__ frame, int64_t n, double* col, double* colq) {
+// Every reduction of this file is two-stage and atomic-free: blocks write partial sums to partials[block][word], one
+// block per word then folds them in a fixed order, so the statistics (and with them the normalised observations) are
+// bit-reproducible from run to run.
+constexpr int PW_COL = 0, PW_COLQ = OD, PW_RET = 2 * OD, PW_RETQ = 2 * OD + 1, PW_CORR = 2 * OD + 2;
+constexpr int PART_WORDS = PW_CORR + 2 * (KMAX - 1) * OD;   // + corr[(k-1)][26], corrq[(k-1)][26]
+
+__global__ void __launch_bounds__(16 * OD) colsum_kernel(const float* __restrict__ frame, int64_t n, double* __restrict__ partials) {
     __shared__ double sh[16 * OD];
     const int t = threadIdx.x, c = t % OD, r = t / OD;
     double s = 0.0, q = 0.0;
@@ -64,11 +70,33 @@ __global__ void __launch_bounds__(16 * OD) colsum_kernel(const float* __restrict
     }
     sh[t] = s;
     __syncthreads();
-    if (r == 0) { double a = 0.0; for (int i = 0; i < 16; ++i) a += sh[i * OD + c]; atomicAdd(col + c, a); }
+    double* mine = partials + (size_t)blockIdx.x * PART_WORDS;
+    if (r == 0) { double a = 0.0; for (int i = 0; i < 16; ++i) a += sh[i * OD + c]; mine[PW_COL + c] = a; }
     __syncthreads();
     sh[t] = q;
     __syncthreads();
-    if (r == 0) { double a = 0.0; for (int i = 0; i < 16; ++i) a += sh[i * OD + c]; atomicAdd(colq + c, a); }
+    if (r == 0) { double a = 0.0; for (int i = 0; i < 16; ++i) a += sh[i * OD + c]; mine[PW_COLQ + c] = a; }
+}
+
+// second stage: block w folds word w of the partial rows (fixed order) into its PostStats field
+__global__ void __launch_bounds__(256) fold_kernel(const double* __restrict__ partials, int nb_col, int nb_ret, int nb_corr, int per,
+                                                   PostStats* st) {
+    __shared__ double sh[256];
+    const int w = blockIdx.x < 2 * OD + 2 ? blockIdx.x : PW_CORR + (blockIdx.x - (2 * OD + 2));
+    const int nblocks = w < 2 * OD ? nb_col : (w < PW_CORR ? nb_ret : nb_corr);
+    double a = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) a += partials[(size_t)b * PART_WORDS + w];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    if (w < 2 * OD) (&st->col[0])[w] = sh[0];                       // col[26], colq[26] are adjacent
+    else if (w < PW_CORR) (&st->ret_sum)[w - 2 * OD] = sh[0];        // ret_sum, ret_sq
+    else if (w - PW_CORR < per) (&st->corr[1][0])[w - PW_CORR] = sh[0];
+    else (&st->corrq[1][0])[w - PW_CORR - per] = sh[0];
 }
 
 // ---- VecNormalize._update_reward: returns = returns * gamma + reward; ret_rms sums; returns[done] = 0 ----
@@ -76,7 +104,7 @@ __global__ void __launch_bounds__(16 * OD) colsum_kernel(const float* __restrict
 // ring belong to the env's current episode).
 __global__ void __launch_bounds__(256) returns_kernel(double* __restrict__ ret, const float* __restrict__ rew,
                                                       const uint8_t* __restrict__ term, const uint8_t* __restrict__ trunc, int64_t n,
-                                                      double gamma, double* ret_sum, double* ret_sq, int training,
+                                                      double gamma, double* __restrict__ partials, int training,
                                                       const uint8_t* __restrict__ age_in, uint8_t* __restrict__ age_out, int k) {
     double s = 0.0, q = 0.0;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
@@ -97,7 +125,7 @@ __global__ void __launch_bounds__(256) returns_kernel(double* __restrict__ ret, 
     if (threadIdx.x == 0) {
         double a = 0.0, b = 0.0;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += shs[i]; b += shq[i]; }
-        atomicAdd(ret_sum, a); atomicAdd(ret_sq, b);
+        partials[(size_t)blockIdx.x * PART_WORDS + PW_RET] = a; partials[(size_t)blockIdx.x * PART_WORDS + PW_RETQ] = b;
     }
 }
 
@@ -105,7 +133,8 @@ __global__ void __launch_bounds__(256) returns_kernel(double* __restrict__ ret, 
 // thread = (record lane r, old lag d in [0, k-2], channel c); old lag d becomes lag d+1 for the envs that go on.
 __global__ void __launch_bounds__(512) done_corr_kernel(const HlynrDoneRecord* __restrict__ recs, const int32_t* __restrict__ counter,
                                                         int32_t cap, const float* __restrict__ frames, int64_t plane,
-                                                        const uint8_t* __restrict__ age_old, int k, int newest_old, PostStats* st) {
+                                                        const uint8_t* __restrict__ age_old, int k, int newest_old,
+                                                        double* __restrict__ partials) {
     const int per = (k - 1) * OD;                 // threads per record
     const int lanes = blockDim.x / per;           // records per block iteration
     const int t = threadIdx.x;
@@ -119,7 +148,16 @@ __global__ void __launch_bounds__(512) done_corr_kernel(const HlynrDoneRecord* _
         const int32_t e = recs[i].env;
         if (d <= (int)age_old[e]) { const double v = (double)src[(int64_t)e * OD + c]; s += v; q += v * v; }
     }
-    if (s != 0.0 || q != 0.0) { atomicAdd(&st->corr[d + 1][c], s); atomicAdd(&st->corrq[d + 1][c], q); }
+    // fold the record lanes of this block, then one partial row per block: [corr (k-1)*26 | corrq (k-1)*26]
+    __shared__ double sh[512];
+    sh[t] = s;
+    __syncthreads();
+    double* mine = partials + (size_t)blockIdx.x * PART_WORDS + PW_CORR;
+    if (r == 0) { double a = 0.0; for (int i = 0; i < lanes; ++i) a += sh[i * per + f]; mine[f] = a; }
+    __syncthreads();
+    sh[t] = q;
+    __syncthreads();
+    if (r == 0) { double a = 0.0; for (int i = 0; i < lanes; ++i) a += sh[i * per + f]; mine[per + f] = a; }
 }
 
 // ---- shift the per-lag sums, merge the batch moments into obs_rms / ret_rms (RunningMeanStd.update_from_moments) ----
@@ -266,6 +304,7 @@ struct hlynr_post {
     int age_cur = 0;
     double* returns = nullptr;
     PostStats* st = nullptr;
+    double* partials = nullptr; // [max_blocks][PART_WORDS] first-stage sums
     uint32_t t = 0;             // frames written so far; target slot = t % k, newest = (t - 1) % k
     bool sums_valid = false;    // the per-lag sums S/Q describe the current ring (maintained by every reset/step that can)
     int sm_count = 148;
@@ -300,6 +339,8 @@ int hlynr_post_create(int64_t n_envs, int device, int n_stack, double clip_obs, 
     if (e == cudaSuccess) e = cudaMalloc(&p->age[1], n_envs);
     if (e == cudaSuccess) e = cudaMalloc(&p->returns, sizeof(double) * n_envs);
     if (e == cudaSuccess) e = cudaMalloc(&p->st, sizeof(PostStats));
+    if (e == cudaSuccess) e = cudaMalloc(&p->partials, sizeof(double) * PART_WORDS * ((size_t)p->sm_count * 8 + 64));
+    if (e == cudaSuccess) e = cudaMemset(p->partials, 0, sizeof(double) * PART_WORDS * ((size_t)p->sm_count * 8 + 64));
     if (e != cudaSuccess) { int r = fail("hlynr_post_create: cudaMalloc failed: %s", cudaGetErrorString(e)); hlynr_post_destroy(p); return r; }
     cudaMemset(p->frames, 0, sizeof(float) * p->plane * n_stack);
     cudaMemset(p->age[0], 0, n_envs); cudaMemset(p->age[1], 0, n_envs);
@@ -319,7 +360,7 @@ int hlynr_post_create(int64_t n_envs, int device, int n_stack, double clip_obs, 
 void hlynr_post_destroy(hlynr_post_t* p) {
     if (!p) return;
     DeviceGuard g(p->device);
-    cudaFree(p->frames); cudaFree(p->age[0]); cudaFree(p->age[1]); cudaFree(p->returns); cudaFree(p->st);
+    cudaFree(p->frames); cudaFree(p->age[0]); cudaFree(p->age[1]); cudaFree(p->returns); cudaFree(p->st); cudaFree(p->partials);
     delete p;
 }
 
@@ -350,10 +391,12 @@ int hlynr_post_reset(hlynr_post_t* p, float* out_dev, int training, void* stream
     const float* frame = p->frames + (int64_t)(p->t % (uint32_t)p->k) * p->plane;
     p->t += 1;
     CK(cudaMemsetAsync(p->returns, 0, sizeof(double) * p->n, st));  // VecNormalize.reset: returns = zeros
-    colsum_kernel<<<blocks_for(p, p->n, 16), 16 * OD, 0, st>>>(frame, p->n, p->st->col, p->st->colq);
+    const int nb_col = blocks_for(p, p->n, 16);
+    colsum_kernel<<<nb_col, 16 * OD, 0, st>>>(frame, p->n, p->partials);
+    fold_kernel<<<2 * OD, 256, 0, st>>>(p->partials, nb_col, 0, 0, 0, p->st);
     merge_kernel<<<1, 256, 0, st>>>(p->st, p->k, (double)p->n, 1, training, 1, 0, p->eps);
     CK(cudaGetLastError());
-    p->launches += 2;
+    p->launches += 3;
     p->sums_valid = true;
     CK(cudaMemsetAsync(p->age[p->age_cur], 0, p->n, st));  // VecFrameStack.reset: only the newest frame is valid
     return launch_normalize(p, out_dev, 0, st);
@@ -375,17 +418,23 @@ int hlynr_post_step(hlynr_post_t* p, const float* reward_dev, const uint8_t* ter
     const float* frame = p->frames + (int64_t)(p->t % (uint32_t)p->k) * p->plane;
     const uint8_t* age_old = p->age[p->age_cur];
     p->t += 1;
-    returns_kernel<<<blocks_for(p, p->n, 256), 256, 0, st>>>(p->returns, reward_dev, terminated_dev, truncated_dev, p->n, p->gamma,
-                                                             &p->st->ret_sum, &p->st->ret_sq, training, age_old, p->age[p->age_cur ^ 1], p->k);
+    const int nb_ret = blocks_for(p, p->n, 256);
+    returns_kernel<<<nb_ret, 256, 0, st>>>(p->returns, reward_dev, terminated_dev, truncated_dev, p->n, p->gamma, p->partials, training,
+                                           age_old, p->age[p->age_cur ^ 1], p->k);
     p->launches += 1;
     if (can_maintain && p->sums_valid) {  // the sums follow the ring on every step; obs_rms / ret_rms only move when training
-        colsum_kernel<<<blocks_for(p, p->n, 16), 16 * OD, 0, st>>>(frame, p->n, p->st->col, p->st->colq);
+        const int nb_col = blocks_for(p, p->n, 16);
+        colsum_kernel<<<nb_col, 16 * OD, 0, st>>>(frame, p->n, p->partials);
         p->launches += 1;
+        const int per = (p->k - 1) * OD;
         if (p->k > 1) {
-            const int per = (p->k - 1) * OD, lanes = 512 / per;
-            done_corr_kernel<<<64, lanes * per, 0, st>>>(records_dev, counter_dev, capacity, p->frames, p->plane, age_old, p->k, newest_old, p->st);
+            const int lanes = 512 / per;
+            done_corr_kernel<<<64, lanes * per, 0, st>>>(records_dev, counter_dev, capacity, p->frames, p->plane, age_old, p->k, newest_old,
+                                                         p->partials);
             p->launches += 1;
         }
+        fold_kernel<<<2 * OD + 2 + 2 * per, 256, 0, st>>>(p->partials, nb_col, training ? nb_ret : 0, 64, per, p->st);
+        p->launches += 1;
         merge_kernel<<<1, 256, 0, st>>>(p->st, p->k, (double)p->n, 1, training, 0, training, p->eps);
         p->launches += 1;
     } else {

@@ -63,13 +63,21 @@ class HlynrObsPipeline:
         return 1 if (self.training and self.norm_obs) else 0
 
     # ---- VecEnv-like surface on device tensors ----
-    def reset(self):
-        """VecFrameStack.reset + VecNormalize.reset: returns the stacked, normalised observation [N, 26*n_stack]."""
-        _lib.check(self.L.hlynr_reset(self.sim.h, None, self._target(), self._stream()))
-        _lib.check(self.L.hlynr_post_reset(self.h, C.c_void_p(self._out.data_ptr()), self._train_flag(), self._stream()))
-        return self._out
+    def _check_out(self, out, shape):
+        t = self._torch
+        if not (out.is_cuda and out.dtype == t.float32 and tuple(out.shape) == shape and out.is_contiguous()):
+            raise ValueError(f"output tensor must be a contiguous cuda float32 tensor of shape {shape}")
+        return out
 
-    def step(self, actions, auto_reset=True):
+    def reset(self, out=None):
+        """VecFrameStack.reset + VecNormalize.reset: returns the stacked, normalised observation [N, 26*n_stack]
+        (written into `out` if given, e.g. a row of a rollout buffer)."""
+        dst = self._out if out is None else self._check_out(out, (self.sim.n, self.obs_dim))
+        _lib.check(self.L.hlynr_reset(self.sim.h, None, self._target(), self._stream()))
+        _lib.check(self.L.hlynr_post_reset(self.h, C.c_void_p(dst.data_ptr()), self._train_flag(), self._stream()))
+        return dst
+
+    def step(self, actions, auto_reset=True, out=None, reward_out=None):
         """One tick + post-processing.  Returns (obs[N, 26k], reward[N], terminated[N], truncated[N], done) where
         `done` = (records uint8 tensor viewable with abi.done_record_numpy_dtype, counter int32[1],
         terminal_obs[capacity, 26k] or None): row r of terminal_obs is the stacked + normalised
@@ -78,17 +86,19 @@ class HlynrObsPipeline:
         if not (actions.is_cuda and actions.dtype == t.float32 and actions.shape == (sim.n, 6) and actions.is_contiguous()):
             actions = actions.to(device=sim.device, dtype=t.float32).reshape(sim.n, 6).contiguous()
         o = sim._alloc_out()
+        dst = self._out if out is None else self._check_out(out, (sim.n, self.obs_dim))
+        rew = o["reward"] if reward_out is None else self._check_out(reward_out, (sim.n,))
         self._counter.zero_()
         st = self._stream()
-        _lib.check(self.L.hlynr_step(sim.h, C.c_void_p(actions.data_ptr()), self._target(), C.c_void_p(o["reward"].data_ptr()),
+        _lib.check(self.L.hlynr_step(sim.h, C.c_void_p(actions.data_ptr()), self._target(), C.c_void_p(rew.data_ptr()),
                                      C.c_void_p(o["terminated"].data_ptr()), C.c_void_p(o["truncated"].data_ptr()), None, None,
                                      int(auto_reset), st))
-        _lib.check(self.L.hlynr_post_step(self.h, C.c_void_p(o["reward"].data_ptr()), C.c_void_p(o["terminated"].data_ptr()),
+        _lib.check(self.L.hlynr_post_step(self.h, C.c_void_p(rew.data_ptr()), C.c_void_p(o["terminated"].data_ptr()),
                                           C.c_void_p(o["truncated"].data_ptr()), C.c_void_p(self._records.data_ptr()),
-                                          C.c_void_p(self._counter.data_ptr()), sim.n, C.c_void_p(self._out.data_ptr()),
+                                          C.c_void_p(self._counter.data_ptr()), sim.n, C.c_void_p(dst.data_ptr()),
                                           C.c_void_p(self._terminal.data_ptr()) if self._terminal is not None else None,
                                           self._train_flag(), st))
-        return self._out, o["reward"], o["terminated"], o["truncated"], (self._records, self._counter, self._terminal)
+        return dst, rew, o["terminated"], o["truncated"], (self._records, self._counter, self._terminal)
 
     def done_records(self):
         """Host copy of the finished episodes of the last step (synchronises)."""

@@ -1,0 +1,127 @@
+"""On-device PPO rollout collection over the tensor API (BASELINE config 5).
+
+The reference collects rollouts through stable-baselines3 (`model.learn`, rl_system/scripts/train_flat_ppo.py:431-448):
+per step a policy forward, env.step through the VecEnv wrappers, the TimeLimit bootstrap
+(`rewards[i] += gamma * V(terminal_observation)`), a NumPy rollout buffer, and GAE(lambda) at the end.  Here the whole
+loop stays on the GPU: the simulator writes into the frame ring, `HlynrObsPipeline` writes the stacked + normalised
+observation straight into the next row of the rollout buffer, finished episodes are a compact device-side list, and the
+two non-GEMM steps (timeout bootstrap, GAE) are CUDA kernels behind include/hlynr_rollout.h.  No host synchronisation
+happens inside `collect()`.
+
+The policy network is the caller's torch module (plumbing: cuBLAS GEMMs); `GaussianMlpPolicy` is a minimal stand-in with
+SB3's MlpPolicy shape (separate pi / vf MLPs, state-independent log_std) for synthetic rollouts and the benchmark.
+"""
+import ctypes as C
+import math
+
+from . import _lib
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+class GaussianMlpPolicy:
+    """Factory: returns a torch.nn.Module with forward(obs) -> (actions, values, log_probs) and value(obs)."""
+
+    def __new__(cls, obs_dim, act_dim=6, net_arch=(512, 512, 256), layer_norm=True, log_std_init=0.0, device="cuda", dtype=None):
+        torch = _torch()
+        nn = torch.nn
+
+        def mlp(out_dim):
+            layers, d = [], obs_dim
+            for h in net_arch:
+                layers.append(nn.Linear(d, h))
+                if layer_norm:
+                    layers.append(nn.LayerNorm(h))
+                layers.append(nn.Tanh())
+                d = h
+            layers.append(nn.Linear(d, out_dim))
+            return nn.Sequential(*layers)
+
+        class _Policy(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.pi, self.vf = mlp(act_dim), mlp(1)
+                self.log_std = nn.Parameter(torch.full((act_dim,), float(log_std_init)))
+
+            def value(self, obs):
+                return self.vf(obs).squeeze(-1).float()
+
+            def forward(self, obs):
+                mean = self.pi(obs).float()
+                std = self.log_std.exp()
+                actions = mean + std * torch.randn_like(mean)
+                logp = (-0.5 * ((actions - mean) / std) ** 2 - self.log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+                return actions, self.value(obs), logp
+
+        m = _Policy().to(device)
+        if dtype is not None:
+            m = m.to(dtype)
+        return m
+
+
+class DeviceRolloutCollector:
+    """SB3 OnPolicyAlgorithm.collect_rollouts + RolloutBuffer.compute_returns_and_advantage on device tensors."""
+
+    def __init__(self, pipe, policy, n_steps, gamma=0.99, gae_lambda=0.95, bootstrap_rows=None):
+        torch = _torch()
+        self.pipe, self.policy, self.sim = pipe, policy, pipe.sim
+        self.T, self.gamma, self.gae_lambda = int(n_steps), float(gamma), float(gae_lambda)
+        n, d, dev = self.sim.n, pipe.obs_dim, self.sim.device
+        f32 = torch.float32
+        self.obs = torch.empty((self.T + 1, n, d), dtype=f32, device=dev)   # row T = observation after the last step
+        self.actions = torch.empty((self.T, n, 6), dtype=f32, device=dev)
+        self.rewards = torch.empty((self.T, n), dtype=f32, device=dev)
+        self.episode_starts = torch.empty((self.T, n), dtype=f32, device=dev)
+        self.values = torch.empty((self.T, n), dtype=f32, device=dev)
+        self.log_probs = torch.empty((self.T, n), dtype=f32, device=dev)
+        self.advantages = torch.empty((self.T, n), dtype=f32, device=dev)
+        self.returns = torch.empty((self.T, n), dtype=f32, device=dev)
+        self.last_dones = torch.ones(n, dtype=torch.uint8, device=dev)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.rows = int(bootstrap_rows) if bootstrap_rows else min(n, max(256, n // 32))
+        self._started = False
+        self.L = pipe.L
+
+    def _stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.sim.device).cuda_stream)
+
+    def reset(self):
+        self.pipe.reset(out=self.obs[0])
+        self.last_dones.fill_(1)   # SB3: _last_episode_starts = ones
+        self._started = True
+
+    def collect(self):
+        """Fills the buffers with n_steps transitions of every env and computes advantages / returns.  Returns self."""
+        torch = _torch()
+        if not self._started:
+            self.reset()
+        else:
+            self.obs[0].copy_(self.obs[self.T])
+        pipe, pol, sim = self.pipe, self.policy, self.sim
+        p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+        with torch.no_grad():
+            for t in range(self.T):
+                o = self.obs[t]
+                a, v, lp = pol(o if next(pol.parameters()).dtype == torch.float32 else o.to(next(pol.parameters()).dtype))
+                self.actions[t].copy_(a)
+                self.values[t].copy_(v)
+                self.log_probs[t].copy_(lp)
+                self.episode_starts[t].copy_(self.last_dones)
+                _, rew, te, tr, (records, counter, terminal) = pipe.step(a.float().clamp(-1.0, 1.0), out=self.obs[t + 1], reward_out=self.rewards[t])
+                # TimeLimit bootstrap on the first `rows` finished episodes of the step (more only if nearly every env
+                # finishes in the same step; counted in self.overflow)
+                term_rows = terminal[: self.rows]
+                tv = pol.value(term_rows if next(pol.parameters()).dtype == torch.float32 else term_rows.to(next(pol.parameters()).dtype)).contiguous()
+                _lib.check(self.L.hlynr_bootstrap_timeouts(p(self.rewards[t]), p(records), p(counter), self.rows, p(tv), self.gamma,
+                                                           p(self.overflow), sim.device_index, self._stream()))
+                torch.bitwise_or(te, tr, out=self.last_dones)
+            o = self.obs[self.T]
+            last_values = pol.value(o if next(pol.parameters()).dtype == torch.float32 else o.to(next(pol.parameters()).dtype)).contiguous()
+            _lib.check(self.L.hlynr_gae(p(self.rewards), p(self.values), p(self.episode_starts), p(last_values), p(self.last_dones),
+                                        self.T, sim.n, self.gamma, self.gae_lambda, p(self.advantages), p(self.returns),
+                                        sim.device_index, self._stream()))
+        return self

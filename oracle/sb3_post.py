@@ -108,3 +108,21 @@ class VecNormalize:
                 info["terminal_observation"] = self.normalize_obs(info["terminal_observation"])
         self.returns[dones.astype(bool)] = 0
         return obs, rewards, dones, infos
+
+
+def compute_returns_and_advantage(rewards, values, episode_starts, last_values, dones, gamma, gae_lambda):
+    """RolloutBuffer.compute_returns_and_advantage (common/buffers.py), float32 arrays [T, N]."""
+    T = rewards.shape[0]
+    advantages = np.zeros_like(rewards)
+    last_gae_lam = 0
+    for step in reversed(range(T)):
+        if step == T - 1:
+            next_non_terminal = 1.0 - dones.astype(np.float32)
+            next_values = last_values
+        else:
+            next_non_terminal = 1.0 - episode_starts[step + 1]
+            next_values = values[step + 1]
+        delta = rewards[step] + gamma * next_values * next_non_terminal - values[step]
+        last_gae_lam = delta + gamma * gae_lambda * next_non_terminal * last_gae_lam
+        advantages[step] = last_gae_lam
+    return advantages, advantages + values

@@ -10,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_symbols():
-    src = open(os.path.join(ROOT, "include", "hlynr.h")).read() + open(os.path.join(ROOT, "include", "hlynr_post.h")).read()
+    src = open(os.path.join(ROOT, "include", "hlynr.h")).read() + open(os.path.join(ROOT, "include", "hlynr_post.h")).read() + \
+        open(os.path.join(ROOT, "include", "hlynr_rollout.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(hlynr_[a-z_0-9]+)\s*\(", src)))
 
