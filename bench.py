@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--ref-envs", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused", type=int, default=64, help="k of the extra fused-rollout measurement (0 = skip)")
+    ap.add_argument("--rollout-steps", type=int, default=16, help="n_steps of the extra on-device PPO rollout-collection measurement (0 = skip)")
+    ap.add_argument("--rollout-envs", type=int, default=131072)
     ap.add_argument("--post-steps", type=int, default=200, help="steps of the extra step + frame-stack/normalise measurement (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -290,6 +292,67 @@ def main():
                 "algorithmic_bytes_per_env_step_post": 104 + 416 + 416 + 25}
         pipe.close()
 
+    # extra: PPO rollout collection fully on the device (SURVEY 8f rank 4 / BASELINE config 5): policy forward (torch MLP
+    # 104 -> 512 -> 512 -> 256, LayerNorm), env step, frame-stack/normalise, TimeLimit bootstrap, GAE; no host
+    # synchronisation inside collect()
+    roll = None
+    if args.rollout_steps > 0:
+        from hlynr_intercept_b200.post import HlynrObsPipeline
+        from hlynr_intercept_b200.rollout import DeviceRolloutCollector, GaussianMlpPolicy
+
+        n_roll = min(n, args.rollout_envs)
+        rsim = HlynrSim(env_cfg, n_envs=n_roll, device=local_rank, seed=4321, env_id_offset=rank * n_roll, precision=args.precision,
+                        warn_dead=False)
+        rpipe = HlynrObsPipeline(rsim, n_stack=4, training=True)
+        torch.manual_seed(rank)
+        torch.backends.cuda.matmul.allow_tf32 = True   # the policy GEMMs are the caller's; TF32 tensor cores as PPO users run them
+        torch.backends.cudnn.allow_tf32 = True
+        pol = GaussianMlpPolicy(104, device=dev)
+        col = DeviceRolloutCollector(rpipe, pol, args.rollout_steps)
+        col.collect()
+        barrier()
+        e0.record()
+        col.collect()
+        e1.record()
+        barrier()
+        tr_ = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tr_, op=dist.ReduceOp.MAX)
+        # the same loop without the policy network (random actions): what the simulator side costs
+        class _NoPolicy(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.dummy = torch.nn.Parameter(torch.zeros(1, device=dev))
+
+            def value(self, obs):
+                return obs[:, 0].contiguous()
+
+            def forward(self, obs):
+                a = torch.rand(obs.shape[0], 6, device=obs.device) * 2 - 1
+                return a, obs[:, 0], obs[:, 1]
+
+        col2 = DeviceRolloutCollector(rpipe, _NoPolicy(), args.rollout_steps)
+        col2._started = True
+        col2.obs[col2.T].copy_(col.obs[col.T])
+        col2.collect()
+        barrier()
+        e0.record()
+        col2.collect()
+        e1.record()
+        barrier()
+        tn_ = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tn_, op=dist.ReduceOp.MAX)
+        roll = {"value": world * n_roll * args.rollout_steps / (float(tr_.item()) * 1e-3), "unit": "env-steps/s",
+                "envs_per_gpu": n_roll, "n_steps": args.rollout_steps,
+                "policy": "GaussianMlpPolicy 104->512->512->256 (pi and vf), LayerNorm, fp32 weights, TF32 GEMMs (torch / cuBLAS)",
+                "without_policy_network": world * n_roll * args.rollout_steps / (float(tn_.item()) * 1e-3),
+                "timeout_bootstrap_overflow": int(col.overflow.item()),
+                "note": "DeviceRolloutCollector.collect(): policy forward + hlynr_step + hlynr_post_step + "
+                        "hlynr_bootstrap_timeouts per step, hlynr_gae at the end; buffers [T,N,*] resident in HBM"}
+        rpipe.close()
+        rsim.close()
+
     # e2e: the numpy VecEnv API a Stable-Baselines3 user calls (host buffers, H2D + D2H inside the timed region)
     venv = HlynrVecEnv(env_cfg, n_envs=n, device=local_rank, seed=99, env_id_offset=rank * n, precision=args.precision,
                        warn_dead=False, lazy_infos=True)
@@ -341,6 +404,7 @@ def main():
                          "kernel_us_per_launch": per_launch_ms * 1e3},
             "fused_rollout": fused,
             "obs_pipeline": post,
+            "rollout_collection": roll,
             "episode_stats": dict(zip(["episodes", "successes", "return_sum", "length_sum"], stats_host[:4])),
         }
         if world == 1 and not args.no_cpu_baseline:
