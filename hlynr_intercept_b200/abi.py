@@ -6,6 +6,7 @@ ABI_VERSION = 1
 OBS_DIM = 26
 ACT_DIM = 6
 N_DR = 13
+MAX_VOLLEY = 8
 STATS_WORDS = 16
 FP32, FP64 = 32, 64
 OBS_WORLD, OBS_BODY, OBS_LOS = 0, 1, 2
@@ -41,7 +42,7 @@ class HlynrParams(C.Structure):
         ("g_sigma_r", C.c_double), ("g_sigma_v", C.c_double), ("g_base_quality", C.c_double),
         ("max_datalink_range", C.c_double), ("datalink_packet_loss", C.c_double),
         ("obs_mode", C.c_int32), ("precision_mode", C.c_int32), ("fuze_enabled", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("volley_size", C.c_int32),
         ("kill_radius", C.c_double),
     ]
 
@@ -55,7 +56,8 @@ class HlynrInfoSoA(C.Structure):
     _fields_ = [("distance", C.c_void_p), ("min_distance", C.c_void_p), ("fuel_remaining", C.c_void_p),
                 ("fuel_used", C.c_void_p), ("steps", C.c_void_p), ("flags", C.c_void_p),
                 ("interceptor_pos", C.c_void_p), ("missile_pos", C.c_void_p),
-                ("episode_return", C.c_void_p), ("episode_length", C.c_void_p)]
+                ("episode_return", C.c_void_p), ("episode_length", C.c_void_p),
+                ("missiles_intercepted", C.c_void_p), ("missiles_remaining", C.c_void_p), ("missile_min_distances", C.c_void_p)]
 
 
 INFO_FIELDS = [  # name, numpy dtype, trailing shape
@@ -63,6 +65,7 @@ INFO_FIELDS = [  # name, numpy dtype, trailing shape
     ("fuel_used", "float32", ()), ("steps", "int32", ()), ("flags", "uint8", ()),
     ("interceptor_pos", "float32", (3,)), ("missile_pos", "float32", (3,)),
     ("episode_return", "float32", ()), ("episode_length", "int32", ()),
+    ("missiles_intercepted", "int32", ()), ("missiles_remaining", "int32", ()), ("missile_min_distances", "float32", (MAX_VOLLEY,)),
 ]
 
 INFO_INTERCEPTED, INFO_HIT_TARGET, INFO_CLAMPED, INFO_RADAR_DETECTED = 0x01, 0x02, 0x04, 0x08
@@ -72,14 +75,15 @@ DONE_TERMINATED, DONE_TRUNCATED = 0x100, 0x200
 
 
 def done_record_numpy_dtype():
-    """numpy structured dtype with the exact memory layout of HlynrDoneRecord (40 words)."""
+    """numpy structured dtype with the exact memory layout of HlynrDoneRecord (50 words)."""
     import numpy as np
 
     dt = np.dtype([("env", np.int32), ("steps", np.int32), ("flags", np.uint32), ("distance", np.float32),
                    ("min_distance", np.float32), ("fuel_remaining", np.float32), ("fuel_used", np.float32),
                    ("episode_return", np.float32), ("interceptor_pos", np.float32, (3,)), ("missile_pos", np.float32, (3,)),
-                   ("terminal_obs", np.float32, (OBS_DIM,))])
-    assert dt.itemsize == 160, dt.itemsize
+                   ("terminal_obs", np.float32, (OBS_DIM,)), ("missiles_intercepted", np.int32), ("missiles_remaining", np.int32),
+                   ("missile_min_distances", np.float32, (MAX_VOLLEY,))])
+    assert dt.itemsize == 200, dt.itemsize
     return dt
 
 
@@ -99,13 +103,16 @@ class HlynrEnvState(C.Structure):
         ("prev_d", C.c_double), ("last_d", C.c_double), ("min_d", C.c_double), ("episode_return", C.c_double),
         ("kf_x", C.c_double * 6), ("kf_P", C.c_double * 4),
         ("T0", C.c_double), ("base_cd", C.c_double), ("peak", C.c_double),
+        ("vpos", C.c_double * (MAX_VOLLEY * 3)), ("vvel", C.c_double * (MAX_VOLLEY * 3)), ("vmin", C.c_double * MAX_VOLLEY),
         ("steps", C.c_int32), ("worsen_count", C.c_int32), ("crossed", C.c_int32), ("kf_init", C.c_int32),
         ("onboard_delay", C.c_int32), ("episode", C.c_int32),
+        ("vactive", C.c_int32 * MAX_VOLLEY), ("vcur", C.c_int32), ("vcount", C.c_int32),
     ]
 
 
 ENV_STATE_VEC_FIELDS = {"ipos": 3, "ivel": 3, "quat": 4, "mpos": 3, "mvel": 3, "wind": 3, "thrust": 3,
-                        "kf_x": 6, "kf_P": 4}
+                        "kf_x": 6, "kf_P": 4, "vpos": MAX_VOLLEY * 3, "vvel": MAX_VOLLEY * 3, "vmin": MAX_VOLLEY}
+ENV_STATE_INT_VEC_FIELDS = {"vactive": MAX_VOLLEY}
 
 
 def env_state_numpy_dtype():
@@ -116,6 +123,8 @@ def env_state_numpy_dtype():
     for name, ctype in HlynrEnvState._fields_:
         if name in ENV_STATE_VEC_FIELDS:
             fields.append((name, np.float64, (ENV_STATE_VEC_FIELDS[name],)))
+        elif name in ENV_STATE_INT_VEC_FIELDS:
+            fields.append((name, np.int32, (ENV_STATE_INT_VEC_FIELDS[name],)))
         elif ctype is C.c_int32:
             fields.append((name, np.int32))
         else:

@@ -47,11 +47,15 @@ def resolve_config(env_cfg=None, warn_dead=True):
         if dk:
             warnings.warn("config keys ignored by the reference environment (and therefore here): " + ", ".join(dk),
                           stacklevel=2)
+    volley_size = 0   # environment.py:42-43: 0 = volley_mode off, else the number of missiles per episode
     if cfg.get("volley_mode", False):
-        raise NotImplementedError("volley_mode is outside the accelerated path (SURVEY 8f rank 3)")
+        volley_size = int(cfg.get("volley_size", 1))
+        if not 1 <= volley_size <= abi.MAX_VOLLEY:
+            raise NotImplementedError(f"volley_size {volley_size} outside [1, {abi.MAX_VOLLEY}]")
 
     p = abi.HlynrParams()
     p.abi_version = abi.ABI_VERSION
+    p.volley_size = volley_size
     p.dt = float(cfg.get("dt", 0.01))
     p.max_steps = int(cfg.get("max_steps", 1000))
     p.max_range = float(cfg.get("max_range", 10000.0))

@@ -16,7 +16,7 @@
 
 using namespace hlynr;
 
-static_assert(sizeof(HlynrDoneRecord) == 160, "HlynrDoneRecord is 40 words (mirrored by abi.done_record_numpy_dtype)");
+static_assert(sizeof(HlynrDoneRecord) == 200, "HlynrDoneRecord is 50 words (mirrored by abi.done_record_numpy_dtype)");
 
 static thread_local char g_err[512] = "";
 static int fail(const char* fmt, ...) {
@@ -202,7 +202,7 @@ template <typename R> static KParams<R> make_kparams(const HlynrParams& p) {
     k.thrust_dyn = p.thrust_dyn_enabled; k.dr = p.dr_enabled; k.validate = p.validate_enabled; k.evasion = p.evasion_enabled;
     k.onboard_delay = p.onboard_delay; k.ground = p.ground_enabled; k.ground_delay = p.ground_enabled ? p.ground_delay : 0;
     k.spherical = p.m_spawn_spherical; k.toward_missile = p.i_vel_toward_missile; k.obs_mode = p.obs_mode;
-    k.precision_mode = p.precision_mode; k.fuze = p.fuze_enabled;
+    k.precision_mode = p.precision_mode; k.fuze = p.fuze_enabled; k.volley_k = p.volley_size;
     k.onb_ring_len = p.onboard_delay > 0 ? (p.dr_enabled ? HLYNR_MAX_ONBOARD_DELAY + 1 : p.onboard_delay + 1) : 0;
     k.gnd_ring_len = k.ground_delay > 0 ? k.ground_delay + 1 : 0;
     return k;
@@ -268,7 +268,13 @@ template <typename R> __global__ void export_kernel(KernelArgs<R> A, int64_t fir
     s.kf_P[0] = e.Ppp; s.kf_P[1] = e.Ppv; s.kf_P[2] = e.Pvp; s.kf_P[3] = e.Pvv;
     s.T0 = e.T0; s.base_cd = e.base_cd; s.peak = e.peak;
     s.steps = e.steps; s.worsen_count = e.worsen; s.crossed = (e.flags & FLAG_CROSSED) ? 1 : 0;
-    s.kf_init = (e.flags & FLAG_KF_INIT) ? 1 : 0; s.onboard_delay = A.P.onboard_delay > 0 ? (e.flags >> 8) : 0; s.episode = e.episode;
+    s.kf_init = (e.flags & FLAG_KF_INIT) ? 1 : 0; s.onboard_delay = A.P.onboard_delay > 0 ? FLAG_ODELAY(e.flags) : 0; s.episode = e.episode;
+    for (int m = 0; m < A.P.volley_k; ++m) {
+        const Vec4<R> a = A.st.vm[(int64_t)(2 * m) * A.ring_stride + first + j], b = A.st.vm[(int64_t)(2 * m + 1) * A.ring_stride + first + j];
+        s.vpos[3 * m] = a.x; s.vpos[3 * m + 1] = a.y; s.vpos[3 * m + 2] = a.z; s.vmin[m] = a.w;
+        s.vvel[3 * m] = b.x; s.vvel[3 * m + 1] = b.y; s.vvel[3 * m + 2] = b.z; s.vactive[m] = b.w != R(0) ? 1 : 0;
+    }
+    s.vcur = A.P.volley_k > 0 ? FLAG_VCUR(e.flags) : 0; s.vcount = A.P.volley_k > 0 ? FLAG_VCOUNT(e.flags) : 0;
     out[j] = s;
 }
 template <typename R> __global__ void import_kernel(KernelArgs<R> A, int64_t first, int64_t count, const HlynrEnvState* in) {
@@ -287,7 +293,12 @@ template <typename R> __global__ void import_kernel(KernelArgs<R> A, int64_t fir
     e.Ppp = (float)s.kf_P[0]; e.Ppv = (float)s.kf_P[1]; e.Pvp = (float)s.kf_P[2]; e.Pvv = (float)s.kf_P[3];
     e.T0 = (R)s.T0; e.base_cd = (float)s.base_cd; e.peak = (float)s.peak;
     e.steps = s.steps; e.worsen = s.worsen_count;
-    e.flags = (s.crossed ? FLAG_CROSSED : 0) | (s.kf_init ? FLAG_KF_INIT : 0) | (s.onboard_delay << 8);
+    e.flags = (s.crossed ? FLAG_CROSSED : 0) | (s.kf_init ? FLAG_KF_INIT : 0) | ((s.onboard_delay & 0xf) << 8) | ((s.vcur & 0x7) << 12) |
+              ((s.vcount & 0xf) << 16);
+    for (int m = 0; m < A.P.volley_k; ++m) {
+        A.st.vm[(int64_t)(2 * m) * A.ring_stride + first + j] = Vec4<R>{(R)s.vpos[3 * m], (R)s.vpos[3 * m + 1], (R)s.vpos[3 * m + 2], (R)s.vmin[m]};
+        A.st.vm[(int64_t)(2 * m + 1) * A.ring_stride + first + j] = Vec4<R>{(R)s.vvel[3 * m], (R)s.vvel[3 * m + 1], (R)s.vvel[3 * m + 2], s.vactive[m] ? R(1) : R(0)};
+    }
     e.episode = s.episode;
     KernelArgs<R> B = A;
     B.P.thrust_dyn = 1; B.P.dr = 1;
@@ -310,12 +321,13 @@ __global__ void debug_draw_kernel(const __grid_constant__ RoundKeys rk, int64_t 
 // ------------------------------------------------------------------------------------------------
 // allocation
 // ------------------------------------------------------------------------------------------------
-template <typename R> static size_t carve(StatePlanes<R>& s, char* base, int64_t n_pad, int gl, int ol) {
+template <typename R> static size_t carve(StatePlanes<R>& s, char* base, int64_t n_pad, int gl, int ol, int vk) {
     size_t off = 0;
     auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += (bytes + 255) & ~size_t(255); return p; };
     for (int k = 0; k < 7; ++k) s.r[k] = (Vec4<R>*)take(sizeof(Vec4<R>) * n_pad);
     for (int k = 0; k < 4; ++k) s.f[k] = (float4*)take(sizeof(float4) * n_pad);
     s.i0 = (int4*)take(sizeof(int4) * n_pad);
+    s.vm = (Vec4<R>*)take(sizeof(Vec4<R>) * n_pad * 2 * (vk > 0 ? vk : 1));
     s.gring = (Vec4<R>*)take(sizeof(Vec4<R>) * n_pad * 2 * (gl > 0 ? gl : 1));
     s.oring = (float4*)take(sizeof(float4) * n_pad * (ol > 0 ? ol : 1));
     return off;
@@ -344,7 +356,7 @@ static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) 
 
 // Feature set of a resolved configuration; a specialised instantiation exists for FT_V2ON and FT_V2OFF.
 static int feature_set(const HlynrParams& p) {
-    if (p.obs_mode != HLYNR_OBS_WORLD) return FT_GENERIC_MODES;
+    if (p.obs_mode != HLYNR_OBS_WORLD || p.volley_size > 0) return FT_GENERIC_MODES;
     if (p.dr_enabled || p.precision_mode || p.fuze_enabled) return FT_GENERIC;
     int f = 0;
     if (p.isa_enabled) f |= FT_ISA;
@@ -440,6 +452,7 @@ void hlynr_destroy(hlynr_t* s) {
     cudaFree(h.d_info.distance); cudaFree(h.d_info.min_distance); cudaFree(h.d_info.fuel_remaining); cudaFree(h.d_info.fuel_used);
     cudaFree(h.d_info.steps); cudaFree(h.d_info.flags); cudaFree(h.d_info.interceptor_pos); cudaFree(h.d_info.missile_pos);
     cudaFree(h.d_info.episode_return); cudaFree(h.d_info.episode_length);
+    cudaFree(h.d_info.missiles_intercepted); cudaFree(h.d_info.missiles_remaining); cudaFree(h.d_info.missile_min_distances);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
@@ -452,6 +465,7 @@ int hlynr_create(const HlynrParams* p, int64_t n_envs, int device, uint64_t seed
     if (precision != HLYNR_FP32 && precision != HLYNR_FP64) return fail("hlynr_create: precision must be 32 or 64");
     if (p->obs_mode != HLYNR_OBS_WORLD && p->obs_mode != HLYNR_OBS_BODY && p->obs_mode != HLYNR_OBS_LOS)
         return fail("hlynr_create: unknown observation_mode %d", p->obs_mode);
+    if (p->volley_size < 0 || p->volley_size > HLYNR_MAX_VOLLEY) return fail("hlynr_create: volley_size must be in [0, %d]", HLYNR_MAX_VOLLEY);
     if (p->onboard_delay < 0 || p->onboard_delay > HLYNR_MAX_ONBOARD_DELAY) return fail("hlynr_create: onboard_delay out of range");
     if (p->ground_delay < 0 || p->ground_delay > HLYNR_MAX_GROUND_DELAY) return fail("hlynr_create: ground_delay out of range");
     int ndev = 0;
@@ -468,8 +482,8 @@ int hlynr_create(const HlynrParams* p, int64_t n_envs, int device, uint64_t seed
     KParams<float> kp = make_kparams<float>(*p);
     const int gl = kp.gnd_ring_len, ol = kp.onb_ring_len;
     cudaError_t e;
-    if (precision == HLYNR_FP32) s->state_bytes = carve<float>(s->pf, nullptr, s->n_pad, gl, ol);
-    else s->state_bytes = carve<double>(s->pd, nullptr, s->n_pad, gl, ol);
+    if (precision == HLYNR_FP32) s->state_bytes = carve<float>(s->pf, nullptr, s->n_pad, gl, ol, p->volley_size);
+    else s->state_bytes = carve<double>(s->pd, nullptr, s->n_pad, gl, ol, p->volley_size);
     e = cudaMalloc(&s->state_mem, s->state_bytes);
     if (e != cudaSuccess) { int r = fail("hlynr_create: cudaMalloc(%zu bytes) failed: %s", s->state_bytes, cudaGetErrorString(e)); delete s; return r; }
     e = cudaMalloc(&s->stats, sizeof(double) * (HLYNR_STAT_SLOTS + 1) * HLYNR_STATS_WORDS);
@@ -480,10 +494,10 @@ int hlynr_create(const HlynrParams* p, int64_t n_envs, int device, uint64_t seed
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     const int blk = 256;
     if (precision == HLYNR_FP32) {
-        carve<float>(s->pf, (char*)s->state_mem, s->n_pad, gl, ol);
+        carve<float>(s->pf, (char*)s->state_mem, s->n_pad, gl, ol, p->volley_size);
         init_kernel<float><<<grid_for(s->n_pad, blk), blk>>>(s->pf, s->n_pad, (float)p->peak_mult, true);
     } else {
-        carve<double>(s->pd, (char*)s->state_mem, s->n_pad, gl, ol);
+        carve<double>(s->pd, (char*)s->state_mem, s->n_pad, gl, ol, p->volley_size);
         init_kernel<double><<<grid_for(s->n_pad, blk), blk>>>(s->pd, s->n_pad, (float)p->peak_mult, true);
     }
     e = cudaDeviceSynchronize();
@@ -559,7 +573,7 @@ static int step_range(hlynr_sim* s, int64_t first, int64_t lim, const float* act
         // measured on B200 (profiles/r01_b): the direct kernel is faster than the TMA-prefetched persistent one (the
         // step is bound by in-warp dependency latency, not by load latency), so auto = direct; the TMA variant stays
         // selectable and parity-tested.  It needs 16-byte aligned actions and works on the whole shard only.
-        bool use_tma = s->kernel_variant == 2 && whole && s->params.obs_mode == HLYNR_OBS_WORLD;  // world_frame only
+        bool use_tma = s->kernel_variant == 2 && whole && s->params.obs_mode == HLYNR_OBS_WORLD && s->params.volley_size == 0;
         if (((uintptr_t)actions_dev & 15u) != 0) use_tma = false;
         if (use_tma) {
             const int64_t n_tiles = (s->n + TMA_TILE - 1) / TMA_TILE;
@@ -582,7 +596,7 @@ static int step_range(hlynr_sim* s, int64_t first, int64_t lim, const float* act
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward = reward_dev; A.io.terminated = terminated_dev;
         A.io.truncated = truncated_dev; A.io.terminal_obs = terminal_obs_dev; A.auto_reset = auto_reset;
         if (info) { A.io.info = *info; A.has_info = 1; }
-        if (s->params.obs_mode != HLYNR_OBS_WORLD)
+        if (s->params.obs_mode != HLYNR_OBS_WORLD || s->params.volley_size > 0)
             step_kernel<double, false, FT_GENERIC_MODES><<<grid_for(lim - first, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
         else
             step_kernel<double, false, FT_GENERIC><<<grid_for(lim - first, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
@@ -629,7 +643,7 @@ int hlynr_rollout(hlynr_t* s, int k_steps, const float* actions_dev, float* obs_
         A.g_row = A.P.gnd_ring_len > 0 ? (int32_t)(A.tick % (uint32_t)A.P.gnd_ring_len) : 0;
         A.o_row = A.P.onb_ring_len > 0 ? (int32_t)(A.tick % (uint32_t)A.P.onb_ring_len) : 0;
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward_sum = reward_sum_dev; A.io.done_count = done_count_dev;
-        if (s->params.obs_mode != HLYNR_OBS_WORLD)
+        if (s->params.obs_mode != HLYNR_OBS_WORLD || s->params.volley_size > 0)
             step_kernel<double, true, FT_GENERIC_MODES><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
         else
             step_kernel<double, true, FT_GENERIC><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
@@ -787,6 +801,8 @@ static int ensure_host_info(hlynr_sim* s) {
     CK(cudaMalloc(&h.d_info.steps, n * 4)); CK(cudaMalloc(&h.d_info.flags, n));
     CK(cudaMalloc(&h.d_info.interceptor_pos, n * 12)); CK(cudaMalloc(&h.d_info.missile_pos, n * 12));
     CK(cudaMalloc(&h.d_info.episode_return, n * 4)); CK(cudaMalloc(&h.d_info.episode_length, n * 4));
+    CK(cudaMalloc(&h.d_info.missiles_intercepted, n * 4)); CK(cudaMalloc(&h.d_info.missiles_remaining, n * 4));
+    CK(cudaMalloc(&h.d_info.missile_min_distances, n * 4 * HLYNR_MAX_VOLLEY));
     h.info_ready = true;
     return 0;
 }
@@ -902,6 +918,10 @@ int hlynr_info_host(hlynr_t* s, HlynrInfoSoA* o) {
     if (o->missile_pos) CK(cudaMemcpyAsync(o->missile_pos, d.missile_pos, n * 12, cudaMemcpyDeviceToHost, st));
     if (o->episode_return) CK(cudaMemcpyAsync(o->episode_return, d.episode_return, n * 4, cudaMemcpyDeviceToHost, st));
     if (o->episode_length) CK(cudaMemcpyAsync(o->episode_length, d.episode_length, n * 4, cudaMemcpyDeviceToHost, st));
+    if (o->missiles_intercepted) CK(cudaMemcpyAsync(o->missiles_intercepted, d.missiles_intercepted, n * 4, cudaMemcpyDeviceToHost, st));
+    if (o->missiles_remaining) CK(cudaMemcpyAsync(o->missiles_remaining, d.missiles_remaining, n * 4, cudaMemcpyDeviceToHost, st));
+    if (o->missile_min_distances)
+        CK(cudaMemcpyAsync(o->missile_min_distances, d.missile_min_distances, n * 4 * HLYNR_MAX_VOLLEY, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return 0;
 }

@@ -183,6 +183,7 @@ template <typename R> struct KParams {
     // ---- switches ----
     int32_t max_steps, isa, mach, enh_wind, thrust_dyn, dr, validate, evasion, onboard_delay, ground, ground_delay;
     int32_t spherical, toward_missile, obs_mode, precision_mode, fuze, onb_ring_len, gnd_ring_len;
+    int32_t volley_k;  // 0 = volley_mode off, else missiles per env (environment.py:42-43)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -192,7 +193,7 @@ template <typename R> struct KParams {
 // ------------------------------------------------------------------------------------------------
 enum { FT_ISA = 1, FT_MACH = 2, FT_ENHW = 4, FT_THRUST = 8, FT_ONBD = 16, FT_GROUND = 32, FT_GDELAY = 64, FT_EVADE = 128 };
 #define FT_GENERIC (-1)        /* every switch at run time, world_frame observations */
-#define FT_GENERIC_MODES (-2)  /* the same + observation_mode body_frame / los_frame (and the LOS action transform) */
+#define FT_GENERIC_MODES (-2)  /* the same + observation_mode body_frame / los_frame (and the LOS action transform) + volley mode */
 #define FT_V2ON (FT_ISA | FT_MACH | FT_ENHW | FT_THRUST | FT_ONBD | FT_GROUND | FT_GDELAY | FT_EVADE)  /* cfg4: medium, v2.0 on */
 #define FT_V2OFF (FT_GROUND | FT_GDELAY | FT_EVADE)                                                   /* cfg2: medium, v2.0 off */
 template <int F> struct Feat {
@@ -209,6 +210,7 @@ template <int F> struct Feat {
     template <typename P> static HD bool dr(const P& p) { if constexpr (F < 0) return p.dr != 0; else return false; }
     template <typename P> static HD bool precision_mode(const P& p) { if constexpr (F < 0) return p.precision_mode != 0; else return false; }
     template <typename P> static HD bool fuze(const P& p) { if constexpr (F < 0) return p.fuze != 0; else return false; }
+    template <typename P> static HD int volley(const P& p) { if constexpr (F == FT_GENERIC_MODES) return p.volley_k; else return 0; }
     template <typename P> static HD int obs_mode(const P& p) { if constexpr (F == FT_GENERIC_MODES) return p.obs_mode; else return HLYNR_OBS_WORLD; }
 };
 
@@ -223,6 +225,7 @@ template <typename R> struct StatePlanes {
                      // r5 kf_xv+ep_return, r6 thrust+T0
     float4* f[4];    // f0 quat, f1 wind+Ppp, f2 Ppv,Pvp,Pvv,base_cd, f3 peak (DR only)
     int4* i0;        // steps, worsen, flags (bit0 crossed, bit1 kf_init, bits 8.. onboard delay), episode
+    Vec4<R>* vm;     // volley mode: [volley_k][2][stride]: {pos.xyz, min_distance}, {vel.xyz, active}
     Vec4<R>* gring;  // [gnd_ring_len][2][stride]: {rel.xyz, quality}, {vel.xyz, -}
     float4* oring;   // [onb_ring_len][stride]: {rel.xyz, detected}
 };
@@ -282,6 +285,11 @@ template <typename R> struct Env {
 };
 #define FLAG_CROSSED 1
 #define FLAG_KF_INIT 2
+// flags word: bit 0 crossed, bit 1 kf_init, bits 8-11 onboard delay (samples), bits 12-14 index of the priority missile
+// (volley: which list entry self.missile_state aliases), bits 16-19 missiles intercepted so far (volley)
+#define FLAG_ODELAY(f) (((f) >> 8) & 0xf)
+#define FLAG_VCUR(f) (((f) >> 12) & 0x7)
+#define FLAG_VCOUNT(f) (((f) >> 16) & 0xf)
 
 template <typename R, int F = FT_GENERIC> HD void load_env(const KernelArgs<R>& A, int64_t i, Env<R>& e) {
     typedef Feat<F> FT;
@@ -466,7 +474,7 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
     bool o_det;
     if (FT::onboard_delay(P)) {
         const int L = P.onb_ring_len;
-        const int odelay = e.flags >> 8;
+        const int odelay = FLAG_ODELAY(e.flags);
         A.st.oring[(int64_t)o_row * n + i] = make_float4(rx, ry, rz, onb ? 1.f : 0.f);
         if (e.steps >= odelay) {
             float4 s;
@@ -731,8 +739,30 @@ struct SpawnOut {
     int odelay;
 };
 
+// one missile's spawn (environment.py:389-427) from its uniform block
 template <typename R>
-__device__ __noinline__ SpawnOut spawn_values(const KernelArgs<R>& A, uint32_t c0, uint32_t c3hi, uint32_t ep) {
+HD void spawn_missile(const KParams<R>& P, const uint4 r, float* mx, float* my, float* mz, float* vx, float* vy, float* vz) {
+    const double u0 = u01(r.x), u1 = u01(r.y), u2 = u01(r.z), u3 = u01(r.w);
+    if (P.spherical) {  // :390-406
+        double radius = P.m_radius_lo + (P.m_radius_hi - P.m_radius_lo) * u0;
+        double az = (P.m_az_lo + (P.m_az_hi - P.m_az_lo) * u1) * CUDART_PI / 180.0;
+        double el = (P.m_el_lo + (P.m_el_hi - P.m_el_lo) * u2) * CUDART_PI / 180.0;
+        *mx = (float)(P.target_d[0] + radius * cos(el) * cos(az));
+        *my = (float)(P.target_d[1] + radius * cos(el) * sin(az));
+        *mz = (float)(P.target_d[2] + radius * sin(el));
+    } else {            // :409
+        *mx = (float)(P.m_pos_lo[0] + (P.m_pos_hi[0] - P.m_pos_lo[0]) * u0);
+        *my = (float)(P.m_pos_lo[1] + (P.m_pos_hi[1] - P.m_pos_lo[1]) * u1);
+        *mz = (float)(P.m_pos_lo[2] + (P.m_pos_hi[2] - P.m_pos_lo[2]) * u2);
+    }
+    const float speed = (float)(P.m_speed_lo + (P.m_speed_hi - P.m_speed_lo) * u3);
+    const float tx = sub((float)P.target_d[0], *mx), ty = sub((float)P.target_d[1], *my), tz = sub((float)P.target_d[2], *mz);
+    const float td = norm3(tx, ty, tz);
+    *vx = mul(dvd(tx, td), speed); *vy = mul(dvd(ty, td), speed); *vz = mul(dvd(tz, td), speed);
+}
+
+template <typename R>
+__device__ __noinline__ SpawnOut spawn_values(const KernelArgs<R>& A, uint32_t c0, uint32_t c3hi, uint32_t ep, int64_t plane_i) {
     const KParams<R>& P = A.P;
     RngKey key;
     key.rk = &A.rk; key.c0 = c0; key.c3hi = c3hi;
@@ -744,27 +774,29 @@ __device__ __noinline__ SpawnOut spawn_values(const KernelArgs<R>& A, uint32_t c
     double u10 = u01(r1.x), u11 = u01(r1.y), u12 = u01(r1.z), u13 = u01(r1.w);
     double u20 = u01(r2.x), u21 = u01(r2.y);
     float mx, my, mz;
-    if (P.spherical) {  // environment.py:390-406
-        double radius = P.m_radius_lo + (P.m_radius_hi - P.m_radius_lo) * u00;
-        double az = (P.m_az_lo + (P.m_az_hi - P.m_az_lo) * u01_) * CUDART_PI / 180.0;
-        double el = (P.m_el_lo + (P.m_el_hi - P.m_el_lo) * u02) * CUDART_PI / 180.0;
-        mx = (float)(P.target_d[0] + radius * cos(el) * cos(az));
-        my = (float)(P.target_d[1] + radius * cos(el) * sin(az));
-        mz = (float)(P.target_d[2] + radius * sin(el));
-    } else {            // :409
-        mx = (float)(P.m_pos_lo[0] + (P.m_pos_hi[0] - P.m_pos_lo[0]) * u00);
-        my = (float)(P.m_pos_lo[1] + (P.m_pos_hi[1] - P.m_pos_lo[1]) * u01_);
-        mz = (float)(P.m_pos_lo[2] + (P.m_pos_hi[2] - P.m_pos_lo[2]) * u02);
-    }
-    float speed = (float)(P.m_speed_lo + (P.m_speed_hi - P.m_speed_lo) * u03);
-    float tx = sub((float)P.target_d[0], mx), ty = sub((float)P.target_d[1], my), tz = sub((float)P.target_d[2], mz);
-    float td = norm3(tx, ty, tz);
-    o.mvx = mul(dvd(tx, td), speed); o.mvy = mul(dvd(ty, td), speed); o.mvz = mul(dvd(tz, td), speed);
+    spawn_missile(P, r0, &mx, &my, &mz, &o.mvx, &o.mvy, &o.mvz);
+    (void)u00; (void)u01_; (void)u02; (void)u03;
     float ix = (float)(P.i_pos_lo[0] + (P.i_pos_hi[0] - P.i_pos_lo[0]) * u10);
     float iy = (float)(P.i_pos_lo[1] + (P.i_pos_hi[1] - P.i_pos_lo[1]) * u11);
     float iz = (float)(P.i_pos_lo[2] + (P.i_pos_hi[2] - P.i_pos_lo[2]) * u12);
     float lx = sub(mx, ix), ly = sub(my, iy), lz = sub(mz, iz);
     float ld = norm3(lx, ly, lz);
+    o.d0 = ld;  // |missile_states[0] - interceptor| on the float32 state (environment.py:579-581)
+    float ox = lx, oy = ly, oz = lz, od = ld;  // the launch orientation points at the CLOSEST missile of a volley (:476-486)
+    if (P.volley_k > 0) {  // fill the missile planes: {pos, min_distance}, {vel, active}
+        const int64_t n = A.ring_stride;
+        A.st.vm[plane_i] = Vec4<R>{(R)mx, (R)my, (R)mz, (R)ld};
+        A.st.vm[n + plane_i] = Vec4<R>{(R)o.mvx, (R)o.mvy, (R)o.mvz, R(1)};
+        for (int m = 1; m < P.volley_k; ++m) {
+            float px, py, pz, vx, vy, vz;
+            spawn_missile(P, draw_raw(key, ep, 0u, HLYNR_BLK_VSPAWN(m)), &px, &py, &pz, &vx, &vy, &vz);
+            const float dx = sub(px, ix), dy = sub(py, iy), dz = sub(pz, iz);
+            const float d = norm3(dx, dy, dz);
+            A.st.vm[(int64_t)(2 * m) * n + plane_i] = Vec4<R>{(R)px, (R)py, (R)pz, (R)d};
+            A.st.vm[(int64_t)(2 * m + 1) * n + plane_i] = Vec4<R>{(R)vx, (R)vy, (R)vz, R(1)};
+            if (d < od) { od = d; ox = dx; oy = dy; oz = dz; }
+        }
+    }
     if (P.toward_missile) {
         float sp = (float)(P.i_speed_lo + (P.i_speed_hi - P.i_speed_lo) * u13);
         o.vx = mul(dvd(lx, ld), sp); o.vy = mul(dvd(ly, ld), sp); o.vz = mul(dvd(lz, ld), sp);
@@ -775,8 +807,8 @@ __device__ __noinline__ SpawnOut spawn_values(const KernelArgs<R>& A, uint32_t c
     }
     // orientation: rotate +Z onto the line of sight (environment.py:492-530); float64 on float32 inputs
     o.qw = 1.f; o.qx = 0.f; o.qy = 0.f; o.qz = 0.f;
-    if (ld > 1e-6f) {
-        double fx = dvd(lx, ld), fy = dvd(ly, ld), fz = dvd(lz, ld);
+    if (od > 1e-6f) {
+        double fx = dvd(ox, od), fy = dvd(oy, od), fz = dvd(oz, od);
         double ax = -fy, ay = fx;
         double al = sqrt(ax * ax + ay * ay + 0.0);
         if (al > 1e-6) {
@@ -786,7 +818,6 @@ __device__ __noinline__ SpawnOut spawn_values(const KernelArgs<R>& A, uint32_t c
         } else if (!(fz > 0)) { o.qw = 0.f; o.qx = 1.f; }  // anti-aligned (quirk Q9: aligned -> identity)
     }
     o.mx = mx; o.my = my; o.mz = mz; o.ix = ix; o.iy = iy; o.iz = iz;
-    o.d0 = ld;  // |mpos - ipos| on the float32 state (environment.py:579-581)
     o.dT0 = 0.0; o.base_cd = 0.3f; o.peak = (float)(P.peak_minus1 + R(1.0)); o.odelay = P.onboard_delay;
     if (P.dr) {  // physics_randomizer.py:166-214, 243-297
         float z0, z1, z2, z3, z4, zd;
@@ -804,9 +835,9 @@ __device__ __noinline__ SpawnOut spawn_values(const KernelArgs<R>& A, uint32_t c
     return o;
 }
 
-template <typename R> HD void spawn(const KernelArgs<R>& A, Env<R>& e, const RngKey& key) {
+template <typename R> HD void spawn(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t plane_i) {
     const KParams<R>& P = A.P;
-    const SpawnOut o = spawn_values(A, key.c0, key.c3hi, (uint32_t)e.episode);
+    const SpawnOut o = spawn_values(A, key.c0, key.c3hi, (uint32_t)e.episode, plane_i);
     e.mpx = o.mx; e.mpy = o.my; e.mpz = o.mz; e.mvx = o.mvx; e.mvy = o.mvy; e.mvz = o.mvz;
     e.ipx = o.ix; e.ipy = o.iy; e.ipz = o.iz; e.ivx = o.vx; e.ivy = o.vy; e.ivz = o.vz;
     e.qw = o.qw; e.qx = o.qx; e.qy = o.qy; e.qz = o.qz;
@@ -877,8 +908,83 @@ HD void quat_step(Env<double>& e, double wx, double wy, double wz, double dt) {
     }
 }
 
+// _update_missile_state (environment.py:1069-1117) for one missile; every missile of a volley sees the same current_wind
 template <typename R, int F>
-HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const float act[6], TickOut& t) {
+HD void missile_update(const KParams<R>& P, const Env<R>& e, const RngKey& key, uint32_t ep, uint32_t st, uint32_t evade_blk,
+                       R& mpx, R& mpy, R& mpz, R& mvx, R& mvy, R& mvz) {
+    typedef Feat<F> FT;
+    const R dt = P.dt;
+    R alt = mpz > R(0) ? mpz : R(0);
+    R vax = sub(mvx, (R)e.wx), vay = sub(mvy, (R)e.wy), vaz = sub(mvz, (R)e.wz);
+    R dax, day, daz;
+    drag_accel<R, F>(P, e, vax, vay, vaz, alt, R(2.0), P.missile_ratio, R(1.0 / 1000.0), R(1000.0), &dax, &day, &daz);
+    double ex = 0.0, ey = 0.0, ez = 0.0;
+    if (FT::evasion(P)) {
+        float z0, z1, z2;
+        draw_normal3(key, ep, st, evade_blk, &z0, &z1, &z2);
+        ex = (double)(z0 * 2.0f); ey = (double)(z1 * 2.0f); ez = (double)(z2 * 2.0f);
+    }
+    // total_accel = drag + gravity + evasion is float64 in the reference even without evasion
+    // (evasion = np.zeros(3)), and velocity += total_accel * dt is evaluated in float64: kept as is.
+    double ax = (double)dax + ex, ay = (double)day + ey, az = (double)add(daz, (R)(-9.81f)) + ez;
+    if (P.validate && any_nonfinite(ax, ay, az)) {
+        ax = nan_guard(ax, 20.0); ay = nan_guard(ay, 20.0); az = nan_guard(az, 20.0);
+    }
+    mvx = (R)add((double)mvx, mul(ax, P.dt_d));
+    mvy = (R)add((double)mvy, mul(ay, P.dt_d));
+    mvz = (R)add((double)mvz, mul(az, P.dt_d));
+    mpx = add(mpx, mul(mvx, dt)); mpy = add(mpy, mul(mvy, dt)); mpz = add(mpz, mul(mvz, dt));
+}
+
+// Volley mode (environment.py:236-267, 631-692, 724-748): advance every active missile, pick the priority missile
+// (closest ACTIVE one after the update, strict <, first wins; missile 0 if none is active), intercept checks with
+// per-missile minimum distances, distance = closest still-active missile (0.0 if none), ground hits.  One pass over the
+// K missile planes; the priority missile's state becomes e.mp* / e.mv* (self.missile_state aliases that list entry).
+struct VolleyOut { bool intercepted, hit, all_inactive; };
+template <typename R, int F>
+HD VolleyOut volley_step(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, uint32_t ep, uint32_t st, int64_t i, R radius, R* distance) {
+    const KParams<R>& P = A.P;
+    const int K = P.volley_k;
+    const int64_t n = A.ring_stride;
+    VolleyOut o{false, false, true};
+    int pri = -1, count = FLAG_VCOUNT(e.flags);
+    R pbest = R(0), dist = R(0);
+    bool any_active = false;
+    R ppx = R(0), ppy = R(0), ppz = R(0), pvx = R(0), pvy = R(0), pvz = R(0);
+#pragma unroll 1
+    for (int m = 0; m < K; ++m) {
+        Vec4<R> a = A.st.vm[(int64_t)(2 * m) * n + i], b = A.st.vm[(int64_t)(2 * m + 1) * n + i];
+        bool act = b.w != R(0);
+        if (act) {
+            missile_update<R, F>(P, e, key, ep, st, m == 0 ? HLYNR_BLK_EVADE : HLYNR_BLK_VEVADE(m), a.x, a.y, a.z, b.x, b.y, b.z);
+            const R d = norm3(sub(a.x, e.ipx), sub(a.y, e.ipy), sub(a.z, e.ipz));
+            if (pri < 0 || d < pbest) { pri = m; pbest = d; ppx = a.x; ppy = a.y; ppz = a.z; pvx = b.x; pvy = b.y; pvz = b.z; }
+            if (d < a.w) a.w = d;
+            if (d < radius) { o.intercepted = true; count += 1; act = false; }
+            else if (!any_active || d < dist) { dist = d; any_active = true; }
+        }
+        if (a.z <= R(0)) {  // every missile at or below the ground, also one that got there in an earlier tick
+            act = false;
+            const R gx = sub(a.x, P.target_x), gy = sub(a.y, P.target_y);
+            if (sqr(dot2(gx, gy, gx, gy)) < R(500.0)) o.hit = true;
+        }
+        if (act) o.all_inactive = false;
+        b.w = act ? R(1) : R(0);
+        A.st.vm[(int64_t)(2 * m) * n + i] = a;
+        A.st.vm[(int64_t)(2 * m + 1) * n + i] = b;
+    }
+    if (pri < 0) {  // nothing was active: self.missile_state = missile_states[0]
+        const Vec4<R> a = A.st.vm[i], b = A.st.vm[n + i];
+        pri = 0; ppx = a.x; ppy = a.y; ppz = a.z; pvx = b.x; pvy = b.y; pvz = b.z;
+    }
+    e.mpx = ppx; e.mpy = ppy; e.mpz = ppz; e.mvx = pvx; e.mvy = pvy; e.mvz = pvz;
+    e.flags = (e.flags & ~((0x7 << 12) | (0xf << 16))) | (pri << 12) | (count << 16);
+    *distance = dist;
+    return o;
+}
+
+template <typename R, int F>
+HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const float act[6], int64_t ring_i, TickOut& t) {
     typedef Feat<F> FT;
     const KParams<R>& P = A.P;
     e.steps += 1;
@@ -947,29 +1053,13 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
         e.ipx = add(e.ipx, mul(e.ivx, dt)); e.ipy = add(e.ipy, mul(e.ivy, dt)); e.ipz = add(e.ipz, mul(e.ivz, dt));
         quat_step(e, mul(a3, R(20.0)), mul(a4, R(20.0)), mul(a5, R(20.0)), dt);
     }
-    // ---- _update_missile_state (environment.py:1069-1117), same current_wind ----
-    {
-        R alt = e.mpz > R(0) ? e.mpz : R(0);
-        R vax = sub(e.mvx, (R)e.wx), vay = sub(e.mvy, (R)e.wy), vaz = sub(e.mvz, (R)e.wz);
-        R dax, day, daz;
-        drag_accel<R, F>(P, e, vax, vay, vaz, alt, R(2.0), P.missile_ratio, R(1.0 / 1000.0), R(1000.0), &dax, &day, &daz);
-        double ex = 0.0, ey = 0.0, ez = 0.0;
-        if (FT::evasion(P)) {
-            float z0, z1, z2;
-            draw_normal3(key, ep, st, HLYNR_BLK_EVADE, &z0, &z1, &z2);
-            ex = (double)(z0 * 2.0f); ey = (double)(z1 * 2.0f); ez = (double)(z2 * 2.0f);
-        }
-        // total_accel = drag + gravity + evasion is float64 in the reference even without evasion
-        // (evasion = np.zeros(3)), and velocity += total_accel * dt is evaluated in float64: kept as is.
-        double ax = (double)dax + ex, ay = (double)day + ey, az = (double)add(daz, (R)(-9.81f)) + ez;
-        if (P.validate && any_nonfinite(ax, ay, az)) {
-            ax = nan_guard(ax, 20.0); ay = nan_guard(ay, 20.0); az = nan_guard(az, 20.0);
-        }
-        e.mvx = (R)add((double)e.mvx, mul(ax, P.dt_d));
-        e.mvy = (R)add((double)e.mvy, mul(ay, P.dt_d));
-        e.mvz = (R)add((double)e.mvz, mul(az, P.dt_d));
-        e.mpx = add(e.mpx, mul(e.mvx, dt)); e.mpy = add(e.mpy, mul(e.mvy, dt)); e.mpz = add(e.mpz, mul(e.mvz, dt));
-    }
+    // ---- missiles (environment.py:631-638), advanced with the wind of THIS tick (before _update_wind); a volley's
+    // missiles, their priority selection and intercept checks are one pass over the missile planes ----
+    R dist = R(0);
+    VolleyOut vo{false, false, false};
+    const R radius = FT::fuze(P) ? P.kill_radius : A.C.intercept_radius;
+    if (FT::volley(P)) vo = volley_step<R, F>(A, e, key, ep, st, ring_i, radius, &dist);
+    else missile_update<R, F>(P, e, key, ep, st, HLYNR_BLK_EVADE, e.mpx, e.mpy, e.mpz, e.mvx, e.mvy, e.mvz);
     // ---- _update_wind (environment.py:1119-1129): the wind used by the NEXT tick ----
     if (FT::enh_wind(P)) {  // EnhancedWindModel.get_wind_vector, physics_models.py:351-387
         R alt = e.ipz > R(0) ? e.ipz : R(0);
@@ -1005,20 +1095,28 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
         e.wz = (float)(R(0.95) * (R)e.wz + R(0.05) * (P.base_wind[2] + (R)z2 * P.wind_var));
     }
     // ---- distance / intercept / termination (environment.py:657-814) ----
-    const R dist = norm3(sub(e.mpx, e.ipx), sub(e.mpy, e.ipy), sub(e.mpz, e.ipz));  // exact: feeds the reward
-    bool intercepted = dist < (FT::fuze(P) ? P.kill_radius : A.C.intercept_radius);
+    bool intercepted, term = false, hit = false;
+    if (FT::volley(P)) {
+        intercepted = vo.intercepted; hit = vo.hit;
+    } else {
+        dist = norm3(sub(e.mpx, e.ipx), sub(e.mpy, e.ipy), sub(e.mpz, e.ipz));  // exact: feeds the reward
+        intercepted = dist < radius;
+    }
     if (dist < e.min_d) e.min_d = dist;
     if (intercepted) e.flags |= FLAG_CROSSED;
     bool fuze = false;
     if (FT::fuze(P) && e.min_d < P.kill_radius) { fuze = true; intercepted = true; }
-    bool term = false, hit = false;
-    const bool missile_down = e.mpz <= R(0);
-    if (FT::precision_mode(P) ? missile_down : (!intercepted && missile_down)) {
-        R gx = sub(e.mpx, P.target_x), gy = sub(e.mpy, P.target_y);
-        hit = sqr(dot2(gx, gy, gx, gy)) < R(500.0);
+    if (FT::volley(P)) {
+        term = vo.all_inactive || fuze;
+    } else {
+        const bool missile_down = e.mpz <= R(0);
+        if (FT::precision_mode(P) ? missile_down : (!intercepted && missile_down)) {
+            R gx = sub(e.mpx, P.target_x), gy = sub(e.mpy, P.target_y);
+            hit = sqr(dot2(gx, gy, gx, gy)) < R(500.0);
+        }
+        if (FT::precision_mode(P)) term = missile_down;
+        else term = intercepted || missile_down;
     }
-    if (FT::precision_mode(P)) term = missile_down;
-    else term = intercepted || missile_down;
     if (e.ipz < R(0)) term = true;
     else if (e.fuel <= R(0)) term = true;
     else if (e.steps > 1000) {  // smart early termination, :795-811 (last_d only refreshed here, quirk Q11)
@@ -1168,6 +1266,23 @@ HD uint32_t info_flags(int eflags, bool intercepted, bool hit, bool clamped, boo
                       ((eflags & FLAG_CROSSED) ? 32 : 0) | (fuze ? 64 : 0) | ((eflags & FLAG_KF_INIT) ? 128 : 0));
 }
 
+// info['missiles_intercepted'], ['missiles_remaining'], ['missile_min_distances'] (environment.py:846-848)
+template <typename R>
+HD void volley_info(const KernelArgs<R>& A, int64_t i, const Env<R>& e, const TickOut& t, int* intercepted_n, int* remaining_n, float md[HLYNR_MAX_VOLLEY]) {
+#pragma unroll
+    for (int m = 0; m < HLYNR_MAX_VOLLEY; ++m) md[m] = 0.f;
+    if (A.P.volley_k > 0) {
+        int left = 0;
+        for (int m = 0; m < A.P.volley_k; ++m) {
+            md[m] = (float)A.st.vm[(int64_t)(2 * m) * A.ring_stride + i].w;
+            left += A.st.vm[(int64_t)(2 * m + 1) * A.ring_stride + i].w != R(0) ? 1 : 0;
+        }
+        *intercepted_n = FLAG_VCOUNT(e.flags); *remaining_n = left;
+    } else {
+        md[0] = t.distance; *intercepted_n = t.intercepted ? 1 : 0; *remaining_n = t.intercepted ? 0 : 1;
+    }
+}
+
 template <typename R> HD void write_info(const KernelArgs<R>& A, int64_t i, const Env<R>& e, const TickOut& t, const ObsOut& ob) {
     const HlynrInfoSoA& f = A.io.info;
     if (f.distance) f.distance[i] = t.distance;
@@ -1180,6 +1295,16 @@ template <typename R> HD void write_info(const KernelArgs<R>& A, int64_t i, cons
     if (f.missile_pos) { f.missile_pos[3 * i] = (float)e.mpx; f.missile_pos[3 * i + 1] = (float)e.mpy; f.missile_pos[3 * i + 2] = (float)e.mpz; }
     if (f.episode_return) f.episode_return[i] = (float)e.ep_ret;
     if (f.episode_length) f.episode_length[i] = e.steps;
+    if (f.missiles_intercepted || f.missiles_remaining || f.missile_min_distances) {  // environment.py:844-848
+        int done_n, left_n;
+        float md[HLYNR_MAX_VOLLEY];
+        volley_info(A, i, e, t, &done_n, &left_n, md);
+        if (f.missiles_intercepted) f.missiles_intercepted[i] = done_n;
+        if (f.missiles_remaining) f.missiles_remaining[i] = left_n;
+        if (f.missile_min_distances)
+#pragma unroll
+            for (int m = 0; m < HLYNR_MAX_VOLLEY; ++m) f.missile_min_distances[(int64_t)HLYNR_MAX_VOLLEY * i + m] = md[m];
+    }
 }
 
 // Appends the finished episode of env i to the compact done list (rare: ~1 per 1000 ticks per env).  Out of line
@@ -1187,7 +1312,8 @@ template <typename R> HD void write_info(const KernelArgs<R>& A, int64_t i, cons
 __device__ __noinline__ void append_done_record(HlynrDoneRecord* recs, int32_t* counter, int32_t cap, int32_t env, int32_t steps,
                                                 uint32_t flags, float distance, float min_d, float fuel, float fuel_used,
                                                 float ep_ret, float ix, float iy, float iz, float mx, float my, float mz,
-                                                const float* obs_row) {
+                                                const float* obs_row, int missiles_intercepted, int missiles_remaining,
+                                                const float* min_distances) {
     const int32_t slot = atomicAdd(counter, 1);
     if (slot >= cap) return;
     HlynrDoneRecord* r = recs + slot;
@@ -1197,6 +1323,9 @@ __device__ __noinline__ void append_done_record(HlynrDoneRecord* recs, int32_t* 
     r->missile_pos[0] = mx; r->missile_pos[1] = my; r->missile_pos[2] = mz;
 #pragma unroll
     for (int k = 0; k < HLYNR_OBS_DIM; ++k) r->terminal_obs[k] = obs_row[k];
+    r->missiles_intercepted = missiles_intercepted; r->missiles_remaining = missiles_remaining;
+#pragma unroll
+    for (int m = 0; m < HLYNR_MAX_VOLLEY; ++m) r->missile_min_distances[m] = min_distances[m];
 }
 template <typename R> HD RngKey make_key(const KernelArgs<R>& A, int64_t global_env) {
     RngKey k;
@@ -1284,7 +1413,7 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, (F == FT_V2OFF && sizeof(R) == 4)
             act[0] = p0.x; act[1] = p0.y; act[2] = p1.x; act[3] = p1.y; act[4] = p2.x; act[5] = p2.y;
         }
         TickOut t;
-        tick_physics<R, F>(A, e, key, act, t);
+        tick_physics<R, F>(A, e, key, act, i, t);
         ob.emit = !kRollout || (s == steps - 1 && A.io.obs != nullptr);
         uint4 ur = t.ur;
         bool need_reset = false;
@@ -1293,7 +1422,7 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, (F == FT_V2OFF && sizeof(R) == 4)
             if (pass == 1) {
                 if (!need_reset) break;
                 e.episode += 1;
-                spawn(A, e, key);
+                spawn(A, e, key, i);
                 ur = draw_raw(key, (uint32_t)e.episode, 0u, HLYNR_BLK_UNI);
             }
             // ring planes are indexed by the lane's OWN (padded) slot: a shadow lane of another warp may run ticks
@@ -1310,12 +1439,16 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, (F == FT_V2OFF && sizeof(R) == 4)
                 }
                 rsum += t.reward;
                 account_episodes(A, active, done, e, t);
-                if (!kRollout && done && active && A.io.done_records)
+                if (!kRollout && done && active && A.io.done_records) {
+                    int vi_n, vr_n;
+                    float vmd[HLYNR_MAX_VOLLEY];
+                    volley_info(A, i, e, t, &vi_n, &vr_n, vmd);
                     append_done_record(A.io.done_records, A.io.done_counter, A.io.done_cap, (int32_t)i, e.steps,
                                        info_flags(e.flags, t.intercepted, t.hit, t.clamped, ob.onboard_det, ob.ground_det, t.fuze) |
                                            (t.terminated ? HLYNR_DONE_TERMINATED : 0u) | (t.truncated ? HLYNR_DONE_TRUNCATED : 0u),
                                        t.distance, (float)e.min_d, (float)e.fuel, (float)e.fuel_used, (float)e.ep_ret, (float)e.ipx,
-                                       (float)e.ipy, (float)e.ipz, (float)e.mpx, (float)e.mpy, (float)e.mpz, ob.row);
+                                       (float)e.ipy, (float)e.ipz, (float)e.mpx, (float)e.mpy, (float)e.mpz, ob.row, vi_n, vr_n, vmd);
+                }
                 need_reset = done && A.auto_reset;
                 if (need_reset) {
                     dcount += 1;
@@ -1484,7 +1617,7 @@ step_kernel_tma(const __grid_constant__ KernelArgs<float> A, const __grid_consta
         // ---- one tick + SB3 auto-reset (same device functions as the direct kernel) ----
         const RngKey key = make_key(A, A.env_offset + ii);
         TickOut t;
-        tick_physics<R, FT_GENERIC>(A, e, key, act, t);
+        tick_physics<R, FT_GENERIC>(A, e, key, act, i, t);
         ObsOut ob;
         ob.row = tiles + warp * OBS_TILE + lane * HLYNR_OBS_DIM;
         ob.emit = true;
@@ -1495,7 +1628,7 @@ step_kernel_tma(const __grid_constant__ KernelArgs<float> A, const __grid_consta
             if (pass == 1) {
                 if (!need_reset) break;
                 e.episode += 1;
-                spawn(A, e, key);
+                spawn(A, e, key, i);
                 ur = draw_raw(key, (uint32_t)e.episode, 0u, HLYNR_BLK_UNI);
             }
             observe<R, FT_GENERIC, true>(A, e, key, ur, i, A.g_row, A.o_row, pre, ob);  // i < n_pad: padded lanes touch only padding
@@ -1534,7 +1667,7 @@ template <typename R> __global__ void __launch_bounds__(HLYNR_BLOCK) reset_kerne
     ob.row = tiles[warp] + lane * HLYNR_OBS_DIM;
     ob.emit = true;
     e.episode += 1;
-    spawn(A, e, key);
+    spawn(A, e, key, i);
     const uint4 ur = draw_raw(key, (uint32_t)e.episode, 0u, HLYNR_BLK_UNI);
     observe<R, FT_GENERIC_MODES>(A, e, key, ur, i, A.g_row, A.o_row, RingPre<R>{}, ob);
     store_env(A, i, e);

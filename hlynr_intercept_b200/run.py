@@ -34,7 +34,7 @@ def make_factory(real_cls, device=0, seed=1234, precision="fp32"):
         if type(inner).__name__ == "InterceptEnvironment" and hasattr(inner, "config"):
             try:
                 venv = HlynrVecEnv(dict(inner.config), n_envs=len(env_fns), device=device, seed=seed, precision=precision)
-            except NotImplementedError as e:  # a mode outside the accelerated path: use the reference env
+            except NotImplementedError as e:  # outside the accelerated path (e.g. volley_size > 8): use the reference env
                 print(f"[hlynr_intercept_b200] falling back to {real_cls.__name__}: {e}", file=sys.stderr)
             else:
                 if hasattr(probe, "close"):

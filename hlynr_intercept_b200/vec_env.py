@@ -205,7 +205,8 @@ class HlynrVecEnv(_VecEnvBase):
                   "crossed_threshold", "precision_mode", "proximity_fuze_enabled", "proximity_fuze_triggered",
                   "proximity_kill_radius")
 
-    def _info_dicts(self, fl, distance, min_distance, fuel_remaining, fuel_used, steps, missile_pos, interceptor_pos, extra=None):
+    def _info_dicts(self, fl, distance, min_distance, fuel_remaining, fuel_used, steps, missile_pos, interceptor_pos,
+                    missiles_intercepted, missiles_remaining, missile_min_distances, extra=None):
         """The reference's info dict, environment.py:829-857 (single-missile mode), for a batch of envs given as
         arrays.  All conversions are vectorised; the per-env Python work is one dict(zip(keys, row)).
         extra: (terminal_obs[k,26], truncated_only list, episode dicts) appended as the SB3 done keys."""
@@ -216,10 +217,12 @@ class HlynrVecEnv(_VecEnvBase):
         hit = (fl & abi.INFO_INTERCEPTED) != 0
         dist = np.asarray(distance).tolist()
         rep = itertools.repeat
+        vk = int(P.volley_size)   # environment.py:844-848
+        mmd = np.asarray(missile_min_distances, dtype=np.float32).reshape(m, -1)[:, :max(vk, 1)].tolist()
         cols = [dist, hit.tolist(), bit(abi.INFO_HIT_TARGET), np.asarray(fuel_remaining).tolist(), np.asarray(fuel_used).tolist(),
                 bit(abi.INFO_CLAMPED), list(np.array(missile_pos, dtype=np.float32)), list(np.array(interceptor_pos, dtype=np.float32)),
                 np.asarray(steps).tolist(), bit(abi.INFO_RADAR_DETECTED), rep(float(P.radar_quality), m), bit(abi.INFO_GROUND_DETECTED),
-                rep(False, m), rep(1, m), hit.astype(np.int64).tolist(), (1 - hit.astype(np.int64)).tolist(), [[d] for d in dist],
+                rep(vk > 0, m), rep(max(vk, 1), m), np.asarray(missiles_intercepted).tolist(), np.asarray(missiles_remaining).tolist(), mmd,
                 np.asarray(min_distance).tolist(), bit(abi.INFO_CROSSED), rep(bool(P.precision_mode), m), rep(bool(P.fuze_enabled), m),
                 bit(abi.INFO_FUZE), rep(float(P.kill_radius), m)]
         keys = self._INFO_KEYS
@@ -234,7 +237,8 @@ class HlynrVecEnv(_VecEnvBase):
         ret, ln = rec["episode_return"].astype(np.float64).round(6).tolist(), rec["steps"].tolist()
         episodes = [{"r": r, "l": l, "t": now} for r, l in zip(ret, ln)]
         return self._info_dicts(fl, rec["distance"], rec["min_distance"], rec["fuel_remaining"], rec["fuel_used"],
-                                rec["steps"], rec["missile_pos"], rec["interceptor_pos"],
+                                rec["steps"], rec["missile_pos"], rec["interceptor_pos"], rec["missiles_intercepted"],
+                                rec["missiles_remaining"], rec["missile_min_distances"],
                                 extra=(rec["terminal_obs"].copy(), tl, episodes))
 
     def _build_infos(self):
@@ -249,7 +253,8 @@ class HlynrVecEnv(_VecEnvBase):
         _lib.check(self.sim.L.hlynr_info_host(self.sim.h, C.byref(self._info_struct)))
         f = self._info
         infos = self._info_dicts(f["flags"], f["distance"], f["min_distance"], f["fuel_remaining"], f["fuel_used"],
-                                 f["steps"], f["missile_pos"], f["interceptor_pos"])
+                                 f["steps"], f["missile_pos"], f["interceptor_pos"], f["missiles_intercepted"],
+                                 f["missiles_remaining"], f["missile_min_distances"])
         if len(rec):
             for i, d in zip(rec["env"].tolist(), self._done_info_dicts(rec, now)):
                 infos[i] = d

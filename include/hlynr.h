@@ -46,6 +46,7 @@ extern "C" {
 #define HLYNR_MAX_ONBOARD_DELAY 10 /* physics_randomizer.py:293 clamps the delay to [1,10] */
 #define HLYNR_MAX_GROUND_DELAY 31
 #define HLYNR_N_DR 13              /* physics_randomizer.py:166-214: 13 draws per episode */
+#define HLYNR_MAX_VOLLEY 8         /* missiles per env in volley mode (environment.py:42-44) */
 
 /* observation_mode, rl_system/environment.py:157-166 */
 enum { HLYNR_OBS_WORLD = 0, HLYNR_OBS_BODY = 1, HLYNR_OBS_LOS = 2 };
@@ -114,7 +115,7 @@ typedef struct HlynrParams {
     int32_t obs_mode;        /* HLYNR_OBS_* */
     int32_t precision_mode;  /* curriculum.precision_mode, environment.py:121 */
     int32_t fuze_enabled;    /* proximity_fuze_enabled :128 */
-    int32_t reserved0;
+    int32_t volley_size;     /* 0 = volley_mode off; 1..HLYNR_MAX_VOLLEY = volley_mode with that many missiles (:42-43) */
     double kill_radius;      /* proximity_kill_radius :129 */
 } HlynrParams;
 
@@ -148,6 +149,9 @@ typedef struct HlynrInfoSoA {
     float* missile_pos;       /* [N,3] info['missile_pos'] */
     float* episode_return;    /* [N] Monitor 'r' of the episode that ended in this call (else running sum) */
     int32_t* episode_length;  /* [N] Monitor 'l' */
+    int32_t* missiles_intercepted;  /* [N] info['missiles_intercepted'] (volley: len(intercepted indices); else 0/1) */
+    int32_t* missiles_remaining;    /* [N] info['missiles_remaining'] */
+    float* missile_min_distances;   /* [N, HLYNR_MAX_VOLLEY] info['missile_min_distances'] (unused slots 0; single mode: [distance]) */
 } HlynrInfoSoA;
 
 #define HLYNR_INFO_INTERCEPTED 0x01
@@ -174,7 +178,9 @@ typedef struct HlynrDoneRecord {
     float episode_return;    /* Monitor 'r' */
     float interceptor_pos[3], missile_pos[3];
     float terminal_obs[HLYNR_OBS_DIM];
-} HlynrDoneRecord;           /* 40 words = 160 bytes */
+    int32_t missiles_intercepted, missiles_remaining;      /* info['missiles_intercepted'], ['missiles_remaining'] */
+    float missile_min_distances[HLYNR_MAX_VOLLEY];         /* info['missile_min_distances'] (single mode: [distance]) */
+} HlynrDoneRecord;           /* 50 words = 200 bytes */
 #define HLYNR_DONE_TERMINATED 0x100u
 #define HLYNR_DONE_TRUNCATED 0x200u
 
@@ -209,7 +215,9 @@ typedef struct HlynrEnvState {
     double prev_d, last_d, min_d, episode_return;
     double kf_x[6], kf_P[4]; /* P as (pp, pv, vp, vv) of the per-axis 2x2 block */
     double T0, base_cd, peak;
+    double vpos[HLYNR_MAX_VOLLEY * 3], vvel[HLYNR_MAX_VOLLEY * 3], vmin[HLYNR_MAX_VOLLEY]; /* volley: missile_states[], min distances */
     int32_t steps, worsen_count, crossed, kf_init, onboard_delay, episode;
+    int32_t vactive[HLYNR_MAX_VOLLEY], vcur, vcount; /* volley: active flags, index of self.missile_state, interceptions */
 } HlynrEnvState;
 
 typedef struct hlynr_sim hlynr_t;

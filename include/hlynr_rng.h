@@ -56,4 +56,9 @@
 #define HLYNR_BLK_ACT0 16u    /* a0..a3 */
 #define HLYNR_BLK_ACT1 17u    /* a4..a5 */
 
+/* volley mode (environment.py:42-44): missile m >= 1 of an env draws from its own blocks (missile 0 uses
+ * HLYNR_BLK_SPAWN0 / HLYNR_BLK_EVADE, so a volley of one missile draws exactly like the single-missile mode) */
+#define HLYNR_BLK_VSPAWN(m) (32u + (unsigned)(m)) /* uniforms: position x,y,z (or radius, azimuth, elevation), speed of missile m */
+#define HLYNR_BLK_VEVADE(m) (48u + (unsigned)(m)) /* normals z0..z2: evasion of missile m */
+
 #endif

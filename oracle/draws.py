@@ -21,6 +21,16 @@ BLK_DR0 = 12
 BLK_ACT0, BLK_ACT1 = 16, 17
 
 
+def blk_vspawn(m):
+    """HLYNR_BLK_VSPAWN(m): spawn uniforms of volley missile m >= 1."""
+    return 32 + m
+
+
+def blk_vevade(m):
+    """HLYNR_BLK_VEVADE(m): evasion normals of volley missile m >= 1."""
+    return 48 + m
+
+
 def philox4x32_10(ctr, key):
     """ctr: (..., 4) uint32, key: (..., 2) uint32 -> (..., 4) uint32."""
     ctr = np.asarray(ctr, dtype=np.uint32)

@@ -93,6 +93,12 @@ CASES.update({
     "hrl_terminal_los_f32_zem": ("yaml:configs/hrl/terminal_los.yaml", None, 8, 1200, False, "zem_los", 500000),
     "hrl_terminal_los_f64_zem": ("yaml:configs/hrl/terminal_los.yaml", None, 4, 1000, True, "zem_los", 500000),
     "hrl_search_los_f32_random": ("yaml:configs/hrl/search_los.yaml", None, 8, 400, False, "random", None),
+    # volley mode (inference.py:392-396): K missiles per env, priority = closest active missile
+    "volley3_cfg4_f32_zem": ("cfg4", dict(volley_mode=True, volley_size=3), 8, 2300, False, "zem", None),
+    "volley3_easy_f64_zem": ("cfg1", dict(volley_mode=True, volley_size=3), 4, 1500, True, "zem", None),
+    "volley5_cfg2_f32_pursuit": ("cfg2", dict(volley_mode=True, volley_size=5), 6, 2100, False, "pursuit", None),
+    "volley4_los_f32_zem": ("yaml:configs/hrl/terminal_los.yaml", dict(volley_mode=True, volley_size=4), 6, 1500, False, "zem_los", 500000),
+    "volley1_cfg4_f32_zem": ("cfg4", dict(volley_mode=True, volley_size=1), 4, 800, False, "zem", None),
     "hrl_eval360los_f32_pn": ("yaml:configs/eval_360_los.yaml", None, 8, 1000, False, "los_pn", None),
 })
 
@@ -105,7 +111,9 @@ def make_policy(policy, ref):
 
 def generate(name):
     base, extra, n, T, f64, policy, tsc = CASES[name]
-    cfg = reference_yaml_env(base[5:]) if base.startswith("yaml:") else case_config(base, extra)
+    cfg = reference_yaml_env(base[5:]) if base.startswith("yaml:") else case_config(base, None)
+    if extra:
+        cfg.update(extra)
     seed = 1234
     ref = rh.RefBatch(cfg, n, seed=seed, float64=f64, training_step_count=tsc)
     pol = make_policy(policy, ref)
@@ -114,6 +122,9 @@ def generate(name):
     rec = dict(actions=[], obs=[], reward=[], terminated=[], truncated=[], terminal_obs=[], distance=[],
                min_distance=[], fuel_remaining=[], fuel_used=[], steps=[], flags=[], interceptor_pos=[],
                missile_pos=[], episode_return=[], episode_length=[])
+    volley_keys = ("missiles_intercepted", "missiles_remaining", "missile_min_distances") if cfg.get("volley_mode") else ()
+    for k in volley_keys:
+        rec[k] = []
     stop_after_first_done = name.startswith("cfg1")
     for t in range(T):
         a = pol(t, obs)
@@ -125,7 +136,7 @@ def generate(name):
         rec["truncated"].append(tr)
         rec["terminal_obs"].append(tobs)
         for k in ("distance", "min_distance", "fuel_remaining", "fuel_used", "steps", "flags", "interceptor_pos",
-                  "missile_pos", "episode_return", "episode_length"):
+                  "missile_pos", "episode_return", "episode_length") + volley_keys:
             rec[k].append(info[k])
         if stop_after_first_done and (te | tr).any():
             break

@@ -289,6 +289,10 @@ typedef struct {
     double thrust[3];
     int steps, worsen, crossed;
     double prev_d, last_d, min_d;
+    /* volley mode (environment.py:42-44, 370-373): missile_states[], missile_min_distances[], intercepted indices;
+     * mpos/mvel above mirror self.missile_state (the priority missile, an alias of one list entry) */
+    double vpos[HLYNR_MAX_VOLLEY][3], vvel[HLYNR_MAX_VOLLEY][3], vmin[HLYNR_MAX_VOLLEY];
+    int vact[HLYNR_MAX_VOLLEY], vcur, vcount;
     /* DR-mutable model constants */
     double T0, base_cd, peak;
     int cd_strong; /* base_cd / peak are np.float64 scalars after DR (physics_randomizer.py:273,278) */
@@ -769,21 +773,29 @@ static void env_reset(Oracle* o, Env* e, float obs[26]) {
     draw_uniform4(&e->rng, 0, HLYNR_BLK_SPAWN1, u1);
     draw_uniform4(&e->rng, 0, HLYNR_BLK_SPAWN2, u2);
     double tgt[3] = {P->target[0], P->target[1], P->target[2]};
-    /* missile :389-435 */
-    if (P->m_spawn_spherical) {
-        double radius = P->m_radius_lo + (P->m_radius_hi - P->m_radius_lo) * u0[0];
-        double az = (P->m_az_lo + (P->m_az_hi - P->m_az_lo) * u0[1]) * M_PI / 180.0;
-        double el = (P->m_el_lo + (P->m_el_hi - P->m_el_lo) * u0[2]) * M_PI / 180.0;
-        double x = radius * cos(el) * cos(az), y = radius * cos(el) * sin(az), z = radius * sin(el);
-        e->mpos[0] = rn(tgt[0] + x, F32); e->mpos[1] = rn(tgt[1] + y, F32); e->mpos[2] = rn(tgt[2] + z, F32);
-    } else {
-        for (int i = 0; i < 3; ++i) e->mpos[i] = rn(P->m_pos_lo[i] + (P->m_pos_hi[i] - P->m_pos_lo[i]) * u0[i], F32);
+    /* missile(s) :386-435 */
+    const int K = P->volley_size > 0 ? P->volley_size : 1;
+    for (int m = 0; m < K; ++m) {
+        double um[4], mp[3], mv[3];
+        if (m == 0) memcpy(um, u0, sizeof(um));
+        else draw_uniform4(&e->rng, 0, HLYNR_BLK_VSPAWN(m), um);
+        if (P->m_spawn_spherical) {
+            double radius = P->m_radius_lo + (P->m_radius_hi - P->m_radius_lo) * um[0];
+            double az = (P->m_az_lo + (P->m_az_hi - P->m_az_lo) * um[1]) * M_PI / 180.0;
+            double el = (P->m_el_lo + (P->m_el_hi - P->m_el_lo) * um[2]) * M_PI / 180.0;
+            double x = radius * cos(el) * cos(az), y = radius * cos(el) * sin(az), z = radius * sin(el);
+            mp[0] = rn(tgt[0] + x, F32); mp[1] = rn(tgt[1] + y, F32); mp[2] = rn(tgt[2] + z, F32);
+        } else {
+            for (int i = 0; i < 3; ++i) mp[i] = rn(P->m_pos_lo[i] + (P->m_pos_hi[i] - P->m_pos_lo[i]) * um[i], F32);
+        }
+        double speed = P->m_speed_lo + (P->m_speed_hi - P->m_speed_lo) * um[3];
+        double tt[3];
+        for (int i = 0; i < 3; ++i) tt[i] = sub(tgt[i], mp[i], F32);
+        double td = norm3(tt, F32);
+        for (int i = 0; i < 3; ++i) mv[i] = mul(dvd(tt[i], td, F32), wk(speed, F32), F32); /* td > 1e-6 always */
+        if (P->volley_size > 0) for (int i = 0; i < 3; ++i) { e->vpos[m][i] = mp[i]; e->vvel[m][i] = mv[i]; }
+        if (m == 0) for (int i = 0; i < 3; ++i) { e->mpos[i] = mp[i]; e->mvel[i] = mv[i]; } /* self.missile_state = missile_states[0] :438 */
     }
-    double speed = P->m_speed_lo + (P->m_speed_hi - P->m_speed_lo) * u0[3];
-    double tt[3];
-    for (int i = 0; i < 3; ++i) tt[i] = sub(tgt[i], e->mpos[i], F32);
-    double td = norm3(tt, F32);
-    for (int i = 0; i < 3; ++i) e->mvel[i] = mul(dvd(tt[i], td, F32), wk(speed, F32), F32); /* td > 1e-6 always */
     /* interceptor :442-467 */
     for (int i = 0; i < 3; ++i) e->ipos[i] = rn(P->i_pos_lo[i] + (P->i_pos_hi[i] - P->i_pos_lo[i]) * u1[i], F32);
     if (P->i_vel_toward_missile) {
@@ -799,6 +811,19 @@ static void env_reset(Oracle* o, Env* e, float obs[26]) {
     /* initial orientation :475-530: rotate +Z onto the line of sight; float64 math on float32 inputs */
     double rv[3];
     for (int i = 0; i < 3; ++i) rv[i] = sub(e->mpos[i], e->ipos[i], F32);
+    if (P->volley_size > 0) { /* :470-486: min distances of every missile, point at the closest one (first wins ties) */
+        double best = INFINITY;
+        int bm = 0;
+        for (int m = 0; m < K; ++m) {
+            double d3[3];
+            for (int i = 0; i < 3; ++i) d3[i] = sub(e->vpos[m][i], e->ipos[i], F32);
+            double d = norm3(d3, F32);
+            e->vmin[m] = d; e->vact[m] = 1;
+            if (d < best) { best = d; bm = m; }
+        }
+        for (int i = 0; i < 3; ++i) rv[i] = sub(e->vpos[bm][i], e->ipos[i], F32);
+        e->vcur = 0; e->vcount = 0;
+    }
     double rd = norm3(rv, F32);
     if (rd > 1e-6) {
         double f[3];
@@ -856,6 +881,51 @@ static void env_reset(Oracle* o, Env* e, float obs[26]) {
 /* ---------------------------------------------------------------------------------------------- */
 /* step :605-859                                                                                   */
 /* ---------------------------------------------------------------------------------------------- */
+/* _update_missile_state :1069-1117 for one missile (same current_wind for all of them) */
+static void missile_physics(Oracle* o, Env* e, uint32_t step, uint32_t evade_blk, double mpos[3], double mvel[3]) {
+    const HlynrParams* P = &o->P;
+    Prec S = o->S;
+    double dt = P->dt;
+        double alt = mpos[2] > 0.0 ? mpos[2] : 0.0;
+        double rho = 1.225, cs = 343.0;
+        int atm_weak = 1;
+        if (P->isa_enabled) { isa_props(e, alt, S, &rho, &cs); atm_weak = 0; }
+        Prec pw = e->wind_f64 ? F64 : F32;
+        Prec pv = PMAX(S, pw);
+        double va[3];
+        for (int i = 0; i < 3; ++i) va[i] = sub(mvel[i], e->wind[i], pv);
+        double vmag = norm3(va, pv);
+        double da[3];
+        Prec pd;
+        if (P->mach_enabled && vmag > 1e-6) {
+            double F[3];
+            mach_drag_force(e, P, va, pv, rho, cs, atm_weak, S, 2.0, F, &pd);
+            double ratio = (0.3 * 1.5) / 0.3; /* python floats :1090,1095 */
+            for (int i = 0; i < 3; ++i) da[i] = dvd(mul(F[i], wk(ratio, pd), pd), wk(1000.0, pd), pd);
+        } else {
+            pd = pv;
+            double c = atm_weak ? wk(-0.5 * 0.3 * rho, pv) : mul(wk(-0.5 * 0.3, S), rho, S);
+            c = mul(c, vmag, pv);
+            for (int i = 0; i < 3; ++i) da[i] = dvd(mul(c, va[i], pv), wk(1000.0, pv), pv);
+        }
+        double ev[3] = {0, 0, 0};
+        if (P->evasion_enabled) {
+            double z[4];
+            draw_normal4(&e->rng, step, evade_blk, z);
+            for (int i = 0; i < 3; ++i) ev[i] = z[i] * 2.0;
+        }
+        double g[3] = {0.0, 0.0, (double)(-9.81f)};
+        double acc[3];
+        Prec p1 = PMAX(pd, F32);
+        for (int i = 0; i < 3; ++i) acc[i] = add(add(da[i], g[i], p1), ev[i], F64); /* evasion = np.zeros(3): float64 */
+        if (P->validate_enabled && !(isfinite(acc[0]) && isfinite(acc[1]) && isfinite(acc[2])))
+            for (int i = 0; i < 3; ++i) acc[i] = isnan(acc[i]) ? 0.0 : (isinf(acc[i]) ? (acc[i] > 0 ? 20.0 : -20.0) : acc[i]);
+        for (int i = 0; i < 3; ++i) {
+            mvel[i] = rn(mvel[i] + acc[i] * dt, S);
+            mpos[i] = add(mpos[i], mul(mvel[i], wk(dt, S), S), S);
+        }
+}
+
 typedef struct {
     float obs[26];
     double reward;
@@ -961,47 +1031,11 @@ static void env_step(Oracle* o, Env* e, const float act[6], StepOut* out) {
             for (int i = 0; i < 4; ++i) e->quat[i] = dvd(nq[i], nn, F32);
         }
     }
-    /* ---- _update_missile_state :1069-1117 (same current_wind) ---- */
-    {
-        double alt = e->mpos[2] > 0.0 ? e->mpos[2] : 0.0;
-        double rho = 1.225, cs = 343.0;
-        int atm_weak = 1;
-        if (P->isa_enabled) { isa_props(e, alt, S, &rho, &cs); atm_weak = 0; }
-        Prec pw = e->wind_f64 ? F64 : F32;
-        Prec pv = PMAX(S, pw);
-        double va[3];
-        for (int i = 0; i < 3; ++i) va[i] = sub(e->mvel[i], e->wind[i], pv);
-        double vmag = norm3(va, pv);
-        double da[3];
-        Prec pd;
-        if (P->mach_enabled && vmag > 1e-6) {
-            double F[3];
-            mach_drag_force(e, P, va, pv, rho, cs, atm_weak, S, 2.0, F, &pd);
-            double ratio = (0.3 * 1.5) / 0.3; /* python floats :1090,1095 */
-            for (int i = 0; i < 3; ++i) da[i] = dvd(mul(F[i], wk(ratio, pd), pd), wk(1000.0, pd), pd);
-        } else {
-            pd = pv;
-            double c = atm_weak ? wk(-0.5 * 0.3 * rho, pv) : mul(wk(-0.5 * 0.3, S), rho, S);
-            c = mul(c, vmag, pv);
-            for (int i = 0; i < 3; ++i) da[i] = dvd(mul(c, va[i], pv), wk(1000.0, pv), pv);
-        }
-        double ev[3] = {0, 0, 0};
-        if (P->evasion_enabled) {
-            double z[4];
-            draw_normal4(&e->rng, step, HLYNR_BLK_EVADE, z);
-            for (int i = 0; i < 3; ++i) ev[i] = z[i] * 2.0;
-        }
-        double g[3] = {0.0, 0.0, (double)(-9.81f)};
-        double acc[3];
-        Prec p1 = PMAX(pd, F32);
-        for (int i = 0; i < 3; ++i) acc[i] = add(add(da[i], g[i], p1), ev[i], F64); /* evasion = np.zeros(3): float64 */
-        if (P->validate_enabled && !(isfinite(acc[0]) && isfinite(acc[1]) && isfinite(acc[2])))
-            for (int i = 0; i < 3; ++i) acc[i] = isnan(acc[i]) ? 0.0 : (isinf(acc[i]) ? (acc[i] > 0 ? 20.0 : -20.0) : acc[i]);
-        for (int i = 0; i < 3; ++i) {
-            e->mvel[i] = rn(e->mvel[i] + acc[i] * dt, S);
-            e->mpos[i] = add(e->mpos[i], mul(e->mvel[i], wk(dt, S), S), S);
-        }
-    }
+    /* ---- missiles :631-638 ---- */
+    if (P->volley_size > 0) {
+        for (int m = 0; m < P->volley_size; ++m)
+            if (e->vact[m]) missile_physics(o, e, step, m == 0 ? HLYNR_BLK_EVADE : HLYNR_BLK_VEVADE(m), e->vpos[m], e->vvel[m]);
+    } else missile_physics(o, e, step, HLYNR_BLK_EVADE, e->mpos, e->mvel);
     /* ---- _update_wind :1119-1129 ---- */
     if (P->enh_wind_enabled) { /* EnhancedWindModel.get_wind_vector physics_models.py:351-387 */
         double alt = e->ipos[2] > 0.0 ? e->ipos[2] : 0.0;
@@ -1057,17 +1091,59 @@ static void env_step(Oracle* o, Env* e, const float act[6], StepOut* out) {
         }
         e->wind_f64 = 1;
     }
-    /* ---- distance / intercept / termination :657-814 ---- */
+    /* ---- distance / intercept / termination :640-814 ---- */
+    double dist;
+    int intercepted = 0, term = 0, trunc = 0, hit = 0, fuze = 0;
+    double radius = P->fuze_enabled ? P->kill_radius : C->intercept_radius;
+    if (P->volley_size > 0) {
+        const int K = P->volley_size;
+        /* _select_priority_missile :236-267: closest ACTIVE missile (strict <, first wins), else missile_states[0] */
+        double dm[HLYNR_MAX_VOLLEY];
+        int pri = -1;
+        double pbest = 0.0;
+        for (int m = 0; m < K; ++m) {
+            double d3[3];
+            for (int i = 0; i < 3; ++i) d3[i] = sub(e->vpos[m][i], e->ipos[i], S);
+            dm[m] = norm3(d3, S);
+            if (e->vact[m] && (pri < 0 || dm[m] < pbest)) { pri = m; pbest = dm[m]; }
+        }
+        if (pri < 0) pri = 0;
+        e->vcur = pri;
+        /* :661-692: per-missile min distance, interception (missile becomes inactive), distance = closest still active */
+        int any_active = 0;
+        dist = 0.0;
+        for (int m = 0; m < K; ++m) {
+            if (!e->vact[m]) continue;
+            if (dm[m] < e->vmin[m]) e->vmin[m] = dm[m];
+            if (LT(e, dm[m], wk(radius, S))) { intercepted = 1; e->vcount += 1; e->vact[m] = 0; }
+        }
+        for (int m = 0; m < K; ++m)
+            if (e->vact[m] && (!any_active || dm[m] < dist)) { dist = dm[m]; any_active = 1; }
+        if (dist < e->min_d) e->min_d = dist;
+        if (intercepted && !e->crossed) e->crossed = 1;
+        if (P->fuze_enabled && LT(e, e->min_d, wk(P->kill_radius, S))) { fuze = 1; intercepted = 1; }
+        /* :724-748: every missile at or below the ground becomes inactive; near the target = mission failure */
+        int all_inactive = 1;
+        for (int m = 0; m < K; ++m) {
+            if (LE(e, e->vpos[m][2], 0.0)) {
+                e->vact[m] = 0;
+                double gx = sub(e->vpos[m][0], P->target[0], S), gy = sub(e->vpos[m][1], P->target[1], S);
+                double gxy[2] = {gx, gy};
+                if (LT(e, sqr(dotn(gxy, gxy, 2, S), S), wk(500.0, S))) hit = 1;
+            }
+            if (e->vact[m]) all_inactive = 0;
+        }
+        if (all_inactive) term = 1;
+        else if (fuze) term = 1;
+        for (int i = 0; i < 3; ++i) { e->mpos[i] = e->vpos[pri][i]; e->mvel[i] = e->vvel[pri][i]; } /* self.missile_state = priority */
+    } else {
     double dd[3];
     for (int i = 0; i < 3; ++i) dd[i] = sub(e->mpos[i], e->ipos[i], S);
-    double dist = norm3(dd, S);
-    double radius = P->fuze_enabled ? P->kill_radius : C->intercept_radius;
-    int intercepted = LT(e, dist, wk(radius, S));
+    dist = norm3(dd, S);
+    intercepted = LT(e, dist, wk(radius, S));
     if (dist < e->min_d) e->min_d = dist;
     if (intercepted && !e->crossed) e->crossed = 1;
-    int fuze = 0;
     if (P->fuze_enabled && LT(e, e->min_d, wk(P->kill_radius, S))) { fuze = 1; intercepted = 1; }
-    int term = 0, trunc = 0, hit = 0;
     if (P->precision_mode) {
         if (LE(e, e->mpos[2], 0.0)) {
             double gx = sub(e->mpos[0], P->target[0], S), gy = sub(e->mpos[1], P->target[1], S);
@@ -1086,6 +1162,7 @@ static void env_step(Oracle* o, Env* e, const float act[6], StepOut* out) {
             if (LT(e, gd, wk(500.0, S))) hit = 1;
             term = 1;
         }
+    }
     }
     if (LT(e, e->ipos[2], 0.0)) term = 1;
     else if (e->fuel <= 0.0) term = 1;
@@ -1246,6 +1323,17 @@ void oracle_step_range(void* h, int64_t i0, int64_t i1, const float* actions, fl
             if (info->missile_pos) for (int k = 0; k < 3; ++k) info->missile_pos[3 * i + k] = (float)e->mpos[k];
             if (info->episode_return) info->episode_return[i] = (float)e->ep_return;
             if (info->episode_length) info->episode_length[i] = e->ep_length;
+            const int vk = o->P.volley_size;
+            if (info->missiles_intercepted) info->missiles_intercepted[i] = vk > 0 ? e->vcount : (s.intercepted ? 1 : 0);
+            if (info->missiles_remaining) {
+                int rem = 0;
+                for (int m = 0; m < vk; ++m) rem += e->vact[m];
+                info->missiles_remaining[i] = vk > 0 ? rem : (s.intercepted ? 0 : 1);
+            }
+            if (info->missile_min_distances)
+                for (int m = 0; m < HLYNR_MAX_VOLLEY; ++m)
+                    info->missile_min_distances[HLYNR_MAX_VOLLEY * i + m] =
+                        vk > 0 ? (m < vk ? (float)e->vmin[m] : 0.f) : (m == 0 ? (float)s.distance : 0.f);
         }
         account(&local, e, &s);
         if ((s.terminated || s.truncated) && auto_reset) {
@@ -1287,6 +1375,11 @@ void oracle_export_state(void* h, int64_t first, int64_t count, HlynrEnvState* o
         s->T0 = e->T0; s->base_cd = e->base_cd; s->peak = e->peak;
         s->steps = e->steps; s->worsen_count = e->worsen; s->crossed = e->crossed; s->kf_init = e->kf.initialized;
         s->onboard_delay = e->has_onb ? e->onb.delay : 0; s->episode = (int32_t)e->rng.episode;
+        for (int m = 0; m < o->P.volley_size; ++m) {
+            for (int k = 0; k < 3; ++k) { s->vpos[3 * m + k] = e->vpos[m][k]; s->vvel[3 * m + k] = e->vvel[m][k]; }
+            s->vmin[m] = e->vmin[m]; s->vactive[m] = e->vact[m];
+        }
+        s->vcur = o->P.volley_size > 0 ? e->vcur : 0; s->vcount = o->P.volley_size > 0 ? e->vcount : 0;
     }
 }
 /* max |P - blockdiag(2x2)| over all envs: checks the decoupling claim the CUDA Kalman relies on */

@@ -99,9 +99,15 @@ class _GlobalRandomTape:
         shape = np.broadcast(lo, hi).shape
         n = int(np.prod(shape)) if shape else 1
         u = np.empty(n, dtype=np.float64)
+        k = getattr(self.ctx, "volley_k", 1)   # reset draws 4 uniforms per missile first (environment.py:389-415), then the interceptor's
         for j in range(n):
             idx = self.ctx.uniform_idx
-            u[j] = self.ctx.uni(draws.BLK_SPAWN0 + idx // 4, idx % 4, step=0)
+            if idx < 4 * k:
+                m = idx // 4
+                blk = draws.BLK_SPAWN0 if m == 0 else draws.blk_vspawn(m)
+                u[j] = self.ctx.uni(blk, idx % 4, step=0)
+            else:
+                u[j] = self.ctx.uni(draws.BLK_SPAWN1 + (idx - 4 * k) // 4, (idx - 4 * k) % 4, step=0)
             self.ctx.uniform_idx += 1
         u = u.reshape(shape) if shape else u[0]
         out = lo + (hi - lo) * u
@@ -110,7 +116,11 @@ class _GlobalRandomTape:
     def randn(self, *shape):
         caller = sys._getframe(1).f_code.co_name
         if caller == "_update_missile_state":
-            blk = draws.BLK_EVADE
+            # which missile of the volley: the caller's `missile_state` argument is an entry of env.missile_states
+            ms = sys._getframe(1).f_locals["missile_state"]
+            env = self.ctx.env
+            m = next((k for k, x in enumerate(getattr(env, "missile_states", [])) if x is ms), 0)
+            blk = draws.BLK_EVADE if m == 0 else draws.blk_vevade(m)
         elif caller == "_update_wind":
             blk = draws.BLK_WIND
         else:
@@ -213,6 +223,8 @@ class RefBatch:
         for i in range(n_envs):
             env = envmod.InterceptEnvironment(dict(env_cfg))
             ctx = _Ctx(seed, env_id_offset + i)
+            ctx.env = env
+            ctx.volley_k = int(env.volley_size) if env.volley_mode else 1
             env.observation_generator.rng = _ObsTape(ctx)
             if env.enhanced_wind_model is not None:
                 env.enhanced_wind_model.rng = _WindTape(ctx)
@@ -231,7 +243,7 @@ class RefBatch:
     def _upcast(self, env):
         if not self.float64:
             return
-        for st in (env.interceptor_state, env.missile_state):
+        for st in [env.interceptor_state] + list(env.missile_states):   # missile_state aliases missile_states[0]
             st["position"] = st["position"].astype(np.float64)
             st["velocity"] = st["velocity"].astype(np.float64)
         if getattr(env, "thrust_dynamics_enabled", False):
@@ -270,7 +282,9 @@ class RefBatch:
         info = dict(distance=np.zeros(n), min_distance=np.zeros(n), fuel_remaining=np.zeros(n),
                     fuel_used=np.zeros(n), steps=np.zeros(n, np.int32), flags=np.zeros(n, np.uint8),
                     interceptor_pos=np.zeros((n, 3)), missile_pos=np.zeros((n, 3)),
-                    episode_return=np.zeros(n), episode_length=np.zeros(n, np.int32))
+                    episode_return=np.zeros(n), episode_length=np.zeros(n, np.int32),
+                    missiles_intercepted=np.zeros(n, np.int32), missiles_remaining=np.zeros(n, np.int32),
+                    missile_min_distances=np.zeros((n, 8)))
         for i in range(n):
             env, ctx = self.envs[i], self.ctxs[i]
             ctx.at(int(self.episode[i]), env.steps + 1)
@@ -302,6 +316,10 @@ class RefBatch:
             info["missile_pos"][i] = inf["missile_pos"]
             info["episode_return"][i] = self.ep_return[i]
             info["episode_length"][i] = self.ep_length[i]
+            info["missiles_intercepted"][i] = inf["missiles_intercepted"]
+            info["missiles_remaining"][i] = inf["missiles_remaining"]
+            md = list(inf["missile_min_distances"])
+            info["missile_min_distances"][i, :len(md)] = md
             if (te or tr) and auto_reset:
                 term_obs[i] = o
                 o = self._reset_one(i)
@@ -318,8 +336,17 @@ class RefBatch:
                    base_cd=np.zeros(n), peak=np.zeros(n), steps=np.zeros(n, np.int32),
                    worsen_count=np.zeros(n, np.int32), crossed=np.zeros(n, np.int32),
                    kf_init=np.zeros(n, np.int32), onboard_delay=np.zeros(n, np.int32),
-                   episode=np.zeros(n, np.int32), kf_decoupling_err=np.zeros(n))
+                   episode=np.zeros(n, np.int32), kf_decoupling_err=np.zeros(n),
+                   vpos=np.zeros((n, 24)), vvel=np.zeros((n, 24)), vmin=np.zeros((n, 8)), vactive=np.zeros((n, 8), np.int32),
+                   vcur=np.zeros(n, np.int32), vcount=np.zeros(n, np.int32))
         for i, env in enumerate(self.envs):
+            if env.volley_mode:
+                for k, ms in enumerate(env.missile_states):
+                    out["vpos"][i, 3 * k:3 * k + 3], out["vvel"][i, 3 * k:3 * k + 3] = ms["position"], ms["velocity"]
+                    out["vmin"][i, k], out["vactive"][i, k] = env.missile_min_distances[k], int(ms["active"])
+                    if ms is env.missile_state:
+                        out["vcur"][i] = k
+                out["vcount"][i] = len(env.intercepted_missile_indices)
             s, m = env.interceptor_state, env.missile_state
             out["ipos"][i], out["ivel"][i], out["quat"][i] = s["position"], s["velocity"], s["orientation"]
             out["fuel"][i], out["fuel_used"][i] = s["fuel"], env.total_fuel_used

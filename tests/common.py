@@ -85,6 +85,11 @@ def replay_against_golden(sim, g, rtol_state, obs_atol, reward_rtol, reward_atol
         for k in ("interceptor_pos", "missile_pos"):
             np.testing.assert_allclose(info[k][a], g[k][t][a], rtol=rtol_state, atol=rtol_state * 100,
                                        err_msg=f"info[{k}] at t={t}")
+        if "missiles_intercepted" in g:   # volley-mode fixtures (environment.py:844-848)
+            assert (info["missiles_intercepted"][a] == g["missiles_intercepted"][t][a]).all(), f"missiles_intercepted at t={t}"
+            assert (info["missiles_remaining"][a] == g["missiles_remaining"][t][a]).all(), f"missiles_remaining at t={t}"
+            np.testing.assert_allclose(info["missile_min_distances"][a], g["missile_min_distances"][t][a],
+                                       rtol=max(rtol_state, reward_rtol), atol=reward_atol, err_msg=f"missile_min_distances at t={t}")
         done = (g["terminated"][t] | g["truncated"][t]).astype(bool)
         for i in np.nonzero(done)[0]:
             assert tuple(g["terminal_idx"][term_k]) == (t, i)
@@ -92,9 +97,10 @@ def replay_against_golden(sim, g, rtol_state, obs_atol, reward_rtol, reward_atol
                 np.testing.assert_allclose(tobs[i], g["terminal_obs"][term_k], rtol=0, atol=max(obs_atol, tti_atol))
             term_k += 1
     st = sim.export_state()
-    for k in STATE_INT_FIELDS:
+    volley = "final_vpos" in g and g["meta"]["env_cfg"].get("volley_mode", False)
+    for k in STATE_INT_FIELDS + (["vactive", "vcur", "vcount"] if volley else []):
         assert (st[k][alive] == g["final_" + k][alive]).all(), k
-    for k in STATE_FLOAT_FIELDS:
+    for k in STATE_FLOAT_FIELDS + (["vpos", "vvel", "vmin"] if volley else []):
         ref = g["final_" + k][alive]
         scale = np.abs(ref).max() + 1e-6 if ref.size else 1.0
         np.testing.assert_allclose(st[k][alive], ref, rtol=rtol_state, atol=rtol_state * scale,

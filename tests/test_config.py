@@ -47,9 +47,13 @@ def test_curriculum_ramps():
     assert abs(cur.onboard_reliability - 0.75) < 1e-12 and abs(cur.ground_reliability - 0.85) < 1e-12
 
 
-def test_unsupported_modes_fail_loudly():
-    with pytest.raises(NotImplementedError):
-        config.resolve_config(dict(volley_mode=True), warn_dead=False)
+def test_volley_mode_resolution_and_limits():
+    P, _ = config.resolve_config(dict(volley_mode=True, volley_size=3), warn_dead=False)
+    assert P.volley_size == 3
+    assert config.resolve_config(dict(volley_size=3), warn_dead=False)[0].volley_size == 0   # volley_mode off: size ignored
+    assert config.resolve_config(dict(volley_mode=True), warn_dead=False)[0].volley_size == 1  # environment.py:43 default
+    with pytest.raises(NotImplementedError):   # more missiles per env than the kernel's planes hold: fail loudly
+        config.resolve_config(dict(volley_mode=True, volley_size=9), warn_dead=False)
 
 
 @pytest.mark.reference

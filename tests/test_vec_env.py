@@ -187,3 +187,29 @@ def test_step_host_with_unpinned_buffers_and_terminal_rows():
             seen += 1
     assert seen > 5 and np.isnan(tobs).any()
     a_env.close(); b_env.close()
+
+
+def test_volley_mode_info_fields():
+    """inference.py --volley reads info['missiles_intercepted'], ['volley_size'], ['missiles_remaining'] (inference.py:561-585)."""
+    from hlynr_intercept_b200.vec_env import HlynrVecEnv
+
+    cfg = config.baseline_config("cfg4")
+    cfg.update(volley_mode=True, volley_size=3)
+    for lazy in (False, True):
+        v = HlynrVecEnv(cfg, n_envs=6, seed=3, warn_dead=False, lazy_infos=lazy)
+        v.reset()
+        obs, rew, dones, infos = v.step(np.zeros((6, 6), np.float32))
+        if not lazy:
+            d = infos[0]
+            assert d["volley_mode"] is True and d["volley_size"] == 3 and d["missiles_intercepted"] == 0
+            assert d["missiles_remaining"] == 3 and len(d["missile_min_distances"]) == 3 and min(d["missile_min_distances"]) > 100.0
+        v.sim.rollout(2100, None)       # every episode ends (max_steps 2000): done records carry the volley fields
+        seen = 0
+        for _ in range(3):
+            obs, rew, dones, infos = v.step(np.zeros((6, 6), np.float32))
+            for i in np.nonzero(dones)[0]:
+                d = infos[int(i)]
+                assert d["volley_size"] == 3 and 0 <= d["missiles_intercepted"] <= 3 and len(d["missile_min_distances"]) == 3
+                assert "terminal_observation" in d and "episode" in d
+                seen += 1
+        v.close()
