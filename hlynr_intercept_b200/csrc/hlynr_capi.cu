@@ -357,8 +357,8 @@ static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) 
 // Feature set of a resolved configuration; a specialised instantiation exists for FT_V2ON and FT_V2OFF.
 static int feature_set(const HlynrParams& p) {
     if (p.obs_mode != HLYNR_OBS_WORLD || p.volley_size > 0) return FT_GENERIC_MODES;
-    if (p.dr_enabled || p.precision_mode || p.fuze_enabled) return FT_GENERIC;
-    int f = 0;
+    if (p.precision_mode || p.fuze_enabled) return FT_GENERIC;
+    int f = p.dr_enabled ? FT_DR : 0;
     if (p.isa_enabled) f |= FT_ISA;
     if (p.mach_enabled) f |= FT_MACH;
     if (p.enh_wind_enabled) f |= FT_ENHW;
@@ -367,7 +367,7 @@ static int feature_set(const HlynrParams& p) {
     if (p.ground_enabled) f |= FT_GROUND;
     if (p.ground_enabled && p.ground_delay > 0) f |= FT_GDELAY;
     if (p.evasion_enabled) f |= FT_EVADE;
-    return (f == FT_V2ON || f == FT_V2OFF) ? f : FT_GENERIC;
+    return (f == FT_V2ON || f == FT_V2OFF || f == FT_V2ON_DR) ? f : FT_GENERIC;
 }
 template <bool kRollout> static void launch_step_f32(const hlynr_sim* s, const KernelArgs<float>& A, cudaStream_t st, bool specialise) {
     const int grid = grid_for(A.lim - A.first, HLYNR_BLOCK);
@@ -375,6 +375,7 @@ template <bool kRollout> static void launch_step_f32(const hlynr_sim* s, const K
     if (!specialise && f >= 0) f = FT_GENERIC;
     if (f == FT_V2ON) step_kernel<float, kRollout, FT_V2ON><<<grid, HLYNR_BLOCK, 0, st>>>(A);
     else if (f == FT_V2OFF) step_kernel<float, kRollout, FT_V2OFF><<<grid, HLYNR_BLOCK, 0, st>>>(A);
+    else if (f == FT_V2ON_DR) step_kernel<float, kRollout, FT_V2ON_DR><<<grid, HLYNR_BLOCK, 0, st>>>(A);
     else if (f == FT_GENERIC_MODES) step_kernel<float, kRollout, FT_GENERIC_MODES><<<grid, HLYNR_BLOCK, 0, st>>>(A);
     else step_kernel<float, kRollout, FT_GENERIC><<<grid, HLYNR_BLOCK, 0, st>>>(A);
 }

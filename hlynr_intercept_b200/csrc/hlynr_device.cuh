@@ -191,11 +191,12 @@ template <typename R> struct KParams {
 // compile-time constants, so the uniform flag tests and the dead branches disappear.  The host launches a
 // specialised instantiation when the resolved configuration matches one, else the generic kernel.
 // ------------------------------------------------------------------------------------------------
-enum { FT_ISA = 1, FT_MACH = 2, FT_ENHW = 4, FT_THRUST = 8, FT_ONBD = 16, FT_GROUND = 32, FT_GDELAY = 64, FT_EVADE = 128 };
+enum { FT_ISA = 1, FT_MACH = 2, FT_ENHW = 4, FT_THRUST = 8, FT_ONBD = 16, FT_GROUND = 32, FT_GDELAY = 64, FT_EVADE = 128, FT_DR = 256 };
 #define FT_GENERIC (-1)        /* every switch at run time, world_frame observations */
 #define FT_GENERIC_MODES (-2)  /* the same + observation_mode body_frame / los_frame (and the LOS action transform) + volley mode */
 #define FT_V2ON (FT_ISA | FT_MACH | FT_ENHW | FT_THRUST | FT_ONBD | FT_GROUND | FT_GDELAY | FT_EVADE)  /* cfg4: medium, v2.0 on */
 #define FT_V2OFF (FT_GROUND | FT_GDELAY | FT_EVADE)                                                   /* cfg2: medium, v2.0 off */
+#define FT_V2ON_DR (FT_V2ON | FT_DR)                                                                   /* cfg3: hard, v2.0 on + domain randomization */
 template <int F> struct Feat {
     static constexpr bool generic = F < 0;
     template <typename P> static HD bool isa(const P& p) { if constexpr (F < 0) return p.isa != 0; else return (F & FT_ISA) != 0; }
@@ -206,8 +207,8 @@ template <int F> struct Feat {
     template <typename P> static HD bool ground(const P& p) { if constexpr (F < 0) return p.ground != 0; else return (F & FT_GROUND) != 0; }
     template <typename P> static HD bool ground_delay(const P& p) { if constexpr (F < 0) return p.ground_delay > 0; else return (F & FT_GDELAY) != 0; }
     template <typename P> static HD bool evasion(const P& p) { if constexpr (F < 0) return p.evasion != 0; else return (F & FT_EVADE) != 0; }
-    // never part of a specialised set: domain randomization and the non-standard modes
-    template <typename P> static HD bool dr(const P& p) { if constexpr (F < 0) return p.dr != 0; else return false; }
+    template <typename P> static HD bool dr(const P& p) { if constexpr (F < 0) return p.dr != 0; else return (F & FT_DR) != 0; }
+    // never part of a specialised set: the non-standard modes
     template <typename P> static HD bool precision_mode(const P& p) { if constexpr (F < 0) return p.precision_mode != 0; else return false; }
     template <typename P> static HD bool fuze(const P& p) { if constexpr (F < 0) return p.fuze != 0; else return false; }
     template <typename P> static HD int volley(const P& p) { if constexpr (F == FT_GENERIC_MODES) return p.volley_k; else return 0; }
