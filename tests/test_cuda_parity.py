@@ -194,3 +194,42 @@ def test_full_size_invariants_1m_envs():
     again = small.reset(torch.zeros(4096, dtype=torch.uint8)).cpu()
     assert (again == first).all()
     assert (small.export_state()["episode"] == 0).all()
+
+
+@pytest.mark.parametrize("f64", [False, True])
+def test_manual_reset_flow_without_auto_reset(f64):
+    """The Gymnasium single-env flow (inference.py:500-520): step(auto_reset=False) returns the terminal observation as
+    obs and leaves the env alone; the caller resets the finished envs with a mask.  CUDA vs oracle, flags exact."""
+    cfg = config.baseline_config("cfg4")
+    cfg["max_steps"] = 45
+    P, cur = config.resolve_config(cfg, warn_dead=False)
+    n = 333
+    cuda = CudaBatch(P, cur, n, seed=21, float64=f64)
+    orc = oracle.OracleBatch(P, cur, n, seed=21, float64=f64)
+    oc, oo = cuda.reset(), orc.reset()
+    np.testing.assert_allclose(oc, oo, atol=1e-3)
+    rng = np.random.default_rng(4)
+    tol = TOL[f64]
+    resets = 0
+    for t in range(140):
+        a = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        c = cuda.step(a, auto_reset=False)
+        o = orc.step(a, auto_reset=False)
+        assert (c[2] == o[2]).all() and (c[3] == o[3]).all() and (c[5]["flags"] == o[5]["flags"]).all(), t
+        assert (c[5]["steps"] == o[5]["steps"]).all()
+        d = np.abs(c[0] - o[0]); d[:, [9, 10, 11, 13, 16]] = 0
+        assert d.max() <= tol["obs_atol"], (t, d.max())
+        np.testing.assert_allclose(c[1], o[1], rtol=tol["reward_rtol"], atol=tol["reward_atol"])
+        done = (c[2] | c[3]).astype(bool)
+        # reset only every other finished env now: the others keep stepping past their end, as the reference env allows
+        mask = (done & (np.arange(n) % 2 == 0)) | (o[5]["steps"] > 60)
+        if mask.any():
+            rc, ro = cuda.reset(mask.astype(np.uint8)), orc.reset(mask.astype(np.uint8))
+            np.testing.assert_allclose(rc[mask], ro[mask], atol=1e-3)
+            resets += int(mask.sum())
+    assert resets > n
+    sc, so = cuda.export_state(), orc.export_state()
+    for k in STATE_INT_FIELDS:
+        assert (sc[k] == so[k]).all(), k
+    for k in ("ipos", "ivel", "mpos", "mvel", "fuel"):
+        np.testing.assert_allclose(sc[k], so[k], rtol=tol["rtol_state"], atol=tol["rtol_state"] * 10)
