@@ -182,7 +182,7 @@ def main():
     ap.add_argument("--ref-envs", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused", type=int, default=64, help="k of the extra fused-rollout measurement (0 = skip)")
-    ap.add_argument("--rollout-steps", type=int, default=16, help="n_steps of the extra on-device PPO rollout-collection measurement (0 = skip)")
+    ap.add_argument("--rollout-steps", type=int, default=24, help="n_steps of the extra on-device PPO rollout-collection measurement (0 = skip)")
     ap.add_argument("--rollout-envs", type=int, default=131072)
     ap.add_argument("--post-steps", type=int, default=200, help="steps of the extra step + frame-stack/normalise measurement (0 = skip)")
     args = ap.parse_args()
@@ -315,6 +315,18 @@ def main():
         col.collect()
         e1.record()
         barrier()
+        te_ = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te_, op=dist.ReduceOp.MAX)
+        graphed = args.rollout_steps % col.graph_period() == 0
+        if graphed:   # the whole collect() as ONE CUDA-graph launch (launch-bound otherwise: ~25 kernels per step)
+            col.capture()
+            col.replay()
+            barrier()
+            e0.record()
+            col.replay()
+            e1.record()
+            barrier()
         tr_ = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tr_, op=dist.ReduceOp.MAX)
@@ -346,6 +358,7 @@ def main():
         roll = {"value": world * n_roll * args.rollout_steps / (float(tr_.item()) * 1e-3), "unit": "env-steps/s",
                 "envs_per_gpu": n_roll, "n_steps": args.rollout_steps,
                 "policy": "GaussianMlpPolicy 104->512->512->256 (pi and vf), LayerNorm, fp32 weights, TF32 GEMMs (torch / cuBLAS)",
+                "cuda_graph": bool(graphed), "eager": world * n_roll * args.rollout_steps / (float(te_.item()) * 1e-3),
                 "without_policy_network": world * n_roll * args.rollout_steps / (float(tn_.item()) * 1e-3),
                 "timeout_bootstrap_overflow": int(col.overflow.item()),
                 "note": "DeviceRolloutCollector.collect(): policy forward + hlynr_step + hlynr_post_step + "

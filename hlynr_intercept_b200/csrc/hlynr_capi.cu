@@ -539,6 +539,20 @@ int hlynr_set_option(hlynr_t* s, const char* name, int64_t value) {
     }
     return fail("hlynr_set_option: unknown option '%s'", name);
 }
+static int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
+int hlynr_ring_period(const hlynr_t* s, int* out) {
+    if (!s || !out) return fail("null argument");
+    const KParams<float> k = make_kparams<float>(s->params);
+    const int64_t a = k.onb_ring_len > 0 ? k.onb_ring_len : 1, b = k.gnd_ring_len > 0 ? k.gnd_ring_len : 1;
+    *out = (int)(a / gcd64(a, b) * b);
+    return 0;
+}
+int hlynr_note_replayed_ticks(hlynr_t* s, int64_t ticks, int64_t launches) {
+    if (!s) return fail("hlynr_note_replayed_ticks: null handle");
+    // negative values undo the host-side bookkeeping of calls that were only RECORDED into a graph (not executed)
+    s->tick = (uint32_t)((int64_t)s->tick + ticks); s->env_steps += (double)s->n * (double)ticks; s->launches += launches;
+    return 0;
+}
 int hlynr_launch_count(const hlynr_t* s, int64_t* out) { if (!s || !out) return fail("null argument"); *out = s->launches; return 0; }
 
 int hlynr_reset(hlynr_t* s, const uint8_t* mask_dev, float* obs_dev, void* stream) {

@@ -367,6 +367,12 @@ void hlynr_post_destroy(hlynr_post_t* p) {
 int hlynr_post_obs_dim(const hlynr_post_t* p, int* out) { if (!p || !out) return fail("null argument"); *out = p->D; return 0; }
 int hlynr_post_launch_count(const hlynr_post_t* p, int64_t* out) { if (!p || !out) return fail("null argument"); *out = p->launches; return 0; }
 
+int hlynr_post_note_replayed_steps(hlynr_post_t* p, int64_t steps, int64_t launches) {
+    if (!p) return fail("hlynr_post_note_replayed_steps: null handle");
+    p->t = (uint32_t)((int64_t)p->t + steps); p->launches += launches;  // negative: undo the bookkeeping of recorded-only calls
+    return 0;
+}
+
 int hlynr_post_obs_target(hlynr_post_t* p, float** obs_dev) {
     if (!p || !obs_dev) return fail("hlynr_post_obs_target: null argument");
     *obs_dev = p->frames + (int64_t)(p->t % (uint32_t)p->k) * p->plane;

@@ -85,6 +85,7 @@ class DeviceRolloutCollector:
         self.rows = int(bootstrap_rows) if bootstrap_rows else min(n, max(256, n // 32))
         self._started = False
         self.L = pipe.L
+        self._graph = None
 
     def _stream(self):
         return C.c_void_p(_torch().cuda.current_stream(self.sim.device).cuda_stream)
@@ -124,4 +125,45 @@ class DeviceRolloutCollector:
             _lib.check(self.L.hlynr_gae(p(self.rewards), p(self.values), p(self.episode_starts), p(last_values), p(self.last_dones),
                                         self.T, sim.n, self.gamma, self.gae_lambda, p(self.advantages), p(self.returns),
                                         sim.device_index, self._stream()))
+        return self
+
+    # ---- CUDA graph: the whole collect() (T x ~20 launches) as one graph launch --------------------------------------
+    def graph_period(self):
+        """collect() can be captured once and replayed iff n_steps is a multiple of this (ring rows of the delay buffers,
+        frame-ring slot and the age ping-pong are kernel arguments derived from host-side tick counters)."""
+        per = C.c_int()
+        _lib.check(self.L.hlynr_ring_period(self.sim.h, C.byref(per)))
+        return math.lcm(per.value, self.pipe.n_stack, 2)
+
+    def capture(self):
+        """Warm-up + stream capture of collect() into a CUDA graph (launch-bound at small n_envs: ~20 launches per step).
+        The curriculum scalars and the seed are baked into the captured kernel arguments: re-capture after changing them."""
+        torch = _torch()
+        if self.T % self.graph_period():
+            raise ValueError(f"n_steps={self.T} must be a multiple of {self.graph_period()} to be graph-captured")
+        cur = torch.cuda.current_stream(self.sim.device)
+        side = torch.cuda.Stream(device=self.sim.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self.collect()   # allocations, cuBLAS workspaces, lazy module init
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.sim.device)
+        l0, p0 = self.sim.launch_count(), self.pipe.launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.collect()   # recorded, not executed: the host-side tick counters advance by T, the device state does not,
+        self._graph = g      # which is consistent because T is a multiple of every ring period
+        self._graph_launches = (self.sim.launch_count() - l0, self.pipe.launch_count() - p0)
+        # the recording advanced the host-side counters although nothing ran: undo (ring phases are unchanged, T % period == 0)
+        _lib.check(self.L.hlynr_note_replayed_ticks(self.sim.h, -self.T, -self._graph_launches[0]))
+        _lib.check(self.L.hlynr_post_note_replayed_steps(self.pipe.h, -self.T, -self._graph_launches[1]))
+        return self
+
+    def replay(self):
+        """One collect() as a single graph launch."""
+        if self._graph is None:
+            raise RuntimeError("capture() first")
+        self._graph.replay()
+        _lib.check(self.L.hlynr_note_replayed_ticks(self.sim.h, self.T, self._graph_launches[0]))
+        _lib.check(self.L.hlynr_post_note_replayed_steps(self.pipe.h, self.T, self._graph_launches[1]))
         return self

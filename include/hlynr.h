@@ -316,6 +316,15 @@ int hlynr_debug_draws(hlynr_t* sim, int64_t env_global_id, uint32_t episode, uin
  * (default 1, measured best on B200; 0 = off). */
 int hlynr_set_option(hlynr_t* sim, const char* name, int64_t value);
 
+/* CUDA-graph support.  Every launch of this library goes to the caller's stream, so a sequence of hlynr_* calls can be
+ * stream-captured (e.g. torch.cuda.graph) once allocations have happened in a warm-up call.  The ring-row indices of a
+ * tick are kernel arguments computed from the handle's tick counter, so a captured sequence of T ticks replays correctly
+ * iff T is a multiple of hlynr_ring_period(); after each replay the host-side counters are advanced with
+ * hlynr_note_replayed_ticks(sim, T) (negative values undo the bookkeeping of calls that were only recorded, not executed).
+ * Curriculum scalars and the seed are baked into the captured arguments. */
+int hlynr_ring_period(const hlynr_t* sim, int* out);   /* lcm(onboard ring length, ground ring length), >= 1 */
+int hlynr_note_replayed_ticks(hlynr_t* sim, int64_t ticks, int64_t launches);
+
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int hlynr_launch_count(const hlynr_t* sim, int64_t* out);
 

@@ -72,6 +72,9 @@ int hlynr_post_set_stats(hlynr_post_t* post, const double* mean, const double* v
  * absolute difference to the incrementally maintained ones; resync != 0 also replaces them. */
 int hlynr_post_check_sums(hlynr_post_t* post, int resync, double* max_abs_diff, void* stream);
 int hlynr_post_launch_count(const hlynr_post_t* post, int64_t* out);
+/* CUDA-graph support (see hlynr_ring_period in hlynr.h): a captured sequence of T steps replays correctly iff T is a
+ * multiple of n_stack; after each replay call hlynr_post_note_replayed_steps(post, T). */
+int hlynr_post_note_replayed_steps(hlynr_post_t* post, int64_t steps, int64_t launches);
 
 #ifdef __cplusplus
 }

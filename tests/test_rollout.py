@@ -101,3 +101,53 @@ def test_collector_matches_step_by_step_restatement():
         p_.close()
     for s in sims:
         s.close()
+
+
+@pytest.mark.gpu
+def test_graph_replay_equals_eager_collect():
+    """collect() captured into a CUDA graph and replayed == the same collects issued eagerly (bit for bit)."""
+    import torch
+
+    from hlynr_intercept_b200.post import HlynrObsPipeline
+    from hlynr_intercept_b200.rollout import DeviceRolloutCollector
+    from hlynr_intercept_b200.sim import HlynrSim
+
+    class Pol(torch.nn.Module):   # deterministic policy: no RNG, so eager and replayed runs are comparable
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(0)
+            self.w = torch.nn.Parameter(torch.randn(104, 6, generator=g).cuda() * 0.3)
+            self.v = torch.nn.Parameter(torch.randn(104, generator=g).cuda() * 0.1)
+
+        def value(self, obs):
+            return obs @ self.v
+
+        def forward(self, obs):
+            a = torch.tanh(obs @ self.w)
+            return a, obs @ self.v, -(a * a).sum(-1)
+
+    n, k = 1500, 4
+    cfg = config.baseline_config("cfg4")
+    cfg["max_steps"] = 30
+    cols = []
+    for _ in range(2):
+        sim = HlynrSim(cfg, n_envs=n, seed=11, warn_dead=False)
+        pipe = HlynrObsPipeline(sim, n_stack=k, training=True)
+        cols.append(DeviceRolloutCollector(pipe, Pol(), n_steps=cols[0].graph_period() if cols else 12, bootstrap_rows=n))
+    T = cols[0].graph_period()
+    assert T % 12 == 0 and cols[0].T == T
+    eager, graphed = cols
+    graphed.capture()            # runs one eager collect (warm-up) before recording
+    eager.collect()
+    for rep in range(3):
+        eager.collect()
+        graphed.replay()
+        torch.cuda.synchronize()
+        for name in ("obs", "actions", "rewards", "episode_starts", "values", "advantages", "returns"):
+            a, b = getattr(eager, name).cpu().numpy(), getattr(graphed, name).cpu().numpy()
+            np.testing.assert_array_equal(a, b, err_msg=f"{name} after replay {rep}")
+    se, sg = eager.sim.export_state(), graphed.sim.export_state()
+    assert (se["steps"] == sg["steps"]).all() and (se["episode"] == sg["episode"]).all() and (se["ipos"] == sg["ipos"]).all()
+    assert eager.sim.stats()["env_steps"] == graphed.sim.stats()["env_steps"] == 4 * T * n
+    with pytest.raises(ValueError):
+        DeviceRolloutCollector(graphed.pipe, Pol(), n_steps=T + 1).capture()
