@@ -16,8 +16,12 @@ from hlynr_intercept_b200 import config
 from . import ref_harness as rh
 from .gen_golden import GOLDEN_DIR
 
-CASES = {"stat_cfg4_random": ("cfg4", "random", 96), "stat_cfg4_pursuit": ("cfg4", "pursuit", 96),
-         "stat_cfg2_pursuit": ("cfg2", "pursuit", 96)}
+# name: (base cfg or "yaml:<path under rl_system>", policy, episodes, extra env keys, training_step_count)
+CASES = {"stat_cfg4_random": ("cfg4", "random", 96, None, None), "stat_cfg4_pursuit": ("cfg4", "pursuit", 96, None, None),
+         "stat_cfg2_pursuit": ("cfg2", "pursuit", 96, None, None),
+         "stat_hrl_los_pn": ("yaml:configs/hrl/terminal_los.yaml", "los_pn", 96, None, 500000),
+         "stat_hrl_rotinv_mixed": ("yaml:configs/hrl/terminal_360_rotinv.yaml", "mixed", 96, None, 1000000),
+         "stat_volley3_pursuit": ("cfg4", "pursuit", 64, dict(volley_mode=True, volley_size=3), None)}
 CAUSES = ["intercepted", "hit_target", "interceptor_crash", "fuel_out", "missile_ground", "worsening", "timeout"]
 
 
@@ -42,12 +46,19 @@ def generate(name):
     import environment as envmod  # noqa: F401  (the reference module; native numpy RNGs are used here)
     from environment import InterceptEnvironment
 
-    base, policy, n_ep = CASES[name]
+    from .gen_golden import reference_yaml_env
+
+    base, policy, n_ep, extra, tsc = CASES[name]
     # the harness may have replaced np in the reference module by the tape proxy: restore real numpy
     envmod.np = np
-    cfg = config.baseline_config(base)
+    cfg = reference_yaml_env(base[5:]) if base.startswith("yaml:") else config.baseline_config(base)
+    if extra:
+        cfg.update(extra)
     env = InterceptEnvironment(dict(cfg))
-    pol = rh.policy_random(11) if policy == "random" else rh.policy_pursuit()
+    if tsc is not None:
+        env.set_training_step_count(tsc)
+    pol = {"random": lambda: rh.policy_random(11), "pursuit": rh.policy_pursuit, "los_pn": lambda: rh.policy_los_pn(11),
+           "mixed": lambda: rh.policy_mixed(11)}[policy]()
     out = dict(length=[], ret=[], min_distance=[], final_distance=[], cause=[], lock_fraction=[])
     for ep in range(n_ep):
         obs, _ = env.reset(seed=1000 + ep)
@@ -62,7 +73,7 @@ def generate(name):
         out["final_distance"].append(float(info["distance"])); out["cause"].append(cause_of(info, te, env))
         out["lock_fraction"].append(locks / t)
     arrs = {k: np.array(v) for k, v in out.items()}
-    arrs["meta"] = np.array(json.dumps(dict(name=name, base=base, policy=policy, env_cfg=cfg, causes=CAUSES,
+    arrs["meta"] = np.array(json.dumps(dict(name=name, base=base, policy=policy, env_cfg=cfg, causes=CAUSES, training_step_count=tsc,
                                             numpy=np.__version__, generator="oracle/gen_stat_golden.py")))
     np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **arrs)
     print(name, "len", arrs["length"].mean(), "ret", arrs["ret"].mean(), "min_d", arrs["min_distance"].mean(),

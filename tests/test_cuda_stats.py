@@ -24,11 +24,14 @@ def load_stat(name):
     return d
 
 
-def play_first_episodes(env_cfg, policy, n=4096, seed=321, max_ticks=2100):
+def play_first_episodes(env_cfg, policy, n=4096, seed=321, max_ticks=2100, training_step_count=None):
     P, cur = config.resolve_config(env_cfg, warn_dead=False)
+    if training_step_count is not None:
+        cur.set_training_step_count(training_step_count)
     sim = CudaBatch(P, cur, n, seed=seed)
     obs = sim.reset()
-    pol = ref_harness.policy_random(5) if policy == "random" else ref_harness.policy_pursuit()
+    pol = {"random": lambda: ref_harness.policy_random(5), "pursuit": ref_harness.policy_pursuit,
+           "los_pn": lambda: ref_harness.policy_los_pn(5), "mixed": lambda: ref_harness.policy_mixed(5)}[policy]()
     out = dict(length=np.zeros(n), ret=np.zeros(n), min_distance=np.zeros(n), final_distance=np.zeros(n),
                cause=np.full(n, -1))
     open_ = np.ones(n, bool)
@@ -55,11 +58,12 @@ def play_first_episodes(env_cfg, policy, n=4096, seed=321, max_ticks=2100):
     return out
 
 
-@pytest.mark.parametrize("name", ["stat_cfg4_random", "stat_cfg4_pursuit", "stat_cfg2_pursuit"])
+@pytest.mark.parametrize("name", ["stat_cfg4_random", "stat_cfg4_pursuit", "stat_cfg2_pursuit", "stat_hrl_los_pn",
+                                  "stat_hrl_rotinv_mixed", "stat_volley3_pursuit"])
 def test_episode_outcome_distributions_match_reference(name):
     ref = load_stat(name)
     meta = ref["meta"]
-    got = play_first_episodes(meta["env_cfg"], meta["policy"])
+    got = play_first_episodes(meta["env_cfg"], meta["policy"], training_step_count=meta.get("training_step_count"))
     n_ref = len(ref["length"])
     # termination-cause proportions: within 4 sigma of the binomial error of the 96-episode reference sample
     for c, cname in enumerate(CAUSES):
