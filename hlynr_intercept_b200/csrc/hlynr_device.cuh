@@ -1267,9 +1267,11 @@ HD uint32_t info_flags(int eflags, bool intercepted, bool hit, bool clamped, boo
                       ((eflags & FLAG_CROSSED) ? 32 : 0) | (fuze ? 64 : 0) | ((eflags & FLAG_KF_INIT) ? 128 : 0));
 }
 
-// info['missiles_intercepted'], ['missiles_remaining'], ['missile_min_distances'] (environment.py:846-848)
+// info['missiles_intercepted'], ['missiles_remaining'], ['missile_min_distances'] (environment.py:846-848), written straight
+// to their destinations; out of line (rare: info requests and finished episodes) so the hot body carries no extra registers
 template <typename R>
-HD void volley_info(const KernelArgs<R>& A, int64_t i, const Env<R>& e, const TickOut& t, int* intercepted_n, int* remaining_n, float md[HLYNR_MAX_VOLLEY]) {
+__device__ __noinline__ void volley_info(const KernelArgs<R>& A, int64_t i, int eflags, float distance, bool intercepted,
+                                         int32_t* intercepted_n, int32_t* remaining_n, float* md) {
 #pragma unroll
     for (int m = 0; m < HLYNR_MAX_VOLLEY; ++m) md[m] = 0.f;
     if (A.P.volley_k > 0) {
@@ -1278,45 +1280,47 @@ HD void volley_info(const KernelArgs<R>& A, int64_t i, const Env<R>& e, const Ti
             md[m] = (float)A.st.vm[(int64_t)(2 * m) * A.ring_stride + i].w;
             left += A.st.vm[(int64_t)(2 * m + 1) * A.ring_stride + i].w != R(0) ? 1 : 0;
         }
-        *intercepted_n = FLAG_VCOUNT(e.flags); *remaining_n = left;
+        *intercepted_n = FLAG_VCOUNT(eflags); *remaining_n = left;
     } else {
-        md[0] = t.distance; *intercepted_n = t.intercepted ? 1 : 0; *remaining_n = t.intercepted ? 0 : 1;
+        md[0] = distance; *intercepted_n = intercepted ? 1 : 0; *remaining_n = intercepted ? 0 : 1;
     }
 }
 
-template <typename R> HD void write_info(const KernelArgs<R>& A, int64_t i, const Env<R>& e, const TickOut& t, const ObsOut& ob) {
+// Optional per-env info arrays (HlynrInfoSoA).  Out of line and fed by value: the eager-info path is not the hot one and
+// must not cost the step kernel registers.
+template <typename R>
+__device__ __noinline__ void write_info_slow(const KernelArgs<R>& A, int64_t i, float distance, float min_d, float fuel, float fuel_used,
+                                             int steps, int eflags, uint32_t flags8, bool intercepted, float ix, float iy, float iz,
+                                             float mx, float my, float mz, float ep_ret) {
     const HlynrInfoSoA& f = A.io.info;
-    if (f.distance) f.distance[i] = t.distance;
-    if (f.min_distance) f.min_distance[i] = (float)e.min_d;
-    if (f.fuel_remaining) f.fuel_remaining[i] = (float)e.fuel;
-    if (f.fuel_used) f.fuel_used[i] = (float)e.fuel_used;
-    if (f.steps) f.steps[i] = e.steps;
-    if (f.flags) f.flags[i] = (uint8_t)info_flags(e.flags, t.intercepted, t.hit, t.clamped, ob.onboard_det, ob.ground_det, t.fuze);
-    if (f.interceptor_pos) { f.interceptor_pos[3 * i] = (float)e.ipx; f.interceptor_pos[3 * i + 1] = (float)e.ipy; f.interceptor_pos[3 * i + 2] = (float)e.ipz; }
-    if (f.missile_pos) { f.missile_pos[3 * i] = (float)e.mpx; f.missile_pos[3 * i + 1] = (float)e.mpy; f.missile_pos[3 * i + 2] = (float)e.mpz; }
-    if (f.episode_return) f.episode_return[i] = (float)e.ep_ret;
-    if (f.episode_length) f.episode_length[i] = e.steps;
-    if (f.missiles_intercepted || f.missiles_remaining || f.missile_min_distances) {  // environment.py:844-848
-        int done_n, left_n;
-        float md[HLYNR_MAX_VOLLEY];
-        volley_info(A, i, e, t, &done_n, &left_n, md);
-        if (f.missiles_intercepted) f.missiles_intercepted[i] = done_n;
-        if (f.missiles_remaining) f.missiles_remaining[i] = left_n;
-        if (f.missile_min_distances)
-#pragma unroll
-            for (int m = 0; m < HLYNR_MAX_VOLLEY; ++m) f.missile_min_distances[(int64_t)HLYNR_MAX_VOLLEY * i + m] = md[m];
-    }
+    if (f.distance) f.distance[i] = distance;
+    if (f.min_distance) f.min_distance[i] = min_d;
+    if (f.fuel_remaining) f.fuel_remaining[i] = fuel;
+    if (f.fuel_used) f.fuel_used[i] = fuel_used;
+    if (f.steps) f.steps[i] = steps;
+    if (f.flags) f.flags[i] = (uint8_t)flags8;
+    if (f.interceptor_pos) { f.interceptor_pos[3 * i] = ix; f.interceptor_pos[3 * i + 1] = iy; f.interceptor_pos[3 * i + 2] = iz; }
+    if (f.missile_pos) { f.missile_pos[3 * i] = mx; f.missile_pos[3 * i + 1] = my; f.missile_pos[3 * i + 2] = mz; }
+    if (f.episode_return) f.episode_return[i] = ep_ret;
+    if (f.episode_length) f.episode_length[i] = steps;
+    if (f.missiles_intercepted && f.missiles_remaining && f.missile_min_distances)  // environment.py:844-848 (all three or none)
+        volley_info(A, i, eflags, distance, intercepted, f.missiles_intercepted + i, f.missiles_remaining + i,
+                    f.missile_min_distances + (int64_t)HLYNR_MAX_VOLLEY * i);
+}
+template <typename R> HD void write_info(const KernelArgs<R>& A, int64_t i, const Env<R>& e, const TickOut& t, const ObsOut& ob) {
+    write_info_slow(A, i, t.distance, (float)e.min_d, (float)e.fuel, (float)e.fuel_used, e.steps, e.flags,
+                    info_flags(e.flags, t.intercepted, t.hit, t.clamped, ob.onboard_det, ob.ground_det, t.fuze), t.intercepted,
+                    (float)e.ipx, (float)e.ipy, (float)e.ipz, (float)e.mpx, (float)e.mpy, (float)e.mpz, (float)e.ep_ret);
 }
 
 // Appends the finished episode of env i to the compact done list (rare: ~1 per 1000 ticks per env).  Out of line
 // and fed by value so the env state never has its address taken.
-__device__ __noinline__ void append_done_record(HlynrDoneRecord* recs, int32_t* counter, int32_t cap, int32_t env, int32_t steps,
+__device__ __noinline__ int32_t append_done_record(HlynrDoneRecord* recs, int32_t* counter, int32_t cap, int32_t env, int32_t steps,
                                                 uint32_t flags, float distance, float min_d, float fuel, float fuel_used,
                                                 float ep_ret, float ix, float iy, float iz, float mx, float my, float mz,
-                                                const float* obs_row, int missiles_intercepted, int missiles_remaining,
-                                                const float* min_distances) {
+                                                const float* obs_row) {
     const int32_t slot = atomicAdd(counter, 1);
-    if (slot >= cap) return;
+    if (slot >= cap) return -1;
     HlynrDoneRecord* r = recs + slot;
     r->env = env; r->steps = steps; r->flags = flags;
     r->distance = distance; r->min_distance = min_d; r->fuel_remaining = fuel; r->fuel_used = fuel_used; r->episode_return = ep_ret;
@@ -1324,9 +1328,7 @@ __device__ __noinline__ void append_done_record(HlynrDoneRecord* recs, int32_t* 
     r->missile_pos[0] = mx; r->missile_pos[1] = my; r->missile_pos[2] = mz;
 #pragma unroll
     for (int k = 0; k < HLYNR_OBS_DIM; ++k) r->terminal_obs[k] = obs_row[k];
-    r->missiles_intercepted = missiles_intercepted; r->missiles_remaining = missiles_remaining;
-#pragma unroll
-    for (int m = 0; m < HLYNR_MAX_VOLLEY; ++m) r->missile_min_distances[m] = min_distances[m];
+    return slot;
 }
 template <typename R> HD RngKey make_key(const KernelArgs<R>& A, int64_t global_env) {
     RngKey k;
@@ -1441,14 +1443,16 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, (F == FT_V2OFF && sizeof(R) == 4)
                 rsum += t.reward;
                 account_episodes(A, active, done, e, t);
                 if (!kRollout && done && active && A.io.done_records) {
-                    int vi_n, vr_n;
-                    float vmd[HLYNR_MAX_VOLLEY];
-                    volley_info(A, i, e, t, &vi_n, &vr_n, vmd);
-                    append_done_record(A.io.done_records, A.io.done_counter, A.io.done_cap, (int32_t)i, e.steps,
+                    const int32_t slot = append_done_record(A.io.done_records, A.io.done_counter, A.io.done_cap, (int32_t)i, e.steps,
                                        info_flags(e.flags, t.intercepted, t.hit, t.clamped, ob.onboard_det, ob.ground_det, t.fuze) |
                                            (t.terminated ? HLYNR_DONE_TERMINATED : 0u) | (t.truncated ? HLYNR_DONE_TRUNCATED : 0u),
                                        t.distance, (float)e.min_d, (float)e.fuel, (float)e.fuel_used, (float)e.ep_ret, (float)e.ipx,
-                                       (float)e.ipy, (float)e.ipz, (float)e.mpx, (float)e.mpy, (float)e.mpz, ob.row, vi_n, vr_n, vmd);
+                                       (float)e.ipy, (float)e.ipz, (float)e.mpx, (float)e.mpy, (float)e.mpz, ob.row);
+                    if (slot >= 0) {
+                        HlynrDoneRecord* r = A.io.done_records + slot;
+                        volley_info(A, i, e.flags, t.distance, t.intercepted, &r->missiles_intercepted, &r->missiles_remaining,
+                                    r->missile_min_distances);
+                    }
                 }
                 need_reset = done && A.auto_reset;
                 if (need_reset) {
