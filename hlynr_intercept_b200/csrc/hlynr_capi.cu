@@ -148,6 +148,7 @@ struct hlynr_sim {
     HostIO hio;
     int host_info = 1, host_chunks = 0, host_threads = 0;
     int prefetch_waves = 1;  // CTAs per SM the step kernel looks ahead when it prefetches upcoming planes into L2 (0 = off)
+    unsigned int* pipe_counters = nullptr;    // tile queue of the persistent-warp kernel (variant 3)
     HlynrDoneRecord* done_records = nullptr;  // attached compact done list (hlynr_set_done_list)
     int32_t* done_counter = nullptr;
     int32_t done_cap = 0;
@@ -438,7 +439,7 @@ size_t hlynr_env_state_size(void) { return sizeof(HlynrEnvState); }
 void hlynr_destroy(hlynr_t* s) {
     if (!s) return;
     DeviceGuard g(s->device);
-    cudaFree(s->state_mem); cudaFree(s->stats); cudaFree(s->xchg);
+    cudaFree(s->state_mem); cudaFree(s->stats); cudaFree(s->xchg); cudaFree(s->pipe_counters);
     HostIO& h = s->hio;
     delete h.pool;
     cudaFreeHost(h.h_actions); cudaFreeHost(h.h_obs); cudaFreeHost(h.h_reward); cudaFreeHost(h.h_records); cudaFreeHost(h.h_count);
@@ -491,6 +492,7 @@ int hlynr_create(const HlynrParams* p, int64_t n_envs, int device, uint64_t seed
     if (e != cudaSuccess) { int r = fail("hlynr_create: cudaMalloc(stats) failed: %s", cudaGetErrorString(e)); cudaFree(s->state_mem); delete s; return r; }
     cudaMemset(s->state_mem, 0, s->state_bytes);
     cudaMemset(s->stats, 0, sizeof(double) * (HLYNR_STAT_SLOTS + 1) * HLYNR_STATS_WORDS);
+    if (cudaMalloc(&s->pipe_counters, 2 * sizeof(unsigned int)) == cudaSuccess) cudaMemset(s->pipe_counters, 0, 2 * sizeof(unsigned int));
     cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     const int blk = 256;
@@ -516,7 +518,7 @@ static int make_pool(hlynr_sim* s);
 int hlynr_set_option(hlynr_t* s, const char* name, int64_t value) {
     if (!s || !name) return fail("null argument");
     if (strcmp(name, "step_kernel_variant") == 0) {
-        if (value < 0 || value > 2) return fail("step_kernel_variant must be 0 (auto), 1 (direct) or 2 (tma)");
+        if (value < 0 || value > 3) return fail("step_kernel_variant must be 0 (auto), 1 (direct), 2 (tma) or 3 (persistent warps + cp.async)");
         s->kernel_variant = (int)value;
         return 0;
     }
@@ -602,6 +604,14 @@ static int step_range(hlynr_sim* s, int64_t first, int64_t lim, const float* act
             const int64_t max_ctas = (int64_t)s->sm_count * 4;
             const int grid = (int)(n_tiles < max_ctas ? n_tiles : max_ctas);
             step_kernel_tma<<<grid, HLYNR_BLOCK, smem, st>>>(A, T);
+        } else if (s->kernel_variant == 3 && whole && s->specialise && feature_set(s->params) >= 0 && s->pipe_counters) {
+            // persistent warps with per-thread cp.async staging (specialised feature sets, whole shard, one launch at a time)
+            const int f = feature_set(s->params);
+            const int grid = s->sm_count * 4;
+            const size_t smem = sizeof(PipeSmem);
+            if (f == FT_V2ON) step_kernel_pipe<FT_V2ON><<<grid, HLYNR_BLOCK, smem, st>>>(A, s->pipe_counters);
+            else if (f == FT_V2OFF) step_kernel_pipe<FT_V2OFF><<<grid, HLYNR_BLOCK, smem, st>>>(A, s->pipe_counters);
+            else step_kernel_pipe<FT_V2ON_DR><<<grid, HLYNR_BLOCK, smem, st>>>(A, s->pipe_counters);
         } else {
             launch_step_f32<false>(s, A, st, s->specialise != 0);
         }

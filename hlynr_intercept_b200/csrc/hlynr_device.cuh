@@ -1658,6 +1658,177 @@ step_kernel_tma(const __grid_constant__ KernelArgs<float> A, const __grid_consta
     if (lane == 0 && wl) atomicAdd(A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS + 13, (double)wl);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent-warp step kernel with per-thread cp.async staging (fp32 build, API mode, specialised feature sets).
+//
+// The direct kernel's warps wait for their up-front plane loads with nothing else to do; here a warp owns a private
+// shared-memory slot per lane per plane, fetches warp-sized tiles (32 envs) dynamically off an atomic counter, and as
+// soon as it has moved tile t from the slots into registers it issues the cp.async copies of tile t+1 into the SAME
+// slots -- each lane only ever touches its own 16-byte slots, so there is no barrier of any kind -- and they land while
+// tile t computes.  The ring samples a tick reads and the tile's actions are staged the same way.
+// ------------------------------------------------------------------------------------------------
+#define PIPE_PLANES 15   // r0..r6, f0..f3, i0, onboard ring slot, ground ring slot (2 planes)
+#define PIPE_WARPS (HLYNR_BLOCK / 32)
+struct PipeSmem {
+    float4 plane[PIPE_WARPS][PIPE_PLANES][32];  // [warp][plane][lane]: conflict-free LDS.128
+    float2 act[PIPE_WARPS][3][32];              // the lane's 6 action floats as 3 x 8 bytes
+    float tiles[PIPE_WARPS][OBS_TILE];
+};
+HD void cp_async16(void* smem, const void* g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(g) : "memory"); }
+HD void cp_async8(void* smem, const void* g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(g) : "memory"); }
+HD void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+HD void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int F>
+HD void pipe_issue(const KernelArgs<float>& A, PipeSmem* sm, unsigned warp, unsigned lane, int64_t ii, int64_t ring_i) {
+    typedef Feat<F> FT;
+    const StatePlanes<float>& s = A.st;
+    float4(*pl)[32] = sm->plane[warp];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cp_async16(&pl[k][lane], s.r[k] + ii);
+    if (FT::thrust_dyn(A.P) || FT::dr(A.P)) cp_async16(&pl[6][lane], s.r[6] + ii);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cp_async16(&pl[7 + k][lane], s.f[k] + ii);
+    if (FT::dr(A.P)) cp_async16(&pl[10][lane], s.f[3] + ii);
+    cp_async16(&pl[11][lane], s.i0 + ii);
+    const int64_t n = A.ring_stride;
+    if (FT::onboard_delay(A.P) && !FT::dr(A.P)) {
+        int rrow = A.o_row - A.P.onboard_delay;
+        if (rrow < 0) rrow += A.P.onb_ring_len;
+        cp_async16(&pl[12][lane], s.oring + (int64_t)rrow * n + ring_i);
+    }
+    if (FT::ground(A.P) && FT::ground_delay(A.P)) {
+        const int rrow = A.g_row + 1 == A.P.gnd_ring_len ? 0 : A.g_row + 1;
+        const Vec4<float>* rr = s.gring + (int64_t)rrow * 2 * n;
+        cp_async16(&pl[13][lane], rr + ring_i);
+        cp_async16(&pl[14][lane], rr + n + ring_i);
+    }
+    const float2* ap = reinterpret_cast<const float2*>(A.io.actions + ii * HLYNR_ACT_DIM);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cp_async8(&sm->act[warp][k][lane], ap + k);
+    cp_async_commit();
+}
+
+// counters[0] = next warp-tile to hand out, counters[1] = warps that have drained the queue (the last one resets both)
+template <int F>
+__global__ void __launch_bounds__(HLYNR_BLOCK, 4) step_kernel_pipe(const __grid_constant__ KernelArgs<float> A, unsigned int* counters) {
+    typedef float R;
+    typedef Feat<F> FT;
+    extern __shared__ __align__(16) unsigned char pipe_smem_raw[];
+    PipeSmem* sm = reinterpret_cast<PipeSmem*>(pipe_smem_raw);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int64_t n_tiles = (A.lim - A.first + 31) / 32;
+    auto grab = [&]() -> int64_t {
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(&counters[0], 1u);
+        return (int64_t)__shfl_sync(0xffffffffu, t, 0);
+    };
+    int locks = 0;
+    int64_t tile = grab();
+    if (tile < n_tiles) {
+        const int64_t i0 = A.first + tile * 32 + lane;
+        pipe_issue<F>(A, sm, warp, lane, i0 < A.lim ? i0 : A.lim - 1, i0);
+    }
+#pragma unroll 1
+    while (tile < n_tiles) {
+        const int64_t i = A.first + tile * 32 + lane;
+        const int64_t warp_first = i - lane;
+        const bool active = i < A.lim;
+        const int64_t ii = active ? i : A.lim - 1;
+        const int64_t next = grab();   // its latency hides behind the wait below
+        cp_async_wait_all();
+        // ---- slots -> registers ----
+        Env<R> e;
+        float act[6];
+        RingPre<R> pre;
+        {
+            float4(*pl)[32] = sm->plane[warp];
+            float4 v;
+            v = pl[0][lane]; e.ipx = v.x; e.ipy = v.y; e.ipz = v.z; e.fuel = v.w;
+            v = pl[1][lane]; e.ivx = v.x; e.ivy = v.y; e.ivz = v.z; e.fuel_used = v.w;
+            v = pl[2][lane]; e.mpx = v.x; e.mpy = v.y; e.mpz = v.z; e.prev_d = v.w;
+            v = pl[3][lane]; e.mvx = v.x; e.mvy = v.y; e.mvz = v.z; e.last_d = v.w;
+            v = pl[4][lane]; e.kpx = v.x; e.kpy = v.y; e.kpz = v.z; e.min_d = v.w;
+            v = pl[5][lane]; e.kvx = v.x; e.kvy = v.y; e.kvz = v.z; e.ep_ret = v.w;
+            if (FT::thrust_dyn(A.P) || FT::dr(A.P)) { v = pl[6][lane]; e.thx = v.x; e.thy = v.y; e.thz = v.z; e.T0 = v.w; }
+            else { e.thx = e.thy = e.thz = 0.f; e.T0 = 288.15f; }
+            v = pl[7][lane]; e.qw = v.x; e.qx = v.y; e.qy = v.z; e.qz = v.w;
+            v = pl[8][lane]; e.wx = v.x; e.wy = v.y; e.wz = v.z; e.Ppp = v.w;
+            v = pl[9][lane]; e.Ppv = v.x; e.Pvp = v.y; e.Pvv = v.z; e.base_cd = v.w;
+            if (FT::dr(A.P)) e.peak = pl[10][lane].x; else e.peak = 0.f;
+            const int4 q = *reinterpret_cast<const int4*>(&pl[11][lane]);
+            e.steps = q.x; e.worsen = q.y; e.flags = q.z; e.episode = q.w;
+            pre.o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (FT::onboard_delay(A.P) && !FT::dr(A.P)) pre.o = pl[12][lane];
+            pre.ga = Vec4<R>{0.f, 0.f, 0.f, 0.f}; pre.gb = pre.ga;
+            if (FT::ground(A.P) && FT::ground_delay(A.P)) {
+                const float4 a = pl[13][lane], b = pl[14][lane];
+                pre.ga = Vec4<R>{a.x, a.y, a.z, a.w}; pre.gb = Vec4<R>{b.x, b.y, b.z, b.w};
+            }
+            const float2 p0 = sm->act[warp][0][lane], p1 = sm->act[warp][1][lane], p2 = sm->act[warp][2][lane];
+            act[0] = p0.x; act[1] = p0.y; act[2] = p1.x; act[3] = p1.y; act[4] = p2.x; act[5] = p2.y;
+        }
+        if (next < n_tiles) {   // the slots are free again: stage the next tile while this one computes
+            const int64_t j = A.first + next * 32 + lane;
+            pipe_issue<F>(A, sm, warp, lane, j < A.lim ? j : A.lim - 1, j);
+        }
+        // ---- one tick + SB3 auto-reset (same device functions as the direct kernel) ----
+        const RngKey key = make_key(A, A.env_offset + ii);
+        TickOut t;
+        tick_physics<R, F>(A, e, key, act, i, t);
+        ObsOut ob;
+        ob.row = sm->tiles[warp] + lane * HLYNR_OBS_DIM;
+        ob.emit = true;
+        uint4 ur = t.ur;
+        bool need_reset = false;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) {
+                if (!need_reset) break;
+                e.episode += 1;
+                spawn(A, e, key, i);
+                ur = draw_raw(key, (uint32_t)e.episode, 0u, HLYNR_BLK_UNI);
+            }
+            observe<R, F, true>(A, e, key, ur, i, A.g_row, A.o_row, pre, ob);   // pass 1: steps == 0 < delay, `pre` is not read
+            if (pass == 0) {
+                const bool done = t.terminated || t.truncated;
+                if (active && ob.onboard_det) locks += 1;
+                if (active) {
+                    A.io.reward[i] = t.reward;
+                    A.io.terminated[i] = t.terminated ? 1 : 0;
+                    A.io.truncated[i] = t.truncated ? 1 : 0;
+                    if (A.has_info) write_info(A, i, e, t, ob);
+                }
+                account_episodes(A, active, done, e, t);
+                if (done && active && A.io.done_records) {
+                    const int32_t slot = append_done_record(A.io.done_records, A.io.done_counter, A.io.done_cap, (int32_t)i, e.steps,
+                                           info_flags(e.flags, t.intercepted, t.hit, t.clamped, ob.onboard_det, ob.ground_det, t.fuze) |
+                                               (t.terminated ? HLYNR_DONE_TERMINATED : 0u) | (t.truncated ? HLYNR_DONE_TRUNCATED : 0u),
+                                           t.distance, (float)e.min_d, (float)e.fuel, (float)e.fuel_used, (float)e.ep_ret, (float)e.ipx,
+                                           (float)e.ipy, (float)e.ipz, (float)e.mpx, (float)e.mpy, (float)e.mpz, ob.row);
+                    if (slot >= 0) {
+                        HlynrDoneRecord* r = A.io.done_records + slot;
+                        volley_info(A, i, e.flags, t.distance, t.intercepted, &r->missiles_intercepted, &r->missiles_remaining,
+                                    r->missile_min_distances);
+                    }
+                }
+                need_reset = done && A.auto_reset;
+                if (need_reset && active && A.io.terminal_obs) copy_obs_row(ob.row, A.io.terminal_obs + i * HLYNR_OBS_DIM);
+            }
+        }
+        if (A.io.obs) flush_obs_tile(sm->tiles[warp], A.io.obs, warp_first, A.lim, lane);
+        if (active) store_env<R, F>(A, i, e);
+        tile = next;
+    }
+    const int wl = __reduce_add_sync(0xffffffffu, locks);
+    if (lane == 0) {
+        if (wl) atomicAdd(A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS + 13, (double)wl);
+        // every warp of the grid passes here exactly once; the last one re-arms the queue for the next launch
+        const unsigned int total = gridDim.x * PIPE_WARPS;
+        if (atomicAdd(&counters[1], 1u) + 1u == total) { counters[0] = 0u; counters[1] = 0u; }
+    }
+}
+
 // reset(): environment.py:353.  mask == NULL resets every env.
 template <typename R> __global__ void __launch_bounds__(HLYNR_BLOCK) reset_kernel(const __grid_constant__ KernelArgs<R> A) {
     __shared__ __align__(16) float tiles[HLYNR_BLOCK / 32][OBS_TILE];

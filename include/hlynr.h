@@ -305,7 +305,8 @@ int hlynr_debug_draws(hlynr_t* sim, int64_t env_global_id, uint32_t episode, uin
                       uint32_t block, uint32_t raw_out[4], float uniform_out[4], float normal_out[4]);
 
 /* Tuning options.  "step_kernel_variant": 0 = auto, 1 = direct kernel (one CTA per 128 envs, plane loads from
- * registers), 2 = persistent kernel whose CTAs prefetch the next tile's planes with TMA bulk copies.
+ * registers), 2 = persistent kernel whose CTAs prefetch the next tile's planes with TMA bulk copies, 3 = persistent warps
+ * that stage the next 32-env tile with per-thread cp.async while the current one computes (specialised feature sets only).
  * "specialise": 1 (default) = use the compile-time feature-specialised step kernels when the configuration matches
  * one (medium scenario with physics v2.0 all on / all off), 0 = always the generic kernel.
  * "host_info": 1 (default) = hlynr_step_host also fills the [N]-sized info arrays read by hlynr_info_host, 0 = skip them

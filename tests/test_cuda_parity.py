@@ -34,18 +34,20 @@ def test_philox_on_device_matches_contract():
 
 
 TRAJ_CASES = [c for c in GOLDEN_CASES if not c.startswith("stat_")]
-DIRECT, TMA = 1, 2  # step_kernel_variant
+DIRECT, TMA, PIPE = 1, 2, 3  # step_kernel_variant (3 = persistent warps + cp.async; falls back to 1 for unspecialised configs)
 
 
-@pytest.mark.parametrize("variant", [DIRECT, TMA])
+@pytest.mark.parametrize("variant", [DIRECT, TMA, PIPE])
 @pytest.mark.parametrize("name", TRAJ_CASES)
 def test_cuda_matches_reference_golden(name, variant):
     g = load_golden(name)
     meta = g["meta"]
     P, cur = golden_setup(g)
     f64 = meta["float64"]
-    if f64 and variant == TMA:
-        pytest.skip("the TMA-prefetched kernel is the fp32 build's")
+    if f64 and variant != DIRECT:
+        pytest.skip("the TMA-prefetched and persistent-warp kernels are the fp32 build's")
+    if variant == PIPE and not (name.startswith("cfg2") or name.startswith("cfg3") or name.startswith("cfg4")):
+        pytest.skip("no specialised feature set: variant 3 falls back to the direct kernel")
     cuda = CudaBatch(P, cur, meta["n_envs"], seed=meta["seed"], float64=f64, variant=variant)
     shadow = oracle.OracleBatch(P, cur, meta["n_envs"], seed=meta["seed"], float64=f64)
     sim = Lockstep(cuda, shadow)
@@ -55,7 +57,7 @@ def test_cuda_matches_reference_golden(name, variant):
 
 
 @pytest.mark.parametrize("base", ["cfg2", "cfg3", "cfg4"])
-@pytest.mark.parametrize("f64,variant", [(False, DIRECT), (False, TMA), (True, DIRECT)])
+@pytest.mark.parametrize("f64,variant", [(False, DIRECT), (False, TMA), (False, PIPE), (True, DIRECT)])
 def test_cuda_matches_oracle_4096_envs_100_steps(base, f64, variant):
     """BASELINE cfg2 size (4096 envs, here 4100 to exercise a partial tile): CUDA vs oracle, 1-step and 100-step horizon."""
     n, T, seed = 4100, 100, 4242
@@ -111,7 +113,7 @@ def test_sharding_invariance_and_rollout_equivalence():
     n, seed, K = 512, 77, 40
     full = CudaBatch(P, cur, n, seed=seed, variant=TMA)      # the two step-kernel variants must agree bit for bit
     lo = CudaBatch(P, cur, n // 2, seed=seed, env_id_offset=0, variant=DIRECT)
-    hi = CudaBatch(P, cur, n // 2, seed=seed, env_id_offset=n // 2)
+    hi = CudaBatch(P, cur, n // 2, seed=seed, env_id_offset=n // 2, variant=PIPE)
     fused = CudaBatch(P, cur, n, seed=seed)
     o_full = full.reset()
     assert (np.concatenate([lo.reset(), hi.reset()]) == o_full).all()

@@ -1,4 +1,4 @@
-import sys, time; sys.path.insert(0, '.')
+import sys, time; sys.path.insert(0, '.'); sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import torch, numpy as np
 from hlynr_intercept_b200 import config
 from hlynr_intercept_b200.sim import HlynrSim

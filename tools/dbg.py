@@ -1,4 +1,4 @@
-import sys; sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+import sys; sys.path.insert(0, '.'); sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))); sys.path.insert(0, 'tests')
 import numpy as np
 from common import CudaBatch, golden_setup, load_golden
 g = load_golden("volley3_cfg4_f32_zem")

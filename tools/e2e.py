@@ -1,6 +1,6 @@
 """e2e sweep of hlynr_step_host: chunks x threads at 2^20 envs (scratch script for gpurun)."""
 import sys, time
-sys.path.insert(0, '.')
+sys.path.insert(0, '.'); sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import numpy as np, torch
 from hlynr_intercept_b200 import config
 from hlynr_intercept_b200.vec_env import HlynrVecEnv

@@ -1,6 +1,6 @@
 """Throughput of step + on-device frame-stack/normalise at 2^20 envs (scratch script for gpurun)."""
 import sys
-sys.path.insert(0, '.')
+sys.path.insert(0, '.'); sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import torch
 from hlynr_intercept_b200 import config
 from hlynr_intercept_b200.sim import HlynrSim

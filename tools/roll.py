@@ -1,5 +1,5 @@
 """Rollout collection eager vs CUDA graph at several batch sizes (scratch script for gpurun)."""
-import sys; sys.path.insert(0, '.')
+import sys; sys.path.insert(0, '.'); sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import torch
 from hlynr_intercept_b200 import config
 from hlynr_intercept_b200.sim import HlynrSim
