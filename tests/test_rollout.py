@@ -151,3 +151,36 @@ def test_graph_replay_equals_eager_collect():
     assert eager.sim.stats()["env_steps"] == graphed.sim.stats()["env_steps"] == 4 * T * n
     with pytest.raises(ValueError):
         DeviceRolloutCollector(graphed.pipe, Pol(), n_steps=T + 1).capture()
+
+
+@pytest.mark.gpu
+def test_episode_recorder_writes_the_reference_logger_format(tmp_path):
+    import json
+
+    import torch
+
+    from hlynr_intercept_b200.episode_log import EpisodeRecorder
+    from hlynr_intercept_b200.sim import HlynrSim
+
+    cfg = config.baseline_config("cfg4")
+    cfg["max_steps"] = 60
+    sim = HlynrSim(cfg, n_envs=64, seed=2, warn_dead=False)
+    sim.reset()
+    rec = EpisodeRecorder(sim, str(tmp_path), env_index=5, metadata={"scenario": "medium"})
+    rng = np.random.default_rng(0)
+    done = False
+    for t in range(80):
+        a = rng.uniform(-1, 1, (64, 6)).astype(np.float32)
+        obs, rew, te, tr, _, info = sim.step(torch.as_tensor(a).cuda(), auto_reset=False, want_info=True)
+        done = rec.record_tick(a[5], float(rew[5]), bool(te[5]), bool(tr[5]), float(info["distance"][5]), bool(info["flags"][5] & 1))
+        if done:
+            break
+    assert done
+    lines = [json.loads(x) for x in open(tmp_path / "episodes" / "ep_000001.jsonl")]
+    assert lines[0]["type"] == "header" and lines[0]["metadata"] == {"scenario": "medium"}
+    states = [x for x in lines if x["type"] == "state"]
+    assert len(states) == 2 * 60 and {x["entity_id"] for x in states} == {"interceptor", "missile"}
+    assert len(states[0]["state"]["position"]) == 3 and len(states[0]["state"]["action"]) == 6
+    foot = lines[-1]
+    assert foot["type"] == "footer" and foot["outcome"] in ("intercepted", "failed") and foot["metrics"]["steps"] == 60
+    sim.close()
