@@ -6,7 +6,8 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libhlynr_b200.so")
+# HLYNR_B200_LIB points the loader at another build of the SAME library (kernel experiments, tools/); there is no other backend
+SO_PATH = os.environ.get("HLYNR_B200_LIB") or os.path.join(_HERE, "libhlynr_b200.so")
 _LIB = None
 
 # every symbol include/hlynr.h declares
@@ -35,7 +36,7 @@ def load(build_if_missing=True):
     global _LIB
     if _LIB is not None:
         return _LIB
-    if build_if_missing:
+    if build_if_missing and "HLYNR_B200_LIB" not in os.environ:
         from . import build as _build
 
         try:

@@ -371,14 +371,14 @@ static int feature_set(const HlynrParams& p) {
     return (f == FT_V2ON || f == FT_V2OFF || f == FT_V2ON_DR) ? f : FT_GENERIC;
 }
 template <bool kRollout> static void launch_step_f32(const hlynr_sim* s, const KernelArgs<float>& A, cudaStream_t st, bool specialise) {
-    const int grid = grid_for(A.lim - A.first, HLYNR_BLOCK);
+    const int grid = grid_for(A.lim - A.first, HLYNR_STEP_BLOCK);
     int f = feature_set(s->params);
     if (!specialise && f >= 0) f = FT_GENERIC;
-    if (f == FT_V2ON) step_kernel<float, kRollout, FT_V2ON><<<grid, HLYNR_BLOCK, 0, st>>>(A);
-    else if (f == FT_V2OFF) step_kernel<float, kRollout, FT_V2OFF><<<grid, HLYNR_BLOCK, 0, st>>>(A);
-    else if (f == FT_V2ON_DR) step_kernel<float, kRollout, FT_V2ON_DR><<<grid, HLYNR_BLOCK, 0, st>>>(A);
-    else if (f == FT_GENERIC_MODES) step_kernel<float, kRollout, FT_GENERIC_MODES><<<grid, HLYNR_BLOCK, 0, st>>>(A);
-    else step_kernel<float, kRollout, FT_GENERIC><<<grid, HLYNR_BLOCK, 0, st>>>(A);
+    if (f == FT_V2ON) step_kernel<float, kRollout, FT_V2ON><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
+    else if (f == FT_V2OFF) step_kernel<float, kRollout, FT_V2OFF><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
+    else if (f == FT_V2ON_DR) step_kernel<float, kRollout, FT_V2ON_DR><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
+    else if (f == FT_GENERIC_MODES) step_kernel<float, kRollout, FT_GENERIC_MODES><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
+    else step_kernel<float, kRollout, FT_GENERIC><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -622,9 +622,9 @@ static int step_range(hlynr_sim* s, int64_t first, int64_t lim, const float* act
         A.io.truncated = truncated_dev; A.io.terminal_obs = terminal_obs_dev; A.auto_reset = auto_reset;
         if (info) { A.io.info = *info; A.has_info = 1; }
         if (s->params.obs_mode != HLYNR_OBS_WORLD || s->params.volley_size > 0)
-            step_kernel<double, false, FT_GENERIC_MODES><<<grid_for(lim - first, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+            step_kernel<double, false, FT_GENERIC_MODES><<<grid_for(lim - first, HLYNR_STEP_BLOCK), HLYNR_STEP_BLOCK, 0, st>>>(A);
         else
-            step_kernel<double, false, FT_GENERIC><<<grid_for(lim - first, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+            step_kernel<double, false, FT_GENERIC><<<grid_for(lim - first, HLYNR_STEP_BLOCK), HLYNR_STEP_BLOCK, 0, st>>>(A);
     }
     CK(cudaGetLastError());
     s->launches += 1;
@@ -669,9 +669,9 @@ int hlynr_rollout(hlynr_t* s, int k_steps, const float* actions_dev, float* obs_
         A.o_row = A.P.onb_ring_len > 0 ? (int32_t)(A.tick % (uint32_t)A.P.onb_ring_len) : 0;
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward_sum = reward_sum_dev; A.io.done_count = done_count_dev;
         if (s->params.obs_mode != HLYNR_OBS_WORLD || s->params.volley_size > 0)
-            step_kernel<double, true, FT_GENERIC_MODES><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+            step_kernel<double, true, FT_GENERIC_MODES><<<grid_for(s->n, HLYNR_STEP_BLOCK), HLYNR_STEP_BLOCK, 0, st>>>(A);
         else
-            step_kernel<double, true, FT_GENERIC><<<grid_for(s->n, HLYNR_BLOCK), HLYNR_BLOCK, 0, st>>>(A);
+            step_kernel<double, true, FT_GENERIC><<<grid_for(s->n, HLYNR_STEP_BLOCK), HLYNR_STEP_BLOCK, 0, st>>>(A);
     }
     CK(cudaGetLastError());
     s->tick += (uint32_t)k_steps;

@@ -1339,6 +1339,11 @@ template <typename R> HD RngKey make_key(const KernelArgs<R>& A, int64_t global_
 }
 
 #define HLYNR_BLOCK 128
+// CTA size of the direct step kernel (a multiple of 32 that divides HLYNR_BLOCK).  Nothing in that kernel is CTA-wide (warp-private
+// observation tiles, no barrier), so the CTA is only the unit in which SM slots are handed back.
+#ifndef HLYNR_STEP_BLOCK
+#define HLYNR_STEP_BLOCK 128
+#endif
 
 // The delay-ring samples a tick reads (one onboard slot, two ground planes) are needed only deep inside observe(),
 // ~1000 instructions after the kernel starts; without help their DRAM latency is fully exposed there (9 % + 3 % of all
@@ -1384,10 +1389,11 @@ template <typename R, int F> HD void prefetch_ring_reads(const KernelArgs<R>& A,
 // ------------------------------------------------------------------------------------------------
 // step(): one tick of every env + SB3 auto-reset.  kRollout: k fused ticks, state stays in registers.
 template <typename R, bool kRollout, int F>
-__global__ void __launch_bounds__(HLYNR_BLOCK, (F == FT_V2OFF && sizeof(R) == 4) ? 5 : 4) step_kernel(const __grid_constant__ KernelArgs<R> A) {
-    __shared__ __align__(16) float tiles[HLYNR_BLOCK / 32][OBS_TILE];
+__global__ void __launch_bounds__(HLYNR_STEP_BLOCK, ((F == FT_V2OFF && sizeof(R) == 4) ? 5 : 4) * (HLYNR_BLOCK / HLYNR_STEP_BLOCK))
+step_kernel(const __grid_constant__ KernelArgs<R> A) {
+    __shared__ __align__(16) float tiles[HLYNR_STEP_BLOCK / 32][OBS_TILE];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const int64_t i = A.first + (int64_t)blockIdx.x * HLYNR_BLOCK + threadIdx.x;
+    const int64_t i = A.first + (int64_t)blockIdx.x * HLYNR_STEP_BLOCK + threadIdx.x;
     const int64_t warp_first = i - lane;
     const bool active = i < A.lim;
     const int64_t ii = active ? i : A.lim - 1;  // inactive lanes shadow the last env and never store

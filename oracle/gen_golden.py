@@ -63,8 +63,9 @@ def reference_yaml_env(rel_path):
     path = os.path.join(rh.REFERENCE_ROOT, "rl_system", rel_path)
     with open(path) as f:
         cfg = yaml.safe_load(f)
-    if "parent_config" in cfg:
-        with open(os.path.normpath(os.path.join(os.path.dirname(path), cfg["parent_config"]))) as f:
+    parent = os.path.normpath(os.path.join(os.path.dirname(path), cfg["parent_config"])) if "parent_config" in cfg else None
+    if parent and os.path.exists(parent):   # a missing parent is skipped silently (:282; configs/hrl/eval_100m.yaml)
+        with open(parent) as f:
             merged = yaml.safe_load(f)
         for key, val in cfg.items():
             if key == "parent_config":
@@ -103,10 +104,35 @@ CASES.update({
 })
 
 
+# One short fixture per remaining reference YAML (every file under rl_system/configs plus config.yaml that has no case
+# above), so that each configuration a reference user can pass is pinned: 2 envs, 1300 ticks (past the first
+# terminations), true-state guidance in the frame the config's action space uses.  Left out because their merged env dict is
+# identical to a listed one: hrl_base / selector_config / track_specialist (= config.yaml), terminal_specialist
+# (= search_specialist), terminal_precision_v3 (= terminal_precision_v2).
+YAML_SWEEP = [
+    "config.yaml", "configs/eval_360_los_no_fuze.yaml", "configs/eval_360_proximity.yaml", "configs/eval_360_rotinv.yaml",
+    "configs/eval_precision.yaml", "configs/eval_proximity_fuze.yaml", "configs/eval_terminal_standalone.yaml",
+    "configs/hrl/eval_100m.yaml", "configs/hrl/hrl_curriculum.yaml",
+    "configs/hrl/search_specialist.yaml", "configs/hrl/selector_los.yaml",
+    "configs/hrl/terminal_2octant_rotinv.yaml", "configs/hrl/terminal_360_fresh.yaml", "configs/hrl/terminal_finetune.yaml",
+    "configs/hrl/terminal_longrange_v1.yaml", "configs/hrl/terminal_precision.yaml", "configs/hrl/terminal_precision_v2.yaml",
+    "configs/hrl/terminal_precision_v4.yaml", "configs/hrl/terminal_precision_v5.yaml",
+    "configs/hrl/terminal_precision_v6.yaml", "configs/hrl/terminal_tight_30m.yaml",
+    "configs/hrl/terminal_tight_50m.yaml", "configs/hrl/track_los.yaml",
+    "configs/scenarios/easy.yaml", "configs/scenarios/medium.yaml", "configs/scenarios/hard.yaml",
+]
+for _rel in YAML_SWEEP:
+    _stem = os.path.splitext(os.path.basename(_rel))[0]
+    _scen = "scenario_" if "/scenarios/" in _rel else ""
+    CASES["yaml_" + _scen + _stem] = ("yaml:" + _rel, None, 2, 1300, False, "zem_auto", None)
+
+
 def make_policy(policy, ref):
     return {"random": lambda: rh.policy_random(7), "pursuit": rh.policy_pursuit, "mixed": lambda: rh.policy_mixed(11),
             "los_pn": lambda: rh.policy_los_pn(13), "zem": lambda: rh.policy_true_guidance(ref),
-            "zem_los": lambda: rh.policy_true_guidance(ref, los_frame=True)}[policy]()
+            "zem_los": lambda: rh.policy_true_guidance(ref, los_frame=True),
+            "zem_auto": lambda: rh.policy_true_guidance(ref, los_frame=ref.envs[0].config.get("observation_mode") == "los_frame"),
+            }[policy]()
 
 
 def generate(name):

@@ -54,3 +54,39 @@ def test_threads_equal_serial():
         ra, rb = a.step(act), b.step(act)
         assert (ra[0] == rb[0]).all() and (ra[1] == rb[1]).all()
     assert a.stats() == b.stats()
+
+
+def _reference_yaml_files():
+    import glob
+    import os
+
+    root = os.path.join(ref_harness.REFERENCE_ROOT, "rl_system")
+    files = sorted(glob.glob(os.path.join(root, "configs", "*.yaml")) + glob.glob(os.path.join(root, "configs", "*", "*.yaml")))
+    return [os.path.relpath(f, root) for f in files + [os.path.join(root, "config.yaml")]]
+
+
+@pytest.mark.reference
+def test_oracle_matches_live_reference_on_every_reference_yaml():
+    """Every YAML the reference ships (configs/*.yaml, configs/hrl/*.yaml, configs/scenarios/*.yaml, config.yaml), merged
+    the way scripts/train_hrl_pretrain.py:270-338 merges it: the resolver accepts it and the oracle follows the unmodified
+    reference through the first interceptions / terminations (integer outputs exact)."""
+    from oracle import gen_golden
+
+    files = _reference_yaml_files()
+    assert len(files) >= 36
+    n, T, seed = 2, 900, 77
+    for rel in files:
+        cfg = gen_golden.reference_yaml_env(rel)
+        P, cur = config.resolve_config(cfg, warn_dead=False)
+        ref = ref_harness.RefBatch(cfg, n, seed=seed)
+        sim = oracle.OracleBatch(P, cur, n, seed=seed)
+        pol = ref_harness.policy_true_guidance(ref, los_frame=cfg.get("observation_mode") == "los_frame")
+        o_r, o_o = ref.reset(), sim.reset()
+        np.testing.assert_allclose(o_o, o_r, atol=2e-6, err_msg=rel)
+        for t in range(T):
+            a = pol(t, o_r)
+            o_r, r_r, te_r, tr_r, _, inf_r = ref.step(a)
+            o_o, r_o, te_o, tr_o, _, inf_o = sim.step(a)
+            assert (te_r == te_o).all() and (tr_r == tr_o).all() and (inf_r["flags"] == inf_o["flags"]).all(), (rel, t)
+            np.testing.assert_allclose(o_o, o_r, atol=2e-5, err_msg=f"{rel} t={t}")
+            np.testing.assert_allclose(r_o, r_r, rtol=1e-5, atol=1e-4, err_msg=f"{rel} t={t}")
