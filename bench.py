@@ -387,9 +387,10 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = {"value": world * n * args.e2e_steps / float(te.item()), "unit": "env-steps/s",
-           "h2d_bytes_per_step": n * 6 * 4, "d2h_bytes_per_step": n * (26 * 4 + 4 + 1 + 1) + 4 + 160 * min(n, 4096),
-           "api": "HlynrVecEnv.step(numpy actions) -> numpy obs, rewards, dones, infos (hlynr_step_host: 8 chunks pipelined "
-                  "over 3 streams, pinned staging, done episodes as compact records)",
+           "h2d_bytes_per_step": n * 6 * 4, "d2h_bytes_per_step": n * (26 * 4 + 4 + 1 + 1 + 1) + 4 + 200 * min(n, 4096),
+           "api": "HlynrVecEnv.step(ordinary numpy actions) -> numpy obs, rewards, dones, infos (hlynr_step_host: chunks pipelined "
+                  "over 3 streams; actions staged with streaming stores; obs by copy engine into alternating page-locked sets; "
+                  "reward/terminated/truncated/dones written by the kernel straight into host memory; done episodes as compact records)",
            "steps": args.e2e_steps, "done_episodes_per_step": n_done / max(args.e2e_steps, 1),
            "ms_per_step": float(te.item()) / args.e2e_steps * 1e3}
     venv.close()

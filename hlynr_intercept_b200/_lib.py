@@ -17,7 +17,7 @@ EXPORTS = [
     "hlynr_step", "hlynr_rollout", "hlynr_reset_host", "hlynr_step_host", "hlynr_pinned_buffers", "hlynr_info_host",
     "hlynr_stats_device_ptr", "hlynr_stats_reduce", "hlynr_get_stats", "hlynr_export_state", "hlynr_import_state",
     "hlynr_debug_draws", "hlynr_launch_count", "hlynr_set_option", "hlynr_set_done_list", "hlynr_done_records_host",
-    "hlynr_ring_period", "hlynr_note_replayed_ticks",
+    "hlynr_ring_period", "hlynr_note_replayed_ticks", "hlynr_pinned_done", "hlynr_host_done_buffer",
     # include/hlynr_post.h
     "hlynr_post_create", "hlynr_post_destroy", "hlynr_post_obs_dim", "hlynr_post_obs_target", "hlynr_post_reset",
     "hlynr_post_step", "hlynr_post_original", "hlynr_post_normalize", "hlynr_post_get_stats", "hlynr_post_set_stats",
@@ -64,6 +64,8 @@ def load(build_if_missing=True):
     L.hlynr_reset_host.argtypes = [vp, vp, vp]
     L.hlynr_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32]
     L.hlynr_pinned_buffers.argtypes = [vp] + [C.POINTER(vp)] * 5
+    L.hlynr_pinned_done.argtypes = [vp, C.POINTER(vp)]
+    L.hlynr_host_done_buffer.argtypes = [vp, vp]
     L.hlynr_info_host.argtypes = [vp, C.POINTER(abi.HlynrInfoSoA)]
     L.hlynr_stats_device_ptr.argtypes = [vp, C.POINTER(vp)]
     L.hlynr_stats_reduce.argtypes = [vp, vp]

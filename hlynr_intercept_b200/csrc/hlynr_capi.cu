@@ -2,6 +2,7 @@
 // Owns the SoA state planes, the ring planes and the statistics block of one GPU shard and launches the
 // kernels of hlynr_device.cuh.  No torch types: callers pass raw device/host pointers and a stream.
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdarg>
@@ -11,6 +12,10 @@
 #include <new>
 #include <thread>
 #include <vector>
+
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include "hlynr_device.cuh"
 
@@ -50,8 +55,10 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-// Staging memcpys between unpinned caller buffers and the pinned buffers: a few persistent helper threads pull
-// 1 MiB blocks off an atomic counter (a single thread copies ~10 GB/s, less than the PCIe link moves).
+// Staging memcpys between unpinned caller buffers and the pinned buffers.  A single thread copies ~5-10 GB/s, less than the
+// PCIe link moves, so a few persistent helper threads pull 256 KiB blocks off an atomic counter, in address order.  start() is
+// asynchronous: hlynr_step_host starts the staging of the WHOLE action array, then waits chunk by chunk (wait_prefix) only
+// for the bytes the next host-to-device copy reads, helping with the copy while it waits.
 class CopyPool {
   public:
     explicit CopyPool(int helpers) {
@@ -62,28 +69,77 @@ class CopyPool {
         cv_.notify_all();
         for (auto& t : th_) t.join();
     }
-    void copy(void* dst, const void* src, size_t bytes) {
-        if (bytes < (size_t(4) << 20) || th_.empty()) { memcpy(dst, src, bytes); return; }
+    // asynchronous copy; exactly one job at a time: every start() is closed by finish()
+    void start(void* dst, const void* src, size_t bytes) {
+        const size_t nb = (bytes + kBlock - 1) / kBlock;
+        if (flags_.size() < nb) flags_ = std::vector<std::atomic<uint8_t>>(nb);
+        for (size_t k = 0; k < nb; ++k) flags_[k].store(0, std::memory_order_relaxed);
+        waited_ = 0;
+        woke_ = !th_.empty() && bytes >= kParallelMin;
         {
             std::lock_guard<std::mutex> l(m_);
-            dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes;
-            next_.store(0); busy_ = (int)th_.size(); ++gen_;
+            dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes; nblocks_ = nb;
+            next_.store(0);
+            if (woke_) { busy_ = (int)th_.size(); ++gen_; }
         }
-        cv_.notify_all();
-        run_blocks();
-        std::unique_lock<std::mutex> l(m_);
-        done_.wait(l, [this] { return busy_ == 0; });
+        if (woke_) cv_.notify_all();
+    }
+    // returns once [0, upto) of the job has been copied
+    void wait_prefix(size_t upto) {
+        const size_t need = upto >= bytes_ ? nblocks_ : upto / kBlock + (upto % kBlock ? 1 : 0);
+        while (next_.load(std::memory_order_relaxed) < need) {
+            const size_t b = next_.fetch_add(1);
+            if (b >= nblocks_) break;
+            copy_block(b);
+        }
+        for (; waited_ < need; ++waited_)
+            while (!flags_[waited_].load(std::memory_order_acquire)) std::this_thread::yield();
+    }
+    void finish() {
+        wait_prefix(bytes_);
+        if (woke_) {  // the helpers must be parked again before the job description changes
+            std::unique_lock<std::mutex> l(m_);
+            done_.wait(l, [this] { return busy_ == 0; });
+            woke_ = false;
+        }
+    }
+    void copy(void* dst, const void* src, size_t bytes) {
+        if (bytes < kParallelMin || th_.empty()) { memcpy(dst, src, bytes); return; }
+        start(dst, src, bytes);
+        finish();
     }
 
   private:
-    static constexpr size_t kBlock = size_t(1) << 20;
-    void run_blocks() {
-        for (;;) {
-            const size_t b = next_.fetch_add(1);
-            const size_t off = b * kBlock;
-            if (off >= bytes_) break;
-            memcpy(dst_ + off, src_ + off, bytes_ - off < kBlock ? bytes_ - off : kBlock);
+    static constexpr size_t kBlock = size_t(256) << 10;
+    static constexpr size_t kParallelMin = size_t(1) << 20;
+    // The destination is a pinned buffer the copy engine reads next (or a caller buffer nobody reads soon): streaming stores
+    // keep it out of the CPU caches, so there is no read-for-ownership traffic and the DMA read is served from DRAM instead
+    // of snooping dirty lines -- measured: a cached memcpy running next to the transfers slows the PCIe DMA itself.
+    static void stream_copy(char* dst, const char* src, size_t bytes) {
+#if defined(__x86_64__)
+        if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+            const size_t vec = bytes / 64;
+            for (size_t k = 0; k < vec; ++k) {
+                const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 4 * k);
+                const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 4 * k + 1);
+                const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 4 * k + 2);
+                const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 4 * k + 3);
+                _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 4 * k, a);
+                _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 4 * k + 1, b);
+                _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 4 * k + 2, c);
+                _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 4 * k + 3, d);
+            }
+            if (bytes % 64) memcpy(dst + vec * 64, src + vec * 64, bytes % 64);
+            _mm_sfence();
+            return;
         }
+#endif
+        memcpy(dst, src, bytes);
+    }
+    void copy_block(size_t b) {
+        const size_t off = b * kBlock;
+        stream_copy(dst_ + off, src_ + off, bytes_ - off < kBlock ? bytes_ - off : kBlock);
+        flags_[b].store(1, std::memory_order_release);
     }
     void worker() {
         uint64_t seen = 0;
@@ -94,7 +150,11 @@ class CopyPool {
                 seen = gen_;
                 if (stop_) return;
             }
-            run_blocks();
+            for (;;) {
+                const size_t b = next_.fetch_add(1);
+                if (b >= nblocks_) break;
+                copy_block(b);
+            }
             { std::lock_guard<std::mutex> l(m_); --busy_; }
             done_.notify_one();
         }
@@ -103,8 +163,9 @@ class CopyPool {
     std::mutex m_;
     std::condition_variable cv_, done_;
     std::atomic<size_t> next_{0};
-    char* dst_ = nullptr; const char* src_ = nullptr; size_t bytes_ = 0;
-    int busy_ = 0; uint64_t gen_ = 0; bool stop_ = false;
+    std::vector<std::atomic<uint8_t>> flags_;
+    char* dst_ = nullptr; const char* src_ = nullptr; size_t bytes_ = 0, nblocks_ = 0, waited_ = 0;
+    int busy_ = 0; uint64_t gen_ = 0; bool stop_ = false, woke_ = false;
 };
 
 #define HLYNR_HOST_STREAMS 3
@@ -113,10 +174,13 @@ class CopyPool {
 struct HostIO {  // pinned host + device staging for the *_host entry points
     float *h_actions = nullptr, *h_obs = nullptr, *h_reward = nullptr;
     uint8_t *h_term = nullptr, *h_trunc = nullptr, *h_mask = nullptr;
-    float *d_actions = nullptr, *d_obs = nullptr, *d_reward = nullptr;
-    uint8_t *d_term = nullptr, *d_trunc = nullptr, *d_mask = nullptr;
+    float *d_actions = nullptr, *d_obs = nullptr;
+    uint8_t* d_mask = nullptr;
     HlynrInfoSoA d_info;
-    HlynrDoneRecord *d_records = nullptr, *h_records = nullptr;  // capacity n
+    HlynrDoneRecord *d_records = nullptr, *h_records = nullptr;  // capacity n; h_records = h_records_ab[call parity]
+    HlynrDoneRecord* h_records_ab[2] = {nullptr, nullptr};       // two host buffers: the records of a call survive the next call
+    uint8_t* h_done = nullptr;                                   // terminated | truncated, written by the kernel
+    uint32_t calls = 0;
     int32_t *d_counter = nullptr, *h_count = nullptr;
     int32_t last_count = 0;
     cudaStream_t streams[HLYNR_HOST_STREAMS] = {nullptr, nullptr, nullptr};
@@ -152,6 +216,8 @@ struct hlynr_sim {
     HlynrDoneRecord* done_records = nullptr;  // attached compact done list (hlynr_set_done_list)
     int32_t* done_counter = nullptr;
     int32_t done_cap = 0;
+    uint8_t* io_done = nullptr;   // set by hlynr_step_host for the duration of the call
+    uint8_t* host_done = nullptr; // caller's page-locked `dones` buffer (hlynr_host_done_buffer), NULL = the handle's own
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -342,6 +408,7 @@ template <typename R> static KernelArgs<R> base_args(hlynr_sim* s, const StatePl
     A.st = planes;
     A.n = s->n; A.first = 0; A.lim = s->n;
     A.io.done_records = s->done_records; A.io.done_counter = s->done_counter; A.io.done_cap = s->done_cap;
+    A.io.done = s->io_done;
     A.ring_stride = s->n_pad;
     A.env_offset = s->env_offset;
     A.rk = make_round_keys(s->seed);
@@ -442,10 +509,10 @@ void hlynr_destroy(hlynr_t* s) {
     cudaFree(s->state_mem); cudaFree(s->stats); cudaFree(s->xchg); cudaFree(s->pipe_counters);
     HostIO& h = s->hio;
     delete h.pool;
-    cudaFreeHost(h.h_actions); cudaFreeHost(h.h_obs); cudaFreeHost(h.h_reward); cudaFreeHost(h.h_records); cudaFreeHost(h.h_count);
+    cudaFreeHost(h.h_actions); cudaFreeHost(h.h_obs); cudaFreeHost(h.h_reward); cudaFreeHost(h.h_records_ab[0]); cudaFreeHost(h.h_records_ab[1]); cudaFreeHost(h.h_count);
+    cudaFreeHost(h.h_done);
     cudaFreeHost(h.h_term); cudaFreeHost(h.h_trunc); cudaFreeHost(h.h_mask);
-    cudaFree(h.d_actions); cudaFree(h.d_obs); cudaFree(h.d_reward); cudaFree(h.d_records); cudaFree(h.d_counter);
-    cudaFree(h.d_term); cudaFree(h.d_trunc); cudaFree(h.d_mask);
+    cudaFree(h.d_actions); cudaFree(h.d_obs); cudaFree(h.d_records); cudaFree(h.d_counter); cudaFree(h.d_mask);
     for (int k = 0; k < HLYNR_HOST_STREAMS; ++k) {
         if (h.streams[k]) cudaStreamDestroy(h.streams[k]);
         if (h.ev_done[k]) cudaEventDestroy(h.ev_done[k]);
@@ -781,6 +848,13 @@ static int make_pool(hlynr_sim* s) {
     if (!h.pool) return fail("out of host memory");
     return 0;
 }
+// Page-locked host memory (cudaMallocHost / cudaHostAlloc / cudaHostRegister, e.g. a torch pin_memory() tensor) can be the
+// source or target of the DMA -- and, under unified addressing, of the kernel's own stores -- without a staging copy.
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
 static int ensure_hostio(hlynr_sim* s) {
     HostIO& h = s->hio;
     if (h.ready) return 0;
@@ -789,12 +863,14 @@ static int ensure_hostio(hlynr_sim* s) {
     CK(cudaMallocHost(&h.h_obs, n * 26 * sizeof(float)));
     CK(cudaMallocHost(&h.h_reward, n * sizeof(float)));
     CK(cudaMallocHost(&h.h_term, n)); CK(cudaMallocHost(&h.h_trunc, n)); CK(cudaMallocHost(&h.h_mask, n));
-    CK(cudaMallocHost(&h.h_records, n * sizeof(HlynrDoneRecord)));
+    CK(cudaMallocHost(&h.h_records_ab[0], n * sizeof(HlynrDoneRecord)));
+    CK(cudaMallocHost(&h.h_records_ab[1], n * sizeof(HlynrDoneRecord)));
+    h.h_records = h.h_records_ab[0];
+    CK(cudaMallocHost(&h.h_done, n));
     CK(cudaMallocHost(&h.h_count, sizeof(int32_t)));
     CK(cudaMalloc(&h.d_actions, n * 6 * sizeof(float)));
     CK(cudaMalloc(&h.d_obs, n * 26 * sizeof(float)));
-    CK(cudaMalloc(&h.d_reward, n * sizeof(float)));
-    CK(cudaMalloc(&h.d_term, n)); CK(cudaMalloc(&h.d_trunc, n)); CK(cudaMalloc(&h.d_mask, n));
+    CK(cudaMalloc(&h.d_mask, n));
     CK(cudaMalloc(&h.d_records, n * sizeof(HlynrDoneRecord)));
     CK(cudaMalloc(&h.d_counter, sizeof(int32_t)));
     CK(cudaMemset(h.d_counter, 0, sizeof(int32_t)));
@@ -867,30 +943,50 @@ int hlynr_step_host(hlynr_t* s, const float* actions_host, float* obs_host, floa
     if (s->host_info && ensure_host_info(s)) return 1;
     HostIO& h = s->hio;
     const int64_t n = s->n;
-    int64_t chunks = s->host_chunks > 0 ? s->host_chunks : (n >= (int64_t(1) << 17) ? 8 : (n >= (int64_t(1) << 15) ? 4 : 1));
+    int64_t chunks = s->host_chunks > 0 ? s->host_chunks : (n >= (int64_t(1) << 19) ? 16 : (n >= (int64_t(1) << 17) ? 8 : (n >= (int64_t(1) << 15) ? 4 : 1)));
     int64_t per = ((n + chunks - 1) / chunks + 127) & ~int64_t(127);
     chunks = (n + per - 1) / per;
     // the handle's own done list for this call (a caller-attached list is restored afterwards)
     HlynrDoneRecord* keep_r = s->done_records; int32_t* keep_c = s->done_counter; const int32_t keep_cap = s->done_cap;
     s->done_records = h.d_records; s->done_counter = h.d_counter; s->done_cap = (int32_t)(n < INT32_MAX ? n : INT32_MAX);
-    struct Restore { hlynr_sim* s; HlynrDoneRecord* r; int32_t* c; int32_t cap; ~Restore() { s->done_records = r; s->done_counter = c; s->done_cap = cap; } }
+    s->io_done = s->host_done ? s->host_done : h.h_done;
+    // caller buffers that are page-locked are used in place; pageable ones go through the handle's pinned staging buffers
+    const bool stage = !(actions_host == h.h_actions || is_pinned_host(actions_host));
+    const float* act_src = stage ? h.h_actions : actions_host;
+    const bool out_direct = (obs_host == h.h_obs || is_pinned_host(obs_host)) && (reward_host == h.h_reward || is_pinned_host(reward_host)) &&
+                            (terminated_host == h.h_term || is_pinned_host(terminated_host)) &&
+                            (truncated_host == h.h_trunc || is_pinned_host(truncated_host));
+    float* obs_dst = out_direct ? obs_host : h.h_obs;
+    float* reward_dst = out_direct ? reward_host : h.h_reward;
+    uint8_t* term_dst = out_direct ? terminated_host : h.h_term;
+    uint8_t* trunc_dst = out_direct ? truncated_host : h.h_trunc;
+    struct Restore { hlynr_sim* s; HlynrDoneRecord* r; int32_t* c; int32_t cap;
+                     ~Restore() { s->done_records = r; s->done_counter = c; s->done_cap = cap; s->io_done = nullptr; } }
         restore{s, keep_r, keep_c, keep_cap};
+    static const bool trace = getenv("HLYNR_HOST_TRACE") != nullptr;   // debugging aid: host-side timeline on stderr
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    double t_staged[64] = {0}, t_issued = 0, t_synced = 0;
     if (host_streams_begin(s)) return 1;
     CK(cudaMemsetAsync(h.d_counter, 0, sizeof(int32_t), h.streams[0]));
     CK(cudaEventRecord(h.ev_start, h.streams[0]));
     for (int k = 1; k < HLYNR_HOST_STREAMS; ++k) CK(cudaStreamWaitEvent(h.streams[k], h.ev_start, 0));
     s->tick += 1;
     const HlynrInfoSoA* info = s->host_info ? &h.d_info : nullptr;
+    struct StageGuard { CopyPool* p; ~StageGuard() { if (p) p->finish(); } } stage_guard{stage ? h.pool : nullptr};
+    if (stage) h.pool->start(h.h_actions, actions_host, (size_t)n * 24);
     for (int64_t c = 0; c < chunks; ++c) {
         const int64_t first = c * per, lim = first + per < n ? first + per : n, cnt = lim - first;
         cudaStream_t st = h.streams[c % HLYNR_HOST_STREAMS];
-        if (actions_host != h.h_actions) h.pool->copy(h.h_actions + first * 6, actions_host + first * 6, (size_t)cnt * 24);
-        CK(cudaMemcpyAsync(h.d_actions + first * 6, h.h_actions + first * 6, (size_t)cnt * 24, cudaMemcpyHostToDevice, st));
-        if (step_range(s, first, lim, h.d_actions, h.d_obs, h.d_reward, h.d_term, h.d_trunc, nullptr, info, auto_reset, st)) return 1;
-        CK(cudaMemcpyAsync(h.h_obs + first * 26, h.d_obs + first * 26, (size_t)cnt * 104, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(h.h_reward + first, h.d_reward + first, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(h.h_term + first, h.d_term + first, (size_t)cnt, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(h.h_trunc + first, h.d_trunc + first, (size_t)cnt, cudaMemcpyDeviceToHost, st));
+        if (stage) h.pool->wait_prefix((size_t)lim * 24);
+        if (trace && c < 64) t_staged[c] = since();
+        CK(cudaMemcpyAsync(h.d_actions + first * 6, act_src + first * 6, (size_t)cnt * 24, cudaMemcpyHostToDevice, st));
+        // reward / terminated / truncated (6 B per env) are written by the kernel STRAIGHT into the pinned host buffers
+        // (cudaMallocHost memory is device-accessible under unified addressing; coalesced posted PCIe writes, +26 us per
+        // 2^20 envs): three small copy-engine transfers per chunk, each with its own fixed latency, disappear and only the
+        // observation (104 B per env) rides the copy engine
+        if (step_range(s, first, lim, h.d_actions, h.d_obs, reward_dst, term_dst, trunc_dst, nullptr, info, auto_reset, st)) return 1;
+        CK(cudaMemcpyAsync(obs_dst + first * 26, h.d_obs + first * 26, (size_t)cnt * 104, cudaMemcpyDeviceToHost, st));
     }
     // done list: after every chunk's kernel; count + the first records in one go on stream 0
     for (int k = 1; k < HLYNR_HOST_STREAMS; ++k) {
@@ -898,13 +994,21 @@ int hlynr_step_host(hlynr_t* s, const float* actions_host, float* obs_host, floa
         CK(cudaStreamWaitEvent(h.streams[0], h.ev_done[k], 0));
     }
     const size_t prefix = (size_t)(n < HLYNR_DONE_PREFIX ? n : HLYNR_DONE_PREFIX);
+    h.h_records = h.h_records_ab[(h.calls++) & 1u];
     CK(cudaMemcpyAsync(h.h_count, h.d_counter, sizeof(int32_t), cudaMemcpyDeviceToHost, h.streams[0]));
     CK(cudaMemcpyAsync(h.h_records, h.d_records, prefix * sizeof(HlynrDoneRecord), cudaMemcpyDeviceToHost, h.streams[0]));
+    if (trace) t_issued = since();
     for (int k = HLYNR_HOST_STREAMS - 1; k >= 0; --k) CK(cudaStreamSynchronize(h.streams[k]));
-    if (obs_host != h.h_obs) h.pool->copy(obs_host, h.h_obs, (size_t)n * 104);
-    if (reward_host != h.h_reward) h.pool->copy(reward_host, h.h_reward, (size_t)n * 4);
-    if (terminated_host != h.h_term) h.pool->copy(terminated_host, h.h_term, (size_t)n);
-    if (truncated_host != h.h_trunc) h.pool->copy(truncated_host, h.h_trunc, (size_t)n);
+    if (trace) {
+        t_synced = since();
+        fprintf(stderr, "hlynr_step_host: staged");
+        for (int64_t c = 0; c < chunks && c < 64; ++c) fprintf(stderr, " %.2f", t_staged[c]);
+        fprintf(stderr, " | issued %.2f | synced %.2f ms\n", t_issued, t_synced);
+    }
+    if (obs_host != obs_dst) h.pool->copy(obs_host, obs_dst, (size_t)n * 104);
+    if (reward_host != reward_dst) h.pool->copy(reward_host, reward_dst, (size_t)n * 4);
+    if (terminated_host != term_dst) h.pool->copy(terminated_host, term_dst, (size_t)n);
+    if (truncated_host != trunc_dst) h.pool->copy(truncated_host, trunc_dst, (size_t)n);
     int32_t count = *h.h_count;
     if (count > s->done_cap) count = s->done_cap;
     if ((size_t)count > prefix) {
@@ -948,6 +1052,24 @@ int hlynr_info_host(hlynr_t* s, HlynrInfoSoA* o) {
     if (o->missile_min_distances)
         CK(cudaMemcpyAsync(o->missile_min_distances, d.missile_min_distances, n * 4 * HLYNR_MAX_VOLLEY, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// terminated | truncated of the last hlynr_step_host call, written by the kernel itself into pinned host memory.
+int hlynr_pinned_done(hlynr_t* s, uint8_t** done) {
+    if (!s || !done) return fail("hlynr_pinned_done: null argument");
+    DeviceGuard g(s->device);
+    if (ensure_hostio(s)) return 1;
+    *done = s->hio.h_done;
+    return 0;
+}
+
+int hlynr_host_done_buffer(hlynr_t* s, uint8_t* done_pinned) {
+    if (!s) return fail("hlynr_host_done_buffer: null handle");
+    DeviceGuard g(s->device);
+    if (done_pinned && !is_pinned_host(done_pinned))
+        return fail("hlynr_host_done_buffer: the buffer must be page-locked host memory (the kernel writes it directly)");
+    s->host_done = done_pinned;
     return 0;
 }
 

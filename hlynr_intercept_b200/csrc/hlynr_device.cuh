@@ -237,6 +237,7 @@ struct StepIO {
     float* reward;          // [N]
     uint8_t* terminated;    // [N]
     uint8_t* truncated;     // [N]
+    uint8_t* done;          // [N] or NULL: terminated | truncated (the host path's SB3 `dones`, saves a host pass over both)
     float* terminal_obs;    // [N,26] or NULL
     HlynrInfoSoA info;      // optional arrays
     const uint8_t* reset_mask;  // reset kernel only
@@ -1443,6 +1444,7 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
                 if (!kRollout && active) {
                     A.io.reward[i] = t.reward;
                     A.io.terminated[i] = t.terminated ? 1 : 0;
+                    if (A.io.done) A.io.done[i] = (t.terminated || t.truncated) ? 1 : 0;
                     A.io.truncated[i] = t.truncated ? 1 : 0;
                     if (A.has_info) write_info(A, i, e, t, ob);
                 }
@@ -1649,6 +1651,7 @@ step_kernel_tma(const __grid_constant__ KernelArgs<float> A, const __grid_consta
                 if (active) {
                     A.io.reward[i] = t.reward;
                     A.io.terminated[i] = t.terminated ? 1 : 0;
+                    if (A.io.done) A.io.done[i] = (t.terminated || t.truncated) ? 1 : 0;
                     A.io.truncated[i] = t.truncated ? 1 : 0;
                     if (A.has_info) write_info(A, i, e, t, ob);
                 }
@@ -1802,6 +1805,7 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, 4) step_kernel_pipe(const __grid_
                 if (active) {
                     A.io.reward[i] = t.reward;
                     A.io.terminated[i] = t.terminated ? 1 : 0;
+                    if (A.io.done) A.io.done[i] = (t.terminated || t.truncated) ? 1 : 0;
                     A.io.truncated[i] = t.truncated ? 1 : 0;
                     if (A.has_info) write_info(A, i, e, t, ob);
                 }

@@ -147,10 +147,25 @@ class HlynrVecEnv(_VecEnvBase):
             return np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(cnt,)).view(dtype).reshape(shape)
 
         self._act = view(ptrs[0], (n, 6), C.c_float, np.float32)
-        self._obs = view(ptrs[1], (n, 26), C.c_float, np.float32)
-        self._rew = view(ptrs[2], (n,), C.c_float, np.float32)
-        self._term = view(ptrs[3], (n,), C.c_uint8, np.uint8)
-        self._trunc = view(ptrs[4], (n,), C.c_uint8, np.uint8)
+        pd = C.c_void_p()
+        _lib.check(L.hlynr_pinned_done(self.sim.h, C.byref(pd)))
+        # Two page-locked output sets that alternate from step to step: the arrays a step returns stay untouched while the
+        # NEXT step runs (SB3's collect_rollouts reads `_last_obs` / `_last_episode_starts` of step k after step k+1 has
+        # returned) and are overwritten by the one after it.  Set 0 is the C library's own pinned buffers, set 1 is torch
+        # pinned memory; hlynr_step_host DMAs into either without a staging copy, and the kernel writes reward /
+        # terminated / truncated / dones straight into them.
+        import torch
+
+        self._pinned = [torch.empty(shape, dtype=dt, pin_memory=True) for shape, dt in
+                        (((n, 26), torch.float32), ((n,), torch.float32), ((n,), torch.uint8), ((n,), torch.uint8), ((n,), torch.uint8))]
+        self._sets = [
+            (view(ptrs[1], (n, 26), C.c_float, np.float32), view(ptrs[2], (n,), C.c_float, np.float32),
+             view(ptrs[3], (n,), C.c_uint8, np.uint8), view(ptrs[4], (n,), C.c_uint8, np.uint8),
+             view(pd, (n,), C.c_uint8, np.uint8)),
+            tuple(t.numpy() for t in self._pinned)]
+        self._set_ptrs = [([x.ctypes.data_as(C.c_void_p) for x in st[:4]], st[4].ctypes.data_as(C.c_void_p) if k else None,
+                           st[4].view(np.bool_)) for k, st in enumerate(self._sets)]
+        self._bind_set(0)
         self._info = None           # [N]-sized info arrays, only in the eager (small-n) mode
         self._info_struct = None
         self.sim.set_option("host_info", 0 if self.lazy_infos else 1)
@@ -160,6 +175,12 @@ class HlynrVecEnv(_VecEnvBase):
         self._pending = None
         self.training_step_count = 0
         self.observation_generator = _ObservationGeneratorView(self)
+
+    def _bind_set(self, k):
+        self._cur = k
+        self._obs, self._rew, self._term, self._trunc, _ = self._sets[k]
+        self._out_ptrs, done_ptr, self._done = self._set_ptrs[k]   # _done: terminated | truncated, written by the kernel
+        _lib.check(self.sim.L.hlynr_host_done_buffer(self.sim.h, done_ptr))
 
     # ---- VecEnv API -----------------------------------------------------------------------------------
     def reset(self):
@@ -180,14 +201,12 @@ class HlynrVecEnv(_VecEnvBase):
     def step_wait(self):
         assert self._pending is not None, "step_wait() without step_async()"
         a, self._pending = self._pending, None
-        p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
-        _lib.check(self.sim.L.hlynr_step_host(self.sim.h, p(a), p(self._obs), p(self._rew), p(self._term),
-                                              p(self._trunc), None, 1))
-        dones = np.logical_or(self._term, self._trunc)
+        self._bind_set(self._cur ^ 1)
+        _lib.check(self.sim.L.hlynr_step_host(self.sim.h, a.ctypes.data_as(C.c_void_p), *self._out_ptrs, None, 1))
         infos = self._build_infos()
         if self.copy_outputs:
-            return self._obs.copy(), self._rew.copy(), dones, infos
-        return self._obs, self._rew, dones, infos
+            return self._obs.copy(), self._rew.copy(), self._done.copy(), infos
+        return self._obs, self._rew, self._done, infos
 
     def done_records(self):
         """Finished episodes of the last step as a structured array (abi.done_record_numpy_dtype), a view of pinned
@@ -246,7 +265,7 @@ class HlynrVecEnv(_VecEnvBase):
         rec = self.done_records()
         now = round(time.time() - self._t_start, 6)
         if self.lazy_infos:
-            return LazyInfos(self, rec.copy(), now)
+            return LazyInfos(self, rec, now)   # a view: the C library alternates two record buffers, valid through the next step
         if self._info is None:
             self._info = {nm: np.zeros((n,) + shp, dtype=dt) for nm, dt, shp in abi.INFO_FIELDS}
             self._info_struct = abi.HlynrInfoSoA(**{nm: self._info[nm].ctypes.data for nm, _, _ in abi.INFO_FIELDS})

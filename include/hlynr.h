@@ -280,12 +280,23 @@ int hlynr_step_host(hlynr_t* sim, const float* actions_host, float* obs_host, fl
                     uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host,
                     int auto_reset);
 /* Finished episodes of the last hlynr_step_host call: pointer to `*count` records in pinned host memory owned by
- * the handle (valid until the next call on the handle). */
+ * the handle.  Two buffers alternate, so the records of a call stay valid during the next hlynr_step_host call and are
+ * overwritten by the one after it (SB3 loops hold `infos` of step k while step k+1 runs). */
 int hlynr_done_records_host(hlynr_t* sim, const HlynrDoneRecord** records, int32_t* count);
 /* Pinned host buffers owned by the handle: float[N,6], float[N,26], float[N], uint8[N], uint8[N].  Passing
- * these very pointers to hlynr_step_host / hlynr_reset_host skips the staging memcpy. */
+ * these very pointers -- or ANY page-locked caller buffer (cudaMallocHost / cudaHostRegister / a torch pin_memory()
+ * tensor; detected with cudaPointerGetAttributes) -- to hlynr_step_host skips the staging memcpy: the copy engine
+ * and the kernel read and write the caller's memory directly.  Callers that alternate two page-locked output sets get
+ * the SB3 loop's "the arrays of step k are still read while step k+1 runs" for free. */
 int hlynr_pinned_buffers(hlynr_t* sim, float** actions, float** obs, float** reward, uint8_t** terminated,
                          uint8_t** truncated);
+/* SB3 `dones` of the last hlynr_step_host call: uint8[N] = terminated | truncated (environment.py:813-816 combined the way
+ * DummyVecEnv.step_wait does), in pinned host memory owned by the handle; the step kernel writes it directly, so the
+ * caller does not need a pass over both flag arrays.  Overwritten by the next call. */
+int hlynr_pinned_done(hlynr_t* sim, uint8_t** done);
+/* Redirects `dones` to a caller-owned PAGE-LOCKED buffer uint8[N] (NULL = back to the handle's own); fails for pageable
+ * memory, because the kernel stores into it directly. */
+int hlynr_host_done_buffer(hlynr_t* sim, uint8_t* done_pinned);
 /* Copies the info arrays of the last hlynr_step_host call to host (each pointer optional, host). */
 int hlynr_info_host(hlynr_t* sim, HlynrInfoSoA* host_arrays);
 

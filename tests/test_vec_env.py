@@ -213,3 +213,25 @@ def test_volley_mode_info_fields():
                 assert "terminal_observation" in d and "episode" in d
                 seen += 1
         v.close()
+
+
+def test_outputs_of_a_step_survive_the_next_step():
+    """Zero-copy mode returns views of page-locked buffers.  SB3's collect_rollouts reads the obs / dones / infos of step k
+    after step k+1 has returned, so two output sets alternate: what step k returned must be untouched by step k+1 and may
+    only be reused by step k+2 (pinned caller buffers, torch or library-owned, are DMA targets without a staging copy)."""
+    n = 70000
+    v = make(n, lazy_infos=True, copy_outputs=False)
+    v.reset()
+    v.sim.rollout(900, None)
+    rng = np.random.default_rng(5)
+    prev = None
+    for t in range(40):
+        obs, rew, dones, infos = v.step(rng.uniform(-1, 1, (n, 6)).astype(np.float32))
+        assert dones.dtype == np.bool_ and (dones == (v._term | v._trunc).astype(bool)).all()
+        if prev is not None:
+            (o_view, r_view, d_view, i_view), (o_copy, r_copy, d_copy, rec_copy) = prev
+            assert (o_view == o_copy).all() and (r_view == r_copy).all() and (d_view == d_copy).all(), t
+            assert (i_view.records == rec_copy).all(), t
+            assert not np.shares_memory(o_view, obs)
+        prev = ((obs, rew, dones, infos), (obs.copy(), rew.copy(), dones.copy(), infos.records.copy()))
+    v.close()
