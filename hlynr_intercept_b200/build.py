@@ -31,8 +31,8 @@ def build(force=False, verbose=False):
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout)
-    with open(os.path.join(HERE, "csrc", "ptxas_report.txt"), "w") as f:
-        f.write(res.stdout)
+    with open(os.path.join(HERE, "csrc", "ptxas_report.txt"), "w") as f:   # registers / spills / smem per kernel (kept in git)
+        f.write("".join(l for l in res.stdout.splitlines(True) if "Compile time" not in l))
     if verbose:
         print(res.stdout)
     return SO

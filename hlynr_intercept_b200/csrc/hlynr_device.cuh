@@ -333,18 +333,32 @@ template <typename R, int F = FT_GENERIC> HD void store_env(const KernelArgs<R>&
 // physics_models.py
 // ------------------------------------------------------------------------------------------------
 // AtmosphericModel.get_atmospheric_properties (physics_models.py:154-177)
+// Hot / cold layout.  ptxas lays basic blocks out in source order, so a rarely taken `if` body in the middle of the tick is
+// a taken branch over it on EVERY tick, and the instruction fetch after a taken branch is what the `no_instructions` stall
+// samples of profiles/r01_e sit on (12 % of all samples in the steady state, almost all on reconvergence points).  The
+// rare bodies below are therefore separate __noinline__ functions that return by value (no addresses taken), and short
+// two-way choices are written branch-free where that is bit-identical.
+template <typename R> struct Pair { R a, b; };
+template <typename R> __device__ __noinline__ Pair<R> isa_above_11km(R alt) {  // physics_models.py:163-171
+    Pair<R> o;
+    if (alt <= R(20000.0)) {
+        o.a = R(216.65);
+        o.b = mul(R(22632.0), nexp(ndiv(mul(R(-9.80665), sub(alt, R(11000.0))), R(287.05 * 216.65))));
+    } else {
+        R ex = sub(alt, R(20000.0));
+        o.a = mul(R(216.65), nexp(ndiv(-ex, R(10000.0))));
+        o.b = mul(R(5474.889421808574), nexp(ndiv(-ex, R(6000.0))));  // get_pressure(20000.0) in python floats
+    }
+    return o;
+}
 template <typename R> HD void isa_props(const KParams<R>& P, R T0, R alt, R* rho, R* cs) {
     R T, Pr;
     if (alt <= R(11000.0)) {
         T = sub(T0, mul(R(0.0065), alt));
         Pr = mul(R(101325.0), npow(ndiv(T, T0), P.isa_expo));
-    } else if (alt <= R(20000.0)) {
-        T = R(216.65);
-        Pr = mul(R(22632.0), nexp(ndiv(mul(R(-9.80665), sub(alt, R(11000.0))), R(287.05 * 216.65))));
     } else {
-        R ex = sub(alt, R(20000.0));
-        T = mul(R(216.65), nexp(ndiv(-ex, R(10000.0))));
-        Pr = mul(R(5474.889421808574), nexp(ndiv(-ex, R(6000.0))));  // get_pressure(20000.0) in python floats
+        const Pair<R> hi = isa_above_11km<R>(alt);
+        T = hi.a; Pr = hi.b;
     }
     *rho = ndiv(Pr, mul(P.gas_R, T));
     *cs = nsqrt(mul(P.gamma_R, T));
@@ -367,15 +381,16 @@ HD void drag_accel(const KParams<R>& P, const Env<R>& e, R vx, R vy, R vz, R alt
         R cd;
         if (FT::dr(P)) {
             double bc = (double)e.base_cd, pk = (double)e.peak, c;
-            if (mach < P.sub_mach) c = bc;
-            else if (mach < P.sup_mach) c = bc * (1.0 + (pk - 1.0) * (double)ndiv(sub(mach, P.sub_mach), P.sup_minus_sub));
-            else c = bc * P.sup_mult_d;
+            R ramp = ndiv(sub(mach, P.sub_mach), P.sup_minus_sub);
+            ramp = mach < P.sub_mach ? R(0) : ramp;   // bc * (1 + (pk - 1) * 0) == bc
+            c = mach < P.sup_mach ? bc * (1.0 + (pk - 1.0) * (double)ramp) : bc * P.sup_mult_d;
             cd = (R)c;
         } else {
-            if (mach < P.sub_mach) cd = P.cd_base;
-            else if (mach < P.sup_mach)
-                cd = mul(P.cd_base, add(R(1.0), mul(P.peak_minus1, ndiv(sub(mach, P.sub_mach), P.sup_minus_sub))));
-            else cd = P.cd_sup;
+            // branch-free and bit-identical: below sub_mach the ramp term is clamped to 0, and base * (1 + peak_minus1 * 0) == base
+            R ramp = ndiv(sub(mach, P.sub_mach), P.sup_minus_sub);
+            ramp = mach < P.sub_mach ? R(0) : ramp;
+            const R mid = mul(P.cd_base, add(R(1.0), mul(P.peak_minus1, ramp)));
+            cd = mach < P.sup_mach ? mid : P.cd_sup;
         }
         if constexpr (std::is_same<R, float>::value) {
             float k = -((weak ? P.half_rho_weak : 0.5f * rho) * vmag * cd * area * post_scale * rc_mass);
@@ -405,6 +420,19 @@ template <typename R> HD R nan_guard(R a, R lim) {  // np.nan_to_num(nan=0, posi
     if (isinf(a)) return a > R(0) ? lim : -lim;
     return a;
 }
+
+template <typename R> struct Tri { R x, y, z; };
+template <typename R> __device__ __noinline__ Tri<R> nan_guard3(R a, R b, R c, R lim) {
+    return Tri<R>{nan_guard(a, lim), nan_guard(b, lim), nan_guard(c, lim)};
+}
+// SafetyClamp scaling (core.py:1085-1097): only reached when the squared norm exceeds the limit (never for actions in [-1, 1])
+template <typename R> __device__ __noinline__ Vec4<R> clamp_norm_slow(R a, R b, R c, R lim) {
+    const R m = norm3(a, b, c);
+    if (m > lim) { const R f = dvd(lim, m); return Vec4<R>{mul(a, f), mul(b, f), mul(c, f), R(1)}; }
+    return Vec4<R>{a, b, c, R(0)};
+}
+// full-range sine / cosine of the quaternion half-angle: actions outside [-1, 1] only
+__device__ __noinline__ Pair<float> sincos_full(float h) { return Pair<float>{sinf(h), cosf(h)}; }
 
 // The LOS basis shared by the observation (core.py:803-845, :929-945) and the action transform
 // (environment.py:965-1020): lu = rel/|rel|, lh = normalize(lu x world_up) = (lu.y, -lu.x, 0)/n, lv = lu x lh.
@@ -860,6 +888,22 @@ template <typename R> HD void spawn(const KernelArgs<R>& A, Env<R>& e, const Rng
     e.ep_ret = R(0);
 }
 
+// EnhancedWindModel gust (physics_models.py:381-385): 0.1 % of the ticks, out of line
+template <typename R>
+__device__ __noinline__ Tri<R> wind_gust(const KernelArgs<R>& A, uint32_t c0, uint32_t c3hi, uint32_t ep, uint32_t st, R wvx, R wvy, R wvz) {
+    RngKey key;
+    key.rk = &A.rk; key.c0 = c0; key.c3hi = c3hi;
+    float g0, g1, g2, g3;
+    uint4 gd = draw_raw(key, ep, st, HLYNR_BLK_GUST_DIR);
+    box_muller(gd.x, gd.y, &g0, &g1);
+    box_muller(gd.z, gd.w, &g2, &g3);
+    uint4 gm = draw_raw(key, ep, st, HLYNR_BLK_GUST_MAG);
+    double nn = sqrt((double)g0 * g0 + (double)g1 * g1 + (double)g2 * g2) + 1e-6;
+    double mag = A.P.gust_scale_d * (double)(-logf(u01_open(gm.x)));
+    return Tri<R>{(R)((double)wvx + ((double)g0 / nn) * mag), (R)((double)wvy + ((double)g1 / nn) * mag),
+                  (R)((double)wvz + ((double)g2 / nn) * mag)};
+}
+
 // ------------------------------------------------------------------------------------------------
 // one tick (environment.py:605-859)
 // ------------------------------------------------------------------------------------------------
@@ -878,7 +922,7 @@ HD void quat_step(Env<float>& e, float wx, float wy, float wz, float dt) {
         float h = 0.5f * wn * dt, h2 = h * h;  // h <= 0.18 rad for |a| <= 1: Taylor to float accuracy
         float sh = h * fmaf(h2, fmaf(h2, fmaf(h2, -1.98412698e-4f, 8.33333333e-3f), -1.66666667e-1f), 1.f);
         float ch = fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, 2.48015873e-5f, -1.38888889e-3f), 4.16666667e-2f), -0.5f), 1.f);
-        if (h > 0.5f) { sh = sinf(h); ch = cosf(h); }  // actions outside [-1,1]
+        if (h > 0.5f) { const Pair<float> sc = sincos_full(h); sh = sc.a; ch = sc.b; }  // actions outside [-1,1]
         float k = sh * nrcp(wn);
         float w1 = ch, x1 = wx * k, y1 = wy * k, z1 = wz * k;
         float w2q = e.qw, x2 = e.qx, y2 = e.qy, z2 = e.qz;
@@ -930,7 +974,8 @@ HD void missile_update(const KParams<R>& P, const Env<R>& e, const RngKey& key, 
     // (evasion = np.zeros(3)), and velocity += total_accel * dt is evaluated in float64: kept as is.
     double ax = (double)dax + ex, ay = (double)day + ey, az = (double)add(daz, (R)(-9.81f)) + ez;
     if (P.validate && any_nonfinite(ax, ay, az)) {
-        ax = nan_guard(ax, 20.0); ay = nan_guard(ay, 20.0); az = nan_guard(az, 20.0);
+        const Tri<double> g = nan_guard3<double>(ax, ay, az, 20.0);
+        ax = g.x; ay = g.y; az = g.z;
     }
     mvx = (R)add((double)mvx, mul(ax, P.dt_d));
     mvy = (R)add((double)mvy, mul(ay, P.dt_d));
@@ -1012,12 +1057,12 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
     bool clamped = false;
     if (e.fuel <= R(0)) { a0 = a1 = a2 = R(0); clamped = true; }
     if (a0 * a0 + a1 * a1 + a2 * a2 > R(2499.0)) {
-        R am = norm3(a0, a1, a2);
-        if (am > R(50.0)) { R f = dvd(R(50.0), am); a0 = mul(a0, f); a1 = mul(a1, f); a2 = mul(a2, f); clamped = true; }
+        const Vec4<R> c = clamp_norm_slow<R>(a0, a1, a2, R(50.0));
+        a0 = c.x; a1 = c.y; a2 = c.z; clamped = clamped || c.w != R(0);
     }
     if (a3 * a3 + a4 * a4 + a5 * a5 > R(24.9)) {
-        R gm = norm3(a3, a4, a5);
-        if (gm > R(5.0)) { R f = dvd(R(5.0), gm); a3 = mul(a3, f); a4 = mul(a4, f); a5 = mul(a5, f); clamped = true; }
+        const Vec4<R> c = clamp_norm_slow<R>(a3, a4, a5, R(5.0));
+        a3 = c.x; a4 = c.y; a5 = c.z; clamped = clamped || c.w != R(0);
     }
     t.clamped = clamped;
     const R dt = P.dt;
@@ -1048,7 +1093,8 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
         drag_accel<R, F>(P, e, vax, vay, vaz, alt, R(1.0), R(1.0), R(1.0 / 500.0), R(500.0), &dax, &day, &daz);
         R ax = add(tax, dax), ay = add(tay, day), az = add(add(taz, daz), (R)(-9.81f));
         if (P.validate && any_nonfinite(ax, ay, az)) {
-            ax = nan_guard(ax, R(50)); ay = nan_guard(ay, R(50)); az = nan_guard(az, R(50));
+            const Tri<R> g = nan_guard3<R>(ax, ay, az, R(50));
+            ax = g.x; ay = g.y; az = g.z;
         }
         // semi-implicit Euler, :933-934 (exact float ops, reference order)
         e.ivx = add(e.ivx, mul(ax, dt)); e.ivy = add(e.ivy, mul(ay, dt)); e.ivz = add(e.ivz, mul(az, dt));
@@ -1077,16 +1123,8 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
             wvx += scale * (R)z0; wvy += scale * (R)z1; wvz += scale * (R)z2;
         }
         if (u01(t.ur.x) < 0.001f) {  // gust, :381-385 (0.1 % of ticks)
-            float g0, g1, g2, g3;
-            uint4 gd = draw_raw(key, ep, st, HLYNR_BLK_GUST_DIR);
-            box_muller(gd.x, gd.y, &g0, &g1);
-            box_muller(gd.z, gd.w, &g2, &g3);
-            uint4 gm = draw_raw(key, ep, st, HLYNR_BLK_GUST_MAG);
-            double nn = sqrt((double)g0 * g0 + (double)g1 * g1 + (double)g2 * g2) + 1e-6;
-            double mag = P.gust_scale_d * (double)(-logf(u01_open(gm.x)));
-            wvx = (R)((double)wvx + ((double)g0 / nn) * mag);
-            wvy = (R)((double)wvy + ((double)g1 / nn) * mag);
-            wvz = (R)((double)wvz + ((double)g2 / nn) * mag);
+            const Tri<R> g = wind_gust<R>(A, key.c0, key.c3hi, ep, st, wvx, wvy, wvz);
+            wvx = g.x; wvy = g.y; wvz = g.z;
         }
         e.wx = (float)wvx; e.wy = (float)wvy; e.wz = (float)wvz;
     } else if (P.wind_var > R(0)) {  // AR(1) wind, environment.py:1127-1129 (float64 in the reference)
