@@ -767,6 +767,7 @@ struct SpawnOut {
     float base_cd, peak;
     double dT0;
     int odelay;
+    uint4 ur;  // BLK_UNI of step 0 of the new episode (the observation of the reset), drawn here to keep the call site short
 };
 
 // one missile's spawn (environment.py:389-427) from its uniform block
@@ -848,6 +849,7 @@ __device__ __noinline__ SpawnOut spawn_values(const KernelArgs<R>& A, uint32_t c
         } else if (!(fz > 0)) { o.qw = 0.f; o.qx = 1.f; }  // anti-aligned (quirk Q9: aligned -> identity)
     }
     o.mx = mx; o.my = my; o.mz = mz; o.ix = ix; o.iy = iy; o.iz = iz;
+    o.ur = draw_raw(key, ep, 0u, HLYNR_BLK_UNI);
     o.dT0 = 0.0; o.base_cd = 0.3f; o.peak = (float)(P.peak_minus1 + R(1.0)); o.odelay = P.onboard_delay;
     if (P.dr) {  // physics_randomizer.py:166-214, 243-297
         float z0, z1, z2, z3, z4, zd;
@@ -865,7 +867,7 @@ __device__ __noinline__ SpawnOut spawn_values(const KernelArgs<R>& A, uint32_t c
     return o;
 }
 
-template <typename R> HD void spawn(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t plane_i) {
+template <typename R> HD uint4 spawn(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, int64_t plane_i) {
     const KParams<R>& P = A.P;
     const SpawnOut o = spawn_values(A, key.c0, key.c3hi, (uint32_t)e.episode, plane_i);
     e.mpx = o.mx; e.mpy = o.my; e.mpz = o.mz; e.mvx = o.mvx; e.mvy = o.mvy; e.mvz = o.mvz;
@@ -886,6 +888,7 @@ template <typename R> HD void spawn(const KernelArgs<R>& A, Env<R>& e, const Rng
     e.Ppp = 1000.f; e.Ppv = 0.f; e.Pvp = 0.f; e.Pvv = 1000.f;
     e.prev_d = e.last_d = e.min_d = (R)o.d0;
     e.ep_ret = R(0);
+    return o.ur;
 }
 
 // EnhancedWindModel gust (physics_models.py:381-385): 0.1 % of the ticks, out of line
@@ -1150,9 +1153,10 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
         term = vo.all_inactive || fuze;
     } else {
         const bool missile_down = e.mpz <= R(0);
-        if (FT::precision_mode(P) ? missile_down : (!intercepted && missile_down)) {
-            R gx = sub(e.mpx, P.target_x), gy = sub(e.mpy, P.target_y);
-            hit = sqr(dot2(gx, gy, gx, gy)) < R(500.0);
+        {   // ground-impact distance to the target < 500 m (environment.py:769-776), branch-free: sqrt.rn(x) < 500 <=> x < 250000
+            // (the largest x below 250000 has a root more than half an ulp below 500, in float and in double)
+            const R gx = sub(e.mpx, P.target_x), gy = sub(e.mpy, P.target_y);
+            hit = (FT::precision_mode(P) ? missile_down : (!intercepted && missile_down)) && dot2(gx, gy, gx, gy) < R(250000.0);
         }
         if (FT::precision_mode(P)) term = missile_down;
         else term = intercepted || missile_down;
@@ -1277,6 +1281,9 @@ HD void account_episodes(const KernelArgs<R>& A, bool active, bool done, const E
 // The observation channels are written by observe() straight into the warp's tile (row pitch 26 words); here the
 // warp streams the 32*26 floats out linearly as float4 (the tile offset of a linear index is the index itself).
 #define OBS_TILE (32 * HLYNR_OBS_DIM)
+__device__ __noinline__ void flush_obs_ragged(const float* tile, float* base, int valid, unsigned lane) {  // last warp of a ragged shard
+    for (int idx = (int)lane; idx < valid; idx += 32) base[idx] = tile[idx];
+}
 HD void flush_obs_tile(const float* tile, float* dst, int64_t warp_first_env, int64_t n, unsigned lane) {
     __syncwarp();
     const int64_t rows = n - warp_first_env;
@@ -1290,13 +1297,12 @@ HD void flush_obs_tile(const float* tile, float* dst, int64_t warp_first_env, in
             if (k < 6 || idx < OBS_TILE / 4) b4[idx] = t4[idx];
         }
     } else if (rows > 0) {
-        const int valid = (int)rows * HLYNR_OBS_DIM;
-        for (int idx = (int)lane; idx < valid; idx += 32) base[idx] = tile[idx];
+        flush_obs_ragged(tile, base, (int)rows * HLYNR_OBS_DIM, lane);
     }
     __syncwarp();
 }
 // this lane's row of the tile -> one row of a [N,26] array (terminal observation of a finished episode: rare)
-HD void copy_obs_row(const float* row, float* dst_row) {
+__device__ __noinline__ void copy_obs_row(const float* row, float* dst_row) {
 #pragma unroll
     for (int k = 0; k < HLYNR_OBS_DIM; ++k) dst_row[k] = row[k];
 }
@@ -1368,6 +1374,21 @@ __device__ __noinline__ int32_t append_done_record(HlynrDoneRecord* recs, int32_
 #pragma unroll
     for (int k = 0; k < HLYNR_OBS_DIM; ++k) r->terminal_obs[k] = obs_row[k];
     return slot;
+}
+// One out-of-line call per finished episode: flag word, record, volley fields (the call site only marshals scalars).
+template <typename R>
+__device__ __noinline__ void record_done(const KernelArgs<R>& A, int64_t i, int steps, int eflags, bool terminated, bool truncated,
+                                         bool intercepted, bool hit, bool clamped, bool onboard_det, bool ground_det, bool fuze,
+                                         float distance, float min_d, float fuel, float fuel_used, float ep_ret, float ix, float iy,
+                                         float iz, float mx, float my, float mz, const float* obs_row) {
+    const uint32_t flags = info_flags(eflags, intercepted, hit, clamped, onboard_det, ground_det, fuze) |
+                           (terminated ? HLYNR_DONE_TERMINATED : 0u) | (truncated ? HLYNR_DONE_TRUNCATED : 0u);
+    const int32_t slot = append_done_record(A.io.done_records, A.io.done_counter, A.io.done_cap, (int32_t)i, steps, flags, distance,
+                                            min_d, fuel, fuel_used, ep_ret, ix, iy, iz, mx, my, mz, obs_row);
+    if (slot >= 0) {
+        HlynrDoneRecord* r = A.io.done_records + slot;
+        volley_info(A, i, eflags, distance, intercepted, &r->missiles_intercepted, &r->missiles_remaining, r->missile_min_distances);
+    }
 }
 template <typename R> HD RngKey make_key(const KernelArgs<R>& A, int64_t global_env) {
     RngKey k;
@@ -1470,8 +1491,7 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
             if (pass == 1) {
                 if (!need_reset) break;
                 e.episode += 1;
-                spawn(A, e, key, i);
-                ur = draw_raw(key, (uint32_t)e.episode, 0u, HLYNR_BLK_UNI);
+                ur = spawn(A, e, key, i);
             }
             // ring planes are indexed by the lane's OWN (padded) slot: a shadow lane of another warp may run ticks
             // ahead in a fused rollout and must never touch the rows of the env it shadows
@@ -1489,16 +1509,9 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
                 rsum += t.reward;
                 account_episodes(A, active, done, e, t);
                 if (!kRollout && done && active && A.io.done_records) {
-                    const int32_t slot = append_done_record(A.io.done_records, A.io.done_counter, A.io.done_cap, (int32_t)i, e.steps,
-                                       info_flags(e.flags, t.intercepted, t.hit, t.clamped, ob.onboard_det, ob.ground_det, t.fuze) |
-                                           (t.terminated ? HLYNR_DONE_TERMINATED : 0u) | (t.truncated ? HLYNR_DONE_TRUNCATED : 0u),
-                                       t.distance, (float)e.min_d, (float)e.fuel, (float)e.fuel_used, (float)e.ep_ret, (float)e.ipx,
-                                       (float)e.ipy, (float)e.ipz, (float)e.mpx, (float)e.mpy, (float)e.mpz, ob.row);
-                    if (slot >= 0) {
-                        HlynrDoneRecord* r = A.io.done_records + slot;
-                        volley_info(A, i, e.flags, t.distance, t.intercepted, &r->missiles_intercepted, &r->missiles_remaining,
-                                    r->missile_min_distances);
-                    }
+                    record_done<R>(A, i, e.steps, e.flags, t.terminated, t.truncated, t.intercepted, t.hit, t.clamped, ob.onboard_det,
+                                   ob.ground_det, t.fuze, t.distance, (float)e.min_d, (float)e.fuel, (float)e.fuel_used, (float)e.ep_ret,
+                                   (float)e.ipx, (float)e.ipy, (float)e.ipz, (float)e.mpx, (float)e.mpy, (float)e.mpz, ob.row);
                 }
                 need_reset = done && A.auto_reset;
                 if (need_reset) {
@@ -1679,8 +1692,7 @@ step_kernel_tma(const __grid_constant__ KernelArgs<float> A, const __grid_consta
             if (pass == 1) {
                 if (!need_reset) break;
                 e.episode += 1;
-                spawn(A, e, key, i);
-                ur = draw_raw(key, (uint32_t)e.episode, 0u, HLYNR_BLK_UNI);
+                ur = spawn(A, e, key, i);
             }
             observe<R, FT_GENERIC, true>(A, e, key, ur, i, A.g_row, A.o_row, pre, ob);  // i < n_pad: padded lanes touch only padding
             if (pass == 0) {
@@ -1833,8 +1845,7 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, 4) step_kernel_pipe(const __grid_
             if (pass == 1) {
                 if (!need_reset) break;
                 e.episode += 1;
-                spawn(A, e, key, i);
-                ur = draw_raw(key, (uint32_t)e.episode, 0u, HLYNR_BLK_UNI);
+                ur = spawn(A, e, key, i);
             }
             observe<R, F, true>(A, e, key, ur, i, A.g_row, A.o_row, pre, ob);   // pass 1: steps == 0 < delay, `pre` is not read
             if (pass == 0) {
@@ -1849,16 +1860,9 @@ __global__ void __launch_bounds__(HLYNR_BLOCK, 4) step_kernel_pipe(const __grid_
                 }
                 account_episodes(A, active, done, e, t);
                 if (done && active && A.io.done_records) {
-                    const int32_t slot = append_done_record(A.io.done_records, A.io.done_counter, A.io.done_cap, (int32_t)i, e.steps,
-                                           info_flags(e.flags, t.intercepted, t.hit, t.clamped, ob.onboard_det, ob.ground_det, t.fuze) |
-                                               (t.terminated ? HLYNR_DONE_TERMINATED : 0u) | (t.truncated ? HLYNR_DONE_TRUNCATED : 0u),
-                                           t.distance, (float)e.min_d, (float)e.fuel, (float)e.fuel_used, (float)e.ep_ret, (float)e.ipx,
-                                           (float)e.ipy, (float)e.ipz, (float)e.mpx, (float)e.mpy, (float)e.mpz, ob.row);
-                    if (slot >= 0) {
-                        HlynrDoneRecord* r = A.io.done_records + slot;
-                        volley_info(A, i, e.flags, t.distance, t.intercepted, &r->missiles_intercepted, &r->missiles_remaining,
-                                    r->missile_min_distances);
-                    }
+                    record_done<R>(A, i, e.steps, e.flags, t.terminated, t.truncated, t.intercepted, t.hit, t.clamped, ob.onboard_det,
+                                   ob.ground_det, t.fuze, t.distance, (float)e.min_d, (float)e.fuel, (float)e.fuel_used, (float)e.ep_ret,
+                                   (float)e.ipx, (float)e.ipy, (float)e.ipz, (float)e.mpx, (float)e.mpy, (float)e.mpz, ob.row);
                 }
                 need_reset = done && A.auto_reset;
                 if (need_reset && active && A.io.terminal_obs) copy_obs_row(ob.row, A.io.terminal_obs + i * HLYNR_OBS_DIM);
@@ -1891,8 +1895,7 @@ template <typename R> __global__ void __launch_bounds__(HLYNR_BLOCK) reset_kerne
     ob.row = tiles[warp] + lane * HLYNR_OBS_DIM;
     ob.emit = true;
     e.episode += 1;
-    spawn(A, e, key, i);
-    const uint4 ur = draw_raw(key, (uint32_t)e.episode, 0u, HLYNR_BLK_UNI);
+    const uint4 ur = spawn(A, e, key, i);
     observe<R, FT_GENERIC_MODES>(A, e, key, ur, i, A.g_row, A.o_row, RingPre<R>{}, ob);
     store_env(A, i, e);
     if (A.io.obs) copy_obs_row(ob.row, A.io.obs + i * HLYNR_OBS_DIM);
