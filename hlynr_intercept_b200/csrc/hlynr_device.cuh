@@ -843,9 +843,21 @@ __device__ __noinline__ SpawnOut spawn_values(const KernelArgs<R>& A, uint32_t c
         double ax = -fy, ay = fx;
         double al = sqrt(ax * ax + ay * ay + 0.0);
         if (al > 1e-6) {
+            // h = acos(fz) / 2 without the transcendentals: cos h = sqrt((1 + fz) / 2), sin h = sqrt((1 - fz) / 2), and the
+            // cancelling one of the two comes from sin(2h) = al instead (al = |f x z| = sin(acos fz) for the unit vector f).
+            // (f is a float32 vector divided by its float32 norm, so |f| = 1 only to ~1e-7 and the two forms differ by that
+            // much: far below the fp32 build's tolerance, visible at the fp64 build's, which therefore keeps acos / sin / cos.)
             ax /= al; ay /= al;
-            double h = acos(clip(fz, -1.0, 1.0)) / 2.0, sh = sin(h);
-            o.qw = (float)cos(h); o.qx = (float)(ax * sh); o.qy = (float)(ay * sh); o.qz = (float)(0.0 * sh);
+            const double cz = clip(fz, -1.0, 1.0);
+            double sh, ch;
+            if constexpr (std::is_same<R, float>::value) {
+                if (cz >= 0.0) { ch = sqrt((1.0 + cz) * 0.5); sh = al / (2.0 * ch); }
+                else { sh = sqrt((1.0 - cz) * 0.5); ch = al / (2.0 * sh); }
+            } else {
+                const double h = acos(cz) / 2.0;
+                sh = sin(h); ch = cos(h);
+            }
+            o.qw = (float)ch; o.qx = (float)(ax * sh); o.qy = (float)(ay * sh); o.qz = 0.f;
         } else if (!(fz > 0)) { o.qw = 0.f; o.qx = 1.f; }  // anti-aligned (quirk Q9: aligned -> identity)
     }
     o.mx = mx; o.my = my; o.mz = mz; o.ix = ix; o.iy = iy; o.iz = iz;
@@ -1240,7 +1252,19 @@ HD double warp_sum(double v) {
 
 __device__ __noinline__ void account_episodes_slow(double* stats, bool d, float ep_ret, int steps, float min_d, float dist,
                                                    int cause, bool intercepted, bool terminated) {
-    double v[12];
+    double* slot = stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS;
+    if (__popc(__ballot_sync(0xffffffffu, d)) <= 4) {   // the usual case is ONE finished env in the warp: its lane adds its own
+        if (d) {                                        // terms (fire-and-forget reductions) instead of 12 warp-wide double sums
+            atomicAdd(slot + 0, 1.0);
+            if (intercepted) atomicAdd(slot + 1, 1.0);
+            atomicAdd(slot + 2, (double)ep_ret); atomicAdd(slot + 3, (double)steps);
+            atomicAdd(slot + 4, (double)min_d); atomicAdd(slot + 5, (double)dist);
+            if (cause >= 0) atomicAdd(slot + 6 + cause, 1.0);
+            if (!terminated) atomicAdd(slot + 11, 1.0);
+        }
+        return;
+    }
+    double v[12];   // many envs of the warp finished together (e.g. a time-out of envs that are still in phase): one atomic per warp
     v[0] = d ? 1.0 : 0.0;
     v[1] = (d && intercepted) ? 1.0 : 0.0;
     v[2] = d ? (double)ep_ret : 0.0;
@@ -1250,7 +1274,6 @@ __device__ __noinline__ void account_episodes_slow(double* stats, bool d, float 
 #pragma unroll
     for (int c = 0; c < 5; ++c) v[6 + c] = (d && cause == c) ? 1.0 : 0.0;
     v[11] = (d && !terminated) ? 1.0 : 0.0;
-    double* slot = stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS;
 #pragma unroll
     for (int k = 0; k < 12; ++k) {
         double s = warp_sum(v[k]);
