@@ -1250,10 +1250,13 @@ HD double warp_sum(double v) {
     return v;
 }
 
+// kDirect = false keeps the pure warp reduction: the v2.0-off kernel runs under a 96-register cap (5 CTAs per SM) and the
+// register needs of the direct-atomics callee cost it 60 B of spills in the hot path (86 -> 100 us per launch).
+template <bool kDirect>
 __device__ __noinline__ void account_episodes_slow(double* stats, bool d, float ep_ret, int steps, float min_d, float dist,
                                                    int cause, bool intercepted, bool terminated) {
     double* slot = stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS;
-    if (__popc(__ballot_sync(0xffffffffu, d)) <= 4) {   // the usual case is ONE finished env in the warp: its lane adds its own
+    if (kDirect && __popc(__ballot_sync(0xffffffffu, d)) <= 4) {   // the usual case is ONE finished env in the warp: its lane adds its own
         if (d) {                                        // terms (fire-and-forget reductions) instead of 12 warp-wide double sums
             atomicAdd(slot + 0, 1.0);
             if (intercepted) atomicAdd(slot + 1, 1.0);
@@ -1281,7 +1284,7 @@ __device__ __noinline__ void account_episodes_slow(double* stats, bool d, float 
     }
 }
 
-template <typename R>
+template <typename R, bool kDirect = true>
 HD void account_episodes(const KernelArgs<R>& A, bool active, bool done, const Env<R>& e, const TickOut& t) {
     // called by all lanes of the warp; finished episodes are rare (~1 per 1000 ticks per env)
     if (__ballot_sync(0xffffffffu, active && done) == 0u) return;
@@ -1294,7 +1297,7 @@ HD void account_episodes(const KernelArgs<R>& A, bool active, bool done, const E
         else if (e.mpz <= R(0)) cause = 3;
         else cause = 4;
     }
-    account_episodes_slow(A.io.stats, d, (float)e.ep_ret, e.steps, (float)e.min_d, t.distance, cause, t.intercepted,
+    account_episodes_slow<kDirect>(A.io.stats, d, (float)e.ep_ret, e.steps, (float)e.min_d, t.distance, cause, t.intercepted,
                           t.terminated);
 }
 
@@ -1530,7 +1533,7 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
                     if (A.has_info) write_info(A, i, e, t, ob);
                 }
                 rsum += t.reward;
-                account_episodes(A, active, done, e, t);
+                account_episodes<R, !(F == FT_V2OFF && sizeof(R) == 4)>(A, active, done, e, t);
                 if (!kRollout && done && active && A.io.done_records) {
                     record_done<R>(A, i, e.steps, e.flags, t.terminated, t.truncated, t.intercepted, t.hit, t.clamped, ob.onboard_det,
                                    ob.ground_det, t.fuze, t.distance, (float)e.min_d, (float)e.fuel, (float)e.fuel_used, (float)e.ep_ret,
