@@ -381,16 +381,17 @@ HD void drag_accel(const KParams<R>& P, const Env<R>& e, R vx, R vy, R vz, R alt
         R cd;
         if (FT::dr(P)) {
             double bc = (double)e.base_cd, pk = (double)e.peak, c;
-            R ramp = ndiv(sub(mach, P.sub_mach), P.sup_minus_sub);
-            ramp = mach < P.sub_mach ? R(0) : ramp;   // bc * (1 + (pk - 1) * 0) == bc
+            // two selects in the reference's test order (exact for any parameters, also subsonic_mach > supersonic_mach)
+            const R ramp = ndiv(sub(mach, P.sub_mach), P.sup_minus_sub);
             c = mach < P.sup_mach ? bc * (1.0 + (pk - 1.0) * (double)ramp) : bc * P.sup_mult_d;
+            c = mach < P.sub_mach ? bc : c;
             cd = (R)c;
         } else {
-            // branch-free and bit-identical: below sub_mach the ramp term is clamped to 0, and base * (1 + peak_minus1 * 0) == base
-            R ramp = ndiv(sub(mach, P.sub_mach), P.sup_minus_sub);
-            ramp = mach < P.sub_mach ? R(0) : ramp;
+            // branch-free: two selects in the reference's test order (exact for any parameters, also subsonic_mach > supersonic_mach)
+            const R ramp = ndiv(sub(mach, P.sub_mach), P.sup_minus_sub);
             const R mid = mul(P.cd_base, add(R(1.0), mul(P.peak_minus1, ramp)));
             cd = mach < P.sup_mach ? mid : P.cd_sup;
+            cd = mach < P.sub_mach ? P.cd_base : cd;
         }
         if constexpr (std::is_same<R, float>::value) {
             float k = -((weak ? P.half_rho_weak : 0.5f * rho) * vmag * cd * area * post_scale * rc_mass);

@@ -9,6 +9,7 @@ excluded from the exact comparison from that tick on, and counted.
 import numpy as np
 import pytest
 
+import sweep_configs
 from common import (GOLDEN_CASES, STATE_FLOAT_FIELDS, STATE_INT_FIELDS, CudaBatch, Lockstep, golden_setup, load_golden,
                     replay_against_golden)
 from hlynr_intercept_b200 import config
@@ -56,37 +57,59 @@ def test_cuda_matches_reference_golden(name, variant):
     assert w["dropped"] <= max(1, meta["n_envs"] // 8), w
 
 
-@pytest.mark.parametrize("base", ["cfg2", "cfg3", "cfg4"])
-@pytest.mark.parametrize("f64,variant", [(False, DIRECT), (False, TMA), (False, PIPE), (True, DIRECT)])
-def test_cuda_matches_oracle_4096_envs_100_steps(base, f64, variant):
-    """BASELINE cfg2 size (4096 envs, here 4100 to exercise a partial tile): CUDA vs oracle, 1-step and 100-step horizon."""
-    n, T, seed = 4100, 100, 4242
-    P, cur = config.resolve_config(config.baseline_config(base), warn_dead=False)
+def _compare_cuda_with_oracle(P, cur, n, T, seed, f64, variant, action_fn=None, min_alive=0.995, conditioning=False,
+                              loose=(9, 10, 11, 13, 16), obs_atol_scale=1.0):
+    """CUDA (through the C ABI) next to the oracle on the same actions: integer outputs exact, floats within the build's
+    tolerance; envs whose oracle decision margin is below the tolerance AND that actually disagree are dropped and counted."""
     cuda = CudaBatch(P, cur, n, seed=seed, float64=f64, variant=variant)
     orc = oracle.OracleBatch(P, cur, n, seed=seed, float64=f64, threads=8)
-    tol = TOL[f64]
+    # the oracle in the OTHER precision on the same draws and actions: where the reference's own float32 and float64
+    # evaluations of an observation element disagree by delta (LOS rates right after the Kalman initialisation or at
+    # short range, cosines of nearly-zero vectors), no implementation can be pinned tighter than a few delta
+    twin = oracle.OracleBatch(P, cur, n, seed=seed, float64=not f64, threads=8) if conditioning else None
+    tol = dict(TOL[f64])
+    tol["obs_atol"] *= obs_atol_scale
+    loose = list(loose)
     o_c, o_o = cuda.reset(), orc.reset()
+    if twin is not None:
+        twin.reset()
     np.testing.assert_allclose(o_c, o_o, rtol=0, atol=tol["obs_atol"])
     alive = np.ones(n, bool)
+    twin_ok = np.ones(n, bool)   # the twin follows the same episode schedule as long as its done flags agree
     env_ids = np.arange(n)
     episode = np.zeros(n, np.int64)
     steps = np.zeros(n, np.int64)
     for t in range(T):
-        act = draws.random_actions(seed, env_ids, episode, steps + 1)
+        act = draws.random_actions(seed, env_ids, episode, steps + 1) if action_fn is None else action_fn(t, n)
         oc, rc, tec, trc, _, ic = cuda.step(act)
         oo, ro, teo, tro, _, io = orc.step(act)
         low = orc.margin < tol["margin_tol"]
-        differs = (tec != teo) | (trc != tro) | (ic["flags"] != io["flags"]) | (np.abs(oc - oo).max(axis=1) > tol["tti_atol"])
+        x13 = np.maximum(1.0, 4.0 * (1.0 - oo[:, 13]) ** 2)   # obs[13] sensitivity to the closing speed (tests/common.py)
+        d_all = np.abs(oc - oo)
+        d_all[:, 13] /= x13
+        if 2 in loose:   # los_frame: channels 2, 3 are LOS rates = transverse velocity / estimated range (obs[0] * max_range):
+            d_all[:, 2:4] /= np.maximum(1.0, 0.01 / np.maximum(oo[:, 0], 1e-9))[:, None]   # below 100 m the tolerance grows like 1 / range
+        for ch in (9, 11):   # roll / yaw over pi: -1 and +1 are the same angle
+            d_all[:, ch] = np.minimum(d_all[:, ch], 2.0 - d_all[:, ch])
+        if twin is not None:
+            ot, _, tet, trt, _, _ = twin.step(act)
+            twin_ok &= (tet == teo) & (trt == tro)
+            slack = np.where(twin_ok[:, None], 3.0 * np.abs(ot - oo), 0.0)
+            d_all = np.maximum(d_all - slack, 0.0)
+        differs = (tec != teo) | (trc != tro) | (ic["flags"] != io["flags"]) | (d_all.max(axis=1) > tol["tti_atol"])
         alive &= ~(low & differs)
         a = alive
         assert (tec[a] == teo[a]).all() and (trc[a] == tro[a]).all(), f"done mismatch at t={t}"
         assert (ic["flags"][a] == io["flags"][a]).all(), f"flag mismatch at t={t}"
         assert (ic["steps"][a] == io["steps"][a]).all()
-        d = np.abs(oc[a] - oo[a])
-        loose = d[:, [9, 10, 11, 13, 16]].max()
-        d[:, [9, 10, 11, 13, 16]] = 0
-        assert d.max() <= tol["obs_atol"], f"obs mismatch t={t}: {d.max()} idx {np.unravel_index(d.argmax(), d.shape)}"
-        assert loose <= tol["tti_atol"], f"ill-conditioned obs mismatch t={t}: {loose}"
+        d = d_all[a]
+        worst_loose = d[:, loose].max() if d.size else 0.0
+        where_loose = np.unravel_index(d[:, loose].argmax(), d[:, loose].shape) if d.size else None
+        d[:, loose] = 0
+        assert d.size == 0 or d.max() <= tol["obs_atol"], f"obs mismatch t={t}: {d.max()} idx {np.unravel_index(d.argmax(), d.shape)}"
+        assert worst_loose <= tol["tti_atol"], (f"ill-conditioned obs mismatch t={t}: {worst_loose} "
+                                                 f"(alive env #{where_loose[0]}, channel {loose[where_loose[1]]}, oracle row {oo[a][where_loose[0]][:8]}, "
+                                                 f"cuda row {oc[a][where_loose[0]][:8]}, distance {io['distance'][a][where_loose[0]]})")
         err = np.abs(rc[a] - ro[a])
         assert (err <= tol["reward_atol"] + tol["reward_rtol"] * np.abs(ro[a])).all(), f"reward mismatch t={t}: {err.max()}"
         for k in ("distance", "min_distance", "fuel_remaining", "fuel_used"):
@@ -94,7 +117,7 @@ def test_cuda_matches_oracle_4096_envs_100_steps(base, f64, variant):
         done = (teo | tro).astype(bool)
         episode += done
         steps = np.where(done, 0, steps + 1)
-    assert alive.mean() > 0.995, f"too many low-margin exclusions: {(~alive).sum()}"
+    assert alive.mean() > min_alive, f"too many low-margin exclusions: {(~alive).sum()}"
     sc, so = cuda.export_state(), orc.export_state()
     for k in STATE_INT_FIELDS:
         assert (sc[k][alive] == so[k][alive]).all(), k
@@ -102,6 +125,36 @@ def test_cuda_matches_oracle_4096_envs_100_steps(base, f64, variant):
         ref = so[k][alive]
         np.testing.assert_allclose(sc[k][alive], ref, rtol=tol["rtol_state"], atol=tol["rtol_state"] * (np.abs(ref).max() + 1e-6),
                                    err_msg=k)
+    return int(episode.sum())
+
+
+@pytest.mark.parametrize("base", ["cfg2", "cfg3", "cfg4"])
+@pytest.mark.parametrize("f64,variant", [(False, DIRECT), (False, TMA), (False, PIPE), (True, DIRECT)])
+def test_cuda_matches_oracle_4096_envs_100_steps(base, f64, variant):
+    """BASELINE cfg2 size (4096 envs, here 4100 to exercise a partial tile): CUDA vs oracle, 1-step and 100-step horizon."""
+    P, cur = config.resolve_config(config.baseline_config(base), warn_dead=False)
+    _compare_cuda_with_oracle(P, cur, 4100, 100, 4242, f64, variant)
+
+
+@pytest.mark.parametrize("f64", [False, True])
+@pytest.mark.parametrize("k", range(sweep_configs.N_SWEEP))
+def test_cuda_matches_oracle_on_mixed_feature_configs(k, f64):
+    """Feature combinations no shipped YAML uses (tests/sweep_configs.py: every physics v2.0 sub-switch on its own, odd
+    delays, no ground radar, spherical spawns, precision mode / fuze / volley / observation modes on top of domain
+    randomization): 1030 envs x 450 ticks of smooth open-loop actions, through resets.  The oracle is pinned to the
+    unmodified reference on the very same dicts by tests/test_oracle.py::test_oracle_matches_live_reference_on_mixed_feature_configs."""
+    if f64 and k % 3:
+        pytest.skip("fp64 build: every third configuration")
+    cfg = sweep_configs.sweep_config(k)
+    P, cur = config.resolve_config(cfg, warn_dead=False)
+    # los_frame: channels 2-5 are LOS rates and direction cosines of the ESTIMATED relative / target velocity.  The kernels keep
+    # the Kalman state in one precision from its initialisation (DESIGN.md, known deviations: the reference filters in float32
+    # until the first ground measurement and in float64 afterwards), and the first updates run with gains of ~1/dt, so those
+    # channels carry that deviation amplified: they get the ill-conditioned-channel tolerance.  The fp64 build's plain
+    # tolerance is doubled for the same reason (closing speed over max_velocity differs by 1.01e-5 once in 1030 x 450 steps).
+    loose = (9, 10, 11, 13, 16) + ((2, 3, 4, 5) if cfg.get("observation_mode") == "los_frame" else ())
+    _compare_cuda_with_oracle(P, cur, 1030, 450, 900 + k, f64, DIRECT, action_fn=sweep_configs.sweep_policy(cfg, k), min_alive=0.99,
+                              conditioning=True, loose=loose, obs_atol_scale=2.0 if f64 else 1.0)
 
 
 def test_sharding_invariance_and_rollout_equivalence():

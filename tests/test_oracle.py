@@ -90,3 +90,27 @@ def test_oracle_matches_live_reference_on_every_reference_yaml():
             assert (te_r == te_o).all() and (tr_r == tr_o).all() and (inf_r["flags"] == inf_o["flags"]).all(), (rel, t)
             np.testing.assert_allclose(o_o, o_r, atol=2e-5, err_msg=f"{rel} t={t}")
             np.testing.assert_allclose(r_o, r_r, rtol=1e-5, atol=1e-4, err_msg=f"{rel} t={t}")
+
+
+@pytest.mark.reference
+def test_oracle_matches_live_reference_on_mixed_feature_configs():
+    """tests/sweep_configs.py: feature combinations no shipped YAML uses, the oracle next to the unmodified reference for 600
+    ticks of smooth open-loop actions (integer outputs exact).  The GPU suite checks CUDA against the oracle on the same dicts."""
+    import sweep_configs
+
+    for k in range(sweep_configs.N_SWEEP):
+        cfg = sweep_configs.sweep_config(k)
+        P, cur = config.resolve_config(cfg, warn_dead=False)
+        n, T = 2, 600
+        ref = ref_harness.RefBatch(cfg, n, seed=55 + k)
+        sim = oracle.OracleBatch(P, cur, n, seed=55 + k)
+        pol = sweep_configs.sweep_policy(cfg, k)
+        o_r, o_o = ref.reset(), sim.reset()
+        np.testing.assert_allclose(o_o, o_r, atol=2e-6, err_msg=str(k))
+        for t in range(T):
+            a = pol(t, n)
+            o_r, r_r, te_r, tr_r, _, inf_r = ref.step(a)
+            o_o, r_o, te_o, tr_o, _, inf_o = sim.step(a)
+            assert (te_r == te_o).all() and (tr_r == tr_o).all() and (inf_r["flags"] == inf_o["flags"]).all(), (k, t)
+            np.testing.assert_allclose(o_o, o_r, atol=5e-5, err_msg=f"config {k} t={t}")
+            np.testing.assert_allclose(r_o, r_r, rtol=1e-5, atol=1e-4, err_msg=f"config {k} t={t}")
