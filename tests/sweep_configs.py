@@ -8,7 +8,7 @@ import numpy as np
 
 from hlynr_intercept_b200 import config
 
-N_SWEEP = 18
+N_SWEEP = 30
 
 
 def sweep_config(k):
