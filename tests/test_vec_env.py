@@ -235,3 +235,43 @@ def test_outputs_of_a_step_survive_the_next_step():
             assert not np.shares_memory(o_view, obs)
         prev = ((obs, rew, dones, infos), (obs.copy(), rew.copy(), dones.copy(), infos.records.copy()))
     v.close()
+
+
+def test_step_host_with_pageable_and_page_locked_caller_buffers_agree():
+    """hlynr_step_host through the raw C ABI, as INTEGRATION.md binds it: ordinary (pageable) numpy arrays are staged through
+    the handle's pinned buffers, page-locked caller arrays (torch pin_memory) are DMA targets in place; both must return the
+    same bits as the device API.  hlynr_host_done_buffer refuses pageable memory (the kernel stores into that buffer)."""
+    import ctypes as C
+
+    import torch
+
+    from hlynr_intercept_b200 import _lib
+    from hlynr_intercept_b200.sim import HlynrSim
+
+    n = 70001
+    sims = [HlynrSim(config.baseline_config("cfg4"), n_envs=n, seed=31, warn_dead=False) for _ in range(3)]
+    for s in sims:
+        s.reset()
+        s.rollout(700, None)
+    L = sims[0].L
+    p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+    page = [np.zeros((n, 26), np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint8), np.zeros(n, np.uint8)]
+    pin_t = [torch.zeros((n, 26), dtype=torch.float32).pin_memory(), torch.zeros(n, dtype=torch.float32).pin_memory(),
+             torch.zeros(n, dtype=torch.uint8).pin_memory(), torch.zeros(n, dtype=torch.uint8).pin_memory(),
+             torch.zeros(n, dtype=torch.uint8).pin_memory()]
+    pin = [t.numpy() for t in pin_t]
+    with pytest.raises(_lib.HlynrError):
+        _lib.check(L.hlynr_host_done_buffer(sims[2].h, p(np.zeros(n, np.uint8))))
+    _lib.check(L.hlynr_host_done_buffer(sims[2].h, p(pin[4])))
+    rng = np.random.default_rng(9)
+    for t in range(60):
+        a = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        o, r, te, tr, _, _ = sims[0].step(torch.as_tensor(a).cuda())
+        _lib.check(L.hlynr_step_host(sims[1].h, p(a), p(page[0]), p(page[1]), p(page[2]), p(page[3]), None, 1))
+        _lib.check(L.hlynr_step_host(sims[2].h, p(a), p(pin[0]), p(pin[1]), p(pin[2]), p(pin[3]), None, 1))
+        want = (o.cpu().numpy(), r.cpu().numpy(), te.cpu().numpy(), tr.cpu().numpy())
+        for k in range(4):
+            assert (page[k] == want[k]).all() and (pin[k] == want[k]).all(), (t, k)
+        assert (pin[4] == (want[2] | want[3])).all(), t
+    for s in sims:
+        s.close()
