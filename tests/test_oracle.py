@@ -69,12 +69,12 @@ def _reference_yaml_files():
 def test_oracle_matches_live_reference_on_every_reference_yaml():
     """Every YAML the reference ships (configs/*.yaml, configs/hrl/*.yaml, configs/scenarios/*.yaml, config.yaml), merged
     the way scripts/train_hrl_pretrain.py:270-338 merges it: the resolver accepts it and the oracle follows the unmodified
-    reference through the first interceptions / terminations (integer outputs exact)."""
+    reference for 500 ticks (integer outputs exact; the yaml_* fixtures carry each configuration through its terminations)."""
     from oracle import gen_golden
 
     files = _reference_yaml_files()
     assert len(files) >= 36
-    n, T, seed = 2, 900, 77
+    n, T, seed = 2, 500, 77
     for rel in files:
         cfg = gen_golden.reference_yaml_env(rel)
         P, cur = config.resolve_config(cfg, warn_dead=False)
@@ -94,14 +94,14 @@ def test_oracle_matches_live_reference_on_every_reference_yaml():
 
 @pytest.mark.reference
 def test_oracle_matches_live_reference_on_mixed_feature_configs():
-    """tests/sweep_configs.py: feature combinations no shipped YAML uses, the oracle next to the unmodified reference for 600
+    """tests/sweep_configs.py: feature combinations no shipped YAML uses, the oracle next to the unmodified reference for 400
     ticks of smooth open-loop actions (integer outputs exact).  The GPU suite checks CUDA against the oracle on the same dicts."""
     import sweep_configs
 
     for k in range(sweep_configs.N_SWEEP):
         cfg = sweep_configs.sweep_config(k)
         P, cur = config.resolve_config(cfg, warn_dead=False)
-        n, T = 2, 600
+        n, T = 2, 400
         ref = ref_harness.RefBatch(cfg, n, seed=55 + k)
         sim = oracle.OracleBatch(P, cur, n, seed=55 + k)
         pol = sweep_configs.sweep_policy(cfg, k)
