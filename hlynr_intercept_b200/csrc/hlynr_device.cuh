@@ -1489,6 +1489,13 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
     load_env<R, F>(A, ii, e);
     if (!kRollout && A.prefetch_ahead > 0 && i + A.prefetch_ahead < A.lim) prefetch_next_wave<R, F>(A, i + A.prefetch_ahead);
     const RngKey key = make_key(A, A.env_offset + ii);
+    if (!kRollout && Feat<F>::onboard_delay(A.P) && Feat<F>::dr(A.P)) {
+        // domain randomization: the onboard delay is per-env state, so the delayed row is only known once the counter plane has
+        // arrived; prefetched here (the tick's first instructions need that plane anyway) instead of read cold deep in observe()
+        int rrow = A.o_row - FLAG_ODELAY(e.flags);
+        if (rrow < 0) rrow += A.P.onb_ring_len;
+        prefetch_l1(A.st.oring + (int64_t)rrow * A.ring_stride + i);
+    }
     const int steps = kRollout ? A.k_steps : 1;
     float rsum = 0.f;
     int dcount = 0, locks = 0;
