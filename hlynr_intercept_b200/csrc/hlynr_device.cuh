@@ -1251,8 +1251,9 @@ HD double warp_sum(double v) {
     return v;
 }
 
-// kDirect = false keeps the pure warp reduction: the v2.0-off kernel runs under a 96-register cap (5 CTAs per SM) and the
-// register needs of the direct-atomics callee cost it 60 B of spills in the hot path (86 -> 100 us per launch).
+// kDirect = false is the pure warp reduction.  ptxas negotiates registers across __noinline__ calls: under a 96-register cap
+// (5 CTAs per SM, as the v2.0-off kernel once ran) the register needs of the direct-atomics path cost the CALLER 60 B of
+// hot-path spills (86 -> 100 us per launch); every step kernel now runs at 4 CTAs per SM, where there is room.
 template <bool kDirect>
 __device__ __noinline__ void account_episodes_slow(double* stats, bool d, float ep_ret, int steps, float min_d, float dist,
                                                    int cause, bool intercepted, bool terminated) {
@@ -1476,7 +1477,7 @@ template <typename R, int F> HD void prefetch_ring_reads(const KernelArgs<R>& A,
 // ------------------------------------------------------------------------------------------------
 // step(): one tick of every env + SB3 auto-reset.  kRollout: k fused ticks, state stays in registers.
 template <typename R, bool kRollout, int F>
-__global__ void __launch_bounds__(HLYNR_STEP_BLOCK, ((F == FT_V2OFF && sizeof(R) == 4) ? 5 : 4) * (HLYNR_BLOCK / HLYNR_STEP_BLOCK))
+__global__ void __launch_bounds__(HLYNR_STEP_BLOCK, 4 * (HLYNR_BLOCK / HLYNR_STEP_BLOCK))
 step_kernel(const __grid_constant__ KernelArgs<R> A) {
     __shared__ __align__(16) float tiles[HLYNR_STEP_BLOCK / 32][OBS_TILE];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -1541,7 +1542,7 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
                     if (A.has_info) write_info(A, i, e, t, ob);
                 }
                 rsum += t.reward;
-                account_episodes<R, !(F == FT_V2OFF && sizeof(R) == 4)>(A, active, done, e, t);
+                account_episodes<R>(A, active, done, e, t);
                 if (!kRollout && done && active && A.io.done_records) {
                     record_done<R>(A, i, e.steps, e.flags, t.terminated, t.truncated, t.intercepted, t.hit, t.clamped, ob.onboard_det,
                                    ob.ground_det, t.fuze, t.distance, (float)e.min_d, (float)e.fuel, (float)e.fuel_used, (float)e.ep_ret,
