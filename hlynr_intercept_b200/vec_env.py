@@ -210,7 +210,8 @@ class HlynrVecEnv(_VecEnvBase):
 
     def done_records(self):
         """Finished episodes of the last step as a structured array (abi.done_record_numpy_dtype), a view of pinned
-        memory owned by the C library that the next step overwrites."""
+        memory owned by the C library: two buffers alternate, so it stays valid while the next step runs and is
+        overwritten by the step after that."""
         ptr, cnt = C.c_void_p(), C.c_int32()
         _lib.check(self.sim.L.hlynr_done_records_host(self.sim.h, C.byref(ptr), C.byref(cnt)))
         if cnt.value == 0:
