@@ -40,4 +40,6 @@ def test_gpu_arm_line():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == d["config"]["envs_per_gpu"] * 24 and e["d2h_bytes_per_step"] > d["config"]["envs_per_gpu"] * 104
     assert e["value"] < d["value"]   # host buffers and PCIe inside the timed region
-    assert d["cpu_baseline"]["kind"] == "port" and d["clocks"]["sm_max_mhz"] > 0
+    assert d["cpu_baseline"]["kind"] == "port"
+    c = d["clocks"]
+    assert "reasons" in c and (c["sm_max_mhz"] is None or (c["sm_max_mhz"] > 0 and c["sm_mhz"] > 0))   # None only without nvidia-smi
