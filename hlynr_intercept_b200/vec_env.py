@@ -127,7 +127,7 @@ class LazyInfos(collections.abc.Sequence):
 
 class HlynrVecEnv(_VecEnvBase):
     def __init__(self, env_cfg=None, n_envs=1, device=0, seed=1234, env_id_offset=0, precision="fp32", warn_dead=True,
-                 lazy_infos=None, copy_outputs=None):
+                 lazy_infos=None, copy_outputs=None, radar_debug=None):
         self.sim = HlynrSim(env_cfg, n_envs=n_envs, device=device, seed=seed, env_id_offset=env_id_offset,
                             precision=precision, warn_dead=warn_dead)
         self.config = dict(env_cfg or {})
@@ -138,6 +138,8 @@ class HlynrVecEnv(_VecEnvBase):
         # many envs: no per-env Python dict churn unless asked for
         self.lazy_infos = (n > 4096) if lazy_infos is None else bool(lazy_infos)
         self.copy_outputs = (n <= 65536) if copy_outputs is None else bool(copy_outputs)
+        # info['radar_debug'] is a per-env Python dict the reference rebuilds every step for its episode logger: small batches only
+        self.radar_debug = (n <= 64 and not self.lazy_infos) if radar_debug is None else (bool(radar_debug) and not self.lazy_infos)
         L = self.sim.L
         ptrs = [C.c_void_p() for _ in range(5)]
         _lib.check(L.hlynr_pinned_buffers(self.sim.h, *[C.byref(p) for p in ptrs]))
@@ -278,7 +280,31 @@ class HlynrVecEnv(_VecEnvBase):
         if len(rec):
             for i, d in zip(rec["env"].tolist(), self._done_info_dicts(rec, now)):
                 infos[i] = d
+        if self.radar_debug:
+            self._add_radar_debug(infos, f, rec)
         return infos
+
+    def _add_radar_debug(self, infos, f, rec):
+        """info['radar_debug'] (core.py:649-682, consumed by inference.py:546): small batches only, see radar_debug.py."""
+        from . import radar_debug as rd
+
+        P, beam = self.sim.params, self.sim.curriculum.beam_width
+        st = self.sim.export_state()
+        done = set(rec["env"].tolist()) if len(rec) else set()
+        for i in range(self.num_envs):
+            if i in done:
+                continue
+            infos[i]["radar_debug"] = rd.radar_debug(P, beam, st["ipos"][i], st["quat"][i], st["mpos"][i], int(f["steps"][i]),
+                                                     int(f["flags"][i]), self._obs[i], onboard_delay=int(st["onboard_delay"][i]))
+        for k, i in enumerate(rec["env"].tolist() if len(rec) else []):   # terminal step: state from the done record
+            r = rec[k]
+            if P.obs_mode != abi.OBS_WORLD:
+                infos[i]["radar_debug"] = None   # the terminal observation carries no euler angles in body / los frame
+                continue
+            e = r["terminal_obs"][9:12].astype(np.float64) * np.pi
+            infos[i]["radar_debug"] = rd.radar_debug(P, beam, r["interceptor_pos"], None, r["missile_pos"], int(r["steps"]),
+                                                     int(r["flags"]) & 0xff, r["terminal_obs"],
+                                                     forward=rd.forward_from_euler(e[0], e[1], e[2]))
 
     def close(self):
         self.sim.close()
