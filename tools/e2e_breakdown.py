@@ -16,7 +16,7 @@ def t(f, K=30):
     t0 = time.perf_counter()
     for k in range(K): f(k)
     return (time.perf_counter() - t0) / K * 1e3
-for chunks in (4, 8, 16):
+for chunks in (8, 16, 24, 32, 48):
     v.sim.set_option("host_chunks", chunks)
     print(f"chunks {chunks}: C call unpinned actions {t(lambda k: c_call(acts[k % 2])):.2f} ms | C call pinned actions {t(lambda k: c_call(v._act)):.2f} ms | "
           f"venv.step unpinned {t(lambda k: v.step(acts[k % 2])):.2f} ms | venv.step pinned {t(lambda k: v.step(v._act)):.2f} ms", flush=True)
