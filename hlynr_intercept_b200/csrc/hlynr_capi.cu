@@ -855,6 +855,14 @@ static bool is_pinned_host(const void* p) {
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
 }
+// The address the DEVICE uses for a page-locked host buffer the kernel stores into (identical to the host address wherever
+// cudaDevAttrCanUseHostPointerForRegisteredMem holds, which is every platform this library targets, but asked for anyway);
+// nullptr if the buffer is not device-accessible.
+static void* device_view(void* host_ptr) {
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, host_ptr, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return d;
+}
 static int ensure_hostio(hlynr_sim* s) {
     HostIO& h = s->hio;
     if (h.ready) return 0;
@@ -963,6 +971,11 @@ int hlynr_step_host(hlynr_t* s, const float* actions_host, float* obs_host, floa
     struct Restore { hlynr_sim* s; HlynrDoneRecord* r; int32_t* c; int32_t cap;
                      ~Restore() { s->done_records = r; s->done_counter = c; s->done_cap = cap; s->io_done = nullptr; } }
         restore{s, keep_r, keep_c, keep_cap};
+    // reward / terminated / truncated / dones are stored by the kernel: it needs their device-side addresses
+    float* reward_k = (float*)device_view(reward_dst);
+    uint8_t *term_k = (uint8_t*)device_view(term_dst), *trunc_k = (uint8_t*)device_view(trunc_dst);
+    s->io_done = (uint8_t*)device_view(s->io_done);
+    if (!reward_k || !term_k || !trunc_k || !s->io_done) return fail("hlynr_step_host: a page-locked output buffer is not device-accessible");
     static const bool trace = getenv("HLYNR_HOST_TRACE") != nullptr;   // debugging aid: host-side timeline on stderr
     const auto t_begin = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
@@ -985,7 +998,7 @@ int hlynr_step_host(hlynr_t* s, const float* actions_host, float* obs_host, floa
         // (cudaMallocHost memory is device-accessible under unified addressing; coalesced posted PCIe writes, +26 us per
         // 2^20 envs): three small copy-engine transfers per chunk, each with its own fixed latency, disappear and only the
         // observation (104 B per env) rides the copy engine
-        if (step_range(s, first, lim, h.d_actions, h.d_obs, reward_dst, term_dst, trunc_dst, nullptr, info, auto_reset, st)) return 1;
+        if (step_range(s, first, lim, h.d_actions, h.d_obs, reward_k, term_k, trunc_k, nullptr, info, auto_reset, st)) return 1;
         CK(cudaMemcpyAsync(obs_dst + first * 26, h.d_obs + first * 26, (size_t)cnt * 104, cudaMemcpyDeviceToHost, st));
     }
     // done list: after every chunk's kernel; count + the first records in one go on stream 0
