@@ -41,6 +41,8 @@ def load(build_if_missing=True):
 
         try:
             _build.build()
+        except RuntimeError as e:   # nvcc ran and rejected the sources: never fall back to a stale library silently
+            raise HlynrError(f"libhlynr_b200.so is stale and its sources do not compile: {e}") from e
         except Exception as e:  # no nvcc on this box: fall through to the prebuilt library, if any
             if not os.path.exists(SO_PATH):
                 raise HlynrError(f"libhlynr_b200.so is missing and could not be built: {e}") from e
