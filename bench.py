@@ -2,22 +2,28 @@
 """bench.py -- env-steps/s of the batched Hlynr Intercept step on B200 (BASELINE.json metric).
 
 A "step" is one tick (environment.py:605 step + SB3 auto-reset) of every env of the batch = ONE launch of
-the sm_100a step kernel through the C ABI (hlynr_step), actions resident in HBM.
+the sm_100a step kernel through the C ABI (hlynr_step), actions resident in HBM.  The episodes are aged
+(desynchronised by a fused rollout) before the warm-up, so the timed ticks run at the steady-state rate of
+finished episodes and in-kernel auto-resets (`done_episodes_per_step`, `episode_stats`).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4] [--envs-per-gpu 1048576]
   torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, envs sharded by global id, no
                                                            per-step communication; one NCCL all-reduce of the
-                                                           episode-statistics block per rollout)
-  python bench.py --impl reference ...                     (reference arm: the CPU oracle port of the reference
-                                                           step on the box's host cores; the reference itself is
-                                                           Python and cannot travel to the GPU box)
+                                                           episode-statistics block per rollout, inside the
+                                                           timed region)
+  python bench.py --impl reference ...                     (reference arm: the C port of the reference step on all
+                                                           host cores at the full workload size, plus the unmodified
+                                                           Python reference under a SubprocVecEnv clone, bounded)
 
-Prints ONE JSON line (rank 0).  `value` = env-steps/s with inputs resident in HBM; `e2e` = the same metric
-through the numpy VecEnv API (pinned H2D of actions, D2H of obs/reward/dones every step); `roofline` = the
-step kernel against the measured HBM copy bandwidth; `cpu_baseline` = the oracle port on the host cores.
+Prints ONE JSON line (rank 0).  `value` = env-steps/s with inputs resident in HBM (weak scaling: --envs-per-gpu
+envs on every GPU); `strong` = the same for BASELINE cfg4's 2^20 envs IN TOTAL sharded over the GPUs; `configs` =
+BASELINE cfg2 at 4096 envs and cfg3 at 262144 envs; `e2e` = the metric through the numpy VecEnv API (pinned H2D of
+actions, D2H of obs/reward/dones every step); `roofline` = the step kernel against the measured HBM copy bandwidth;
+`cpu_baseline` = the C port and the Python reference on the host cores.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -34,9 +40,23 @@ ALGO_BYTES = {"cfg2": 526, "cfg3": 630, "cfg3_radar": 630, "cfg4": 630, "cfg1": 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
+def layout_bytes(workload, precision="fp32"):
+    """Bytes per env-step the kernel's OWN layout moves: state planes read + written, one delay-ring
+    slot read + written per sensor, actions in, obs / reward / terminated / truncated out."""
+    r = 4 if precision == "fp32" else 8
+    v2 = workload in ("cfg1", "cfg3", "cfg3_radar", "cfg4")
+    dr = workload in ("cfg3", "cfg3_radar")
+    r_planes = 7 if v2 else 6                  # r0-r5 (+ r6 thrust / T0 with thrust lag or DR)
+    f_planes = 3 + (1 if dr else 0)            # quaternion, wind + Ppp, P block + base_cd (+ DR peak)
+    state = r_planes * 4 * r + f_planes * 16 + 16          # + the counter plane i0
+    rings = 2 * 4 * r + (16 if v2 else 0)                  # ground slot {rel, q}, {vel, flag}; onboard slot (sensor delay, v2.0)
+    io = 24 + 104 + 4 + 1 + 1
+    return 2 * state + 2 * rings + io
+
+
 def measured_traffic(workload, n):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel from the committed ncu --set full
-    capture (profiles/traffic.json), scaled to n envs; None if no capture matches."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the committed ncu capture of >= 10
+    back-to-back steady-state launches (profiles/traffic.json, which names the capture), scaled to n envs; None if absent."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         t = json.load(open(p))[workload]
@@ -108,60 +128,73 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(workload, seconds=12.0, n_envs=16384, threads=None):
-    """The oracle port (C restatement of the reference step) on the host cores, bounded sample."""
+# ----------------------------------------------------------------------------------------------------------
+# CPU legs
+# ----------------------------------------------------------------------------------------------------------
+def port_steps(workload, n_envs, steps, warmup, threads, seconds=None):
+    """The oracle port (C restatement of the reference step) on `threads` host threads: K steps of n_envs envs, or as many as
+    fit into `seconds`.  Returns (env-steps/s, steps, seconds)."""
     from hlynr_intercept_b200 import config
-    from oracle import draws, oracle
+    from oracle import oracle
 
-    threads = threads or os.cpu_count() or 1
     P, cur = config.resolve_config(config.baseline_config(workload), warn_dead=False)
     sim = oracle.OracleBatch(P, cur, n_envs, seed=1234, threads=threads)
     sim.reset()
     rng = np.random.default_rng(0)
-    acts = [rng.uniform(-1, 1, (n_envs, 6)).astype(np.float32) for _ in range(4)]
-    for k in range(3):
-        sim.step(acts[k % 4], want_info=False)
+    acts = [rng.uniform(-1, 1, (n_envs, 6)).astype(np.float32) for _ in range(2)]
+    for k in range(warmup):
+        sim.step(acts[k % 2], want_info=False)
     t0 = time.perf_counter()
-    steps = 0
-    while time.perf_counter() - t0 < seconds:
-        sim.step(acts[steps % 4], want_info=False)
-        steps += 1
+    done = 0
+    while (done < steps) if seconds is None else (time.perf_counter() - t0 < seconds):
+        sim.step(acts[done % 2], want_info=False)
+        done += 1
     dt = time.perf_counter() - t0
     sim.close()
-    return {"value": n_envs * steps / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
-            "sample": f"{n_envs} envs x {steps} ticks of {workload} ({dt:.1f} s), C oracle port of the reference step "
-                      f"(the reference is Python: ~2.4e3 env-steps/s/core measured in the build container)"}
+    return n_envs * done / dt, done, dt
+
+
+def reference_python(workload, seconds):
+    """The unmodified Python reference under the Pipe clone of SubprocVecEnv (baseline/ref_vecenv.py); None if not staged."""
+    try:
+        from baseline import ref_vecenv
+        from hlynr_intercept_b200 import config
+
+        if not ref_vecenv.available():
+            return {"unavailable": "baseline/_ref/ is not staged (run __graft_entry__.build() where /root/reference exists)"}
+        return ref_vecenv.measure(config.baseline_config(workload), seconds=seconds)
+    except Exception as e:  # the baseline must never take the GPU measurement down with it
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
+def cpu_baseline(workload, seconds=12.0, n_envs=65536, threads=None, ref_seconds=10.0):
+    threads = threads or os.cpu_count() or 1
+    v, steps, dt = port_steps(workload, n_envs, 0, 3, threads, seconds=seconds)
+    out = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
+           "sample": f"{n_envs} envs x {steps} ticks of {workload} ({dt:.1f} s), C oracle port of the reference step on {threads} threads"}
+    if ref_seconds > 0:
+        out["reference_python"] = reference_python(workload, ref_seconds)
+    return out
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation (oracle port) on all host threads, K bounded steps."""
+    """--impl reference: the reference's CPU implementation of the step on all host threads, K steps of the FULL workload
+    (the C port: the Python reference cannot hold 2^20 envs), and the unmodified Python reference as `reference_python`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from hlynr_intercept_b200 import config
-    from oracle import oracle
-
     threads = os.cpu_count() or 1
-    n_envs = args.ref_envs
-    P, cur = config.resolve_config(config.baseline_config(args.workload), warn_dead=False)
-    sim = oracle.OracleBatch(P, cur, n_envs, seed=1234, threads=threads)
-    sim.reset()
-    rng = np.random.default_rng(0)
-    acts = [rng.uniform(-1, 1, (n_envs, 6)).astype(np.float32) for _ in range(4)]
-    for k in range(args.warmup):
-        sim.step(acts[k % 4], want_info=False)
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        sim.step(acts[k % 4], want_info=False)
-    dt = time.perf_counter() - t0
-    v = n_envs * args.steps / dt
+    n_envs = args.ref_envs if args.ref_envs > 0 else args.envs_per_gpu
+    v, steps, dt = port_steps(args.workload, n_envs, args.steps, args.warmup, threads)
+    refpy = reference_python(args.workload, args.ref_python_seconds) if args.ref_python_seconds > 0 else None
     line = {"impl": "reference", "metric": "env-steps/s", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload), "envs_per_step_sample": n_envs,
-                       "actions": "U(-1,1)^6 float32"},
+            "config": {"workload": workload_name(args.workload), "envs_per_gpu": n_envs, "total_envs": n_envs,
+                       "actions": "U(-1,1)^6 float32", "timed_region_s": dt},
             "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                             "sample": f"{n_envs} envs per step (bounded sample of the 2^20-env workload)"},
+                             "sample": f"{n_envs} envs per step x {steps} steps ({dt:.1f} s): C oracle port of the reference step, "
+                                       f"{threads} threads", "reference_python": refpy},
             "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -172,6 +205,119 @@ def workload_name(w):
             "cfg2": "cfg2: medium scenario, physics v2.0 off",
             "cfg3": "cfg3: hard scenario, physics v2.0 on + domain randomization",
             "cfg1": "cfg1: easy scenario"}.get(w, w)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# device legs
+# ----------------------------------------------------------------------------------------------------------
+class Ctx:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+AGE_TICKS = 2000   # fused random-policy ticks before the warm-up: every env has finished >= 1 episode (they last 800-1600 ticks)
+
+
+def make_aged_sim(ctx, workload, n, first, precision, seed=1234):
+    from hlynr_intercept_b200 import config
+    from hlynr_intercept_b200.sim import HlynrSim
+
+    torch = ctx.torch
+    sim = HlynrSim(config.baseline_config(workload), n_envs=n, device=ctx.local_rank, seed=seed, env_id_offset=first,
+                   precision=precision, warn_dead=False)
+    sim.reset()
+    sim.rollout(AGE_TICKS, None, want_obs=False)
+    g = torch.Generator(device=ctx.dev)
+    g.manual_seed(seed + first)
+    pool = [(torch.rand(n, 6, device=ctx.dev, generator=g) * 2 - 1).contiguous() for _ in range(4)]  # U(-1,1)^6 in HBM
+    return sim, pool
+
+
+def timed_ticks(ctx, sim, pool, K, W, collective=True, graph=False):
+    """W warm-up ticks, then K timed ticks bracketed by barrier + synchronize, CUDA events on the launching stream; the
+    rollout's one statistics all-reduce is inside the timed region.  Returns a dict (times are this rank's; max over ranks too)."""
+    torch, dist = ctx.torch, ctx.dist
+    sg = None
+    T = 0
+    if graph:
+        T = math.lcm(sim.ring_period(), len(pool))
+        while sim.tick_count() % sim.ring_period():     # captures start on a ring-period boundary
+            sim.step(pool[0], want_terminal_obs=False)
+        sg = sim.capture_steps([pool[k % len(pool)] for k in range(T)])
+    for k in range(W):
+        sim.step(pool[k % 4], want_terminal_obs=False)
+    if sg is not None:
+        while sim.tick_count() % sim.ring_period() != sg.phase:
+            sim.step(pool[0], want_terminal_obs=False)
+        sg.replay()
+    stats_t = sim.stats_tensor()
+    if ctx.world > 1 and collective:
+        dist.all_reduce(stats_t)  # warm NCCL
+    sim.stats(zero_after=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = sim.launch_count()
+    sync = ctx.barrier if collective else torch.cuda.synchronize   # single-rank legs must not enter a collective barrier
+    sync()
+    t0 = time.perf_counter()
+    e0.record()
+    done = 0
+    if sg is not None:
+        while done + T <= K:
+            sg.replay()
+            done += T
+    for k in range(done, K):
+        sim.step(pool[k % 4], want_terminal_obs=False)
+    t_issue = time.perf_counter() - t0
+    stats_t = sim.stats_tensor()  # one stats all-reduce per rollout (NVLink); tiny, latency-bound
+    if ctx.world > 1 and collective:
+        dist.all_reduce(stats_t)
+    e1.record()
+    sync()
+    t1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    return {"ms": ms, "ms_max": ctx.max_over_ranks(ms) if collective else ms, "launches": sim.launch_count() - launches0,
+            "stats": stats_t.cpu().numpy().tolist(), "window": (t0, t1), "host_issue_ms": t_issue * 1e3,
+            "graph_ticks": T if sg is not None else 0}
+
+
+def config_line(ctx, workload, n, K, W, precision, peak):
+    """One BASELINE configuration at its own size on this rank's GPU (no collective): eager launches and CUDA-graph replay."""
+    sim, pool = make_aged_sim(ctx, workload, n, 0, precision, seed=777)
+    r = timed_ticks(ctx, sim, pool, K, W, collective=False)
+    rg = timed_ticks(ctx, sim, pool, K, W, collective=False, graph=True)
+    sim.close()
+    us, us_g = r["ms"] / K * 1e3, rg["ms"] / K * 1e3
+    best = min(us, us_g)
+    lb = layout_bytes(workload, precision)
+    ws_mb = n * lb / 1e6
+    return {"workload": workload_name(workload), "envs": n, "steps": K, "us_per_tick_eager": us, "us_per_tick_graph": us_g,
+            "graph_ticks_per_replay": rg["graph_ticks"], "host_issue_us_per_tick_eager": r["host_issue_ms"] / K * 1e3,
+            "value": n / (best * 1e-6), "unit": "env-steps/s", "done_episodes_per_step": r["stats"][0] / K,
+            "roofline_frac_contract": n * ALGO_BYTES[workload] / (best * 1e-6) / 1e9 / peak,
+            "roofline_frac_layout": n * lb / (best * 1e-6) / 1e9 / peak,
+            "note": (f"per-tick working set {ws_mb:.1f} MB " + ("fits the 126 MB L2: the tick is latency-bound, the HBM roofline is not the binding one"
+                                                               if ws_mb < 100 else "exceeds the 126 MB L2"))}
 
 
 def main():
@@ -185,8 +331,11 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--ref-envs", type=int, default=16384)
+    ap.add_argument("--ref-python-seconds", type=float, default=10.0, help="Python-reference SubprocVecEnv sample (0 = skip)")
+    ap.add_argument("--ref-envs", type=int, default=0, help="--impl reference: envs per step (0 = the workload's --envs-per-gpu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg2@4096 / cfg3@262144 block")
+    ap.add_argument("--strong-total", type=int, default=1 << 20, help="total envs of the strong-scaling block (0 = skip)")
     ap.add_argument("--fused", type=int, default=64, help="k of the extra fused-rollout measurement (0 = skip)")
     ap.add_argument("--rollout-steps", type=int, default=24, help="n_steps of the extra on-device PPO rollout-collection measurement (0 = skip)")
     ap.add_argument("--rollout-envs", type=int, default=131072)
@@ -196,67 +345,29 @@ def main():
         run_reference_arm(args)
         return
 
-    import torch
-    import torch.distributed as dist
-
+    ctx = Ctx()
+    torch, dist = ctx.torch, ctx.dist
+    from hlynr_intercept_b200 import config, dist as hdist
     from hlynr_intercept_b200.sim import HlynrSim
     from hlynr_intercept_b200.vec_env import HlynrVecEnv
-    from hlynr_intercept_b200 import config
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    world, rank, local_rank, dev = ctx.world, ctx.rank, ctx.local_rank, ctx.dev
+    barrier = ctx.barrier
     n = args.envs_per_gpu
     K, W = args.steps, max(args.warmup, 3)
     env_cfg = config.baseline_config(args.workload)
-    sim = HlynrSim(env_cfg, n_envs=n, device=local_rank, seed=1234, env_id_offset=rank * n, precision=args.precision,
-                   warn_dead=False)
-    sim.reset()
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    pool = [(torch.rand(n, 6, device=dev, generator=g) * 2 - 1).contiguous() for _ in range(4)]  # U(-1,1)^6 in HBM
+    peak, peak_src = measured_peak()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for k in range(W):
-        sim.step(pool[k % 4], want_terminal_obs=False)
-    stats_t = sim.stats_tensor()
-    if world > 1:
-        dist.all_reduce(stats_t)  # warm NCCL
-    sim.stats(zero_after=True)
-    barrier()
+    # ---- headline: weak scaling, n envs per GPU, steady state ---------------------------------------------------------------
+    sim, pool = make_aged_sim(ctx, args.workload, n, rank * n, args.precision)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = sim.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_region0 = time.perf_counter()
-    e0.record()
-    for k in range(K):
-        sim.step(pool[k % 4], want_terminal_obs=False)
-    e1.record()
-    stats_t = sim.stats_tensor()  # one stats all-reduce per rollout (NVLink); tiny, latency-bound
-    if world > 1:
-        dist.all_reduce(stats_t)
-    barrier()
-    t_region1 = time.perf_counter()
-    step_ms_total = e0.elapsed_time(e1)
-    launches = sim.launch_count() - launches0   # the timed region's launches (read before any clock probe)
-    tmax = torch.tensor([step_ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms = float(tmax.item())
-    clock_windows, clock_note = [(t_region0, t_region1)], None
-    if rank == 0 and sampler.proc and sampler.count_between(t_region0, t_region1) < 3:
-        # a timed region shorter than a few 20 ms sampler periods: sample over an UNTIMED repeat of the same launches
+    head = timed_ticks(ctx, sim, pool, K, W)
+    total_ms = head["ms_max"]
+    clock_windows, clock_note = [head["window"]], None
+    if rank == 0 and sampler.proc and sampler.count_between(*head["window"]) < 3:
+        # a timed region shorter than a few 20 ms sampler periods: sample over an UNTIMED repeat of the same launches as well
         t_probe0 = time.perf_counter()
         while time.perf_counter() - t_probe0 < 0.4:
             for k in range(50):
@@ -268,9 +379,10 @@ def main():
     if clocks is not None and clock_note:
         clocks["note"] = clock_note
     value = world * n * K / (total_ms * 1e-3)
-    stats_host = stats_t.cpu().numpy().tolist()
+    stats_host = head["stats"]   # all-reduced over the ranks
 
     # extra: fused k-step rollout with the in-kernel random policy (state in registers between ticks)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fused = None
     if args.fused > 0:
         sim.rollout(args.fused, None, want_obs=False)
@@ -281,10 +393,8 @@ def main():
             sim.rollout(args.fused, None, want_obs=False)
         e1.record()
         barrier()
-        tf = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-        fused = {"k": args.fused, "value": world * n * args.fused * reps / (float(tf.item()) * 1e-3), "unit": "env-steps/s",
+        tf = ctx.max_over_ranks(e0.elapsed_time(e1))
+        fused = {"k": args.fused, "value": world * n * args.fused * reps / (tf * 1e-3), "unit": "env-steps/s",
                  "note": "hlynr_rollout: k ticks per launch, in-kernel Philox random policy, obs written once"}
 
     # extra: step + on-device VecFrameStack(4) + VecNormalize, the tensor a policy on the same GPU consumes
@@ -302,153 +412,206 @@ def main():
             pipe.step(pool[k % 4])
         e1.record()
         barrier()
-        tp = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-        ms_post = float(tp.item()) / args.post_steps
+        ms_post = ctx.max_over_ranks(e0.elapsed_time(e1)) / args.post_steps
         post = {"value": world * n / (ms_post * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_post, "n_stack": 4,
                 "note": "hlynr_step writing into the frame ring + hlynr_post_step (stacked, normalised [N,104] output, running "
-                        "mean/var updated every step, stacked terminal observations)",
+                        "mean/var updated every step, stacked terminal observations); SB3 parity of this pipeline is UNPINNED "
+                        "(stable_baselines3 is not importable here; checked against a numpy restatement only)",
                 "algorithmic_bytes_per_env_step_post": 104 + 416 + 416 + 25}
         pipe.close()
+    sim.close()
+    del pool
 
-    # extra: PPO rollout collection fully on the device (SURVEY 8f rank 4 / BASELINE config 5): policy forward (torch MLP
-    # 104 -> 512 -> 512 -> 256, LayerNorm), env step, frame-stack/normalise, TimeLimit bootstrap, GAE; no host
-    # synchronisation inside collect()
+    # ---- strong scaling: BASELINE cfg4's 2^20 envs IN TOTAL, sharded by global id --------------------------------------------
+    strong = None
+    if args.strong_total > 0:
+        first, count = hdist.shard_range(args.strong_total, rank, world)
+        if world == 1 and count == n:
+            strong = {"total_envs": args.strong_total, "envs_per_gpu": count, "value": value, "us_per_launch": total_ms / K * 1e3,
+                      "note": "one GPU: identical to the headline measurement"}
+        else:
+            ssim, spool = make_aged_sim(ctx, args.workload, count, first, args.precision)
+            se = timed_ticks(ctx, ssim, spool, K, W)
+            sg = timed_ticks(ctx, ssim, spool, K, W, graph=True)
+            ssim.close()
+            best = min(se["ms_max"], sg["ms_max"])
+            strong = {"total_envs": args.strong_total, "envs_per_gpu": count, "value": args.strong_total * K / (best * 1e-3),
+                      "unit": "env-steps/s", "us_per_launch_eager": se["ms_max"] / K * 1e3, "us_per_launch_graph": sg["ms_max"] / K * 1e3,
+                      "host_issue_us_per_launch_eager": se["host_issue_ms"] / K * 1e3, "graph_ticks_per_replay": sg["graph_ticks"],
+                      "done_episodes_per_step": se["stats"][0] / K,
+                      "note": "2^20 envs in total through dist.shard_range, max over ranks, the rollout's stats all-reduce inside the "
+                              "timed region; eager = one hlynr_step call per tick from Python, graph = ring-period ticks per CUDA-graph replay"}
+            del spool
+
+    # ---- BASELINE cfg2 at 4096 envs and cfg3 at 262144 envs (rank 0's GPU, no collective) --------------------------------------
+    configs = None
+    if not args.no_configs and rank == 0:
+        kc = max(K, 600)
+        configs = {"cfg2@4096": config_line(ctx, "cfg2", 4096, kc, W, args.precision, peak),
+                   "cfg3@262144": config_line(ctx, "cfg3", 262144, max(K, 200), W, args.precision, peak)}
+    barrier()
+
+    # extra: PPO rollout collection fully on the device (SURVEY 8f rank 4 / BASELINE config 5)
     roll = None
     if args.rollout_steps > 0:
-        from hlynr_intercept_b200.post import HlynrObsPipeline
-        from hlynr_intercept_b200.rollout import DeviceRolloutCollector, GaussianMlpPolicy
+        roll = rollout_leg(ctx, args, env_cfg)
 
-        n_roll = min(n, args.rollout_envs)
-        rsim = HlynrSim(env_cfg, n_envs=n_roll, device=local_rank, seed=4321, env_id_offset=rank * n_roll, precision=args.precision,
-                        warn_dead=False)
-        rpipe = HlynrObsPipeline(rsim, n_stack=4, training=True)
-        torch.manual_seed(rank)
-        torch.backends.cuda.matmul.allow_tf32 = True   # the policy GEMMs are the caller's; TF32 tensor cores as PPO users run them
-        torch.backends.cudnn.allow_tf32 = True
-        pol = GaussianMlpPolicy(104, device=dev)
-        col = DeviceRolloutCollector(rpipe, pol, args.rollout_steps)
-        col.collect()
-        barrier()
-        e0.record()
-        col.collect()
-        e1.record()
-        barrier()
-        te_ = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te_, op=dist.ReduceOp.MAX)
-        graphed = args.rollout_steps % col.graph_period() == 0
-        if graphed:   # the whole collect() as ONE CUDA-graph launch (launch-bound otherwise: ~25 kernels per step)
-            col.capture()
-            col.replay()
-            barrier()
-            e0.record()
-            col.replay()
-            e1.record()
-            barrier()
-        tr_ = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tr_, op=dist.ReduceOp.MAX)
-        # the same loop without the policy network (random actions): what the simulator side costs
-        class _NoPolicy(torch.nn.Module):
-            def __init__(self):
-                super().__init__()
-                self.dummy = torch.nn.Parameter(torch.zeros(1, device=dev))
-
-            def value(self, obs):
-                return obs[:, 0].contiguous()
-
-            def forward(self, obs):
-                a = torch.rand(obs.shape[0], 6, device=obs.device) * 2 - 1
-                return a, obs[:, 0], obs[:, 1]
-
-        col2 = DeviceRolloutCollector(rpipe, _NoPolicy(), args.rollout_steps)
-        col2._started = True
-        col2.obs[col2.T].copy_(col.obs[col.T])
-        col2.collect()
-        barrier()
-        e0.record()
-        col2.collect()
-        e1.record()
-        barrier()
-        tn_ = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tn_, op=dist.ReduceOp.MAX)
-        roll = {"value": world * n_roll * args.rollout_steps / (float(tr_.item()) * 1e-3), "unit": "env-steps/s",
-                "envs_per_gpu": n_roll, "n_steps": args.rollout_steps,
-                "policy": "GaussianMlpPolicy 104->512->512->256 (pi and vf), LayerNorm, fp32 weights, TF32 GEMMs (torch / cuBLAS)",
-                "cuda_graph": bool(graphed), "eager": world * n_roll * args.rollout_steps / (float(te_.item()) * 1e-3),
-                "without_policy_network": world * n_roll * args.rollout_steps / (float(tn_.item()) * 1e-3),
-                "timeout_bootstrap_overflow": int(col.overflow.item()),
-                "note": "DeviceRolloutCollector.collect(): policy forward + hlynr_step + hlynr_post_step + "
-                        "hlynr_bootstrap_timeouts per step, hlynr_gae at the end; buffers [T,N,*] resident in HBM"}
-        rpipe.close()
-        rsim.close()
-
-    # e2e: the numpy VecEnv API a Stable-Baselines3 user calls (host buffers, H2D + D2H inside the timed region)
-    venv = HlynrVecEnv(env_cfg, n_envs=n, device=local_rank, seed=99, env_id_offset=rank * n, precision=args.precision,
-                       warn_dead=False, lazy_infos=True)
-    venv.reset()
-    venv.sim.rollout(1200, None, want_obs=False)  # age the episodes: the timed steps see the steady-state done rate
-    rng = np.random.default_rng(rank)
-    host_actions = [rng.uniform(-1, 1, (n, 6)).astype(np.float32) for _ in range(2)]  # ordinary (unpinned) numpy arrays
-    for k in range(3):
-        venv.step(host_actions[k % 2])
-    barrier()
-    n_done = 0
-    t0 = time.perf_counter()
-    for k in range(args.e2e_steps):
-        _, rew_h, _, infos_h = venv.step(host_actions[k % 2])
-        n_done += len(infos_h.records)  # finished episodes (terminal observation + info) arrive as compact records
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e = {"value": world * n * args.e2e_steps / float(te.item()), "unit": "env-steps/s",
-           "h2d_bytes_per_step": n * 6 * 4, "d2h_bytes_per_step": n * (26 * 4 + 4 + 1 + 1 + 1) + 4 + 200 * min(n, 4096),
-           "api": "HlynrVecEnv.step(ordinary numpy actions) -> numpy obs, rewards, dones, infos (hlynr_step_host: chunks pipelined "
-                  "over 3 streams; actions staged with streaming stores; obs by copy engine into alternating page-locked sets; "
-                  "reward/terminated/truncated/dones written by the kernel straight into host memory; done episodes as compact records)",
-           "steps": args.e2e_steps, "done_episodes_per_step": n_done / max(args.e2e_steps, 1),
-           "ms_per_step": float(te.item()) / args.e2e_steps * 1e3}
-    venv.close()
+    # ---- e2e: the numpy VecEnv API a Stable-Baselines3 user calls (host buffers, H2D + D2H inside the timed region) ------------
+    e2e = e2e_leg(ctx, args, env_cfg, n)
 
     if rank == 0:
-        peak, peak_src = measured_peak()
-        bytes_per_step = ALGO_BYTES.get(args.workload, 630) * (1 if args.precision == "fp32" else 1)
-        per_launch_ms = step_ms_total / K  # rank-0 kernel time per launch, CUDA events on the launching stream
+        bytes_per_step = ALGO_BYTES.get(args.workload, 630) if args.precision == "fp32" else layout_bytes(args.workload, "fp64")
+        lb = layout_bytes(args.workload, args.precision)
+        per_launch_ms = head["ms"] / K  # rank-0 kernel time per launch, CUDA events on the launching stream
         achieved = n * bytes_per_step / (per_launch_ms * 1e-3) / 1e9
+        traffic = measured_traffic(args.workload, n) if args.precision == "fp32" else None
+        episodes = stats_host[0]
         line = {
             "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.workload), "envs_per_gpu": n, "total_envs": n * world,
                        "mode": "API: one hlynr_step launch per tick, actions U(-1,1)^6 float32 resident in HBM",
-                       "parallelism": f"env-sharded x{world}, no per-step communication, 1 NCCL stats all-reduce per rollout",
+                       "state": f"steady state: episodes desynchronised by {AGE_TICKS} fused random-policy ticks before the warm-up",
+                       "parallelism": f"env-sharded x{world}, no per-step communication, 1 NCCL stats all-reduce per rollout (inside the timed region)",
                        "l2": "per-tick working set (~0.6 GB state + I/O) exceeds the 126 MB L2, no flush needed",
                        "seed": 1234},
             "clocks": clocks,
             "e2e": e2e,
-            "gpu_launches": int(launches),
+            "gpu_launches": int(head["launches"]),
+            "done_episodes_per_step": episodes / K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(args.workload, n), "peak_source": peak_src, "kernel": "hlynr::step_kernel<float,false>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "hlynr::step_kernel<float,false,F>",
                          "algorithmic_bytes_per_env_step": bytes_per_step, "units_per_launch": n,
-                         "kernel_us_per_launch": per_launch_ms * 1e3},
+                         "kernel_us_per_launch": per_launch_ms * 1e3,
+                         "layout_bytes_per_env_step": lb, "frac_layout": n * lb / (per_launch_ms * 1e-3) / 1e9 / peak,
+                         "frac_traffic": (traffic / (per_launch_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                         "note": "achieved/frac use SURVEY 8(d)'s contract bytes; frac_layout uses the bytes the kernel's own SoA layout "
+                                 "moves (DESIGN.md section 2); frac_traffic uses the ncu-measured DRAM bytes of profiles/traffic.json"},
+            "strong": strong,
+            "configs": configs,
             "fused_rollout": fused,
             "obs_pipeline": post,
             "rollout_collection": roll,
             "episode_stats": dict(zip(["episodes", "successes", "return_sum", "length_sum"], stats_host[:4])),
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args.workload, seconds=args.cpu_seconds)
+            line["cpu_baseline"] = cpu_baseline(args.workload, seconds=args.cpu_seconds, ref_seconds=args.ref_python_seconds)
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
-    sim.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def e2e_leg(ctx, args, env_cfg, n):
+    from hlynr_intercept_b200.vec_env import HlynrVecEnv
+
+    torch, world, rank = ctx.torch, ctx.world, ctx.rank
+    out = None
+    for obs_dim in (26, 17):
+        venv = HlynrVecEnv(env_cfg, n_envs=n, device=ctx.local_rank, seed=99, env_id_offset=rank * n, precision=args.precision,
+                           warn_dead=False, lazy_infos=True, obs_dim=obs_dim)
+        venv.reset()
+        venv.sim.rollout(1200, None, want_obs=False)  # age the episodes: the timed steps see the steady-state done rate
+        rng = np.random.default_rng(rank)
+        host_actions = [rng.uniform(-1, 1, (n, 6)).astype(np.float32) for _ in range(2)]  # ordinary (unpinned) numpy arrays
+        for k in range(3):
+            venv.step(host_actions[k % 2])
+        ctx.barrier()
+        n_done = 0
+        t0 = time.perf_counter()
+        for k in range(args.e2e_steps):
+            _, rew_h, _, infos_h = venv.step(host_actions[k % 2])
+            n_done += len(infos_h.records)  # finished episodes (terminal observation + info) arrive as compact records
+        torch.cuda.synchronize()
+        sec = ctx.max_over_ranks(time.perf_counter() - t0)
+        venv.close()
+        blk = {"value": world * n * args.e2e_steps / sec, "unit": "env-steps/s", "obs_dim": obs_dim,
+               "h2d_bytes_per_step": n * 6 * 4, "d2h_bytes_per_step": n * (obs_dim * 4 + 4 + 1 + 1 + 1) + 4 + 200 * min(n, 4096),
+               "steps": args.e2e_steps, "done_episodes_per_step": n_done / max(args.e2e_steps, 1), "ms_per_step": sec / args.e2e_steps * 1e3}
+        if obs_dim == 26:
+            out = blk
+            out["api"] = ("HlynrVecEnv.step(ordinary numpy actions) -> numpy obs, rewards, dones, infos (hlynr_step_host: chunks pipelined "
+                          "over 3 streams; actions staged with streaming stores; obs by copy engine into alternating page-locked sets; "
+                          "reward/terminated/truncated/dones written by the kernel straight into host memory; done episodes as compact records)")
+        else:
+            out["obs17"] = blk
+            out["obs17"]["note"] = "HlynrVecEnv(obs_dim=17): the 17-D radar layout obs[0:17] of the 26-D vector, 36 B per env less to download"
+    return out
+
+
+def rollout_leg(ctx, args, env_cfg):
+    """PPO rollout collection fully on the device: policy forward, env step, frame-stack/normalise, TimeLimit bootstrap, GAE;
+    no host synchronisation inside collect()."""
+    from hlynr_intercept_b200.post import HlynrObsPipeline
+    from hlynr_intercept_b200.rollout import DeviceRolloutCollector, GaussianMlpPolicy
+    from hlynr_intercept_b200.sim import HlynrSim
+
+    torch, world, rank, dev = ctx.torch, ctx.world, ctx.rank, ctx.dev
+    barrier = ctx.barrier
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_roll = min(args.envs_per_gpu, args.rollout_envs)
+    rsim = HlynrSim(env_cfg, n_envs=n_roll, device=ctx.local_rank, seed=4321, env_id_offset=rank * n_roll, precision=args.precision,
+                    warn_dead=False)
+    rpipe = HlynrObsPipeline(rsim, n_stack=4, training=True)
+    torch.manual_seed(rank)
+    torch.backends.cuda.matmul.allow_tf32 = True   # the policy GEMMs are the caller's; TF32 tensor cores as PPO users run them
+    torch.backends.cudnn.allow_tf32 = True
+    pol = GaussianMlpPolicy(104, device=dev)
+    col = DeviceRolloutCollector(rpipe, pol, args.rollout_steps)
+    col.collect()
+    barrier()
+    e0.record()
+    col.collect()
+    e1.record()
+    barrier()
+    te_ = ctx.max_over_ranks(e0.elapsed_time(e1))
+    graphed = args.rollout_steps % col.graph_period() == 0
+    if graphed:   # the whole collect() as ONE CUDA-graph launch (launch-bound otherwise: ~25 kernels per step)
+        col.capture()
+        col.replay()
+        barrier()
+        e0.record()
+        col.replay()
+        e1.record()
+        barrier()
+    tr_ = ctx.max_over_ranks(e0.elapsed_time(e1))
+
+    class _NoPolicy(torch.nn.Module):   # the same loop without the policy network (random actions): what the simulator side costs
+        def __init__(self):
+            super().__init__()
+            self.dummy = torch.nn.Parameter(torch.zeros(1, device=dev))
+
+        def value(self, obs):
+            return obs[:, 0].contiguous()
+
+        def forward(self, obs):
+            a = torch.rand(obs.shape[0], 6, device=obs.device) * 2 - 1
+            return a, obs[:, 0], obs[:, 1]
+
+    col2 = DeviceRolloutCollector(rpipe, _NoPolicy(), args.rollout_steps)
+    col2._started = True
+    col2.obs[col2.T].copy_(col.obs[col.T])
+    col2.collect()
+    barrier()
+    e0.record()
+    col2.collect()
+    e1.record()
+    barrier()
+    tn_ = ctx.max_over_ranks(e0.elapsed_time(e1))
+    roll = {"value": world * n_roll * args.rollout_steps / (tr_ * 1e-3), "unit": "env-steps/s",
+            "envs_per_gpu": n_roll, "n_steps": args.rollout_steps,
+            "policy": "GaussianMlpPolicy 104->512->512->256 (pi and vf), LayerNorm, fp32 weights, TF32 GEMMs (torch / cuBLAS)",
+            "cuda_graph": bool(graphed), "eager": world * n_roll * args.rollout_steps / (te_ * 1e-3),
+            "without_policy_network": world * n_roll * args.rollout_steps / (tn_ * 1e-3),
+            "timeout_bootstrap_overflow": int(col.overflow.item()),
+            "note": "DeviceRolloutCollector.collect(): policy forward + hlynr_step + hlynr_post_step + "
+                    "hlynr_bootstrap_timeouts per step, hlynr_gae at the end; buffers [T,N,*] resident in HBM; SB3 parity of the "
+                    "GAE / bootstrap restatement is UNPINNED (stable_baselines3 not importable here)"}
+    rpipe.close()
+    rsim.close()
+    return roll
 
 
 if __name__ == "__main__":

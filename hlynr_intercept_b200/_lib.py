@@ -17,7 +17,7 @@ EXPORTS = [
     "hlynr_step", "hlynr_rollout", "hlynr_reset_host", "hlynr_step_host", "hlynr_pinned_buffers", "hlynr_info_host",
     "hlynr_stats_device_ptr", "hlynr_stats_reduce", "hlynr_get_stats", "hlynr_export_state", "hlynr_import_state",
     "hlynr_debug_draws", "hlynr_launch_count", "hlynr_set_option", "hlynr_set_done_list", "hlynr_done_records_host",
-    "hlynr_ring_period", "hlynr_note_replayed_ticks", "hlynr_pinned_done", "hlynr_host_done_buffer",
+    "hlynr_ring_period", "hlynr_note_replayed_ticks", "hlynr_tick_count", "hlynr_pinned_done", "hlynr_host_done_buffer",
     # include/hlynr_post.h
     "hlynr_post_create", "hlynr_post_destroy", "hlynr_post_obs_dim", "hlynr_post_obs_target", "hlynr_post_reset",
     "hlynr_post_step", "hlynr_post_original", "hlynr_post_normalize", "hlynr_post_get_stats", "hlynr_post_set_stats",
@@ -96,6 +96,7 @@ def load(build_if_missing=True):
     L.hlynr_post_note_replayed_steps.argtypes = [vp, i64, i64]
     L.hlynr_ring_period.argtypes = [vp, C.POINTER(i32)]
     L.hlynr_note_replayed_ticks.argtypes = [vp, i64, i64]
+    L.hlynr_tick_count.argtypes = [vp, C.POINTER(i64)]
     L.hlynr_bootstrap_timeouts.argtypes = [vp, vp, vp, C.c_int32, vp, C.c_double, vp, i32, vp]
     L.hlynr_gae.argtypes = [vp, vp, vp, vp, vp, i64, i64, C.c_double, C.c_double, vp, vp, i32, vp]
     if L.hlynr_abi_version() != abi.ABI_VERSION:

@@ -57,7 +57,8 @@ class HlynrInfoSoA(C.Structure):
                 ("fuel_used", C.c_void_p), ("steps", C.c_void_p), ("flags", C.c_void_p),
                 ("interceptor_pos", C.c_void_p), ("missile_pos", C.c_void_p),
                 ("episode_return", C.c_void_p), ("episode_length", C.c_void_p),
-                ("missiles_intercepted", C.c_void_p), ("missiles_remaining", C.c_void_p), ("missile_min_distances", C.c_void_p)]
+                ("missiles_intercepted", C.c_void_p), ("missiles_remaining", C.c_void_p), ("missile_min_distances", C.c_void_p),
+                ("radar_quality", C.c_void_p)]
 
 
 INFO_FIELDS = [  # name, numpy dtype, trailing shape
@@ -66,12 +67,13 @@ INFO_FIELDS = [  # name, numpy dtype, trailing shape
     ("interceptor_pos", "float32", (3,)), ("missile_pos", "float32", (3,)),
     ("episode_return", "float32", ()), ("episode_length", "int32", ()),
     ("missiles_intercepted", "int32", ()), ("missiles_remaining", "int32", ()), ("missile_min_distances", "float32", (MAX_VOLLEY,)),
+    ("radar_quality", "float32", ()),
 ]
 
 INFO_INTERCEPTED, INFO_HIT_TARGET, INFO_CLAMPED, INFO_RADAR_DETECTED = 0x01, 0x02, 0x04, 0x08
 INFO_GROUND_DETECTED, INFO_CROSSED, INFO_FUZE, INFO_KF_INIT = 0x10, 0x20, 0x40, 0x80
 
-DONE_TERMINATED, DONE_TRUNCATED = 0x100, 0x200
+DONE_TERMINATED, DONE_TRUNCATED, DONE_ONBOARD_FILL = 0x100, 0x200, 0x400
 
 
 def done_record_numpy_dtype():
@@ -107,6 +109,7 @@ class HlynrEnvState(C.Structure):
         ("steps", C.c_int32), ("worsen_count", C.c_int32), ("crossed", C.c_int32), ("kf_init", C.c_int32),
         ("onboard_delay", C.c_int32), ("episode", C.c_int32),
         ("vactive", C.c_int32 * MAX_VOLLEY), ("vcur", C.c_int32), ("vcount", C.c_int32),
+        ("kf_f64", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

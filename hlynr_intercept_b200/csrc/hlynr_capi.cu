@@ -195,10 +195,9 @@ struct hlynr_sim {
     int64_t n = 0, n_pad = 0, env_offset = 0;
     int device = 0, precision = HLYNR_FP32;
     uint64_t seed = 0;
-    uint32_t tick = 0;
+    uint64_t tick = 0;  // 64-bit: ring rows are tick % ring_len with lengths that are not powers of two, so the counter must never wrap
     int64_t launches = 0;
     double env_steps = 0.0;
-    int kernel_variant = 0;  // 0 auto, 1 direct, 2 TMA-prefetched persistent kernel
     int specialise = 1;      // use the feature-specialised instantiations when the configuration matches one
     int sm_count = 148;  // ticks simulated since the statistics were last zeroed (n per launch tick)
     void* state_mem = nullptr;
@@ -211,8 +210,8 @@ struct hlynr_sim {
     cudaStream_t own_stream = nullptr;
     HostIO hio;
     int host_info = 1, host_chunks = 0, host_threads = 0;
+    int obs_dim = HLYNR_OBS_DIM;  // row pitch of every observation array of the API: 26, or 17 (option "obs_dim")
     int prefetch_waves = 1;  // CTAs per SM the step kernel looks ahead when it prefetches upcoming planes into L2 (0 = off)
-    unsigned int* pipe_counters = nullptr;    // tile queue of the persistent-warp kernel (variant 3)
     HlynrDoneRecord* done_records = nullptr;  // attached compact done list (hlynr_set_done_list)
     int32_t* done_counter = nullptr;
     int32_t done_cap = 0;
@@ -342,6 +341,7 @@ template <typename R> __global__ void export_kernel(KernelArgs<R> A, int64_t fir
         s.vvel[3 * m] = b.x; s.vvel[3 * m + 1] = b.y; s.vvel[3 * m + 2] = b.z; s.vactive[m] = b.w != R(0) ? 1 : 0;
     }
     s.vcur = A.P.volley_k > 0 ? FLAG_VCUR(e.flags) : 0; s.vcount = A.P.volley_k > 0 ? FLAG_VCOUNT(e.flags) : 0;
+    s.kf_f64 = (e.flags & FLAG_KF_F64) ? 1 : 0;
     out[j] = s;
 }
 template <typename R> __global__ void import_kernel(KernelArgs<R> A, int64_t first, int64_t count, const HlynrEnvState* in) {
@@ -360,7 +360,7 @@ template <typename R> __global__ void import_kernel(KernelArgs<R> A, int64_t fir
     e.Ppp = (float)s.kf_P[0]; e.Ppv = (float)s.kf_P[1]; e.Pvp = (float)s.kf_P[2]; e.Pvv = (float)s.kf_P[3];
     e.T0 = (R)s.T0; e.base_cd = (float)s.base_cd; e.peak = (float)s.peak;
     e.steps = s.steps; e.worsen = s.worsen_count;
-    e.flags = (s.crossed ? FLAG_CROSSED : 0) | (s.kf_init ? FLAG_KF_INIT : 0) | ((s.onboard_delay & 0xf) << 8) | ((s.vcur & 0x7) << 12) |
+    e.flags = (s.crossed ? FLAG_CROSSED : 0) | (s.kf_init ? FLAG_KF_INIT : 0) | (s.kf_f64 ? FLAG_KF_F64 : 0) | ((s.onboard_delay & 0xf) << 8) | ((s.vcur & 0x7) << 12) |
               ((s.vcount & 0xf) << 16);
     for (int m = 0; m < A.P.volley_k; ++m) {
         A.st.vm[(int64_t)(2 * m) * A.ring_stride + first + j] = Vec4<R>{(R)s.vpos[3 * m], (R)s.vpos[3 * m + 1], (R)s.vpos[3 * m + 2], (R)s.vmin[m]};
@@ -400,6 +400,11 @@ template <typename R> static size_t carve(StatePlanes<R>& s, char* base, int64_t
     return off;
 }
 
+template <typename R> static void set_tick(KernelArgs<R>& A, uint64_t tick) {
+    A.tick = (uint32_t)tick;
+    A.g_row = A.P.gnd_ring_len > 0 ? (int32_t)(tick % (uint64_t)A.P.gnd_ring_len) : 0;
+    A.o_row = A.P.onb_ring_len > 0 ? (int32_t)(tick % (uint64_t)A.P.onb_ring_len) : 0;
+}
 template <typename R> static KernelArgs<R> base_args(hlynr_sim* s, const StatePlanes<R>& planes) {
     KernelArgs<R> A;
     memset(&A, 0, sizeof(A));
@@ -412,12 +417,11 @@ template <typename R> static KernelArgs<R> base_args(hlynr_sim* s, const StatePl
     A.ring_stride = s->n_pad;
     A.env_offset = s->env_offset;
     A.rk = make_round_keys(s->seed);
-    A.tick = s->tick;
-    A.g_row = A.P.gnd_ring_len > 0 ? (int32_t)(s->tick % (uint32_t)A.P.gnd_ring_len) : 0;
-    A.o_row = A.P.onb_ring_len > 0 ? (int32_t)(s->tick % (uint32_t)A.P.onb_ring_len) : 0;
+    set_tick(A, s->tick);
     A.io.stats = s->stats;
     A.k_steps = 1;
     A.prefetch_ahead = s->sm_count * s->prefetch_waves * HLYNR_BLOCK;
+    A.obs_dim = s->obs_dim;
     return A;
 }
 static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
@@ -437,61 +441,17 @@ static int feature_set(const HlynrParams& p) {
     if (p.evasion_enabled) f |= FT_EVADE;
     return (f == FT_V2ON || f == FT_V2OFF || f == FT_V2ON_DR) ? f : FT_GENERIC;
 }
-template <bool kRollout> static void launch_step_f32(const hlynr_sim* s, const KernelArgs<float>& A, cudaStream_t st, bool specialise) {
+// Both builds dispatch to the feature-specialised instantiation of the three BASELINE configurations when it matches.
+template <typename R, bool kRollout> static void launch_step(const hlynr_sim* s, const KernelArgs<R>& A, cudaStream_t st, bool specialise) {
     const int grid = grid_for(A.lim - A.first, HLYNR_STEP_BLOCK);
     int f = feature_set(s->params);
     if (!specialise && f >= 0) f = FT_GENERIC;
-    if (f == FT_V2ON) step_kernel<float, kRollout, FT_V2ON><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
-    else if (f == FT_V2OFF) step_kernel<float, kRollout, FT_V2OFF><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
-    else if (f == FT_V2ON_DR) step_kernel<float, kRollout, FT_V2ON_DR><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
-    else if (f == FT_GENERIC_MODES) step_kernel<float, kRollout, FT_GENERIC_MODES><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
-    else step_kernel<float, kRollout, FT_GENERIC><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
+    if (f == FT_V2ON) step_kernel<R, kRollout, FT_V2ON><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
+    else if (f == FT_V2OFF) step_kernel<R, kRollout, FT_V2OFF><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
+    else if (f == FT_V2ON_DR) step_kernel<R, kRollout, FT_V2ON_DR><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
+    else if (f == FT_GENERIC_MODES) step_kernel<R, kRollout, FT_GENERIC_MODES><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
+    else step_kernel<R, kRollout, FT_GENERIC><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
 }
-
-// ------------------------------------------------------------------------------------------------
-// TMA-prefetched persistent step kernel: host-side plan
-// ------------------------------------------------------------------------------------------------
-static TmaPlan make_tma_plan(const hlynr_sim* s, const KernelArgs<float>& A, const float* actions_dev) {
-    TmaPlan T;
-    memset(&T, 0, sizeof(T));
-    uint32_t off = 0;
-    int c = 0;
-    auto add = [&](const void* base, uint32_t stride, uint32_t* off_out) {
-        T.src[c] = (const char*)base; T.stride[c] = stride; T.smem_off[c] = off;
-        if (off_out) *off_out = off;
-        off += stride * TMA_TILE;
-        off = (off + 127u) & ~127u;
-        return c++;
-    };
-    const KParams<float>& P = A.P;
-    for (int k = 0; k < 6; ++k) add(A.st.r[k], 16, &T.off_r[k]);
-    if (P.thrust_dyn | P.dr) add(A.st.r[6], 16, &T.off_r[6]);
-    for (int k = 0; k < 3; ++k) add(A.st.f[k], 16, &T.off_f[k]);
-    if (P.dr) add(A.st.f[3], 16, &T.off_f[3]);
-    add(A.st.i0, 16, &T.off_i0);
-    if (P.onboard_delay > 0 && !P.dr) {  // the row read this tick: written onboard_delay ticks ago
-        int rrow = A.o_row - P.onboard_delay;
-        if (rrow < 0) rrow += P.onb_ring_len;
-        add(A.st.oring + (int64_t)rrow * A.ring_stride, 16, &T.off_oring);
-    }
-    if (P.ground_delay > 0) {            // oldest ground slot: two planes {rel, quality}, {vel}
-        const int rrow = A.g_row + 1 == P.gnd_ring_len ? 0 : A.g_row + 1;
-        const Vec4<float>* row = A.st.gring + (int64_t)rrow * 2 * A.ring_stride;
-        add(row, 16, &T.off_gring);
-        uint32_t dummy;
-        add(row + A.ring_stride, 16, &dummy);
-    }
-    T.actions_idx = add(actions_dev, 24, &T.off_actions);
-    T.count = c;
-    T.tx_full = 0;
-    for (int k = 0; k < c; ++k) T.tx_full += T.stride[k] * TMA_TILE;
-    T.off_obs_tile = off; off += (HLYNR_BLOCK / 32) * OBS_TILE * sizeof(float);
-    off = (off + 15u) & ~15u;
-    T.off_bar = off; off += 16;
-    (void)s;
-    return T;
-}
-static uint32_t tma_smem_bytes(const TmaPlan& T) { return T.off_bar + 16; }
 
 // ------------------------------------------------------------------------------------------------
 // C ABI
@@ -506,7 +466,7 @@ size_t hlynr_env_state_size(void) { return sizeof(HlynrEnvState); }
 void hlynr_destroy(hlynr_t* s) {
     if (!s) return;
     DeviceGuard g(s->device);
-    cudaFree(s->state_mem); cudaFree(s->stats); cudaFree(s->xchg); cudaFree(s->pipe_counters);
+    cudaFree(s->state_mem); cudaFree(s->stats); cudaFree(s->xchg);
     HostIO& h = s->hio;
     delete h.pool;
     cudaFreeHost(h.h_actions); cudaFreeHost(h.h_obs); cudaFreeHost(h.h_reward); cudaFreeHost(h.h_records_ab[0]); cudaFreeHost(h.h_records_ab[1]); cudaFreeHost(h.h_count);
@@ -522,6 +482,7 @@ void hlynr_destroy(hlynr_t* s) {
     cudaFree(h.d_info.steps); cudaFree(h.d_info.flags); cudaFree(h.d_info.interceptor_pos); cudaFree(h.d_info.missile_pos);
     cudaFree(h.d_info.episode_return); cudaFree(h.d_info.episode_length);
     cudaFree(h.d_info.missiles_intercepted); cudaFree(h.d_info.missiles_remaining); cudaFree(h.d_info.missile_min_distances);
+    cudaFree(h.d_info.radar_quality);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
@@ -559,7 +520,6 @@ int hlynr_create(const HlynrParams* p, int64_t n_envs, int device, uint64_t seed
     if (e != cudaSuccess) { int r = fail("hlynr_create: cudaMalloc(stats) failed: %s", cudaGetErrorString(e)); cudaFree(s->state_mem); delete s; return r; }
     cudaMemset(s->state_mem, 0, s->state_bytes);
     cudaMemset(s->stats, 0, sizeof(double) * (HLYNR_STAT_SLOTS + 1) * HLYNR_STATS_WORDS);
-    if (cudaMalloc(&s->pipe_counters, 2 * sizeof(unsigned int)) == cudaSuccess) cudaMemset(s->pipe_counters, 0, 2 * sizeof(unsigned int));
     cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     const int blk = 256;
@@ -584,16 +544,16 @@ int hlynr_seed(hlynr_t* s, uint64_t seed) { if (!s) return fail("null handle"); 
 static int make_pool(hlynr_sim* s);
 int hlynr_set_option(hlynr_t* s, const char* name, int64_t value) {
     if (!s || !name) return fail("null argument");
-    if (strcmp(name, "step_kernel_variant") == 0) {
-        if (value < 0 || value > 3) return fail("step_kernel_variant must be 0 (auto), 1 (direct), 2 (tma) or 3 (persistent warps + cp.async)");
-        s->kernel_variant = (int)value;
-        return 0;
-    }
     if (strcmp(name, "specialise") == 0) { s->specialise = value != 0; return 0; }
     if (strcmp(name, "host_info") == 0) { s->host_info = value != 0; return 0; }
     if (strcmp(name, "prefetch_waves") == 0) {
         if (value < 0 || value > 64) return fail("prefetch_waves must be in [0, 64]");
         s->prefetch_waves = (int)value;
+        return 0;
+    }
+    if (strcmp(name, "obs_dim") == 0) {
+        if (value != HLYNR_OBS_DIM && value != 17) return fail("obs_dim must be 26 (the reference's vector) or 17 (its leading radar channels obs[0:17])");
+        s->obs_dim = (int)value;
         return 0;
     }
     if (strcmp(name, "host_chunks") == 0) {
@@ -619,9 +579,10 @@ int hlynr_ring_period(const hlynr_t* s, int* out) {
 int hlynr_note_replayed_ticks(hlynr_t* s, int64_t ticks, int64_t launches) {
     if (!s) return fail("hlynr_note_replayed_ticks: null handle");
     // negative values undo the host-side bookkeeping of calls that were only RECORDED into a graph (not executed)
-    s->tick = (uint32_t)((int64_t)s->tick + ticks); s->env_steps += (double)s->n * (double)ticks; s->launches += launches;
+    s->tick = (uint64_t)((int64_t)s->tick + ticks); s->env_steps += (double)s->n * (double)ticks; s->launches += launches;
     return 0;
 }
+int hlynr_tick_count(const hlynr_t* s, int64_t* out) { if (!s || !out) return fail("null argument"); *out = (int64_t)s->tick; return 0; }
 int hlynr_launch_count(const hlynr_t* s, int64_t* out) { if (!s || !out) return fail("null argument"); *out = s->launches; return 0; }
 
 int hlynr_reset(hlynr_t* s, const uint8_t* mask_dev, float* obs_dev, void* stream) {
@@ -647,51 +608,20 @@ int hlynr_reset(hlynr_t* s, const uint8_t* mask_dev, float* obs_dev, void* strea
 static int step_range(hlynr_sim* s, int64_t first, int64_t lim, const float* actions_dev, float* obs_dev, float* reward_dev,
                       uint8_t* terminated_dev, uint8_t* truncated_dev, float* terminal_obs_dev, const HlynrInfoSoA* info,
                       int auto_reset, cudaStream_t st) {
-    const bool whole = first == 0 && lim == s->n;
     if (s->precision == HLYNR_FP32) {
         KernelArgs<float> A = base_args<float>(s, s->pf);
         A.first = first; A.lim = lim;
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward = reward_dev; A.io.terminated = terminated_dev;
         A.io.truncated = truncated_dev; A.io.terminal_obs = terminal_obs_dev; A.auto_reset = auto_reset;
         if (info) { A.io.info = *info; A.has_info = 1; }
-        // measured on B200 (profiles/r01_b): the direct kernel is faster than the TMA-prefetched persistent one (the
-        // step is bound by in-warp dependency latency, not by load latency), so auto = direct; the TMA variant stays
-        // selectable and parity-tested.  It needs 16-byte aligned actions and works on the whole shard only.
-        bool use_tma = s->kernel_variant == 2 && whole && s->params.obs_mode == HLYNR_OBS_WORLD && s->params.volley_size == 0;
-        if (((uintptr_t)actions_dev & 15u) != 0) use_tma = false;
-        if (use_tma) {
-            const int64_t n_tiles = (s->n + TMA_TILE - 1) / TMA_TILE;
-            const TmaPlan T = make_tma_plan(s, A, actions_dev);
-            const uint32_t smem = tma_smem_bytes(T);
-            static thread_local uint32_t smem_set = 0;
-            if (smem > smem_set) {
-                CK(cudaFuncSetAttribute(step_kernel_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                smem_set = smem;
-            }
-            const int64_t max_ctas = (int64_t)s->sm_count * 4;
-            const int grid = (int)(n_tiles < max_ctas ? n_tiles : max_ctas);
-            step_kernel_tma<<<grid, HLYNR_BLOCK, smem, st>>>(A, T);
-        } else if (s->kernel_variant == 3 && whole && s->specialise && feature_set(s->params) >= 0 && s->pipe_counters) {
-            // persistent warps with per-thread cp.async staging (specialised feature sets, whole shard, one launch at a time)
-            const int f = feature_set(s->params);
-            const int grid = s->sm_count * 4;
-            const size_t smem = sizeof(PipeSmem);
-            if (f == FT_V2ON) step_kernel_pipe<FT_V2ON><<<grid, HLYNR_BLOCK, smem, st>>>(A, s->pipe_counters);
-            else if (f == FT_V2OFF) step_kernel_pipe<FT_V2OFF><<<grid, HLYNR_BLOCK, smem, st>>>(A, s->pipe_counters);
-            else step_kernel_pipe<FT_V2ON_DR><<<grid, HLYNR_BLOCK, smem, st>>>(A, s->pipe_counters);
-        } else {
-            launch_step_f32<false>(s, A, st, s->specialise != 0);
-        }
+        launch_step<float, false>(s, A, st, s->specialise != 0);
     } else {
         KernelArgs<double> A = base_args<double>(s, s->pd);
         A.first = first; A.lim = lim;
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward = reward_dev; A.io.terminated = terminated_dev;
         A.io.truncated = truncated_dev; A.io.terminal_obs = terminal_obs_dev; A.auto_reset = auto_reset;
         if (info) { A.io.info = *info; A.has_info = 1; }
-        if (s->params.obs_mode != HLYNR_OBS_WORLD || s->params.volley_size > 0)
-            step_kernel<double, false, FT_GENERIC_MODES><<<grid_for(lim - first, HLYNR_STEP_BLOCK), HLYNR_STEP_BLOCK, 0, st>>>(A);
-        else
-            step_kernel<double, false, FT_GENERIC><<<grid_for(lim - first, HLYNR_STEP_BLOCK), HLYNR_STEP_BLOCK, 0, st>>>(A);
+        launch_step<double, false>(s, A, st, s->specialise != 0);
     }
     CK(cudaGetLastError());
     s->launches += 1;
@@ -724,24 +654,17 @@ int hlynr_rollout(hlynr_t* s, int k_steps, const float* actions_dev, float* obs_
     cudaStream_t st = (cudaStream_t)stream;
     if (s->precision == HLYNR_FP32) {
         KernelArgs<float> A = base_args<float>(s, s->pf);
-        A.tick = s->tick + 1; A.k_steps = k_steps; A.auto_reset = 1;
-        A.g_row = A.P.gnd_ring_len > 0 ? (int32_t)(A.tick % (uint32_t)A.P.gnd_ring_len) : 0;
-        A.o_row = A.P.onb_ring_len > 0 ? (int32_t)(A.tick % (uint32_t)A.P.onb_ring_len) : 0;
+        set_tick(A, s->tick + 1); A.k_steps = k_steps; A.auto_reset = 1;
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward_sum = reward_sum_dev; A.io.done_count = done_count_dev;
-        launch_step_f32<true>(s, A, st, s->specialise != 0);
+        launch_step<float, true>(s, A, st, s->specialise != 0);
     } else {
         KernelArgs<double> A = base_args<double>(s, s->pd);
-        A.tick = s->tick + 1; A.k_steps = k_steps; A.auto_reset = 1;
-        A.g_row = A.P.gnd_ring_len > 0 ? (int32_t)(A.tick % (uint32_t)A.P.gnd_ring_len) : 0;
-        A.o_row = A.P.onb_ring_len > 0 ? (int32_t)(A.tick % (uint32_t)A.P.onb_ring_len) : 0;
+        set_tick(A, s->tick + 1); A.k_steps = k_steps; A.auto_reset = 1;
         A.io.actions = actions_dev; A.io.obs = obs_dev; A.io.reward_sum = reward_sum_dev; A.io.done_count = done_count_dev;
-        if (s->params.obs_mode != HLYNR_OBS_WORLD || s->params.volley_size > 0)
-            step_kernel<double, true, FT_GENERIC_MODES><<<grid_for(s->n, HLYNR_STEP_BLOCK), HLYNR_STEP_BLOCK, 0, st>>>(A);
-        else
-            step_kernel<double, true, FT_GENERIC><<<grid_for(s->n, HLYNR_STEP_BLOCK), HLYNR_STEP_BLOCK, 0, st>>>(A);
+        launch_step<double, true>(s, A, st, s->specialise != 0);
     }
     CK(cudaGetLastError());
-    s->tick += (uint32_t)k_steps;
+    s->tick += (uint64_t)k_steps;
     s->launches += 1;
     s->env_steps += (double)s->n * k_steps;
     return 0;
@@ -912,6 +835,7 @@ static int ensure_host_info(hlynr_sim* s) {
     CK(cudaMalloc(&h.d_info.episode_return, n * 4)); CK(cudaMalloc(&h.d_info.episode_length, n * 4));
     CK(cudaMalloc(&h.d_info.missiles_intercepted, n * 4)); CK(cudaMalloc(&h.d_info.missiles_remaining, n * 4));
     CK(cudaMalloc(&h.d_info.missile_min_distances, n * 4 * HLYNR_MAX_VOLLEY));
+    CK(cudaMalloc(&h.d_info.radar_quality, n * 4));
     h.info_ready = true;
     return 0;
 }
@@ -922,19 +846,19 @@ int hlynr_reset_host(hlynr_t* s, const uint8_t* mask_host, float* obs_host) {
     if (ensure_hostio(s)) return 1;
     HostIO& h = s->hio;
     cudaStream_t st = h.streams[0];
-    const size_t n = (size_t)s->n;
+    const size_t n = (size_t)s->n, ob = (size_t)s->obs_dim * sizeof(float);
     if (host_streams_begin(s)) return 1;
     if (mask_host) {
         memcpy(h.h_mask, mask_host, n);
         CK(cudaMemcpyAsync(h.d_mask, h.h_mask, n, cudaMemcpyHostToDevice, st));
         // rows of envs that are not reset keep the caller's content
-        if (obs_host != h.h_obs) h.pool->copy(h.h_obs, obs_host, n * 26 * 4);
-        CK(cudaMemcpyAsync(h.d_obs, h.h_obs, n * 26 * 4, cudaMemcpyHostToDevice, st));
+        if (obs_host != h.h_obs) h.pool->copy(h.h_obs, obs_host, n * ob);
+        CK(cudaMemcpyAsync(h.d_obs, h.h_obs, n * ob, cudaMemcpyHostToDevice, st));
     }
     if (hlynr_reset(s, mask_host ? h.d_mask : nullptr, h.d_obs, st)) return 1;
-    CK(cudaMemcpyAsync(h.h_obs, h.d_obs, n * 26 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h.h_obs, h.d_obs, n * ob, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (obs_host != h.h_obs) h.pool->copy(obs_host, h.h_obs, n * 26 * 4);
+    if (obs_host != h.h_obs) h.pool->copy(obs_host, h.h_obs, n * ob);
     return 0;
 }
 
@@ -950,7 +874,7 @@ int hlynr_step_host(hlynr_t* s, const float* actions_host, float* obs_host, floa
     if (ensure_hostio(s)) return 1;
     if (s->host_info && ensure_host_info(s)) return 1;
     HostIO& h = s->hio;
-    const int64_t n = s->n;
+    const int64_t n = s->n, od = s->obs_dim;
     int64_t chunks = s->host_chunks > 0 ? s->host_chunks : (n >= (int64_t(1) << 19) ? 16 : (n >= (int64_t(1) << 17) ? 8 : (n >= (int64_t(1) << 15) ? 4 : 1)));
     int64_t per = ((n + chunks - 1) / chunks + 127) & ~int64_t(127);
     chunks = (n + per - 1) / per;
@@ -999,7 +923,7 @@ int hlynr_step_host(hlynr_t* s, const float* actions_host, float* obs_host, floa
         // 2^20 envs): three small copy-engine transfers per chunk, each with its own fixed latency, disappear and only the
         // observation (104 B per env) rides the copy engine
         if (step_range(s, first, lim, h.d_actions, h.d_obs, reward_k, term_k, trunc_k, nullptr, info, auto_reset, st)) return 1;
-        CK(cudaMemcpyAsync(obs_dst + first * 26, h.d_obs + first * 26, (size_t)cnt * 104, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(obs_dst + first * od, h.d_obs + first * od, (size_t)(cnt * od) * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     // done list: after every chunk's kernel; count + the first records in one go on stream 0
     for (int k = 1; k < HLYNR_HOST_STREAMS; ++k) {
@@ -1018,7 +942,7 @@ int hlynr_step_host(hlynr_t* s, const float* actions_host, float* obs_host, floa
         for (int64_t c = 0; c < chunks && c < 64; ++c) fprintf(stderr, " %.2f", t_staged[c]);
         fprintf(stderr, " | issued %.2f | synced %.2f ms\n", t_issued, t_synced);
     }
-    if (obs_host != obs_dst) h.pool->copy(obs_host, obs_dst, (size_t)n * 104);
+    if (obs_host != obs_dst) h.pool->copy(obs_host, obs_dst, (size_t)(n * od) * sizeof(float));
     if (reward_host != reward_dst) h.pool->copy(reward_host, reward_dst, (size_t)n * 4);
     if (terminated_host != term_dst) h.pool->copy(terminated_host, term_dst, (size_t)n);
     if (truncated_host != trunc_dst) h.pool->copy(truncated_host, trunc_dst, (size_t)n);
@@ -1032,7 +956,7 @@ int hlynr_step_host(hlynr_t* s, const float* actions_host, float* obs_host, floa
     h.last_count = count;
     if (terminal_obs_host)  // only rows of finished envs are written (info['terminal_observation'])
         for (int32_t k = 0; k < count; ++k)
-            memcpy(terminal_obs_host + (size_t)h.h_records[k].env * 26, h.h_records[k].terminal_obs, 26 * sizeof(float));
+            memcpy(terminal_obs_host + (size_t)h.h_records[k].env * od, h.h_records[k].terminal_obs, (size_t)od * sizeof(float));
     return 0;
 }
 
@@ -1064,6 +988,7 @@ int hlynr_info_host(hlynr_t* s, HlynrInfoSoA* o) {
     if (o->missiles_remaining) CK(cudaMemcpyAsync(o->missiles_remaining, d.missiles_remaining, n * 4, cudaMemcpyDeviceToHost, st));
     if (o->missile_min_distances)
         CK(cudaMemcpyAsync(o->missile_min_distances, d.missile_min_distances, n * 4 * HLYNR_MAX_VOLLEY, cudaMemcpyDeviceToHost, st));
+    if (o->radar_quality) CK(cudaMemcpyAsync(o->radar_quality, d.radar_quality, n * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return 0;
 }

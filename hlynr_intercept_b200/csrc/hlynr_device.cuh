@@ -266,6 +266,7 @@ template <typename R> struct KernelArgs {
     int32_t k_steps;
     int32_t has_info;
     int32_t prefetch_ahead;  // envs per resident wave of CTAs (0 = no L2 prefetch of the next wave's planes)
+    int32_t obs_dim;         // row pitch of io.obs / io.terminal_obs: HLYNR_OBS_DIM, or 17 = the leading "17-D radar" channels only
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -287,7 +288,8 @@ template <typename R> struct Env {
 };
 #define FLAG_CROSSED 1
 #define FLAG_KF_INIT 2
-// flags word: bit 0 crossed, bit 1 kf_init, bits 8-11 onboard delay (samples), bits 12-14 index of the priority missile
+#define FLAG_KF_F64 4   /* fp64 build: the reference's Kalman state array has become float64 (core.py:108) */
+// flags word: bit 0 crossed, bit 1 kf_init, bit 2 kf state is float64 (fp64 build), bits 8-11 onboard delay (samples), bits 12-14 index of the priority missile
 // (volley: which list entry self.missile_state aliases), bits 16-19 missiles intercepted so far (volley)
 #define FLAG_ODELAY(f) (((f) >> 8) & 0xf)
 #define FLAG_VCUR(f) (((f) >> 12) & 0x7)
@@ -465,12 +467,8 @@ struct ObsOut {
 // Geometry is float32 in both builds (the reference casts the state to float32 on entry, core.py:522-529);
 // W = R is the dtype of the reference's float64 islands (ground measurement, Kalman state).
 // ------------------------------------------------------------------------------------------------
-// ring samples already staged by the caller (TMA kernel); used instead of the global ring reads when kPre
-template <typename R> struct RingPre { float4 o; Vec4<R> ga, gb; };
-
-template <typename R, int F, bool kPre = false>
-HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint4 ur, int64_t i, int g_row, int o_row,
-                const RingPre<R>& pre, ObsOut& out) {
+template <typename R, int F>
+HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint4 ur, int64_t i, int g_row, int o_row, ObsOut& out) {
     typedef R W;
     typedef Feat<F> FT;
     const KParams<R>& P = A.P;
@@ -508,13 +506,9 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
         const int odelay = FLAG_ODELAY(e.flags);
         A.st.oring[(int64_t)o_row * n + i] = make_float4(rx, ry, rz, onb ? 1.f : 0.f);
         if (e.steps >= odelay) {
-            float4 s;
-            if (kPre && !FT::dr(P)) s = pre.o;
-            else {
-                int rrow = o_row - odelay;  // sample written `odelay` ticks ago
-                if (rrow < 0) rrow += L;
-                s = A.st.oring[(int64_t)rrow * n + i];
-            }
+            int rrow = o_row - odelay;  // sample written `odelay` ticks ago
+            if (rrow < 0) rrow += L;
+            const float4 s = A.st.oring[(int64_t)rrow * n + i];
             orx = s.x; ory = s.y; orz = s.z; o_det = s.w != 0.f;
         } else { orx = ory = orz = 0.f; o_det = false; }
     } else { orx = rx; ory = ry; orz = rz; o_det = onb; }
@@ -551,21 +545,18 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
     W dgx, dgy, dgz, dvx, dvy, dvz;
     float dgq;
     bool dg_det;
+    bool dg_f64 = gdet;  // the measurement arrays are float64 iff they hold a detected sample (float32 geometry + float64 noise)
     if (FT::ground(P) && FT::ground_delay(P)) {  // delayed values, CURRENT flag (core.py:626, quirk Q3)
         const int L = P.gnd_ring_len;
         Vec4<W>* wr = A.st.gring + (int64_t)g_row * 2 * n;
         wr[i] = Vec4<W>{grx, gry, grz, (W)gq};
-        wr[n + i] = Vec4<W>{gvx, gvy, gvz, W(0)};
+        wr[n + i] = Vec4<W>{gvx, gvy, gvz, gdet ? W(1) : W(0)};   // .w: the sample is a detection (dtype of the reference's arrays)
         if (e.steps >= P.ground_delay) {
-            Vec4<W> a, b;
-            if (kPre) { a = pre.ga; b = pre.gb; }
-            else {
-                const int rrow = g_row + 1 == L ? 0 : g_row + 1;  // oldest slot = written ground_delay ticks ago
-                const Vec4<W>* rr = A.st.gring + (int64_t)rrow * 2 * n;
-                a = rr[i]; b = rr[n + i];
-            }
+            const int rrow = g_row + 1 == L ? 0 : g_row + 1;  // oldest slot = written ground_delay ticks ago
+            const Vec4<W>* rr = A.st.gring + (int64_t)rrow * 2 * n;
+            const Vec4<W> a = rr[i], b = rr[n + i];
             dgx = a.x; dgy = a.y; dgz = a.z; dgq = (float)a.w; dvx = b.x; dvy = b.y; dvz = b.z;
-            dg_det = gdet;
+            dg_det = gdet; dg_f64 = b.w != W(0);
         } else { dgx = dgy = dgz = dvx = dvy = dvz = W(0); dgq = 0.f; dg_det = false; }
     } else { dgx = grx; dgy = gry; dgz = grz; dvx = gvx; dvy = gvy; dvz = gvz; dgq = gq; dg_det = gdet; }
 
@@ -596,7 +587,75 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
     out.ground_det = dg_det;
 
     // === Kalman filter (core.py:12-133) reduced to x[6] + one shared 2x2 covariance block ===
+    // dtype of self.state in the reference: float32 from reset() / initialize() until the first update() with a float64
+    // measurement (any measurement that contains a DETECTED ground sample: float32 geometry + float64 noise, core.py:424-428),
+    // float64 from then on (`self.state = self.state + K @ y` rebinds the array).  P, K, F, Q stay float32 throughout.
+    // The fp64 build reproduces the switch (FLAG_KF_F64); the fp32 build keeps the state in float (documented deviation,
+    // below its rtol 1e-3: the reference's float64 phase is then followed in float32).
     bool kf_init = (e.flags & FLAG_KF_INIT) != 0;
+    if constexpr (std::is_same<R, double>::value) {
+        bool x64 = (e.flags & FLAG_KF_F64) != 0;
+        if (o_det || dg_det) {
+            const bool z64 = dg_det && dg_f64;
+            double zx, zy, zz;
+            const float ow = P.radar_quality;
+            if (o_det && dg_det) {  // quality-weighted fusion, core.py:734-739; total_weight is float32
+                const float tw = add(ow, dgq);
+                if (z64) {
+                    zx = add((double)ipx, dvd(add((double)mul(orx, ow), mul(dgx, (double)dgq)), (double)tw));
+                    zy = add((double)ipy, dvd(add((double)mul(ory, ow), mul(dgy, (double)dgq)), (double)tw));
+                    zz = add((double)ipz, dvd(add((double)mul(orz, ow), mul(dgz, (double)dgq)), (double)tw));
+                } else {            // the delayed ground sample is the float32 zero placeholder of a non-detection
+                    zx = (double)add(ipx, dvd(add(mul(orx, ow), mul((float)dgx, dgq)), tw));
+                    zy = (double)add(ipy, dvd(add(mul(ory, ow), mul((float)dgy, dgq)), tw));
+                    zz = (double)add(ipz, dvd(add(mul(orz, ow), mul((float)dgz, dgq)), tw));
+                }
+            } else if (o_det) {
+                zx = (double)add(ipx, orx); zy = (double)add(ipy, ory); zz = (double)add(ipz, orz);
+            } else if (z64) {
+                zx = add((double)ipx, dgx); zy = add((double)ipy, dgy); zz = add((double)ipz, dgz);
+            } else {
+                zx = (double)add(ipx, (float)dgx); zy = (double)add(ipy, (float)dgy); zz = (double)add(ipz, (float)dgz);
+            }
+            if (!kf_init) {  // first measurement only initialises (core.py:93-96): assignment into the float32 state array
+                e.kpx = (double)(float)zx; e.kpy = (double)(float)zy; e.kpz = (double)(float)zz;
+                e.kvx = e.kvy = e.kvz = 0.0;
+                kf_init = true;
+            } else {
+                const float Si = dvd(1.f, add(e.Ppp, 400.f));   // inv(S): exact reciprocal of the diagonal innovation block
+                const float Kp = mul(e.Ppp, Si), Kv = mul(e.Pvp, Si);
+                if (x64 || z64) {   // state = state + K @ y in float64
+                    const double yx = sub(zx, e.kpx), yy = sub(zy, e.kpy), yz = sub(zz, e.kpz);
+                    e.kpx = add(e.kpx, mul((double)Kp, yx)); e.kpy = add(e.kpy, mul((double)Kp, yy)); e.kpz = add(e.kpz, mul((double)Kp, yz));
+                    e.kvx = add(e.kvx, mul((double)Kv, yx)); e.kvy = add(e.kvy, mul((double)Kv, yy)); e.kvz = add(e.kvz, mul((double)Kv, yz));
+                    x64 = true;
+                } else {            // ... in float32
+                    const float yx = sub((float)zx, (float)e.kpx), yy = sub((float)zy, (float)e.kpy), yz = sub((float)zz, (float)e.kpz);
+                    e.kpx = (double)add((float)e.kpx, mul(Kp, yx)); e.kpy = (double)add((float)e.kpy, mul(Kp, yy));
+                    e.kpz = (double)add((float)e.kpz, mul(Kp, yz));
+                    e.kvx = (double)add((float)e.kvx, mul(Kv, yx)); e.kvy = (double)add((float)e.kvy, mul(Kv, yy));
+                    e.kvz = (double)add((float)e.kvz, mul(Kv, yz));
+                }
+                // P = (I - K H) @ P, float32, sgemm accumulation order (FMA chain over k, oracle matmul66)
+                const float a = sub(1.f, Kp);
+                const float npp = mul(a, e.Ppp), npv = mul(a, e.Ppv);
+                const float nvp = add(mul(-Kv, e.Ppp), e.Pvp), nvv = add(mul(-Kv, e.Ppv), e.Pvv);
+                e.Ppp = npp; e.Ppv = npv; e.Pvp = nvp; e.Pvv = nvv;
+            }
+        } else if (kf_init) {  // predict only when no measurement (quirk Q4)
+            if (x64) {
+                const double d = (double)P.dtf;
+                e.kpx = add(e.kpx, mul(d, e.kvx)); e.kpy = add(e.kpy, mul(d, e.kvy)); e.kpz = add(e.kpz, mul(d, e.kvz));
+            } else {
+                e.kpx = (double)add((float)e.kpx, mul(P.dtf, (float)e.kvx)); e.kpy = (double)add((float)e.kpy, mul(P.dtf, (float)e.kvy));
+                e.kpz = (double)add((float)e.kpz, mul(P.dtf, (float)e.kvz));
+            }
+            const float fpp = __fmaf_rn(P.dtf, e.Pvp, e.Ppp), fpv = __fmaf_rn(P.dtf, e.Pvv, e.Ppv);  // F @ P
+            const float cpp = __fmaf_rn(fpv, P.dtf, fpp), cvp = __fmaf_rn(e.Pvv, P.dtf, e.Pvp);      // (F P) @ F^T
+            e.Ppp = add(cpp, P.q_pp); e.Ppv = add(fpv, P.q_pv); e.Pvp = add(cvp, P.q_pv); e.Pvv = add(e.Pvv, P.q_vv);
+        }
+        e.flags = (e.flags & ~(FLAG_KF_INIT | FLAG_KF_F64)) | (kf_init ? FLAG_KF_INIT : 0) | (x64 ? FLAG_KF_F64 : 0);
+    } else {
     if (o_det || dg_det) {
         W zx, zy, zz;
         if (o_det && dg_det) {  // quality-weighted fusion, core.py:734-739
@@ -633,6 +692,7 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
         e.Ppp = cpp + P.q_pp; e.Ppv = fpv + P.q_pv; e.Pvp = cvp + P.q_pv; e.Pvv = e.Pvv + P.q_vv;
     }
     e.flags = (e.flags & ~FLAG_KF_INIT) | (kf_init ? FLAG_KF_INIT : 0);
+    }
 
     const int mode = FT::obs_mode(P);
     LosBasis<W> lb;
@@ -1329,6 +1389,18 @@ HD void flush_obs_tile(const float* tile, float* dst, int64_t warp_first_env, in
     }
     __syncwarp();
 }
+// narrow observation rows (obs_dim < 26: the 17-D radar layout obs[0:17], rl_system/hrl/observation_schema.py:13-46): the warp
+// streams rows * dim floats out linearly (coalesced 128-byte stores), gathering them from the 26-word tile rows
+__device__ __noinline__ void flush_obs_narrow(const float* tile, float* base, int rows, int dim, unsigned lane) {
+    const int total = rows * dim;
+    for (int idx = (int)lane; idx < total; idx += 32) {
+        const int r = idx / dim;
+        base[idx] = tile[r * HLYNR_OBS_DIM + (idx - r * dim)];
+    }
+}
+__device__ __noinline__ void copy_obs_row_n(const float* row, float* dst_row, int dim) {
+    for (int k = 0; k < dim; ++k) dst_row[k] = row[k];
+}
 // this lane's row of the tile -> one row of a [N,26] array (terminal observation of a finished episode: rare)
 __device__ __noinline__ void copy_obs_row(const float* row, float* dst_row) {
 #pragma unroll
@@ -1376,6 +1448,8 @@ __device__ __noinline__ void write_info_slow(const KernelArgs<R>& A, int64_t i, 
     if (f.missile_pos) { f.missile_pos[3 * i] = mx; f.missile_pos[3 * i + 1] = my; f.missile_pos[3 * i + 2] = mz; }
     if (f.episode_return) f.episode_return[i] = ep_ret;
     if (f.episode_length) f.episode_length[i] = steps;
+    if (f.radar_quality)   // 0.0 while the onboard delay buffer fills (core.py:579-584), else the configured quality
+        f.radar_quality[i] = (A.P.onboard_delay > 0 && steps < FLAG_ODELAY(eflags)) ? 0.f : A.P.radar_quality;
     if (f.missiles_intercepted && f.missiles_remaining && f.missile_min_distances)  // environment.py:844-848 (all three or none)
         volley_info(A, i, eflags, distance, intercepted, f.missiles_intercepted + i, f.missiles_remaining + i,
                     f.missile_min_distances + (int64_t)HLYNR_MAX_VOLLEY * i);
@@ -1410,7 +1484,8 @@ __device__ __noinline__ void record_done(const KernelArgs<R>& A, int64_t i, int 
                                          float distance, float min_d, float fuel, float fuel_used, float ep_ret, float ix, float iy,
                                          float iz, float mx, float my, float mz, const float* obs_row) {
     const uint32_t flags = info_flags(eflags, intercepted, hit, clamped, onboard_det, ground_det, fuze) |
-                           (terminated ? HLYNR_DONE_TERMINATED : 0u) | (truncated ? HLYNR_DONE_TRUNCATED : 0u);
+                           (terminated ? HLYNR_DONE_TERMINATED : 0u) | (truncated ? HLYNR_DONE_TRUNCATED : 0u) |
+                           ((A.P.onboard_delay > 0 && steps < FLAG_ODELAY(eflags)) ? HLYNR_DONE_ONBOARD_FILL : 0u);
     const int32_t slot = append_done_record(A.io.done_records, A.io.done_counter, A.io.done_cap, (int32_t)i, steps, flags, distance,
                                             min_d, fuel, fuel_used, ep_ret, ix, iy, iz, mx, my, mz, obs_row);
     if (slot >= 0) {
@@ -1476,8 +1551,14 @@ template <typename R, int F> HD void prefetch_ring_reads(const KernelArgs<R>& A,
 // kernels
 // ------------------------------------------------------------------------------------------------
 // step(): one tick of every env + SB3 auto-reset.  kRollout: k fused ticks, state stays in registers.
+// CTAs per SM: 4 for the fp32 build (<= 128 registers, no spills).  The fp64 build holds ~60 doubles of env state (120
+// registers) before any temporaries: at 4 CTAs per SM it spills, so it runs at HLYNR_F64_MIN_BLOCKS (2 = up to 255 registers).
+#ifndef HLYNR_F64_MIN_BLOCKS
+#define HLYNR_F64_MIN_BLOCKS 2
+#endif
+template <typename R> struct StepOcc { static constexpr int ctas = std::is_same<R, double>::value ? HLYNR_F64_MIN_BLOCKS : 4; };
 template <typename R, bool kRollout, int F>
-__global__ void __launch_bounds__(HLYNR_STEP_BLOCK, 4 * (HLYNR_BLOCK / HLYNR_STEP_BLOCK))
+__global__ void __launch_bounds__(HLYNR_STEP_BLOCK, StepOcc<R>::ctas * (HLYNR_BLOCK / HLYNR_STEP_BLOCK))
 step_kernel(const __grid_constant__ KernelArgs<R> A) {
     __shared__ __align__(16) float tiles[HLYNR_STEP_BLOCK / 32][OBS_TILE];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -1530,7 +1611,7 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
             }
             // ring planes are indexed by the lane's OWN (padded) slot: a shadow lane of another warp may run ticks
             // ahead in a fused rollout and must never touch the rows of the env it shadows
-            observe<R, F>(A, e, key, ur, i, g_row, o_row, RingPre<R>{}, ob);
+            observe<R, F>(A, e, key, ur, i, g_row, o_row, ob);
             if (pass == 0) {
                 const bool done = t.terminated || t.truncated;
                 if (ob.onboard_det) locks += 1;
@@ -1551,7 +1632,10 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
                 need_reset = done && A.auto_reset;
                 if (need_reset) {
                     dcount += 1;
-                    if (!kRollout && active && A.io.terminal_obs) copy_obs_row(ob.row, A.io.terminal_obs + i * HLYNR_OBS_DIM);
+                    if (!kRollout && active && A.io.terminal_obs) {
+                        if (A.obs_dim == HLYNR_OBS_DIM) copy_obs_row(ob.row, A.io.terminal_obs + i * HLYNR_OBS_DIM);
+                        else copy_obs_row_n(ob.row, A.io.terminal_obs + i * A.obs_dim, A.obs_dim);
+                    }
                 }
             }
         }
@@ -1561,7 +1645,15 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
             if (s + 1 < steps) prefetch_ring_reads<R, F>(A, i, g_row, o_row);
         }
     }
-    if (A.io.obs) flush_obs_tile(tiles[warp], A.io.obs, warp_first, A.lim, lane);
+    if (A.io.obs) {
+        if (A.obs_dim == HLYNR_OBS_DIM) flush_obs_tile(tiles[warp], A.io.obs, warp_first, A.lim, lane);
+        else {
+            __syncwarp();
+            const int64_t rows = A.lim - warp_first;
+            if (rows > 0) flush_obs_narrow(tiles[warp], A.io.obs + warp_first * A.obs_dim, rows >= 32 ? 32 : (int)rows, A.obs_dim, lane);
+            __syncwarp();
+        }
+    }
     if (kRollout && active) {
         if (A.io.reward_sum) A.io.reward_sum[i] = rsum;
         if (A.io.done_count) A.io.done_count[i] = dcount;
@@ -1570,349 +1662,6 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
     {   // onboard-lock ticks: one atomic per warp that saw a lock, spread over the stat slots
         const int wl = __reduce_add_sync(0xffffffffu, active ? locks : 0);
         if (lane == 0 && wl) atomicAdd(A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS + 13, (double)wl);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Persistent step kernel with TMA-prefetched tiles (fp32 build, API mode).
-//
-// The direct kernel above is latency-bound: every warp waits ~1 us for its 11 plane loads before ~1.9 k
-// instructions of arithmetic, with only ~16 warps resident per SM.  Here each CTA owns a 128-env tile buffer in
-// shared memory that one elected thread fills with 1-D bulk copies (cp.async.bulk -> UBLKCP, completion on an
-// mbarrier): 2 KiB per state plane, the ring rows read this tick and the tile's actions.  As soon as every
-// thread has moved its env from the buffer into registers the NEXT tile's copies are issued, so they land
-// while the current tile computes.  Tiles are assigned round-robin to a persistent grid.
-// ------------------------------------------------------------------------------------------------
-#define TMA_TILE HLYNR_BLOCK
-#define TMA_MAX_PLANES 18
-
-struct TmaPlan {              // what one tile transfer consists of (built on the host)
-    const char* src[TMA_MAX_PLANES];   // global base of each source array
-    uint32_t stride[TMA_MAX_PLANES];   // bytes per env in that array (16 for planes, 24 for actions)
-    uint32_t smem_off[TMA_MAX_PLANES]; // byte offset of the copy inside the tile buffer
-    int32_t count;
-    int32_t actions_idx;               // index of the actions copy (skipped for a partial tile), or -1
-    uint32_t off_r[7], off_f[4], off_i0, off_oring, off_gring, off_actions, off_obs_tile, off_bar;
-    uint32_t tx_full;                  // bytes per full tile
-};
-
-HD uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-HD void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-HD void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-HD void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-HD bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-HD void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > (1u << 26)) __trap();  // never hang the GPU: a lost transfer becomes a launch failure
-}
-
-__device__ __forceinline__ void tma_issue_tile(const TmaPlan& T, uint32_t buf, uint32_t bar, int64_t tile, int rows) {
-    uint32_t tx = 0;
-#pragma unroll 1
-    for (int p = 0; p < T.count; ++p)
-        if (p != T.actions_idx || rows == TMA_TILE) tx += T.stride[p] * TMA_TILE;
-    mbar_expect_tx(bar, tx);
-#pragma unroll 1
-    for (int p = 0; p < T.count; ++p) {
-        if (p == T.actions_idx && rows != TMA_TILE) continue;
-        const uint32_t bytes = T.stride[p] * TMA_TILE;
-        bulk_g2s(buf + T.smem_off[p], T.src[p] + (size_t)tile * bytes, bytes, bar);
-    }
-}
-
-__global__ void __launch_bounds__(HLYNR_BLOCK, 4)
-step_kernel_tma(const __grid_constant__ KernelArgs<float> A, const __grid_constant__ TmaPlan T) {
-    typedef float R;
-    extern __shared__ __align__(128) unsigned char smem[];
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t buf = smem_u32(smem), bar = buf + T.off_bar;
-    float* tiles = reinterpret_cast<float*>(smem + T.off_obs_tile);
-    const int64_t n_tiles = (A.n + TMA_TILE - 1) / TMA_TILE;
-    int64_t tile = blockIdx.x;
-    if (tile >= n_tiles) return;
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int64_t left = A.n - tile * TMA_TILE;
-        tma_issue_tile(T, buf, bar, tile, left >= TMA_TILE ? TMA_TILE : (int)left);
-    }
-    uint32_t parity = 0;
-    int locks = 0;
-#pragma unroll 1
-    for (; tile < n_tiles; tile += gridDim.x) {
-        const int64_t i = tile * TMA_TILE + threadIdx.x;
-        const int64_t warp_first = i - lane;
-        const bool active = i < A.n;
-        const int64_t ii = active ? i : A.n - 1;
-        const int rows_here = (A.n - tile * TMA_TILE) >= TMA_TILE ? TMA_TILE : (int)(A.n - tile * TMA_TILE);
-        mbar_wait(bar, parity);
-        parity ^= 1u;
-        // ---- tile buffer -> registers ----
-        Env<R> e;
-        float act[6];
-        RingPre<R> pre;
-        {
-            const unsigned t = threadIdx.x;
-            const float4* pl;
-            float4 v;
-            pl = reinterpret_cast<const float4*>(smem + T.off_r[0]); v = pl[t]; e.ipx = v.x; e.ipy = v.y; e.ipz = v.z; e.fuel = v.w;
-            pl = reinterpret_cast<const float4*>(smem + T.off_r[1]); v = pl[t]; e.ivx = v.x; e.ivy = v.y; e.ivz = v.z; e.fuel_used = v.w;
-            pl = reinterpret_cast<const float4*>(smem + T.off_r[2]); v = pl[t]; e.mpx = v.x; e.mpy = v.y; e.mpz = v.z; e.prev_d = v.w;
-            pl = reinterpret_cast<const float4*>(smem + T.off_r[3]); v = pl[t]; e.mvx = v.x; e.mvy = v.y; e.mvz = v.z; e.last_d = v.w;
-            pl = reinterpret_cast<const float4*>(smem + T.off_r[4]); v = pl[t]; e.kpx = v.x; e.kpy = v.y; e.kpz = v.z; e.min_d = v.w;
-            pl = reinterpret_cast<const float4*>(smem + T.off_r[5]); v = pl[t]; e.kvx = v.x; e.kvy = v.y; e.kvz = v.z; e.ep_ret = v.w;
-            if (A.P.thrust_dyn | A.P.dr) {
-                pl = reinterpret_cast<const float4*>(smem + T.off_r[6]); v = pl[t]; e.thx = v.x; e.thy = v.y; e.thz = v.z; e.T0 = v.w;
-            } else { e.thx = e.thy = e.thz = 0.f; e.T0 = 288.15f; }
-            pl = reinterpret_cast<const float4*>(smem + T.off_f[0]); v = pl[t]; e.qw = v.x; e.qx = v.y; e.qy = v.z; e.qz = v.w;
-            pl = reinterpret_cast<const float4*>(smem + T.off_f[1]); v = pl[t]; e.wx = v.x; e.wy = v.y; e.wz = v.z; e.Ppp = v.w;
-            pl = reinterpret_cast<const float4*>(smem + T.off_f[2]); v = pl[t]; e.Ppv = v.x; e.Pvp = v.y; e.Pvv = v.z; e.base_cd = v.w;
-            if (A.P.dr) { pl = reinterpret_cast<const float4*>(smem + T.off_f[3]); e.peak = pl[t].x; } else e.peak = 0.f;
-            const int4 q = reinterpret_cast<const int4*>(smem + T.off_i0)[t];
-            e.steps = q.x; e.worsen = q.y; e.flags = q.z; e.episode = q.w;
-            pre.o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (A.P.onboard_delay > 0 && !A.P.dr) pre.o = reinterpret_cast<const float4*>(smem + T.off_oring)[t];
-            pre.ga = Vec4<R>{0.f, 0.f, 0.f, 0.f}; pre.gb = pre.ga;
-            if (A.P.ground_delay > 0) {
-                const float4 a = reinterpret_cast<const float4*>(smem + T.off_gring)[t];
-                const float4 b = reinterpret_cast<const float4*>(smem + T.off_gring)[TMA_TILE + t];
-                pre.ga = Vec4<R>{a.x, a.y, a.z, a.w}; pre.gb = Vec4<R>{b.x, b.y, b.z, b.w};
-            }
-            if (rows_here == TMA_TILE) {
-                const float2* ap = reinterpret_cast<const float2*>(smem + T.off_actions) + 3 * t;
-                const float2 p0 = ap[0], p1 = ap[1], p2 = ap[2];
-                act[0] = p0.x; act[1] = p0.y; act[2] = p1.x; act[3] = p1.y; act[4] = p2.x; act[5] = p2.y;
-            } else {
-                const float2* ap = reinterpret_cast<const float2*>(A.io.actions + ii * HLYNR_ACT_DIM);
-                const float2 p0 = __ldg(ap), p1 = __ldg(ap + 1), p2 = __ldg(ap + 2);
-                act[0] = p0.x; act[1] = p0.y; act[2] = p1.x; act[3] = p1.y; act[4] = p2.x; act[5] = p2.y;
-            }
-        }
-        __syncthreads();  // every thread has drained the tile buffer
-        if (threadIdx.x == 0) {
-            const int64_t nt = tile + gridDim.x;
-            if (nt < n_tiles) {
-                const int64_t left = A.n - nt * TMA_TILE;
-                tma_issue_tile(T, buf, bar, nt, left >= TMA_TILE ? TMA_TILE : (int)left);
-            }
-        }
-        // ---- one tick + SB3 auto-reset (same device functions as the direct kernel) ----
-        const RngKey key = make_key(A, A.env_offset + ii);
-        TickOut t;
-        tick_physics<R, FT_GENERIC>(A, e, key, act, i, t);
-        ObsOut ob;
-        ob.row = tiles + warp * OBS_TILE + lane * HLYNR_OBS_DIM;
-        ob.emit = true;
-        uint4 ur = t.ur;
-        bool need_reset = false;
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            if (pass == 1) {
-                if (!need_reset) break;
-                e.episode += 1;
-                ur = spawn(A, e, key, i);
-            }
-            observe<R, FT_GENERIC, true>(A, e, key, ur, i, A.g_row, A.o_row, pre, ob);  // i < n_pad: padded lanes touch only padding
-            if (pass == 0) {
-                const bool done = t.terminated || t.truncated;
-                if (active && ob.onboard_det) locks += 1;
-                if (active) {
-                    A.io.reward[i] = t.reward;
-                    A.io.terminated[i] = t.terminated ? 1 : 0;
-                    if (A.io.done) A.io.done[i] = (t.terminated || t.truncated) ? 1 : 0;
-                    A.io.truncated[i] = t.truncated ? 1 : 0;
-                    if (A.has_info) write_info(A, i, e, t, ob);
-                }
-                account_episodes(A, active, done, e, t);
-                need_reset = done && A.auto_reset;
-                if (need_reset && active && A.io.terminal_obs) copy_obs_row(ob.row, A.io.terminal_obs + i * HLYNR_OBS_DIM);
-            }
-        }
-        if (A.io.obs) flush_obs_tile(tiles + warp * OBS_TILE, A.io.obs, warp_first, A.n, lane);
-        if (active) store_env(A, i, e);
-    }
-    const int wl = __reduce_add_sync(0xffffffffu, locks);
-    if (lane == 0 && wl) atomicAdd(A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS + 13, (double)wl);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Persistent-warp step kernel with per-thread cp.async staging (fp32 build, API mode, specialised feature sets).
-//
-// The direct kernel's warps wait for their up-front plane loads with nothing else to do; here a warp owns a private
-// shared-memory slot per lane per plane, fetches warp-sized tiles (32 envs) dynamically off an atomic counter, and as
-// soon as it has moved tile t from the slots into registers it issues the cp.async copies of tile t+1 into the SAME
-// slots -- each lane only ever touches its own 16-byte slots, so there is no barrier of any kind -- and they land while
-// tile t computes.  The ring samples a tick reads and the tile's actions are staged the same way.
-// ------------------------------------------------------------------------------------------------
-#define PIPE_PLANES 15   // r0..r6, f0..f3, i0, onboard ring slot, ground ring slot (2 planes)
-#define PIPE_WARPS (HLYNR_BLOCK / 32)
-struct PipeSmem {
-    float4 plane[PIPE_WARPS][PIPE_PLANES][32];  // [warp][plane][lane]: conflict-free LDS.128
-    float2 act[PIPE_WARPS][3][32];              // the lane's 6 action floats as 3 x 8 bytes
-    float tiles[PIPE_WARPS][OBS_TILE];
-};
-HD void cp_async16(void* smem, const void* g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(g) : "memory"); }
-HD void cp_async8(void* smem, const void* g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(g) : "memory"); }
-HD void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-HD void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-template <int F>
-HD void pipe_issue(const KernelArgs<float>& A, PipeSmem* sm, unsigned warp, unsigned lane, int64_t ii, int64_t ring_i) {
-    typedef Feat<F> FT;
-    const StatePlanes<float>& s = A.st;
-    float4(*pl)[32] = sm->plane[warp];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) cp_async16(&pl[k][lane], s.r[k] + ii);
-    if (FT::thrust_dyn(A.P) || FT::dr(A.P)) cp_async16(&pl[6][lane], s.r[6] + ii);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) cp_async16(&pl[7 + k][lane], s.f[k] + ii);
-    if (FT::dr(A.P)) cp_async16(&pl[10][lane], s.f[3] + ii);
-    cp_async16(&pl[11][lane], s.i0 + ii);
-    const int64_t n = A.ring_stride;
-    if (FT::onboard_delay(A.P) && !FT::dr(A.P)) {
-        int rrow = A.o_row - A.P.onboard_delay;
-        if (rrow < 0) rrow += A.P.onb_ring_len;
-        cp_async16(&pl[12][lane], s.oring + (int64_t)rrow * n + ring_i);
-    }
-    if (FT::ground(A.P) && FT::ground_delay(A.P)) {
-        const int rrow = A.g_row + 1 == A.P.gnd_ring_len ? 0 : A.g_row + 1;
-        const Vec4<float>* rr = s.gring + (int64_t)rrow * 2 * n;
-        cp_async16(&pl[13][lane], rr + ring_i);
-        cp_async16(&pl[14][lane], rr + n + ring_i);
-    }
-    const float2* ap = reinterpret_cast<const float2*>(A.io.actions + ii * HLYNR_ACT_DIM);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) cp_async8(&sm->act[warp][k][lane], ap + k);
-    cp_async_commit();
-}
-
-// counters[0] = next warp-tile to hand out, counters[1] = warps that have drained the queue (the last one resets both)
-template <int F>
-__global__ void __launch_bounds__(HLYNR_BLOCK, 4) step_kernel_pipe(const __grid_constant__ KernelArgs<float> A, unsigned int* counters) {
-    typedef float R;
-    typedef Feat<F> FT;
-    extern __shared__ __align__(16) unsigned char pipe_smem_raw[];
-    PipeSmem* sm = reinterpret_cast<PipeSmem*>(pipe_smem_raw);
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const int64_t n_tiles = (A.lim - A.first + 31) / 32;
-    auto grab = [&]() -> int64_t {
-        unsigned int t = 0;
-        if (lane == 0) t = atomicAdd(&counters[0], 1u);
-        return (int64_t)__shfl_sync(0xffffffffu, t, 0);
-    };
-    int locks = 0;
-    int64_t tile = grab();
-    if (tile < n_tiles) {
-        const int64_t i0 = A.first + tile * 32 + lane;
-        pipe_issue<F>(A, sm, warp, lane, i0 < A.lim ? i0 : A.lim - 1, i0);
-    }
-#pragma unroll 1
-    while (tile < n_tiles) {
-        const int64_t i = A.first + tile * 32 + lane;
-        const int64_t warp_first = i - lane;
-        const bool active = i < A.lim;
-        const int64_t ii = active ? i : A.lim - 1;
-        const int64_t next = grab();   // its latency hides behind the wait below
-        cp_async_wait_all();
-        // ---- slots -> registers ----
-        Env<R> e;
-        float act[6];
-        RingPre<R> pre;
-        {
-            float4(*pl)[32] = sm->plane[warp];
-            float4 v;
-            v = pl[0][lane]; e.ipx = v.x; e.ipy = v.y; e.ipz = v.z; e.fuel = v.w;
-            v = pl[1][lane]; e.ivx = v.x; e.ivy = v.y; e.ivz = v.z; e.fuel_used = v.w;
-            v = pl[2][lane]; e.mpx = v.x; e.mpy = v.y; e.mpz = v.z; e.prev_d = v.w;
-            v = pl[3][lane]; e.mvx = v.x; e.mvy = v.y; e.mvz = v.z; e.last_d = v.w;
-            v = pl[4][lane]; e.kpx = v.x; e.kpy = v.y; e.kpz = v.z; e.min_d = v.w;
-            v = pl[5][lane]; e.kvx = v.x; e.kvy = v.y; e.kvz = v.z; e.ep_ret = v.w;
-            if (FT::thrust_dyn(A.P) || FT::dr(A.P)) { v = pl[6][lane]; e.thx = v.x; e.thy = v.y; e.thz = v.z; e.T0 = v.w; }
-            else { e.thx = e.thy = e.thz = 0.f; e.T0 = 288.15f; }
-            v = pl[7][lane]; e.qw = v.x; e.qx = v.y; e.qy = v.z; e.qz = v.w;
-            v = pl[8][lane]; e.wx = v.x; e.wy = v.y; e.wz = v.z; e.Ppp = v.w;
-            v = pl[9][lane]; e.Ppv = v.x; e.Pvp = v.y; e.Pvv = v.z; e.base_cd = v.w;
-            if (FT::dr(A.P)) e.peak = pl[10][lane].x; else e.peak = 0.f;
-            const int4 q = *reinterpret_cast<const int4*>(&pl[11][lane]);
-            e.steps = q.x; e.worsen = q.y; e.flags = q.z; e.episode = q.w;
-            pre.o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (FT::onboard_delay(A.P) && !FT::dr(A.P)) pre.o = pl[12][lane];
-            pre.ga = Vec4<R>{0.f, 0.f, 0.f, 0.f}; pre.gb = pre.ga;
-            if (FT::ground(A.P) && FT::ground_delay(A.P)) {
-                const float4 a = pl[13][lane], b = pl[14][lane];
-                pre.ga = Vec4<R>{a.x, a.y, a.z, a.w}; pre.gb = Vec4<R>{b.x, b.y, b.z, b.w};
-            }
-            const float2 p0 = sm->act[warp][0][lane], p1 = sm->act[warp][1][lane], p2 = sm->act[warp][2][lane];
-            act[0] = p0.x; act[1] = p0.y; act[2] = p1.x; act[3] = p1.y; act[4] = p2.x; act[5] = p2.y;
-        }
-        if (next < n_tiles) {   // the slots are free again: stage the next tile while this one computes
-            const int64_t j = A.first + next * 32 + lane;
-            pipe_issue<F>(A, sm, warp, lane, j < A.lim ? j : A.lim - 1, j);
-        }
-        // ---- one tick + SB3 auto-reset (same device functions as the direct kernel) ----
-        const RngKey key = make_key(A, A.env_offset + ii);
-        TickOut t;
-        tick_physics<R, F>(A, e, key, act, i, t);
-        ObsOut ob;
-        ob.row = sm->tiles[warp] + lane * HLYNR_OBS_DIM;
-        ob.emit = true;
-        uint4 ur = t.ur;
-        bool need_reset = false;
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            if (pass == 1) {
-                if (!need_reset) break;
-                e.episode += 1;
-                ur = spawn(A, e, key, i);
-            }
-            observe<R, F, true>(A, e, key, ur, i, A.g_row, A.o_row, pre, ob);   // pass 1: steps == 0 < delay, `pre` is not read
-            if (pass == 0) {
-                const bool done = t.terminated || t.truncated;
-                if (active && ob.onboard_det) locks += 1;
-                if (active) {
-                    A.io.reward[i] = t.reward;
-                    A.io.terminated[i] = t.terminated ? 1 : 0;
-                    if (A.io.done) A.io.done[i] = (t.terminated || t.truncated) ? 1 : 0;
-                    A.io.truncated[i] = t.truncated ? 1 : 0;
-                    if (A.has_info) write_info(A, i, e, t, ob);
-                }
-                account_episodes(A, active, done, e, t);
-                if (done && active && A.io.done_records) {
-                    record_done<R>(A, i, e.steps, e.flags, t.terminated, t.truncated, t.intercepted, t.hit, t.clamped, ob.onboard_det,
-                                   ob.ground_det, t.fuze, t.distance, (float)e.min_d, (float)e.fuel, (float)e.fuel_used, (float)e.ep_ret,
-                                   (float)e.ipx, (float)e.ipy, (float)e.ipz, (float)e.mpx, (float)e.mpy, (float)e.mpz, ob.row);
-                }
-                need_reset = done && A.auto_reset;
-                if (need_reset && active && A.io.terminal_obs) copy_obs_row(ob.row, A.io.terminal_obs + i * HLYNR_OBS_DIM);
-            }
-        }
-        if (A.io.obs) flush_obs_tile(sm->tiles[warp], A.io.obs, warp_first, A.lim, lane);
-        if (active) store_env<R, F>(A, i, e);
-        tile = next;
-    }
-    const int wl = __reduce_add_sync(0xffffffffu, locks);
-    if (lane == 0) {
-        if (wl) atomicAdd(A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS + 13, (double)wl);
-        // every warp of the grid passes here exactly once; the last one re-arms the queue for the next launch
-        const unsigned int total = gridDim.x * PIPE_WARPS;
-        if (atomicAdd(&counters[1], 1u) + 1u == total) { counters[0] = 0u; counters[1] = 0u; }
     }
 }
 
@@ -1931,9 +1680,9 @@ template <typename R> __global__ void __launch_bounds__(HLYNR_BLOCK) reset_kerne
     ob.emit = true;
     e.episode += 1;
     const uint4 ur = spawn(A, e, key, i);
-    observe<R, FT_GENERIC_MODES>(A, e, key, ur, i, A.g_row, A.o_row, RingPre<R>{}, ob);
+    observe<R, FT_GENERIC_MODES>(A, e, key, ur, i, A.g_row, A.o_row, ob);
     store_env(A, i, e);
-    if (A.io.obs) copy_obs_row(ob.row, A.io.obs + i * HLYNR_OBS_DIM);
+    if (A.io.obs) copy_obs_row_n(ob.row, A.io.obs + i * A.obs_dim, A.obs_dim);
 }
 
 }  // namespace hlynr

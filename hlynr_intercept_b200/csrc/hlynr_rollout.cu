@@ -27,7 +27,16 @@ __global__ void bootstrap_kernel(float* __restrict__ rewards, const HlynrDoneRec
             rewards[e] = __fadd_rn(rewards[e], __fmul_rn(gamma, tv[r]));
         }
     }
-    if (overflow && blockIdx.x == 0 && threadIdx.x == 0 && count > rows) atomicAdd(overflow, count - rows);
+    // records beyond `rows` got no value: count the ones that NEEDED one (truncated and not terminated) -- a non-zero *overflow
+    // means timeouts went without their gamma * V(terminal_observation)
+    if (overflow && count > rows) {
+        int32_t missed = 0;
+        for (int32_t r = rows + blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x) {
+            const uint32_t fl = recs[r].flags;
+            missed += ((fl & HLYNR_DONE_TRUNCATED) && !(fl & HLYNR_DONE_TERMINATED)) ? 1 : 0;
+        }
+        if (missed) atomicAdd(overflow, missed);
+    }
 }
 
 // one thread per env, reverse scan over T; every access is coalesced over N

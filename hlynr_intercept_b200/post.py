@@ -30,6 +30,8 @@ class HlynrObsPipeline:
             raise NotImplementedError("norm_reward=True is not on the reference's path (train_flat_ppo.py:395)")
         import torch
 
+        if getattr(sim, "obs_dim", abi.OBS_DIM) != abi.OBS_DIM:
+            raise ValueError("HlynrObsPipeline stacks the full 26-D frames: create the HlynrSim with obs_dim=26")
         self.sim, self.L, self._torch = sim, sim.L, torch
         self.n_stack, self.training, self.norm_obs = int(n_stack), bool(training), bool(norm_obs)
         self.clip_obs, self.clip_reward, self.gamma, self.epsilon = float(clip_obs), float(clip_reward), float(gamma), float(epsilon)
@@ -159,15 +161,28 @@ class HlynrObsPipeline:
         assert int(z["n_stack"]) == self.n_stack, "frame_stack of the statistics differs"
         self.set_stats(z["mean"], z["var"], float(z["count"]), float(z["ret_mean"]), float(z["ret_var"]), float(z["ret_count"]))
 
-    def load_sb3_pickle(self, path):
-        """Statistics from a vec_normalize.pkl written by the reference (needs stable_baselines3 for unpickling)."""
-        import pickle
+    def save_sb3_pickle(self, path):
+        """`VecNormalize.save(path)` (scripts/train_flat_ppo.py:477,530): a vec_normalize.pkl that `VecNormalize.load` of
+        inference.py:163-170 accepts -- the wrapper object pickled under SB3's module paths with the device-side statistics
+        (sb3_pickle.py; works without stable_baselines3 installed; parity unpinned, see there)."""
+        from . import sb3_pickle
 
-        with open(path, "rb") as f:
-            vn = pickle.load(f)
-        self.set_stats(vn.obs_rms.mean, vn.obs_rms.var, vn.obs_rms.count, float(vn.ret_rms.mean), float(vn.ret_rms.var), vn.ret_rms.count)
-        if (float(vn.clip_obs), float(vn.epsilon)) != (self.clip_obs, self.epsilon):
+        s = self.get_stats()
+        sb3_pickle.dump(path, mean=s["mean"], var=s["var"], count=s["count"], ret_mean=s["ret_mean"], ret_var=s["ret_var"],
+                        ret_count=s["ret_count"], obs_shape=(self.obs_dim,), num_envs=self.sim.n, clip_obs=self.clip_obs,
+                        clip_reward=self.clip_reward, gamma=self.gamma, epsilon=self.epsilon, training=self.training,
+                        norm_obs=self.norm_obs, norm_reward=False)
+
+    def load_sb3_pickle(self, path):
+        """Statistics from a vec_normalize.pkl written by the reference's trainer or by save_sb3_pickle()."""
+        from . import sb3_pickle
+
+        d = sb3_pickle.load(path)
+        if d["obs_shape"] != (self.obs_dim,):
+            raise ValueError(f"the pickle normalises observations of shape {d['obs_shape']}, this pipeline {(self.obs_dim,)}")
+        if (d["clip_obs"], d["epsilon"]) != (self.clip_obs, self.epsilon):
             raise ValueError("clip_obs / epsilon of the pickle differ from this pipeline's")
+        self.set_stats(d["mean"], d["var"], d["count"], d["ret_mean"], d["ret_var"], d["ret_count"])
 
     def check_sums(self, resync=False):
         d = C.c_double()

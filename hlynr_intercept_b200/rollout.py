@@ -82,7 +82,10 @@ class DeviceRolloutCollector:
         self.returns = torch.empty((self.T, n), dtype=f32, device=dev)
         self.last_dones = torch.ones(n, dtype=torch.uint8, device=dev)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.rows = int(bootstrap_rows) if bootstrap_rows else min(n, max(256, n // 32))
+        # rows of the done list whose terminal observation gets a value (TimeLimit bootstrap).  Default: ALL n -- after a
+        # synchronised reset an untrained policy lets most envs time out in the SAME tick, and SB3 bootstraps every one of
+        # them.  A smaller bound is a speed knob for the value net; collect() then verifies that no timeout was left out.
+        self.rows = min(n, int(bootstrap_rows)) if bootstrap_rows else n
         self._started = False
         self.L = pipe.L
         self._graph = None
@@ -125,6 +128,12 @@ class DeviceRolloutCollector:
             _lib.check(self.L.hlynr_gae(p(self.rewards), p(self.values), p(self.episode_starts), p(last_values), p(self.last_dones),
                                         self.T, sim.n, self.gamma, self.gae_lambda, p(self.advantages), p(self.returns),
                                         sim.device_index, self._stream()))
+        if self.rows < sim.n and not torch.cuda.is_current_stream_capturing():
+            missed = int(self.overflow.item())   # one synchronisation per rollout (the caller consumes the rollout next anyway)
+            if missed:
+                self.overflow.zero_()
+                raise RuntimeError(f"{missed} timed-out episodes of this rollout finished beyond bootstrap_rows={self.rows} and got no "
+                                   f"gamma * V(terminal_observation): create the collector with bootstrap_rows=None (all envs)")
         return self
 
     # ---- CUDA graph: the whole collect() (T x ~20 launches) as one graph launch --------------------------------------

@@ -5,9 +5,10 @@
 
 The reference imports `DummyVecEnv` / `SubprocVecEnv` by name (rl_system/scripts/train_flat_ppo.py:22,371;
 scripts/train_hrl_pretrain.py:349-361; inference.py:413).  Before running the target script this module patches
-`stable_baselines3.common.vec_env.{DummyVecEnv,SubprocVecEnv}` with a factory: it calls env_fns[0]() once, unwraps
-to the innermost env; if that is the reference's InterceptEnvironment with a configuration the accelerated path
-covers, it returns `HlynrVecEnv(env.config, n_envs=len(env_fns))`, otherwise it falls through to the real class.
+`stable_baselines3.common.vec_env.{DummyVecEnv,SubprocVecEnv}` with SUBCLASSES of themselves whose __new__ probes a few
+env_fns, unwraps to the innermost env and, if all of them are the reference's InterceptEnvironment with one and the same
+configuration that the accelerated path covers, returns `HlynrVecEnv(env.config, n_envs=len(env_fns))`; otherwise the
+real class is constructed as usual.
 
 stable_baselines3 / gymnasium are not installed in the build image, so this file can only be exercised where they
 are; the VecEnv contract itself is tested in tests/test_vec_env.py.
@@ -25,27 +26,60 @@ def _innermost(env):
     return env
 
 
-def make_factory(real_cls, device=0, seed=1234, precision="fp32"):
+def _same_config(a, b):
+    try:
+        return a == b
+    except Exception:   # numpy arrays inside the dicts
+        return repr(a) == repr(b)
+
+
+def make_factory(real_cls, device=0, seed=1234, precision="fp32", max_probes=8):
+    """A SUBCLASS of the real vec-env class (so `isinstance(x, DummyVecEnv)` / subclassing keep working) whose __new__ returns a
+    HlynrVecEnv when every probed env_fn builds the reference's InterceptEnvironment with one and the same configuration, and
+    otherwise falls through to the real class.  Up to `max_probes` env_fns are built (always the first and the last): the GPU
+    batch shares one configuration, so per-env differences must send the caller back to the reference's own path."""
     from .vec_env import HlynrVecEnv
 
-    def factory(env_fns, *args, **kwargs):
-        probe = env_fns[0]()
-        inner = _innermost(probe)
-        if type(inner).__name__ == "InterceptEnvironment" and hasattr(inner, "config"):
-            try:
-                venv = HlynrVecEnv(dict(inner.config), n_envs=len(env_fns), device=device, seed=seed, precision=precision)
-            except NotImplementedError as e:  # outside the accelerated path (e.g. volley_size > 8): use the reference env
-                print(f"[hlynr_intercept_b200] falling back to {real_cls.__name__}: {e}", file=sys.stderr)
-            else:
-                if hasattr(probe, "close"):
-                    probe.close()
-                return venv
-        rest = list(env_fns)
-        first = [probe]
-        rest[0] = lambda: first.pop() if first else env_fns[0]()   # do not build env 0 twice
-        return real_cls(rest, *args, **kwargs)
+    class Patched(real_cls):
+        def __new__(cls, env_fns, *args, **kwargs):
+            env_fns = list(env_fns)
+            n = len(env_fns)
+            idx = sorted({0, n - 1} | {round(k * (n - 1) / (max_probes - 1)) for k in range(max_probes)}) if n > 1 else [0]
+            probes = {}
+            accelerated, cfg0 = True, None
+            for i in idx:
+                probes[i] = env_fns[i]()
+                inner = _innermost(probes[i])
+                if not (type(inner).__name__ == "InterceptEnvironment" and hasattr(inner, "config")):
+                    accelerated = False
+                    break
+                if cfg0 is None:
+                    cfg0 = dict(inner.config)
+                elif not _same_config(cfg0, dict(inner.config)):
+                    print(f"[hlynr_intercept_b200] env_fns[{i}] has a different configuration than env_fns[0]: using "
+                          f"{real_cls.__name__}", file=sys.stderr)
+                    accelerated = False
+                    break
+            if accelerated:
+                try:
+                    venv = HlynrVecEnv(cfg0, n_envs=n, device=device, seed=seed, precision=precision)
+                except NotImplementedError as e:  # outside the accelerated path (e.g. volley_size > 8): use the reference env
+                    print(f"[hlynr_intercept_b200] falling back to {real_cls.__name__}: {e}", file=sys.stderr)
+                else:
+                    for p in probes.values():
+                        if hasattr(p, "close"):
+                            p.close()
+                    return venv   # not an instance of cls: Python skips __init__
+            obj = super().__new__(cls)
+            # the probes that were already built are handed to the real class instead of being built twice
+            obj._hlynr_env_fns = [(lambda p=probes[i]: p) if i in probes else f for i, f in enumerate(env_fns)]
+            return obj
 
-    return factory
+        def __init__(self, env_fns, *args, **kwargs):
+            super().__init__(self.__dict__.pop("_hlynr_env_fns", env_fns), *args, **kwargs)
+
+    Patched.__name__, Patched.__qualname__ = real_cls.__name__, real_cls.__qualname__
+    return Patched
 
 
 def patch_sb3(device=None, seed=None, precision=None):

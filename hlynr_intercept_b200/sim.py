@@ -13,7 +13,7 @@ from . import _lib, abi, config as _config
 
 class HlynrSim:
     def __init__(self, env_cfg=None, n_envs=1, device=0, seed=1234, env_id_offset=0, precision="fp32",
-                 params=None, curriculum=None, warn_dead=True):
+                 params=None, curriculum=None, warn_dead=True, obs_dim=26):
         import torch
 
         if not torch.cuda.is_available():
@@ -32,6 +32,9 @@ class HlynrSim:
         _lib.check(self.L.hlynr_create(C.byref(params), self.n, self.device_index, self.seed_value, self.env_id_offset,
                                        self.precision, C.byref(h)))
         self.h = h
+        self.obs_dim = int(obs_dim)
+        if self.obs_dim != 26:   # 17: the leading radar channels obs[0:17] only (include/hlynr.h, option "obs_dim")
+            _lib.check(self.L.hlynr_set_option(self.h, b"obs_dim", self.obs_dim))
         self.push_curriculum()
         self._torch = torch
         self._info_t = None
@@ -45,9 +48,9 @@ class HlynrSim:
         t = self._torch
         if self._out is None:
             n, d = self.n, self.device
-            self._out = dict(obs=t.empty((n, 26), dtype=t.float32, device=d), reward=t.empty(n, dtype=t.float32, device=d),
+            self._out = dict(obs=t.empty((n, self.obs_dim), dtype=t.float32, device=d), reward=t.empty(n, dtype=t.float32, device=d),
                              terminated=t.empty(n, dtype=t.uint8, device=d), truncated=t.empty(n, dtype=t.uint8, device=d),
-                             terminal_obs=t.full((n, 26), float("nan"), dtype=t.float32, device=d))
+                             terminal_obs=t.full((n, self.obs_dim), float("nan"), dtype=t.float32, device=d))
         return self._out
 
     def info_tensors(self):
@@ -159,6 +162,24 @@ class HlynrSim:
                                             uni.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p)))
         return raw, uni, nrm
 
+    def ring_period(self):
+        """A captured sequence of T ticks replays correctly iff T is a multiple of this (include/hlynr.h, CUDA-graph support)."""
+        per = C.c_int()
+        _lib.check(self.L.hlynr_ring_period(self.h, C.byref(per)))
+        return per.value
+
+    def tick_count(self):
+        v = C.c_int64()
+        _lib.check(self.L.hlynr_tick_count(self.h, C.byref(v)))
+        return v.value
+
+    def capture_steps(self, actions_seq, want_terminal_obs=False):
+        """Captures len(actions_seq) consecutive step() calls into ONE CUDA graph (small batches are launch-bound: a tick of 4096
+        envs is ~6 us of GPU work behind ~10 us of Python + launch overhead).  actions_seq: list of persistent float32 cuda
+        tensors [N,6] the caller refills between replays; its length must be a multiple of ring_period().  Returns a StepGraph
+        whose replay() runs the ticks and leaves the LAST tick's outputs in the tensors step() returns."""
+        return StepGraph(self, actions_seq, want_terminal_obs)
+
     def set_option(self, name, value):
         _lib.check(self.L.hlynr_set_option(self.h, name.encode(), int(value)))
 
@@ -177,6 +198,35 @@ class HlynrSim:
             self.close()
         except Exception:
             pass
+
+
+class StepGraph:
+    def __init__(self, sim, actions_seq, want_terminal_obs=False):
+        torch = sim._torch
+        T = len(actions_seq)
+        if T == 0 or T % sim.ring_period():
+            raise ValueError(f"a step graph needs a multiple of ring_period() = {sim.ring_period()} ticks, got {T}")
+        self.sim, self.T = sim, T
+        self.period = sim.ring_period()
+        self.phase = sim.tick_count() % self.period
+        sim._alloc_out()
+        torch.cuda.synchronize(sim.device)
+        l0 = sim.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):   # recorded, not executed: only the host-side tick counter advances ...
+            for a in actions_seq:
+                self.out = sim.step(a, want_terminal_obs=want_terminal_obs)
+        self.launches = sim.launch_count() - l0
+        # ... and is put back (ring phases are unchanged: T is a multiple of every ring length)
+        _lib.check(sim.L.hlynr_note_replayed_ticks(sim.h, -T, -self.launches))
+
+    def replay(self):
+        if self.sim.tick_count() % self.period != self.phase:   # the delay-ring rows are baked into the captured launches
+            raise _lib.HlynrError(f"StepGraph captured at tick phase {self.phase} (mod {self.period}) cannot replay at phase "
+                                  f"{self.sim.tick_count() % self.period}: step eagerly to the next multiple of ring_period() first")
+        self.graph.replay()
+        _lib.check(self.sim.L.hlynr_note_replayed_ticks(self.sim.h, self.T, self.launches))
+        return self.out
 
 
 def _tensor_from_ptr(torch, ptr, shape, dtype, device):

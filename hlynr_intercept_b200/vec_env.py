@@ -91,17 +91,30 @@ class LazyInfos(collections.abc.Sequence):
     reference's info dict (+ the SB3 done keys) when env i finished an episode in this step, materialised on first
     access and cached (so wrappers that patch infos[i]['terminal_observation'] in place keep working), and one shared
     empty dict otherwise.  Creating it is O(1) Python work; vectorised consumers read `.records` (structured array,
-    abi.done_record_numpy_dtype) and `.done_indices` instead of touching dicts at all."""
+    abi.done_record_numpy_dtype) and `.done_indices` instead of touching dicts at all.
+
+    With HlynrVecEnv(info_arrays=True) the per-step info of EVERY env (environment.py:829-857: distance, fuel_remaining,
+    radar flags ...) is available as well: `.arrays` is a dict of [N]-sized numpy arrays (fetched from the device on first
+    access; valid until the next step), and entry i of an unfinished env is then the reference's full info dict built from
+    row i instead of the shared empty dict."""
 
     def __init__(self, venv, records, now):
         self._venv, self.records, self._now = venv, records, now
         self._n = venv.num_envs
         self._index = None
         self._cache = {}
+        self._arrays = None
 
     @property
     def done_indices(self):
         return self.records["env"]
+
+    @property
+    def arrays(self):
+        """{name: array[N, ...]} of abi.INFO_FIELDS for the tick just executed (terminal tick for envs that finished)."""
+        if self._arrays is None:
+            self._arrays = self._venv._fetch_info_arrays()
+        return self._arrays
 
     def __len__(self):
         return self._n
@@ -118,7 +131,15 @@ class LazyInfos(collections.abc.Sequence):
             self._index = {e: k for k, e in enumerate(self.records["env"].tolist())}
         k = self._index.get(i)
         if k is None:
-            return self._venv._shared_info
+            if not self._venv.info_arrays:
+                return self._venv._shared_info
+            d = self._cache.get(-1 - i)
+            if d is None:
+                f = self.arrays
+                d = self._cache[-1 - i] = self._venv._info_dicts(*[f[nm][i:i + 1] for nm in (
+                    "flags", "distance", "min_distance", "fuel_remaining", "fuel_used", "steps", "missile_pos", "interceptor_pos",
+                    "missiles_intercepted", "missiles_remaining", "missile_min_distances", "radar_quality")])[0]
+            return d
         d = self._cache.get(k)
         if d is None:
             d = self._cache[k] = self._venv._done_info_dicts(self.records[k:k + 1], self._now)[0]
@@ -127,12 +148,13 @@ class LazyInfos(collections.abc.Sequence):
 
 class HlynrVecEnv(_VecEnvBase):
     def __init__(self, env_cfg=None, n_envs=1, device=0, seed=1234, env_id_offset=0, precision="fp32", warn_dead=True,
-                 lazy_infos=None, copy_outputs=None, radar_debug=None):
+                 lazy_infos=None, copy_outputs=None, radar_debug=None, obs_dim=26, info_arrays=False):
         self.sim = HlynrSim(env_cfg, n_envs=n_envs, device=device, seed=seed, env_id_offset=env_id_offset,
-                            precision=precision, warn_dead=warn_dead)
+                            precision=precision, warn_dead=warn_dead, obs_dim=obs_dim)
+        od = self.obs_dim = self.sim.obs_dim   # 26 = the reference's vector; 17 = its radar channels obs[0:17] (17-D layout)
         self.config = dict(env_cfg or {})
         n = self.sim.n
-        obs_space = _spaces.Box(low=-2.0, high=1.0, shape=(26,), dtype=np.float32)   # environment.py:192-194
+        obs_space = _spaces.Box(low=-2.0, high=1.0, shape=(od,), dtype=np.float32)   # environment.py:192-194
         act_space = _spaces.Box(low=-1.0, high=1.0, shape=(6,), dtype=np.float32)    # environment.py:195-197
         super().__init__(n, obs_space, act_space)
         # many envs: no per-env Python dict churn unless asked for
@@ -159,9 +181,9 @@ class HlynrVecEnv(_VecEnvBase):
         import torch
 
         self._pinned = [torch.empty(shape, dtype=dt, pin_memory=True) for shape, dt in
-                        (((n, 26), torch.float32), ((n,), torch.float32), ((n,), torch.uint8), ((n,), torch.uint8), ((n,), torch.uint8))]
+                        (((n, od), torch.float32), ((n,), torch.float32), ((n,), torch.uint8), ((n,), torch.uint8), ((n,), torch.uint8))]
         self._sets = [
-            (view(ptrs[1], (n, 26), C.c_float, np.float32), view(ptrs[2], (n,), C.c_float, np.float32),
+            (view(ptrs[1], (n, od), C.c_float, np.float32), view(ptrs[2], (n,), C.c_float, np.float32),
              view(ptrs[3], (n,), C.c_uint8, np.uint8), view(ptrs[4], (n,), C.c_uint8, np.uint8),
              view(pd, (n,), C.c_uint8, np.uint8)),
             tuple(t.numpy() for t in self._pinned)]
@@ -170,11 +192,14 @@ class HlynrVecEnv(_VecEnvBase):
         self._bind_set(0)
         self._info = None           # [N]-sized info arrays, only in the eager (small-n) mode
         self._info_struct = None
-        self.sim.set_option("host_info", 0 if self.lazy_infos else 1)
+        # lazy infos + info_arrays: the kernel also fills the [N]-sized info arrays, read on request through infos.arrays
+        self.info_arrays = bool(info_arrays) or not self.lazy_infos
+        self.sim.set_option("host_info", 1 if self.info_arrays else 0)
         self._rec_dtype = abi.done_record_numpy_dtype()
         self._t_start = time.time()
         self._shared_info = {}
         self._pending = None
+        self._pending_seed = None
         self.training_step_count = 0
         self.observation_generator = _ObservationGeneratorView(self)
 
@@ -186,6 +211,9 @@ class HlynrVecEnv(_VecEnvBase):
 
     # ---- VecEnv API -----------------------------------------------------------------------------------
     def reset(self):
+        if self._pending_seed is not None:   # SB3 semantics: seed() takes effect at the next reset(), never mid-episode
+            self.sim.seed(self._pending_seed)
+            self._pending_seed = None
         _lib.check(self.sim.L.hlynr_reset_host(self.sim.h, None, self._obs.ctypes.data_as(C.c_void_p)))
         self.reset_infos = ([{} for _ in range(self.num_envs)] if not self.lazy_infos
                             else LazyInfos(self, np.zeros(0, dtype=self._rec_dtype), 0.0))
@@ -228,7 +256,7 @@ class HlynrVecEnv(_VecEnvBase):
                   "proximity_kill_radius")
 
     def _info_dicts(self, fl, distance, min_distance, fuel_remaining, fuel_used, steps, missile_pos, interceptor_pos,
-                    missiles_intercepted, missiles_remaining, missile_min_distances, extra=None):
+                    missiles_intercepted, missiles_remaining, missile_min_distances, radar_quality, extra=None):
         """The reference's info dict, environment.py:829-857 (single-missile mode), for a batch of envs given as
         arrays.  All conversions are vectorised; the per-env Python work is one dict(zip(keys, row)).
         extra: (terminal_obs[k,26], truncated_only list, episode dicts) appended as the SB3 done keys."""
@@ -243,7 +271,7 @@ class HlynrVecEnv(_VecEnvBase):
         mmd = np.asarray(missile_min_distances, dtype=np.float32).reshape(m, -1)[:, :max(vk, 1)].tolist()
         cols = [dist, hit.tolist(), bit(abi.INFO_HIT_TARGET), np.asarray(fuel_remaining).tolist(), np.asarray(fuel_used).tolist(),
                 bit(abi.INFO_CLAMPED), list(np.array(missile_pos, dtype=np.float32)), list(np.array(interceptor_pos, dtype=np.float32)),
-                np.asarray(steps).tolist(), bit(abi.INFO_RADAR_DETECTED), rep(float(P.radar_quality), m), bit(abi.INFO_GROUND_DETECTED),
+                np.asarray(steps).tolist(), bit(abi.INFO_RADAR_DETECTED), np.asarray(radar_quality, dtype=np.float64).tolist(), bit(abi.INFO_GROUND_DETECTED),
                 rep(vk > 0, m), rep(max(vk, 1), m), np.asarray(missiles_intercepted).tolist(), np.asarray(missiles_remaining).tolist(), mmd,
                 np.asarray(min_distance).tolist(), bit(abi.INFO_CROSSED), rep(bool(P.precision_mode), m), rep(bool(P.fuze_enabled), m),
                 bit(abi.INFO_FUZE), rep(float(P.kill_radius), m)]
@@ -261,7 +289,8 @@ class HlynrVecEnv(_VecEnvBase):
         return self._info_dicts(fl, rec["distance"], rec["min_distance"], rec["fuel_remaining"], rec["fuel_used"],
                                 rec["steps"], rec["missile_pos"], rec["interceptor_pos"], rec["missiles_intercepted"],
                                 rec["missiles_remaining"], rec["missile_min_distances"],
-                                extra=(rec["terminal_obs"].copy(), tl, episodes))
+                                np.where((fl & abi.DONE_ONBOARD_FILL) != 0, 0.0, float(self.sim.params.radar_quality)),
+                                extra=(rec["terminal_obs"][:, :self.obs_dim].copy(), tl, episodes))
 
     def _build_infos(self):
         n = self.num_envs
@@ -269,20 +298,26 @@ class HlynrVecEnv(_VecEnvBase):
         now = round(time.time() - self._t_start, 6)
         if self.lazy_infos:
             return LazyInfos(self, rec, now)   # a view: the C library alternates two record buffers, valid through the next step
-        if self._info is None:
-            self._info = {nm: np.zeros((n,) + shp, dtype=dt) for nm, dt, shp in abi.INFO_FIELDS}
-            self._info_struct = abi.HlynrInfoSoA(**{nm: self._info[nm].ctypes.data for nm, _, _ in abi.INFO_FIELDS})
-        _lib.check(self.sim.L.hlynr_info_host(self.sim.h, C.byref(self._info_struct)))
-        f = self._info
+        f = self._fetch_info_arrays()
         infos = self._info_dicts(f["flags"], f["distance"], f["min_distance"], f["fuel_remaining"], f["fuel_used"],
                                  f["steps"], f["missile_pos"], f["interceptor_pos"], f["missiles_intercepted"],
-                                 f["missiles_remaining"], f["missile_min_distances"])
+                                 f["missiles_remaining"], f["missile_min_distances"], f["radar_quality"])
         if len(rec):
             for i, d in zip(rec["env"].tolist(), self._done_info_dicts(rec, now)):
                 infos[i] = d
         if self.radar_debug:
             self._add_radar_debug(infos, f, rec)
         return infos
+
+    def _fetch_info_arrays(self):
+        if not self.info_arrays:
+            raise _lib.HlynrError("per-env info arrays were not requested: HlynrVecEnv(..., info_arrays=True)")
+        if self._info is None:
+            n = self.num_envs
+            self._info = {nm: np.zeros((n,) + shp, dtype=dt) for nm, dt, shp in abi.INFO_FIELDS}
+            self._info_struct = abi.HlynrInfoSoA(**{nm: self._info[nm].ctypes.data for nm, _, _ in abi.INFO_FIELDS})
+        _lib.check(self.sim.L.hlynr_info_host(self.sim.h, C.byref(self._info_struct)))
+        return self._info
 
     def _add_radar_debug(self, infos, f, rec):
         """info['radar_debug'] (core.py:649-682, consumed by inference.py:546): small batches only, see radar_debug.py."""
@@ -310,9 +345,12 @@ class HlynrVecEnv(_VecEnvBase):
         self.sim.close()
 
     def seed(self, seed=None):
+        """SB3 VecEnv.seed: stored and applied by the next reset() (env i gets seed + i there; here env i is keyed by
+        (seed, global env id), which is the same kind of per-env stream).  Re-keying Philox in the middle of running episodes
+        would change their draws from one tick to the next."""
         if seed is not None:
-            self.sim.seed(int(seed))
-        return [seed] * self.num_envs
+            self._pending_seed = int(seed)
+        return [None if seed is None else int(seed) + i for i in range(self.num_envs)] if self.num_envs <= 4096 else [seed] * self.num_envs
 
     def _indices(self, indices):
         if indices is None:

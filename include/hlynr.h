@@ -152,6 +152,8 @@ typedef struct HlynrInfoSoA {
     int32_t* missiles_intercepted;  /* [N] info['missiles_intercepted'] (volley: len(intercepted indices); else 0/1) */
     int32_t* missiles_remaining;    /* [N] info['missiles_remaining'] */
     float* missile_min_distances;   /* [N, HLYNR_MAX_VOLLEY] info['missile_min_distances'] (unused slots 0; single mode: [distance]) */
+    float* radar_quality;           /* [N] info['radar_quality'] (environment.py:840): the configured quality, 0.0 while the onboard
+                                       SensorDelayBuffer is still filling ('sensor_delay_initialization', core.py:579-584) */
 } HlynrInfoSoA;
 
 #define HLYNR_INFO_INTERCEPTED 0x01
@@ -183,6 +185,7 @@ typedef struct HlynrDoneRecord {
 } HlynrDoneRecord;           /* 50 words = 200 bytes */
 #define HLYNR_DONE_TERMINATED 0x100u
 #define HLYNR_DONE_TRUNCATED 0x200u
+#define HLYNR_DONE_ONBOARD_FILL 0x400u /* the onboard delay buffer was still filling on the terminal tick: info['radar_quality'] = 0.0 */
 
 /* Episode statistics accumulated on the device since the last reset of the block (per handle). */
 typedef struct HlynrStats {
@@ -218,6 +221,9 @@ typedef struct HlynrEnvState {
     double vpos[HLYNR_MAX_VOLLEY * 3], vvel[HLYNR_MAX_VOLLEY * 3], vmin[HLYNR_MAX_VOLLEY]; /* volley: missile_states[], min distances */
     int32_t steps, worsen_count, crossed, kf_init, onboard_delay, episode;
     int32_t vactive[HLYNR_MAX_VOLLEY], vcur, vcount; /* volley: active flags, index of self.missile_state, interceptions */
+    int32_t kf_f64;   /* dtype of the reference's Kalman state array: 0 = float32, 1 = float64 (core.py:108 rebinds it at the first
+                         float64 measurement); tracked by the fp64 build, always 0 in the fp32 build */
+    int32_t reserved;
 } HlynrEnvState;
 
 typedef struct hlynr_sim hlynr_t;
@@ -315,15 +321,16 @@ int hlynr_import_state(hlynr_t* sim, int64_t first, int64_t count, const HlynrEn
 int hlynr_debug_draws(hlynr_t* sim, int64_t env_global_id, uint32_t episode, uint32_t step,
                       uint32_t block, uint32_t raw_out[4], float uniform_out[4], float normal_out[4]);
 
-/* Tuning options.  "step_kernel_variant": 0 = auto, 1 = direct kernel (one CTA per 128 envs, plane loads from
- * registers), 2 = persistent kernel whose CTAs prefetch the next tile's planes with TMA bulk copies, 3 = persistent warps
- * that stage the next 32-env tile with per-thread cp.async while the current one computes (specialised feature sets only).
- * "specialise": 1 (default) = use the compile-time feature-specialised step kernels when the configuration matches
+/* Options.  "specialise": 1 (default) = use the compile-time feature-specialised step kernels when the configuration matches
  * one (medium scenario with physics v2.0 all on / all off), 0 = always the generic kernel.
  * "host_info": 1 (default) = hlynr_step_host also fills the [N]-sized info arrays read by hlynr_info_host, 0 = skip them
  * (finished episodes are still reported through hlynr_done_records_host).
  * "host_chunks": number of chunks hlynr_step_host pipelines (H2D | kernel | D2H on separate streams), 0 = auto.
  * "host_threads": threads used for staging memcpys of unpinned caller buffers, 0 = auto.
+ * "obs_dim": 26 (default) or 17.  With 17 every observation array of this API (obs_dev / obs_host / terminal_obs_*) is float[N,17]:
+ * the leading "17-D radar" channels obs[0:17] of the reference's vector (rl_system/hrl/observation_schema.py:13-46 MIN_DIMENSION,
+ * the layout of the pre-ground-radar models, rl_system/config_17d_compat.yaml); the ground-radar channels 17-25 are not written and
+ * the host path downloads 36 B per env less.  HlynrDoneRecord.terminal_obs always holds all 26 channels.
  * "prefetch_waves": the step kernel prefetches into L2 the state planes of the CTA this many CTAs-per-SM further on
  * (default 1, measured best on B200; 0 = off). */
 int hlynr_set_option(hlynr_t* sim, const char* name, int64_t value);
@@ -336,6 +343,9 @@ int hlynr_set_option(hlynr_t* sim, const char* name, int64_t value);
  * Curriculum scalars and the seed are baked into the captured arguments. */
 int hlynr_ring_period(const hlynr_t* sim, int* out);   /* lcm(onboard ring length, ground ring length), >= 1 */
 int hlynr_note_replayed_ticks(hlynr_t* sim, int64_t ticks, int64_t launches);
+/* Ticks executed (or accounted for by hlynr_note_replayed_ticks) since hlynr_create: a captured sequence may only be replayed
+ * when this is congruent, modulo hlynr_ring_period(), to its value when the capture started. */
+int hlynr_tick_count(const hlynr_t* sim, int64_t* out);
 
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int hlynr_launch_count(const hlynr_t* sim, int64_t* out);

@@ -24,7 +24,8 @@ extern "C" {
 /* rewards_dev[env] += gamma * terminal_values_dev[r] for every record r < min(*counter_dev, rows) of the step's done list
  * that was truncated but not terminated (info['TimeLimit.truncated']).  terminal_values_dev has `rows` entries (the value
  * net evaluated on the first `rows` stacked terminal observations).  If the step finished more than `rows` episodes,
- * *overflow_dev (int32, device, may be NULL) is incremented by the number of records left out. */
+ * *overflow_dev (int32, device, may be NULL) is incremented by the number of truncated-and-not-terminated records left out
+ * (timeouts that went without their bootstrap value): callers pass rows = N, or check *overflow_dev once per rollout. */
 int hlynr_bootstrap_timeouts(float* rewards_dev, const HlynrDoneRecord* records_dev, const int32_t* counter_dev,
                              int32_t rows, const float* terminal_values_dev, double gamma, int32_t* overflow_dev,
                              int device, void* stream);

@@ -301,6 +301,7 @@ typedef struct {
     int has_onb;
     Kalman kf;
     int last_onb_det, last_gnd_det;
+    int last_onb_fill; /* the delayed onboard sample was None (buffer still filling): last_detection_info['radar_quality'] = 0.0 */
     /* Monitor-like accounting */
     double ep_return;
     int ep_length;
@@ -518,7 +519,7 @@ static void observe(Oracle* o, Env* e, uint32_t step, float obs[26]) {
         for (int i = 0; i < 3; ++i) { o_rel[i] = rel[i]; o_mv[i] = mv[i]; }
         o_det = onb;
     }
-    (void)o_zeros64; (void)o_mv;
+    (void)o_mv;
 
     /* === ground radar :368-438 === */
     int gdet = 0;
@@ -606,6 +607,7 @@ static void observe(Oracle* o, Env* e, uint32_t step, float obs[26]) {
         fus = clipd(add(t, mul(wk(0.15, pe), agr, pe), pe), 0.0, 1.0);
     }
     e->last_onb_det = o_det;
+    e->last_onb_fill = o_zeros64;
     e->last_gnd_det = dg_det;
 
     /* === compute() :693-1032 === */
@@ -1330,6 +1332,7 @@ void oracle_step_range(void* h, int64_t i0, int64_t i1, const float* actions, fl
                 for (int m = 0; m < vk; ++m) rem += e->vact[m];
                 info->missiles_remaining[i] = vk > 0 ? rem : (s.intercepted ? 0 : 1);
             }
+            if (info->radar_quality) info->radar_quality[i] = e->last_onb_fill ? 0.f : (float)o->P.radar_quality; /* environment.py:840 */
             if (info->missile_min_distances)
                 for (int m = 0; m < HLYNR_MAX_VOLLEY; ++m)
                     info->missile_min_distances[HLYNR_MAX_VOLLEY * i + m] =
@@ -1380,6 +1383,7 @@ void oracle_export_state(void* h, int64_t first, int64_t count, HlynrEnvState* o
             s->vmin[m] = e->vmin[m]; s->vactive[m] = e->vact[m];
         }
         s->vcur = o->P.volley_size > 0 ? e->vcur : 0; s->vcount = o->P.volley_size > 0 ? e->vcount : 0;
+        s->kf_f64 = e->kf.x_f64;
     }
 }
 /* max |P - blockdiag(2x2)| over all envs: checks the decoupling claim the CUDA Kalman relies on */

@@ -284,7 +284,7 @@ class RefBatch:
                     interceptor_pos=np.zeros((n, 3)), missile_pos=np.zeros((n, 3)),
                     episode_return=np.zeros(n), episode_length=np.zeros(n, np.int32),
                     missiles_intercepted=np.zeros(n, np.int32), missiles_remaining=np.zeros(n, np.int32),
-                    missile_min_distances=np.zeros((n, 8)))
+                    missile_min_distances=np.zeros((n, 8)), radar_quality=np.zeros(n))
         for i in range(n):
             env, ctx = self.envs[i], self.ctxs[i]
             ctx.at(int(self.episode[i]), env.steps + 1)
@@ -317,6 +317,7 @@ class RefBatch:
             info["episode_return"][i] = self.ep_return[i]
             info["episode_length"][i] = self.ep_length[i]
             info["missiles_intercepted"][i] = inf["missiles_intercepted"]
+            info["radar_quality"][i] = inf["radar_quality"]
             info["missiles_remaining"][i] = inf["missiles_remaining"]
             md = list(inf["missile_min_distances"])
             info["missile_min_distances"][i, :len(md)] = md

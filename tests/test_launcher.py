@@ -60,6 +60,21 @@ def test_other_environments_fall_through_to_the_real_class(fake_sb3):
     v = fake_sb3.DummyVecEnv([_OtherEnv] * 5)
     assert isinstance(v, real) and v.num_envs == 5
     assert _OtherEnv.built == 5   # the probe of env 0 is reused, not built twice
+    assert isinstance(fake_sb3.DummyVecEnv, type) and issubclass(fake_sb3.DummyVecEnv, real)   # still a class: isinstance / subclassing work
+    assert fake_sb3.DummyVecEnv.__name__ == "DummyVecEnv"
+
+
+def test_env_fns_with_different_configs_fall_back(fake_sb3, capsys):
+    """The GPU batch shares ONE configuration: env_fns whose configs differ must go to the reference's own vec env."""
+    real = fake_sb3.SubprocVecEnv
+    run.patch_sb3(device=0, seed=1, precision="fp32")
+    a, b = config.baseline_config("cfg4"), config.baseline_config("cfg2")
+    InterceptEnvironment.built = 0
+    fns = [lambda: _Monitor(InterceptEnvironment(a))] * 3 + [lambda: _Monitor(InterceptEnvironment(b))]
+    v = fake_sb3.SubprocVecEnv(fns)
+    assert isinstance(v, real) and v.num_envs == 4
+    assert InterceptEnvironment.built == 4    # probes reused
+    assert "different configuration" in capsys.readouterr().err
 
 
 @pytest.mark.gpu

@@ -38,6 +38,7 @@ def test_oracle_matches_live_reference(base, f64):
         o_r, r_r, te_r, tr_r, _, inf_r = ref.step(a)
         o_o, r_o, te_o, tr_o, _, inf_o = sim.step(a)
         assert (te_r == te_o).all() and (tr_r == tr_o).all() and (inf_r["flags"] == inf_o["flags"]).all()
+        assert (inf_r["radar_quality"].astype(np.float32) == inf_o["radar_quality"]).all()
         np.testing.assert_allclose(o_o, o_r, atol=2e-5)
         np.testing.assert_allclose(r_o, r_r, rtol=2e-6, atol=2e-6)
 
@@ -112,5 +113,6 @@ def test_oracle_matches_live_reference_on_mixed_feature_configs():
             o_r, r_r, te_r, tr_r, _, inf_r = ref.step(a)
             o_o, r_o, te_o, tr_o, _, inf_o = sim.step(a)
             assert (te_r == te_o).all() and (tr_r == tr_o).all() and (inf_r["flags"] == inf_o["flags"]).all(), (k, t)
+            assert (inf_r["radar_quality"].astype(np.float32) == inf_o["radar_quality"]).all(), (k, t)   # 0.0 while the onboard delay buffer fills
             np.testing.assert_allclose(o_o, o_r, atol=5e-5, err_msg=f"config {k} t={t}")
             np.testing.assert_allclose(r_o, r_r, rtol=1e-5, atol=1e-4, err_msg=f"config {k} t={t}")

@@ -275,3 +275,159 @@ def test_step_host_with_pageable_and_page_locked_caller_buffers_agree():
         assert (pin[4] == (want[2] | want[3])).all(), t
     for s in sims:
         s.close()
+
+
+def test_obs_dim_17_is_the_leading_radar_channels():
+    """HlynrVecEnv(obs_dim=17): the 17-D radar layout (rl_system/hrl/observation_schema.py:13-46) = obs[0:17] of the 26-D vector,
+    bit for bit, through the host path (pipelined chunks, ragged last tile) and the tensor API; terminal observations too."""
+    import torch
+    from hlynr_intercept_b200.sim import HlynrSim
+
+    cfg = config.baseline_config("cfg4")
+    cfg["max_steps"] = 30
+    from hlynr_intercept_b200.vec_env import HlynrVecEnv
+
+    n = 70001   # > 65536: zero-copy outputs, several chunks
+    a26 = HlynrVecEnv(cfg, n_envs=n, seed=5, warn_dead=False)
+    a17 = HlynrVecEnv(cfg, n_envs=n, seed=5, warn_dead=False, obs_dim=17)
+    assert a17.observation_space.shape == (17,)
+    o26, o17 = a26.reset(), a17.reset()
+    assert o17.shape == (n, 17) and (o17 == o26[:, :17]).all()
+    rng = np.random.default_rng(0)
+    finished = 0
+    for t in range(40):
+        act = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        o26, r26, d26, i26 = a26.step(act)
+        o17, r17, d17, i17 = a17.step(act)
+        assert (o17 == o26[:, :17]).all() and (r17 == r26).all() and (d17 == d26).all(), t
+        for i in np.nonzero(d26)[0][:5]:
+            assert (i17[i]["terminal_observation"] == i26[i]["terminal_observation"][:17]).all()
+            assert i17[i]["terminal_observation"].shape == (17,)
+            finished += 1
+    assert finished > 0
+    a26.close(); a17.close()
+    s26 = HlynrSim(cfg, n_envs=333, seed=5, warn_dead=False)
+    s17 = HlynrSim(cfg, n_envs=333, seed=5, warn_dead=False, obs_dim=17)
+    assert (s17.reset().cpu() == s26.reset().cpu()[:, :17]).all()
+    for t in range(35):
+        act = torch.rand(333, 6, device="cuda") * 2 - 1
+        x26, x17 = s26.step(act), s17.step(act)
+        assert x17[0].shape == (333, 17) and (x17[0].cpu() == x26[0].cpu()[:, :17]).all()
+        done = (x26[2] | x26[3]).bool().cpu()
+        if done.any():
+            assert (x17[4].cpu()[done] == x26[4].cpu()[done][:, :17]).all()
+    s26.close(); s17.close()
+
+
+def test_radar_quality_is_zero_while_the_onboard_delay_buffer_fills():
+    """info['radar_quality'] (environment.py:840) is last_detection_info['radar_quality']: 0.0 during the first onboard_delay
+    steps of every episode ('sensor_delay_initialization', core.py:579-584), the configured quality afterwards."""
+    cfg = config.baseline_config("cfg4")   # sensor delay 30 ms = 3 samples
+    cfg["max_steps"] = 7
+    from hlynr_intercept_b200.vec_env import HlynrVecEnv
+
+    v = HlynrVecEnv(cfg, n_envs=4, seed=3, warn_dead=False)
+    q = float(v.sim.params.radar_quality)
+    delay = int(v.sim.params.onboard_delay)
+    assert delay == 3 and q > 0
+    v.reset()
+    for t in range(1, 20):
+        _, _, dones, infos = v.step(np.zeros((4, 6), np.float32))
+        steps = infos[0]["steps"]
+        assert steps == (t - 1) % 7 + 1
+        assert infos[0]["radar_quality"] == (0.0 if steps < delay else q), (t, steps, infos[0]["radar_quality"])
+    v.close()
+    # without sensor delays the quality is there from the first step
+    v = HlynrVecEnv(config.baseline_config("cfg2"), n_envs=2, seed=3, warn_dead=False)
+    v.reset()
+    assert v.step(np.zeros((2, 6), np.float32))[3][0]["radar_quality"] == float(v.sim.params.radar_quality)
+    v.close()
+
+
+def test_lazy_infos_expose_the_per_env_info_arrays_on_request():
+    from hlynr_intercept_b200.vec_env import HlynrVecEnv
+
+    cfg = config.baseline_config("cfg4")
+    n = 5000
+    lazy = HlynrVecEnv(cfg, n_envs=n, seed=8, warn_dead=False, lazy_infos=True, info_arrays=True)
+    eager = HlynrVecEnv(cfg, n_envs=n, seed=8, warn_dead=False, lazy_infos=False)
+    plain = HlynrVecEnv(cfg, n_envs=n, seed=8, warn_dead=False, lazy_infos=True)
+    lazy.reset(); eager.reset(); plain.reset()
+    rng = np.random.default_rng(1)
+    for t in range(3):
+        act = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        _, _, _, li = lazy.step(act)
+        _, _, _, ei = eager.step(act)
+        _, _, _, pi = plain.step(act)
+    arr = li.arrays
+    assert arr["distance"].shape == (n,) and arr["interceptor_pos"].shape == (n, 3)
+    for i in (0, 17, n - 1):
+        assert li[i].keys() == ei[i].keys()
+        for k in ("distance", "fuel_remaining", "steps", "radar_detected", "radar_quality", "min_distance"):
+            assert li[i][k] == ei[i][k], (i, k)
+        assert (li[i]["missile_pos"] == ei[i]["missile_pos"]).all()
+        assert arr["distance"][i] == ei[i]["distance"]
+    assert pi[0] == {}   # not requested: unfinished envs share one empty dict
+    with pytest.raises(Exception):
+        pi.arrays
+    lazy.close(); eager.close(); plain.close()
+
+
+def test_seed_takes_effect_at_the_next_reset():
+    """SB3 VecEnv.seed semantics: stored, applied by the next reset(); running episodes keep their draws."""
+    a, b = make(64), make(64)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(2)
+    acts = rng.uniform(-1, 1, (12, 64, 6)).astype(np.float32)
+    for t in range(6):
+        if t == 3:
+            a.seed(777)
+        oa, ob = a.step(acts[t])[0], b.step(acts[t])[0]
+        assert (oa == ob).all(), t          # mid-episode: unchanged
+    ra, rb = a.reset(), b.reset()
+    assert not (ra == rb).all()              # the new seed keys the episodes that start at the reset
+    c = make(64)
+    c.seed(777)
+    assert (c.reset() == ra).all()
+    a.close(); b.close(); c.close()
+
+
+def test_step_graph_replays_bit_identically():
+    """HlynrSim.capture_steps: ring_period() ticks in ONE CUDA graph == the same ticks launched one by one; a replay at the
+    wrong ring phase is refused."""
+    import torch
+    from hlynr_intercept_b200 import _lib
+    from hlynr_intercept_b200.sim import HlynrSim
+
+    for name in ("cfg2", "cfg4"):
+        cfg = config.baseline_config(name)
+        n = 4096
+        a = HlynrSim(cfg, n_envs=n, seed=11, warn_dead=False)
+        b = HlynrSim(cfg, n_envs=n, seed=11, warn_dead=False)
+        a.reset(); b.reset()
+        a.rollout(1000, None, want_obs=False); b.rollout(1000, None, want_obs=False)
+        T = a.ring_period()
+        assert T in (6, 12)
+        while a.tick_count() % T:
+            act = torch.zeros(n, 6, device="cuda")
+            a.step(act); b.step(act)
+        g = torch.Generator(device="cuda"); g.manual_seed(3)
+        bufs = [torch.empty(n, 6, device="cuda") for _ in range(T)]
+        sg = a.capture_steps(bufs)
+        for rep in range(3):
+            for k in range(T):
+                bufs[k].copy_(torch.rand(n, 6, device="cuda", generator=g) * 2 - 1)
+            out = sg.replay()
+            for k in range(T):
+                ref = b.step(bufs[k])
+            torch.cuda.synchronize()
+            for x, y in zip(out[:4], ref[:4]):
+                assert (x == y).all()
+        sa, sb = a.export_state(), b.export_state()
+        for k in sa:
+            assert (sa[k] == sb[k]).all(), k
+        assert a.stats() == b.stats()
+        a.step(bufs[0])
+        with pytest.raises(_lib.HlynrError):
+            sg.replay()
+        a.close(); b.close()
