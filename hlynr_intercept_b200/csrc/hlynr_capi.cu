@@ -249,6 +249,7 @@ template <typename R> static KParams<R> make_kparams(const HlynrParams& p) {
     k.radar_range = (float)p.radar_range; k.rc_radar_range = (float)(1.0 / p.radar_range);
     k.radar_quality = (float)p.radar_quality; k.radar_quality_d = p.radar_quality;
     k.rc_max_velocity_f = (float)(1.0 / p.max_velocity); k.rc_max_range_f = (float)(1.0 / p.max_range);
+    k.max_velocity_f = (float)p.max_velocity; k.max_range_f = (float)p.max_range;
     k.g_max_range = (float)p.g_max_range; k.rc_g_max_range = (float)(1.0 / p.g_max_range);
     // elevation gates asin(s) < min_el / > max_el (core.py:402-406) as thresholds on s itself
     k.g_sin_min_el = (float)sin(p.g_min_el); k.g_sin_max_el = (float)sin(p.g_max_el);

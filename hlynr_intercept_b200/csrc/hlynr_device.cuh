@@ -170,7 +170,7 @@ template <typename R> struct KParams {
     double dt_d;        // dt as the Python float it is in the reference
     double radar_quality_d, gust_scale_d;
     // ---- float context (observation geometry) ----
-    float radar_range, rc_radar_range, radar_quality, rc_max_velocity_f, rc_max_range_f;
+    float radar_range, rc_radar_range, radar_quality, rc_max_velocity_f, rc_max_range_f, max_velocity_f, max_range_f;
     float gpos[3], g_max_range, rc_g_max_range, g_sin_min_el, g_sin_max_el, g_base_q, max_link, rc_max_link, pkt_loss;
     float dtf, q_pp, q_pv, q_vv;  // Kalman F/Q entries (float32 matrices, core.py:33-56)
     float fus_035q;
@@ -467,6 +467,68 @@ struct ObsOut {
 // Geometry is float32 in both builds (the reference casts the state to float32 on entry, core.py:522-529);
 // W = R is the dtype of the reference's float64 islands (ground measurement, Kalman state).
 // ------------------------------------------------------------------------------------------------
+// fp64 build, float32 phase of the Kalman state (FLAG_KF_F64 clear): the reference evaluates the track-derived channels
+// (core.py:779-918: filtered relative position / velocity, range, closing speed, LOS rates, time to intercept, off-axis cosine) in
+// float32 because every operand is a float32 array.  Positions of ~1e4 m carry 5e-4 m of float32 rounding, which the LOS-rate and
+// direction-cosine channels amplify by |v| / range to ~3e-5 -- above this build's 1e-5 tolerance -- so the phase is followed with
+// the same correctly rounded float32 operations in the same order (oracle/hlynr_oracle.c observe(), pk == F32) instead of in double.
+struct TrackF32 { float ux, uy, uz, hx, hy, hz, vx, vy, vz; bool have_los; };
+template <typename R>
+__device__ __noinline__ TrackF32 track_obs_f32_phase(const KParams<R>& P, int mode, bool o_det, float Ppp, float kpx, float kpy, float kpz,
+                                                     float kvx, float kvy, float kvz, float ipx, float ipy, float ipz, float ivx, float ivy,
+                                                     float ivz, float fx, float fy, float fz, float rx_, float ry_, float rz_, float ux_,
+                                                     float uy_, float uz_, const ObsOut out) {
+    TrackF32 lb{1.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, false};
+    const float mr = P.max_range_f, mv = P.max_velocity_f;   // weak Python scalars rounded to float32
+    const float px = sub(kpx, ipx), py = sub(kpy, ipy), pz = sub(kpz, ipz);
+    const float vx = sub(kvx, ivx), vy = sub(kvy, ivy), vz = sub(kvz, ivz);
+    const float rr = norm3(px, py, pz);
+    const float cl = dvd(-dot3(px, py, pz, vx, vy, vz), add(rr, 1e-6f));
+    if (mode == HLYNR_OBS_LOS) {
+        lb.have_los = true;
+        out.put(0, clip(dvd(rr, mr), 0.f, 1.f));
+        out.put(1, clip(dvd(cl, mv), -1.f, 1.f));
+        if (rr > 1e-6f) { lb.ux = dvd(px, rr); lb.uy = dvd(py, rr); lb.uz = dvd(pz, rr); }
+        {   // lh = normalize(lu x world_up), lv = lu x lh (oracle los_basis / cross3)
+            const float cx = sub(mul(lb.uy, 1.f), mul(lb.uz, 0.f)), cy = sub(mul(lb.uz, 0.f), mul(lb.ux, 1.f)), cz = sub(mul(lb.ux, 0.f), mul(lb.uy, 0.f));
+            const float n = norm3(cx, cy, cz);
+            if (n > 1e-6f) { lb.hx = dvd(cx, n); lb.hy = dvd(cy, n); lb.hz = dvd(cz, n); }
+            lb.vx = sub(mul(lb.uy, lb.hz), mul(lb.uz, lb.hy));
+            lb.vy = sub(mul(lb.uz, lb.hx), mul(lb.ux, lb.hz));
+            lb.vz = sub(mul(lb.ux, lb.hy), mul(lb.uy, lb.hx));
+        }
+        const float rden = add(rr, 1e-6f);
+        const float tx = dvd(sub(vx, mul(cl, lb.ux)), rden), ty = dvd(sub(vy, mul(cl, lb.uy)), rden), tz = dvd(sub(vz, mul(cl, lb.uz)), rden);
+        out.put(2, clip(dvd(dot3(tx, ty, tz, lb.hx, lb.hy, lb.hz), 0.5f), -1.f, 1.f));
+        out.put(3, clip(dvd(dot3(tx, ty, tz, lb.vx, lb.vy, lb.vz), 0.5f), -1.f, 1.f));
+        const float ivm = norm3(ivx, ivy, ivz);
+        out.put(4, ivm > 1e-6f ? dot3(dvd(ivx, ivm), dvd(ivy, ivm), dvd(ivz, ivm), lb.ux, lb.uy, lb.uz) : 0.f);
+        const float ax = add(vx, ivx), ay = add(vy, ivy), az = add(vz, ivz);
+        const float am = norm3(ax, ay, az);
+        out.put(5, am > 1e-6f ? dot3(dvd(ax, am), dvd(ay, am), dvd(az, am), -lb.ux, -lb.uy, -lb.uz) : 0.f);
+    } else if (mode == HLYNR_OBS_BODY) {
+        out.put(0, clip(dvd(dot3(px, py, pz, fx, fy, fz), mr), -1.f, 1.f));
+        out.put(1, clip(dvd(dot3(px, py, pz, rx_, ry_, rz_), mr), -1.f, 1.f));
+        out.put(2, clip(dvd(dot3(px, py, pz, ux_, uy_, uz_), mr), -1.f, 1.f));
+        out.put(3, clip(dvd(dot3(vx, vy, vz, fx, fy, fz), mv), -1.f, 1.f));
+        out.put(4, clip(dvd(dot3(vx, vy, vz, rx_, ry_, rz_), mv), -1.f, 1.f));
+        out.put(5, clip(dvd(dot3(vx, vy, vz, ux_, uy_, uz_), mv), -1.f, 1.f));
+    } else {
+        out.put(0, clip(dvd(px, mr), -1.f, 1.f)); out.put(1, clip(dvd(py, mr), -1.f, 1.f)); out.put(2, clip(dvd(pz, mr), -1.f, 1.f));
+        out.put(3, clip(dvd(vx, mv), -1.f, 1.f)); out.put(4, clip(dvd(vy, mv), -1.f, 1.f)); out.put(5, clip(dvd(vz, mv), -1.f, 1.f));
+    }
+    out.put(13, cl > 0.f ? clip(sub(1.f, dvd(dvd(rr, cl), 100.f)), -1.f, 1.f) : -1.f);
+    {   // np.trace(P[0:3,0:3]) in float32, then python-float arithmetic (core.py:899-905)
+        const float tr = add(add(Ppp, Ppp), Ppp);
+        double tq = clip(1.0 - (double)tr / 10000.0, 0.0, 1.0);
+        if (o_det) tq *= P.radar_quality_d;
+        out.put(14, (float)tq);
+    }
+    out.put(15, clip(dvd(cl, mv), -1.f, 1.f));
+    out.put(16, rr > 1e-6f ? dot3(fx, fy, fz, dvd(px, rr), dvd(py, rr), dvd(pz, rr)) : 1.f);
+    return lb;
+}
+
 template <typename R, int F>
 HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint4 ur, int64_t i, int g_row, int o_row, ObsOut& out) {
     typedef R W;
@@ -697,7 +759,7 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
     const int mode = FT::obs_mode(P);
     LosBasis<W> lb;
     bool have_los = false;
-    struct { float rx, ry, rz, ux, uy, uz; } bx;  // body right / up axes (core.py:1155-1176), body_frame only
+    struct { float rx, ry, rz, ux, uy, uz; } bx = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // body right / up axes (core.py:1155-1176), body_frame only
     if (mode == HLYNR_OBS_BODY) {
         const float w = e.qw, x = e.qx, y = e.qy, z = e.qz;
         float a = 1.f - 2.f * fmaf(y, y, z * z), b = 2.f * fmaf(x, y, w * z), c = 2.f * fmaf(x, z, -(w * y));
@@ -707,7 +769,17 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
         inv = nrcp(nnorm3(a, b, c) + 1e-6f);
         bx.ux = a * inv; bx.uy = b * inv; bx.uz = c * inv;
     }
-    if (kf_init) {
+    bool f32_phase = false;
+    if constexpr (std::is_same<R, double>::value) f32_phase = kf_init && !(e.flags & FLAG_KF_F64);
+    if (f32_phase) {
+        if constexpr (std::is_same<R, double>::value) {
+            const TrackF32 t = track_obs_f32_phase<R>(P, mode, o_det, e.Ppp, (float)e.kpx, (float)e.kpy, (float)e.kpz, (float)e.kvx,
+                                                      (float)e.kvy, (float)e.kvz, ipx, ipy, ipz, ivx, ivy, ivz, fx, fy, fz, bx.rx, bx.ry, bx.rz,
+                                                      bx.ux, bx.uy, bx.uz, out);
+            have_los = t.have_los;   // channels 7 / 8 of the los_frame (core.py:929-945) project the interceptor velocity on this basis
+            lb.ux = t.ux; lb.uy = t.uy; lb.uz = t.uz; lb.hx = t.hx; lb.hy = t.hy; lb.vx = t.vx; lb.vy = t.vy; lb.vz = t.vz;
+        }
+    } else if (kf_init) {
         const W px = e.kpx - (W)ipx, py = e.kpy - (W)ipy, pz = e.kpz - (W)ipz;
         const W vx = e.kvx - (W)ivx, vy = e.kvy - (W)ivy, vz = e.kvz - (W)ivz;
         const W rr = nnorm3(px, py, pz);
@@ -1552,9 +1624,10 @@ template <typename R, int F> HD void prefetch_ring_reads(const KernelArgs<R>& A,
 // ------------------------------------------------------------------------------------------------
 // step(): one tick of every env + SB3 auto-reset.  kRollout: k fused ticks, state stays in registers.
 // CTAs per SM: 4 for the fp32 build (<= 128 registers, no spills).  The fp64 build holds ~60 doubles of env state (120
-// registers) before any temporaries: at 4 CTAs per SM it spills, so it runs at HLYNR_F64_MIN_BLOCKS (2 = up to 255 registers).
+// registers) before any temporaries: at 4 CTAs per SM it spills (cfg4 steady state 308 us at 2^20 envs), at 2 (<= 255 registers)
+// too few warps are resident (355 us); 3 CTAs per SM (<= 168 registers, no spills) is the measured optimum (300 us).
 #ifndef HLYNR_F64_MIN_BLOCKS
-#define HLYNR_F64_MIN_BLOCKS 2
+#define HLYNR_F64_MIN_BLOCKS 3
 #endif
 template <typename R> struct StepOcc { static constexpr int ctas = std::is_same<R, double>::value ? HLYNR_F64_MIN_BLOCKS : 4; };
 template <typename R, bool kRollout, int F>

@@ -386,7 +386,8 @@ def test_seed_takes_effect_at_the_next_reset():
         assert (oa == ob).all(), t          # mid-episode: unchanged
     ra, rb = a.reset(), b.reset()
     assert not (ra == rb).all()              # the new seed keys the episodes that start at the reset
-    c = make(64)
+    c = make(64)   # same draws as `a` after its re-seeded reset: seed 777, second episode of every env
+    c.reset()
     c.seed(777)
     assert (c.reset() == ra).all()
     a.close(); b.close(); c.close()
