@@ -543,40 +543,63 @@ def e2e_leg(ctx, args, env_cfg, n):
 
 def rollout_leg(ctx, args, env_cfg):
     """PPO rollout collection fully on the device: policy forward, env step, frame-stack/normalise, TimeLimit bootstrap, GAE;
-    no host synchronisation inside collect()."""
+    no host synchronisation inside collect().  The policy is the reference's network (train_flat_ppo.py:37-85 CustomMLP
+    104 -> 512 -> 512 -> 256 + LayerNorm + ReLU, action_net / value_net / log_std): once as the fused sm_100a kernel
+    (include/hlynr_policy.h: tcgen05 GEMMs, LayerNorm epilogues, heads and sampling in one launch) and once as the torch module
+    on cuBLAS TF32."""
+    from hlynr_intercept_b200.policy import FusedActorCritic, ReferenceActorCritic
     from hlynr_intercept_b200.post import HlynrObsPipeline
-    from hlynr_intercept_b200.rollout import DeviceRolloutCollector, GaussianMlpPolicy
+    from hlynr_intercept_b200.rollout import DeviceRolloutCollector
     from hlynr_intercept_b200.sim import HlynrSim
 
     torch, world, rank, dev = ctx.torch, ctx.world, ctx.rank, ctx.dev
     barrier = ctx.barrier
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_roll = min(args.envs_per_gpu, args.rollout_envs)
+    T = args.rollout_steps
     rsim = HlynrSim(env_cfg, n_envs=n_roll, device=ctx.local_rank, seed=4321, env_id_offset=rank * n_roll, precision=args.precision,
                     warn_dead=False)
     rpipe = HlynrObsPipeline(rsim, n_stack=4, training=True)
     torch.manual_seed(rank)
-    torch.backends.cuda.matmul.allow_tf32 = True   # the policy GEMMs are the caller's; TF32 tensor cores as PPO users run them
+    torch.backends.cuda.matmul.allow_tf32 = True   # the torch comparison runs its GEMMs on TF32 tensor cores, as PPO users do
     torch.backends.cudnn.allow_tf32 = True
-    pol = GaussianMlpPolicy(104, device=dev)
-    col = DeviceRolloutCollector(rpipe, pol, args.rollout_steps)
-    col.collect()
-    barrier()
-    e0.record()
-    col.collect()
-    e1.record()
-    barrier()
-    te_ = ctx.max_over_ranks(e0.elapsed_time(e1))
-    graphed = args.rollout_steps % col.graph_period() == 0
-    if graphed:   # the whole collect() as ONE CUDA-graph launch (launch-bound otherwise: ~25 kernels per step)
-        col.capture()
+    net = ReferenceActorCritic(device=dev)
+    fused = FusedActorCritic(net, device=ctx.local_rank, seed=rank)
+
+    def timed_collect(col, graph):
+        col.collect()
+        barrier()
+        e0.record()
+        col.collect()
+        e1.record()
+        barrier()
+        eager = ctx.max_over_ranks(e0.elapsed_time(e1))
+        if not graph:
+            return eager, eager
+        col.capture()   # the whole collect() as ONE CUDA-graph launch (launch-bound otherwise: ~25 kernels per step)
         col.replay()
         barrier()
         e0.record()
         col.replay()
         e1.record()
         barrier()
-    tr_ = ctx.max_over_ranks(e0.elapsed_time(e1))
+        return eager, ctx.max_over_ranks(e0.elapsed_time(e1))
+
+    col = DeviceRolloutCollector(rpipe, fused, T)
+    graphed = T % col.graph_period() == 0
+    te_, tr_ = timed_collect(col, graphed)
+    # the forward alone (policy step of one tick) at this batch size
+    o = col.obs[0]
+    fused(o); barrier(); e0.record()
+    for _ in range(10):
+        fused(o)
+    e1.record(); barrier()
+    fwd_us = e0.elapsed_time(e1) / 10 * 1e3
+    flop = 2 * (104 * 512 + 512 * 512 + 512 * 256 + 256 * 7) * n_roll
+    colt = DeviceRolloutCollector(rpipe, net, T)
+    colt._started = True
+    colt.obs[colt.T].copy_(col.obs[col.T])
+    tte_, ttr_ = timed_collect(colt, graphed)
 
     class _NoPolicy(torch.nn.Module):   # the same loop without the policy network (random actions): what the simulator side costs
         def __init__(self):
@@ -590,25 +613,24 @@ def rollout_leg(ctx, args, env_cfg):
             a = torch.rand(obs.shape[0], 6, device=obs.device) * 2 - 1
             return a, obs[:, 0], obs[:, 1]
 
-    col2 = DeviceRolloutCollector(rpipe, _NoPolicy(), args.rollout_steps)
+    col2 = DeviceRolloutCollector(rpipe, _NoPolicy(), T, bootstrap_rows=max(256, n_roll // 32))
     col2._started = True
     col2.obs[col2.T].copy_(col.obs[col.T])
-    col2.collect()
-    barrier()
-    e0.record()
-    col2.collect()
-    e1.record()
-    barrier()
-    tn_ = ctx.max_over_ranks(e0.elapsed_time(e1))
-    roll = {"value": world * n_roll * args.rollout_steps / (tr_ * 1e-3), "unit": "env-steps/s",
-            "envs_per_gpu": n_roll, "n_steps": args.rollout_steps,
-            "policy": "GaussianMlpPolicy 104->512->512->256 (pi and vf), LayerNorm, fp32 weights, TF32 GEMMs (torch / cuBLAS)",
-            "cuda_graph": bool(graphed), "eager": world * n_roll * args.rollout_steps / (te_ * 1e-3),
-            "without_policy_network": world * n_roll * args.rollout_steps / (tn_ * 1e-3),
+    tn_, _ = timed_collect(col2, False)
+    rate = lambda ms: world * n_roll * T / (ms * 1e-3)  # noqa: E731
+    roll = {"value": rate(tr_), "unit": "env-steps/s", "envs_per_gpu": n_roll, "n_steps": T,
+            "policy": "reference network 104->512->512->256 (LayerNorm, ReLU) + action_net/value_net, fused sm_100a forward "
+                      "(hlynr_policy_forward: tcgen05 bf16 GEMMs, fp32 TMEM accumulators, TMA weight ring, LayerNorm/ReLU epilogues, "
+                      "heads + Gaussian sampling in ONE kernel)",
+            "cuda_graph": bool(graphed), "eager": rate(te_), "us_per_step": tr_ / T * 1e3,
+            "policy_forward_us": fwd_us, "policy_forward_tflops": flop / (fwd_us * 1e-6) / 1e12,
+            "with_torch_policy_tf32": rate(ttr_), "with_torch_policy_tf32_eager": rate(tte_),
+            "without_policy_network": rate(tn_),
             "timeout_bootstrap_overflow": int(col.overflow.item()),
-            "note": "DeviceRolloutCollector.collect(): policy forward + hlynr_step + hlynr_post_step + "
-                    "hlynr_bootstrap_timeouts per step, hlynr_gae at the end; buffers [T,N,*] resident in HBM; SB3 parity of the "
-                    "GAE / bootstrap restatement is UNPINNED (stable_baselines3 not importable here)"}
+            "note": "DeviceRolloutCollector.collect(): policy forward + hlynr_step + hlynr_post_step + value net on the finished "
+                    "episodes (device-side row count) + hlynr_bootstrap_timeouts per step, hlynr_gae at the end; buffers [T,N,*] "
+                    "resident in HBM; SB3 parity of the GAE / bootstrap restatement is UNPINNED (stable_baselines3 not importable here)"}
+    fused.close()
     rpipe.close()
     rsim.close()
     return roll

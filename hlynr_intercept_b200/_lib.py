@@ -24,6 +24,8 @@ EXPORTS = [
     "hlynr_post_check_sums", "hlynr_post_launch_count", "hlynr_post_note_replayed_steps",
     # include/hlynr_rollout.h
     "hlynr_bootstrap_timeouts", "hlynr_gae",
+    # include/hlynr_policy.h
+    "hlynr_policy_create", "hlynr_policy_destroy", "hlynr_policy_set_weights", "hlynr_policy_forward", "hlynr_policy_launch_count",
 ]
 
 
@@ -99,6 +101,12 @@ def load(build_if_missing=True):
     L.hlynr_tick_count.argtypes = [vp, C.POINTER(i64)]
     L.hlynr_bootstrap_timeouts.argtypes = [vp, vp, vp, C.c_int32, vp, C.c_double, vp, i32, vp]
     L.hlynr_gae.argtypes = [vp, vp, vp, vp, vp, i64, i64, C.c_double, C.c_double, vp, vp, i32, vp]
+    L.hlynr_policy_create.argtypes = [i32, C.POINTER(vp)]
+    L.hlynr_policy_destroy.argtypes = [vp]
+    L.hlynr_policy_destroy.restype = None
+    L.hlynr_policy_set_weights.argtypes = [vp, C.POINTER(abi.HlynrPolicyWeights), vp]
+    L.hlynr_policy_forward.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, u64, u64, i32, vp]
+    L.hlynr_policy_launch_count.argtypes = [vp, C.POINTER(i64)]
     if L.hlynr_abi_version() != abi.ABI_VERSION:
         raise HlynrError("ABI version mismatch between libhlynr_b200.so and hlynr_intercept_b200.abi")
     if L.hlynr_params_size() != C.sizeof(abi.HlynrParams):

@@ -47,6 +47,11 @@ class HlynrParams(C.Structure):
     ]
 
 
+class HlynrPolicyWeights(C.Structure):   # include/hlynr_policy.h
+    _fields_ = [(n, C.c_void_p) for n in ("w1", "b1", "ln1_g", "ln1_b", "w2", "b2", "ln2_g", "ln2_b", "w3", "b3", "ln3_g", "ln3_b",
+                                          "wa", "ba", "wv", "bv", "log_std")] + [("ln_eps", C.c_float)]
+
+
 class HlynrCurriculum(C.Structure):
     _fields_ = [("intercept_radius", C.c_double), ("beam_width_deg", C.c_double),
                 ("onboard_reliability", C.c_double), ("ground_reliability", C.c_double)]

@@ -6,11 +6,12 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libhlynr_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "hlynr_capi.cu"), os.path.join(HERE, "csrc", "hlynr_post.cu"),
-           os.path.join(HERE, "csrc", "hlynr_rollout.cu")]
+           os.path.join(HERE, "csrc", "hlynr_rollout.cu"), os.path.join(HERE, "csrc", "hlynr_policy.cu")]
 DEPS = SOURCES + [os.path.join(HERE, "csrc", "hlynr_device.cuh"),
                   os.path.join(os.path.dirname(HERE), "include", "hlynr.h"),
                   os.path.join(os.path.dirname(HERE), "include", "hlynr_post.h"),
                   os.path.join(os.path.dirname(HERE), "include", "hlynr_rollout.h"),
+                  os.path.join(os.path.dirname(HERE), "include", "hlynr_policy.h"),
                   os.path.join(os.path.dirname(HERE), "include", "hlynr_rng.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]

@@ -209,7 +209,8 @@ struct hlynr_sim {
     int64_t xchg_cap = 0;
     cudaStream_t own_stream = nullptr;
     HostIO hio;
-    int host_info = 1, host_chunks = 0, host_threads = 0;
+    int host_info = 1, host_chunks = 0, host_threads = 0, host_chunk_growth = 0;
+    int pdl = 0;   // step kernels are launched with programmatic stream serialization (option "pdl")
     int obs_dim = HLYNR_OBS_DIM;  // row pitch of every observation array of the API: 26, or 17 (option "obs_dim")
     int prefetch_waves = 1;  // CTAs per SM the step kernel looks ahead when it prefetches upcoming planes into L2 (0 = off)
     HlynrDoneRecord* done_records = nullptr;  // attached compact done list (hlynr_set_done_list)
@@ -443,15 +444,30 @@ static int feature_set(const HlynrParams& p) {
     return (f == FT_V2ON || f == FT_V2OFF || f == FT_V2ON_DR) ? f : FT_GENERIC;
 }
 // Both builds dispatch to the feature-specialised instantiation of the three BASELINE configurations when it matches.
+// One launch of an instantiation.  pdl: programmatic dependent launch -- the grid may be scheduled while the previous kernel
+// of the stream is still draining; the kernel itself waits (griddepcontrol.wait, its first instruction that matters) until
+// that kernel has completed and its writes are visible, so only launch latency and the tail of the previous grid overlap.
+template <typename R, bool kRollout, int F> static void launch_inst(const KernelArgs<R>& A, int grid, cudaStream_t st, bool pdl) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(HLYNR_STEP_BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
+    cudaLaunchKernelEx(&cfg, step_kernel<R, kRollout, F>, A);
+}
+// Both builds dispatch to the feature-specialised instantiation of the three BASELINE configurations when it matches.
 template <typename R, bool kRollout> static void launch_step(const hlynr_sim* s, const KernelArgs<R>& A, cudaStream_t st, bool specialise) {
     const int grid = grid_for(A.lim - A.first, HLYNR_STEP_BLOCK);
+    const bool pdl = s->pdl != 0;
     int f = feature_set(s->params);
     if (!specialise && f >= 0) f = FT_GENERIC;
-    if (f == FT_V2ON) step_kernel<R, kRollout, FT_V2ON><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
-    else if (f == FT_V2OFF) step_kernel<R, kRollout, FT_V2OFF><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
-    else if (f == FT_V2ON_DR) step_kernel<R, kRollout, FT_V2ON_DR><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
-    else if (f == FT_GENERIC_MODES) step_kernel<R, kRollout, FT_GENERIC_MODES><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
-    else step_kernel<R, kRollout, FT_GENERIC><<<grid, HLYNR_STEP_BLOCK, 0, st>>>(A);
+    if (f == FT_V2ON) launch_inst<R, kRollout, FT_V2ON>(A, grid, st, pdl);
+    else if (f == FT_V2OFF) launch_inst<R, kRollout, FT_V2OFF>(A, grid, st, pdl);
+    else if (f == FT_V2ON_DR) launch_inst<R, kRollout, FT_V2ON_DR>(A, grid, st, pdl);
+    else if (f == FT_GENERIC_MODES) launch_inst<R, kRollout, FT_GENERIC_MODES>(A, grid, st, pdl);
+    else launch_inst<R, kRollout, FT_GENERIC>(A, grid, st, pdl);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -560,6 +576,12 @@ int hlynr_set_option(hlynr_t* s, const char* name, int64_t value) {
     if (strcmp(name, "host_chunks") == 0) {
         if (value < 0 || value > 64) return fail("host_chunks must be in [0, 64]");
         s->host_chunks = (int)value;
+        return 0;
+    }
+    if (strcmp(name, "pdl") == 0) { s->pdl = value != 0; return 0; }
+    if (strcmp(name, "host_chunk_growth") == 0) {
+        if (value < 0 || value > 64) return fail("host_chunk_growth must be in [0, 64] (eighths: 16 = chunks double, 0 = uniform chunks)");
+        s->host_chunk_growth = (int)value;
         return 0;
     }
     if (strcmp(name, "host_threads") == 0) {
@@ -876,9 +898,30 @@ int hlynr_step_host(hlynr_t* s, const float* actions_host, float* obs_host, floa
     if (s->host_info && ensure_host_info(s)) return 1;
     HostIO& h = s->hio;
     const int64_t n = s->n, od = s->obs_dim;
-    int64_t chunks = s->host_chunks > 0 ? s->host_chunks : (n >= (int64_t(1) << 19) ? 16 : (n >= (int64_t(1) << 17) ? 8 : (n >= (int64_t(1) << 15) ? 4 : 1)));
-    int64_t per = ((n + chunks - 1) / chunks + 127) & ~int64_t(127);
-    chunks = (n + per - 1) / per;
+    // chunk boundaries (whole 128-env tiles).  Uniform: host_chunks equal chunks.  Geometric (option "host_chunk_growth" > 0, the
+    // default for large shards): a small first chunk so the download starts early, then chunks that grow by the factor growth/8
+    // up to a cap -- the download of the chunks already in flight (75-111 B per env) always outlasts the upload + kernel of the
+    // next, larger one (24 B per env), so the copy engine never idles and there are fewer per-copy gaps.
+    int64_t bounds[65];
+    int64_t chunks = 0;
+    bounds[0] = 0;
+    if (s->host_chunks > 0 || s->host_chunk_growth <= 0 || n < (int64_t(1) << 17)) {
+        chunks = s->host_chunks > 0 ? s->host_chunks : (n >= (int64_t(1) << 19) ? 16 : (n >= (int64_t(1) << 17) ? 8 : (n >= (int64_t(1) << 15) ? 4 : 1)));
+        const int64_t per = ((n + chunks - 1) / chunks + 127) & ~int64_t(127);
+        chunks = (n + per - 1) / per;
+        for (int64_t c = 1; c <= chunks; ++c) bounds[c] = c * per < n ? c * per : n;
+    } else {
+        int64_t sz = 16384;
+        const int64_t cap = (int64_t(1) << 17) + (int64_t(1) << 16);   // 196608 envs: ~20 MB of observations per copy
+        while (bounds[chunks] < n && chunks < 63) {
+            const int64_t next = bounds[chunks] + sz;
+            bounds[chunks + 1] = (next >= n || n - next < sz / 2) ? n : next;
+            ++chunks;
+            sz = (sz * s->host_chunk_growth / 8 + 127) & ~int64_t(127);
+            if (sz > cap) sz = cap;
+        }
+        bounds[chunks] = n;
+    }
     // the handle's own done list for this call (a caller-attached list is restored afterwards)
     HlynrDoneRecord* keep_r = s->done_records; int32_t* keep_c = s->done_counter; const int32_t keep_cap = s->done_cap;
     s->done_records = h.d_records; s->done_counter = h.d_counter; s->done_cap = (int32_t)(n < INT32_MAX ? n : INT32_MAX);
@@ -914,7 +957,7 @@ int hlynr_step_host(hlynr_t* s, const float* actions_host, float* obs_host, floa
     struct StageGuard { CopyPool* p; ~StageGuard() { if (p) p->finish(); } } stage_guard{stage ? h.pool : nullptr};
     if (stage) h.pool->start(h.h_actions, actions_host, (size_t)n * 24);
     for (int64_t c = 0; c < chunks; ++c) {
-        const int64_t first = c * per, lim = first + per < n ? first + per : n, cnt = lim - first;
+        const int64_t first = bounds[c], lim = bounds[c + 1], cnt = lim - first;
         cudaStream_t st = h.streams[c % HLYNR_HOST_STREAMS];
         if (stage) h.pool->wait_prefix((size_t)lim * 24);
         if (trace && c < 64) t_staged[c] = since();

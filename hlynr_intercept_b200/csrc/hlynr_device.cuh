@@ -1639,6 +1639,11 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
     const int64_t warp_first = i - lane;
     const bool active = i < A.lim;
     const int64_t ii = active ? i : A.lim - 1;  // inactive lanes shadow the last env and never store
+    // Programmatic dependent launch (option "pdl"): this grid may have been scheduled while the previous kernel of the stream was
+    // still running.  Tell the scheduler the NEXT launch may do the same, then wait until the previous kernel has completed and
+    // its writes are visible -- nothing above touches global memory.  Both are no-ops in an ordinary launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     prefetch_ring_reads<R, F>(A, i, A.g_row, A.o_row);
     Env<R> e;
     load_env<R, F>(A, ii, e);

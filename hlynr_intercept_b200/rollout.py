@@ -107,10 +107,12 @@ class DeviceRolloutCollector:
             self.obs[0].copy_(self.obs[self.T])
         pipe, pol, sim = self.pipe, self.policy, self.sim
         p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+        fused = bool(getattr(pol, "fused", False))   # policy.FusedActorCritic: one sm_100a kernel per forward, fp32 rows in
+        cast = (lambda x: x) if fused or next(pol.parameters()).dtype == torch.float32 else (lambda x: x.to(next(pol.parameters()).dtype))
         with torch.no_grad():
             for t in range(self.T):
                 o = self.obs[t]
-                a, v, lp = pol(o if next(pol.parameters()).dtype == torch.float32 else o.to(next(pol.parameters()).dtype))
+                a, v, lp = pol(cast(o))
                 self.actions[t].copy_(a)
                 self.values[t].copy_(v)
                 self.log_probs[t].copy_(lp)
@@ -119,12 +121,14 @@ class DeviceRolloutCollector:
                 # TimeLimit bootstrap on the first `rows` finished episodes of the step (more only if nearly every env
                 # finishes in the same step; counted in self.overflow)
                 term_rows = terminal[: self.rows]
-                tv = pol.value(term_rows if next(pol.parameters()).dtype == torch.float32 else term_rows.to(next(pol.parameters()).dtype)).contiguous()
+                # the fused kernel reads the number of finished episodes from the device-side counter and skips every tile beyond
+                # it, so bootstrapping ALL rows costs nothing in the common case of a handful of finished episodes per step
+                tv = pol.value_rows(term_rows, counter) if fused else pol.value(cast(term_rows)).contiguous()
                 _lib.check(self.L.hlynr_bootstrap_timeouts(p(self.rewards[t]), p(records), p(counter), self.rows, p(tv), self.gamma,
                                                            p(self.overflow), sim.device_index, self._stream()))
                 torch.bitwise_or(te, tr, out=self.last_dones)
             o = self.obs[self.T]
-            last_values = pol.value(o if next(pol.parameters()).dtype == torch.float32 else o.to(next(pol.parameters()).dtype)).contiguous()
+            last_values = pol.value(cast(o)).contiguous()
             _lib.check(self.L.hlynr_gae(p(self.rewards), p(self.values), p(self.episode_starts), p(last_values), p(self.last_dones),
                                         self.T, sim.n, self.gamma, self.gae_lambda, p(self.advantages), p(self.returns),
                                         sim.device_index, self._stream()))

@@ -1,5 +1,5 @@
-"""The C-ABI library loads and exports every symbol include/hlynr.h and include/hlynr_post.h declare (no compute calls:
-CPU-safe)."""
+"""The C-ABI library loads and exports every symbol include/hlynr.h, hlynr_post.h, hlynr_rollout.h and hlynr_policy.h declare
+(no compute calls: CPU-safe)."""
 import ctypes
 import os
 import re
@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     src = open(os.path.join(ROOT, "include", "hlynr.h")).read() + open(os.path.join(ROOT, "include", "hlynr_post.h")).read() + \
-        open(os.path.join(ROOT, "include", "hlynr_rollout.h")).read()
+        open(os.path.join(ROOT, "include", "hlynr_rollout.h")).read() + open(os.path.join(ROOT, "include", "hlynr_policy.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(hlynr_[a-z_0-9]+)\s*\(", src)))
 

@@ -8,7 +8,7 @@ from hlynr_intercept_b200.sim import HlynrSim
 names = sys.argv[1].split(',') if len(sys.argv) > 1 else ['cfg4']
 precision = sys.argv[2] if len(sys.argv) > 2 else 'fp32'
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 20
-tag = os.path.basename(os.environ.get("HLYNR_B200_LIB", "default"))
+tag = os.path.basename(os.environ.get("HLYNR_B200_LIB", "default")) + " " + os.environ.get("HLYNR_OPTS", "")
 def timed(sim, pool, K):
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -17,6 +17,8 @@ def timed(sim, pool, K):
     return e0.elapsed_time(e1) / K * 1e3
 for name in names:
     sim = HlynrSim(config.baseline_config(name), n_envs=n, warn_dead=False, precision=precision)
+    for kv in filter(None, os.environ.get("HLYNR_OPTS", "").split(",")):   # e.g. HLYNR_OPTS=pdl=1
+        sim.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     sim.reset()
     pool = [(torch.rand(n, 6, device='cuda') * 2 - 1) for _ in range(4)]
     timed(sim, pool, 50)
