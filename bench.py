@@ -334,6 +334,7 @@ def main():
     ap.add_argument("--ref-python-seconds", type=float, default=10.0, help="Python-reference SubprocVecEnv sample (0 = skip)")
     ap.add_argument("--ref-envs", type=int, default=0, help="--impl reference: envs per step (0 = the workload's --envs-per-gpu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cfg5-cpu-seconds", type=float, default=8.0, help="CPU counterpart of the rollout collection (0 = skip)")
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg2@4096 / cfg3@262144 block")
     ap.add_argument("--strong-total", type=int, default=1 << 20, help="total envs of the strong-scaling block (0 = skip)")
     ap.add_argument("--fused", type=int, default=64, help="k of the extra fused-rollout measurement (0 = skip)")
@@ -499,6 +500,18 @@ def main():
             line["cpu_baseline"] = cpu_baseline(args.workload, seconds=args.cpu_seconds, ref_seconds=args.ref_python_seconds)
         else:
             line["cpu_baseline"] = None
+        if not args.no_cpu_baseline and args.rollout_steps > 0 and args.cfg5_cpu_seconds > 0:
+            # BASELINE cfg5's CPU side: the same collection loop on the host cores (reference env + torch policy on the CPU), bounded
+            try:
+                from baseline import ref_collector
+
+                c5 = ref_collector.collect(env_cfg, seconds=args.cfg5_cpu_seconds)
+            except Exception as e:
+                c5 = {"unavailable": f"{type(e).__name__}: {e}"}
+            if line["cpu_baseline"] is None:
+                line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": os.cpu_count(), "kind": "reference",
+                                        "sample": "N > 1: only the cfg5 CPU collector is timed (rank 0)"}
+            line["cpu_baseline"]["cfg5_collector"] = c5
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -618,6 +631,19 @@ def rollout_leg(ctx, args, env_cfg):
     col2.obs[col2.T].copy_(col.obs[col.T])
     tn_, _ = timed_collect(col2, False)
     rate = lambda ms: world * n_roll * T / (ms * 1e-3)  # noqa: E731
+    # BASELINE configuration 5: >= 5 M env-steps of PPO rollout collection end to end (wall clock around the collect() calls of all
+    # ranks, host-side launch work and the final synchronisation included), fused policy, graph replay when n_steps allows it
+    reps = max(1, -(-5_000_000 // (world * n_roll * T)))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        col.replay() if graphed else col.collect()
+    torch.cuda.synchronize()
+    cfg5_s = ctx.max_over_ranks(time.perf_counter() - t0)
+    cfg5 = {"env_steps": world * n_roll * T * reps, "seconds": cfg5_s, "value": world * n_roll * T * reps / cfg5_s, "unit": "env-steps/s",
+            "collects": reps, "n_steps": T, "envs_per_gpu": n_roll, "n_gpus": world,
+            "note": "BASELINE cfg5: end-to-end PPO rollout collection (policy forward, env step, frame stack + normalisation, TimeLimit "
+                    "bootstrap, GAE), >= 5 M env-steps, wall clock; the CPU counterpart of the same loop is cpu_baseline.cfg5_collector"}
     roll = {"value": rate(tr_), "unit": "env-steps/s", "envs_per_gpu": n_roll, "n_steps": T,
             "policy": "reference network 104->512->512->256 (LayerNorm, ReLU) + action_net/value_net, fused sm_100a forward "
                       "(hlynr_policy_forward: tcgen05 bf16 GEMMs, fp32 TMEM accumulators, TMA weight ring, LayerNorm/ReLU epilogues, "
@@ -627,6 +653,7 @@ def rollout_leg(ctx, args, env_cfg):
             "with_torch_policy_tf32": rate(ttr_), "with_torch_policy_tf32_eager": rate(tte_),
             "without_policy_network": rate(tn_),
             "timeout_bootstrap_overflow": int(col.overflow.item()),
+            "cfg5": cfg5,
             "note": "DeviceRolloutCollector.collect(): policy forward + hlynr_step + hlynr_post_step + value net on the finished "
                     "episodes (device-side row count) + hlynr_bootstrap_timeouts per step, hlynr_gae at the end; buffers [T,N,*] "
                     "resident in HBM; SB3 parity of the GAE / bootstrap restatement is UNPINNED (stable_baselines3 not importable here)"}

@@ -25,7 +25,7 @@ EXPORTS = [
     # include/hlynr_rollout.h
     "hlynr_bootstrap_timeouts", "hlynr_gae",
     # include/hlynr_policy.h
-    "hlynr_policy_create", "hlynr_policy_destroy", "hlynr_policy_set_weights", "hlynr_policy_forward", "hlynr_policy_launch_count",
+    "hlynr_policy_create", "hlynr_policy_destroy", "hlynr_policy_set_weights", "hlynr_policy_forward", "hlynr_policy_launch_count", "hlynr_policy_set_option", "hlynr_policy_get_timing",
 ]
 
 
@@ -107,6 +107,8 @@ def load(build_if_missing=True):
     L.hlynr_policy_set_weights.argtypes = [vp, C.POINTER(abi.HlynrPolicyWeights), vp]
     L.hlynr_policy_forward.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, u64, u64, i32, vp]
     L.hlynr_policy_launch_count.argtypes = [vp, C.POINTER(i64)]
+    L.hlynr_policy_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.hlynr_policy_get_timing.argtypes = [vp, vp]
     if L.hlynr_abi_version() != abi.ABI_VERSION:
         raise HlynrError("ABI version mismatch between libhlynr_b200.so and hlynr_intercept_b200.abi")
     if L.hlynr_params_size() != C.sizeof(abi.HlynrParams):

@@ -41,7 +41,25 @@ HD float sqr(float a) { return __fsqrt_rn(a); }
 HD double mul(double a, double b) { return __dmul_rn(a, b); }
 HD double add(double a, double b) { return __dadd_rn(a, b); }
 HD double sub(double a, double b) { return __dsub_rn(a, b); }
+// fp64 build: a / b as a * (1 / b) with the reciprocal from rcp.approx.ftz.f64 (20 bits) + two Newton steps (80 bits -> full
+// double): ~8 instructions and no slow-path call instead of the ~30 of the correctly rounded IEEE division.  The build's contract
+// is rtol 1e-5 against the float64 reference, not bit-exactness, and the quotient is within 1-2 ulp (1e-16); the profile that
+// motivated it (profiles/r02_b_fp64_*) shows 3729 instructions per env-step of 165 KB straight-line code with `no_instruction`
+// (instruction-cache misses) as the top stall reason.  Every divisor on the path is positive and finite (guards are at the call
+// sites, as in the reference).  -DHLYNR_F64_EXACT_DIV restores __ddiv_rn.
+HD double drcp(double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    return fma(r, e, r);
+}
+#ifdef HLYNR_F64_EXACT_DIV
 HD double dvd(double a, double b) { return __ddiv_rn(a, b); }
+#else
+HD double dvd(double a, double b) { return a * drcp(b); }
+#endif
 HD double sqr(double a) { return __dsqrt_rn(a); }
 
 // np.dot / np.linalg.norm on float32 vectors: float products, double accumulator, one final rounding
@@ -66,7 +84,18 @@ HD float clip(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 // float: MUFU approximations / FMA chains; double (fp64 build): the exact operation.
 // ------------------------------------------------------------------------------------------------
 HD float nrcp(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
-HD double nrcp(double a) { return dvd(1.0, a); }
+#ifdef HLYNR_F64_EXACT_DIV
+HD double nrcp(double a) { return __ddiv_rn(1.0, a); }
+#else
+HD double nrcp(double a) {   // defined below: rcp.approx.ftz.f64 + two Newton steps
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    return fma(r, e, r);
+}
+#endif
 HD float ndiv(float a, float b) { return a * nrcp(b); }
 HD double ndiv(double a, double b) { return dvd(a, b); }
 HD float nsqrt(float a) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
@@ -75,7 +104,7 @@ HD float ndot3(float ax, float ay, float az, float bx, float by, float bz) { ret
 HD double ndot3(double ax, double ay, double az, double bx, double by, double bz) { return dot3(ax, ay, az, bx, by, bz); }
 template <typename T> HD T nnorm3(T x, T y, T z) { return nsqrt(ndot3(x, y, z, x, y, z)); }
 HD float npow(float x, float y) { return exp2f(y * __log2f(x)); }
-HD double npow(double x, double y) { return pow(x, y); }
+HD double npow(double x, double y) { return exp(y * log(x)); }   // x > 0 on this path (temperature ratio, altitude / 10 m): within a few ulp of pow() at a third of its code
 HD float nexp(float x) { return __expf(x); }
 HD double nexp(double x) { return exp(x); }
 // x / c for a constant c with rc = RN(1/c): Markstein's correction yields the correctly rounded quotient
@@ -85,7 +114,14 @@ HD float cdiv(float x, float c, float rc) {
     float r = __fmaf_rn(-q, c, x);
     return __fmaf_rn(r, rc, q);
 }
+#ifdef HLYNR_F64_EXACT_DIV
 HD double cdiv(double x, double c, double) { return __ddiv_rn(x, c); }
+#else
+HD double cdiv(double x, double c, double rc) {   // division by a constant: Markstein's correction with rc = RN(1 / c)
+    const double q = x * rc;
+    return fma(fma(-q, c, x), rc, q);
+}
+#endif
 
 // atan2 / asin for the euler-angle channels obs[9:12] (core.py:1103-1121): degree-7 minimax polynomial of atan(a)/a in
 // a^2 on [0,1] (max error 1.9e-7 rad, fitted and checked in float32), one MUFU reciprocal, quadrant fix-up: ~20
@@ -436,6 +472,7 @@ template <typename R> __device__ __noinline__ Vec4<R> clamp_norm_slow(R a, R b, 
 }
 // full-range sine / cosine of the quaternion half-angle: actions outside [-1, 1] only
 __device__ __noinline__ Pair<float> sincos_full(float h) { return Pair<float>{sinf(h), cosf(h)}; }
+__device__ __noinline__ Pair<double> sincos_full_d(double h) { double s, c; sincos(h, &s, &c); return Pair<double>{s, c}; }
 
 // The LOS basis shared by the observation (core.py:803-845, :929-945) and the action transform
 // (environment.py:965-1020): lu = rel/|rel|, lh = normalize(lu x world_up) = (lu.y, -lu.x, 0)/n, lv = lu x lh.
@@ -1087,7 +1124,18 @@ HD void quat_step(Env<double>& e, double wx, double wy, double wz, double dt) {
     double ang = mul(wn, dt);
     if (ang > 1e-6) {
         double sh, ch;
-        sincos(mul(ang, 0.5), &sh, &ch);
+        const double h = mul(ang, 0.5), h2 = h * h;
+        if (h <= 0.5) {   // |a| <= 1 gives h <= 0.18 rad: Taylor series to 1e-19 instead of the full-range sincos (Payne-Hanek slow path)
+            sh = h * fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, -7.6471637318198164e-13, 1.6059043836821613e-10), -2.5052108385441720e-08),
+                                                                       2.7557319223985893e-06), -1.9841269841269841e-04), 8.3333333333333332e-03),
+                                 -1.6666666666666666e-01), 1.0);
+            ch = fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, 4.7794773323873853e-14, -1.1470745597729725e-11), 2.0876756987868100e-09),
+                                                                     -2.7557319223985888e-07), 2.4801587301587302e-05), -1.3888888888888889e-03),
+                                             4.1666666666666664e-02), -0.5), 1.0);
+        } else {
+            const Pair<double> sc = sincos_full_d(h);
+            sh = sc.a; ch = sc.b;
+        }
         double w1 = ch, x1 = mul(dvd(wx, wn), sh), y1 = mul(dvd(wy, wn), sh), z1 = mul(dvd(wz, wn), sh);
         double w2 = (double)e.qw, x2 = (double)e.qx, y2 = (double)e.qy, z2 = (double)e.qz;
         float nw = (float)sub(sub(sub(mul(w1, w2), mul(x1, x2)), mul(y1, y2)), mul(z1, z2));

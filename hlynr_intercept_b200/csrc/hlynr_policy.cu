@@ -72,17 +72,25 @@ __host__ __device__ constexpr uint32_t instr_desc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// Per-column vectors of the epilogues (biases, LayerNorm gamma / beta, head biases, log_std) live in one global array read with
+// warp-uniform 128-bit loads (L1 hits).  Passing them by value as a 15 KiB kernel parameter (constant bank, indexed LDC.64) was
+// measured SLOWER: 9.5 instead of 6.8 us per 512-wide epilogue.
+constexpr int VEC_B1 = 0, VEC_G1 = 512, VEC_BE1 = 1024, VEC_B2 = 1536, VEC_G2 = 2048, VEC_BE2 = 2560, VEC_B3 = 3072, VEC_G3 = 3328,
+              VEC_BE3 = 3584, VEC_BH = 3840, VEC_LS = 3856, VEC_TOTAL = 3864;
+
 struct Params {
     const float* obs;
     int64_t n_rows;
     const int32_t* n_rows_dev;
-    const float *b1, *g1, *be1, *b2, *g2, *be2, *b3, *g3, *be3, *bh, *log_std;
+    const float* vec;   // the per-column vectors, VEC_* offsets
     float* actions; float* values; float* logp; float* mean;
     float ln_eps;
     uint32_t k0, k1;        // Philox key (seed)
     uint32_t ctr_lo, ctr_hi; // call counter
     int deterministic;
     int* error_flag;
+    long long* timing;   // debug: SM-clock timestamps of the phases of CTA 0's tiles (NULL = off), [tile][16]
+    int timing_tiles;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -106,6 +114,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// multicast variants (thread-block clusters): one L2 read of a weight slice lands in the shared memory of every CTA of the
+// cluster (same offset), completing bytes on each CTA's own mbarrier; the commit arrives on the empty barrier of every CTA
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -138,6 +159,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
                  : "r"(addr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait + a data dependency on the loaded registers, so that no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait_ld32(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :: "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :: "memory");
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -167,60 +203,122 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float* z0, 
     *z0 = r * c; *z1 = r * s;
 }
 
+// packed fp32 pairs (sm_100 FADD2 / FFMA2: two lanes of fp32 per instruction) and the fused ReLU + bf16x2 conversion
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint32_t relu_bf16x2(uint64_t v) {   // {lo, hi} fp32 -> max(., 0) -> bf16x2 (lo in the low half)
+    float lo, hi;
+    upk2(v, lo, hi);
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
 // bias + LayerNorm + ReLU epilogue of one hidden layer: TMEM accumulators -> bf16 A operand of the next GEMM.
 // Two warps share a row quarter: warp w and w + 4 read TMEM lanes 32 * (w % 4) ..., each over half of the N columns.
+// The arithmetic runs on packed fp32 pairs (3.5 instead of 8.5 floating-point instructions per element over the two passes).
+// one 32-column chunk of pass 1: x = v + b, accumulate the sum and the sum of squares (packed fp32 pairs)
+__device__ __forceinline__ void stats_chunk(const uint32_t (&v)[32], const float4 (&b)[8], uint64_t& s2, uint64_t& ss2) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint64_t x0 = add2(pk2u(v[4 * j], v[4 * j + 1]), pk2(b[j].x, b[j].y)), x1 = add2(pk2u(v[4 * j + 2], v[4 * j + 3]), pk2(b[j].z, b[j].w));
+        s2 = add2(s2, add2(x0, x1));
+        ss2 = fma2(x0, x0, fma2(x1, x1, ss2));
+    }
+}
+// one 16-column chunk of pass 2: y = ((v + b) * rstd - mean * rstd) * gamma + beta, ReLU fused into the bf16 conversion, two
+// 16-byte chunks of the swizzled K-major A operand
+__device__ __forceinline__ void norm_chunk(const uint32_t (&v)[16], const float4 (&b)[4], const float4 (&g)[4], const float4 (&be)[4],
+                                           uint64_t rstd2, uint64_t shift2, uint32_t a_base, int row, int c0) {
+    uint32_t out[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint64_t t0 = fma2(add2(pk2u(v[4 * j], v[4 * j + 1]), pk2(b[j].x, b[j].y)), rstd2, shift2);
+        const uint64_t t1 = fma2(add2(pk2u(v[4 * j + 2], v[4 * j + 3]), pk2(b[j].z, b[j].w)), rstd2, shift2);
+        out[2 * j] = relu_bf16x2(fma2(t0, pk2(g[j].x, g[j].y), pk2(be[j].x, be[j].y)));
+        out[2 * j + 1] = relu_bf16x2(fma2(t1, pk2(g[j].z, g[j].w), pk2(be[j].z, be[j].w)));
+    }
+    st_shared_v4(a_base + a_chunk_offset(row, c0 >> 3), make_uint4(out[0], out[1], out[2], out[3]));
+    st_shared_v4(a_base + a_chunk_offset(row, (c0 >> 3) + 1), make_uint4(out[4], out[5], out[6], out[7]));
+}
+
+// bias + LayerNorm + ReLU epilogue of one hidden layer: TMEM accumulators -> bf16 A operand of the next GEMM.
+// Two warps share a row quarter: warp w and w + 4 read TMEM lanes 32 * (w % 4) ..., each over half of the N columns.
+// The arithmetic runs on packed fp32 pairs (3.5 instead of 8.5 floating-point instructions per element over the two passes), and
+// the TMEM loads are double-buffered in registers: the load of chunk i + 1 is in flight while chunk i is processed (a TMEM round
+// trip per chunk, exposed at 2 warps per scheduler, was most of the epilogue's time: profiles/r02_c_policy_phases.log).
 template <int N>
 __device__ __forceinline__ void layer_epilogue(uint32_t lane_addr, uint32_t a_base, float2 (*stats)[BM], int row, int half,
                                                const float* __restrict__ bias, const float* __restrict__ gamma,
                                                const float* __restrict__ beta, float eps) {
     constexpr int HALF = N / 2;
+    static_assert(HALF % 64 == 0, "two 32-column chunks per iteration");
     const int cbeg = half * HALF;
-    float s = 0.f, ss = 0.f;
+    uint64_t s2 = pk2(0.f, 0.f), ss2 = pk2(0.f, 0.f);
+    {
+        uint32_t va[32], vb[32];
+        tmem_ld32(lane_addr + (uint32_t)cbeg, va);
 #pragma unroll 1
-    for (int c0 = cbeg; c0 < cbeg + HALF; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + (uint32_t)c0, v);
-        tmem_wait_ld();
+        for (int c0 = cbeg; c0 < cbeg + HALF; c0 += 64) {
+            float4 b[8];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
-            const float x0 = __uint_as_float(v[j]) + b.x, x1 = __uint_as_float(v[j + 1]) + b.y;
-            const float x2 = __uint_as_float(v[j + 2]) + b.z, x3 = __uint_as_float(v[j + 3]) + b.w;
-            s += (x0 + x1) + (x2 + x3);
-            ss = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, ss))));
+            for (int j = 0; j < 8; ++j) b[j] = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+            tmem_wait_ld32(va);
+            tmem_ld32(lane_addr + (uint32_t)(c0 + 32), vb);           // in flight while chunk A is summed
+            stats_chunk(va, b, s2, ss2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = __ldg(reinterpret_cast<const float4*>(bias + c0 + 32) + j);
+            tmem_wait_ld32(vb);
+            if (c0 + 64 < cbeg + HALF) tmem_ld32(lane_addr + (uint32_t)(c0 + 64), va);
+            stats_chunk(vb, b, s2, ss2);
         }
     }
+    float s_lo, s_hi, q_lo, q_hi;
+    upk2(s2, s_lo, s_hi); upk2(ss2, q_lo, q_hi);
+    const float s = s_lo + s_hi, ss = q_lo + q_hi;
     stats[half][row] = make_float2(s, ss);
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // the two halves of every row have published their sums
     const float2 o = stats[half ^ 1][row];
     const float mean = (s + o.x) * (1.0f / N);
     const float var = fmaxf((ss + o.y) * (1.0f / N) - mean * mean, 0.f);   // biased variance, as nn.LayerNorm
     const float rstd = rsqrtf(var + eps);
-    const float shift = -mean * rstd;
+    const uint64_t rstd2 = pk2(rstd, rstd), shift2 = pk2(-mean * rstd, -mean * rstd);
+    {
+        uint32_t va[16], vb[16];
+        tmem_ld16(lane_addr + (uint32_t)cbeg, va);
 #pragma unroll 1
-    for (int c0 = cbeg; c0 < cbeg + HALF; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + (uint32_t)c0, v);
-        tmem_wait_ld();
+        for (int c0 = cbeg; c0 < cbeg + HALF; c0 += 32) {
+            float4 b[4], g[4], be[4];
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-            float y[8];
-#pragma unroll
-            for (int h = 0; h < 8; h += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + j + h));
-                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c0 + j + h));
-                const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0 + j + h));
-                y[h] = fmaxf(fmaf(fmaf(__uint_as_float(v[j + h]) + b.x, rstd, shift), g.x, be.x), 0.f);
-                y[h + 1] = fmaxf(fmaf(fmaf(__uint_as_float(v[j + h + 1]) + b.y, rstd, shift), g.y, be.y), 0.f);
-                y[h + 2] = fmaxf(fmaf(fmaf(__uint_as_float(v[j + h + 2]) + b.z, rstd, shift), g.z, be.z), 0.f);
-                y[h + 3] = fmaxf(fmaf(fmaf(__uint_as_float(v[j + h + 3]) + b.w, rstd, shift), g.w, be.w), 0.f);
+            for (int j = 0; j < 4; ++j) {
+                b[j] = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+                g[j] = __ldg(reinterpret_cast<const float4*>(gamma + c0) + j);
+                be[j] = __ldg(reinterpret_cast<const float4*>(beta + c0) + j);
             }
-            st_shared_v4(a_base + a_chunk_offset(row, (c0 + j) >> 3),
-                         make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7])));
+            tmem_wait_ld16(va);
+            tmem_ld16(lane_addr + (uint32_t)(c0 + 16), vb);
+            norm_chunk(va, b, g, be, rstd2, shift2, a_base, row, c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                b[j] = __ldg(reinterpret_cast<const float4*>(bias + c0 + 16) + j);
+                g[j] = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 16) + j);
+                be[j] = __ldg(reinterpret_cast<const float4*>(beta + c0 + 16) + j);
+            }
+            tmem_wait_ld16(vb);
+            if (c0 + 32 < cbeg + HALF) tmem_ld16(lane_addr + (uint32_t)(c0 + 32), va);
+            norm_chunk(vb, b, g, be, rstd2, shift2, a_base, row, c0 + 16);
         }
     }
 }
 
+// CL = CTAs per thread-block cluster (1, 2 or 4).  The CTAs of a cluster work on different row tiles in lock step and share
+// every weight tile: CTA r loads rows [r * N / CL, (r + 1) * N / CL) of a stage and multicasts them to all, so the L2 -> SM weight
+// traffic (904 KiB per 128-row tile, the kernel's bottleneck at CL = 1) is divided by CL.  A stage may be refilled only after the
+// MMAs of ALL CTAs have read it: the empty barriers count CL arrivals, delivered by multicast tcgen05.commit.
+template <int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                       const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tm3, const Params P) {
@@ -235,11 +333,17 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_cons
     int64_t n_rows = P.n_rows;
     if (P.n_rows_dev) { const int64_t lim = (int64_t)*P.n_rows_dev; n_rows = lim < n_rows ? (lim < 0 ? 0 : lim) : n_rows; }
     const int64_t n_tiles = (n_rows + BM - 1) / BM;
-    if ((int64_t)blockIdx.x >= n_tiles) return;   // uniform for the whole CTA: nothing was allocated yet
+    if ((int64_t)(blockIdx.x / CL) * CL >= n_tiles) return;   // uniform for the whole cluster: nothing was allocated yet
+    // every CTA that stays runs the same number of iterations (the ring protocol is cluster-wide); a tile index beyond n_tiles is
+    // an all-padding tile: zero rows in, no rows out
+    const int64_t n_iter = (n_tiles + gridDim.x - 1) / gridDim.x;
+    uint32_t cta_rank = 0;
+    if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
     if ((sbase & 1023u) != 0) { if (threadIdx.x == 0 && P.error_flag) atomicExch(P.error_flag, 100); __trap(); }
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, CL); }
         mbar_init(bar_a, EPI_THREADS);
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -249,7 +353,8 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_cons
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all();   // the peers' barriers are initialised before anything arrives on them remotely
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -258,15 +363,18 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_cons
         if (lane == 0) {
             const CUtensorMap* maps[N_LAYERS] = {&tm0, &tm1, &tm2, &tm3};
             int stage = 0; uint32_t phase = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int64_t it = 0; it < n_iter; ++it) {
 #pragma unroll 1
                 for (int l = 0; l < N_LAYERS; ++l) {
-                    const uint32_t bytes = (uint32_t)(layer_n(l) * BK * 2);
+                    const uint32_t bytes = (uint32_t)(layer_n(l) * BK * 2);        // of the whole stage, all slices
+                    const int slice_rows = layer_n(l) / CL;
                     for (int nc = 0; nc < layer_nchunks(l); ++nc)
                         for (int kb = 0; kb < layer_kblocks(l); ++kb) {
-                            mbar_wait(bar_empty + stage * 8, phase ^ 1u, P.error_flag, 1);
+                            mbar_wait(bar_empty + stage * 8, phase ^ 1u, P.error_flag, 1);   // released by the MMAs of all CL CTAs
                             mbar_expect_tx(bar_full + stage * 8, bytes);
-                            tma_load_2d(ring + stage * STAGE_BYTES, maps[l], bar_full + stage * 8, kb * BK, nc * BN);
+                            const uint32_t dst = ring + stage * STAGE_BYTES + cta_rank * (uint32_t)(slice_rows * BK * 2);
+                            if (CL == 1) tma_load_2d(dst, maps[l], bar_full + stage * 8, kb * BK, nc * BN);
+                            else tma_load_2d_mc(dst, maps[l], bar_full + stage * 8, kb * BK, nc * BN + (int)cta_rank * slice_rows, MC_MASK);
                             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                         }
                 }
@@ -277,7 +385,7 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_cons
         // ===== MMA issuer =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0, pa = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int64_t it = 0; it < n_iter; ++it) {
 #pragma unroll 1
                 for (int l = 0; l < N_LAYERS; ++l) {
                     mbar_wait(bar_a, pa, P.error_flag, 2);   // A operand of this layer is in shared memory, TMEM is drained
@@ -293,7 +401,8 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_cons
 #pragma unroll
                             for (int s = 0; s < BK / 16; ++s)   // UMMA_K = 16 bf16 = 32 bytes inside the swizzle span
                                 umma_f16(d, adesc + (uint64_t)(2 * s), bdesc + (uint64_t)(2 * s), idesc, (kb | s) ? 1u : 0u);
-                            umma_commit(bar_empty + stage * 8);   // the stage is free once these MMAs have read it
+                            if (CL == 1) umma_commit(bar_empty + stage * 8);   // the stage is free once these MMAs have read it
+                            else umma_commit_mc(bar_empty + stage * 8, MC_MASK);   // ... in every CTA of the cluster
                             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                         }
                     }
@@ -308,7 +417,11 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_cons
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t pacc = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        long long* tstamp = nullptr;
+        for (int64_t it = 0; it < n_iter; ++it) {
+            const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+            tstamp = (P.timing && blockIdx.x == 0 && threadIdx.x == 0 && it < P.timing_tiles) ? P.timing + it * 16 : nullptr;
+            if (tstamp) tstamp[0] = clock64();
             // x tile: fp32 [128, 104] -> bf16, K padded to 128 with zeros, swizzled K-major
 #pragma unroll
             for (int i = 0; i < (BM * IN_PAD / 8) / EPI_THREADS; ++i) {
@@ -326,23 +439,27 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_cons
             fence_async_smem();    // generic-proxy writes -> visible to the tensor core's async-proxy reads
             tc_fence_before();
             mbar_arrive(bar_a);
+            if (tstamp) tstamp[1] = clock64();
             // hidden layers
 #pragma unroll 1
             for (int l = 0; l < 3; ++l) {
                 mbar_wait(bar_acc, pacc, P.error_flag, 4);
                 pacc ^= 1u;
                 tc_fence_after();
-                if (l == 0) layer_epilogue<H1>(lane_addr, a_base, stats, row, half, P.b1, P.g1, P.be1, P.ln_eps);
-                else if (l == 1) layer_epilogue<H2>(lane_addr, a_base, stats, row, half, P.b2, P.g2, P.be2, P.ln_eps);
-                else layer_epilogue<H3>(lane_addr, a_base, stats, row, half, P.b3, P.g3, P.be3, P.ln_eps);
+                if (tstamp) tstamp[2 + 2 * l] = clock64();
+                if (l == 0) layer_epilogue<H1>(lane_addr, a_base, stats, row, half, P.vec + VEC_B1, P.vec + VEC_G1, P.vec + VEC_BE1, P.ln_eps);
+                else if (l == 1) layer_epilogue<H2>(lane_addr, a_base, stats, row, half, P.vec + VEC_B2, P.vec + VEC_G2, P.vec + VEC_BE2, P.ln_eps);
+                else layer_epilogue<H3>(lane_addr, a_base, stats, row, half, P.vec + VEC_B3, P.vec + VEC_G3, P.vec + VEC_BE3, P.ln_eps);
                 fence_async_smem();
                 tc_fence_before();
                 mbar_arrive(bar_a);
+                if (tstamp) tstamp[3 + 2 * l] = clock64();
             }
             // heads
             mbar_wait(bar_acc, pacc, P.error_flag, 5);
             pacc ^= 1u;
             tc_fence_after();
+            if (tstamp) tstamp[8] = clock64();
             if (half == 0) {
                 uint32_t v[16];
                 tmem_ld16(lane_addr + 256u, v);
@@ -350,9 +467,10 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_cons
                 const int64_t grow = tile * BM + row;
                 if (grow < n_rows) {
                     float mean[ACT], eps[ACT + 2];
+                    const float* vf = P.vec;
 #pragma unroll
-                    for (int k = 0; k < ACT; ++k) { mean[k] = __uint_as_float(v[k]) + __ldg(P.bh + k); eps[k] = 0.f; }
-                    const float value = __uint_as_float(v[ACT]) + __ldg(P.bh + ACT);
+                    for (int k = 0; k < ACT; ++k) { mean[k] = __uint_as_float(v[k]) + vf[VEC_BH + k]; eps[k] = 0.f; }
+                    const float value = __uint_as_float(v[ACT]) + vf[VEC_BH + ACT];
                     if (!P.deterministic && (P.actions || P.logp)) {
                         const uint4 r0 = philox((uint32_t)grow, (uint32_t)((uint64_t)grow >> 32), P.ctr_lo, P.ctr_hi, P.k0, P.k1);
                         const uint4 r1 = philox((uint32_t)grow, (uint32_t)((uint64_t)grow >> 32) | 0x80000000u, P.ctr_lo, P.ctr_hi, P.k0, P.k1);
@@ -363,7 +481,7 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_cons
                     float lp = -0.5f * ACT * 1.8378770664093453f;   // -(k/2) log(2 pi)
 #pragma unroll
                     for (int k = 0; k < ACT; ++k) {
-                        const float ls = __ldg(P.log_std + k);
+                        const float ls = vf[VEC_LS + k];
                         lp += -0.5f * eps[k] * eps[k] - ls;
                         if (P.actions) P.actions[grow * ACT + k] = fmaf(__expf(ls), eps[k], mean[k]);
                         if (P.mean) P.mean[grow * ACT + k] = mean[k];
@@ -373,10 +491,12 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_cons
                 }
             }
             tc_fence_before();   // the next tile's first GEMM overwrites the head accumulators: order the loads before its a_ready
+            if (tstamp) tstamp[9] = clock64();
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into its shared memory or arrive on its barriers
+    else __syncthreads();
     if (warp == 9) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -412,16 +532,17 @@ struct hlynr_policy {
     __nv_bfloat16 *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *wh = nullptr;   // [512,128], [512,512], [256,512], [16,256]
     float* vec = nullptr;   // b1 g1 be1 (512 x3) | b2 g2 be2 (512 x3) | b3 g3 be3 (256 x3) | bh (16) | log_std (8)
     int* error_flag = nullptr;
-    CUtensorMap tm[4];
+    long long* timing = nullptr;   // debug timestamps (option "timing")
+    int timing_on = 0;
+    CUtensorMap tm[3][4];   // [log2(cluster size)][layer]: box rows = N / cluster size
+    int cluster = 1;        // CTAs per cluster (option "cluster": 1, 2 or 4)
+    int grid_for_cluster[3] = {0, 0, 0};
     float ln_eps = 1e-5f;
     bool ready = false, smem_configured = false;
     int64_t launches = 0;
 };
 
 namespace {
-constexpr int VEC_B1 = 0, VEC_G1 = 512, VEC_BE1 = 1024, VEC_B2 = 1536, VEC_G2 = 2048, VEC_BE2 = 2560, VEC_B3 = 3072, VEC_G3 = 3328,
-              VEC_BE3 = 3584, VEC_BH = 3840, VEC_LS = 3856, VEC_TOTAL = 3864;
-
 int make_map(EncodeTiledFn enc, CUtensorMap* m, void* base, int rows, int k, int box_rows) {
     const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
@@ -438,7 +559,7 @@ extern "C" {
 void hlynr_policy_destroy(hlynr_policy_t* p) {
     if (!p) return;
     DeviceGuard g(p->device);
-    cudaFree(p->w1); cudaFree(p->w2); cudaFree(p->w3); cudaFree(p->wh); cudaFree(p->vec); cudaFree(p->error_flag);
+    cudaFree(p->w1); cudaFree(p->w2); cudaFree(p->w3); cudaFree(p->wh); cudaFree(p->vec); cudaFree(p->error_flag); cudaFree(p->timing);
     delete p;
 }
 
@@ -472,10 +593,13 @@ int hlynr_policy_create(int device, hlynr_policy_t** out) {
         return r;
     }
     EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fn);
-    if (make_map(enc, &p->tm[0], p->w1, H1, IN_PAD, BN) || make_map(enc, &p->tm[1], p->w2, H2, H1, BN) ||
-        make_map(enc, &p->tm[2], p->w3, H3, H2, BN) || make_map(enc, &p->tm[3], p->wh, HEAD_N, H3, HEAD_N)) {
-        hlynr_policy_destroy(p);
-        return 1;
+    for (int c = 0; c < 3; ++c) {
+        const int cl = 1 << c;
+        if (make_map(enc, &p->tm[c][0], p->w1, H1, IN_PAD, BN / cl) || make_map(enc, &p->tm[c][1], p->w2, H2, H1, BN / cl) ||
+            make_map(enc, &p->tm[c][2], p->w3, H3, H2, BN / cl) || make_map(enc, &p->tm[c][3], p->wh, HEAD_N, H3, HEAD_N / cl)) {
+            hlynr_policy_destroy(p);
+            return 1;
+        }
     }
     *out = p;
     return 0;
@@ -521,24 +645,78 @@ int hlynr_policy_forward(hlynr_policy_t* p, const float* obs_dev, int64_t n_rows
     if (((uintptr_t)obs_dev & 15u) != 0) return fail("hlynr_policy_forward: obs_dev must be 16-byte aligned");
     DeviceGuard g(p->device);
     if (!p->smem_configured) {
-        CK(cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CK(cudaFuncSetAttribute(policy_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CK(cudaFuncSetAttribute(policy_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CK(cudaFuncSetAttribute(policy_forward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         p->smem_configured = true;
     }
     Params P;
     memset(&P, 0, sizeof(P));
     P.obs = obs_dev; P.n_rows = n_rows; P.n_rows_dev = n_rows_dev;
-    const float* v = p->vec;
-    P.b1 = v + VEC_B1; P.g1 = v + VEC_G1; P.be1 = v + VEC_BE1; P.b2 = v + VEC_B2; P.g2 = v + VEC_G2; P.be2 = v + VEC_BE2;
-    P.b3 = v + VEC_B3; P.g3 = v + VEC_G3; P.be3 = v + VEC_BE3; P.bh = v + VEC_BH; P.log_std = v + VEC_LS;
+    P.vec = p->vec;
     P.actions = actions_dev; P.values = values_dev; P.logp = logp_dev; P.mean = mean_dev;
     P.ln_eps = p->ln_eps;
     P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.ctr_lo = (uint32_t)counter; P.ctr_hi = (uint32_t)(counter >> 32);
     P.deterministic = deterministic; P.error_flag = p->error_flag;
+    P.timing = p->timing_on ? p->timing : nullptr; P.timing_tiles = 8;
     const int64_t n_tiles = (n_rows + BM - 1) / BM;
-    const int grid = (int)(n_tiles < p->sm_count ? n_tiles : p->sm_count);
-    policy_forward_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(p->tm[0], p->tm[1], p->tm[2], p->tm[3], P);
+    const int cl = p->cluster, ci = cl == 4 ? 2 : (cl == 2 ? 1 : 0);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = cl > 1 ? 1u : 0u;
+    if (p->grid_for_cluster[ci] == 0) {   // one resident wave: as many clusters as fit the device (GPC boundaries limit cl = 4)
+        int clusters = p->sm_count / cl;
+        if (cl > 1) {
+            cfg.gridDim = dim3((unsigned)(clusters * cl));
+            int fit = 0;
+            const cudaError_t oe = cl == 2 ? cudaOccupancyMaxActiveClusters(&fit, policy_forward_kernel<2>, &cfg)
+                                           : cudaOccupancyMaxActiveClusters(&fit, policy_forward_kernel<4>, &cfg);
+            if (oe == cudaSuccess && fit > 0 && fit < clusters) clusters = fit;
+            else if (oe != cudaSuccess) cudaGetLastError();
+        }
+        p->grid_for_cluster[ci] = clusters * cl;
+    }
+    int64_t grid = ((n_tiles + cl - 1) / cl) * cl;
+    if (grid > p->grid_for_cluster[ci]) grid = p->grid_for_cluster[ci];
+    cfg.gridDim = dim3((unsigned)grid);
+    const CUtensorMap* tm = p->tm[ci];
+    cudaError_t le;
+    if (cl == 1) le = cudaLaunchKernelEx(&cfg, policy_forward_kernel<1>, tm[0], tm[1], tm[2], tm[3], P);
+    else if (cl == 2) le = cudaLaunchKernelEx(&cfg, policy_forward_kernel<2>, tm[0], tm[1], tm[2], tm[3], P);
+    else le = cudaLaunchKernelEx(&cfg, policy_forward_kernel<4>, tm[0], tm[1], tm[2], tm[3], P);
+    if (le != cudaSuccess) return fail("hlynr_policy_forward: launch failed: %s", cudaGetErrorString(le));
     CK(cudaGetLastError());
     p->launches += 1;
+    return 0;
+}
+
+int hlynr_policy_set_option(hlynr_policy_t* p, const char* name, int64_t value) {
+    if (!p || !name) return fail("null argument");
+    if (strcmp(name, "timing") == 0) {   // debug: record SM-clock timestamps of the phases of CTA 0's first 8 tiles
+        DeviceGuard g(p->device);
+        if (value && !p->timing) { CK(cudaMalloc(&p->timing, sizeof(long long) * 8 * 16)); CK(cudaMemset(p->timing, 0, sizeof(long long) * 8 * 16)); }
+        p->timing_on = value != 0;
+        return 0;
+    }
+    if (strcmp(name, "cluster") == 0) {
+        if (value != 1 && value != 2 && value != 4) return fail("hlynr_policy_set_option: cluster must be 1, 2 or 4");
+        p->cluster = (int)value;
+        return 0;
+    }
+    return fail("hlynr_policy_set_option: unknown option '%s'", name);
+}
+
+/* Debug: the timestamps recorded by the last forward with option "timing" = 1: out[tile][16] (SM clock cycles): 0 tile start,
+ * 1 x loaded, 2/4/6 accumulators of layer 1/2/3 ready, 3/5/7 epilogue of layer 1/2/3 done, 8 head accumulators ready, 9 tile done. */
+int hlynr_policy_get_timing(hlynr_policy_t* p, long long* host_out) {
+    if (!p || !host_out || !p->timing) return fail("hlynr_policy_get_timing: option \"timing\" was never enabled");
+    DeviceGuard g(p->device);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(host_out, p->timing, sizeof(long long) * 8 * 16, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -176,6 +176,9 @@ class FusedActorCritic:
         _, v, _, m = self.forward(obs, deterministic=True, want=("values", "mean"))
         return m, v
 
+    def set_option(self, name, value):
+        _lib.check(self.L.hlynr_policy_set_option(self.h, name.encode(), int(value)))
+
     def parameters(self):
         return self.net.parameters()
 

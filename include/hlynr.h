@@ -326,11 +326,11 @@ int hlynr_debug_draws(hlynr_t* sim, int64_t env_global_id, uint32_t episode, uin
  * "host_info": 1 (default) = hlynr_step_host also fills the [N]-sized info arrays read by hlynr_info_host, 0 = skip them
  * (finished episodes are still reported through hlynr_done_records_host).
  * "host_chunks": number of chunks hlynr_step_host pipelines (H2D | kernel | D2H on separate streams), 0 = auto.
- * "pdl": 1 = step kernels are launched with programmatic stream serialization (cudaLaunchAttributeProgrammaticStreamSerialization):
+ * "pdl": 1 (default) = step kernels are launched with programmatic stream serialization (cudaLaunchAttributeProgrammaticStreamSerialization):
  * a tick's grid is scheduled while the previous kernel of the stream drains and waits (griddepcontrol.wait) for its completion
  * before touching memory, which hides the launch latency between back-to-back ticks; 0 = ordinary launches.
- * "host_chunk_growth": 0 (default) = uniform chunks; g > 0 = a 16384-env first chunk, then every chunk g/8 times the previous one
- * (16 = doubling) up to 196608 envs, for shards of >= 131072 envs when "host_chunks" is 0.
+ * "host_chunk_growth": g > 0 (default 12) = a 16384-env first chunk, then every chunk g/8 times the previous one (12 = x1.5,
+ * 16 = doubling) up to 196608 envs, for shards of >= 131072 envs when "host_chunks" is 0; 0 = uniform chunks.
  * "host_threads": threads used for staging memcpys of unpinned caller buffers, 0 = auto.
  * "obs_dim": 26 (default) or 17.  With 17 every observation array of this API (obs_dev / obs_host / terminal_obs_*) is float[N,17]:
  * the leading "17-D radar" channels obs[0:17] of the reference's vector (rl_system/hrl/observation_schema.py:13-46 MIN_DIMENSION,

@@ -65,6 +65,15 @@ int hlynr_policy_forward(hlynr_policy_t* p, const float* obs_dev, int64_t n_rows
                          float* actions_dev, float* values_dev, float* logp_dev, float* mean_dev, uint64_t seed,
                          uint64_t counter, int deterministic, void* stream);
 
+/* Options.  "cluster": CTAs per thread-block cluster, 1, 2 (default) or 4: the CTAs of a cluster share every weight tile through
+ * TMA multicast, which divides the L2 -> SM weight traffic (the kernel's bottleneck without it) by the cluster size. */
+int hlynr_policy_set_option(hlynr_policy_t* p, const char* name, int64_t value);
+
+/* Debug: with option "timing" = 1 the kernel records SM-clock timestamps of the phases of CTA 0's first 8 tiles; host_out is
+ * long long[8][16]: 0 tile start, 1 x loaded, 2/4/6 accumulators of layer 1/2/3 ready, 3/5/7 epilogue of layer 1/2/3 done,
+ * 8 head accumulators ready, 9 tile done. */
+int hlynr_policy_get_timing(hlynr_policy_t* p, long long* host_out);
+
 /* Kernel launches issued by this handle so far. */
 int hlynr_policy_launch_count(const hlynr_policy_t* p, int64_t* out);
 

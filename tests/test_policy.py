@@ -35,13 +35,15 @@ def _nets(seed=0, scale_heads=True):
     return net
 
 
+@pytest.mark.parametrize("cluster", [1, 2, 4])
 @pytest.mark.parametrize("n", [1, 127, 128, 129, 1000, 148 * 128 * 2 + 77])
-def test_fused_forward_matches_torch(n):
+def test_fused_forward_matches_torch(n, cluster):
     import torch
     from hlynr_intercept_b200.policy import FusedActorCritic, bf16_emulated_forward
 
     net = _nets()
     fused = FusedActorCritic(net, device=0, seed=5)
+    fused.set_option("cluster", cluster)   # thread-block clusters: the CTAs of a cluster share the weight tiles by TMA multicast
     g = torch.Generator(device="cuda"); g.manual_seed(n)
     obs = (torch.randn(n, 104, device="cuda", generator=g) * 1.5).clamp(-10, 10).contiguous()
     obs[:, 7] = 10.0   # a clipped VecNormalize channel
@@ -83,6 +85,7 @@ def test_device_side_row_count_and_weight_sync():
 
     net = _nets(seed=1)
     fused = FusedActorCritic(net, device=0)
+    fused.set_option("cluster", 2)
     obs = torch.randn(5000, 104, device="cuda")
     full = fused.value(obs).clone()
     buf = fused._out("values", (5000,))

@@ -4,7 +4,7 @@ from common import CudaBatch, golden_setup, load_golden
 g = load_golden("volley3_cfg4_f32_zem")
 P, cur = golden_setup(g)
 meta = g["meta"]
-cuda = CudaBatch(P, cur, meta["n_envs"], seed=meta["seed"], float64=False, variant=1)
+cuda = CudaBatch(P, cur, meta["n_envs"], seed=meta["seed"], float64=False)
 obs0 = cuda.reset()
 e = 3
 np.set_printoptions(linewidth=250, precision=5, suppress=True)

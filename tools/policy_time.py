@@ -14,11 +14,14 @@ def timed(f, reps):
     return e0.elapsed_time(e1) / reps * 1e3
 for n in (4096, 16384, 131072, 1 << 20):
     obs = torch.randn(n, 104, device="cuda")
-    us = timed(lambda: fused(obs), 20)
-    line = f"n={n}: fused {us:.1f} us ({n * FLOP_PER_ROW / us / 1e6:.0f} TFLOP/s)"
+    line = f"n={n}:"
+    for cl in (1, 2, 4):
+        fused.set_option("cluster", cl)
+        us = timed(lambda: fused(obs), 20)
+        line += f" fused cluster {cl}: {us:.1f} us ({n * FLOP_PER_ROW / us / 1e6:.0f} TFLOP/s);"
     with torch.no_grad():
         torch.backends.cuda.matmul.allow_tf32 = False
-        line += f"; torch fp32 {timed(lambda: net(obs), 5):.1f} us"
+        line += f" torch fp32 {timed(lambda: net(obs), 5):.1f} us"
         torch.backends.cuda.matmul.allow_tf32 = True
         line += f"; torch tf32 {timed(lambda: net(obs), 10):.1f} us"
         with torch.autocast("cuda", dtype=torch.bfloat16):

@@ -8,9 +8,8 @@ from hlynr_intercept_b200.sim import HlynrSim
 from hlynr_intercept_b200.vec_env import HlynrVecEnv
 import sweep_configs
 n = 1000   # ragged: not a multiple of 32 or 128
-for name, variant, prec in (("cfg4", 1, "fp32"), ("cfg4", 2, "fp32"), ("cfg4", 3, "fp32"), ("cfg2", 1, "fp32"), ("cfg3", 1, "fp32"), ("cfg3", 1, "fp64")):
+for name, prec in (("cfg4", "fp32"), ("cfg2", "fp32"), ("cfg3", "fp32"), ("cfg3", "fp64"), ("cfg4", "fp64")):
     sim = HlynrSim(config.baseline_config(name), n_envs=n, precision=prec, warn_dead=False)
-    sim.set_option("step_kernel_variant", variant)
     sim.reset()
     sim.rollout(40, None)
     for k in range(6):
