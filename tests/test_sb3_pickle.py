@@ -13,6 +13,7 @@ from hlynr_intercept_b200 import sb3_pickle
 
 def test_round_trip_and_class_paths(tmp_path):
     rng = np.random.default_rng(0)
+    before = set(sys.modules)
     mean, var = rng.normal(size=104), rng.uniform(0.1, 2.0, 104)
     p = tmp_path / "vec_normalize.pkl"
     sb3_pickle.dump(p, mean=mean, var=var, count=12345.0, ret_mean=0.5, ret_var=2.0, ret_count=99.0, obs_shape=(104,), num_envs=16,
@@ -29,8 +30,8 @@ def test_round_trip_and_class_paths(tmp_path):
     for k in ("venv", "class_attributes", "returns"):   # VecNormalize.__getstate__ drops these
         assert k not in names
     if not sb3_pickle._have_real():
-        assert "stable_baselines3" not in sys.modules and "gymnasium" not in sys.modules   # the stubs are gone again
-        with pytest.raises(ModuleNotFoundError):
+        assert set(sys.modules) == before   # the stub modules are gone again
+        with pytest.raises((ModuleNotFoundError, AttributeError)):
             pickle.loads(p.read_bytes())   # the file really needs SB3's classes (or the stub tree) to load
 
 
