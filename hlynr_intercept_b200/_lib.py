@@ -105,7 +105,7 @@ def load(build_if_missing=True):
     L.hlynr_policy_destroy.argtypes = [vp]
     L.hlynr_policy_destroy.restype = None
     L.hlynr_policy_set_weights.argtypes = [vp, C.POINTER(abi.HlynrPolicyWeights), vp]
-    L.hlynr_policy_forward.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, u64, u64, i32, vp]
+    L.hlynr_policy_forward.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, u64, u64, i32, vp]
     L.hlynr_policy_launch_count.argtypes = [vp, C.POINTER(i64)]
     L.hlynr_policy_set_option.argtypes = [vp, C.c_char_p, i64]
     L.hlynr_policy_get_timing.argtypes = [vp, vp]

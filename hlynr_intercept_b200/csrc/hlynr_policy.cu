@@ -83,7 +83,7 @@ struct Params {
     int64_t n_rows;
     const int32_t* n_rows_dev;
     const float* vec;   // the per-column vectors, VEC_* offsets
-    float* actions; float* values; float* logp; float* mean;
+    float* actions; float* values; float* logp; float* mean; float* actions_clipped;
     float ln_eps;
     uint32_t k0, k1;        // Philox key (seed)
     uint32_t ctr_lo, ctr_hi; // call counter
@@ -471,7 +471,7 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_cons
 #pragma unroll
                     for (int k = 0; k < ACT; ++k) { mean[k] = __uint_as_float(v[k]) + vf[VEC_BH + k]; eps[k] = 0.f; }
                     const float value = __uint_as_float(v[ACT]) + vf[VEC_BH + ACT];
-                    if (!P.deterministic && (P.actions || P.logp)) {
+                    if (!P.deterministic && (P.actions || P.logp || P.actions_clipped)) {
                         const uint4 r0 = philox((uint32_t)grow, (uint32_t)((uint64_t)grow >> 32), P.ctr_lo, P.ctr_hi, P.k0, P.k1);
                         const uint4 r1 = philox((uint32_t)grow, (uint32_t)((uint64_t)grow >> 32) | 0x80000000u, P.ctr_lo, P.ctr_hi, P.k0, P.k1);
                         box_muller(r0.x, r0.y, &eps[0], &eps[1]);
@@ -483,7 +483,9 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_cons
                     for (int k = 0; k < ACT; ++k) {
                         const float ls = vf[VEC_LS + k];
                         lp += -0.5f * eps[k] * eps[k] - ls;
-                        if (P.actions) P.actions[grow * ACT + k] = fmaf(__expf(ls), eps[k], mean[k]);
+                        const float a = fmaf(__expf(ls), eps[k], mean[k]);
+                        if (P.actions) P.actions[grow * ACT + k] = a;
+                        if (P.actions_clipped) P.actions_clipped[grow * ACT + k] = fminf(fmaxf(a, -1.f), 1.f);   // np.clip to the action space
                         if (P.mean) P.mean[grow * ACT + k] = mean[k];
                     }
                     if (P.values) P.values[grow] = value;
@@ -637,8 +639,8 @@ int hlynr_policy_set_weights(hlynr_policy_t* p, const HlynrPolicyWeights* w, voi
 }
 
 int hlynr_policy_forward(hlynr_policy_t* p, const float* obs_dev, int64_t n_rows, const int32_t* n_rows_dev, float* actions_dev,
-                         float* values_dev, float* logp_dev, float* mean_dev, uint64_t seed, uint64_t counter, int deterministic,
-                         void* stream) {
+                         float* values_dev, float* logp_dev, float* mean_dev, float* actions_clipped_dev, uint64_t seed,
+                         uint64_t counter, int deterministic, void* stream) {
     if (!p || !obs_dev) return fail("hlynr_policy_forward: null argument");
     if (!p->ready) return fail("hlynr_policy_forward: hlynr_policy_set_weights has not been called");
     if (n_rows <= 0) return fail("hlynr_policy_forward: n_rows must be positive");
@@ -654,7 +656,7 @@ int hlynr_policy_forward(hlynr_policy_t* p, const float* obs_dev, int64_t n_rows
     memset(&P, 0, sizeof(P));
     P.obs = obs_dev; P.n_rows = n_rows; P.n_rows_dev = n_rows_dev;
     P.vec = p->vec;
-    P.actions = actions_dev; P.values = values_dev; P.logp = logp_dev; P.mean = mean_dev;
+    P.actions = actions_dev; P.values = values_dev; P.logp = logp_dev; P.mean = mean_dev; P.actions_clipped = actions_clipped_dev;
     P.ln_eps = p->ln_eps;
     P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.ctr_lo = (uint32_t)counter; P.ctr_hi = (uint32_t)(counter >> 32);
     P.deterministic = deterministic; P.error_flag = p->error_flag;

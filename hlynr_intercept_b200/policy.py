@@ -145,20 +145,30 @@ class FusedActorCritic:
             t = self._buf[name] = torch.empty(shape, dtype=torch.float32, device=self.device)
         return t
 
-    def forward(self, obs, deterministic=False, n_rows_dev=None, want=("actions", "values", "logp")):
+    def forward(self, obs, deterministic=False, n_rows_dev=None, want=("actions", "values", "logp"), out=None):
         """obs: float32 cuda tensor [n, 104] (contiguous).  Returns (actions [n,6], values [n], log_probs [n]); the tensors are
-        reused by the next call.  n_rows_dev: optional int32 cuda tensor [1] limiting the rows that are computed."""
+        reused by the next call.  n_rows_dev: optional int32 cuda tensor [1] limiting the rows that are computed.
+        out: optional dict of caller tensors the kernel writes into directly ('actions', 'values', 'logp', 'mean', and
+        'clipped' = the action clipped to [-1, 1]^6 as SB3 passes it to env.step), e.g. rows of a rollout buffer."""
         torch = _torch()
         if not (obs.is_cuda and obs.dtype == torch.float32 and obs.dim() == 2 and obs.shape[1] == 104 and obs.is_contiguous()):
             obs = obs.to(device=self.device, dtype=torch.float32).reshape(-1, 104).contiguous()
         n = obs.shape[0]
-        a = self._out("actions", (n, 6)) if "actions" in want else None
-        v = self._out("values", (n,)) if "values" in want else None
-        lp = self._out("logp", (n,)) if "logp" in want else None
-        m = self._out("mean", (n, 6)) if "mean" in want else None
+        out = out or {}
+
+        def buf(name, shape):
+            t = out.get(name)
+            if t is not None:
+                if not (t.is_cuda and t.dtype == torch.float32 and tuple(t.shape) == tuple(shape) and t.is_contiguous()):
+                    raise ValueError(f"out['{name}'] must be a contiguous cuda float32 tensor of shape {tuple(shape)}")
+                return t
+            return self._out(name, shape) if name in want else None
+
+        a, v, lp, m = buf("actions", (n, 6)), buf("values", (n,)), buf("logp", (n,)), buf("mean", (n, 6))
+        cl = buf("clipped", (n, 6))
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
         self.calls += 1
-        _lib.check(self.L.hlynr_policy_forward(self.h, ptr(obs), n, ptr(n_rows_dev), ptr(a), ptr(v), ptr(lp), ptr(m), self.seed,
+        _lib.check(self.L.hlynr_policy_forward(self.h, ptr(obs), n, ptr(n_rows_dev), ptr(a), ptr(v), ptr(lp), ptr(m), ptr(cl), self.seed,
                                                self.calls, int(bool(deterministic)), self._stream()))
         return (a, v, lp) if m is None else (a, v, lp, m)
 

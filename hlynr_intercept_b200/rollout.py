@@ -87,6 +87,7 @@ class DeviceRolloutCollector:
         # them.  A smaller bound is a speed knob for the value net; collect() then verifies that no timeout was left out.
         self.rows = min(n, int(bootstrap_rows)) if bootstrap_rows else n
         self._started = False
+        self._clipped = None
         self.L = pipe.L
         self._graph = None
 
@@ -112,12 +113,19 @@ class DeviceRolloutCollector:
         with torch.no_grad():
             for t in range(self.T):
                 o = self.obs[t]
-                a, v, lp = pol(cast(o))
-                self.actions[t].copy_(a)
-                self.values[t].copy_(v)
-                self.log_probs[t].copy_(lp)
+                if fused:   # the kernel writes the rollout-buffer rows and the clipped action itself: no copies, no clamp kernel
+                    if self._clipped is None:
+                        self._clipped = torch.empty((sim.n, 6), dtype=torch.float32, device=sim.device)
+                    pol.forward(o, out=dict(actions=self.actions[t], values=self.values[t], logp=self.log_probs[t], clipped=self._clipped))
+                    env_actions = self._clipped
+                else:
+                    a, v, lp = pol(cast(o))
+                    self.actions[t].copy_(a)
+                    self.values[t].copy_(v)
+                    self.log_probs[t].copy_(lp)
+                    env_actions = a.float().clamp(-1.0, 1.0)
                 self.episode_starts[t].copy_(self.last_dones)
-                _, rew, te, tr, (records, counter, terminal) = pipe.step(a.float().clamp(-1.0, 1.0), out=self.obs[t + 1], reward_out=self.rewards[t])
+                _, rew, te, tr, (records, counter, terminal) = pipe.step(env_actions, out=self.obs[t + 1], reward_out=self.rewards[t])
                 # TimeLimit bootstrap on the first `rows` finished episodes of the step (more only if nearly every env
                 # finishes in the same step; counted in self.overflow)
                 term_rows = terminal[: self.rows]

@@ -60,10 +60,12 @@ int hlynr_policy_set_weights(hlynr_policy_t* p, const HlynrPolicyWeights* w, voi
  *   values_dev   float[n_rows]    or NULL
  *   logp_dev     float[n_rows]    or NULL: log-probability of the sampled action under the diagonal Gaussian
  *   mean_dev     float[n_rows, 6] or NULL
+ *   actions_clipped_dev float[n_rows, 6] or NULL: the sampled action clipped to the action space [-1, 1]^6 -- what SB3's
+ *                collect_rollouts passes to env.step while the rollout buffer keeps the unclipped one
  *   seed, counter: eps comes from Philox4x32-10 keyed by seed with counter (row, counter): pass a new counter per call */
 int hlynr_policy_forward(hlynr_policy_t* p, const float* obs_dev, int64_t n_rows, const int32_t* n_rows_dev,
-                         float* actions_dev, float* values_dev, float* logp_dev, float* mean_dev, uint64_t seed,
-                         uint64_t counter, int deterministic, void* stream);
+                         float* actions_dev, float* values_dev, float* logp_dev, float* mean_dev, float* actions_clipped_dev,
+                         uint64_t seed, uint64_t counter, int deterministic, void* stream);
 
 /* Options.  "cluster": CTAs per thread-block cluster, 1, 2 (default) or 4: the CTAs of a cluster share every weight tile through
  * TMA multicast, which divides the L2 -> SM weight traffic (the kernel's bottleneck without it) by the cluster size. */

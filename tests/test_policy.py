@@ -76,6 +76,14 @@ def test_fused_forward_matches_torch(n, cluster):
     ad, _, _ = fused(obs, deterministic=True)
     torch.cuda.synchronize()
     assert torch.equal(ad, m)
+    # caller-provided outputs (rows of a rollout buffer) and the clipped action SB3 passes to env.step
+    big = torch.zeros(3, n, 6, device="cuda"); vals = torch.zeros(2, n, device="cuda"); clipped = torch.zeros(n, 6, device="cuda")
+    lp_out = torch.zeros(n, device="cuda")
+    a3, v3, lp3 = fused.forward(obs, out=dict(actions=big[1], values=vals[1], logp=lp_out, clipped=clipped))
+    torch.cuda.synchronize()
+    assert a3.data_ptr() == big[1].data_ptr() and (big[0] == 0).all() and (big[2] == 0).all() and (vals[0] == 0).all()
+    assert torch.equal(vals[1], v) and torch.equal(clipped, big[1].clamp(-1.0, 1.0)) and (clipped.abs() <= 1).all()
+    assert not torch.equal(clipped, big[1])   # the test's head gain makes some actions leave [-1, 1]
     fused.close()
 
 
