@@ -302,8 +302,8 @@ template <typename R> __global__ void init_kernel(StatePlanes<R> s, int64_t n_pa
     for (int k = 0; k < 6; ++k) s.r[k][i] = z;
     s.r[6][i] = Vec4<R>{R(0), R(0), R(0), R(288.15)};  // SEA_LEVEL_TEMPERATURE, physics_models.py:22
     s.f[0][i] = make_float4(1.f, 0.f, 0.f, 0.f);
-    s.f[1][i] = make_float4(0.f, 0.f, 0.f, 1000.f);
-    s.f[2][i] = make_float4(0.f, 0.f, 1000.f, 0.3f);
+    s.f[1][i] = make_float4(0.f, 0.f, 0.f, 0.3f);        // wind, base Cd
+    s.f[2][i] = make_float4(0.f, 0.f, 1000.f, 1000.f);   // Kalman P_pv, P_vp, P_vv, P_pp
     s.f[3][i] = make_float4(peak, 0.f, 0.f, 0.f);
     s.i0[i] = make_int4(0, 0, 0, -1);  // episode -1: the first reset starts episode 0
     (void)has_r6;
@@ -452,6 +452,14 @@ template <typename R, bool kRollout, int F> static void launch_inst(const Kernel
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(HLYNR_STEP_BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    {   // measurement aid (tools/occupancy_sweep.sh): HLYNR_OCC_PAD_BYTES of unused dynamic shared memory per CTA lower the
+        // resident CTAs per SM, which gives the sensitivity of the launch time to the number of resident warps
+        static const int pad = getenv("HLYNR_OCC_PAD_BYTES") ? atoi(getenv("HLYNR_OCC_PAD_BYTES")) : 0;
+        if (pad > 0) {
+            cudaFuncSetAttribute(step_kernel<R, kRollout, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+            cfg.dynamicSmemBytes = (size_t)pad;
+        }
+    }
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;

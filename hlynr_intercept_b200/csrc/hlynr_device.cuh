@@ -60,7 +60,18 @@ HD double dvd(double a, double b) { return __ddiv_rn(a, b); }
 #else
 HD double dvd(double a, double b) { return a * drcp(b); }
 #endif
+#if defined(HLYNR_F64_EXACT_DIV) || defined(HLYNR_F64_EXACT_SQRT)
 HD double sqr(double a) { return __dsqrt_rn(a); }
+#else
+HD double sqr(double a) {   // sqrt(a) = a * rsqrt(a): rsqrt.approx.ftz.f64 + two Newton steps (1-2 ulp), exact 0 for a == 0 and for denormals
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    return a > 2.3e-308 ? a * y : 0.0;
+}
+#endif
 
 // np.dot / np.linalg.norm on float32 vectors: float products, double accumulator, one final rounding
 // (OpenBLAS sdot as used by the reference's NumPy; see oracle/hlynr_oracle.c dotn).
@@ -260,7 +271,7 @@ template <typename R> struct KCurriculum {
 template <typename R> struct StatePlanes {
     Vec4<R>* r[7];   // r0 ipos+fuel, r1 ivel+fuel_used, r2 mpos+prev_d, r3 mvel+last_d, r4 kf_xp+min_d,
                      // r5 kf_xv+ep_return, r6 thrust+T0
-    float4* f[4];    // f0 quat, f1 wind+Ppp, f2 Ppv,Pvp,Pvv,base_cd, f3 peak (DR only)
+    float4* f[4];    // f0 quat, f1 wind+base_cd, f2 Ppv,Pvp,Pvv,Ppp, f3 peak (DR only)
     int4* i0;        // steps, worsen, flags (bit0 crossed, bit1 kf_init, bits 8.. onboard delay), episode
     Vec4<R>* vm;     // volley mode: [volley_k][2][stride]: {pos.xyz, min_distance}, {vel.xyz, active}
     Vec4<R>* gring;  // [gnd_ring_len][2][stride]: {rel.xyz, quality}, {vel.xyz, -}
@@ -331,40 +342,45 @@ template <typename R> struct Env {
 #define FLAG_VCUR(f) (((f) >> 12) & 0x7)
 #define FLAG_VCOUNT(f) (((f) >> 16) & 0xf)
 
-template <typename R, int F = FT_GENERIC> HD void load_env(const KernelArgs<R>& A, int64_t i, Env<R>& e) {
+// ROLE_ALL moves every plane.  The warp-pair split divides them by owner: the interceptor warp (ROLE_I) reads and writes r0, r1, r6,
+// f0, f1 and only reads the counters (i0: the Philox counter words) and, with domain randomization, the drag terms in f3; the missile
+// warp (ROLE_M) reads and writes r2-r5, f2, f3, i0 and only reads the wind / base Cd (f1) and, with DR, the temperature T0 (r6).
+template <typename R, int F = FT_GENERIC, int ROLE = 0> HD void load_env(const KernelArgs<R>& A, int64_t i, Env<R>& e) {
     typedef Feat<F> FT;
     const StatePlanes<R>& s = A.st;
+    constexpr bool kI = ROLE != 2, kM = ROLE != 1;
     Vec4<R> v;
-    v = s.r[0][i]; e.ipx = v.x; e.ipy = v.y; e.ipz = v.z; e.fuel = v.w;
-    v = s.r[1][i]; e.ivx = v.x; e.ivy = v.y; e.ivz = v.z; e.fuel_used = v.w;
-    v = s.r[2][i]; e.mpx = v.x; e.mpy = v.y; e.mpz = v.z; e.prev_d = v.w;
-    v = s.r[3][i]; e.mvx = v.x; e.mvy = v.y; e.mvz = v.z; e.last_d = v.w;
-    v = s.r[4][i]; e.kpx = v.x; e.kpy = v.y; e.kpz = v.z; e.min_d = v.w;
-    v = s.r[5][i]; e.kvx = v.x; e.kvy = v.y; e.kvz = v.z; e.ep_ret = v.w;
-    if (FT::thrust_dyn(A.P) || FT::dr(A.P)) { v = s.r[6][i]; e.thx = v.x; e.thy = v.y; e.thz = v.z; e.T0 = v.w; }
+    if (kI) { v = s.r[0][i]; e.ipx = v.x; e.ipy = v.y; e.ipz = v.z; e.fuel = v.w; }
+    if (kI) { v = s.r[1][i]; e.ivx = v.x; e.ivy = v.y; e.ivz = v.z; e.fuel_used = v.w; }
+    if (kM) { v = s.r[2][i]; e.mpx = v.x; e.mpy = v.y; e.mpz = v.z; e.prev_d = v.w; }
+    if (kM) { v = s.r[3][i]; e.mvx = v.x; e.mvy = v.y; e.mvz = v.z; e.last_d = v.w; }
+    if (kM) { v = s.r[4][i]; e.kpx = v.x; e.kpy = v.y; e.kpz = v.z; e.min_d = v.w; }
+    if (kM) { v = s.r[5][i]; e.kvx = v.x; e.kvy = v.y; e.kvz = v.z; e.ep_ret = v.w; }
+    if ((kI && (FT::thrust_dyn(A.P) || FT::dr(A.P))) || (ROLE == 2 && FT::dr(A.P))) { v = s.r[6][i]; e.thx = v.x; e.thy = v.y; e.thz = v.z; e.T0 = v.w; }
     else { e.thx = e.thy = e.thz = R(0); e.T0 = R(288.15); }
     float4 f;
-    f = s.f[0][i]; e.qw = f.x; e.qx = f.y; e.qy = f.z; e.qz = f.w;
-    f = s.f[1][i]; e.wx = f.x; e.wy = f.y; e.wz = f.z; e.Ppp = f.w;
-    f = s.f[2][i]; e.Ppv = f.x; e.Pvp = f.y; e.Pvv = f.z; e.base_cd = f.w;
+    if (kI) { f = s.f[0][i]; e.qw = f.x; e.qx = f.y; e.qy = f.z; e.qz = f.w; }
+    f = s.f[1][i]; e.wx = f.x; e.wy = f.y; e.wz = f.z; e.base_cd = f.w;
+    if (kM) { f = s.f[2][i]; e.Ppv = f.x; e.Pvp = f.y; e.Pvv = f.z; e.Ppp = f.w; }
     if (FT::dr(A.P)) { f = s.f[3][i]; e.peak = f.x; } else e.peak = 0.f;
     int4 q = s.i0[i]; e.steps = q.x; e.worsen = q.y; e.flags = q.z; e.episode = q.w;
 }
-template <typename R, int F = FT_GENERIC> HD void store_env(const KernelArgs<R>& A, int64_t i, const Env<R>& e) {
+template <typename R, int F = FT_GENERIC, int ROLE = 0> HD void store_env(const KernelArgs<R>& A, int64_t i, const Env<R>& e) {
     typedef Feat<F> FT;
     const StatePlanes<R>& s = A.st;
-    s.r[0][i] = Vec4<R>{e.ipx, e.ipy, e.ipz, e.fuel};
-    s.r[1][i] = Vec4<R>{e.ivx, e.ivy, e.ivz, e.fuel_used};
-    s.r[2][i] = Vec4<R>{e.mpx, e.mpy, e.mpz, e.prev_d};
-    s.r[3][i] = Vec4<R>{e.mvx, e.mvy, e.mvz, e.last_d};
-    s.r[4][i] = Vec4<R>{e.kpx, e.kpy, e.kpz, e.min_d};
-    s.r[5][i] = Vec4<R>{e.kvx, e.kvy, e.kvz, e.ep_ret};
-    if (FT::thrust_dyn(A.P) || FT::dr(A.P)) s.r[6][i] = Vec4<R>{e.thx, e.thy, e.thz, e.T0};
-    s.f[0][i] = make_float4(e.qw, e.qx, e.qy, e.qz);
-    s.f[1][i] = make_float4(e.wx, e.wy, e.wz, e.Ppp);
-    s.f[2][i] = make_float4(e.Ppv, e.Pvp, e.Pvv, e.base_cd);
-    if (FT::dr(A.P)) s.f[3][i] = make_float4(e.peak, 0.f, 0.f, 0.f);
-    s.i0[i] = make_int4(e.steps, e.worsen, e.flags, e.episode);
+    constexpr bool kI = ROLE != 2, kM = ROLE != 1;
+    if (kI) s.r[0][i] = Vec4<R>{e.ipx, e.ipy, e.ipz, e.fuel};
+    if (kI) s.r[1][i] = Vec4<R>{e.ivx, e.ivy, e.ivz, e.fuel_used};
+    if (kM) s.r[2][i] = Vec4<R>{e.mpx, e.mpy, e.mpz, e.prev_d};
+    if (kM) s.r[3][i] = Vec4<R>{e.mvx, e.mvy, e.mvz, e.last_d};
+    if (kM) s.r[4][i] = Vec4<R>{e.kpx, e.kpy, e.kpz, e.min_d};
+    if (kM) s.r[5][i] = Vec4<R>{e.kvx, e.kvy, e.kvz, e.ep_ret};
+    if (kI && (FT::thrust_dyn(A.P) || FT::dr(A.P))) s.r[6][i] = Vec4<R>{e.thx, e.thy, e.thz, e.T0};
+    if (kI) s.f[0][i] = make_float4(e.qw, e.qx, e.qy, e.qz);
+    if (kI) s.f[1][i] = make_float4(e.wx, e.wy, e.wz, e.base_cd);
+    if (kM) s.f[2][i] = make_float4(e.Ppv, e.Pvp, e.Pvv, e.Ppp);
+    if (kM && FT::dr(A.P)) s.f[3][i] = make_float4(e.peak, 0.f, 0.f, 0.f);
+    if (kM) s.i0[i] = make_int4(e.steps, e.worsen, e.flags, e.episode);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -566,10 +582,57 @@ __device__ __noinline__ TrackF32 track_obs_f32_phase(const KParams<R>& P, int mo
     return lb;
 }
 
-template <typename R, int F>
-HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint4 ur, int64_t i, int g_row, int o_row, ObsOut& out) {
+// Warp-pair split (step_kernel_split below): the interceptor warp (ROLE_I) owns the interceptor / wind state and the channels that
+// only depend on it, the missile warp (ROLE_M) owns everything else and receives the interceptor's new state, its forward vector
+// and the datalink quality through shared memory.  ROLE_ALL is the one-thread-per-env code every other kernel runs.  The pieces the
+// roles share are the helper functions below, so all three evaluate the same operations in the same order.
+enum { ROLE_ALL = 0, ROLE_I = 1, ROLE_M = 2 };
+struct ObsShared { float fx, fy, fz, link; };   // ROLE_I -> ROLE_M
+
+// forward vector, core.py:1143-1152
+HD void forward_vec(float w, float x, float y, float z, float* fx, float* fy, float* fz) {
+    float a = 2.f * fmaf(x, z, w * y), b = 2.f * fmaf(y, z, -(w * x)), c = 1.f - 2.f * fmaf(x, x, y * y);
+    float inv = nrcp(nnorm3(a, b, c) + 1e-6f);
+    *fx = a * inv; *fy = b * inv; *fz = c * inv;
+}
+// datalink quality, core.py:440-474 (urw = the tick's packet-loss draw)
+template <typename R>
+HD float datalink_quality(const KParams<R>& P, float ipx, float ipy, float ipz, float ivx, float ivy, float ivz, uint32_t urw) {
+    float link = 0.f;
+    float lr = nnorm3(ipx - P.gpos[0], ipy - P.gpos[1], ipz - P.gpos[2]);
+    if (!(lr > P.max_link)) {
+        float r1 = lr * P.rc_max_link;
+        float dop = 1.f - fminf(nnorm3(ivx, ivy, ivz) * 1e-3f, 0.3f);
+        if (u01(urw) < P.pkt_loss) link = 0.f;
+        else link = clip((1.f - r1 * r1) * dop * 0.95f, 0.f, 1.f);
+    }
+    return link;
+}
+// world_frame channels 6-11: own velocity (core.py:963-965) and quaternion_to_euler / pi (core.py:1103-1121, float32)
+template <typename R>
+HD void put_own_motion_world(const KParams<R>& P, const Env<R>& e, float ivx, float ivy, float ivz, const ObsOut& out) {
+    out.put(6, clip(ivx * P.rc_max_velocity_f, -1.f, 1.f));
+    out.put(7, clip(ivy * P.rc_max_velocity_f, -1.f, 1.f));
+    out.put(8, clip(ivz * P.rc_max_velocity_f, -1.f, 1.f));
+    if (out.emit) {
+        const float w = e.qw, x = e.qx, y = e.qy, z = e.qz;
+        const float sinr = 2.f * fmaf(w, x, y * z), cosr = 1.f - 2.f * fmaf(x, x, y * y);
+        const float sinp = 2.f * fmaf(w, y, -(z * x));
+        const float siny = 2.f * fmaf(w, z, x * y), cosy = 1.f - 2.f * fmaf(y, y, z * z);
+        const float ipi = 0.318309886183790672f;
+        out.put(9, fast_atan2(sinr, cosr) * ipi);
+        out.put(10, fast_asin(clip(sinp, -1.f, 1.f)) * ipi);
+        out.put(11, fast_atan2(siny, cosy) * ipi);
+    }
+}
+
+template <typename R, int F, int ROLE = ROLE_ALL>
+HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint4 ur, int64_t i, int g_row, int o_row, ObsOut& out,
+                const ObsShared sh = ObsShared{0.f, 0.f, 0.f, 0.f}) {
     typedef R W;
     typedef Feat<F> FT;
+    static_assert(ROLE != ROLE_I, "the interceptor warp runs observe_own()");
+    static_assert(ROLE == ROLE_ALL || F >= 0, "the warp-pair split exists for the specialised world_frame feature sets only");
     const KParams<R>& P = A.P;
     const KCurriculum<R>& C = A.C;
     const int64_t n = A.ring_stride;
@@ -581,14 +644,9 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
     // === onboard radar, core.py:531-593 ===
     const float rx = sub(mpx, ipx), ry = sub(mpy, ipy), rz = sub(mpz, ipz);
     const float range = nnorm3(rx, ry, rz);
-    // forward vector, core.py:1143-1152
     float fx, fy, fz;
-    {
-        const float w = e.qw, x = e.qx, y = e.qy, z = e.qz;
-        float a = 2.f * fmaf(x, z, w * y), b = 2.f * fmaf(y, z, -(w * x)), c = 1.f - 2.f * fmaf(x, x, y * y);
-        float inv = nrcp(nnorm3(a, b, c) + 1e-6f);
-        fx = a * inv; fy = b * inv; fz = c * inv;
-    }
+    if constexpr (ROLE == ROLE_M) { fx = sh.fx; fy = sh.fy; fz = sh.fz; }
+    else forward_vec(e.qw, e.qx, e.qy, e.qz, &fx, &fy, &fz);
     bool onb = !(range > P.radar_range);
     if (onb) {
         float cb = ndot3(fx, fy, fz, rx, ry, rz) * nrcp(range + 1e-6f);
@@ -661,15 +719,8 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
 
     // === datalink, core.py:440-474 ===
     float link = 0.f;
-    if (FT::ground(P)) {
-        float lr = nnorm3(ipx - P.gpos[0], ipy - P.gpos[1], ipz - P.gpos[2]);
-        if (!(lr > P.max_link)) {
-            float r1 = lr * P.rc_max_link;
-            float dop = 1.f - fminf(nnorm3(ivx, ivy, ivz) * 1e-3f, 0.3f);
-            if (u01(ur.w) < P.pkt_loss) link = 0.f;
-            else link = clip((1.f - r1 * r1) * dop * 0.95f, 0.f, 1.f);
-        }
-    }
+    if constexpr (ROLE == ROLE_M) link = sh.link;
+    else if (FT::ground(P)) link = datalink_quality(P, ipx, ipy, ipz, ivx, ivy, ivz, ur.w);
 
     // === fusion confidence, core.py:476-509 ===
     float fus;
@@ -873,23 +924,11 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
         out.put(6, clip(ndot3(ivx, ivy, ivz, fx, fy, fz) * P.rc_max_velocity_f, -1.f, 1.f));
         out.put(7, clip(ndot3(ivx, ivy, ivz, bx.rx, bx.ry, bx.rz) * P.rc_max_velocity_f, -1.f, 1.f));
         out.put(8, clip(ndot3(ivx, ivy, ivz, bx.ux, bx.uy, bx.uz) * P.rc_max_velocity_f, -1.f, 1.f));
-    } else {
-    out.put(6, clip(ivx * P.rc_max_velocity_f, -1.f, 1.f));
-    out.put(7, clip(ivy * P.rc_max_velocity_f, -1.f, 1.f));
-    out.put(8, clip(ivz * P.rc_max_velocity_f, -1.f, 1.f));
+    } else if (ROLE != ROLE_M) {
+        put_own_motion_world(P, e, ivx, ivy, ivz, out);
     }
     if (mode != HLYNR_OBS_WORLD) { out.put(9, 0.f); out.put(10, 0.f); out.put(11, 0.f); }  // core.py:966-970
-    else if (out.emit) {  // quaternion_to_euler, core.py:1103-1121 (float32), divided by pi
-        const float w = e.qw, x = e.qx, y = e.qy, z = e.qz;
-        const float sinr = 2.f * fmaf(w, x, y * z), cosr = 1.f - 2.f * fmaf(x, x, y * y);
-        const float sinp = 2.f * fmaf(w, y, -(z * x));
-        const float siny = 2.f * fmaf(w, z, x * y), cosy = 1.f - 2.f * fmaf(y, y, z * z);
-        const float ipi = 0.318309886183790672f;
-        out.put(9, fast_atan2(sinr, cosr) * ipi);
-        out.put(10, fast_asin(clip(sinp, -1.f, 1.f)) * ipi);
-        out.put(11, fast_atan2(siny, cosy) * ipi);
-    }
-    out.put(12, clip((float)e.fuel * 0.01f, 0.f, 1.f));
+    if (ROLE != ROLE_M) out.put(12, clip((float)e.fuel * 0.01f, 0.f, 1.f));
     if (dg_det && link > 0.1f && mode == HLYNR_OBS_LOS) {  // core.py:985-1006: redundant range / rate measurements
         const W gr = nnorm3(dgx, dgy, dgz);
         const W gc = -ndot3(dgx, dgy, dgz, dvx, dvy, dvz) * nrcp(gr + W(1e-6));
@@ -923,8 +962,25 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
         for (int k = 17; k < 23; ++k) out.put(k, -2.f);
         out.put(23, 0.f);
     }
-    out.put(24, link);
+    if (ROLE != ROLE_M) out.put(24, link);
     out.put(25, fus);
+}
+
+// ROLE_I's share of the observation: forward vector and datalink quality (handed to the missile warp), channels 6-12 and 24
+template <typename R, int F>
+HD ObsShared observe_own(const KernelArgs<R>& A, const Env<R>& e, const uint4 ur, const ObsOut& out) {
+    typedef Feat<F> FT;
+    const KParams<R>& P = A.P;
+    const float ipx = (float)e.ipx, ipy = (float)e.ipy, ipz = (float)e.ipz;
+    const float ivx = (float)e.ivx, ivy = (float)e.ivy, ivz = (float)e.ivz;
+    ObsShared sh;
+    forward_vec(e.qw, e.qx, e.qy, e.qz, &sh.fx, &sh.fy, &sh.fz);
+    sh.link = 0.f;
+    if (FT::ground(P)) sh.link = datalink_quality(P, ipx, ipy, ipz, ivx, ivy, ivz, ur.w);
+    put_own_motion_world(P, e, ivx, ivy, ivz, out);
+    out.put(12, clip((float)e.fuel * 0.01f, 0.f, 1.f));
+    out.put(24, sh.link);
+    return sh;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1226,13 +1282,12 @@ HD VolleyOut volley_step(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, u
     return o;
 }
 
+// The tick in four sections (the order of environment.py:605-859): interceptor, missile(s), wind, outcome.  tick_physics() runs
+// them for one env per thread; step_kernel_split runs the first and third on the interceptor warp, the others on the missile warp.
 template <typename R, int F>
-HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const float act[6], int64_t ring_i, TickOut& t) {
+HD void tick_interceptor(const KernelArgs<R>& A, Env<R>& e, const float act[6], bool* clamped_out) {
     typedef Feat<F> FT;
     const KParams<R>& P = A.P;
-    e.steps += 1;
-    const uint32_t ep = (uint32_t)e.episode, st = (uint32_t)e.steps;
-    t.ur = draw_raw(key, ep, st, HLYNR_BLK_UNI);
     R a0 = (R)act[0], a1 = (R)act[1], a2 = (R)act[2], a3 = (R)act[3], a4 = (R)act[4], a5 = (R)act[5];
     if (FT::obs_mode(P) == HLYNR_OBS_LOS) {
         // _update_los_frame + _transform_los_action_to_world (environment.py:965-1061): the basis is built in float32
@@ -1260,7 +1315,7 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
         const Vec4<R> c = clamp_norm_slow<R>(a3, a4, a5, R(5.0));
         a3 = c.x; a4 = c.y; a5 = c.z; clamped = clamped || c.w != R(0);
     }
-    t.clamped = clamped;
+    *clamped_out = clamped;
     const R dt = P.dt;
     // ---- _update_interceptor (environment.py:861-963) ----
     {
@@ -1297,14 +1352,13 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
         e.ipx = add(e.ipx, mul(e.ivx, dt)); e.ipy = add(e.ipy, mul(e.ivy, dt)); e.ipz = add(e.ipz, mul(e.ivz, dt));
         quat_step(e, mul(a3, R(20.0)), mul(a4, R(20.0)), mul(a5, R(20.0)), dt);
     }
-    // ---- missiles (environment.py:631-638), advanced with the wind of THIS tick (before _update_wind); a volley's
-    // missiles, their priority selection and intercept checks are one pass over the missile planes ----
-    R dist = R(0);
-    VolleyOut vo{false, false, false};
-    const R radius = FT::fuze(P) ? P.kill_radius : A.C.intercept_radius;
-    if (FT::volley(P)) vo = volley_step<R, F>(A, e, key, ep, st, ring_i, radius, &dist);
-    else missile_update<R, F>(P, e, key, ep, st, HLYNR_BLK_EVADE, e.mpx, e.mpy, e.mpz, e.mvx, e.mvy, e.mvz);
-    // ---- _update_wind (environment.py:1119-1129): the wind used by the NEXT tick ----
+}
+
+// ---- _update_wind (environment.py:1119-1129): the wind used by the NEXT tick; ur = the tick's BLK_UNI block ----
+template <typename R, int F>
+HD void tick_wind(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, uint32_t ep, uint32_t st, const uint4 ur) {
+    typedef Feat<F> FT;
+    const KParams<R>& P = A.P;
     if (FT::enh_wind(P)) {  // EnhancedWindModel.get_wind_vector, physics_models.py:351-387
         R alt = e.ipz > R(0) ? e.ipz : R(0);
         R pf, ti;
@@ -1318,7 +1372,7 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
             draw_normal3(key, ep, st, HLYNR_BLK_WIND, &z0, &z1, &z2);
             wvx += scale * (R)z0; wvy += scale * (R)z1; wvz += scale * (R)z2;
         }
-        if (u01(t.ur.x) < 0.001f) {  // gust, :381-385 (0.1 % of ticks)
+        if (u01(ur.x) < 0.001f) {  // gust, :381-385 (0.1 % of ticks)
             const Tri<R> g = wind_gust<R>(A, key.c0, key.c3hi, ep, st, wvx, wvy, wvz);
             wvx = g.x; wvy = g.y; wvz = g.z;
         }
@@ -1330,7 +1384,16 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
         e.wy = (float)(R(0.95) * (R)e.wy + R(0.05) * (P.base_wind[1] + (R)z1 * P.wind_var));
         e.wz = (float)(R(0.95) * (R)e.wz + R(0.05) * (P.base_wind[2] + (R)z2 * P.wind_var));
     }
-    // ---- distance / intercept / termination (environment.py:657-814) ----
+}
+
+// ---- distance / intercept / termination (environment.py:657-814) and _calculate_reward (:1131-1320).  Reads the interceptor's
+// position, velocity and fuel AFTER its update; `dist` / `vo` come from volley_step() in volley mode ----
+template <typename R, int F>
+HD void tick_outcome(const KernelArgs<R>& A, Env<R>& e, const float act0, R dist, const VolleyOut vo, TickOut& t) {
+    typedef Feat<F> FT;
+    const KParams<R>& P = A.P;
+    const R dt = P.dt;
+    const R radius = FT::fuze(P) ? P.kill_radius : A.C.intercept_radius;
     bool intercepted, term = false, hit = false;
     if (FT::volley(P)) {
         intercepted = vo.intercepted; hit = vo.hit;
@@ -1399,7 +1462,7 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
                             dvd(sub(e.mpy, e.ipy), dist), dvd(sub(e.mpz, e.ipz), dist));
                 r = add(r, mul(al, R(0.3)));
             }
-            if (FT::obs_mode(P) == HLYNR_OBS_LOS) r = add(r, mul((R)act[0], R(0.4)));  // forward-thrust shaping, :1252-1264
+            if (FT::obs_mode(P) == HLYNR_OBS_LOS) r = add(r, mul((R)act0, R(0.4)));  // forward-thrust shaping, :1252-1264
             r = sub(r, R(0.2));
             e.prev_d = dist;
         }
@@ -1420,6 +1483,25 @@ HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const
     }
     e.ep_ret = e.ep_ret + r;
     t.reward = (float)r;
+}
+
+template <typename R, int F>
+HD void tick_physics(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const float act[6], int64_t ring_i, TickOut& t) {
+    typedef Feat<F> FT;
+    const KParams<R>& P = A.P;
+    e.steps += 1;
+    const uint32_t ep = (uint32_t)e.episode, st = (uint32_t)e.steps;
+    t.ur = draw_raw(key, ep, st, HLYNR_BLK_UNI);
+    tick_interceptor<R, F>(A, e, act, &t.clamped);
+    // ---- missiles (environment.py:631-638), advanced with the wind of THIS tick (before _update_wind); a volley's
+    // missiles, their priority selection and intercept checks are one pass over the missile planes ----
+    R dist = R(0);
+    VolleyOut vo{false, false, false};
+    const R radius = FT::fuze(P) ? P.kill_radius : A.C.intercept_radius;
+    if (FT::volley(P)) vo = volley_step<R, F>(A, e, key, ep, st, ring_i, radius, &dist);
+    else missile_update<R, F>(P, e, key, ep, st, HLYNR_BLK_EVADE, e.mpx, e.mpy, e.mpz, e.mvx, e.mvy, e.mvz);
+    tick_wind<R, F>(A, e, key, ep, st, t.ur);
+    tick_outcome<R, F>(A, e, act[0], dist, vo, t);
 }
 
 // ------------------------------------------------------------------------------------------------
