@@ -211,6 +211,8 @@ struct hlynr_sim {
     HostIO hio;
     int host_info = 1, host_chunks = 0, host_threads = 0;
     int host_chunk_growth = 12;   // geometric chunk schedule of the host path, x1.5 per chunk (measured best on B200: 2.43 -> 2.35 ms at 2^20 envs, 26-D)
+    int split = 0;   // option "split": API-mode ticks of the specialised configurations run on specialised warps (step_kernel_ws)
+    int ws_ctas_per_sm = 0;   // option "ws_ctas_per_sm": persistent CTAs per SM of step_kernel_ws (0 = what its launch bounds allow)
     int pdl = 1;   // step kernels are launched with programmatic stream serialization (option "pdl"; -1.5 us per launch on B200)
     int obs_dim = HLYNR_OBS_DIM;  // row pitch of every observation array of the API: 26, or 17 (option "obs_dim")
     int prefetch_waves = 1;  // CTAs per SM the step kernel looks ahead when it prefetches upcoming planes into L2 (0 = off)
@@ -466,12 +468,54 @@ template <typename R, bool kRollout, int F> static void launch_inst(const Kernel
     cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
     cudaLaunchKernelEx(&cfg, step_kernel<R, kRollout, F>, A);
 }
+// The warp-specialised persistent step kernel (step_kernel_ws) of a specialised instantiation: one CTA of 1 interceptor + NM missile
+// warps per resident slot, walking over the 32-env tiles of the range.
+template <typename R, int F> static void launch_ws(const hlynr_sim* s, const KernelArgs<R>& A, cudaStream_t st, bool pdl) {
+    const int64_t ntiles = (A.lim - A.first + 31) / 32;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(HLYNR_WS_BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
+    {   // the CTAs are persistent: all of them must be resident, so the shared-memory carve-out has to hold grid / SMs of them
+        static thread_local int carved[16] = {0};   // resident CTAs per SM, per device (the attribute belongs to the device's copy of the function)
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 16) dev = 0;
+        if (!carved[dev]) {
+            cudaFuncAttributes fa;
+            cudaFuncGetAttributes(&fa, step_kernel_ws<R, F>);
+            const size_t need = (size_t)WsOcc<R>::ctas * (fa.sharedSizeBytes + 1024);
+            int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024)) + 3;
+            cudaFuncSetAttribute(step_kernel_ws<R, F>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+            int occ = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_ws<R, F>, HLYNR_WS_BLOCK, 0);
+            carved[dev] = occ > 0 ? occ : 1;
+        }
+        int per_sm = s->ws_ctas_per_sm > 0 ? s->ws_ctas_per_sm : WsOcc<R>::ctas;
+        if (per_sm > carved[dev]) per_sm = carved[dev];
+        int64_t grid = (int64_t)s->sm_count * per_sm;
+        if (grid > ntiles) grid = ntiles;
+        cfg.gridDim = dim3((unsigned)grid);
+    }
+    cudaLaunchKernelEx(&cfg, step_kernel_ws<R, F>, A);
+}
 // Both builds dispatch to the feature-specialised instantiation of the three BASELINE configurations when it matches.
 template <typename R, bool kRollout> static void launch_step(const hlynr_sim* s, const KernelArgs<R>& A, cudaStream_t st, bool specialise) {
     const int grid = grid_for(A.lim - A.first, HLYNR_STEP_BLOCK);
     const bool pdl = s->pdl != 0;
     int f = feature_set(s->params);
     if (!specialise && f >= 0) f = FT_GENERIC;
+    if constexpr (!kRollout) {
+        if (s->split && f >= 0) {   // option "split": API-mode ticks of a specialised configuration on specialised warps
+            if (f == FT_V2ON) launch_ws<R, FT_V2ON>(s, A, st, pdl);
+            else if (f == FT_V2OFF) launch_ws<R, FT_V2OFF>(s, A, st, pdl);
+            else launch_ws<R, FT_V2ON_DR>(s, A, st, pdl);
+            return;
+        }
+    }
     if (f == FT_V2ON) launch_inst<R, kRollout, FT_V2ON>(A, grid, st, pdl);
     else if (f == FT_V2OFF) launch_inst<R, kRollout, FT_V2OFF>(A, grid, st, pdl);
     else if (f == FT_V2ON_DR) launch_inst<R, kRollout, FT_V2ON_DR>(A, grid, st, pdl);
@@ -588,15 +632,10 @@ int hlynr_set_option(hlynr_t* s, const char* name, int64_t value) {
         return 0;
     }
     if (strcmp(name, "pdl") == 0) { s->pdl = value != 0; return 0; }
-    if (strcmp(name, "host_chunk_growth") == 0) {
-        if (value < 0 || value > 64) return fail("host_chunk_growth must be in [0, 64] (eighths: 16 = chunks double, 0 = uniform chunks)");
-        s->host_chunk_growth = (int)value;
-        return 0;
-    }
-    if (strcmp(name, "host_threads") == 0) {
-        if (value < 0 || value > 64) return fail("host_threads must be in [0, 64]");
-        s->host_threads = (int)value;
-        return s->hio.ready ? make_pool(s) : 0;
+    if (strcmp(name, "split") == 0) { s->split = value != 0; return 0; }
+    if (strcmp(name, "ws_ctas_per_sm") == 0) {
+        if (value < 0 || value > 32) return fail("hlynr_set_option: ws_ctas_per_sm must be in [0, 32]");
+        s->ws_ctas_per_sm = (int)value; return 0;
     }
     return fail("hlynr_set_option: unknown option '%s'", name);
 }

@@ -582,12 +582,12 @@ __device__ __noinline__ TrackF32 track_obs_f32_phase(const KParams<R>& P, int mo
     return lb;
 }
 
-// Warp-pair split (step_kernel_split below): the interceptor warp (ROLE_I) owns the interceptor / wind state and the channels that
-// only depend on it, the missile warp (ROLE_M) owns everything else and receives the interceptor's new state, its forward vector
-// and the datalink quality through shared memory.  ROLE_ALL is the one-thread-per-env code every other kernel runs.  The pieces the
-// roles share are the helper functions below, so all three evaluate the same operations in the same order.
+// Warp-specialised step kernel (step_kernel_ws below): interceptor warps (ROLE_I) own the interceptor / wind state, missile warps
+// (ROLE_M) own everything else and receive the interceptor's new state, its forward vector, euler angles and the datalink quality
+// through shared memory.  ROLE_ALL is the one-thread-per-env code every other kernel runs.  The pieces the roles share are the helper
+// functions below, so all of them evaluate the same operations in the same order.
 enum { ROLE_ALL = 0, ROLE_I = 1, ROLE_M = 2 };
-struct ObsShared { float fx, fy, fz, link; };   // ROLE_I -> ROLE_M
+struct ObsShared { float fx, fy, fz, link, roll, pitch, yaw; };   // ROLE_I -> ROLE_M
 
 // forward vector, core.py:1143-1152
 HD void forward_vec(float w, float x, float y, float z, float* fx, float* fy, float* fz) {
@@ -608,30 +608,34 @@ HD float datalink_quality(const KParams<R>& P, float ipx, float ipy, float ipz, 
     }
     return link;
 }
-// world_frame channels 6-11: own velocity (core.py:963-965) and quaternion_to_euler / pi (core.py:1103-1121, float32)
-template <typename R>
-HD void put_own_motion_world(const KParams<R>& P, const Env<R>& e, float ivx, float ivy, float ivz, const ObsOut& out) {
-    out.put(6, clip(ivx * P.rc_max_velocity_f, -1.f, 1.f));
-    out.put(7, clip(ivy * P.rc_max_velocity_f, -1.f, 1.f));
-    out.put(8, clip(ivz * P.rc_max_velocity_f, -1.f, 1.f));
-    if (out.emit) {
-        const float w = e.qw, x = e.qx, y = e.qy, z = e.qz;
-        const float sinr = 2.f * fmaf(w, x, y * z), cosr = 1.f - 2.f * fmaf(x, x, y * y);
-        const float sinp = 2.f * fmaf(w, y, -(z * x));
-        const float siny = 2.f * fmaf(w, z, x * y), cosy = 1.f - 2.f * fmaf(y, y, z * z);
-        const float ipi = 0.318309886183790672f;
-        out.put(9, fast_atan2(sinr, cosr) * ipi);
-        out.put(10, fast_asin(clip(sinp, -1.f, 1.f)) * ipi);
-        out.put(11, fast_atan2(siny, cosy) * ipi);
-    }
+// quaternion_to_euler / pi, core.py:1103-1121 (float32): observation channels 9-11 of the world frame
+HD void euler_over_pi(float w, float x, float y, float z, float* roll, float* pitch, float* yaw) {
+    const float sinr = 2.f * fmaf(w, x, y * z), cosr = 1.f - 2.f * fmaf(x, x, y * y);
+    const float sinp = 2.f * fmaf(w, y, -(z * x));
+    const float siny = 2.f * fmaf(w, z, x * y), cosy = 1.f - 2.f * fmaf(y, y, z * z);
+    const float ipi = 0.318309886183790672f;
+    *roll = fast_atan2(sinr, cosr) * ipi;
+    *pitch = fast_asin(clip(sinp, -1.f, 1.f)) * ipi;
+    *yaw = fast_atan2(siny, cosy) * ipi;
+}
+// what ROLE_I computes of the observation: forward vector, datalink quality, euler angles
+template <typename R, int F>
+HD ObsShared own_obs(const KernelArgs<R>& A, const Env<R>& e, const uint32_t urw) {
+    ObsShared sh;
+    forward_vec(e.qw, e.qx, e.qy, e.qz, &sh.fx, &sh.fy, &sh.fz);
+    sh.link = 0.f;
+    if (Feat<F>::ground(A.P))
+        sh.link = datalink_quality(A.P, (float)e.ipx, (float)e.ipy, (float)e.ipz, (float)e.ivx, (float)e.ivy, (float)e.ivz, urw);
+    euler_over_pi(e.qw, e.qx, e.qy, e.qz, &sh.roll, &sh.pitch, &sh.yaw);
+    return sh;
 }
 
 template <typename R, int F, int ROLE = ROLE_ALL>
 HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint4 ur, int64_t i, int g_row, int o_row, ObsOut& out,
-                const ObsShared sh = ObsShared{0.f, 0.f, 0.f, 0.f}) {
+                const ObsShared sh = ObsShared{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}) {
     typedef R W;
     typedef Feat<F> FT;
-    static_assert(ROLE != ROLE_I, "the interceptor warp runs observe_own()");
+    static_assert(ROLE != ROLE_I, "the interceptor warps run own_obs()");
     static_assert(ROLE == ROLE_ALL || F >= 0, "the warp-pair split exists for the specialised world_frame feature sets only");
     const KParams<R>& P = A.P;
     const KCurriculum<R>& C = A.C;
@@ -904,7 +908,7 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
         out.put(5, (float)clip(vz * P.rc_max_velocity_w, W(-1), W(1)));
         }
         out.put(13, cl > W(0) ? (float)clip(W(1) - rr * nrcp(cl) * W(0.01), W(-1), W(1)) : -1.f);
-        float tq = clip(1.f - (e.Ppp * 3.f) * 1e-4f, 0.f, 1.f);
+        float tq = clip(fmaf(e.Ppp * 3.f, -1e-4f, 1.f), 0.f, 1.f);   // explicit fma: the contraction must not depend on the surrounding code
         if (o_det) tq *= P.radar_quality;
         out.put(14, tq);
         out.put(15, (float)clip(cl * P.rc_max_velocity_w, W(-1), W(1)));
@@ -924,11 +928,19 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
         out.put(6, clip(ndot3(ivx, ivy, ivz, fx, fy, fz) * P.rc_max_velocity_f, -1.f, 1.f));
         out.put(7, clip(ndot3(ivx, ivy, ivz, bx.rx, bx.ry, bx.rz) * P.rc_max_velocity_f, -1.f, 1.f));
         out.put(8, clip(ndot3(ivx, ivy, ivz, bx.ux, bx.uy, bx.uz) * P.rc_max_velocity_f, -1.f, 1.f));
-    } else if (ROLE != ROLE_M) {
-        put_own_motion_world(P, e, ivx, ivy, ivz, out);
+    } else {
+    out.put(6, clip(ivx * P.rc_max_velocity_f, -1.f, 1.f));
+    out.put(7, clip(ivy * P.rc_max_velocity_f, -1.f, 1.f));
+    out.put(8, clip(ivz * P.rc_max_velocity_f, -1.f, 1.f));
     }
     if (mode != HLYNR_OBS_WORLD) { out.put(9, 0.f); out.put(10, 0.f); out.put(11, 0.f); }  // core.py:966-970
-    if (ROLE != ROLE_M) out.put(12, clip((float)e.fuel * 0.01f, 0.f, 1.f));
+    else if (ROLE == ROLE_M) { out.put(9, sh.roll); out.put(10, sh.pitch); out.put(11, sh.yaw); }
+    else if (out.emit) {
+        float roll, pitch, yaw;
+        euler_over_pi(e.qw, e.qx, e.qy, e.qz, &roll, &pitch, &yaw);
+        out.put(9, roll); out.put(10, pitch); out.put(11, yaw);
+    }
+    out.put(12, clip((float)e.fuel * 0.01f, 0.f, 1.f));
     if (dg_det && link > 0.1f && mode == HLYNR_OBS_LOS) {  // core.py:985-1006: redundant range / rate measurements
         const W gr = nnorm3(dgx, dgy, dgz);
         const W gc = -ndot3(dgx, dgy, dgz, dvx, dvy, dvz) * nrcp(gr + W(1e-6));
@@ -962,25 +974,8 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
         for (int k = 17; k < 23; ++k) out.put(k, -2.f);
         out.put(23, 0.f);
     }
-    if (ROLE != ROLE_M) out.put(24, link);
+    out.put(24, link);
     out.put(25, fus);
-}
-
-// ROLE_I's share of the observation: forward vector and datalink quality (handed to the missile warp), channels 6-12 and 24
-template <typename R, int F>
-HD ObsShared observe_own(const KernelArgs<R>& A, const Env<R>& e, const uint4 ur, const ObsOut& out) {
-    typedef Feat<F> FT;
-    const KParams<R>& P = A.P;
-    const float ipx = (float)e.ipx, ipy = (float)e.ipy, ipz = (float)e.ipz;
-    const float ivx = (float)e.ivx, ivy = (float)e.ivy, ivz = (float)e.ivz;
-    ObsShared sh;
-    forward_vec(e.qw, e.qx, e.qy, e.qz, &sh.fx, &sh.fy, &sh.fz);
-    sh.link = 0.f;
-    if (FT::ground(P)) sh.link = datalink_quality(P, ipx, ipy, ipz, ivx, ivy, ivz, ur.w);
-    put_own_motion_world(P, e, ivx, ivy, ivz, out);
-    out.put(12, clip((float)e.fuel * 0.01f, 0.f, 1.f));
-    out.put(24, sh.link);
-    return sh;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1870,6 +1865,235 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
     {   // onboard-lock ticks: one atomic per warp that saw a lock, spread over the stat slots
         const int wl = __reduce_add_sync(0xffffffffu, active ? locks : 0);
         if (lane == 0 && wl) atomicAdd(A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS + 13, (double)wl);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// step(), warp-specialised: interceptor warps feed missile warps through shared memory
+// ------------------------------------------------------------------------------------------------
+// The one-thread-per-env kernel above is bound by the dependent-instruction latency of its ~1900-instruction chain at 16 resident
+// warps per SM (profiles/r02_e_occupancy_sweep.log: 8 / 12 / 16 warps per SM -> 161 / 120 / 104 us at 2^20 envs).  Lanes of one warp
+// that ran different code would be serialised by the SIMT front end, so the env is split across WARPS:
+//   ROLE_I (warp 0 of a CTA): interceptor state (r0, r1, r6, f0) and the wind (f1); SafetyClamp, thrust lag, fuel, drag, integration,
+//           quaternion, wind update, and of the observation the forward vector, the euler angles and the datalink quality.
+//   ROLE_M (warps 1..NM): missile, track filter, counters (r2-r5, f2, f3, i0) and the delay rings; missile update, distance /
+//           termination / reward, both radars, fusion, Kalman filter, the 26 observation channels, all outputs, statistics, resets.
+// Data only flows ROLE_I -> ROLE_M (new position / velocity / fuel, forward vector, euler angles, datalink quality, the tick's uniform
+// draws: one shared-memory slot per missile warp, handed over with a full / empty pair of named barriers), so the interceptor warp
+// runs a tile AHEAD of its missile warps instead of waiting for them: a CTA is persistent and walks over 32-env tiles
+// (tile = blockIdx.x + k * gridDim.x), the interceptor warp serves its NM missile warps in turn (it has about half of their work).
+// A finished env is reset by its missile warp alone (spawn() + the whole observation); the interceptor planes travel through the slot
+// as well and are written by the missile warp -- the stepped values for envs that go on, spawn()'s for the others -- so every plane
+// row has one writer and the interceptor warp never waits for a global store.
+// Both roles run the sections of tick_physics() / observe() on their own copy of the env registers, so every value is produced by the
+// same operations in the same order as in step_kernel (tests/test_cuda_parity.py::test_split_kernel_is_bit_identical).
+#ifndef HLYNR_WS_NM
+#define HLYNR_WS_NM 2
+#endif
+#define HLYNR_WS_BLOCK (32 * (1 + HLYNR_WS_NM))
+template <typename R> struct WsSlot {   // one hand-over ROLE_I -> ROLE_M: the interceptor planes of the tile as they will be stored + scalars [word][lane]
+    Vec4<R> r0[32], r1[32], r6[32];
+    float4 f0[32], f1[32];
+    float fwd[3][32], link[32], euler[3][32];
+    uint32_t ury[32], urz[32], clamped[32];
+};
+// Named barriers between the interceptor warp and missile warp m (64 threads each).  The ids are immediates: with a register operand
+// ptxas reserves all 16 barriers for the CTA, and the SM's 64 then cap the residency at 4 CTAs.
+template <int ID> HD void bar_sync64_id() { asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory"); }
+template <int ID> HD void bar_arrive64_id() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
+template <int BASE> HD void bar_sync64(int m) {
+    if (HLYNR_WS_NM == 1 || m == 0) bar_sync64_id<BASE>();
+    else if (HLYNR_WS_NM == 2 || m == 1) bar_sync64_id<BASE + (HLYNR_WS_NM > 1 ? 1 : 0)>();
+    else if (HLYNR_WS_NM == 3 || m == 2) bar_sync64_id<BASE + (HLYNR_WS_NM > 2 ? 2 : 0)>();
+    else bar_sync64_id<BASE + (HLYNR_WS_NM > 3 ? 3 : 0)>();
+}
+template <int BASE> HD void bar_arrive64(int m) {
+    if (HLYNR_WS_NM == 1 || m == 0) bar_arrive64_id<BASE>();
+    else if (HLYNR_WS_NM == 2 || m == 1) bar_arrive64_id<BASE + (HLYNR_WS_NM > 1 ? 1 : 0)>();
+    else if (HLYNR_WS_NM == 3 || m == 2) bar_arrive64_id<BASE + (HLYNR_WS_NM > 2 ? 2 : 0)>();
+    else bar_arrive64_id<BASE + (HLYNR_WS_NM > 3 ? 3 : 0)>();
+}
+static_assert(HLYNR_WS_NM >= 1 && HLYNR_WS_NM <= 4, "1 to 4 missile warps per interceptor warp");
+#define WS_BAR_FULL 1
+#define WS_BAR_EMPTY (1 + HLYNR_WS_NM)
+
+// Registers per thread (the resident CTAs per SM follow: 65536 / (96 * registers)); __maxnreg__ instead of a minimum-blocks launch
+// bound because ptxas derives a lower cap than necessary from the latter for 96-thread CTAs.
+#ifndef HLYNR_WS_REGS_F32
+#define HLYNR_WS_REGS_F32 96
+#endif
+#ifndef HLYNR_WS_REGS_F64
+#define HLYNR_WS_REGS_F64 168
+#endif
+template <typename R> struct WsOcc {
+    static constexpr int regs = std::is_same<R, double>::value ? HLYNR_WS_REGS_F64 : HLYNR_WS_REGS_F32;
+    static constexpr int ctas = 65536 / (HLYNR_WS_BLOCK * regs);
+};
+
+template <typename R, int F>
+__global__ void __maxnreg__(WsOcc<R>::regs)
+step_kernel_ws(const __grid_constant__ KernelArgs<R> A) {
+    typedef Feat<F> FT;
+    static_assert(F >= 0, "specialised world_frame feature sets only");
+    __shared__ __align__(16) float tiles[HLYNR_WS_NM][OBS_TILE];
+    __shared__ WsSlot<R> slots[HLYNR_WS_NM];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int64_t ntiles = (A.lim - A.first + 31) >> 5;
+    const int64_t G = gridDim.x;
+    const StatePlanes<R>& s = A.st;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (warp == 0) {
+        // ======================================= interceptor warp =======================================
+#ifdef WS_ONLY_M
+        return;
+#endif
+        int k = 0;
+#pragma unroll 1
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += G, ++k) {
+            const int m = k % HLYNR_WS_NM;
+            const int64_t i = A.first + tile * 32 + lane;
+            const int64_t ii = i < A.lim ? i : A.lim - 1;  // inactive lanes shadow the last env
+            Env<R> e;
+            load_env<R, F, ROLE_I>(A, ii, e);
+            float act[6];
+            {
+                const float2* ap = reinterpret_cast<const float2*>(A.io.actions + ii * HLYNR_ACT_DIM);
+                float2 p0 = __ldg(ap), p1 = __ldg(ap + 1), p2 = __ldg(ap + 2);
+                act[0] = p0.x; act[1] = p0.y; act[2] = p1.x; act[3] = p1.y; act[4] = p2.x; act[5] = p2.y;
+            }
+            if (tile + G < ntiles) {   // this warp's next tile: pull its planes into L2
+                const int64_t j = i + G * 32 < A.lim ? i + G * 32 : A.lim - 1;
+                prefetch_l2(s.r[0] + j); prefetch_l2(s.r[1] + j);
+                if (FT::thrust_dyn(A.P) || FT::dr(A.P)) prefetch_l2(s.r[6] + j);
+                prefetch_l2(s.f[0] + j); prefetch_l2(s.f[1] + j);
+                prefetch_l2(A.io.actions + j * HLYNR_ACT_DIM);
+            }
+            const RngKey key = make_key(A, A.env_offset + ii);
+            e.steps += 1;
+            const uint4 ur = draw_raw(key, (uint32_t)e.episode, (uint32_t)e.steps, HLYNR_BLK_UNI);
+            bool clamped;
+            tick_interceptor<R, F>(A, e, act, &clamped);
+            const ObsShared sh = own_obs<R, F>(A, e, ur.w);
+            const Vec4<R> p0{e.ipx, e.ipy, e.ipz, e.fuel}, p1{e.ivx, e.ivy, e.ivz, e.fuel_used};   // what the missile warp's tick sees
+            tick_wind<R, F>(A, e, key, (uint32_t)e.episode, (uint32_t)e.steps, ur);
+            if (k >= HLYNR_WS_NM) bar_sync64<WS_BAR_EMPTY>(m);   // the missile warp has read the previous contents of its slot
+            // The interceptor warp never stores to global memory: the missile warp writes these planes for the envs that go on and
+            // spawn()'s values for the envs it resets (one writer per plane row, and no fence that has to wait for global stores here).
+            WsSlot<R>& X = slots[m];
+            X.r0[lane] = p0; X.r1[lane] = p1;
+            if (FT::thrust_dyn(A.P) || FT::dr(A.P)) X.r6[lane] = Vec4<R>{e.thx, e.thy, e.thz, e.T0};
+            X.f0[lane] = make_float4(e.qw, e.qx, e.qy, e.qz);
+            X.f1[lane] = make_float4(e.wx, e.wy, e.wz, e.base_cd);
+            X.fwd[0][lane] = sh.fx; X.fwd[1][lane] = sh.fy; X.fwd[2][lane] = sh.fz; X.link[lane] = sh.link;
+            X.euler[0][lane] = sh.roll; X.euler[1][lane] = sh.pitch; X.euler[2][lane] = sh.yaw;
+            X.ury[lane] = ur.y; X.urz[lane] = ur.z; X.clamped[lane] = clamped ? 1u : 0u;
+            __threadfence_block();
+            bar_arrive64<WS_BAR_FULL>(m);
+        }
+    } else {
+        // ========================================= missile warps =========================================
+#ifdef WS_ONLY_I
+        return;
+#endif
+        const int m = (int)warp - 1;
+        int locks = 0;
+        ObsOut ob;
+        ob.row = tiles[m] + lane * HLYNR_OBS_DIM;
+        ob.emit = true;
+        const WsSlot<R>& X = slots[m];
+#pragma unroll 1
+        for (int64_t tile = blockIdx.x + m * G; tile < ntiles; tile += HLYNR_WS_NM * G) {
+            const int64_t warp_first = A.first + tile * 32;
+            const int64_t i = warp_first + lane;
+            const bool active = i < A.lim;
+            const int64_t ii = active ? i : A.lim - 1;
+            prefetch_ring_reads<R, F>(A, i, A.g_row, A.o_row);
+            Env<R> e;
+            load_env<R, F, ROLE_M>(A, ii, e);
+            if (tile + HLYNR_WS_NM * G < ntiles) {
+                const int64_t j = i + HLYNR_WS_NM * G * 32 < A.lim ? i + HLYNR_WS_NM * G * 32 : A.lim - 1;
+#pragma unroll
+                for (int q = 2; q < 6; ++q) prefetch_l2(s.r[q] + j);
+                prefetch_l2(s.f[2] + j);
+                if (FT::dr(A.P)) prefetch_l2(s.f[3] + j);
+                prefetch_l2(s.i0 + j);
+            }
+            if (FT::onboard_delay(A.P) && FT::dr(A.P)) {   // per-env onboard delay: the delayed row is known once the counter plane has arrived
+                int rrow = A.o_row - FLAG_ODELAY(e.flags);
+                if (rrow < 0) rrow += A.P.onb_ring_len;
+                prefetch_l1(A.st.oring + (int64_t)rrow * A.ring_stride + i);
+            }
+            const RngKey key = make_key(A, A.env_offset + ii);
+            e.steps += 1;
+            missile_update<R, F>(A.P, e, key, (uint32_t)e.episode, (uint32_t)e.steps, HLYNR_BLK_EVADE, e.mpx, e.mpy, e.mpz, e.mvx, e.mvy, e.mvz);
+            bar_sync64<WS_BAR_FULL>(m);
+            const Vec4<R> p0 = X.r0[lane], p1 = X.r1[lane];
+            e.ipx = p0.x; e.ipy = p0.y; e.ipz = p0.z; e.fuel = p0.w;
+            e.ivx = p1.x; e.ivy = p1.y; e.ivz = p1.z; e.fuel_used = p1.w;
+            ObsShared sh{X.fwd[0][lane], X.fwd[1][lane], X.fwd[2][lane], X.link[lane], X.euler[0][lane], X.euler[1][lane], X.euler[2][lane]};
+            uint4 ur = make_uint4(0u, X.ury[lane], X.urz[lane], 0u);
+            TickOut t;
+            t.clamped = X.clamped[lane] != 0u;
+            tick_outcome<R, F>(A, e, 0.f, R(0), VolleyOut{false, false, false}, t);
+            if (active && !((t.terminated || t.truncated) && A.auto_reset)) {   // interceptor planes of the envs that go on (reset envs: pass 1)
+                s.r[0][i] = p0; s.r[1][i] = p1;
+                if (FT::thrust_dyn(A.P) || FT::dr(A.P)) s.r[6][i] = X.r6[lane];
+                s.f[0][i] = X.f0[lane]; s.f[1][i] = X.f1[lane];
+            }
+            if (tile + HLYNR_WS_NM * G < ntiles) bar_arrive64<WS_BAR_EMPTY>(m);   // the slot is free for this warp's next tile
+            bool need_reset = false;
+#pragma unroll   // two copies of observe(): with one copy in a rolled loop ptxas needs 40 more registers for this warp role
+            for (int pass = 0; pass < 2; ++pass) {  // pass 1 = in-kernel auto-reset of finished envs
+                if (pass == 1) {
+                    if (!need_reset) break;
+                    e.episode += 1;
+                    ur = spawn(A, e, key, i);
+                    sh = own_obs<R, F>(A, e, ur.w);
+                    if (active) store_env<R, F, ROLE_I>(A, i, e);   // the interceptor planes of a reset env
+                }
+                observe<R, F, ROLE_M>(A, e, key, ur, i, A.g_row, A.o_row, ob, sh);
+                if (pass == 0) {
+                    const bool done = t.terminated || t.truncated;
+                    if (ob.onboard_det) locks += active ? 1 : 0;
+                    if (active) {
+                        A.io.reward[i] = t.reward;
+                        A.io.terminated[i] = t.terminated ? 1 : 0;
+                        if (A.io.done) A.io.done[i] = done ? 1 : 0;
+                        A.io.truncated[i] = t.truncated ? 1 : 0;
+                        if (A.has_info) write_info(A, i, e, t, ob);
+                    }
+                    account_episodes<R>(A, active, done, e, t);
+                    if (done && active && A.io.done_records) {
+                        record_done<R>(A, i, e.steps, e.flags, t.terminated, t.truncated, t.intercepted, t.hit, t.clamped, ob.onboard_det,
+                                       ob.ground_det, t.fuze, t.distance, (float)e.min_d, (float)e.fuel, (float)e.fuel_used, (float)e.ep_ret,
+                                       (float)e.ipx, (float)e.ipy, (float)e.ipz, (float)e.mpx, (float)e.mpy, (float)e.mpz, ob.row);
+                    }
+                    need_reset = done && A.auto_reset;
+                    if (need_reset && active && A.io.terminal_obs) {
+                        if (A.obs_dim == HLYNR_OBS_DIM) copy_obs_row(ob.row, A.io.terminal_obs + i * HLYNR_OBS_DIM);
+                        else copy_obs_row_n(ob.row, A.io.terminal_obs + i * A.obs_dim, A.obs_dim);
+                    }
+                }
+            }
+            if (A.io.obs) {
+                if (A.obs_dim == HLYNR_OBS_DIM) flush_obs_tile(tiles[m], A.io.obs, warp_first, A.lim, lane);
+                else {
+                    __syncwarp();
+                    const int64_t rows = A.lim - warp_first;
+                    if (rows > 0) flush_obs_narrow(tiles[m], A.io.obs + warp_first * A.obs_dim, rows >= 32 ? 32 : (int)rows, A.obs_dim, lane);
+                    __syncwarp();
+                }
+            }
+            if (active) store_env<R, F, ROLE_M>(A, i, e);
+#ifdef WS_ONE_TILE
+            break;
+#endif
+        }
+        {   // onboard-lock ticks: one atomic per warp that saw a lock, spread over the stat slots
+            const int wl = __reduce_add_sync(0xffffffffu, locks);
+            if (lane == 0 && wl) atomicAdd(A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS + 13, (double)wl);
+        }
     }
 }
 

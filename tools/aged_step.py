@@ -6,7 +6,9 @@ from hlynr_intercept_b200 import config
 from hlynr_intercept_b200.sim import HlynrSim
 n = 1 << 20
 name = sys.argv[1] if len(sys.argv) > 1 else 'cfg4'
-sim = HlynrSim(config.baseline_config(name), n_envs=n, warn_dead=False)
+sim = HlynrSim(config.baseline_config(name), n_envs=n, warn_dead=False, precision=os.environ.get('HLYNR_PRECISION', 'fp32'))
+for kv in filter(None, os.environ.get('HLYNR_OPTS', '').split(',')):   # e.g. HLYNR_OPTS=split=1
+    sim.set_option(kv.split('=')[0], int(kv.split('=')[1]))
 sim.reset()
 sim.rollout(1500, None, want_obs=False)
 pool = [(torch.rand(n, 6, device='cuda') * 2 - 1) for _ in range(4)]
