@@ -211,8 +211,7 @@ struct hlynr_sim {
     HostIO hio;
     int host_info = 1, host_chunks = 0, host_threads = 0;
     int host_chunk_growth = 12;   // geometric chunk schedule of the host path, x1.5 per chunk (measured best on B200: 2.43 -> 2.35 ms at 2^20 envs, 26-D)
-    int split = 0;   // option "split": API-mode ticks of the specialised configurations run on specialised warps (step_kernel_ws)
-    int ws_ctas_per_sm = 0;   // option "ws_ctas_per_sm": persistent CTAs per SM of step_kernel_ws (0 = what its launch bounds allow)
+    int compact = 0;   // compact plane layout (fp32 build, cfg4 feature set): the counters ride in r6.w / f1.w and the i0 plane is unused
     int pdl = 1;   // step kernels are launched with programmatic stream serialization (option "pdl"; -1.5 us per launch on B200)
     int obs_dim = HLYNR_OBS_DIM;  // row pitch of every observation array of the API: 26, or 17 (option "obs_dim")
     int prefetch_waves = 1;  // CTAs per SM the step kernel looks ahead when it prefetches upcoming planes into L2 (0 = off)
@@ -297,7 +296,7 @@ static RoundKeys make_round_keys(uint64_t seed) {
 // ------------------------------------------------------------------------------------------------
 // small utility kernels
 // ------------------------------------------------------------------------------------------------
-template <typename R> __global__ void init_kernel(StatePlanes<R> s, int64_t n_pad, float peak, bool has_r6) {
+template <typename R> __global__ void init_kernel(StatePlanes<R> s, int64_t n_pad, float peak, bool compact) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
     Vec4<R> z{R(0), R(0), R(0), R(0)};
@@ -308,7 +307,10 @@ template <typename R> __global__ void init_kernel(StatePlanes<R> s, int64_t n_pa
     s.f[2][i] = make_float4(0.f, 0.f, 1000.f, 1000.f);   // Kalman P_pv, P_vp, P_vv, P_pp
     s.f[3][i] = make_float4(peak, 0.f, 0.f, 0.f);
     s.i0[i] = make_int4(0, 0, 0, -1);  // episode -1: the first reset starts episode 0
-    (void)has_r6;
+    if (compact) {   // the same counters in the compact layout (hlynr_device.cuh load_env): steps = worsen = 0, episode = -1, flags = 0
+        s.r[6][i] = Vec4<R>{R(0), R(0), R(0), bits_word(0, R(0))};
+        s.f[1][i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x1ffffff));
+    }
 }
 
 // [SLOTS+1][WORDS]: last row = sum of the slots; word 12 (ticks simulated) is known on the host
@@ -427,6 +429,7 @@ template <typename R> static KernelArgs<R> base_args(hlynr_sim* s, const StatePl
     A.k_steps = 1;
     A.prefetch_ahead = s->sm_count * s->prefetch_waves * HLYNR_BLOCK;
     A.obs_dim = s->obs_dim;
+    A.compact = s->compact;
     return A;
 }
 static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
@@ -468,54 +471,12 @@ template <typename R, bool kRollout, int F> static void launch_inst(const Kernel
     cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
     cudaLaunchKernelEx(&cfg, step_kernel<R, kRollout, F>, A);
 }
-// The warp-specialised persistent step kernel (step_kernel_ws) of a specialised instantiation: one CTA of 1 interceptor + NM missile
-// warps per resident slot, walking over the 32-env tiles of the range.
-template <typename R, int F> static void launch_ws(const hlynr_sim* s, const KernelArgs<R>& A, cudaStream_t st, bool pdl) {
-    const int64_t ntiles = (A.lim - A.first + 31) / 32;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.blockDim = dim3(HLYNR_WS_BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
-    {   // the CTAs are persistent: all of them must be resident, so the shared-memory carve-out has to hold grid / SMs of them
-        static thread_local int carved[16] = {0};   // resident CTAs per SM, per device (the attribute belongs to the device's copy of the function)
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev < 0 || dev >= 16) dev = 0;
-        if (!carved[dev]) {
-            cudaFuncAttributes fa;
-            cudaFuncGetAttributes(&fa, step_kernel_ws<R, F>);
-            const size_t need = (size_t)WsOcc<R>::ctas * (fa.sharedSizeBytes + 1024);
-            int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024)) + 3;
-            cudaFuncSetAttribute(step_kernel_ws<R, F>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
-            int occ = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_ws<R, F>, HLYNR_WS_BLOCK, 0);
-            carved[dev] = occ > 0 ? occ : 1;
-        }
-        int per_sm = s->ws_ctas_per_sm > 0 ? s->ws_ctas_per_sm : WsOcc<R>::ctas;
-        if (per_sm > carved[dev]) per_sm = carved[dev];
-        int64_t grid = (int64_t)s->sm_count * per_sm;
-        if (grid > ntiles) grid = ntiles;
-        cfg.gridDim = dim3((unsigned)grid);
-    }
-    cudaLaunchKernelEx(&cfg, step_kernel_ws<R, F>, A);
-}
 // Both builds dispatch to the feature-specialised instantiation of the three BASELINE configurations when it matches.
 template <typename R, bool kRollout> static void launch_step(const hlynr_sim* s, const KernelArgs<R>& A, cudaStream_t st, bool specialise) {
     const int grid = grid_for(A.lim - A.first, HLYNR_STEP_BLOCK);
     const bool pdl = s->pdl != 0;
     int f = feature_set(s->params);
     if (!specialise && f >= 0) f = FT_GENERIC;
-    if constexpr (!kRollout) {
-        if (s->split && f >= 0) {   // option "split": API-mode ticks of a specialised configuration on specialised warps
-            if (f == FT_V2ON) launch_ws<R, FT_V2ON>(s, A, st, pdl);
-            else if (f == FT_V2OFF) launch_ws<R, FT_V2OFF>(s, A, st, pdl);
-            else launch_ws<R, FT_V2ON_DR>(s, A, st, pdl);
-            return;
-        }
-    }
     if (f == FT_V2ON) launch_inst<R, kRollout, FT_V2ON>(A, grid, st, pdl);
     else if (f == FT_V2OFF) launch_inst<R, kRollout, FT_V2OFF>(A, grid, st, pdl);
     else if (f == FT_V2ON_DR) launch_inst<R, kRollout, FT_V2ON_DR>(A, grid, st, pdl);
@@ -595,10 +556,12 @@ int hlynr_create(const HlynrParams* p, int64_t n_envs, int device, uint64_t seed
     const int blk = 256;
     if (precision == HLYNR_FP32) {
         carve<float>(s->pf, (char*)s->state_mem, s->n_pad, gl, ol, p->volley_size);
-        init_kernel<float><<<grid_for(s->n_pad, blk), blk>>>(s->pf, s->n_pad, (float)p->peak_mult, true);
+        // compact plane layout (hlynr_device.cuh load_env): fixed for the life of the handle, whichever kernel instantiation runs
+        s->compact = (feature_set(*p) == FT_V2ON && p->max_steps < 65536 && !getenv("HLYNR_NO_COMPACT")) ? 1 : 0;
+        init_kernel<float><<<grid_for(s->n_pad, blk), blk>>>(s->pf, s->n_pad, (float)p->peak_mult, s->compact != 0);
     } else {
         carve<double>(s->pd, (char*)s->state_mem, s->n_pad, gl, ol, p->volley_size);
-        init_kernel<double><<<grid_for(s->n_pad, blk), blk>>>(s->pd, s->n_pad, (float)p->peak_mult, true);
+        init_kernel<double><<<grid_for(s->n_pad, blk), blk>>>(s->pd, s->n_pad, (float)p->peak_mult, false);
     }
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { int r = fail("hlynr_create: init kernel failed: %s", cudaGetErrorString(e)); hlynr_destroy(s); return r; }
@@ -632,11 +595,6 @@ int hlynr_set_option(hlynr_t* s, const char* name, int64_t value) {
         return 0;
     }
     if (strcmp(name, "pdl") == 0) { s->pdl = value != 0; return 0; }
-    if (strcmp(name, "split") == 0) { s->split = value != 0; return 0; }
-    if (strcmp(name, "ws_ctas_per_sm") == 0) {
-        if (value < 0 || value > 32) return fail("hlynr_set_option: ws_ctas_per_sm must be in [0, 32]");
-        s->ws_ctas_per_sm = (int)value; return 0;
-    }
     return fail("hlynr_set_option: unknown option '%s'", name);
 }
 static int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }

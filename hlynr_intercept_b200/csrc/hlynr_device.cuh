@@ -314,6 +314,7 @@ template <typename R> struct KernelArgs {
     int32_t has_info;
     int32_t prefetch_ahead;  // envs per resident wave of CTAs (0 = no L2 prefetch of the next wave's planes)
     int32_t obs_dim;         // row pitch of io.obs / io.terminal_obs: HLYNR_OBS_DIM, or 17 = the leading "17-D radar" channels only
+    int32_t compact;         // compact plane layout (see load_env): the counters ride in r6.w / f1.w, the i0 plane is unused
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -342,45 +343,68 @@ template <typename R> struct Env {
 #define FLAG_VCUR(f) (((f) >> 12) & 0x7)
 #define FLAG_VCOUNT(f) (((f) >> 16) & 0xf)
 
-// ROLE_ALL moves every plane.  The warp-pair split divides them by owner: the interceptor warp (ROLE_I) reads and writes r0, r1, r6,
-// f0, f1 and only reads the counters (i0: the Philox counter words) and, with domain randomization, the drag terms in f3; the missile
-// warp (ROLE_M) reads and writes r2-r5, f2, f3, i0 and only reads the wind / base Cd (f1) and, with DR, the temperature T0 (r6).
-template <typename R, int F = FT_GENERIC, int ROLE = 0> HD void load_env(const KernelArgs<R>& A, int64_t i, Env<R>& e) {
+// Compact layout (KernelArgs::compact; fp32 build, the cfg4 feature set FT_V2ON without domain randomization, max_steps < 65536):
+// the two words that are constants there -- T0 in r6.w and the base Cd in f1.w -- carry the counters instead, so the i0 plane is
+// never touched: 10 planes (160 B read + 160 B written per env-step) instead of 11.
+//   r6.w = bits(steps | worsen << 16)          f1.w = bits(episode (25 bits, signed) | flags7 << 25)
+//   flags7 = crossed | kf_init << 1 | kf_f64 << 2 | onboard delay << 3   (the volley fields of the flag word do not exist here)
+HD int word_bits(float x) { return __float_as_int(x); }
+HD int word_bits(double) { return 0; }
+HD float bits_word(int x, float) { return __int_as_float(x); }
+HD double bits_word(int, double) { return 0.0; }
+template <typename R> HD bool compact_layout(const KernelArgs<R>& A) { return std::is_same<R, float>::value && A.compact != 0; }
+
+template <typename R, int F = FT_GENERIC> HD void load_env(const KernelArgs<R>& A, int64_t i, Env<R>& e) {
     typedef Feat<F> FT;
     const StatePlanes<R>& s = A.st;
-    constexpr bool kI = ROLE != 2, kM = ROLE != 1;
+    const bool compact = compact_layout(A);
     Vec4<R> v;
-    if (kI) { v = s.r[0][i]; e.ipx = v.x; e.ipy = v.y; e.ipz = v.z; e.fuel = v.w; }
-    if (kI) { v = s.r[1][i]; e.ivx = v.x; e.ivy = v.y; e.ivz = v.z; e.fuel_used = v.w; }
-    if (kM) { v = s.r[2][i]; e.mpx = v.x; e.mpy = v.y; e.mpz = v.z; e.prev_d = v.w; }
-    if (kM) { v = s.r[3][i]; e.mvx = v.x; e.mvy = v.y; e.mvz = v.z; e.last_d = v.w; }
-    if (kM) { v = s.r[4][i]; e.kpx = v.x; e.kpy = v.y; e.kpz = v.z; e.min_d = v.w; }
-    if (kM) { v = s.r[5][i]; e.kvx = v.x; e.kvy = v.y; e.kvz = v.z; e.ep_ret = v.w; }
-    if ((kI && (FT::thrust_dyn(A.P) || FT::dr(A.P))) || (ROLE == 2 && FT::dr(A.P))) { v = s.r[6][i]; e.thx = v.x; e.thy = v.y; e.thz = v.z; e.T0 = v.w; }
+    v = s.r[0][i]; e.ipx = v.x; e.ipy = v.y; e.ipz = v.z; e.fuel = v.w;
+    v = s.r[1][i]; e.ivx = v.x; e.ivy = v.y; e.ivz = v.z; e.fuel_used = v.w;
+    v = s.r[2][i]; e.mpx = v.x; e.mpy = v.y; e.mpz = v.z; e.prev_d = v.w;
+    v = s.r[3][i]; e.mvx = v.x; e.mvy = v.y; e.mvz = v.z; e.last_d = v.w;
+    v = s.r[4][i]; e.kpx = v.x; e.kpy = v.y; e.kpz = v.z; e.min_d = v.w;
+    v = s.r[5][i]; e.kvx = v.x; e.kvy = v.y; e.kvz = v.z; e.ep_ret = v.w;
+    if (compact || FT::thrust_dyn(A.P) || FT::dr(A.P)) { v = s.r[6][i]; e.thx = v.x; e.thy = v.y; e.thz = v.z; e.T0 = v.w; }
     else { e.thx = e.thy = e.thz = R(0); e.T0 = R(288.15); }
     float4 f;
-    if (kI) { f = s.f[0][i]; e.qw = f.x; e.qx = f.y; e.qy = f.z; e.qz = f.w; }
+    f = s.f[0][i]; e.qw = f.x; e.qx = f.y; e.qy = f.z; e.qz = f.w;
     f = s.f[1][i]; e.wx = f.x; e.wy = f.y; e.wz = f.z; e.base_cd = f.w;
-    if (kM) { f = s.f[2][i]; e.Ppv = f.x; e.Pvp = f.y; e.Pvv = f.z; e.Ppp = f.w; }
+    f = s.f[2][i]; e.Ppv = f.x; e.Pvp = f.y; e.Pvv = f.z; e.Ppp = f.w;
     if (FT::dr(A.P)) { f = s.f[3][i]; e.peak = f.x; } else e.peak = 0.f;
-    int4 q = s.i0[i]; e.steps = q.x; e.worsen = q.y; e.flags = q.z; e.episode = q.w;
+    if (compact) {
+        const int sw = word_bits(e.T0), ef = word_bits(e.base_cd);
+        e.T0 = R(288.15); e.base_cd = 0.3f;
+        e.steps = sw & 0xffff; e.worsen = (int)((unsigned)sw >> 16);
+        e.episode = (ef << 7) >> 7;
+        const int p = (int)((unsigned)ef >> 25);
+        e.flags = (p & 7) | (((p >> 3) & 0xf) << 8);
+    } else {
+        int4 q = s.i0[i]; e.steps = q.x; e.worsen = q.y; e.flags = q.z; e.episode = q.w;
+    }
 }
-template <typename R, int F = FT_GENERIC, int ROLE = 0> HD void store_env(const KernelArgs<R>& A, int64_t i, const Env<R>& e) {
+template <typename R, int F = FT_GENERIC> HD void store_env(const KernelArgs<R>& A, int64_t i, const Env<R>& e) {
     typedef Feat<F> FT;
     const StatePlanes<R>& s = A.st;
-    constexpr bool kI = ROLE != 2, kM = ROLE != 1;
-    if (kI) s.r[0][i] = Vec4<R>{e.ipx, e.ipy, e.ipz, e.fuel};
-    if (kI) s.r[1][i] = Vec4<R>{e.ivx, e.ivy, e.ivz, e.fuel_used};
-    if (kM) s.r[2][i] = Vec4<R>{e.mpx, e.mpy, e.mpz, e.prev_d};
-    if (kM) s.r[3][i] = Vec4<R>{e.mvx, e.mvy, e.mvz, e.last_d};
-    if (kM) s.r[4][i] = Vec4<R>{e.kpx, e.kpy, e.kpz, e.min_d};
-    if (kM) s.r[5][i] = Vec4<R>{e.kvx, e.kvy, e.kvz, e.ep_ret};
-    if (kI && (FT::thrust_dyn(A.P) || FT::dr(A.P))) s.r[6][i] = Vec4<R>{e.thx, e.thy, e.thz, e.T0};
-    if (kI) s.f[0][i] = make_float4(e.qw, e.qx, e.qy, e.qz);
-    if (kI) s.f[1][i] = make_float4(e.wx, e.wy, e.wz, e.base_cd);
-    if (kM) s.f[2][i] = make_float4(e.Ppv, e.Pvp, e.Pvv, e.Ppp);
-    if (kM && FT::dr(A.P)) s.f[3][i] = make_float4(e.peak, 0.f, 0.f, 0.f);
-    if (kM) s.i0[i] = make_int4(e.steps, e.worsen, e.flags, e.episode);
+    const bool compact = compact_layout(A);
+    R r6w = e.T0;
+    float f1w = e.base_cd;
+    if (compact) {
+        r6w = bits_word((e.steps & 0xffff) | (e.worsen << 16), R(0));
+        f1w = __int_as_float((e.episode & 0x1ffffff) | (((e.flags & 7) | (((e.flags >> 8) & 0xf) << 3)) << 25));
+    }
+    s.r[0][i] = Vec4<R>{e.ipx, e.ipy, e.ipz, e.fuel};
+    s.r[1][i] = Vec4<R>{e.ivx, e.ivy, e.ivz, e.fuel_used};
+    s.r[2][i] = Vec4<R>{e.mpx, e.mpy, e.mpz, e.prev_d};
+    s.r[3][i] = Vec4<R>{e.mvx, e.mvy, e.mvz, e.last_d};
+    s.r[4][i] = Vec4<R>{e.kpx, e.kpy, e.kpz, e.min_d};
+    s.r[5][i] = Vec4<R>{e.kvx, e.kvy, e.kvz, e.ep_ret};
+    if (compact || FT::thrust_dyn(A.P) || FT::dr(A.P)) s.r[6][i] = Vec4<R>{e.thx, e.thy, e.thz, r6w};
+    s.f[0][i] = make_float4(e.qw, e.qx, e.qy, e.qz);
+    s.f[1][i] = make_float4(e.wx, e.wy, e.wz, f1w);
+    s.f[2][i] = make_float4(e.Ppv, e.Pvp, e.Pvv, e.Ppp);
+    if (FT::dr(A.P)) s.f[3][i] = make_float4(e.peak, 0.f, 0.f, 0.f);
+    if (!compact) s.i0[i] = make_int4(e.steps, e.worsen, e.flags, e.episode);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -582,13 +606,7 @@ __device__ __noinline__ TrackF32 track_obs_f32_phase(const KParams<R>& P, int mo
     return lb;
 }
 
-// Warp-specialised step kernel (step_kernel_ws below): interceptor warps (ROLE_I) own the interceptor / wind state, missile warps
-// (ROLE_M) own everything else and receive the interceptor's new state, its forward vector, euler angles and the datalink quality
-// through shared memory.  ROLE_ALL is the one-thread-per-env code every other kernel runs.  The pieces the roles share are the helper
-// functions below, so all of them evaluate the same operations in the same order.
-enum { ROLE_ALL = 0, ROLE_I = 1, ROLE_M = 2 };
-struct ObsShared { float fx, fy, fz, link, roll, pitch, yaw; };   // ROLE_I -> ROLE_M
-
+// Pieces of the observation that depend on the interceptor state only.
 // forward vector, core.py:1143-1152
 HD void forward_vec(float w, float x, float y, float z, float* fx, float* fy, float* fz) {
     float a = 2.f * fmaf(x, z, w * y), b = 2.f * fmaf(y, z, -(w * x)), c = 1.f - 2.f * fmaf(x, x, y * y);
@@ -618,25 +636,10 @@ HD void euler_over_pi(float w, float x, float y, float z, float* roll, float* pi
     *pitch = fast_asin(clip(sinp, -1.f, 1.f)) * ipi;
     *yaw = fast_atan2(siny, cosy) * ipi;
 }
-// what ROLE_I computes of the observation: forward vector, datalink quality, euler angles
 template <typename R, int F>
-HD ObsShared own_obs(const KernelArgs<R>& A, const Env<R>& e, const uint32_t urw) {
-    ObsShared sh;
-    forward_vec(e.qw, e.qx, e.qy, e.qz, &sh.fx, &sh.fy, &sh.fz);
-    sh.link = 0.f;
-    if (Feat<F>::ground(A.P))
-        sh.link = datalink_quality(A.P, (float)e.ipx, (float)e.ipy, (float)e.ipz, (float)e.ivx, (float)e.ivy, (float)e.ivz, urw);
-    euler_over_pi(e.qw, e.qx, e.qy, e.qz, &sh.roll, &sh.pitch, &sh.yaw);
-    return sh;
-}
-
-template <typename R, int F, int ROLE = ROLE_ALL>
-HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint4 ur, int64_t i, int g_row, int o_row, ObsOut& out,
-                const ObsShared sh = ObsShared{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}) {
+HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint4 ur, int64_t i, int g_row, int o_row, ObsOut& out) {
     typedef R W;
     typedef Feat<F> FT;
-    static_assert(ROLE != ROLE_I, "the interceptor warps run own_obs()");
-    static_assert(ROLE == ROLE_ALL || F >= 0, "the warp-pair split exists for the specialised world_frame feature sets only");
     const KParams<R>& P = A.P;
     const KCurriculum<R>& C = A.C;
     const int64_t n = A.ring_stride;
@@ -649,8 +652,7 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
     const float rx = sub(mpx, ipx), ry = sub(mpy, ipy), rz = sub(mpz, ipz);
     const float range = nnorm3(rx, ry, rz);
     float fx, fy, fz;
-    if constexpr (ROLE == ROLE_M) { fx = sh.fx; fy = sh.fy; fz = sh.fz; }
-    else forward_vec(e.qw, e.qx, e.qy, e.qz, &fx, &fy, &fz);
+    forward_vec(e.qw, e.qx, e.qy, e.qz, &fx, &fy, &fz);
     bool onb = !(range > P.radar_range);
     if (onb) {
         float cb = ndot3(fx, fy, fz, rx, ry, rz) * nrcp(range + 1e-6f);
@@ -723,8 +725,7 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
 
     // === datalink, core.py:440-474 ===
     float link = 0.f;
-    if constexpr (ROLE == ROLE_M) link = sh.link;
-    else if (FT::ground(P)) link = datalink_quality(P, ipx, ipy, ipz, ivx, ivy, ivz, ur.w);
+    if (FT::ground(P)) link = datalink_quality(P, ipx, ipy, ipz, ivx, ivy, ivz, ur.w);
 
     // === fusion confidence, core.py:476-509 ===
     float fus;
@@ -934,7 +935,6 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
     out.put(8, clip(ivz * P.rc_max_velocity_f, -1.f, 1.f));
     }
     if (mode != HLYNR_OBS_WORLD) { out.put(9, 0.f); out.put(10, 0.f); out.put(11, 0.f); }  // core.py:966-970
-    else if (ROLE == ROLE_M) { out.put(9, sh.roll); out.put(10, sh.pitch); out.put(11, sh.yaw); }
     else if (out.emit) {
         float roll, pitch, yaw;
         euler_over_pi(e.qw, e.qx, e.qy, e.qz, &roll, &pitch, &yaw);
@@ -1277,8 +1277,7 @@ HD VolleyOut volley_step(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, u
     return o;
 }
 
-// The tick in four sections (the order of environment.py:605-859): interceptor, missile(s), wind, outcome.  tick_physics() runs
-// them for one env per thread; step_kernel_split runs the first and third on the interceptor warp, the others on the missile warp.
+// The tick in four sections (the order of environment.py:605-859): interceptor, missile(s), wind, outcome.
 template <typename R, int F>
 HD void tick_interceptor(const KernelArgs<R>& A, Env<R>& e, const float act[6], bool* clamped_out) {
     typedef Feat<F> FT;
@@ -1724,7 +1723,7 @@ template <typename R, int F> HD void prefetch_next_wave(const KernelArgs<R>& A, 
 #pragma unroll
     for (int k = 0; k < 3; ++k) prefetch_l2(s.f[k] + j);
     if (FT::dr(A.P)) prefetch_l2(s.f[3] + j);
-    prefetch_l2(s.i0 + j);
+    if (!compact_layout(A)) prefetch_l2(s.i0 + j);
     if (A.io.actions) prefetch_l2(A.io.actions + j * HLYNR_ACT_DIM);
 }
 template <typename R, int F> HD void prefetch_ring_reads(const KernelArgs<R>& A, int64_t i, int g_row, int o_row) {
@@ -1865,235 +1864,6 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
     {   // onboard-lock ticks: one atomic per warp that saw a lock, spread over the stat slots
         const int wl = __reduce_add_sync(0xffffffffu, active ? locks : 0);
         if (lane == 0 && wl) atomicAdd(A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS + 13, (double)wl);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// step(), warp-specialised: interceptor warps feed missile warps through shared memory
-// ------------------------------------------------------------------------------------------------
-// The one-thread-per-env kernel above is bound by the dependent-instruction latency of its ~1900-instruction chain at 16 resident
-// warps per SM (profiles/r02_e_occupancy_sweep.log: 8 / 12 / 16 warps per SM -> 161 / 120 / 104 us at 2^20 envs).  Lanes of one warp
-// that ran different code would be serialised by the SIMT front end, so the env is split across WARPS:
-//   ROLE_I (warp 0 of a CTA): interceptor state (r0, r1, r6, f0) and the wind (f1); SafetyClamp, thrust lag, fuel, drag, integration,
-//           quaternion, wind update, and of the observation the forward vector, the euler angles and the datalink quality.
-//   ROLE_M (warps 1..NM): missile, track filter, counters (r2-r5, f2, f3, i0) and the delay rings; missile update, distance /
-//           termination / reward, both radars, fusion, Kalman filter, the 26 observation channels, all outputs, statistics, resets.
-// Data only flows ROLE_I -> ROLE_M (new position / velocity / fuel, forward vector, euler angles, datalink quality, the tick's uniform
-// draws: one shared-memory slot per missile warp, handed over with a full / empty pair of named barriers), so the interceptor warp
-// runs a tile AHEAD of its missile warps instead of waiting for them: a CTA is persistent and walks over 32-env tiles
-// (tile = blockIdx.x + k * gridDim.x), the interceptor warp serves its NM missile warps in turn (it has about half of their work).
-// A finished env is reset by its missile warp alone (spawn() + the whole observation); the interceptor planes travel through the slot
-// as well and are written by the missile warp -- the stepped values for envs that go on, spawn()'s for the others -- so every plane
-// row has one writer and the interceptor warp never waits for a global store.
-// Both roles run the sections of tick_physics() / observe() on their own copy of the env registers, so every value is produced by the
-// same operations in the same order as in step_kernel (tests/test_cuda_parity.py::test_split_kernel_is_bit_identical).
-#ifndef HLYNR_WS_NM
-#define HLYNR_WS_NM 2
-#endif
-#define HLYNR_WS_BLOCK (32 * (1 + HLYNR_WS_NM))
-template <typename R> struct WsSlot {   // one hand-over ROLE_I -> ROLE_M: the interceptor planes of the tile as they will be stored + scalars [word][lane]
-    Vec4<R> r0[32], r1[32], r6[32];
-    float4 f0[32], f1[32];
-    float fwd[3][32], link[32], euler[3][32];
-    uint32_t ury[32], urz[32], clamped[32];
-};
-// Named barriers between the interceptor warp and missile warp m (64 threads each).  The ids are immediates: with a register operand
-// ptxas reserves all 16 barriers for the CTA, and the SM's 64 then cap the residency at 4 CTAs.
-template <int ID> HD void bar_sync64_id() { asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory"); }
-template <int ID> HD void bar_arrive64_id() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
-template <int BASE> HD void bar_sync64(int m) {
-    if (HLYNR_WS_NM == 1 || m == 0) bar_sync64_id<BASE>();
-    else if (HLYNR_WS_NM == 2 || m == 1) bar_sync64_id<BASE + (HLYNR_WS_NM > 1 ? 1 : 0)>();
-    else if (HLYNR_WS_NM == 3 || m == 2) bar_sync64_id<BASE + (HLYNR_WS_NM > 2 ? 2 : 0)>();
-    else bar_sync64_id<BASE + (HLYNR_WS_NM > 3 ? 3 : 0)>();
-}
-template <int BASE> HD void bar_arrive64(int m) {
-    if (HLYNR_WS_NM == 1 || m == 0) bar_arrive64_id<BASE>();
-    else if (HLYNR_WS_NM == 2 || m == 1) bar_arrive64_id<BASE + (HLYNR_WS_NM > 1 ? 1 : 0)>();
-    else if (HLYNR_WS_NM == 3 || m == 2) bar_arrive64_id<BASE + (HLYNR_WS_NM > 2 ? 2 : 0)>();
-    else bar_arrive64_id<BASE + (HLYNR_WS_NM > 3 ? 3 : 0)>();
-}
-static_assert(HLYNR_WS_NM >= 1 && HLYNR_WS_NM <= 4, "1 to 4 missile warps per interceptor warp");
-#define WS_BAR_FULL 1
-#define WS_BAR_EMPTY (1 + HLYNR_WS_NM)
-
-// Registers per thread (the resident CTAs per SM follow: 65536 / (96 * registers)); __maxnreg__ instead of a minimum-blocks launch
-// bound because ptxas derives a lower cap than necessary from the latter for 96-thread CTAs.
-#ifndef HLYNR_WS_REGS_F32
-#define HLYNR_WS_REGS_F32 96
-#endif
-#ifndef HLYNR_WS_REGS_F64
-#define HLYNR_WS_REGS_F64 168
-#endif
-template <typename R> struct WsOcc {
-    static constexpr int regs = std::is_same<R, double>::value ? HLYNR_WS_REGS_F64 : HLYNR_WS_REGS_F32;
-    static constexpr int ctas = 65536 / (HLYNR_WS_BLOCK * regs);
-};
-
-template <typename R, int F>
-__global__ void __maxnreg__(WsOcc<R>::regs)
-step_kernel_ws(const __grid_constant__ KernelArgs<R> A) {
-    typedef Feat<F> FT;
-    static_assert(F >= 0, "specialised world_frame feature sets only");
-    __shared__ __align__(16) float tiles[HLYNR_WS_NM][OBS_TILE];
-    __shared__ WsSlot<R> slots[HLYNR_WS_NM];
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const int64_t ntiles = (A.lim - A.first + 31) >> 5;
-    const int64_t G = gridDim.x;
-    const StatePlanes<R>& s = A.st;
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (warp == 0) {
-        // ======================================= interceptor warp =======================================
-#ifdef WS_ONLY_M
-        return;
-#endif
-        int k = 0;
-#pragma unroll 1
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += G, ++k) {
-            const int m = k % HLYNR_WS_NM;
-            const int64_t i = A.first + tile * 32 + lane;
-            const int64_t ii = i < A.lim ? i : A.lim - 1;  // inactive lanes shadow the last env
-            Env<R> e;
-            load_env<R, F, ROLE_I>(A, ii, e);
-            float act[6];
-            {
-                const float2* ap = reinterpret_cast<const float2*>(A.io.actions + ii * HLYNR_ACT_DIM);
-                float2 p0 = __ldg(ap), p1 = __ldg(ap + 1), p2 = __ldg(ap + 2);
-                act[0] = p0.x; act[1] = p0.y; act[2] = p1.x; act[3] = p1.y; act[4] = p2.x; act[5] = p2.y;
-            }
-            if (tile + G < ntiles) {   // this warp's next tile: pull its planes into L2
-                const int64_t j = i + G * 32 < A.lim ? i + G * 32 : A.lim - 1;
-                prefetch_l2(s.r[0] + j); prefetch_l2(s.r[1] + j);
-                if (FT::thrust_dyn(A.P) || FT::dr(A.P)) prefetch_l2(s.r[6] + j);
-                prefetch_l2(s.f[0] + j); prefetch_l2(s.f[1] + j);
-                prefetch_l2(A.io.actions + j * HLYNR_ACT_DIM);
-            }
-            const RngKey key = make_key(A, A.env_offset + ii);
-            e.steps += 1;
-            const uint4 ur = draw_raw(key, (uint32_t)e.episode, (uint32_t)e.steps, HLYNR_BLK_UNI);
-            bool clamped;
-            tick_interceptor<R, F>(A, e, act, &clamped);
-            const ObsShared sh = own_obs<R, F>(A, e, ur.w);
-            const Vec4<R> p0{e.ipx, e.ipy, e.ipz, e.fuel}, p1{e.ivx, e.ivy, e.ivz, e.fuel_used};   // what the missile warp's tick sees
-            tick_wind<R, F>(A, e, key, (uint32_t)e.episode, (uint32_t)e.steps, ur);
-            if (k >= HLYNR_WS_NM) bar_sync64<WS_BAR_EMPTY>(m);   // the missile warp has read the previous contents of its slot
-            // The interceptor warp never stores to global memory: the missile warp writes these planes for the envs that go on and
-            // spawn()'s values for the envs it resets (one writer per plane row, and no fence that has to wait for global stores here).
-            WsSlot<R>& X = slots[m];
-            X.r0[lane] = p0; X.r1[lane] = p1;
-            if (FT::thrust_dyn(A.P) || FT::dr(A.P)) X.r6[lane] = Vec4<R>{e.thx, e.thy, e.thz, e.T0};
-            X.f0[lane] = make_float4(e.qw, e.qx, e.qy, e.qz);
-            X.f1[lane] = make_float4(e.wx, e.wy, e.wz, e.base_cd);
-            X.fwd[0][lane] = sh.fx; X.fwd[1][lane] = sh.fy; X.fwd[2][lane] = sh.fz; X.link[lane] = sh.link;
-            X.euler[0][lane] = sh.roll; X.euler[1][lane] = sh.pitch; X.euler[2][lane] = sh.yaw;
-            X.ury[lane] = ur.y; X.urz[lane] = ur.z; X.clamped[lane] = clamped ? 1u : 0u;
-            __threadfence_block();
-            bar_arrive64<WS_BAR_FULL>(m);
-        }
-    } else {
-        // ========================================= missile warps =========================================
-#ifdef WS_ONLY_I
-        return;
-#endif
-        const int m = (int)warp - 1;
-        int locks = 0;
-        ObsOut ob;
-        ob.row = tiles[m] + lane * HLYNR_OBS_DIM;
-        ob.emit = true;
-        const WsSlot<R>& X = slots[m];
-#pragma unroll 1
-        for (int64_t tile = blockIdx.x + m * G; tile < ntiles; tile += HLYNR_WS_NM * G) {
-            const int64_t warp_first = A.first + tile * 32;
-            const int64_t i = warp_first + lane;
-            const bool active = i < A.lim;
-            const int64_t ii = active ? i : A.lim - 1;
-            prefetch_ring_reads<R, F>(A, i, A.g_row, A.o_row);
-            Env<R> e;
-            load_env<R, F, ROLE_M>(A, ii, e);
-            if (tile + HLYNR_WS_NM * G < ntiles) {
-                const int64_t j = i + HLYNR_WS_NM * G * 32 < A.lim ? i + HLYNR_WS_NM * G * 32 : A.lim - 1;
-#pragma unroll
-                for (int q = 2; q < 6; ++q) prefetch_l2(s.r[q] + j);
-                prefetch_l2(s.f[2] + j);
-                if (FT::dr(A.P)) prefetch_l2(s.f[3] + j);
-                prefetch_l2(s.i0 + j);
-            }
-            if (FT::onboard_delay(A.P) && FT::dr(A.P)) {   // per-env onboard delay: the delayed row is known once the counter plane has arrived
-                int rrow = A.o_row - FLAG_ODELAY(e.flags);
-                if (rrow < 0) rrow += A.P.onb_ring_len;
-                prefetch_l1(A.st.oring + (int64_t)rrow * A.ring_stride + i);
-            }
-            const RngKey key = make_key(A, A.env_offset + ii);
-            e.steps += 1;
-            missile_update<R, F>(A.P, e, key, (uint32_t)e.episode, (uint32_t)e.steps, HLYNR_BLK_EVADE, e.mpx, e.mpy, e.mpz, e.mvx, e.mvy, e.mvz);
-            bar_sync64<WS_BAR_FULL>(m);
-            const Vec4<R> p0 = X.r0[lane], p1 = X.r1[lane];
-            e.ipx = p0.x; e.ipy = p0.y; e.ipz = p0.z; e.fuel = p0.w;
-            e.ivx = p1.x; e.ivy = p1.y; e.ivz = p1.z; e.fuel_used = p1.w;
-            ObsShared sh{X.fwd[0][lane], X.fwd[1][lane], X.fwd[2][lane], X.link[lane], X.euler[0][lane], X.euler[1][lane], X.euler[2][lane]};
-            uint4 ur = make_uint4(0u, X.ury[lane], X.urz[lane], 0u);
-            TickOut t;
-            t.clamped = X.clamped[lane] != 0u;
-            tick_outcome<R, F>(A, e, 0.f, R(0), VolleyOut{false, false, false}, t);
-            if (active && !((t.terminated || t.truncated) && A.auto_reset)) {   // interceptor planes of the envs that go on (reset envs: pass 1)
-                s.r[0][i] = p0; s.r[1][i] = p1;
-                if (FT::thrust_dyn(A.P) || FT::dr(A.P)) s.r[6][i] = X.r6[lane];
-                s.f[0][i] = X.f0[lane]; s.f[1][i] = X.f1[lane];
-            }
-            if (tile + HLYNR_WS_NM * G < ntiles) bar_arrive64<WS_BAR_EMPTY>(m);   // the slot is free for this warp's next tile
-            bool need_reset = false;
-#pragma unroll   // two copies of observe(): with one copy in a rolled loop ptxas needs 40 more registers for this warp role
-            for (int pass = 0; pass < 2; ++pass) {  // pass 1 = in-kernel auto-reset of finished envs
-                if (pass == 1) {
-                    if (!need_reset) break;
-                    e.episode += 1;
-                    ur = spawn(A, e, key, i);
-                    sh = own_obs<R, F>(A, e, ur.w);
-                    if (active) store_env<R, F, ROLE_I>(A, i, e);   // the interceptor planes of a reset env
-                }
-                observe<R, F, ROLE_M>(A, e, key, ur, i, A.g_row, A.o_row, ob, sh);
-                if (pass == 0) {
-                    const bool done = t.terminated || t.truncated;
-                    if (ob.onboard_det) locks += active ? 1 : 0;
-                    if (active) {
-                        A.io.reward[i] = t.reward;
-                        A.io.terminated[i] = t.terminated ? 1 : 0;
-                        if (A.io.done) A.io.done[i] = done ? 1 : 0;
-                        A.io.truncated[i] = t.truncated ? 1 : 0;
-                        if (A.has_info) write_info(A, i, e, t, ob);
-                    }
-                    account_episodes<R>(A, active, done, e, t);
-                    if (done && active && A.io.done_records) {
-                        record_done<R>(A, i, e.steps, e.flags, t.terminated, t.truncated, t.intercepted, t.hit, t.clamped, ob.onboard_det,
-                                       ob.ground_det, t.fuze, t.distance, (float)e.min_d, (float)e.fuel, (float)e.fuel_used, (float)e.ep_ret,
-                                       (float)e.ipx, (float)e.ipy, (float)e.ipz, (float)e.mpx, (float)e.mpy, (float)e.mpz, ob.row);
-                    }
-                    need_reset = done && A.auto_reset;
-                    if (need_reset && active && A.io.terminal_obs) {
-                        if (A.obs_dim == HLYNR_OBS_DIM) copy_obs_row(ob.row, A.io.terminal_obs + i * HLYNR_OBS_DIM);
-                        else copy_obs_row_n(ob.row, A.io.terminal_obs + i * A.obs_dim, A.obs_dim);
-                    }
-                }
-            }
-            if (A.io.obs) {
-                if (A.obs_dim == HLYNR_OBS_DIM) flush_obs_tile(tiles[m], A.io.obs, warp_first, A.lim, lane);
-                else {
-                    __syncwarp();
-                    const int64_t rows = A.lim - warp_first;
-                    if (rows > 0) flush_obs_narrow(tiles[m], A.io.obs + warp_first * A.obs_dim, rows >= 32 ? 32 : (int)rows, A.obs_dim, lane);
-                    __syncwarp();
-                }
-            }
-            if (active) store_env<R, F, ROLE_M>(A, i, e);
-#ifdef WS_ONE_TILE
-            break;
-#endif
-        }
-        {   // onboard-lock ticks: one atomic per warp that saw a lock, spread over the stat slots
-            const int wl = __reduce_add_sync(0xffffffffu, locks);
-            if (lane == 0 && wl) atomicAdd(A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS + 13, (double)wl);
-        }
     }
 }
 

@@ -355,45 +355,3 @@ def test_manual_reset_flow_without_auto_reset(f64):
         assert (sc[k] == so[k]).all(), k
     for k in ("ipos", "ivel", "mpos", "mvel", "fuel"):
         np.testing.assert_allclose(sc[k], so[k], rtol=tol["rtol_state"], atol=tol["rtol_state"] * 10)
-
-
-@pytest.mark.parametrize("base,f64,n", [("cfg4", False, 40000 + 13), ("cfg2", False, 8192), ("cfg3", False, 20000 - 5),
-                                        ("cfg4", True, 12000 + 7), ("cfg3", True, 6000)])
-def test_split_kernel_is_bit_identical(base, f64, n):
-    """Option "split" (step_kernel_split: two warps per 32 envs, the interceptor warp and the missile / sensor warp exchanging through
-    shared memory) against the one-thread-per-env kernel on the same seed and actions: every output of every tick, the episode
-    statistics, the compact done records and the exported env state bit for bit -- early in the episode and at the steady state
-    with auto-resets in every tick (episodes aged by a fused 1700-tick rollout), ragged last tile included."""
-    import torch
-
-    P, cur = config.resolve_config(config.baseline_config(base), warn_dead=False)
-    a = CudaBatch(P, cur, n, seed=777, float64=f64).sim
-    b = CudaBatch(P, cur, n, seed=777, float64=f64).sim
-    b.set_option("split", 1)
-    assert torch.equal(a.reset(), b.reset())
-    g = torch.Generator(device="cuda")
-    g.manual_seed(5)
-    resets = 0
-    for phase, ticks in (("early", 40), ("steady", 160)):
-        if phase == "steady":
-            a.rollout(1700, None, want_obs=False)
-            b.rollout(1700, None, want_obs=False)
-        for t in range(ticks):
-            act = (torch.rand(n, 6, device="cuda", generator=g) * 2.4 - 1.2).contiguous()   # some outside [-1, 1]: SafetyClamp paths
-            oa = a.step(act, want_info=True)
-            ob = b.step(act, want_info=True)
-            for x, y, name in zip(oa[:4], ob[:4], ("obs", "reward", "terminated", "truncated")):
-                assert torch.equal(x, y), (phase, t, name, (x != y).nonzero()[:4].tolist())
-            done = (oa[2] | oa[3]).bool()
-            resets += int(done.sum())
-            assert torch.equal(oa[4][done], ob[4][done]), (phase, t, "terminal_obs")
-            for k in oa[5]:
-                assert torch.equal(oa[5][k], ob[5][k]), (phase, t, k)
-    assert resets > 0
-    sa, sb = a.export_state(), b.export_state()
-    for k in sa:
-        assert np.array_equal(sa[k], sb[k], equal_nan=True), k
-    st_a, st_b = a.stats(), b.stats()   # double sums of atomics: the order of the additions is not fixed
-    for k in st_a:
-        assert np.isclose(st_a[k], st_b[k], rtol=1e-9, atol=0), (k, st_a[k], st_b[k])
-    assert st_a["episodes"] == st_b["episodes"] and st_a["episodes"] > 0
