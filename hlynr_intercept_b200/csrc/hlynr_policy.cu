@@ -7,13 +7,13 @@
 //
 // One persistent CTA per SM walks over 128-row tiles.  Per tile the activations never leave the SM:
 //
-//   warps 0-7  (256 threads)  load x (fp32 -> bf16) into the A-operand region of shared memory; after every GEMM read the fp32
+//   warps 0-15 (512 threads)  load x (fp32 -> bf16) into the A-operand region of shared memory; after every GEMM read the fp32
 //                             accumulators from TMEM (tcgen05.ld, thread = row), add the bias, LayerNorm + ReLU in fp32, and
 //                             write the bf16 result back into the A region in the canonical 128B-swizzled K-major layout the
 //                             next GEMM reads; after the head GEMM they add the head biases, sample the action and store
-//   warp  8    (1 thread)     TMA producer: streams the weight tiles [256 rows x 64 K] bf16 (32 KiB, SWIZZLE_128B) of all four
+//   warp  16   (1 thread)     TMA producer: streams the weight tiles [256 rows x 64 K] bf16 (32 KiB, SWIZZLE_128B) of all four
 //                             GEMMs through a 3-stage shared-memory ring (cp.async.bulk.tensor.2d, mbarrier complete_tx)
-//   warp  9    (1 thread)     MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M = 128, N = 256 (16 for the heads), K = 16 per
+//   warp  17   (1 thread)     MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M = 128, N = 256 (16 for the heads), K = 16 per
 //                             instruction, fp32 accumulators in TMEM (512 columns); tcgen05.commit frees ring stages and
 //                             signals "accumulators ready"
 //
@@ -51,7 +51,12 @@ constexpr int STAGES = 3;
 constexpr int KBLOCK_BYTES = BM * BK * 2;            // 16 KiB: one K block of the A operand
 constexpr int A_BYTES = BM * 512 * 2;                // 128 KiB: x (2 K blocks), then H1 / H2 (8), then H3 (4)
 constexpr int STAGE_BYTES = BN * BK * 2;             // 32 KiB
-constexpr int EPI_WARPS = 8, EPI_THREADS = EPI_WARPS * 32;
+#ifndef HLYNR_POLICY_EPI_WARPS
+#define HLYNR_POLICY_EPI_WARPS 16   /* measured on B200 at 131072 rows: 8 warps 219 us, 16 warps 203 us (profiles/r02_h_policy_epilogue_warps.log) */
+#endif
+constexpr int EPI_WARPS = HLYNR_POLICY_EPI_WARPS, EPI_THREADS = EPI_WARPS * 32;   // 8 or 16: PARTS warps share a TMEM lane quarter
+constexpr int PARTS = EPI_WARPS / 4;                                              // ... and split the columns of a layer PARTS ways
+static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "two or four column parts per lane quarter");
 constexpr int THREADS = EPI_THREADS + 64;
 constexpr int OFF_RING = A_BYTES;
 constexpr int OFF_STATS = OFF_RING + STAGES * STAGE_BYTES;      // float2[2][128]
@@ -229,6 +234,14 @@ __device__ __forceinline__ void stats_chunk(const uint32_t (&v)[32], const float
         ss2 = fma2(x0, x0, fma2(x1, x1, ss2));
     }
 }
+__device__ __forceinline__ void stats_chunk16(const uint32_t (&v)[16], const float4 (&b)[4], uint64_t& s2, uint64_t& ss2) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint64_t x0 = add2(pk2u(v[4 * j], v[4 * j + 1]), pk2(b[j].x, b[j].y)), x1 = add2(pk2u(v[4 * j + 2], v[4 * j + 3]), pk2(b[j].z, b[j].w));
+        s2 = add2(s2, add2(x0, x1));
+        ss2 = fma2(x0, x0, fma2(x1, x1, ss2));
+    }
+}
 // one 16-column chunk of pass 2: y = ((v + b) * rstd - mean * rstd) * gamma + beta, ReLU fused into the bf16 conversion, two
 // 16-byte chunks of the swizzled K-major A operand
 __device__ __forceinline__ void norm_chunk(const uint32_t (&v)[16], const float4 (&b)[4], const float4 (&g)[4], const float4 (&be)[4],
@@ -254,11 +267,11 @@ template <int N>
 __device__ __forceinline__ void layer_epilogue(uint32_t lane_addr, uint32_t a_base, float2 (*stats)[BM], int row, int half,
                                                const float* __restrict__ bias, const float* __restrict__ gamma,
                                                const float* __restrict__ beta, float eps) {
-    constexpr int HALF = N / 2;
+    constexpr int HALF = N / PARTS;   // columns of this warp
     static_assert(HALF % 64 == 0, "two 32-column chunks per iteration");
     const int cbeg = half * HALF;
     uint64_t s2 = pk2(0.f, 0.f), ss2 = pk2(0.f, 0.f);
-    {
+    if constexpr (PARTS == 2) {
         uint32_t va[32], vb[32];
         tmem_ld32(lane_addr + (uint32_t)cbeg, va);
 #pragma unroll 1
@@ -275,15 +288,45 @@ __device__ __forceinline__ void layer_epilogue(uint32_t lane_addr, uint32_t a_ba
             if (c0 + 64 < cbeg + HALF) tmem_ld32(lane_addr + (uint32_t)(c0 + 64), va);
             stats_chunk(vb, b, s2, ss2);
         }
+    } else {   // 18 warps share the register file (96 per thread): 16-column chunks
+        uint32_t va[16], vb[16];
+        tmem_ld16(lane_addr + (uint32_t)cbeg, va);
+#pragma unroll 1
+        for (int c0 = cbeg; c0 < cbeg + HALF; c0 += 32) {
+            float4 b[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+            tmem_wait_ld16(va);
+            tmem_ld16(lane_addr + (uint32_t)(c0 + 16), vb);
+            stats_chunk16(va, b, s2, ss2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = __ldg(reinterpret_cast<const float4*>(bias + c0 + 16) + j);
+            tmem_wait_ld16(vb);
+            if (c0 + 32 < cbeg + HALF) tmem_ld16(lane_addr + (uint32_t)(c0 + 32), va);
+            stats_chunk16(vb, b, s2, ss2);
+        }
     }
     float s_lo, s_hi, q_lo, q_hi;
     upk2(s2, s_lo, s_hi); upk2(ss2, q_lo, q_hi);
     const float s = s_lo + s_hi, ss = q_lo + q_hi;
-    stats[half][row] = make_float2(s, ss);
-    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // the two halves of every row have published their sums
-    const float2 o = stats[half ^ 1][row];
-    const float mean = (s + o.x) * (1.0f / N);
-    const float var = fmaxf((ss + o.y) * (1.0f / N) - mean * mean, 0.f);   // biased variance, as nn.LayerNorm
+    float mean, var;
+    if (PARTS == 2) {
+        stats[half][row] = make_float2(s, ss);
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // the two halves of every row have published their sums
+        const float2 o = stats[half ^ 1][row];
+        mean = (s + o.x) * (1.0f / N);
+        var = fmaxf((ss + o.y) * (1.0f / N) - mean * mean, 0.f);   // biased variance, as nn.LayerNorm
+    } else {
+        // four parts through the same 2 KiB (224 of the 227 KiB are operands and weight ring): parts 2, 3 hand their sums to parts
+        // 0, 1, which publish the pair sums; everybody adds the two pair sums in the same order
+        if (half >= 2) stats[half - 2][row] = make_float2(s, ss);
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        if (half < 2) { const float2 o = stats[half][row]; stats[half][row] = make_float2(s + o.x, ss + o.y); }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        const float2 p0 = stats[0][row], p1 = stats[1][row];
+        mean = (p0.x + p1.x) * (1.0f / N);
+        var = fmaxf((p0.y + p1.y) * (1.0f / N) - mean * mean, 0.f);
+    }   // (the next layer's writes come after a_ready / acc_ready, which every epilogue thread passes first)
     const float rstd = rsqrtf(var + eps);
     const uint64_t rstd2 = pk2(rstd, rstd), shift2 = pk2(-mean * rstd, -mean * rstd);
     {
@@ -319,7 +362,7 @@ __device__ __forceinline__ void layer_epilogue(uint32_t lane_addr, uint32_t a_ba
 // traffic (904 KiB per 128-row tile, the kernel's bottleneck at CL = 1) is divided by CL.  A stage may be refilled only after the
 // MMAs of ALL CTAs have read it: the empty barriers count CL arrivals, delivered by multicast tcgen05.commit.
 template <int CL>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 1)   // (ptxas caps the registers per SM sub-partition: 3 of 10 warps x 168, 5 of 18 warps x 96)
 policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                       const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tm3, const Params P) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -348,7 +391,7 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_cons
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 9) {   // TMEM: all 512 columns (one CTA per SM by its shared-memory footprint)
+    if (warp == EPI_WARPS + 1) {   // TMEM: all 512 columns (one CTA per SM by its shared-memory footprint)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + OFF_TMEM), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -358,7 +401,7 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == EPI_WARPS) {
         // ===== TMA producer =====
         if (lane == 0) {
             const CUtensorMap* maps[N_LAYERS] = {&tm0, &tm1, &tm2, &tm3};
@@ -381,7 +424,7 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_cons
             }
         }
         __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == EPI_WARPS + 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0, pa = 0;
@@ -499,7 +542,7 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_cons
     tc_fence_before();
     if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into its shared memory or arrive on its barriers
     else __syncthreads();
-    if (warp == 9) {
+    if (warp == EPI_WARPS + 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }

@@ -46,7 +46,7 @@ def test_gpu_arm_line():
     assert d["cpu_baseline"]["kind"] == "port"
     # the timed region runs at the steady state: finished episodes and in-kernel auto-resets inside it
     assert d["episode_stats"]["episodes"] > 0 and d["done_episodes_per_step"] > 100
-    assert r["layout_bytes_per_env_step"] == 582 and 0 < r["frac_layout"] < r["frac"]
+    assert r["layout_bytes_per_env_step"] == 550 and 0 < r["frac_layout"] < r["frac"]
     assert d["strong"]["total_envs"] == 1 << 20
     for k in ("cfg2@4096", "cfg3@262144"):
         c = d["configs"][k]

@@ -355,3 +355,48 @@ def test_manual_reset_flow_without_auto_reset(f64):
         assert (sc[k] == so[k]).all(), k
     for k in ("ipos", "ivel", "mpos", "mvel", "fuel"):
         np.testing.assert_allclose(sc[k], so[k], rtol=tol["rtol_state"], atol=tol["rtol_state"] * 10)
+
+
+def test_compact_layout_is_bit_identical(monkeypatch):
+    """The compact 10-plane layout of the cfg4 feature set (fp32 build: the counters ride in the constant words r6.w / f1.w and
+    the i0 plane is never touched, hlynr_device.cuh load_env) against the 11-plane layout (HLYNR_NO_COMPACT=1 at create time) on
+    the same seed and actions: every output of every tick, the info arrays, the terminal observations and the exported env
+    state bit for bit -- early in the episode and at the steady state with auto-resets in every tick, ragged last tile included;
+    plus an export -> import round trip into a fresh compact handle."""
+    import torch
+
+    P, cur = config.resolve_config(config.baseline_config("cfg4"), warn_dead=False)
+    n = 30000 + 13
+    a = CudaBatch(P, cur, n, seed=777).sim
+    monkeypatch.setenv("HLYNR_NO_COMPACT", "1")
+    b = CudaBatch(P, cur, n, seed=777).sim
+    monkeypatch.delenv("HLYNR_NO_COMPACT")
+    assert torch.equal(a.reset(), b.reset())
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    resets = 0
+    for phase, ticks in (("early", 30), ("steady", 120)):
+        if phase == "steady":
+            a.rollout(1700, None, want_obs=False)
+            b.rollout(1700, None, want_obs=False)
+        for t in range(ticks):
+            act = (torch.rand(n, 6, device="cuda", generator=g) * 2.4 - 1.2).contiguous()
+            oa = a.step(act, want_info=True)
+            ob = b.step(act, want_info=True)
+            for x, y, name in zip(oa[:4], ob[:4], ("obs", "reward", "terminated", "truncated")):
+                assert torch.equal(x, y), (phase, t, name)
+            done = (oa[2] | oa[3]).bool()
+            resets += int(done.sum())
+            assert torch.equal(oa[4][done], ob[4][done]), (phase, t, "terminal_obs")
+            for k in oa[5]:
+                assert torch.equal(oa[5][k], ob[5][k]), (phase, t, k)
+    assert resets > 0
+    sa, sb = a.export_state(), b.export_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k], equal_nan=True), k
+    c = CudaBatch(P, cur, n, seed=777).sim   # a fresh compact handle continues from the exported state exactly
+    c.reset()
+    c.import_state(sa)
+    sc = c.export_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sc[k], equal_nan=True), k
