@@ -1768,9 +1768,18 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
     // its writes are visible -- nothing above touches global memory.  Both are no-ops in an ordinary launch.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    prefetch_ring_reads<R, F>(A, i, A.g_row, A.o_row);
     Env<R> e;
     load_env<R, F>(A, ii, e);
+    // Issue order of the prologue: every demand load (planes, actions) first, THEN the prefetches.  A prefetch (CCTL.E.PF1 / PF2) keeps
+    // its address registers on the scoreboard until it completes; with the ring prefetches ahead of the loads, the third action load
+    // reused such a register and waited a full memory latency (6 % of all stall samples in profiles/r02_i_step_kernel_*), holding back
+    // the eight plane loads queued behind it.  Loads first: -0.9 us per launch on every configuration (profiles/r02_j_*).
+    float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
+    if (!kRollout) {
+        const float2* ap = reinterpret_cast<const float2*>(A.io.actions + ii * HLYNR_ACT_DIM);
+        a0 = __ldg(ap); a1 = __ldg(ap + 1); a2 = __ldg(ap + 2);
+    }
+    prefetch_ring_reads<R, F>(A, i, A.g_row, A.o_row);
     if (!kRollout && A.prefetch_ahead > 0 && i + A.prefetch_ahead < A.lim) prefetch_next_wave<R, F>(A, i + A.prefetch_ahead);
     const RngKey key = make_key(A, A.env_offset + ii);
     if (!kRollout && Feat<F>::onboard_delay(A.P) && Feat<F>::dr(A.P)) {
@@ -1795,8 +1804,11 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
             act[0] = 2.f * u01(r0.x) - 1.f; act[1] = 2.f * u01(r0.y) - 1.f; act[2] = 2.f * u01(r0.z) - 1.f;
             act[3] = 2.f * u01(r0.w) - 1.f; act[4] = 2.f * u01(r1.x) - 1.f; act[5] = 2.f * u01(r1.y) - 1.f;
         } else {
-            const float2* ap = reinterpret_cast<const float2*>(A.io.actions + ((int64_t)s * A.n + ii) * HLYNR_ACT_DIM);
-            float2 p0 = __ldg(ap), p1 = __ldg(ap + 1), p2 = __ldg(ap + 2);
+            float2 p0 = a0, p1 = a1, p2 = a2;   // API mode: loaded in the prologue
+            if (kRollout) {
+                const float2* ap = reinterpret_cast<const float2*>(A.io.actions + ((int64_t)s * A.n + ii) * HLYNR_ACT_DIM);
+                p0 = __ldg(ap); p1 = __ldg(ap + 1); p2 = __ldg(ap + 2);
+            }
             act[0] = p0.x; act[1] = p0.y; act[2] = p1.x; act[3] = p1.y; act[4] = p2.x; act[5] = p2.y;
         }
         TickOut t;
