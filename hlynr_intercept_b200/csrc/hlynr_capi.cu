@@ -538,7 +538,7 @@ int hlynr_create(const HlynrParams* p, int64_t n_envs, int device, uint64_t seed
     if (!s) return fail("hlynr_create: out of host memory");
     s->params = *p;
     s->cur = HlynrCurriculum{200.0, 60.0, 1.0, 1.0};
-    s->n = n_envs; s->n_pad = (n_envs + 127) & ~int64_t(127);  // whole 128-env tiles (TMA kernel)
+    s->n = n_envs; s->n_pad = (n_envs + 127) & ~int64_t(127);  // whole 128-env tiles
     s->device = device; s->precision = precision; s->seed = seed; s->env_offset = env_id_offset;
     KParams<float> kp = make_kparams<float>(*p);
     const int gl = kp.gnd_ring_len, ol = kp.onb_ring_len;
