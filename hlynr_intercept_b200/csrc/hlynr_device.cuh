@@ -1726,6 +1726,13 @@ template <typename R, int F> HD void prefetch_next_wave(const KernelArgs<R>& A, 
     if (!compact_layout(A)) prefetch_l2(s.i0 + j);
     if (A.io.actions) prefetch_l2(A.io.actions + j * HLYNR_ACT_DIM);
 }
+#ifndef HLYNR_RING_PF
+#define HLYNR_RING_PF 1   /* 0 = no prefetch of the delayed ring rows, 1 = prefetch.global.L1, 2 = prefetch.global.L2 */
+#endif
+HD void prefetch_ring(const void* p) {
+    if (HLYNR_RING_PF == 1) prefetch_l1(p);
+    else if (HLYNR_RING_PF == 2) prefetch_l2(p);
+}
 template <typename R, int F> HD void prefetch_ring_reads(const KernelArgs<R>& A, int64_t i, int g_row, int o_row) {
     typedef Feat<F> FT;
     const KParams<R>& P = A.P;
@@ -1733,13 +1740,13 @@ template <typename R, int F> HD void prefetch_ring_reads(const KernelArgs<R>& A,
     if (FT::onboard_delay(P) && !FT::dr(P)) {
         int rrow = o_row - P.onboard_delay;
         if (rrow < 0) rrow += P.onb_ring_len;
-        prefetch_l1(A.st.oring + (int64_t)rrow * n + i);
+        prefetch_ring(A.st.oring + (int64_t)rrow * n + i);
     }
     if (FT::ground(P) && FT::ground_delay(P)) {
         const int rrow = g_row + 1 == P.gnd_ring_len ? 0 : g_row + 1;
         const Vec4<R>* rr = A.st.gring + (int64_t)rrow * 2 * n;
-        prefetch_l1(rr + i);
-        prefetch_l1(rr + n + i);
+        prefetch_ring(rr + i);
+        prefetch_ring(rr + n + i);
     }
 }
 
