@@ -595,6 +595,16 @@ int hlynr_set_option(hlynr_t* s, const char* name, int64_t value) {
         return 0;
     }
     if (strcmp(name, "pdl") == 0) { s->pdl = value != 0; return 0; }
+    if (strcmp(name, "host_chunk_growth") == 0) {
+        if (value < 0 || value > 64) return fail("host_chunk_growth must be in [0, 64] (eighths: 16 = chunks double, 0 = uniform chunks)");
+        s->host_chunk_growth = (int)value;
+        return 0;
+    }
+    if (strcmp(name, "host_threads") == 0) {
+        if (value < 0 || value > 64) return fail("host_threads must be in [0, 64]");
+        s->host_threads = (int)value;
+        return s->hio.ready ? make_pool(s) : 0;
+    }
     return fail("hlynr_set_option: unknown option '%s'", name);
 }
 static int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }

@@ -432,3 +432,18 @@ def test_step_graph_replays_bit_identically():
         with pytest.raises(_lib.HlynrError):
             sg.replay()
         a.close(); b.close()
+
+
+@pytest.mark.gpu
+def test_every_documented_option_is_accepted():
+    """hlynr_set_option knows every option name the headers, tools and docs use (a clean-up once dropped two of them silently)."""
+    from hlynr_intercept_b200 import config
+    from hlynr_intercept_b200.sim import HlynrSim
+
+    sim = HlynrSim(config.baseline_config("cfg4"), n_envs=256, warn_dead=False)
+    for name, value in (("specialise", 1), ("host_info", 1), ("prefetch_waves", 1), ("obs_dim", 26), ("host_chunks", 0), ("pdl", 1),
+                        ("host_chunk_growth", 12), ("host_threads", 0)):
+        sim.set_option(name, value)
+    with pytest.raises(Exception):
+        sim.set_option("no_such_option", 1)
+    sim.close()
