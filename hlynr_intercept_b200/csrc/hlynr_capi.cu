@@ -411,6 +411,17 @@ template <typename R> static void set_tick(KernelArgs<R>& A, uint64_t tick) {
     A.tick = (uint32_t)tick;
     A.g_row = A.P.gnd_ring_len > 0 ? (int32_t)(tick % (uint64_t)A.P.gnd_ring_len) : 0;
     A.o_row = A.P.onb_ring_len > 0 ? (int32_t)(tick % (uint64_t)A.P.onb_ring_len) : 0;
+    // the rows an API-mode tick reads (prefetched in the kernel prologue); they are valid row addresses even while a ring still fills
+    A.pf_o = nullptr; A.pf_g = nullptr;
+    if (A.P.onb_ring_len > 0 && !A.P.dr) {
+        int rrow = A.o_row - A.P.onboard_delay;
+        if (rrow < 0) rrow += A.P.onb_ring_len;
+        A.pf_o = A.st.oring + (int64_t)rrow * A.ring_stride;
+    }
+    if (A.P.gnd_ring_len > 0) {
+        const int rrow = A.g_row + 1 == A.P.gnd_ring_len ? 0 : A.g_row + 1;
+        A.pf_g = A.st.gring + (int64_t)rrow * 2 * A.ring_stride;
+    }
 }
 template <typename R> static KernelArgs<R> base_args(hlynr_sim* s, const StatePlanes<R>& planes) {
     KernelArgs<R> A;

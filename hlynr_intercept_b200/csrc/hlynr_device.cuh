@@ -301,6 +301,11 @@ template <typename R> struct KernelArgs {
     KParams<R> P;
     KCurriculum<R> C;
     StatePlanes<R> st;
+    // Delayed ring rows this tick READS (API-mode launches; set with the tick on the host, next to the plane pointers so the
+    // prologue gets them with the same constant-bank lines): the row written `onboard_delay` ticks ago, the two planes of the oldest
+    // ground row.  NULL = no such ring (or a per-env delay: domain randomization).
+    const float4* pf_o;
+    const Vec4<R>* pf_g;
     StepIO io;
     RoundKeys rk;
     int64_t n;
@@ -1733,6 +1738,14 @@ HD void prefetch_ring(const void* p) {
     if (HLYNR_RING_PF == 1) prefetch_l1(p);
     else if (HLYNR_RING_PF == 2) prefetch_l2(p);
 }
+// API-mode prologue: the row addresses come ready-made from the host.  Computing them here (o_row - P.onboard_delay, ring lengths)
+// put two more constant-bank lines on the path in front of the demand loads: with the loads-first order of the prologue the stall
+// of profiles/r02_k_* simply moved to the uniform subtraction that waited for them (6.5 % of the samples; worth 0.3 us per launch).
+template <typename R, int F> HD void prefetch_ring_reads_api(const KernelArgs<R>& A, int64_t i) {
+    typedef Feat<F> FT;
+    if (FT::onboard_delay(A.P) && !FT::dr(A.P)) prefetch_ring(A.pf_o + i);
+    if (FT::ground(A.P) && FT::ground_delay(A.P)) { prefetch_ring(A.pf_g + i); prefetch_ring(A.pf_g + A.ring_stride + i); }
+}
 template <typename R, int F> HD void prefetch_ring_reads(const KernelArgs<R>& A, int64_t i, int g_row, int o_row) {
     typedef Feat<F> FT;
     const KParams<R>& P = A.P;
@@ -1786,7 +1799,8 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
         const float2* ap = reinterpret_cast<const float2*>(A.io.actions + ii * HLYNR_ACT_DIM);
         a0 = __ldg(ap); a1 = __ldg(ap + 1); a2 = __ldg(ap + 2);
     }
-    prefetch_ring_reads<R, F>(A, i, A.g_row, A.o_row);
+    if (kRollout) prefetch_ring_reads<R, F>(A, i, A.g_row, A.o_row);
+    else prefetch_ring_reads_api<R, F>(A, i);
     if (!kRollout && A.prefetch_ahead > 0 && i + A.prefetch_ahead < A.lim) prefetch_next_wave<R, F>(A, i + A.prefetch_ahead);
     const RngKey key = make_key(A, A.env_offset + ii);
     if (!kRollout && Feat<F>::onboard_delay(A.P) && Feat<F>::dr(A.P)) {
