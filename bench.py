@@ -76,6 +76,22 @@ def measured_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def policy_roofline(flop, us):
+    """The fused policy forward against the measured dense bf16 throughput of this pool's B200s (cuBLAS 8192^3, MEASURED_PEAKS.json:
+    the burst figure, the kernel is timed alone); the nominal 2250 TFLOP/s if the file is absent."""
+    peak, src = 2250.0, "nominal dense bf16"
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            peak, src = float(json.load(open(p))["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops)"
+        except Exception:
+            pass
+    ach = flop / (us * 1e-6) / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": src,
+            "note": "per 128-row tile the GEMM phases run at tensor-pipe speed (9.9 us) and do not overlap the LayerNorm epilogues (16.2 us): "
+                    "one tile's accumulators fill the 512 TMEM columns (DESIGN.md section 12)"}
+
+
 class ClockSampler:
     """Samples nvidia-smi SM clocks / throttle reasons during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -307,6 +323,22 @@ def config_line(ctx, workload, n, K, W, precision, peak):
     sim, pool = make_aged_sim(ctx, workload, n, 0, precision, seed=777)
     r = timed_ticks(ctx, sim, pool, K, W, collective=False)
     rg = timed_ticks(ctx, sim, pool, K, W, collective=False, graph=True)
+    # the same ticks as ONE launch per 48 (hlynr_rollout with caller actions [k, N, 6]: state in registers, one observation at the
+    # end): what a caller that knows its actions in advance -- the only case a step graph can serve too -- pays per tick
+    import torch
+    kf = 48
+    acts = (torch.rand(kf, n, 6, device=sim.device) * 2 - 1).contiguous()
+    sim.rollout(kf, acts)
+    torch.cuda.synchronize(sim.device)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(2, min(10, K // kf))
+    f0.record()
+    for _ in range(reps):
+        sim.rollout(kf, acts)
+    f1.record()
+    torch.cuda.synchronize(sim.device)
+    us_f = f0.elapsed_time(f1) / (reps * kf) * 1e3
+    del acts
     sim.close()
     us, us_g = r["ms"] / K * 1e3, rg["ms"] / K * 1e3
     best = min(us, us_g)
@@ -314,6 +346,7 @@ def config_line(ctx, workload, n, K, W, precision, peak):
     ws_mb = n * lb / 1e6
     return {"workload": workload_name(workload), "envs": n, "steps": K, "us_per_tick_eager": us, "us_per_tick_graph": us_g,
             "graph_ticks_per_replay": rg["graph_ticks"], "host_issue_us_per_tick_eager": r["host_issue_ms"] / K * 1e3,
+            "us_per_tick_fused_rollout": us_f, "fused_ticks_per_launch": kf,
             "value": n / (best * 1e-6), "unit": "env-steps/s", "done_episodes_per_step": r["stats"][0] / K,
             "roofline_frac_contract": n * ALGO_BYTES[workload] / (best * 1e-6) / 1e9 / peak,
             "roofline_frac_layout": n * lb / (best * 1e-6) / 1e9 / peak,
@@ -651,6 +684,7 @@ def rollout_leg(ctx, args, env_cfg):
                       "heads + Gaussian sampling in ONE kernel)",
             "cuda_graph": bool(graphed), "eager": rate(te_), "us_per_step": tr_ / T * 1e3,
             "policy_forward_us": fwd_us, "policy_forward_tflops": flop / (fwd_us * 1e-6) / 1e12,
+            "policy_roofline": policy_roofline(flop, fwd_us),
             "with_torch_policy_tf32": rate(ttr_), "with_torch_policy_tf32_eager": rate(tte_),
             "without_policy_network": rate(tn_),
             "timeout_bootstrap_overflow": int(col.overflow.item()),
