@@ -353,6 +353,9 @@ template <typename R> struct Env {
 // never touched: 10 planes (160 B read + 160 B written per env-step) instead of 11.
 //   r6.w = bits(steps | worsen << 16)          f1.w = bits(episode (25 bits, signed) | flags7 << 25)
 //   flags7 = crossed | kf_init << 1 | kf_f64 << 2 | onboard delay << 3   (the volley fields of the flag word do not exist here)
+// Limits that follow: steps and the worsening counter stay below 65536 (hlynr_create checks max_steps), the episode counter of an
+// env wraps after 2^25 episodes (~3e10 ticks of one env; it only keys the Philox streams), and hlynr_import_state cannot set T0 /
+// base Cd to anything but the constants the configuration implies (they are not state here).
 HD int word_bits(float x) { return __float_as_int(x); }
 HD int word_bits(double) { return 0; }
 HD float bits_word(int x, float) { return __int_as_float(x); }
