@@ -1883,6 +1883,12 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
             if (s + 1 < steps) prefetch_ring_reads<R, F>(A, i, g_row, o_row);
         }
     }
+    {   // onboard-lock ticks: one atomic per warp that saw a lock, spread over the stat slots.  Ahead of the output stores: placed
+        // after them, the thread-index re-read it needs landed in a register the in-flight observation stores still held as their
+        // address, and waited for them (3.4 % of the fp64 build's stall samples, profiles/r02_k_*)
+        const int wl = __reduce_add_sync(0xffffffffu, active ? locks : 0);
+        if (lane == 0 && wl) atomicAdd(A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS + 13, (double)wl);
+    }
     if (A.io.obs) {
         if (A.obs_dim == HLYNR_OBS_DIM) flush_obs_tile(tiles[warp], A.io.obs, warp_first, A.lim, lane);
         else {
@@ -1897,10 +1903,6 @@ step_kernel(const __grid_constant__ KernelArgs<R> A) {
         if (A.io.done_count) A.io.done_count[i] = dcount;
     }
     if (active) store_env<R, F>(A, i, e);
-    {   // onboard-lock ticks: one atomic per warp that saw a lock, spread over the stat slots
-        const int wl = __reduce_add_sync(0xffffffffu, active ? locks : 0);
-        if (lane == 0 && wl) atomicAdd(A.io.stats + (size_t)(blockIdx.x % HLYNR_STAT_SLOTS) * HLYNR_STATS_WORDS + 13, (double)wl);
-    }
 }
 
 // reset(): environment.py:353.  mask == NULL resets every env.
