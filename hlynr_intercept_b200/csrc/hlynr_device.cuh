@@ -735,6 +735,22 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
     float link = 0.f;
     if (FT::ground(P)) link = datalink_quality(P, ipx, ipy, ipz, ivx, ivy, ivz, ur.w);
 
+    // fp32 build, world frame: the channels that depend on the interceptor alone (own velocity, euler angles, fuel) are emitted
+    // HERE, between the issue of the delayed ring loads and the first use of their samples (fusion, Kalman filter): ~100 independent
+    // instructions behind which part of that latency hides (-0.9 ... -1.2 us per launch on cfg2 / cfg3 / cfg4; the fp64 build, bound by
+    // instruction fetch, loses 3.7 us with the same move and keeps them at the end; profiles/r02_l_own_channels_ab.log)
+    constexpr bool kOwnEarly = std::is_same<R, float>::value;
+    if (kOwnEarly && FT::obs_mode(P) == HLYNR_OBS_WORLD) {
+        out.put(6, clip(ivx * P.rc_max_velocity_f, -1.f, 1.f));
+        out.put(7, clip(ivy * P.rc_max_velocity_f, -1.f, 1.f));
+        out.put(8, clip(ivz * P.rc_max_velocity_f, -1.f, 1.f));
+        if (out.emit) {
+            float roll, pitch, yaw;
+            euler_over_pi(e.qw, e.qx, e.qy, e.qz, &roll, &pitch, &yaw);
+            out.put(9, roll); out.put(10, pitch); out.put(11, yaw);
+        }
+        out.put(12, clip((float)e.fuel * 0.01f, 0.f, 1.f));
+    }
     // === fusion confidence, core.py:476-509 ===
     float fus;
     if (!o_det && !dg_det) fus = 0.f;
@@ -937,18 +953,18 @@ HD void observe(const KernelArgs<R>& A, Env<R>& e, const RngKey& key, const uint
         out.put(6, clip(ndot3(ivx, ivy, ivz, fx, fy, fz) * P.rc_max_velocity_f, -1.f, 1.f));
         out.put(7, clip(ndot3(ivx, ivy, ivz, bx.rx, bx.ry, bx.rz) * P.rc_max_velocity_f, -1.f, 1.f));
         out.put(8, clip(ndot3(ivx, ivy, ivz, bx.ux, bx.uy, bx.uz) * P.rc_max_velocity_f, -1.f, 1.f));
-    } else {
+    } else if (!kOwnEarly) {
     out.put(6, clip(ivx * P.rc_max_velocity_f, -1.f, 1.f));
     out.put(7, clip(ivy * P.rc_max_velocity_f, -1.f, 1.f));
     out.put(8, clip(ivz * P.rc_max_velocity_f, -1.f, 1.f));
     }
     if (mode != HLYNR_OBS_WORLD) { out.put(9, 0.f); out.put(10, 0.f); out.put(11, 0.f); }  // core.py:966-970
-    else if (out.emit) {
+    else if (!kOwnEarly && out.emit) {
         float roll, pitch, yaw;
         euler_over_pi(e.qw, e.qx, e.qy, e.qz, &roll, &pitch, &yaw);
         out.put(9, roll); out.put(10, pitch); out.put(11, yaw);
     }
-    out.put(12, clip((float)e.fuel * 0.01f, 0.f, 1.f));
+    if (!kOwnEarly || mode != HLYNR_OBS_WORLD) out.put(12, clip((float)e.fuel * 0.01f, 0.f, 1.f));
     if (dg_det && link > 0.1f && mode == HLYNR_OBS_LOS) {  // core.py:985-1006: redundant range / rate measurements
         const W gr = nnorm3(dgx, dgy, dgz);
         const W gc = -ndot3(dgx, dgy, dgz, dvx, dvy, dvz) * nrcp(gr + W(1e-6));
