@@ -1,0 +1,11 @@
+# policy epilogue: single TMEM pass with an fp16 register stash (variants) against two TMEM passes (main)
+set -x
+mkdir -p gpurun_out
+V=$PWD/hlynr_intercept_b200/_variants
+rm -f gpurun_out/policy_stash_ab.log
+for lib in "" $V/libhlynr_b200_stash.so $V/libhlynr_b200_stash1.so; do
+  echo "== ${lib:-main}" | tee -a gpurun_out/policy_stash_ab.log
+  HLYNR_B200_LIB=$lib timeout 600 python -m pytest tests/test_policy.py -m gpu -q 2>&1 | tail -3 | tee -a gpurun_out/policy_stash_ab.log
+  HLYNR_B200_LIB=$lib timeout 300 python tools/policy_time.py 2>&1 | grep "n=131072\|n=1048576" | cut -c1-110 | tee -a gpurun_out/policy_stash_ab.log
+  HLYNR_B200_LIB=$lib timeout 300 python tools/policy_phases.py 2>&1 | grep "cluster 1" | tee -a gpurun_out/policy_stash_ab.log
+done
