@@ -360,12 +360,17 @@ HD int word_bits(float x) { return __float_as_int(x); }
 HD int word_bits(double) { return 0; }
 HD float bits_word(int x, float) { return __int_as_float(x); }
 HD double bits_word(int, double) { return 0.0; }
-template <typename R> HD bool compact_layout(const KernelArgs<R>& A) { return std::is_same<R, float>::value && A.compact != 0; }
+// F = the kernel's feature set: only FT_V2ON (and the generic kernels, which serve every handle) can meet a compact handle, so the
+// other specialised instantiations carry no trace of it
+template <typename R, int F = FT_GENERIC> HD bool compact_layout(const KernelArgs<R>& A) {
+    if constexpr (!std::is_same<R, float>::value || F == FT_V2OFF || F == FT_V2ON_DR) return false;
+    else return A.compact != 0;
+}
 
 template <typename R, int F = FT_GENERIC> HD void load_env(const KernelArgs<R>& A, int64_t i, Env<R>& e) {
     typedef Feat<F> FT;
     const StatePlanes<R>& s = A.st;
-    const bool compact = compact_layout(A);
+    const bool compact = compact_layout<R, F>(A);
     Vec4<R> v;
     float4 f;
     // Issue order = order of first use.  The planes that carry the counters go first: steps / episode key every Philox draw of the
@@ -400,7 +405,7 @@ template <typename R, int F = FT_GENERIC> HD void load_env(const KernelArgs<R>& 
 template <typename R, int F = FT_GENERIC> HD void store_env(const KernelArgs<R>& A, int64_t i, const Env<R>& e) {
     typedef Feat<F> FT;
     const StatePlanes<R>& s = A.st;
-    const bool compact = compact_layout(A);
+    const bool compact = compact_layout<R, F>(A);
     R r6w = e.T0;
     float f1w = e.base_cd;
     if (compact) {
@@ -1762,7 +1767,7 @@ template <typename R, int F> HD void prefetch_next_wave(const KernelArgs<R>& A, 
 #pragma unroll
     for (int k = 0; k < 3; ++k) prefetch_l2(s.f[k] + j);
     if (FT::dr(A.P)) prefetch_l2(s.f[3] + j);
-    if (!compact_layout(A)) prefetch_l2(s.i0 + j);
+    if (!compact_layout<R, F>(A)) prefetch_l2(s.i0 + j);
     if (A.io.actions) prefetch_l2(A.io.actions + j * HLYNR_ACT_DIM);
 }
 #ifndef HLYNR_RING_PF
