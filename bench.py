@@ -253,7 +253,12 @@ class Ctx:
         return float(t.item())
 
 
-AGE_TICKS = 2000   # fused random-policy ticks before the warm-up: every env has finished >= 1 episode (they last 800-1600 ticks)
+# Fused random-policy ticks before the warm-up.  Episodes last 800-1600 ticks and all start together, so the rate of finished episodes
+# (= in-kernel auto-resets) oscillates for several episode lengths before it settles: 0 until tick 750, 1441 per tick at 1500, 349 at
+# 1750, 740 at 2000-2025 (where a 2000-tick ageing put a 20-step timed region: a trough), 1280 at 2500 ... 871-895 from tick 8000 on
+# (tools/done_rate_series.py, profiles/r02_n_done_rate_series.log).  8000 ticks cost 0.6 s and make a 20-step run and a 2000-step run
+# time the same stationary workload.
+AGE_TICKS = 8000
 
 
 def make_aged_sim(ctx, workload, n, first, precision, seed=1234):
