@@ -571,7 +571,7 @@ def e2e_leg(ctx, args, env_cfg, n):
         venv = HlynrVecEnv(env_cfg, n_envs=n, device=ctx.local_rank, seed=99, env_id_offset=rank * n, precision=args.precision,
                            warn_dead=False, lazy_infos=True, obs_dim=obs_dim)
         venv.reset()
-        venv.sim.rollout(1200, None, want_obs=False)  # age the episodes: the timed steps see the steady-state done rate
+        venv.sim.rollout(AGE_TICKS, None, want_obs=False)  # age the episodes: the timed steps see the stationary done rate
         rng = np.random.default_rng(rank)
         host_actions = [rng.uniform(-1, 1, (n, 6)).astype(np.float32) for _ in range(2)]  # ordinary (unpinned) numpy arrays
         for k in range(3):
