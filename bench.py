@@ -47,7 +47,7 @@ def layout_bytes(workload, precision="fp32"):
     v2 = workload in ("cfg1", "cfg3", "cfg3_radar", "cfg4")
     dr = workload in ("cfg3", "cfg3_radar")
     r_planes = 7 if v2 else 6                  # r0-r5 (+ r6 thrust / T0 with thrust lag or DR)
-    f_planes = 3 + (1 if dr else 0)            # quaternion, wind + base Cd, Kalman P block (+ DR peak)
+    f_planes = 3 + (1 if (dr and precision != "fp32") else 0)   # quaternion, wind + base Cd, Kalman P block (+ DR peak: in i0.y in the fp32 build)
     compact = workload == "cfg4" and precision == "fp32"   # counters ride in r6.w / f1.w: no i0 plane (hlynr_device.cuh load_env)
     state = r_planes * 4 * r + f_planes * 16 + (0 if compact else 16)   # + the counter plane i0
     rings = 2 * 4 * r + (16 if v2 else 0)                  # ground slot {rel, q}, {vel, flag}; onboard slot (sensor delay, v2.0)

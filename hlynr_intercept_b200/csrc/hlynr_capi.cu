@@ -296,7 +296,7 @@ static RoundKeys make_round_keys(uint64_t seed) {
 // ------------------------------------------------------------------------------------------------
 // small utility kernels
 // ------------------------------------------------------------------------------------------------
-template <typename R> __global__ void init_kernel(StatePlanes<R> s, int64_t n_pad, float peak, bool compact) {
+template <typename R> __global__ void init_kernel(StatePlanes<R> s, int64_t n_pad, float peak, int compact) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
     Vec4<R> z{R(0), R(0), R(0), R(0)};
@@ -307,7 +307,8 @@ template <typename R> __global__ void init_kernel(StatePlanes<R> s, int64_t n_pa
     s.f[2][i] = make_float4(0.f, 0.f, 1000.f, 1000.f);   // Kalman P_pv, P_vp, P_vv, P_pp
     s.f[3][i] = make_float4(peak, 0.f, 0.f, 0.f);
     s.i0[i] = make_int4(0, 0, 0, -1);  // episode -1: the first reset starts episode 0
-    if (compact) {   // the same counters in the compact layout (hlynr_device.cuh load_env): steps = worsen = 0, episode = -1, flags = 0
+    if (compact == 2) s.i0[i] = make_int4(0, __float_as_int(peak), 0, -1);   // DR-compact: the drag peak rides in i0.y
+    if (compact == 1) {   // the same counters in the compact layout (hlynr_device.cuh load_env): steps = worsen = 0, episode = -1, flags = 0
         s.r[6][i] = Vec4<R>{R(0), R(0), R(0), bits_word(0, R(0))};
         s.f[1][i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x1ffffff));
     }
@@ -568,11 +569,12 @@ int hlynr_create(const HlynrParams* p, int64_t n_envs, int device, uint64_t seed
     if (precision == HLYNR_FP32) {
         carve<float>(s->pf, (char*)s->state_mem, s->n_pad, gl, ol, p->volley_size);
         // compact plane layout (hlynr_device.cuh load_env): fixed for the life of the handle, whichever kernel instantiation runs
-        s->compact = (feature_set(*p) == FT_V2ON && p->max_steps < 65536 && !getenv("HLYNR_NO_COMPACT")) ? 1 : 0;
-        init_kernel<float><<<grid_for(s->n_pad, blk), blk>>>(s->pf, s->n_pad, (float)p->peak_mult, s->compact != 0);
+        s->compact = 0;
+        if (p->max_steps < 65536 && !getenv("HLYNR_NO_COMPACT")) s->compact = feature_set(*p) == FT_V2ON ? 1 : (feature_set(*p) == FT_V2ON_DR ? 2 : 0);
+        init_kernel<float><<<grid_for(s->n_pad, blk), blk>>>(s->pf, s->n_pad, (float)p->peak_mult, s->compact);
     } else {
         carve<double>(s->pd, (char*)s->state_mem, s->n_pad, gl, ol, p->volley_size);
-        init_kernel<double><<<grid_for(s->n_pad, blk), blk>>>(s->pd, s->n_pad, (float)p->peak_mult, false);
+        init_kernel<double><<<grid_for(s->n_pad, blk), blk>>>(s->pd, s->n_pad, (float)p->peak_mult, 0);
     }
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { int r = fail("hlynr_create: init kernel failed: %s", cudaGetErrorString(e)); hlynr_destroy(s); return r; }

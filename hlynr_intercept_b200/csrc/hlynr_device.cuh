@@ -364,13 +364,21 @@ HD double bits_word(int, double) { return 0.0; }
 // other specialised instantiations carry no trace of it
 template <typename R, int F = FT_GENERIC> HD bool compact_layout(const KernelArgs<R>& A) {
     if constexpr (!std::is_same<R, float>::value || F == FT_V2OFF || F == FT_V2ON_DR) return false;
-    else return A.compact != 0;
+    else return A.compact == 1;
+}
+// Second compact layout (KernelArgs::compact == 2; fp32 build, cfg3's feature set FT_V2ON_DR, max_steps < 65536): with domain
+// randomization T0 and the base Cd are real state, but the f3 plane holds ONE float (the transonic drag peak).  steps and the worsening
+// counter share a word of i0, the peak takes the freed one, and the f3 plane is never touched: 11 planes instead of 12.
+//   i0 = { steps | worsen << 16, bits(peak), flags, episode }
+template <typename R, int F = FT_GENERIC> HD bool dr_compact_layout(const KernelArgs<R>& A) {
+    if constexpr (!std::is_same<R, float>::value || F == FT_V2OFF || F == FT_V2ON) return false;
+    else return A.compact == 2;
 }
 
 template <typename R, int F = FT_GENERIC> HD void load_env(const KernelArgs<R>& A, int64_t i, Env<R>& e) {
     typedef Feat<F> FT;
     const StatePlanes<R>& s = A.st;
-    const bool compact = compact_layout<R, F>(A);
+    const bool compact = compact_layout<R, F>(A), drc = dr_compact_layout<R, F>(A);
     Vec4<R> v;
     float4 f;
     // Issue order = order of first use.  The planes that carry the counters go first: steps / episode key every Philox draw of the
@@ -390,7 +398,7 @@ template <typename R, int F = FT_GENERIC> HD void load_env(const KernelArgs<R>& 
     v = s.r[5][i]; e.kvx = v.x; e.kvy = v.y; e.kvz = v.z; e.ep_ret = v.w;
     f = s.f[0][i]; e.qw = f.x; e.qx = f.y; e.qy = f.z; e.qz = f.w;
     f = s.f[2][i]; e.Ppv = f.x; e.Pvp = f.y; e.Pvv = f.z; e.Ppp = f.w;
-    if (FT::dr(A.P)) { f = s.f[3][i]; e.peak = f.x; } else e.peak = 0.f;
+    if (FT::dr(A.P) && !drc) { f = s.f[3][i]; e.peak = f.x; } else e.peak = 0.f;
     if (compact) {
         const int sw = word_bits(e.T0), ef = word_bits(e.base_cd);
         e.T0 = R(288.15); e.base_cd = 0.3f;
@@ -398,6 +406,8 @@ template <typename R, int F = FT_GENERIC> HD void load_env(const KernelArgs<R>& 
         e.episode = (ef << 7) >> 7;
         const int p = (int)((unsigned)ef >> 25);
         e.flags = (p & 7) | (((p >> 3) & 0xf) << 8);
+    } else if (drc) {
+        e.steps = q.x & 0xffff; e.worsen = (int)((unsigned)q.x >> 16); e.peak = __int_as_float(q.y); e.flags = q.z; e.episode = q.w;
     } else {
         e.steps = q.x; e.worsen = q.y; e.flags = q.z; e.episode = q.w;
     }
@@ -405,7 +415,7 @@ template <typename R, int F = FT_GENERIC> HD void load_env(const KernelArgs<R>& 
 template <typename R, int F = FT_GENERIC> HD void store_env(const KernelArgs<R>& A, int64_t i, const Env<R>& e) {
     typedef Feat<F> FT;
     const StatePlanes<R>& s = A.st;
-    const bool compact = compact_layout<R, F>(A);
+    const bool compact = compact_layout<R, F>(A), drc = dr_compact_layout<R, F>(A);
     R r6w = e.T0;
     float f1w = e.base_cd;
     if (compact) {
@@ -422,8 +432,9 @@ template <typename R, int F = FT_GENERIC> HD void store_env(const KernelArgs<R>&
     s.f[0][i] = make_float4(e.qw, e.qx, e.qy, e.qz);
     s.f[1][i] = make_float4(e.wx, e.wy, e.wz, f1w);
     s.f[2][i] = make_float4(e.Ppv, e.Pvp, e.Pvv, e.Ppp);
-    if (FT::dr(A.P)) s.f[3][i] = make_float4(e.peak, 0.f, 0.f, 0.f);
-    if (!compact) s.i0[i] = make_int4(e.steps, e.worsen, e.flags, e.episode);
+    if (FT::dr(A.P) && !drc) s.f[3][i] = make_float4(e.peak, 0.f, 0.f, 0.f);
+    if (drc) s.i0[i] = make_int4((e.steps & 0xffff) | (e.worsen << 16), __float_as_int(e.peak), e.flags, e.episode);
+    else if (!compact) s.i0[i] = make_int4(e.steps, e.worsen, e.flags, e.episode);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1766,7 +1777,7 @@ template <typename R, int F> HD void prefetch_next_wave(const KernelArgs<R>& A, 
     if (FT::thrust_dyn(A.P) || FT::dr(A.P)) prefetch_l2(s.r[6] + j);
 #pragma unroll
     for (int k = 0; k < 3; ++k) prefetch_l2(s.f[k] + j);
-    if (FT::dr(A.P)) prefetch_l2(s.f[3] + j);
+    if (FT::dr(A.P) && !dr_compact_layout<R, F>(A)) prefetch_l2(s.f[3] + j);
     if (!compact_layout<R, F>(A)) prefetch_l2(s.i0 + j);
     if (A.io.actions) prefetch_l2(A.io.actions + j * HLYNR_ACT_DIM);
 }

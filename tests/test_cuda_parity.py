@@ -357,7 +357,8 @@ def test_manual_reset_flow_without_auto_reset(f64):
         np.testing.assert_allclose(sc[k], so[k], rtol=tol["rtol_state"], atol=tol["rtol_state"] * 10)
 
 
-def test_compact_layout_is_bit_identical(monkeypatch):
+@pytest.mark.parametrize("base", ["cfg4", "cfg3"])
+def test_compact_layout_is_bit_identical(monkeypatch, base):
     """The compact 10-plane layout of the cfg4 feature set (fp32 build: the counters ride in the constant words r6.w / f1.w and
     the i0 plane is never touched, hlynr_device.cuh load_env) against the 11-plane layout (HLYNR_NO_COMPACT=1 at create time) on
     the same seed and actions: every output of every tick, the info arrays, the terminal observations and the exported env
@@ -365,7 +366,8 @@ def test_compact_layout_is_bit_identical(monkeypatch):
     plus an export -> import round trip into a fresh compact handle."""
     import torch
 
-    P, cur = config.resolve_config(config.baseline_config("cfg4"), warn_dead=False)
+    # cfg3: the second compact layout (domain randomization: the drag peak rides in i0.y and the f3 plane is never touched)
+    P, cur = config.resolve_config(config.baseline_config(base), warn_dead=False)
     n = 30000 + 13
     a = CudaBatch(P, cur, n, seed=777).sim
     monkeypatch.setenv("HLYNR_NO_COMPACT", "1")
