@@ -1756,7 +1756,7 @@ template <typename R> HD RngKey make_key(const KernelArgs<R>& A, int64_t global_
 // CTA size of the direct step kernel (a multiple of 32 that divides HLYNR_BLOCK).  Nothing in that kernel is CTA-wide (warp-private
 // observation tiles, no barrier), so the CTA is only the unit in which SM slots are handed back.
 #ifndef HLYNR_STEP_BLOCK
-#define HLYNR_STEP_BLOCK 128
+#define HLYNR_STEP_BLOCK 64   /* 128 / 64 / 32 threads with the final kernel of round 2: cfg4 99.0 / 98.0 / 98.0 us at 2^20 envs, cfg3 at 262144 envs 35.0 / 34.6 / 34.4 us, cfg2 at 4096 envs 8.16 / 8.01 / 8.01 us per tick in a graph (profiles/r02_o_cta_size_ab.log): SM slots are handed back at a finer grain */
 #endif
 
 // The delay-ring samples a tick reads (one onboard slot, two ground planes) are needed only deep inside observe(),
